@@ -1,0 +1,258 @@
+/* TEST INFRASTRUCTURE (oracle) -- plain-C CPU restatement of one day of DySTUrbD's epidemic step.
+ *
+ * NOT the product.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product path (dysturbd_b200/) never does and has no CPU fallback.
+ *
+ * What it restates: /root/reference/contagious3.py:176-366 (the per-day `while` body), phase by phase, on a
+ * structure-of-arrays state instead of the reference's agents[N,29] float64 matrix, and with the dense
+ * U x I pair matrices of :230-248 replaced by a walk over the non-zeros of interaction_prob (a pair with
+ * interaction_prob == 0 has P == 0 and `0 > u` is never true, so the sparse walk is exact).
+ * Parity status: PINNED against the literal reference loop run under identical injected draws
+ * (oracle/literal.py -> tests/golden/ fixtures, tests/test_oracle_vs_literal.py).  The reference itself
+ * ships no tests or golden vectors.
+ *
+ * Status codes are the reference's float codes times two (1,2,3,3.5,4,5,6,7 -> 2,4,6,7,8,10,12,14).
+ * Build:  gcc -O2 -fopenmp -shared -fPIC -ffp-contract=off oracle/dys_oracle.c -o oracle/libdys_oracle.so
+ *         (-ffp-contract=off: the probability chain must be four separately rounded IEEE multiplies.)
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ST_S 2
+#define ST_I 4
+#define ST_QH 6
+#define ST_QI 7
+#define ST_D 8
+#define ST_H 10
+#define ST_R 12
+#define ST_X 14
+
+/* ---- Philox4x32-10 (Salmon et al., SC'11; Random123 constants), see oracle/philox_np.py ---- */
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+
+double orc_keyed_uniform(uint64_t seed, uint32_t day, uint32_t stream, uint32_t a, uint32_t b)
+{
+    uint32_t ctr[4] = {a, b, day, stream}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+    philox4x32_10(ctr, key, o);
+    uint64_t w = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+    return (double)(w >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* ---- the day ---- */
+typedef struct {
+    int64_t N, H, B, S;
+    int32_t V;
+    int32_t recover, hospital_recover, diagnosis, quarantine; /* parameters.py:42-46 */
+    int32_t adm_min_day, adm_max_day, death_min_adm_day;       /* contagious3.py:205 (4, 14), :219 (3) */
+    double norm_factor;                                        /* parameters.py:41 */
+    double compliance;                                         /* extension; 1.0 == reference */
+    double pdf[64];                                            /* contagious_risk_day.pdf(0..63), parameters.py:44 */
+    uint64_t seed;
+    /* state (mutated) */
+    uint8_t* status;
+    int32_t *t_inf, *t_q, *t_adm, *src;
+    /* static per-agent */
+    const int32_t *hh, *home, *sa;
+    const double *risk, *p_adm, *p_death;
+    const int32_t* routine;          /* [N*V] building index or -1 */
+    /* interaction_prob CSR */
+    const int64_t* rowptr;
+    const int32_t* col;
+    const double* val;
+    /* buildings */
+    const uint8_t* open;             /* [B] */
+    /* household-isin quirk of contagious3.py:267 */
+    const uint8_t* hh_always;        /* [H] or NULL */
+    const int64_t* trig_ptr;         /* [N+1] or NULL */
+    const int32_t* trig_hh;
+    /* injected draws (NULL -> keyed Philox) */
+    const double *u_adm, *u_death, *u_pair;   /* [N], [N], [N*N] */
+    /* outputs */
+    int64_t* stats;                  /* [64]: counters 0..31, global days-since-infection histogram 32..52 */
+    int32_t* sa_hist;                /* [S*21] or NULL */
+    int32_t* bld_infected;           /* [B] or NULL */
+    int32_t *ev_agent, *ev_src;      /* [N] or NULL: today's infections in ascending agent order */
+    double* pair_prob;               /* [N*N] or NULL: P written for every evaluated (u,i) pair (tests) */
+} orc_ctx;
+
+enum { O_ACTIVE, O_DAILY_INF, O_RECOVERED, O_QUARANTINED, O_DAILY_QUAR, O_HOSP, O_DAILY_HOSP, O_DEAD, O_DAILY_DEATHS,
+       O_EVER_INFECTED, O_NEW_DIAG, O_N_EVENTS, O_SUS0, O_INF0, O_EDGES_SCANNED, O_CANDIDATES, O_EXPOSED, O_HITS };
+
+static int eff_list(const orc_ctx* c, int64_t a, uint8_t st0, int32_t* out)
+{
+    /* contagious3.py:181-189: closed buildings removed; isolated agents keep slot 0; admitted/dead keep nothing */
+    int n = 0;
+    if (st0 == ST_H || st0 == ST_X) return 0;
+    int iso = (st0 == ST_QH || st0 == ST_QI || st0 == ST_D);
+    for (int s = 0; s < c->V; ++s) {
+        int32_t b = c->routine[a * c->V + s];
+        if (b < 0) continue;
+        if (!c->open[b]) continue;
+        if (s > 0 && iso) continue;
+        out[n++] = b;
+    }
+    return n;
+}
+
+int orc_day(orc_ctx* c, int32_t day)
+{
+    const int64_t N = c->N;
+    uint8_t* st0 = (uint8_t*)malloc(N);
+    if (!st0) return -1;
+    memcpy(st0, c->status, N);
+    memset(c->stats, 0, 64 * sizeof(int64_t));
+    int64_t n_adm = 0, n_death = 0, n_sus0 = 0, n_inf0 = 0;
+
+    /* phases B and C (contagious3.py:205-227), both on the day-start snapshot */
+    for (int64_t a = 0; a < N; ++a) {
+        uint8_t s = st0[a];
+        int inf0 = (s == ST_I || s == ST_QI || s == ST_D);
+        n_inf0 += inf0;
+        n_sus0 += (s == ST_S || s == ST_QH);
+        if (inf0 && c->t_inf[a] >= c->adm_min_day && c->t_inf[a] <= c->adm_max_day) {
+            double u = c->u_adm ? c->u_adm[a] : orc_keyed_uniform(c->seed, day, 0, (uint32_t)a, 0);
+            if (c->p_adm[a] > u) { c->status[a] = ST_H; c->t_adm[a] = day; ++n_adm; }
+        }
+        if (s == ST_H && c->t_adm[a] >= c->death_min_adm_day) {
+            double u = c->u_death ? c->u_death[a] : orc_keyed_uniform(c->seed, day, 1, (uint32_t)a, 0);
+            if (c->p_death[a] > u) { c->status[a] = ST_X; ++n_death; }
+        }
+    }
+
+    /* phase D (contagious3.py:230-248) */
+    int64_t scanned = 0, cand = 0, expo = 0, hits = 0;
+#pragma omp parallel for schedule(dynamic, 512) reduction(+ : scanned, cand, expo, hits)
+    for (int64_t u = 0; u < N; ++u) {
+        uint8_t su = st0[u];
+        if (!(su == ST_S || su == ST_QH)) continue;
+        int32_t eu[16], ei[16];
+        int nu = eff_list(c, u, su, eu);
+        int32_t best = -1;
+        for (int64_t e = c->rowptr[u]; e < c->rowptr[u + 1]; ++e) {
+            int32_t i = c->col[e];
+            ++scanned;
+            uint8_t si = st0[i];
+            if (!(si == ST_I || si == ST_QI || si == ST_D)) continue;
+            ++cand;
+            int ni = eff_list(c, i, si, ei), share = 0;
+            for (int x = 0; x < nu && !share; ++x)
+                for (int y = 0; y < ni; ++y)
+                    if (eu[x] == ei[y]) { share = 1; break; }
+            int n_inf = day - c->t_inf[i];
+            if (n_inf > 63) n_inf = 63;
+            double p = c->val[e] * c->risk[u];          /* :232-233 */
+            p = p * c->pdf[n_inf];                      /* :234 */
+            p = p * (share ? 1.0 : 0.0);                /* :237 */
+            p = p * c->norm_factor;                     /* :238 */
+            if (c->pair_prob) c->pair_prob[u * N + i] = p;
+            if (!share) continue;
+            ++expo;
+            double r = c->u_pair ? c->u_pair[u * N + i] : orc_keyed_uniform(c->seed, day, 2, (uint32_t)u, (uint32_t)i);
+            if (p > r) { ++hits; if (i > best) best = i; }   /* :240, :248 last writer = largest index */
+        }
+        if (best >= 0) {
+            c->status[u] = (su == ST_S) ? ST_I : ST_QI;  /* :243, :245 */
+            c->t_inf[u] = day;
+            c->src[u] = best;
+        }
+    }
+
+    /* phase E (contagious3.py:250-259), rule by rule; day counters derived as day - start */
+    for (int64_t a = 0; a < N; ++a) {
+        uint8_t s = c->status[a];
+        int n_inf = day - c->t_inf[a], n_q = day - c->t_q[a];
+        if (s == ST_QH && n_q == c->quarantine) s = ST_S;
+        if (s == ST_QI && n_q == c->quarantine) s = ST_I;
+        if (s == ST_I && n_inf == c->diagnosis) c->t_q[a] = day;
+        if ((s == ST_I || s == ST_QI) && n_inf == c->diagnosis) s = ST_D;
+        if (s == ST_D && n_inf == c->recover) s = ST_R;
+        if (s == ST_H && n_inf == c->hospital_recover) s = ST_R;
+        if (s == ST_S || s == ST_I || s == ST_R || s == ST_X) c->t_adm[a] = 0;
+        c->status[a] = s;
+    }
+
+    /* phase F (contagious3.py:261-270) */
+    int64_t n_diag = 0;
+    uint8_t* hh_hit = (uint8_t*)calloc(c->H > 0 ? c->H : 1, 1);
+    uint8_t* hh_quirk = (uint8_t*)calloc(c->H > 0 ? c->H : 1, 1);
+    for (int64_t a = 0; a < N; ++a) {
+        if (c->status[a] == ST_D && day - c->t_inf[a] == c->diagnosis) {
+            ++n_diag;
+            hh_hit[c->hh[a]] = 1;
+            if (c->trig_ptr)
+                for (int64_t t = c->trig_ptr[a]; t < c->trig_ptr[a + 1]; ++t) hh_quirk[c->trig_hh[t]] = 1;
+        }
+    }
+    if (n_diag > 0) {
+        for (int64_t a = 0; a < N; ++a) {
+            int32_t h = c->hh[a];
+            uint8_t s = c->status[a];
+            int obey = 1;
+            if (c->compliance < 1.0) obey = orc_keyed_uniform(c->seed, day, 3, (uint32_t)a, 0) < c->compliance;
+            if (s == ST_S && hh_hit[h] && obey) { c->status[a] = ST_QH; c->t_q[a] = day; }
+            else if (s == ST_I && (hh_hit[h] || hh_quirk[h] || (c->hh_always && c->hh_always[h])) && obey) {
+                c->status[a] = ST_QI; c->t_q[a] = day;
+            }
+        }
+    }
+    free(hh_hit); free(hh_quirk);
+
+    /* phase G: integer statistics (contagious3.py:273-366); floats (R) are formed on the host */
+    int64_t* S = c->stats;
+    if (c->sa_hist) memset(c->sa_hist, 0, sizeof(int32_t) * 21 * c->S);
+    if (c->bld_infected) memset(c->bld_infected, 0, sizeof(int32_t) * c->B);
+    int64_t nev = 0;
+    for (int64_t a = 0; a < N; ++a) {
+        uint8_t s = c->status[a];
+        int ever = !(s == ST_S || s == ST_QH);
+        S[O_ACTIVE] += (s == ST_I || s == ST_QI || s == ST_D || s == ST_H);
+        S[O_DAILY_INF] += (ever && c->t_inf[a] == day);
+        S[O_RECOVERED] += (s == ST_R);
+        S[O_QUARANTINED] += (s == ST_QH || s == ST_QI || s == ST_D);
+        S[O_DAILY_QUAR] += ((s == ST_QH || s == ST_QI || s == ST_D) && c->t_q[a] == day);
+        S[O_HOSP] += (s == ST_H);
+        S[O_DEAD] += (s == ST_X);
+        S[O_EVER_INFECTED] += ever;
+        if (ever) {
+            int k = day - c->t_inf[a];
+            if (k >= 0 && k <= 20) {
+                S[32 + k] += 1;
+                if (c->sa_hist) c->sa_hist[c->sa[a] * 21 + k] += 1;
+            }
+        }
+        if (c->bld_infected && (s == ST_I || s == ST_QI || s == ST_D)) c->bld_infected[c->home[a]] += 1;
+        if (ever && c->t_inf[a] == day && st0[a] != s && (st0[a] == ST_S || st0[a] == ST_QH)) {
+            if (c->ev_agent) { c->ev_agent[nev] = (int32_t)a; c->ev_src[nev] = c->src[a]; }
+            ++nev;
+        }
+    }
+    S[O_DAILY_HOSP] = n_adm;
+    S[O_DAILY_DEATHS] = n_death;
+    S[O_NEW_DIAG] = n_diag;
+    S[O_N_EVENTS] = nev;
+    S[O_SUS0] = n_sus0;
+    S[O_INF0] = n_inf0;
+    S[O_EDGES_SCANNED] = scanned;
+    S[O_CANDIDATES] = cand;
+    S[O_EXPOSED] = expo;
+    S[O_HITS] = hits;
+    free(st0);
+    return 0;
+}

@@ -1,0 +1,145 @@
+"""TEST INFRASTRUCTURE (oracle) -- ctypes wrapper of oracle/dys_oracle.c (the CPU restatement).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libdys_oracle.so")
+
+N_STATS = 64
+HIST0 = 32
+STAT_NAMES = ["active", "daily_inf", "recovered", "quarantined", "daily_quar", "hosp", "daily_hosp", "dead",
+              "daily_deaths", "ever_infected", "new_diag", "n_events", "sus0", "inf0", "edges_scanned",
+              "candidates", "exposed", "hits"]
+
+
+def build(force=False):
+    src = os.path.join(HERE, "dys_oracle.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off", "-shared", src, "-o", LIB])
+    return LIB
+
+
+class _Ctx(C.Structure):
+    _fields_ = [
+        ("N", C.c_int64), ("H", C.c_int64), ("B", C.c_int64), ("S", C.c_int64),
+        ("V", C.c_int32),
+        ("recover", C.c_int32), ("hospital_recover", C.c_int32), ("diagnosis", C.c_int32), ("quarantine", C.c_int32),
+        ("adm_min_day", C.c_int32), ("adm_max_day", C.c_int32), ("death_min_adm_day", C.c_int32),
+        ("norm_factor", C.c_double), ("compliance", C.c_double), ("pdf", C.c_double * 64),
+        ("seed", C.c_uint64),
+        ("status", C.c_void_p), ("t_inf", C.c_void_p), ("t_q", C.c_void_p), ("t_adm", C.c_void_p), ("src", C.c_void_p),
+        ("hh", C.c_void_p), ("home", C.c_void_p), ("sa", C.c_void_p),
+        ("risk", C.c_void_p), ("p_adm", C.c_void_p), ("p_death", C.c_void_p),
+        ("routine", C.c_void_p),
+        ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
+        ("open", C.c_void_p),
+        ("hh_always", C.c_void_p), ("trig_ptr", C.c_void_p), ("trig_hh", C.c_void_p),
+        ("u_adm", C.c_void_p), ("u_death", C.c_void_p), ("u_pair", C.c_void_p),
+        ("stats", C.c_void_p), ("sa_hist", C.c_void_p), ("bld_infected", C.c_void_p),
+        ("ev_agent", C.c_void_p), ("ev_src", C.c_void_p), ("pair_prob", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_day.argtypes = [C.POINTER(_Ctx), C.c_int32]
+        _lib.orc_day.restype = C.c_int
+        _lib.orc_keyed_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        _lib.orc_keyed_uniform.restype = C.c_double
+        _lib.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def keyed_uniform(seed, day, stream, a, b=0):
+    return lib().orc_keyed_uniform(seed, day, stream, a, b)
+
+
+def philox4x32_10(ctr, key):
+    ctr = np.ascontiguousarray(ctr, dtype=np.uint32)
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(ctr.ctypes.data, key.ctypes.data, out.ctypes.data)
+    return out
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class OracleSim:
+    """One population, stepped day by day on the CPU.  `pop` is a dysturbd_b200.population.Population (its
+    state arrays are COPIED); `params` a dysturbd_b200.population.EpiParams."""
+
+    def __init__(self, pop, params, capture_prob=False, threads=None):
+        self.pop, self.params = pop, params
+        self.threads = threads
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        self.status = c(pop.status, np.uint8).copy()
+        self.t_inf = c(pop.t_inf, np.int32).copy()
+        self.t_q = c(pop.t_q, np.int32).copy()
+        self.t_adm = c(pop.t_adm, np.int32).copy()
+        self.src = c(pop.src, np.int32).copy()
+        self.open = c(pop.open, np.uint8).copy()
+        self._keep = dict(
+            hh=c(pop.hh, np.int32), home=c(pop.home, np.int32), sa=c(pop.sa, np.int32),
+            risk=c(pop.risk, np.float64), p_adm=c(pop.p_adm, np.float64), p_death=c(pop.p_death, np.float64),
+            routine=c(pop.routine, np.int32), rowptr=c(pop.ip_rowptr, np.int64), col=c(pop.ip_col, np.int32),
+            val=c(pop.ip_val, np.float64), hh_always=c(pop.hh_always, np.uint8),
+            trig_ptr=c(pop.trig_ptr, np.int64), trig_hh=c(pop.trig_hh, np.int32))
+        self.stats = np.zeros(N_STATS, dtype=np.int64)
+        self.sa_hist = np.zeros((max(pop.S, 1), 21), dtype=np.int32)
+        self.bld_infected = np.zeros(pop.B, dtype=np.int32)
+        self.ev_agent = np.zeros(pop.N, dtype=np.int32)
+        self.ev_src = np.zeros(pop.N, dtype=np.int32)
+        self.pair_prob = np.zeros((pop.N, pop.N)) if capture_prob else None
+        k = self._keep
+        ctx = _Ctx()
+        ctx.N, ctx.H, ctx.B, ctx.S, ctx.V = pop.N, pop.H, pop.B, pop.S, pop.V
+        p = params
+        ctx.recover, ctx.hospital_recover, ctx.diagnosis, ctx.quarantine = p.recover, p.hospital_recover, p.diagnosis, p.quarantine
+        ctx.adm_min_day, ctx.adm_max_day, ctx.death_min_adm_day = p.adm_min_day, p.adm_max_day, p.death_min_adm_day
+        ctx.norm_factor, ctx.compliance, ctx.seed = p.norm_factor, p.compliance, p.seed
+        for i in range(64):
+            ctx.pdf[i] = float(p.pdf[i])
+        ctx.status, ctx.t_inf, ctx.t_q, ctx.t_adm, ctx.src = map(_p, (self.status, self.t_inf, self.t_q, self.t_adm, self.src))
+        for name in ("hh", "home", "sa", "risk", "p_adm", "p_death", "routine", "rowptr", "col", "val",
+                     "hh_always", "trig_ptr", "trig_hh"):
+            setattr(ctx, name, _p(k[name]))
+        ctx.open = _p(self.open)
+        ctx.stats, ctx.sa_hist, ctx.bld_infected = _p(self.stats), _p(self.sa_hist), _p(self.bld_infected)
+        ctx.ev_agent, ctx.ev_src, ctx.pair_prob = _p(self.ev_agent), _p(self.ev_src), _p(self.pair_prob)
+        self.ctx = ctx
+
+    def set_open(self, open_flags):
+        self.open[:] = np.asarray(open_flags, dtype=np.uint8)
+
+    def step(self, day, u_adm=None, u_death=None, u_pair=None):
+        keep = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None for x in (u_adm, u_death, u_pair)]
+        self.ctx.u_adm, self.ctx.u_death, self.ctx.u_pair = map(_p, keep)
+        if self.pair_prob is not None:
+            self.pair_prob[:] = 0.0
+        if self.threads is not None:
+            os.environ["OMP_NUM_THREADS"] = str(self.threads)
+        rc = lib().orc_day(C.byref(self.ctx), int(day))
+        if rc != 0:
+            raise RuntimeError("orc_day failed")
+        return self.stats.copy()
+
+    def state(self):
+        return dict(status=self.status.copy(), t_inf=self.t_inf.copy(), t_q=self.t_q.copy(),
+                    t_adm=self.t_adm.copy(), src=self.src.copy())
+
+    def events(self):
+        n = int(self.stats[STAT_NAMES.index("n_events")])
+        return self.ev_agent[:n].copy(), self.ev_src[:n].copy()
