@@ -1,0 +1,637 @@
+// C ABI of the B200-native epidemic step (include/dysturbd.h).  Host-side bookkeeping only: owns the device
+// structure-of-arrays, launches the kernels of dys_kernels.cuh on one stream, and moves the small per-day
+// integer outputs to pinned host memory.  No CPU implementation of any phase lives here.
+#include "../../include/dysturbd.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dys_kernels.cuh"
+
+using namespace dys;
+
+static_assert(DYS_N_STATS == N_STATS && DYS_ST_HIST0 == HIST0 && DYS_HIST_LEN == HIST_LEN, "header/kernel mismatch");
+static_assert(DYS_ST_CHANGED == ST_CHANGED && DYS_ST_N_EVENTS == ST_N_EVENTS, "header/kernel mismatch");
+
+static thread_local std::string g_create_error;
+
+struct dys_handle {
+    dys_params p{};
+    DevCtx c{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    int64_t dev_bytes = 0;
+    std::string err;
+    bool have_pop = false, have_graph = false, begun = false;
+    int lpr = 4;
+    int64_t nnz = 0;
+    int32_t last_day = -1;
+    int64_t steps = 0;
+    // pinned ring of per-day stats + completion events
+    int64_t* h_stats = nullptr;
+    int32_t ring_day[DYS_STATS_RING];
+    cudaEvent_t ring_ev[DYS_STATS_RING];
+    int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags, [1] event count
+    int32_t* d_bad = nullptr;
+    double* d_pair_prob = nullptr;
+    double *d_u_adm = nullptr, *d_u_death = nullptr, *d_u_pair = nullptr;   // staged injected draws
+    // kernel timing
+    std::vector<cudaEvent_t> tev;    // per step: 4 events (before K1, after K1 / before K2, after K2, after K3)
+    int64_t t_begin = 0, t_end = 0;  // steps [t_begin, t_end) hold unread timings
+    static constexpr int64_t T_RING = 4096;
+};
+
+static int fail(dys_handle* h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) return fail(h, DYS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(dys_handle* h, T** out, int64_t count, bool zero = true)
+{
+    void* p = nullptr;
+    const size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+    CK(h, cudaMalloc(&p, bytes));
+    if (zero) CK(h, cudaMemsetAsync(p, 0, bytes, h->stream));
+    h->allocs.push_back(p);
+    h->dev_bytes += (int64_t)bytes;
+    *out = (T*)p;
+    return DYS_OK;
+}
+
+static int copy_in(dys_handle* h, void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0) return DYS_OK;
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));
+    return DYS_OK;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+extern "C" const char* dys_version(void) { return "dysturbd-b200 0.1 (sm_100a)"; }
+
+extern "C" const char* dys_last_error(const dys_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int dys_create(const dys_params* params, int device, dys_handle** out)
+{
+    if (!params || !out) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_create: null argument");
+    const dys_params& p = *params;
+    if (p.n_agents <= 0 || p.n_agents > (int64_t)COL_MASK + 1) return fail(nullptr, DYS_ERR_INVALID_ARG, "n_agents must be in [1, 2^27]");
+    if (p.n_households <= 0 || p.n_buildings <= 0 || p.n_areas < 0) return fail(nullptr, DYS_ERR_INVALID_ARG, "bad H/B/S");
+    if (p.n_slots < 1 || p.n_slots > 16) return fail(nullptr, DYS_ERR_INVALID_ARG, "n_slots must be in [1,16]");
+    const int world = p.world > 1 ? p.world : 1;
+    int64_t lo = 0, hi = p.n_agents;
+    if (world > 1) {
+        lo = p.shard_lo; hi = p.shard_hi;
+        if (lo < 0 || hi > p.n_agents || lo >= hi || (lo % 1024) != 0) return fail(nullptr, DYS_ERR_INVALID_ARG, "bad shard range (lo must be a multiple of 1024)");
+        if (p.flags & DYS_WANT_IO_MAT) return fail(nullptr, DYS_ERR_INVALID_ARG, "DYS_WANT_IO_MAT is not available in sharded mode");
+    }
+    if ((p.flags & DYS_WANT_IO_MAT) && p.n_areas * p.n_areas > (int64_t)1 << 26)
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "DYS_WANT_IO_MAT needs S*S <= 2^26; use dys_get_events");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, DYS_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, DYS_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+    dys_handle* h = new dys_handle();
+    h->p = p;
+    h->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { fail(nullptr, DYS_ERR_CUDA, "cuda init: %s", cudaGetErrorString(e)); delete h; return DYS_ERR_CUDA; }
+    DevCtx& c = h->c;
+    c.n_loc = hi - lo; c.n_pad = round_up(c.n_loc, 1024); c.n_glob = p.n_agents; c.lo = lo;
+    c.rt_lo = 0; c.rt_n = p.n_agents;
+    if (p.halo_hi > p.halo_lo) {
+        if (p.halo_lo < 0 || p.halo_hi > p.n_agents || p.halo_lo > lo || p.halo_hi < hi) { delete h; return fail(nullptr, DYS_ERR_INVALID_ARG, "halo must contain the owned range"); }
+        c.rt_lo = p.halo_lo; c.rt_n = p.halo_hi - p.halo_lo;
+    }
+    c.H = p.n_households; c.B = p.n_buildings; c.S = p.n_areas; c.V = p.n_slots;
+    c.recover = p.recover; c.hospital_recover = p.hospital_recover; c.diagnosis = p.diagnosis; c.quarantine = p.quarantine;
+    c.adm_min = p.adm_min_day; c.adm_max = p.adm_max_day; c.death_min = p.death_min_adm_day;
+    c.norm_factor = p.norm_factor; c.compliance = p.compliance; c.seed = p.seed;
+    int rc = DYS_OK;
+    auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
+    double* d_pdf = nullptr;
+    A(dev_alloc(h, &c.status, c.n_pad)); A(dev_alloc(h, &c.t_inf, c.n_pad)); A(dev_alloc(h, &c.t_q, c.n_pad));
+    A(dev_alloc(h, &c.t_adm, c.n_pad)); A(dev_alloc(h, &c.src, c.n_pad));
+    A(dev_alloc(h, (int32_t**)&c.hh, c.n_pad)); A(dev_alloc(h, (int32_t**)&c.home, c.n_pad)); A(dev_alloc(h, (int32_t**)&c.sa, c.n_pad));
+    A(dev_alloc(h, (double**)&c.risk, c.n_pad)); A(dev_alloc(h, (double**)&c.p_adm, c.n_pad)); A(dev_alloc(h, (double**)&c.p_death, c.n_pad));
+    A(dev_alloc(h, (int32_t**)&c.routine, c.rt_n * c.V));
+    A(dev_alloc(h, &c.ib, round_up(c.n_glob, 1024) + 1024));
+    A(dev_alloc(h, (uint8_t**)&c.open, c.B));
+    A(dev_alloc(h, &c.hh_flag, c.H)); A(dev_alloc(h, &c.hh_qflag, c.H));
+    A(dev_alloc(h, &c.day_flags, 8));
+    A(dev_alloc(h, &c.part, (int64_t)N_SLOTS * N_STATS)); A(dev_alloc(h, &c.stats, N_STATS)); A(dev_alloc(h, &c.ticket, 1));
+    A(dev_alloc(h, &d_pdf, DYS_PDF_LEN));
+    A(dev_alloc(h, &h->d_bad, 1));
+    if (p.flags & DYS_WANT_SA_HIST) A(dev_alloc(h, &c.sa_hist, c.S * HIST_LEN));
+    if (p.flags & DYS_WANT_BUILDING_COUNTS) A(dev_alloc(h, &c.bcount, c.B));
+    if (p.flags & DYS_WANT_EVENTS) { A(dev_alloc(h, &c.ev_agent, c.n_pad)); A(dev_alloc(h, &c.ev_src, c.n_pad)); }
+    if (p.flags & DYS_WANT_IO_MAT) A(dev_alloc(h, &c.io_mat, c.S * c.S));
+    c.pdf = d_pdf;
+    if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_stats, sizeof(int64_t) * N_STATS * DYS_STATS_RING) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_small, sizeof(int32_t) * 16) != cudaSuccess) rc = DYS_ERR_CUDA;
+    for (int i = 0; i < DYS_STATS_RING; ++i) {
+        h->ring_day[i] = -1;
+        h->ring_ev[i] = nullptr;
+        if (rc == DYS_OK && cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = DYS_ERR_CUDA;
+    }
+    if (rc == DYS_OK && (p.flags & DYS_TIME_KERNELS)) {
+        h->tev.resize(dys_handle::T_RING * 4);
+        for (auto& ev : h->tev) if (cudaEventCreate(&ev) != cudaSuccess) { rc = DYS_ERR_CUDA; break; }
+    }
+    if (rc == DYS_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc != DYS_OK) {
+        fail(nullptr, rc, "dys_create: allocation failed: %s", h->err.empty() ? cudaGetErrorString(cudaGetLastError()) : h->err.c_str());
+        dys_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return DYS_OK;
+}
+
+extern "C" int dys_destroy(dys_handle* h)
+{
+    if (!h) return DYS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    for (int i = 0; i < DYS_STATS_RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    for (auto ev : h->tev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return DYS_OK;
+}
+
+static int check_bad(dys_handle* h, const char* what)
+{
+    CK(h, cudaMemcpyAsync(h->h_small, h->d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const int bad = h->h_small[0];
+    if (bad) {
+        CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int32_t), h->stream));
+        return fail(h, DYS_ERR_RANGE, "%s: invalid input (flags 0x%x: 1 status code, 2 hh/home/sa index, 4 t_adm != 0 for a "
+                    "never-admitted status, 8 src index, 16 routine building index, 32 rowptr not monotone, 64 column index, "
+                    "128 columns not strictly ascending, 256 day out of int16 range)", what, bad);
+    }
+    return DYS_OK;
+}
+
+static int load_days(dys_handle* h, int16_t* dst, const int32_t* src, int32_t* tmp, int64_t n)
+{
+    int rc = copy_in(h, tmp, src, sizeof(int32_t) * (size_t)n);
+    if (rc != DYS_OK) return rc;
+    k_narrow_days<<<grid_for(n, 256), 256, 0, h->stream>>>(tmp, dst, n, h->d_bad);
+    CK(h, cudaGetLastError());
+    return DYS_OK;
+}
+
+static int load_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q, const int32_t* t_adm,
+                      const int32_t* src)
+{
+    DevCtx& c = h->c;
+    const int64_t n = c.n_loc;
+    int32_t* tmp = nullptr;
+    CK(h, cudaMalloc((void**)&tmp, sizeof(int32_t) * (size_t)n));
+    int rc = DYS_OK;
+    auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
+    A(copy_in(h, c.status, status_x2, (size_t)n));
+    A(load_days(h, c.t_inf, t_inf, tmp, n));
+    A(load_days(h, c.t_q, t_q, tmp, n));
+    A(load_days(h, c.t_adm, t_adm, tmp, n));
+    A(copy_in(h, c.src, src, sizeof(int32_t) * (size_t)n));
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    return rc;
+}
+
+extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
+                                   const int32_t* t_adm, const int32_t* src, const int32_t* hh, const int32_t* home,
+                                   const int32_t* sa, const double* risk, const double* p_adm, const double* p_death,
+                                   const int32_t* routine)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (!status_x2 || !t_inf || !t_q || !t_adm || !src || !hh || !home || !sa || !risk || !p_adm || !p_death || !routine)
+        return fail(h, DYS_ERR_INVALID_ARG, "dys_load_population: null array");
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    const size_t n = (size_t)c.n_loc;
+    int rc = load_state(h, status_x2, t_inf, t_q, t_adm, src);
+    auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
+    A(copy_in(h, (void*)c.hh, hh, 4 * n)); A(copy_in(h, (void*)c.home, home, 4 * n)); A(copy_in(h, (void*)c.sa, sa, 4 * n));
+    A(copy_in(h, (void*)c.risk, risk, 8 * n)); A(copy_in(h, (void*)c.p_adm, p_adm, 8 * n)); A(copy_in(h, (void*)c.p_death, p_death, 8 * n));
+    A(copy_in(h, (void*)c.routine, routine, 4 * (size_t)c.rt_n * c.V));
+    if (rc != DYS_OK) return rc;
+    k_validate_population<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c, h->d_bad);
+    k_validate_routine<<<grid_for(c.rt_n * c.V, 256), 256, 0, h->stream>>>(c.routine, c.rt_n * c.V, c.B, h->d_bad);
+    CK(h, cudaGetLastError());
+    rc = check_bad(h, "dys_load_population");
+    if (rc != DYS_OK) return rc;
+    h->have_pop = true;
+    h->have_graph = false;
+    return DYS_OK;
+}
+
+extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
+                             const int32_t* t_adm, const int32_t* src)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_set_state before dys_load_population");
+    if (!status_x2 || !t_inf || !t_q || !t_adm || !src) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_state: null array");
+    CK(h, cudaSetDevice(h->device));
+    int rc = load_state(h, status_x2, t_inf, t_q, t_adm, src);
+    if (rc != DYS_OK) return rc;
+    k_validate_population<<<grid_for(h->c.n_loc, 256), 256, 0, h->stream>>>(h->c, h->d_bad);
+    CK(h, cudaGetLastError());
+    rc = check_bad(h, "dys_set_state");
+    if (rc != DYS_OK) return rc;
+    for (int i = 0; i < DYS_STATS_RING; ++i) h->ring_day[i] = -1;
+    h->last_day = -1;
+    return DYS_OK;
+}
+
+extern "C" int dys_set_run(dys_handle* h, double norm_factor, double compliance, uint64_t seed)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    h->c.norm_factor = norm_factor; h->c.compliance = compliance; h->c.seed = seed;
+    h->p.norm_factor = norm_factor; h->p.compliance = compliance; h->p.seed = seed;
+    return DYS_OK;
+}
+
+extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_t* col, const double* val)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_load_graph before dys_load_population");
+    if (!rowptr) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_graph: null rowptr");
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    int64_t* d_rowptr = nullptr;
+    int rc = dev_alloc(h, &d_rowptr, c.n_pad + 1);
+    if (rc != DYS_OK) return rc;
+    rc = copy_in(h, d_rowptr, rowptr, sizeof(int64_t) * (size_t)(c.n_loc + 1));
+    if (rc != DYS_OK) return rc;
+    int64_t ends[2] = {0, 0};
+    CK(h, cudaMemcpyAsync(&ends[0], d_rowptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(&ends[1], d_rowptr + c.n_loc, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (ends[0] != 0 || ends[1] < 0) return fail(h, DYS_ERR_RANGE, "dys_load_graph: rowptr[0] must be 0 and rowptr[N] >= 0");
+    const int64_t nnz = ends[1];
+    if (nnz > 0 && (!col || !val)) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_graph: null col/val");
+    if (c.n_pad > c.n_loc) {   // padded rows are empty
+        std::vector<int64_t> tail((size_t)(c.n_pad - c.n_loc), nnz);
+        CK(h, cudaMemcpyAsync(d_rowptr + c.n_loc + 1, tail.data(), sizeof(int64_t) * tail.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    uint32_t* d_colx = nullptr;
+    double* d_val = nullptr;
+    int32_t* d_col = nullptr;
+    rc = dev_alloc(h, &d_colx, nnz + 16);
+    if (rc == DYS_OK) rc = dev_alloc(h, &d_val, nnz + 2, false);
+    if (rc != DYS_OK) return rc;
+    CK(h, cudaMalloc((void**)&d_col, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    rc = copy_in(h, d_col, col, sizeof(int32_t) * (size_t)nnz);
+    if (rc == DYS_OK) rc = copy_in(h, d_val, val, sizeof(double) * (size_t)nnz);
+    if (rc == DYS_OK) {
+        c.rowptr = d_rowptr; c.colx = d_colx; c.val = d_val;
+        k_validate_graph<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(d_rowptr, d_col, c.n_loc, c.rt_lo, c.rt_lo + c.rt_n, h->d_bad);
+        rc = check_bad(h, "dys_load_graph");
+    }
+    if (rc == DYS_OK) {
+        k_edge_classes<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_col, d_colx);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
+            rc = fail(h, DYS_ERR_CUDA, "k_edge_classes failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d_col);
+    if (rc != DYS_OK) return rc;
+    h->nnz = nnz;
+    const double mean_deg = (double)nnz / (double)c.n_loc;
+    h->lpr = mean_deg <= 24.0 ? 4 : (mean_deg <= 96.0 ? 8 : 32);
+    h->have_graph = true;
+    return DYS_OK;
+}
+
+extern "C" int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int64_t* trig_ptr, const int32_t* trig_hh)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_load_quirk before dys_load_population");
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    int rc = DYS_OK;
+    if (hh_always) {
+        uint8_t* d = nullptr;
+        rc = dev_alloc(h, &d, c.H);
+        if (rc == DYS_OK) rc = copy_in(h, d, hh_always, (size_t)c.H);
+        if (rc != DYS_OK) return rc;
+        c.hh_always = d;
+    } else c.hh_always = nullptr;
+    if (trig_ptr) {
+        int64_t* d = nullptr;
+        rc = dev_alloc(h, &d, c.n_pad + 1);
+        if (rc == DYS_OK) rc = copy_in(h, d, trig_ptr, sizeof(int64_t) * (size_t)(c.n_loc + 1));
+        if (rc != DYS_OK) return rc;
+        int64_t nt = 0;
+        CK(h, cudaMemcpyAsync(&nt, d + c.n_loc, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (nt < 0) return fail(h, DYS_ERR_RANGE, "dys_load_quirk: negative trigger count");
+        if (nt == 0) { c.trig_ptr = nullptr; c.trig_hh = nullptr; return DYS_OK; }
+        if (!trig_hh) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_quirk: null trig_hh");
+        if (c.n_pad > c.n_loc) {
+            std::vector<int64_t> tail((size_t)(c.n_pad - c.n_loc), nt);
+            CK(h, cudaMemcpyAsync(d + c.n_loc + 1, tail.data(), sizeof(int64_t) * tail.size(), cudaMemcpyHostToDevice, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));
+        }
+        int32_t* t = nullptr;
+        rc = dev_alloc(h, &t, nt);
+        if (rc == DYS_OK) rc = copy_in(h, t, trig_hh, sizeof(int32_t) * (size_t)nt);
+        if (rc != DYS_OK) return rc;
+        c.trig_ptr = d; c.trig_hh = t;
+    } else { c.trig_ptr = nullptr; c.trig_hh = nullptr; }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return DYS_OK;
+}
+
+extern "C" int dys_set_open(dys_handle* h, const uint8_t* open_flags)
+{
+    if (!h || !open_flags) return h ? fail(h, DYS_ERR_INVALID_ARG, "dys_set_open: null") : DYS_ERR_INVALID_ARG;
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    int rc = copy_in(h, (void*)c.open, open_flags, (size_t)c.B);
+    if (rc != DYS_OK) return rc;
+    CK(h, cudaMemsetAsync(c.day_flags + 2, 0, sizeof(int32_t), h->stream));
+    k_count_closed<<<grid_for(c.B, 256), 256, 0, h->stream>>>(c.open, c.B, c.day_flags + 2);
+    CK(h, cudaGetLastError());
+    return DYS_OK;
+}
+
+static void tick(dys_handle* h, int which)
+{
+    if (h->tev.empty()) return;
+    cudaEventRecord(h->tev[(size_t)((h->t_end % dys_handle::T_RING) * 4 + which)], h->stream);
+}
+
+static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
+{
+    if (!h->have_pop || !h->have_graph) return fail(h, DYS_ERR_STATE, "dys_step before dys_load_population/dys_load_graph");
+    if (h->begun) return fail(h, DYS_ERR_STATE, "dys_step_begin called twice without dys_step_end");
+    if (day < 0 || day > 32000) return fail(h, DYS_ERR_INVALID_ARG, "day out of range");
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    c.u_adm = c.u_death = c.u_pair = nullptr;
+    c.pair_prob = nullptr;
+    if (inj) {   // injected draws are staged into library-owned device buffers (the caller's may be host memory)
+        const double* srcs[3] = {inj->u_adm, inj->u_death, inj->u_pair};
+        double** dsts[3] = {&h->d_u_adm, &h->d_u_death, &h->d_u_pair};
+        const double** ctxp[3] = {&c.u_adm, &c.u_death, &c.u_pair};
+        if (inj->u_pair && c.n_glob > 8192) return fail(h, DYS_ERR_INVALID_ARG, "injected pair draws are limited to N <= 8192");
+        for (int k = 0; k < 3; ++k) {
+            if (!srcs[k]) continue;
+            const int64_t cnt = k == 2 ? c.n_glob * c.n_glob : c.n_glob;
+            if (!*dsts[k]) { int rc = dev_alloc(h, dsts[k], cnt, false); if (rc != DYS_OK) return rc; }
+            int rc = copy_in(h, *dsts[k], srcs[k], sizeof(double) * (size_t)cnt);
+            if (rc != DYS_OK) return rc;
+            *ctxp[k] = *dsts[k];
+        }
+        if (inj->u_pair) {
+            if (!h->d_pair_prob) { int rc = dev_alloc(h, &h->d_pair_prob, c.n_glob * c.n_glob); if (rc != DYS_OK) return rc; }
+            CK(h, cudaMemsetAsync(h->d_pair_prob, 0, sizeof(double) * (size_t)(c.n_glob * c.n_glob), h->stream));
+            c.pair_prob = h->d_pair_prob;
+        }
+    }
+    if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
+    tick(h, 0);
+    k_day_start<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    tick(h, 1);
+    CK(h, cudaGetLastError());
+    h->begun = true;
+    return DYS_OK;
+}
+
+static int step_end(dys_handle* h, int32_t day)
+{
+    if (!h->begun) return fail(h, DYS_ERR_STATE, "dys_step_end without dys_step_begin");
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    const unsigned g = (unsigned)(c.n_pad / 256);
+    switch (h->lpr) {
+        case 4: k_contagion<4><<<g, 256, 0, h->stream>>>(c, day); break;
+        case 8: k_contagion<8><<<g, 256, 0, h->stream>>>(c, day); break;
+        default: k_contagion<32><<<g, 256, 0, h->stream>>>(c, day); break;
+    }
+    tick(h, 2);
+    k_household_stats<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    tick(h, 3);
+    CK(h, cudaGetLastError());
+    const int slot = (int)(h->steps % DYS_STATS_RING);
+    CK(h, cudaMemcpyAsync(h->h_stats + (size_t)slot * N_STATS, c.stats, sizeof(int64_t) * N_STATS, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaEventRecord(h->ring_ev[slot], h->stream));
+    h->ring_day[slot] = day;
+    h->last_day = day;
+    ++h->steps;
+    if (!h->tev.empty()) ++h->t_end;
+    h->begun = false;
+    return DYS_OK;
+}
+
+extern "C" int dys_step_begin(dys_handle* h, int32_t day, const dys_injected* injected)
+{
+    return h ? step_begin(h, day, injected) : DYS_ERR_INVALID_ARG;
+}
+
+extern "C" int dys_step_end(dys_handle* h, int32_t day) { return h ? step_end(h, day) : DYS_ERR_INVALID_ARG; }
+
+extern "C" int dys_step(dys_handle* h, int32_t day, const dys_injected* injected)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    int rc = step_begin(h, day, injected);
+    return rc == DYS_OK ? step_end(h, day) : rc;
+}
+
+extern "C" int dys_get_stats(dys_handle* h, int32_t day, int64_t* out)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    for (int i = 0; i < DYS_STATS_RING; ++i) {
+        if (h->ring_day[i] != day) continue;
+        CK(h, cudaEventSynchronize(h->ring_ev[i]));
+        memcpy(out, h->h_stats + (size_t)i * N_STATS, sizeof(int64_t) * N_STATS);
+        return DYS_OK;
+    }
+    return fail(h, DYS_ERR_NOT_AVAILABLE, "stats of day %d are not in the ring (last %d days are kept)", day, DYS_STATS_RING);
+}
+
+static int need_last_day(dys_handle* h, int32_t day, const void* buf, const char* what)
+{
+    if (!buf) return fail(h, DYS_ERR_NOT_AVAILABLE, "%s was not requested in dys_params.flags", what);
+    if (day != h->last_day) return fail(h, DYS_ERR_NOT_AVAILABLE, "%s is only kept for the most recent day (%d)", what, h->last_day);
+    return DYS_OK;
+}
+
+static int copy_out(dys_handle* h, void* dst, const void* src, size_t bytes)
+{
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return DYS_OK;
+}
+
+extern "C" int dys_get_sa_hist(dys_handle* h, int32_t day, int32_t* out)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    int rc = need_last_day(h, day, h->c.sa_hist, "sa_hist");
+    return rc != DYS_OK ? rc : copy_out(h, out, h->c.sa_hist, sizeof(int32_t) * (size_t)(h->c.S * HIST_LEN));
+}
+
+extern "C" int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    int rc = need_last_day(h, day, h->c.bcount, "building counts");
+    return rc != DYS_OK ? rc : copy_out(h, out, h->c.bcount, sizeof(int32_t) * (size_t)h->c.B);
+}
+
+extern "C" int dys_get_io_mat(dys_handle* h, int32_t day, int32_t* out)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    int rc = need_last_day(h, day, h->c.io_mat, "io_mat");
+    return rc != DYS_OK ? rc : copy_out(h, out, h->c.io_mat, sizeof(int32_t) * (size_t)(h->c.S * h->c.S));
+}
+
+extern "C" int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_t* infector, int64_t cap, int64_t* n)
+{
+    if (!h || !n) return DYS_ERR_INVALID_ARG;
+    int rc = need_last_day(h, day, h->c.ev_agent, "events");
+    if (rc != DYS_OK) return rc;
+    rc = copy_out(h, h->h_small + 1, h->c.day_flags + 1, sizeof(int32_t));
+    if (rc != DYS_OK) return rc;
+    const int64_t cnt = h->h_small[1];
+    *n = cnt;
+    if (cnt == 0 || (!agent && !infector)) return DYS_OK;
+    if (cap < cnt) return fail(h, DYS_ERR_INVALID_ARG, "dys_get_events: capacity %lld < %lld events", (long long)cap, (long long)cnt);
+    if (agent) rc = copy_out(h, agent, h->c.ev_agent, sizeof(int32_t) * (size_t)cnt);
+    if (rc == DYS_OK && infector) rc = copy_out(h, infector, h->c.ev_src, sizeof(int32_t) * (size_t)cnt);
+    return rc;
+}
+
+extern "C" int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, int32_t* t_q, int32_t* t_adm, int32_t* src)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_get_state before dys_load_population");
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    const int64_t n = c.n_loc;
+    if (status_x2) CK(h, cudaMemcpyAsync(status_x2, c.status, (size_t)n, cudaMemcpyDefault, h->stream));
+    if (src) CK(h, cudaMemcpyAsync(src, c.src, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, h->stream));
+    const int16_t* cols[3] = {c.t_inf, c.t_q, c.t_adm};
+    int32_t* outs[3] = {t_inf, t_q, t_adm};
+    int32_t* tmp = nullptr;
+    for (int k = 0; k < 3; ++k) {
+        if (!outs[k]) continue;
+        if (!tmp) CK(h, cudaMalloc((void**)&tmp, sizeof(int32_t) * (size_t)n));
+        k_widen_days<<<grid_for(n, 256), 256, 0, h->stream>>>(cols[k], tmp, n);
+        cudaError_t e = cudaMemcpyAsync(outs[k], tmp, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { cudaFree(tmp); return fail(h, DYS_ERR_CUDA, "dys_get_state: %s", cudaGetErrorString(e)); }
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (tmp) cudaFree(tmp);
+    return DYS_OK;
+}
+
+extern "C" int dys_get_pair_prob(dys_handle* h, double* out)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    if (!h->d_pair_prob) return fail(h, DYS_ERR_NOT_AVAILABLE, "pair probabilities are only recorded in injected mode");
+    return copy_out(h, out, h->d_pair_prob, sizeof(double) * (size_t)(h->c.n_glob * h->c.n_glob));
+}
+
+extern "C" int dys_sync(dys_handle* h)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return DYS_OK;
+}
+
+extern "C" int dys_get_kernel_times(dys_handle* h, double* ms_total, int64_t* launches)
+{
+    if (!h || !ms_total || !launches) return DYS_ERR_INVALID_ARG;
+    if (h->tev.empty()) return fail(h, DYS_ERR_NOT_AVAILABLE, "DYS_TIME_KERNELS was not set");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < DYS_N_KERNELS; ++k) { ms_total[k] = 0.0; launches[k] = 0; }
+    for (int64_t s = h->t_begin; s < h->t_end; ++s) {
+        const size_t b = (size_t)((s % dys_handle::T_RING) * 4);
+        for (int k = 0; k < DYS_N_KERNELS; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->tev[b + k], h->tev[b + k + 1]) == cudaSuccess) { ms_total[k] += ms; ++launches[k]; }
+        }
+    }
+    h->t_begin = h->t_end;
+    return DYS_OK;
+}
+
+extern "C" int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* bytes)
+{
+    if (!h || !ptr || !bytes) return DYS_ERR_INVALID_ARG;
+    const DevCtx& c = h->c;
+    switch (which) {
+        case DYS_BUF_STATUS: *ptr = c.status; *bytes = c.n_pad; break;
+        case DYS_BUF_INFECTIOUS: *ptr = c.ib; *bytes = round_up(c.n_glob, 1024); break;
+        case DYS_BUF_STATS: *ptr = c.stats; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
+        case DYS_BUF_T_INF: *ptr = c.t_inf; *bytes = c.n_pad * 2; break;
+        default: return fail(h, DYS_ERR_INVALID_ARG, "unknown buffer %d", which);
+    }
+    return DYS_OK;
+}
+
+extern "C" int dys_cuda_stream(dys_handle* h, void** stream)
+{
+    if (!h || !stream) return DYS_ERR_INVALID_ARG;
+    *stream = (void*)h->stream;
+    return DYS_OK;
+}
+
+extern "C" int64_t dys_device_bytes(const dys_handle* h) { return h ? h->dev_bytes : 0; }
+
+extern "C" int dys_keyed_uniform_device(int device, uint64_t seed, uint32_t day, uint32_t stream, const uint32_t* a,
+                                        const uint32_t* b, int64_t n, double* out)
+{
+    if (!a || !b || !out || n <= 0) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_keyed_uniform_device: bad argument");
+    uint32_t *da = nullptr, *db = nullptr;
+    double* dout = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&da, 4 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&db, 4 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, 8 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_keyed_uniform<<<grid_for(n, 256), 256>>>(seed, day, stream, da, db, n, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    if (e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "dys_keyed_uniform_device: %s", cudaGetErrorString(e));
+    return DYS_OK;
+}

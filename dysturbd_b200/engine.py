@@ -1,0 +1,303 @@
+"""ctypes binding of include/dysturbd.h (dysturbd_b200/libdysturbd.so) -- the reference-side stub a maintainer
+would add.  Arrays may be numpy arrays (host) or torch tensors (CPU or CUDA on the engine's
+device); only their data pointers cross the ABI.
+
+There is deliberately NO fallback: if the shared library is missing or no B200 is visible, construction fails.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .population import EpiParams, Population
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdysturbd.so")
+
+N_STATS = 64
+HIST0 = 32
+HIST_LEN = 21
+N_KERNELS = 3
+KERNEL_NAMES = ("k_day_start", "k_contagion", "k_household_stats")
+STAT = {name: i for i, name in enumerate(
+    ["active", "daily_inf", "recovered", "quarantined", "daily_quar", "hosp", "daily_hosp", "dead", "daily_deaths",
+     "ever_infected", "new_diag", "n_events", "sus0", "inf0", "edges_scanned", "candidates", "exposed", "hits",
+     "changed"])}
+
+WANT_SA_HIST, WANT_BUILDING_COUNTS, WANT_EVENTS, WANT_IO_MAT, TIME_KERNELS = 1, 2, 4, 8, 16
+BUF_STATUS, BUF_INFECTIOUS, BUF_STATS, BUF_T_INF = 0, 1, 2, 3
+
+
+class DysError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dysturbd error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("n_agents", C.c_int64), ("n_households", C.c_int64), ("n_buildings", C.c_int64), ("n_areas", C.c_int64),
+        ("n_slots", C.c_int32), ("recover", C.c_int32), ("hospital_recover", C.c_int32), ("diagnosis", C.c_int32),
+        ("quarantine", C.c_int32), ("adm_min_day", C.c_int32), ("adm_max_day", C.c_int32), ("death_min_adm_day", C.c_int32),
+        ("norm_factor", C.c_double), ("compliance", C.c_double), ("pdf_table", C.c_double * 64),
+        ("seed", C.c_uint64), ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("rank", C.c_int32), ("world", C.c_int32), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
+        ("halo_lo", C.c_int64), ("halo_hi", C.c_int64),
+    ]
+
+
+class _Injected(C.Structure):
+    _fields_ = [("u_adm", C.c_void_p), ("u_death", C.c_void_p), ("u_pair", C.c_void_p)]
+
+
+EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population", "dys_load_graph", "dys_load_quirk",
+           "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_begin", "dys_step_end", "dys_get_stats",
+           "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
+           "dys_get_pair_prob", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
+           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library (built by dysturbd_b200._build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DysError(-2, "%s is missing: run `python -m dysturbd_b200._build` (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.dys_create.argtypes = [C.POINTER(_Params), C.c_int, C.POINTER(vp)]
+    lib.dys_destroy.argtypes = [vp]
+    lib.dys_last_error.argtypes = [vp]
+    lib.dys_last_error.restype = C.c_char_p
+    lib.dys_load_population.argtypes = [vp] + [vp] * 12
+    lib.dys_load_graph.argtypes = [vp, vp, vp, vp]
+    lib.dys_load_quirk.argtypes = [vp, vp, vp, vp]
+    lib.dys_set_open.argtypes = [vp, vp]
+    lib.dys_set_run.argtypes = [vp, C.c_double, C.c_double, C.c_uint64]
+    lib.dys_set_state.argtypes = [vp] + [vp] * 5
+    lib.dys_step.argtypes = [vp, i32, C.POINTER(_Injected)]
+    lib.dys_step_begin.argtypes = [vp, i32, C.POINTER(_Injected)]
+    lib.dys_step_end.argtypes = [vp, i32]
+    lib.dys_get_stats.argtypes = [vp, i32, vp]
+    lib.dys_get_sa_hist.argtypes = [vp, i32, vp]
+    lib.dys_get_building_counts.argtypes = [vp, i32, vp]
+    lib.dys_get_events.argtypes = [vp, i32, vp, vp, i64, C.POINTER(i64)]
+    lib.dys_get_io_mat.argtypes = [vp, i32, vp]
+    lib.dys_get_state.argtypes = [vp] + [vp] * 5
+    lib.dys_get_pair_prob.argtypes = [vp, vp]
+    lib.dys_sync.argtypes = [vp]
+    lib.dys_get_kernel_times.argtypes = [vp, vp, vp]
+    lib.dys_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    lib.dys_cuda_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.dys_device_bytes.argtypes = [vp]
+    lib.dys_device_bytes.restype = i64
+    lib.dys_version.restype = C.c_char_p
+    lib.dys_keyed_uniform_device.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, i64, vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(x, dtype=None, n=None):
+    """data pointer of a numpy array or torch tensor (must be contiguous, of the expected dtype)."""
+    if x is None:
+        return None, None
+    if isinstance(x, np.ndarray):
+        if dtype is not None and x.dtype != dtype:
+            raise TypeError("expected %s, got %s" % (dtype, x.dtype))
+        if not x.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous")
+        if n is not None and x.size != n:
+            raise ValueError("expected %d elements, got %d" % (n, x.size))
+        return x.ctypes.data, x
+    if hasattr(x, "data_ptr"):      # torch tensor (CPU or CUDA); the DLPack exchange of the north star reduces to this
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        if n is not None and x.numel() != n:
+            raise ValueError("expected %d elements, got %d" % (n, x.numel()))
+        return x.data_ptr(), x
+    raise TypeError("numpy array or torch tensor expected")
+
+
+def keyed_uniform_device(seed, day, stream, a, b, device=0):
+    """u(day, stream, a, b) evaluated by the CUDA Philox (tests)."""
+    lib = load_library()
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(np.broadcast_to(b, a.shape), dtype=np.uint32)
+    out = np.zeros(a.shape, dtype=np.float64)
+    rc = lib.dys_keyed_uniform_device(device, seed, day, stream, a.ctypes.data, b.ctypes.data, a.size, out.ctypes.data)
+    if rc != 0:
+        raise DysError(rc, (lib.dys_last_error(None) or b"").decode())
+    return out
+
+
+class Engine:
+    """One population on one GPU.  Mirrors the call order of run_EM() (epidemiological_model.py:224-234):
+    `step(day)` is one pass of the reference's day loop; outputs are the integer arrays behind contagious3.py:326-366."""
+
+    def __init__(self, pop: Population, params: EpiParams, device=0, flags=WANT_SA_HIST | WANT_BUILDING_COUNTS | WANT_EVENTS,
+                 rank=0, world=1):
+        self.lib = load_library()
+        self.pop, self.params = pop, params
+        self.N_glob = pop.N_glob
+        p = _Params()
+        p.n_agents, p.n_households, p.n_buildings, p.n_areas, p.n_slots = self.N_glob, pop.H, pop.B, pop.S, pop.V
+        p.recover, p.hospital_recover, p.diagnosis, p.quarantine = params.recover, params.hospital_recover, params.diagnosis, params.quarantine
+        p.adm_min_day, p.adm_max_day, p.death_min_adm_day = params.adm_min_day, params.adm_max_day, params.death_min_adm_day
+        p.norm_factor, p.compliance, p.seed, p.flags = params.norm_factor, params.compliance, params.seed, flags
+        for i in range(64):
+            p.pdf_table[i] = float(params.pdf[i])
+        p.rank, p.world = rank, world
+        p.shard_lo, p.shard_hi = pop.lo, pop.lo + pop.N
+        p.halo_lo, p.halo_hi = pop.halo
+        self.flags = flags
+        self.h = C.c_void_p()
+        rc = self.lib.dys_create(C.byref(p), device, C.byref(self.h))
+        if rc != 0:
+            raise DysError(rc, (self.lib.dys_last_error(None) or b"").decode())
+        self.n_loc = pop.N
+        self.load(pop)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DysError(rc, (self.lib.dys_last_error(self.h) or b"").decode())
+
+    def load(self, pop):
+        n = pop.N
+        a = lambda x, dt, cnt=n: _ptr(np.ascontiguousarray(x, dtype=dt) if isinstance(x, np.ndarray) else x, None, cnt)
+        keep = [a(pop.status, np.uint8), a(pop.t_inf, np.int32), a(pop.t_q, np.int32), a(pop.t_adm, np.int32),
+                a(pop.src, np.int32), a(pop.hh, np.int32), a(pop.home, np.int32), a(pop.sa, np.int32),
+                a(pop.risk, np.float64), a(pop.p_adm, np.float64), a(pop.p_death, np.float64),
+                a(pop.routine, np.int32, (pop.halo[1] - pop.halo[0]) * pop.V)]
+        self._ck(self.lib.dys_load_population(self.h, *[k[0] for k in keep]))
+        g = [a(pop.ip_rowptr, np.int64, n + 1), a(pop.ip_col, np.int32, None), a(pop.ip_val, np.float64, None)]
+        self._ck(self.lib.dys_load_graph(self.h, *[k[0] for k in g]))
+        if pop.hh_always is not None and (pop.hh_always.any() or len(pop.trig_hh)):
+            q = [a(pop.hh_always, np.uint8, pop.H), a(pop.trig_ptr, np.int64, n + 1), a(pop.trig_hh, np.int32, None)]
+            self._ck(self.lib.dys_load_quirk(self.h, *[k[0] for k in q]))
+        self.set_open(pop.open)
+
+    def set_open(self, open_flags):
+        p, keep = _ptr(np.ascontiguousarray(open_flags, dtype=np.uint8) if isinstance(open_flags, np.ndarray) else open_flags,
+                       None, self.pop.B)
+        self._ck(self.lib.dys_set_open(self.h, p))
+
+    def set_run(self, norm_factor=None, compliance=None, seed=None):
+        pr = self.params
+        if norm_factor is not None:
+            pr.norm_factor = norm_factor
+        if compliance is not None:
+            pr.compliance = compliance
+        if seed is not None:
+            pr.seed = seed
+        self._ck(self.lib.dys_set_run(self.h, pr.norm_factor, pr.compliance, pr.seed))
+
+    def set_state(self, status, t_inf, t_q, t_adm, src):
+        n = self.n_loc
+        ks = [_ptr(np.ascontiguousarray(status, np.uint8), None, n)] + [_ptr(np.ascontiguousarray(x, np.int32), None, n)
+                                                                         for x in (t_inf, t_q, t_adm, src)]
+        self._ck(self.lib.dys_set_state(self.h, *[k[0] for k in ks]))
+
+    def _inj(self, u_adm, u_death, u_pair):
+        if u_adm is None and u_death is None and u_pair is None:
+            return None, None
+        inj = _Injected()
+        keep = []
+        for name, x, cnt in (("u_adm", u_adm, self.N_glob), ("u_death", u_death, self.N_glob), ("u_pair", u_pair, self.N_glob ** 2)):
+            if x is None:
+                continue
+            if isinstance(x, np.ndarray):
+                x = np.ascontiguousarray(x, dtype=np.float64)
+            p, k = _ptr(x, None, cnt)
+            keep.append(k)
+            setattr(inj, name, p)
+        return inj, keep
+
+    def step(self, day, u_adm=None, u_death=None, u_pair=None):
+        inj, keep = self._inj(u_adm, u_death, u_pair)
+        self._ck(self.lib.dys_step(self.h, int(day), C.byref(inj) if inj is not None else None))
+
+    def step_begin(self, day):
+        self._ck(self.lib.dys_step_begin(self.h, int(day), None))
+
+    def step_end(self, day):
+        self._ck(self.lib.dys_step_end(self.h, int(day)))
+
+    def stats(self, day):
+        out = np.zeros(N_STATS, dtype=np.int64)
+        self._ck(self.lib.dys_get_stats(self.h, int(day), out.ctypes.data))
+        return out
+
+    def sa_hist(self, day):
+        out = np.zeros((self.pop.S, HIST_LEN), dtype=np.int32)
+        self._ck(self.lib.dys_get_sa_hist(self.h, int(day), out.ctypes.data))
+        return out
+
+    def building_counts(self, day):
+        out = np.zeros(self.pop.B, dtype=np.int32)
+        self._ck(self.lib.dys_get_building_counts(self.h, int(day), out.ctypes.data))
+        return out
+
+    def events(self, day):
+        """today's (infected, infector) row indices, sorted by infected index (the device order is arbitrary)."""
+        n = C.c_int64(0)
+        self._ck(self.lib.dys_get_events(self.h, int(day), None, None, 0, C.byref(n)))
+        a = np.zeros(n.value, dtype=np.int32)
+        s = np.zeros(n.value, dtype=np.int32)
+        if n.value:
+            self._ck(self.lib.dys_get_events(self.h, int(day), a.ctypes.data, s.ctypes.data, n.value, C.byref(n)))
+            o = np.argsort(a, kind="stable")
+            a, s = a[o], s[o]
+        return a, s
+
+    def io_mat(self, day):
+        out = np.zeros((self.pop.S, self.pop.S), dtype=np.int32)
+        self._ck(self.lib.dys_get_io_mat(self.h, int(day), out.ctypes.data))
+        return out
+
+    def state(self):
+        n = self.n_loc
+        out = dict(status=np.zeros(n, np.uint8), t_inf=np.zeros(n, np.int32), t_q=np.zeros(n, np.int32),
+                   t_adm=np.zeros(n, np.int32), src=np.zeros(n, np.int32))
+        self._ck(self.lib.dys_get_state(self.h, *[out[k].ctypes.data for k in ("status", "t_inf", "t_q", "t_adm", "src")]))
+        return out
+
+    def pair_prob(self):
+        out = np.zeros((self.N_glob, self.N_glob), dtype=np.float64)
+        self._ck(self.lib.dys_get_pair_prob(self.h, out.ctypes.data))
+        return out
+
+    def sync(self):
+        self._ck(self.lib.dys_sync(self.h))
+
+    def kernel_times(self):
+        ms = np.zeros(N_KERNELS, dtype=np.float64)
+        cnt = np.zeros(N_KERNELS, dtype=np.int64)
+        self._ck(self.lib.dys_get_kernel_times(self.h, ms.ctypes.data, cnt.ctypes.data))
+        return ms, cnt
+
+    def device_buffer(self, which):
+        p, b = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.dys_device_buffer(self.h, which, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def cuda_stream(self):
+        p = C.c_void_p()
+        self._ck(self.lib.dys_cuda_stream(self.h, C.byref(p)))
+        return p.value
+
+    def device_bytes(self):
+        return int(self.lib.dys_device_bytes(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.dys_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

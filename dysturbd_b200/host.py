@@ -1,0 +1,140 @@
+"""Host side of the day loop: the reference's call surface over the device library.
+
+`EpidemicModel` takes exactly what contagious3.py has in hand when its `while` starts (agents, build,
+bld_visits_by_agents, interaction_prob, scenario -- contagious3.py:114-174), runs each day on the GPU through the
+C ABI (`Engine.step` == one pass of contagious3.py:176-366) and rebuilds the reference's own `outputs` dict
+(contagious3.py:111, 326-366, 389) from the integer arrays the device emits.  Every float in that dict (R, Known R,
+building fractions) is formed here, on the host, with the reference's order of operations (compute_R,
+contagious3.py:29-42), so results compare with `==`.  Phase H (building_lockdown, contagious3.py:57-107, 368-385)
+is O(B) bookkeeping and stays on the host.
+"""
+import numpy as np
+
+from .engine import HIST0, HIST_LEN, STAT, Engine
+from .population import EpiParams, Population
+
+EDU_CODES = (5310, 5312, 5338, 5523, 5525, 5305, 5300, 5340)     # contagious3.py:67-70
+REL_CODES = (5501, 5521)                                         # contagious3.py:74
+
+
+def compute_R_from_hist(hist, pdf, recover):
+    """compute_R (contagious3.py:29-42) on a days-since-infection histogram: hist[0] = today's infections,
+    hist[i] = #agents ever infected with day - t_inf == i.  Same accumulation order, python floats."""
+    new_infections = int(hist[0])
+    sum_I = 0.
+    for i in range(1, recover):
+        sum_I += int(hist[i]) * pdf[i]
+    return new_infections / sum_I if sum_I > 0 else 0
+
+
+def building_lockdown(lu, usg, current, sc, vR, prevVR, choice):
+    """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
+    (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice."""
+    lockdown = np.ones(len(lu))
+    edu = np.where(np.isin(usg, EDU_CODES))[0]
+    rel = np.where(np.isin(usg, REL_CODES))[0]
+    non_res = np.where(lu >= 3)[0]
+
+    def close(idx, half):
+        if half:
+            lockdown[choice(idx, replace=False, size=int(idx.size * 0.5))] = 0
+        else:
+            lockdown[idx] = 0
+
+    def apply(half):
+        if 'ALL' in sc:
+            close(non_res, half)
+        else:
+            if 'EDU' in sc:
+                close(edu, half)
+            if 'REL' in sc:
+                close(rel, half)
+
+    if 'GRADUAL' in sc:
+        if 1 < vR < 2:
+            if prevVR <= 1 or prevVR >= 2:
+                apply(True)
+            else:
+                lockdown = np.array(current, dtype=float)
+        elif vR >= 2:
+            apply(False)
+    elif 1 < vR:
+        apply(False)
+    return lockdown
+
+
+class EpidemicModel:
+    def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
+                 device=0, choice_seed=None, backend=None, population=None):
+        self.params = params or EpiParams()
+        self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob)
+        self.scenario = list(scenario)
+        self.sim = backend(self.pop, self.params) if backend is not None else Engine(self.pop, self.params, device=device)
+        self.day = 0
+        self.open = self.pop.open.astype(float)
+        self.outputs = {'Results': {'Stats': {}, 'Buildings': {}, 'SAs': {}, 'IO_mat': {}}}
+        self._choice = np.random.RandomState(choice_seed).choice
+        p = self.pop
+        self._bld_pop = np.bincount(p.home, minlength=p.B)
+        self._inhabited = np.nonzero(self._bld_pop > 0)[0]
+        self._pdf = [float(x) for x in self.params.pdf]
+        self._active = int(np.isin(p.status, (4, 7, 8, 10)).sum())
+
+    def active(self):
+        """the `while` condition of contagious3.py:176"""
+        return self._active > 0
+
+    def step(self):
+        p, sim, day, prm = self.pop, self.sim, self.day, self.params
+        res = self.outputs['Results']
+        sim.set_open(self.open.astype(np.uint8))
+        closed_today = int((self.open == 0).sum())
+        sim.step(day)
+        st = sim.stats(day)
+        hist = st[HIST0:HIST0 + HIST_LEN]
+        R = compute_R_from_hist(hist, self._pdf, prm.recover)
+        sa_hist = sim.sa_hist(day)
+        sas = [float(x) for x in p.sa_ids]
+        res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
+        vis_R = res['Stats'][day - prm.diagnosis]['R'] if day > prm.diagnosis else 0          # :306-309
+        res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
+        new_infections = int(st[STAT['daily_inf']])
+        S = {'Active infected': int(st[STAT['active']]), 'Daily infections': new_infections,
+             'Recovered': int(st[STAT['recovered']]), 'Quarantined': int(st[STAT['quarantined']]),
+             'Daily quarantined': int(st[STAT['daily_quar']]), 'Hospitalized': int(st[STAT['hosp']]),
+             'Daily hospitalizations': int(st[STAT['daily_hosp']]), 'Total Dead': int(st[STAT['dead']]),
+             'Daily deaths': int(st[STAT['daily_deaths']]), 'R': R, 'Known R': vis_R, 'Closed buildings': closed_today}
+        if day == 0:
+            S['Total infected'] = S['Active infected']                                          # :347-348
+        else:
+            S['Total infected'] = res['Stats'][day - 1]['Total infected'] + new_infections
+        S['Susceptible'] = p.N - S['Total infected']
+        res['Stats'][day] = S
+        bc = sim.building_counts(day)
+        res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
+        ev_a, ev_s = sim.events(day)
+        mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                       # :356-366
+        if len(ev_a):
+            for a, s in zip(p.sa[ev_a], p.sa[ev_s]):
+                mat[sas[a]][sas[s]] += 1
+        res['IO_mat'][day] = mat
+        # phase H: tomorrow's open flags (contagious3.py:368-385)
+        if 'DIFF' in self.scenario:
+            if day != 0:
+                raise KeyError('Vis_R')          # the reference reads a key it never writes (:371 vs :319)
+            self.open = np.ones(p.B)
+        else:
+            prevVR = res['Stats'][day - 1]['Known R'] if day != 0 else 0
+            self.open = building_lockdown(p.bld_lu, p.bld_usg, self.open, self.scenario, vis_R, prevVR, self._choice)
+        self._active = S['Active infected']
+        self.day += 1
+        return S
+
+    def run(self, max_days=None):
+        while self.active() and (max_days is None or self.day < max_days):
+            self.step()
+        st = self.sim.state()
+        src_id = np.where(st['src'] >= 0, self.pop.agent_ids[np.maximum(st['src'], 0)], 0.0)
+        self.outputs['Results']['Infections chain'] = np.stack(
+            [self.pop.agent_ids, st['t_inf'].astype(float), src_id], axis=1).tolist()          # :389
+        return self.outputs

@@ -94,6 +94,17 @@ class Population:
     bld_lu: np.ndarray = None      # build[:,1]
     bld_usg: np.ndarray = None     # build[:,9]
     bld_sa: np.ndarray = None      # i32 [B] index into sa_ids
+    # sharded populations (synth.py): this object holds agents [lo, lo+N) of N_glob; `routine` covers `halo`
+    N_glob: int = None
+    lo: int = 0
+    halo: tuple = None
+    age: np.ndarray = None
+
+    def __post_init__(self):
+        if self.N_glob is None:
+            self.N_glob = self.N
+        if self.halo is None:
+            self.halo = (0, self.N_glob)
 
     @property
     def nnz(self):

@@ -1,0 +1,180 @@
+/* dysturbd.h -- C ABI of the B200-native per-day epidemic step of DySTUrbD.
+ *
+ * The reference (yair-grinb/DySTUrbD) is pure Python and has no FFI; the boundary below is reconstructed from
+ * the function set of `epidemiological model.py` (update_buildings_status :8, update_counts :23,
+ * calculate_hospitalizations :58, calculate_mortality :85, calculate_infections :108), the call order of
+ * run_EM() (epidemiological_model.py:224-234) and the authoritative inline loop contagious3.py:176-387.
+ * One dys_step() == one iteration of that `while` body (phases A-G of SURVEY.md section 3.2); phase H
+ * (building_lockdown, contagious3.py:57-107) stays on the host and feeds dys_set_open().
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns DYS_OK (0) or a negative dys_status; dys_last_error(h)
+ *     gives the message (h may be NULL for errors of dys_create).
+ *   - one handle == one CUDA device + one stream; NOT thread-safe (one host thread per handle; replicas and
+ *     shards use separate handles).
+ *   - every array pointer may be a HOST pointer or a DEVICE pointer on the handle's device (e.g. a torch
+ *     tensor's data_ptr()); the library copies on its own stream.  Caller keeps ownership of everything.
+ *   - status codes are the reference's agents[:,13] values times two (contagious3.py:115-118):
+ *       1 susceptible -> 2, 2 infected undiagnosed -> 4, 3 quarantined healthy -> 6, 3.5 quarantined infected
+ *       -> 7, 4 diagnosed/home isolation -> 8, 5 hospitalised -> 10, 6 recovered -> 12, 7 dead -> 14.
+ *   - agents, households, buildings, statistical areas are dense 0-based indices; the ORIGINAL row order of
+ *     agents[] is significant (infector = largest infecting row index, contagious3.py:248; random keys).
+ */
+#ifndef DYSTURBD_H
+#define DYSTURBD_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dys_handle dys_handle;
+
+typedef enum {
+    DYS_OK = 0,
+    DYS_ERR_INVALID_ARG = -1,
+    DYS_ERR_CUDA = -2,
+    DYS_ERR_STATE = -3,     /* call order (e.g. step before load) */
+    DYS_ERR_NOMEM = -4,
+    DYS_ERR_RANGE = -5,     /* index out of range in an input array */
+    DYS_ERR_NOT_AVAILABLE = -6
+} dys_status;
+
+enum { DYS_S = 2, DYS_I = 4, DYS_QH = 6, DYS_QI = 7, DYS_D = 8, DYS_H = 10, DYS_R = 12, DYS_X = 14 };
+
+/* dys_params.flags */
+enum {
+    DYS_WANT_SA_HIST = 1,        /* per-area days-since-infection histograms (compute_R per area, contagious3.py:282-291) */
+    DYS_WANT_BUILDING_COUNTS = 2,/* infected residents per home building (contagious3.py:339-346) */
+    DYS_WANT_EVENTS = 4,         /* today's (infected, infector) pairs ('Infections chain' / IO_mat inputs, :356-366) */
+    DYS_WANT_IO_MAT = 8,         /* dense S x S origin matrix on the device (small S only) */
+    DYS_TIME_KERNELS = 16        /* record CUDA events around each kernel (dys_get_kernel_times) */
+};
+
+#define DYS_PDF_LEN 64
+#define DYS_HIST_LEN 21          /* days-since-infection 0..20: [0] = new infections, [1..recover-1] feed compute_R (:29-42) */
+#define DYS_N_STATS 64
+
+/* index into the int64 stats block returned by dys_get_stats() */
+enum {
+    DYS_ST_ACTIVE = 0,       /* #status in {2,3.5,4,5}                       'Active infected' (contagious3.py:326) */
+    DYS_ST_DAILY_INF,        /* #status not in {1,3} and t_inf == day        'Daily infections' */
+    DYS_ST_RECOVERED,        /* #6 */
+    DYS_ST_QUARANTINED,      /* #3 <= status <= 4 */
+    DYS_ST_DAILY_QUAR,       /* ... and t_q == day */
+    DYS_ST_HOSPITALIZED,     /* #5 */
+    DYS_ST_DAILY_HOSP,       /* admissions drawn today (:215) */
+    DYS_ST_DEAD,             /* #7 */
+    DYS_ST_DAILY_DEATHS,     /* deaths drawn today (:226) */
+    DYS_ST_EVER_INFECTED,    /* #status not in {1,3} */
+    DYS_ST_NEW_DIAG,         /* #status 4 with days-since-infection == diagnosis (today's diagnoses, :261) */
+    DYS_ST_N_EVENTS,         /* infections applied today (phase D) */
+    /* work counters of the day (feed the algorithmic-bytes formula of DESIGN.md) */
+    DYS_ST_SUS0,             /* susceptible at day start (status 1 or 3) */
+    DYS_ST_INF0,             /* infectious at day start (status 2, 3.5, 4) */
+    DYS_ST_EDGES_SCANNED,    /* interaction_prob non-zeros visited */
+    DYS_ST_CANDIDATES,       /* ... whose column agent is infectious */
+    DYS_ST_EXPOSED,          /* ... and shares a building today: one Bernoulli each */
+    DYS_ST_HITS,             /* Bernoulli successes */
+    DYS_ST_CHANGED,          /* agents whose state was rewritten today */
+    DYS_ST_HIST0 = 32        /* [32 .. 32+20]: global days-since-infection histogram */
+};
+
+typedef struct dys_params {
+    int64_t n_agents;            /* N (<= 2^27) */
+    int64_t n_households;        /* H */
+    int64_t n_buildings;         /* B */
+    int64_t n_areas;             /* S */
+    int32_t n_slots;             /* V: routine slots per agent (<= 16; 10 in the reference) */
+    int32_t recover;             /* parameters.py:42  (21) */
+    int32_t hospital_recover;    /* parameters.py:43  (28) */
+    int32_t diagnosis;           /* parameters.py:45  (7)  */
+    int32_t quarantine;          /* parameters.py:46  (7)  */
+    int32_t adm_min_day;         /* contagious3.py:205 (4)  -- absolute infection day window for admission */
+    int32_t adm_max_day;         /* contagious3.py:205 (14) */
+    int32_t death_min_adm_day;   /* contagious3.py:219 (3)  */
+    double norm_factor;          /* parameters.py:41  (0.08) */
+    double compliance;           /* extension: P(household member obeys quarantine); 1.0 == reference */
+    double pdf_table[DYS_PDF_LEN]; /* contagious_risk_day.pdf(0..63), host-computed (parameters.py:44) */
+    uint64_t seed;               /* Philox key; counter = (a, b, day, stream) */
+    int32_t flags;
+    int32_t reserved;
+    /* sharded mode (world > 1): this handle owns agents [shard_lo, shard_hi) of the n_agents global agents */
+    int32_t rank, world;
+    int64_t shard_lo, shard_hi;
+    /* `routine` passed to dys_load_population covers global agents [halo_lo, halo_hi) -- the owned range plus every
+     * agent an owned interaction_prob row references; 0, 0 means all n_agents */
+    int64_t halo_lo, halo_hi;
+} dys_params;
+
+/* literal pre-drawn uniforms (small N only): replaces np.random.random at contagious3.py:212, :224, :239 */
+typedef struct dys_injected {
+    const double* u_adm;         /* [N]   */
+    const double* u_death;       /* [N]   */
+    const double* u_pair;        /* [N*N] row = susceptible, col = infectious, original indices */
+} dys_injected;
+
+int dys_create(const dys_params* params, int device, dys_handle** out);
+int dys_destroy(dys_handle* h);
+const char* dys_last_error(const dys_handle* h);
+
+/* agents[N,29] as structure-of-arrays (host wrapper: dysturbd_b200/population.py).
+ * status_x2 <- col 13, t_inf <- col 16, t_q <- col 19, t_adm <- col 24, src <- row index of col 21 (-1 none),
+ * hh <- col 1, home <- col 7, sa <- col 22 (-1 = none), risk <- col 14, p_adm <- col 23, p_death <- col 26,
+ * routine <- bld_visits_by_agents[N,V] as building indices, -1 = empty (contagious3.py:139-170). */
+int dys_load_population(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
+                        const int32_t* t_adm, const int32_t* src, const int32_t* hh, const int32_t* home,
+                        const int32_t* sa, const double* risk, const double* p_adm, const double* p_death,
+                        const int32_t* routine);
+/* interaction_prob (contagious3.py:129) as CSR over its non-zeros; columns ascending within a row.
+ * Must follow dys_load_population (the per-edge shared-building classes are derived from the routines). */
+int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_t* col, const double* val);
+/* the whole-row isin of contagious3.py:267; all three may be NULL (no quirk) */
+int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int64_t* trig_ptr, const int32_t* trig_hh);
+/* build[:,10] for the coming day (contagious3.py:181, 384) */
+int dys_set_open(dys_handle* h, const uint8_t* open_flags);
+/* parameter sweeps / Monte-Carlo replicas on a loaded population */
+int dys_set_run(dys_handle* h, double norm_factor, double compliance, uint64_t seed);
+int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
+                  const int32_t* t_adm, const int32_t* src);
+
+/* one day: contagious3.py:176-366, asynchronous on the handle's stream */
+int dys_step(dys_handle* h, int32_t day, const dys_injected* injected /* nullable */);
+/* the same day in two halves, for sharded populations: _begin writes this shard's slice of the day-start
+ * infectious bytes (DYS_BUF_INFECTIOUS) and applies phases B, C; the caller exchanges the slices between ranks
+ * (all-gather over NCCL); _end runs phases D-G.  dys_step == dys_step_begin + dys_step_end. */
+int dys_step_begin(dys_handle* h, int32_t day, const dys_injected* injected /* nullable */);
+int dys_step_end(dys_handle* h, int32_t day);
+
+/* per-day integer outputs; these wait for `day` to finish.  Stats of the last DYS_STATS_RING days are kept;
+ * histograms, building counts, events and the IO matrix only for the most recent day. */
+#define DYS_STATS_RING 64
+int dys_get_stats(dys_handle* h, int32_t day, int64_t* out /* [DYS_N_STATS] */);
+int dys_get_sa_hist(dys_handle* h, int32_t day, int32_t* out /* [S*DYS_HIST_LEN] */);
+int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out /* [B] */);
+int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_t* infector, int64_t cap, int64_t* n);
+int dys_get_io_mat(dys_handle* h, int32_t day, int32_t* out /* [S*S] */);
+int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, int32_t* t_q, int32_t* t_adm, int32_t* src);
+/* P for every evaluated pair of the most recent day (tests; requires injected mode): out[N*N] */
+int dys_get_pair_prob(dys_handle* h, double* out);
+
+int dys_sync(dys_handle* h);
+/* mean milliseconds per launch and launch counts since the last call, per kernel
+ * (0 day_start, 1 contagion, 2 household_stats); needs DYS_TIME_KERNELS */
+#define DYS_N_KERNELS 3
+int dys_get_kernel_times(dys_handle* h, double* ms_total /* [DYS_N_KERNELS] */, int64_t* launches /* [DYS_N_KERNELS] */);
+/* raw device pointers for zero-copy interop (torch / DLPack / NCCL): which = one of dys_buffer */
+typedef enum { DYS_BUF_STATUS = 0, DYS_BUF_INFECTIOUS = 1, DYS_BUF_STATS = 2, DYS_BUF_T_INF = 3 } dys_buffer;
+int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* bytes);
+int dys_cuda_stream(dys_handle* h, void** stream);
+int64_t dys_device_bytes(const dys_handle* h);
+/* evaluates the keyed uniform u(day, stream, a[k], b[k]) ON THE DEVICE for n host-side index pairs (known-answer
+ * tests of the device Philox against oracle/philox_np.py) */
+int dys_keyed_uniform_device(int device, uint64_t seed, uint32_t day, uint32_t stream, const uint32_t* a,
+                             const uint32_t* b, int64_t n, double* out);
+const char* dys_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -18,6 +18,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ST_S 2
 #define ST_I 4
@@ -53,6 +56,24 @@ double orc_keyed_uniform(uint64_t seed, uint32_t day, uint32_t stream, uint32_t 
     philox4x32_10(ctr, key, o);
     uint64_t w = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
     return (double)(w >> 11) * (1.0 / 9007199254740992.0);
+}
+
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }
 
 /* ---- the day ---- */

@@ -61,6 +61,10 @@ def lib():
     return _lib
 
 
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
 def keyed_uniform(seed, day, stream, a, b=0):
     return lib().orc_keyed_uniform(seed, day, stream, a, b)
 
@@ -97,8 +101,8 @@ class OracleSim:
             routine=c(pop.routine, np.int32), rowptr=c(pop.ip_rowptr, np.int64), col=c(pop.ip_col, np.int32),
             val=c(pop.ip_val, np.float64), hh_always=c(pop.hh_always, np.uint8),
             trig_ptr=c(pop.trig_ptr, np.int64), trig_hh=c(pop.trig_hh, np.int32))
-        self.stats = np.zeros(N_STATS, dtype=np.int64)
-        self.sa_hist = np.zeros((max(pop.S, 1), 21), dtype=np.int32)
+        self._stats = np.zeros(N_STATS, dtype=np.int64)
+        self._sa_hist = np.zeros((max(pop.S, 1), 21), dtype=np.int32)
         self.bld_infected = np.zeros(pop.B, dtype=np.int32)
         self.ev_agent = np.zeros(pop.N, dtype=np.int32)
         self.ev_src = np.zeros(pop.N, dtype=np.int32)
@@ -117,7 +121,7 @@ class OracleSim:
                      "hh_always", "trig_ptr", "trig_hh"):
             setattr(ctx, name, _p(k[name]))
         ctx.open = _p(self.open)
-        ctx.stats, ctx.sa_hist, ctx.bld_infected = _p(self.stats), _p(self.sa_hist), _p(self.bld_infected)
+        ctx.stats, ctx.sa_hist, ctx.bld_infected = _p(self._stats), _p(self._sa_hist), _p(self.bld_infected)
         ctx.ev_agent, ctx.ev_src, ctx.pair_prob = _p(self.ev_agent), _p(self.ev_src), _p(self.pair_prob)
         self.ctx = ctx
 
@@ -130,16 +134,26 @@ class OracleSim:
         if self.pair_prob is not None:
             self.pair_prob[:] = 0.0
         if self.threads is not None:
-            os.environ["OMP_NUM_THREADS"] = str(self.threads)
+            lib().orc_set_threads(int(self.threads))
         rc = lib().orc_day(C.byref(self.ctx), int(day))
         if rc != 0:
             raise RuntimeError("orc_day failed")
-        return self.stats.copy()
+        return self._stats.copy()
+
+    # the same read-out surface as dysturbd_b200.engine.Engine, so tests can drive either through one harness
+    def stats(self, day=None):
+        return self._stats.copy()
+
+    def sa_hist(self, day=None):
+        return self._sa_hist[:self.pop.S].copy()
+
+    def building_counts(self, day=None):
+        return self.bld_infected.copy()
 
     def state(self):
         return dict(status=self.status.copy(), t_inf=self.t_inf.copy(), t_q=self.t_q.copy(),
                     t_adm=self.t_adm.copy(), src=self.src.copy())
 
-    def events(self):
-        n = int(self.stats[STAT_NAMES.index("n_events")])
+    def events(self, day=None):
+        n = int(self._stats[STAT_NAMES.index("n_events")])
         return self.ev_agent[:n].copy(), self.ev_src[:n].copy()

@@ -1,0 +1,112 @@
+"""Shared test harness: golden-fixture loading and a day-by-day comparison that drives either the CPU oracle
+(oracle/port.OracleSim) or the CUDA engine (dysturbd_b200.engine.Engine) through the same calls."""
+import json
+import os
+
+import numpy as np
+
+from dysturbd_b200.population import EpiParams, Population
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURES = ["city300_dense_nolockdown", "city300_philox_gradual_all", "city800_philox_edu_rel", "synth2000_philox_all"]
+
+
+class Fixture:
+    def __init__(self, name):
+        import scipy.sparse as sp
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.meta = json.loads(str(z["meta"]))
+        self.agents, self.build, self.visits = z["agents"], z["build"], z["visits"]
+        n = len(self.agents)
+        self.ip = sp.csr_matrix((z["ip_data"], z["ip_indices"], z["ip_indptr"]), shape=(n, n))
+        self.exp = {k: z[k] for k in ("status_x2", "t_inf", "t_q", "t_adm", "src_id", "open_next")}
+        self.outputs = json.loads(str(z["outputs"]))
+        self.days = len(self.exp["status_x2"])
+        self.pop = Population.from_reference(self.agents, self.build, self.visits, self.ip)
+        self.params = EpiParams(norm_factor=self.meta["norm_factor"], seed=self.meta["draws_seed"])
+        self.scenario = self.meta["scenario"]
+
+    def dense_draws(self, day, cache={}):
+        """the MT19937 arrays oracle/literal.DenseDraws handed the reference, regenerated (RandomState is stable)"""
+        key = self.name
+        if key not in cache:
+            cache.clear()
+            cache[key] = (np.random.RandomState(self.meta["draws_seed"]), {})
+        rs, days = cache[key]
+        n = len(self.agents)
+        while len(days) <= day:
+            days[len(days)] = (rs.random_sample(n), rs.random_sample(n), rs.random_sample((n, n)))
+        return days[day]
+
+    def expected_src(self, day):
+        ids = self.exp["src_id"][day]
+        idx = {v: i for i, v in enumerate(self.pop.agent_ids)}
+        return np.array([idx[v] if v != 0 else -1 for v in ids], dtype=np.int32)
+
+
+def run_against_fixture(sim, fx, days=None):
+    """Steps `sim` through the fixture's days, feeding the reference's own open flags, and asserts bit-exact agent
+    state and Stats integers every day."""
+    days = fx.days if days is None else min(days, fx.days)
+    for d in range(days):
+        if fx.meta["draws"] == "dense":
+            ua, ud, up = fx.dense_draws(d)
+            sim.step(d, ua, ud, up)
+        else:
+            sim.step(d)
+        st = sim.state()
+        assert np.array_equal(st["status"], fx.exp["status_x2"][d]), "status day %d" % d
+        assert np.array_equal(st["t_inf"], fx.exp["t_inf"][d]), "t_inf day %d" % d
+        assert np.array_equal(st["t_q"], fx.exp["t_q"][d]), "t_q day %d" % d
+        assert np.array_equal(st["t_adm"], fx.exp["t_adm"][d]), "t_adm day %d" % d
+        assert np.array_equal(st["src"], fx.expected_src(d)), "infector day %d" % d
+        S = fx.outputs["Results"]["Stats"][str(d)]
+        s = sim.stats(d)
+        got = dict(zip(["Active infected", "Daily infections", "Recovered", "Quarantined", "Daily quarantined", "Hospitalized",
+                        "Daily hospitalizations", "Total Dead", "Daily deaths"], [int(x) for x in s[:9]]))
+        for k, v in got.items():
+            assert S[k] == v, "%s day %d: %s != %s" % (k, d, S[k], v)
+        sim.set_open(fx.exp["open_next"][d])
+    return days
+
+
+def compare_outputs(got, exp, days):
+    """the reference's outputs dict (JSON round-tripped) vs EpidemicModel.outputs: exact, floats included."""
+    for d in range(days):
+        g, e = got["Results"]["Stats"][d], exp["Results"]["Stats"][str(d)]
+        for k, v in e.items():
+            assert g[k] == v, ("Stats", d, k, g[k], v)
+        gs, es = got["Results"]["SAs"][d], exp["Results"]["SAs"][str(d)]
+        for key in ("R", "vis_R"):
+            for sa, v in es[key].items():
+                assert gs[key][float(sa)] == v, ("SAs", d, key, sa)
+        gb, eb = got["Results"]["Buildings"][d], exp["Results"]["Buildings"][str(d)]
+        assert len(gb) == len(eb)
+        for x, y in zip(gb, eb):
+            assert x[0] == y[0] and x[1] == y[1] and x[2] == y[2], ("Buildings", d, x, y)
+        gm, em = got["Results"]["IO_mat"][d], exp["Results"]["IO_mat"][str(d)]
+        for sa, row in em.items():
+            for sa2, v in row.items():
+                assert gm[float(sa)][float(sa2)] == v, ("IO_mat", d, sa, sa2)
+
+
+def compare_sims(a, b, days, open_fn=None):
+    """two simulators (oracle / engine) on the same population and keyed draws: bit-exact state + every counter"""
+    for d in range(days):
+        if open_fn is not None:
+            o = open_fn(d)
+            a.set_open(o)
+            b.set_open(o)
+        a.step(d)
+        b.step(d)
+        sa, sb = a.state(), b.state()
+        for k in ("status", "t_inf", "t_q", "t_adm", "src"):
+            assert np.array_equal(sa[k], sb[k]), "%s differs on day %d (%d agents)" % (k, d, int((sa[k] != sb[k]).sum()))
+        xa, xb = a.stats(d), b.stats(d)
+        assert np.array_equal(xa[:18], xb[:18]), "counters differ on day %d: %s vs %s" % (d, xa[:18], xb[:18])
+        assert np.array_equal(xa[32:53], xb[32:53]), "histogram differs on day %d" % d
+        assert np.array_equal(a.sa_hist(d), b.sa_hist(d)), "sa_hist day %d" % d
+        assert np.array_equal(a.building_counts(d), b.building_counts(d)), "building counts day %d" % d
+        ea, eb = a.events(d), b.events(d)
+        assert np.array_equal(ea[0], eb[0]) and np.array_equal(ea[1], eb[1]), "events day %d" % d

@@ -1,0 +1,59 @@
+"""BASELINE.json's full single-GPU size (1 M agents) through size-independent properties, plus an oracle comparison at
+a size the oracle still finishes in seconds per day."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_200k_agents_vs_oracle(oracle_lib):
+    from dysturbd_b200 import engine
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import synth_population
+    from helpers import compare_sims
+    pop = synth_population(200_000, seed=4, seeds_per_22493=60)
+    prm = EpiParams(norm_factor=4.0, seed=77)
+    g = engine.Engine(pop, prm)
+    o = oracle_lib.OracleSim(pop, prm)
+    compare_sims(o, g, 30)
+    g.close()
+
+
+def test_one_million_agents_properties():
+    from dysturbd_b200 import engine
+    from dysturbd_b200.engine import STAT
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import synth_population
+    pop = synth_population(1_000_000, seed=1, seeds_per_22493=60)
+    g = engine.Engine(pop, EpiParams(norm_factor=4.0, seed=5))
+    ever_prev, dead_prev, rec_prev = 0, 0, 0
+    events_total = int((pop.status == 4).sum())
+    for d in range(60):
+        g.step(d)
+        s = g.stats(d)
+        st = g.state()
+        cnt = np.bincount(st["status"], minlength=16)
+        # compartments partition the population
+        assert cnt[[2, 4, 6, 7, 8, 10, 12, 14]].sum() == pop.N
+        assert s[STAT["active"]] == cnt[4] + cnt[7] + cnt[8] + cnt[10]
+        assert s[STAT["recovered"]] == cnt[12] and s[STAT["dead"]] == cnt[14] and s[STAT["hosp"]] == cnt[10]
+        assert s[STAT["quarantined"]] == cnt[6] + cnt[7] + cnt[8]
+        ever = int(s[STAT["ever_infected"]])
+        events_total += int(s[STAT["n_events"]])
+        assert ever == events_total                        # every infection is an event, nobody is infected twice
+        assert ever >= ever_prev and s[STAT["dead"]] >= dead_prev and s[STAT["recovered"]] >= rec_prev
+        assert s[STAT["dead"]] == dead_prev + s[STAT["daily_deaths"]]
+        ever_prev, dead_prev, rec_prev = ever, int(s[STAT["dead"]]), int(s[STAT["recovered"]])
+        # histogram: bin k counts agents infected k days ago
+        h = s[32:53]
+        tinf = st["t_inf"][(st["status"] != 2) & (st["status"] != 6)]
+        assert np.array_equal(h, np.bincount(d - tinf, minlength=21)[:21])
+        assert g.sa_hist(d).sum(axis=0).tolist() == h.tolist()
+        bc = g.building_counts(d)
+        assert bc.sum() == cnt[4] + cnt[7] + cnt[8]
+        a, src = g.events(d)
+        assert len(a) == s[STAT["n_events"]] and (st["t_inf"][a] == d).all() and np.array_equal(st["src"][a], src)
+        # an infector was infectious this morning: infected at least one day ago
+        assert (st["t_inf"][src] < d).all() if len(a) else True
+    assert ever_prev > 100_000
+    g.close()
