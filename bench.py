@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- agent-days/s of the per-day epidemic step (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N=1: the synthetic ~1 M-agent city, BASELINE.json configs[1])
+  torchrun ... bench.py --gpus N --steps K --warmup W      (N>1: ONE coupled city of N x ~1 M agents, sharded by
+                                                            community, per-day NCCL exchange; weak scaling)
+  python bench.py --impl reference ...                     (the CPU path on the host cores, same config and metric)
+
+A step is one simulated day (one pass of contagious3.py:176-366) over the whole population.  Prints ONE JSON line.
+`value`  : K days back to back with the population resident in HBM, timed with CUDA events on the library's stream.
+`e2e`    : the same K days through the C ABI the way the reference-facing host loop uses it: every day the open
+           flags come from pinned host memory and the day's outputs (stats, per-area histograms, per-building counts,
+           infection events) are read back to host memory.
+`roofline`: k_contagion (the dominant kernel) -- algorithmic bytes per launch from the day's own work counters
+           (formula in DESIGN.md) over its mean CUDA-event duration, against MEASURED_PEAKS.json.
+`cpu_baseline`: the C oracle (OpenMP) on the same population, a bounded sample of days, rank 0 / N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=365)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--communities-per-gpu", type=int, default=89, help="89 x 11 264 = 1 002 496 agents per GPU")
+    ap.add_argument("--norm-factor", type=float, default=4.0)
+    ap.add_argument("--seeds-per-22493", type=int, default=20)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_population(args, rank, world):
+    from dysturbd_b200.synth import COMMUNITY, synth_population
+    cpg = args.communities_per_gpu
+    n_total = COMMUNITY * cpg * world
+    comm = None if world == 1 else (rank * cpg, (rank + 1) * cpg)
+    pop = synth_population(n_total, seed=args.seed, communities=comm, seeds_per_22493=args.seeds_per_22493)
+    return pop, n_total
+
+
+def make_params(args):
+    from dysturbd_b200.population import EpiParams
+    return EpiParams(norm_factor=args.norm_factor, seed=20201019)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.gpu, self.proc = [], gpu_index, None
+        self.active = False
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            if self.active:
+                self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def contagion_bytes(N, st, prev_active_like):
+    """Algorithmic bytes one k_contagion launch must move (DESIGN.md section 'k_contagion: bytes per launch'),
+    from the day's own counters: each needed datum once, at its stored width."""
+    from dysturbd_b200.engine import STAT
+    sus0, inf0 = int(st[STAT["sus0"]]), int(st[STAT["inf0"]])
+    edges, exposed, events, changed = (int(st[STAT[k]]) for k in ("edges_scanned", "exposed", "n_events", "changed"))
+    b = N * 1                      # status of every agent (u8)
+    b += sus0 * 8                  # row pointers of susceptible rows (i64, consecutive rows share one)
+    b += edges * 4                 # column words of every scanned non-zero (u32)
+    b += min(N, edges) * 1         # infectious bytes of the column agents (u8), each distinct agent once
+    b += exposed * 8               # interaction_prob value per Bernoulli (f64)
+    b += min(sus0, exposed) * 8    # risk of the rows that drew at least once (f64)
+    b += (inf0 + prev_active_like) * 2   # t_inf of infectious / hospitalised (i16), t_q of quarantined (i16)
+    b += events * (2 + 4)          # t_inf + infector written for the newly infected
+    b += changed * 1               # status rewritten
+    return b
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dysturbd_b200 import engine
+    from dysturbd_b200.engine import STAT
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pop, n_total = make_population(args, rank, world)
+    prm = make_params(args)
+    W, K = args.warmup, args.steps
+    all_out = engine.WANT_SA_HIST | engine.WANT_BUILDING_COUNTS | engine.WANT_EVENTS
+    t0 = time.perf_counter()
+    eng = engine.Engine(pop, prm, device=local, flags=all_out, rank=rank, world=world)
+    eng.sync()
+    load_s = time.perf_counter() - t0
+    stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=local)
+    init = pop.copy_state()
+
+    ib_t = None
+    if world > 1:
+        ptr, nbytes = eng.device_buffer(engine.BUF_INFECTIOUS)
+
+        class _Cai:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        ib_t = torch.as_tensor(_Cai(), device=torch.device("cuda", local))[:n_total]
+        shard = pop.N
+
+    def day_step(e, day):
+        if world == 1:
+            e.step(day)
+        else:
+            e.step_begin(day)
+            dist.all_gather_into_tensor(ib_t, ib_t[rank * shard:(rank + 1) * shard])   # in place: day-start infectious bytes
+            e.step_end(day)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+
+    # ---- pass 1: resident throughput (`value`) ----
+    with torch.cuda.stream(stream):
+        for d in range(W):
+            day_step(eng, d)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.active = True
+        ev0.record(stream)
+        for d in range(W, W + K):
+            day_step(eng, d)
+        ev1.record(stream)
+        barrier()
+        clocks.active = False
+        ms_value = max_over_ranks(ev0.elapsed_time(ev1))
+    st_last = eng.stats(W + K - 1)
+
+    # ---- pass 2: end to end through the C ABI with host buffers (`e2e`) ----
+    eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
+    open_pinned = torch.ones(pop.B, dtype=torch.uint8).pin_memory()
+    h2d = d2h = 0
+    stats_days = []
+    with torch.cuda.stream(stream):
+        def e2e_day(d, count):
+            nonlocal h2d, d2h
+            eng.set_open(open_pinned)
+            day_step(eng, d)
+            st = eng.stats(d)
+            sa = eng.sa_hist(d)
+            bc = eng.building_counts(d)
+            ea, es = eng.events(d)
+            if world > 1:   # global stats block (the host loop needs it for R / the lockdown decision)
+                t = torch.from_numpy(st).cuda()
+                dist.all_reduce(t)
+                st = t.cpu().numpy()
+            if count:
+                h2d += pop.B
+                d2h += st.nbytes + sa.nbytes + bc.nbytes + ea.nbytes + es.nbytes
+                stats_days.append(st)
+        for d in range(W):
+            e2e_day(d, False)
+        barrier()
+        clocks.active = True
+        t0 = time.perf_counter()
+        for d in range(W, W + K):
+            e2e_day(d, True)
+        barrier()
+        s_e2e = max_over_ranks(time.perf_counter() - t0)
+        clocks.active = False
+    assert np.array_equal(stats_days[-1][:12], st_last[:12]) or world > 1, "e2e replay diverged from the resident pass"
+
+    # ---- pass 3: per-kernel CUDA-event durations for the roofline (same days, same state) ----
+    eng.close()
+    eng_t = engine.Engine(pop, prm, device=local, flags=all_out | engine.TIME_KERNELS, rank=rank, world=world)
+    stream_t = torch.cuda.ExternalStream(eng_t.cuda_stream(), device=local)
+    if world > 1:
+        ptr, nbytes = eng_t.device_buffer(engine.BUF_INFECTIOUS)
+
+        class _Cai2:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        ib_t = torch.as_tensor(_Cai2(), device=torch.device("cuda", local))[:n_total]
+    kbytes = 0
+    with torch.cuda.stream(stream_t):
+        for d in range(W):
+            day_step(eng_t, d)
+        eng_t.kernel_times()
+        barrier()
+        for d in range(W, W + K):
+            day_step(eng_t, d)
+        ms_k, n_k = eng_t.kernel_times()
+    for i, st in enumerate(stats_days):     # the e2e pass ran the same days from the same state: same counters
+        prev = stats_days[i - 1] if i else st
+        kbytes += contagion_bytes(n_total, st, int(prev[STAT["hosp"]]) + int(prev[STAT["quarantined"]]))
+    kbytes //= world                        # counters are global after the all-reduce; a rank moves its share
+    eng_t.close()
+    clocks.stop()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = ms_k[1] / max(1, n_k[1])
+    achieved = (kbytes / max(1, K)) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = n_total * K / (ms_value * 1e-3)
+    line = {
+        "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/i16 state, f64 probabilities", "data": "synthetic",
+        "config": {
+            "workload": "synthetic city, %d agents per GPU (%d communities of 11264; ~300k households, ~50k buildings per "
+                        "million), communities social network (degree ~16.7), days %d..%d of one epidemic" %
+                        (pop.N, args.communities_per_gpu, W, W + K - 1),
+            "agents_total": n_total, "edges_per_gpu": pop.nnz, "norm_factor": args.norm_factor,
+            "seeds_per_22493": args.seeds_per_22493, "scenario": "noLockdown",
+            "parallelism": "1 GPU" if world == 1 else "sharded by community x%d, per-day NCCL all-gather of infectious bytes" % world,
+            "l2": "state + network of one day (%.0f MB) exceed L2 only partly; every day rewrites the state, no flush" %
+                  (eng_bytes(pop) / 1e6),
+            "ever_infected_at_end": int(st_last[STAT["ever_infected"]]) if world == 1 else None,
+            "load_seconds": load_s,
+        },
+        "e2e": {"value": n_total * K / s_e2e, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                "ms_per_step": s_e2e * 1e3 / K},
+        "gpu_launches": int(sum(n_k)) if sum(n_k) else 3 * K,
+        "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
+        "roofline": {"bound": "hbm", "kernel": "k_contagion", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms},
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(pop, prm, args.cpu_baseline_seconds, W, K)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def eng_bytes(pop):
+    return pop.N * (1 + 6 + 4 + 12 + 24 + 1) + pop.nnz * 12 + pop.routine.size * 4
+
+
+def cpu_baseline(pop, prm, budget_s, W, K, threads=None):
+    """the C oracle (kind 'port': the literal numpy reference cannot run at this size -- its interaction_prob is a
+    dense N x N float64 matrix, 8 TB at 1 M agents) on the same population, all host threads, bounded sample."""
+    from oracle import port
+    o = port.OracleSim(pop, prm, threads=threads)
+    cores = threads or port.max_threads()
+    t_all, d = 0.0, 0
+    while d < W + K and (d < W + 3 or t_all < budget_s):
+        t0 = time.perf_counter()
+        o.step(d)
+        dt = time.perf_counter() - t0
+        if d >= W:
+            t_all += dt
+        d += 1
+    days = d - W
+    return {"value": pop.N * days / t_all, "unit": "agent-days/s", "cores": cores, "kind": "port", "days": days,
+            "sample": "days %d..%d of the same epidemic (%d of %d timed days), C oracle with OpenMP" % (W, d - 1, days, K),
+            "seconds": t_all}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pop, n_total = make_population(args, 0, 1)
+    prm = make_params(args)
+    W, K = args.warmup, args.steps
+    cb = cpu_baseline(pop, prm, 120.0, W, K)
+    days = cb["days"]
+    line = {
+        "impl": "reference", "metric": "agent-days/sec", "value": cb["value"], "unit": "agent-days/s", "n_gpus": args.gpus,
+        "steps": K, "warmup": W, "ms_per_step": cb["seconds"] * 1e3 / max(1, days), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 state, f64 probabilities", "data": "synthetic",
+        "config": {"workload": "synthetic city, %d agents (%d communities of 11264), CPU path on the host cores" %
+                               (pop.N, args.communities_per_gpu), "norm_factor": args.norm_factor,
+                   "note": "contagious3.py itself cannot run this size (dense N x N interaction_prob = 8 TB); this is its "
+                           "sparse C restatement, bit-identical to the literal loop on the golden vectors"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "agent-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

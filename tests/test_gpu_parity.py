@@ -92,7 +92,7 @@ def test_engine_vs_oracle_synthetic(n, degree, norm, days, eng, oracle_lib):
     g = eng.Engine(pop, prm)
     o = oracle_lib.OracleSim(pop, prm)
     compare_sims(o, g, days, open_fn=_closures(pop, n))
-    assert o.stats()[9] > n // 10          # a real epidemic (ever infected)
+    assert o.stats()[9] > n // 25          # a real epidemic (ever infected), not a fizzle
     g.close()
 
 
