@@ -434,12 +434,8 @@ static int step_end(dys_handle* h, int32_t day)
     if (!h->begun) return fail(h, DYS_ERR_STATE, "dys_step_end without dys_step_begin");
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
-    const unsigned g = (unsigned)(c.n_pad / 256);
-    switch (h->lpr) {
-        case 4: k_contagion<4><<<g, 256, 0, h->stream>>>(c, day); break;
-        case 8: k_contagion<8><<<g, 256, 0, h->stream>>>(c, day); break;
-        default: k_contagion<32><<<g, 256, 0, h->stream>>>(c, day); break;
-    }
+    const unsigned g = (unsigned)(c.n_pad / TILE);
+    k_contagion<<<g, TILE, 0, h->stream>>>(c, day);
     tick(h, 2);
     k_household_stats<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);

@@ -60,7 +60,7 @@ struct DevCtx {
     const int64_t* trig_ptr;             // [n_pad + 1] or null
     const int32_t* trig_hh;
     int32_t* day_flags;                  // [0] any new diagnosis today, [1] events claimed today, [2] closed buildings
-    unsigned long long* part;            // [N_SLOTS][N_STATS] spread partial sums
+    unsigned long long* part;            // [N_STATS][N_SLOTS] spread partial sums
     int64_t* stats;                      // [N_STATS]
     unsigned int* ticket;
     int32_t* sa_hist;                    // [S * 21] or null
@@ -93,7 +93,7 @@ __device__ __forceinline__ void block_accumulate(const DevCtx& c, const int (&id
     }
     __syncthreads();
     if (threadIdx.x < NC && s_acc[threadIdx.x])
-        atomicAdd(&c.part[(size_t)(blockIdx.x & (N_SLOTS - 1)) * N_STATS + idx[threadIdx.x]],
+        atomicAdd(&c.part[(size_t)idx[threadIdx.x] * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))],
                   (unsigned long long)s_acc[threadIdx.x]);
 }
 
@@ -186,89 +186,87 @@ __device__ __noinline__ bool exposed_slow(const int32_t* __restrict__ routine, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_contagion: one lane per owned agent for the per-agent parts, LPR lanes per interaction_prob row for the scan.
-// A warp owns 32 consecutive agents; its susceptible rows are dealt to the 32/LPR sub-warps, each of which streams
-// a row with aligned 128-bit loads of the column words (4 edges per lane per step).  The infector of a newly
-// infected agent is the LARGEST infecting row index (contagious3.py:248) = a max-reduction, done with shuffles.
+// k_contagion: a block owns a tile of 256 consecutive agents = one CONTIGUOUS run of interaction_prob column words.
+// The run is streamed in lock step with aligned 128-bit loads (two chunks = 8 edges per thread in flight), each
+// column's day-start infectious byte is gathered (L1/L2 resident: neighbours live in the same community), and only
+// for an infectious column is the row looked up (binary search over the tile's row offsets staged in shared
+// memory).  The infector of a newly infected agent is the LARGEST infecting row index (contagious3.py:248) = a max,
+// kept per row with shared-memory atomicMax (order independent, no global atomics).
 // ---------------------------------------------------------------------------------------------------------------
-template <int LPR>
-__global__ void __launch_bounds__(256) k_contagion(const DevCtx c, const int day)
+constexpr int TILE = 256;
+
+__global__ void __launch_bounds__(TILE, 4) k_contagion(const DevCtx c, const int day)
 {
-    constexpr int NS = 32 / LPR;
-    __shared__ int s_best[8][32];
+    __shared__ int s_rp[TILE + 1];
+    __shared__ int s_best[TILE];
+    __shared__ uint8_t s_st[TILE];
     __shared__ double s_pdf[64];
     __shared__ int s_nev, s_evbase;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int sub = lane / LPR, sl = lane % LPR;
-    const unsigned submask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-    if (threadIdx.x < 64) s_pdf[threadIdx.x] = c.pdf[threadIdx.x];
-    if (threadIdx.x == 0) s_nev = 0;
-    s_best[wid][lane] = -1;
-    __syncthreads();
-
-    const int64_t a = (int64_t)blockIdx.x * 256 + threadIdx.x;      // n_pad is a multiple of 1024
-    const int64_t wbase = a - lane;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;     // n_pad is a multiple of 1024
+    const int64_t a = tile0 + tid;
+    const int64_t e0 = c.rowptr[tile0];
     const uint8_t st0 = c.status[a];
     const bool sus = (st0 == ST_S) | (st0 == ST_QH);
-    int64_t rp0 = 0, rp1 = 0;
-    if (sus) { rp0 = c.rowptr[a]; rp1 = c.rowptr[a + 1]; }
-    const bool any_closed = c.day_flags[2] != 0;
-    const unsigned rows = __ballot_sync(0xffffffffu, sus && rp1 > rp0);
-    const int nrows = __popc(rows);
-    unsigned int n_scan = 0, n_cand = 0, n_exp = 0, n_hit = 0;
+    s_rp[tid + 1] = (int)(c.rowptr[a + 1] - e0);
+    s_st[tid] = st0;
+    s_best[tid] = -1;
+    if (tid == 0) { s_rp[0] = 0; s_nev = 0; }
+    if (tid < 64) s_pdf[tid] = c.pdf[tid];
+    const int any_sus = __syncthreads_or(sus);
+    const int T = s_rp[TILE];
+    unsigned int n_scan = sus ? (unsigned)(s_rp[tid + 1] - s_rp[tid]) : 0u, n_cand = 0, n_exp = 0, n_hit = 0;
 
-    for (int k0 = 0; k0 < nrows; k0 += NS) {
-        const int k = k0 + sub;
-        const bool act = k < nrows;
-        const int r = act ? (int)__fns(rows, 0, k + 1) : 0;
-        const int64_t g0 = __shfl_sync(0xffffffffu, rp0, r), g1 = __shfl_sync(0xffffffffu, rp1, r);
-        const int st_r = __shfl_sync(0xffffffffu, (int)st0, r);
-        int best = -1;
-        if (act) {
-            const int64_t ul = wbase + r, ug = c.lo + ul;
-            const bool iso_u = (st_r == ST_QH);
-            double risk_u = -1.0;
-            for (int64_t base = (g0 & ~3LL) + 4 * sl; base < g1; base += 4 * LPR) {
-                const uint4 cv = __ldg(reinterpret_cast<const uint4*>(c.colx + base));
-                const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
-                uint8_t ibv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t e = base + j;
-                    ibv[j] = (e >= g0 && e < g1) ? __ldg(c.ib + (cw[j] & COL_MASK)) : (uint8_t)0;
-                    n_scan += (e >= g0 && e < g1);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!(ibv[j] & IB_INF)) continue;
-                    ++n_cand;
-                    const int64_t e = base + j;
-                    const uint32_t ig = cw[j] & COL_MASK, cls = cw[j] >> CLS_SHIFT;
-                    const bool iso_i = ibv[j] & IB_ISO;
-                    bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
-                              ((cls & CLS_OO) && !iso_u && !iso_i);
-                    if (ex && any_closed) ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, (int64_t)ig - c.rt_lo, iso_u, iso_i);
-                    if (!ex) continue;
-                    ++n_exp;
-                    if (risk_u < 0.0) risk_u = __ldg(c.risk + ul);
-                    // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
-                    double p = __dmul_rn(__ldg(c.val + e), risk_u);
-                    p = __dmul_rn(p, s_pdf[ibv[j] & IB_DAYS]);
-                    p = __dmul_rn(p, c.norm_factor);
-                    if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
-                    const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
-                    if (p > u) { ++n_hit; best = max(best, (int)ig); }     // :240, :248
-                }
+    if (any_sus && T > 0) {
+        const bool any_closed = c.day_flags[2] != 0;
+        const int64_t eend = e0 + T;
+        auto candidate = [&](const int64_t e, const uint32_t cw, const uint8_t ibv) {
+            const int rel = (int)(e - e0);
+            int lo = 0, hi = TILE;                         // s_rp[lo] <= rel < s_rp[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_rp[mid] <= rel) lo = mid; else hi = mid;
             }
-        }
+            const uint8_t st_r = s_st[lo];
+            if (st_r != ST_S && st_r != ST_QH) return;
+            ++n_cand;
+            const int64_t ul = tile0 + lo, ug = c.lo + ul;
+            const uint32_t ig = cw & COL_MASK, cls = cw >> CLS_SHIFT;
+            const bool iso_u = (st_r == ST_QH), iso_i = ibv & IB_ISO;
+            bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
+                      ((cls & CLS_OO) && !iso_u && !iso_i);
+            if (ex && any_closed) ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, (int64_t)ig - c.rt_lo, iso_u, iso_i);
+            if (!ex) return;
+            ++n_exp;
+            // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
+            double p = __dmul_rn(__ldg(c.val + e), __ldg(c.risk + ul));
+            p = __dmul_rn(p, s_pdf[ibv & IB_DAYS]);
+            p = __dmul_rn(p, c.norm_factor);
+            if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+            const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
+            if (p > u) { ++n_hit; atomicMax(&s_best[lo], (int)ig); }        // :240, :248
+        };
+        for (int64_t base = (e0 & ~3LL) + 4 * tid; base < eend; base += 8 * TILE) {
+            const int64_t base1 = base + 4 * TILE;
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(c.colx + base));
+            uint4 v1 = make_uint4(0, 0, 0, 0);
+            if (base1 < eend) v1 = __ldg(reinterpret_cast<const uint4*>(c.colx + base1));
+            const uint32_t cw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint8_t ibv[8];
 #pragma unroll
-        for (int o = LPR / 2; o; o >>= 1) best = max(best, __shfl_xor_sync(submask, best, o));
-        if (act && sl == 0) s_best[wid][r] = best;
+            for (int j = 0; j < 8; ++j) {
+                const int64_t e = (j < 4 ? base : base1 - 4) + j;
+                ibv[j] = (e >= e0 && e < eend) ? __ldg(c.ib + (cw[j] & COL_MASK)) : (uint8_t)0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (ibv[j] & IB_INF) candidate((j < 4 ? base : base1 - 4) + j, cw[j], ibv[j]);
+        }
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---- per-agent: apply infection (contagious3.py:241-248), then the ordered rules of :250-259 ----
-    const int best = s_best[wid][lane];
+    const int best = s_best[tid];
     uint8_t s = st0;
     int tinf = 0, tq = 0;
     bool w_tinf = false, w_tq = false, w_tadm = false;
@@ -403,7 +401,7 @@ __global__ void __launch_bounds__(256) k_household_stats(const DevCtx c, const i
                         ST_EVER_INFECTED, ST_CHANGED};
     block_accumulate<9>(c, idx, cnt);
     if (threadIdx.x < HIST_LEN && s_hist[threadIdx.x])
-        atomicAdd(&c.part[(size_t)(blockIdx.x & (N_SLOTS - 1)) * N_STATS + HIST0 + threadIdx.x],
+        atomicAdd(&c.part[(size_t)(HIST0 + threadIdx.x) * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))],
                   (unsigned long long)s_hist[threadIdx.x]);
 
     // last block folds the partial sums (threadfence reduction) and re-zeroes them for the next day
@@ -413,14 +411,16 @@ __global__ void __launch_bounds__(256) k_household_stats(const DevCtx c, const i
     __syncthreads();
     if (s_last) {
         __threadfence();
-        if (threadIdx.x < N_STATS) {
-            unsigned long long t = 0;
-            for (int sl = 0; sl < N_SLOTS; ++sl) {
-                volatile unsigned long long* p = c.part + (size_t)sl * N_STATS + threadIdx.x;
-                t += *p;
-                *p = 0ull;
-            }
-            c.stats[threadIdx.x] = (int64_t)t;
+        // part[counter][slot]: a warp folds one counter with two coalesced loads and a shuffle tree
+        const int lane = threadIdx.x & 31;
+        for (int k = threadIdx.x >> 5; k < N_STATS; k += 8) {
+            unsigned long long* p = c.part + (size_t)k * N_SLOTS;
+            unsigned long long t = __ldcg(p + lane) + __ldcg(p + lane + 32);
+            p[lane] = 0ull;
+            p[lane + 32] = 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) c.stats[k] = (int64_t)t;
         }
         if (threadIdx.x == 0) *c.ticket = 0u;
     }
