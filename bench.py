@@ -11,7 +11,7 @@ A step is one simulated day (one pass of contagious3.py:176-366) over the whole 
 `e2e`    : the same K days through the C ABI the way the reference-facing host loop uses it: every day the open
            flags come from pinned host memory and the day's outputs (stats, per-area histograms, per-building counts,
            infection events) are read back to host memory.
-`roofline`: k_contagion (the dominant kernel) -- algorithmic bytes per launch from the day's own work counters
+`roofline`: k_day (the dominant kernel: hospitalisation, mortality, pairwise infection, transitions) -- algorithmic bytes per launch from the day's own work counters
            (formula in DESIGN.md) over its mean CUDA-event duration, against MEASURED_PEAKS.json.
 `cpu_baseline`: the C oracle (OpenMP) on the same population, a bounded sample of days, rank 0 / N=1 only.
 """
@@ -102,7 +102,7 @@ class ClockSampler:
 
 
 def contagion_bytes(N, st, prev_active_like):
-    """Algorithmic bytes one k_contagion launch must move (DESIGN.md section 'k_contagion: bytes per launch'),
+    """Algorithmic bytes one k_day launch must move (DESIGN.md section 'k_day: bytes per launch'),
     from the day's own counters: each needed datum once, at its stored width."""
     from dysturbd_b200.engine import STAT
     sus0, inf0 = int(st[STAT["sus0"]]), int(st[STAT["inf0"]])
@@ -289,7 +289,7 @@ def run_ours(args):
                 "ms_per_step": s_e2e * 1e3 / K},
         "gpu_launches": int(sum(n_k)) if sum(n_k) else 3 * K,
         "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
-        "roofline": {"bound": "hbm", "kernel": "k_contagion", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_day", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms},

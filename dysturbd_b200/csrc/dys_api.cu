@@ -39,6 +39,11 @@ struct dys_handle {
     cudaEvent_t ring_ev[DYS_STATS_RING];
     int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags, [1] event count
     int32_t* d_bad = nullptr;
+    uint8_t *d_hh_flag[2] = {nullptr, nullptr}, *d_hh_qflag[2] = {nullptr, nullptr};
+    int32_t* d_flags = nullptr;      // [2][DF_LEN] per-parity day flags, then [1] closed-building count
+    int32_t ib_day = -1;             // the day the infectious bytes in c.ib are the day-start snapshot of
+    int day_grid = 0;                // persistent grid of k_day
+    int64_t last_parity = 0;
     double* d_pair_prob = nullptr;
     double *d_u_adm = nullptr, *d_u_death = nullptr, *d_u_pair = nullptr;   // staged injected draws
     // kernel timing
@@ -138,8 +143,8 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     A(dev_alloc(h, (int32_t**)&c.routine, c.rt_n * c.V));
     A(dev_alloc(h, &c.ib, round_up(c.n_glob, 1024) + 1024));
     A(dev_alloc(h, (uint8_t**)&c.open, c.B));
-    A(dev_alloc(h, &c.hh_flag, c.H)); A(dev_alloc(h, &c.hh_qflag, c.H));
-    A(dev_alloc(h, &c.day_flags, 8));
+    for (int k = 0; k < 2; ++k) { A(dev_alloc(h, &h->d_hh_flag[k], c.H + 16)); A(dev_alloc(h, &h->d_hh_qflag[k], c.H + 16)); }
+    A(dev_alloc(h, &h->d_flags, 2 * DF_LEN + 4));
     A(dev_alloc(h, &c.part, (int64_t)N_SLOTS * N_STATS)); A(dev_alloc(h, &c.stats, N_STATS)); A(dev_alloc(h, &c.ticket, 1));
     A(dev_alloc(h, &d_pdf, DYS_PDF_LEN));
     A(dev_alloc(h, &h->d_bad, 1));
@@ -148,6 +153,17 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     if (p.flags & DYS_WANT_EVENTS) { A(dev_alloc(h, &c.ev_agent, c.n_pad)); A(dev_alloc(h, &c.ev_src, c.n_pad)); }
     if (p.flags & DYS_WANT_IO_MAT) A(dev_alloc(h, &c.io_mat, c.S * c.S));
     c.pdf = d_pdf;
+    c.n_closed = h->d_flags + 2 * DF_LEN;
+    if (rc == DYS_OK) {
+        int per_sm = 0, sms = 0;
+        cudaError_t e2 = cudaFuncSetAttribute(k_day, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K_DAY_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_day, TILE, K_DAY_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e2 != cudaSuccess || per_sm < 1) { h->err = std::string("k_day occupancy: ") + cudaGetErrorString(e2); rc = DYS_ERR_CUDA; }
+        const int64_t n_tiles = c.n_pad / TILE;
+        const int64_t want = (int64_t)per_sm * sms;
+        h->day_grid = (int)(n_tiles < want ? n_tiles : want);
+    }
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMallocHost((void**)&h->h_stats, sizeof(int64_t) * N_STATS * DYS_STATS_RING) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -183,6 +199,22 @@ extern "C" int dys_destroy(dys_handle* h)
     for (auto ev : h->tev) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    return DYS_OK;
+}
+
+// state was (re)loaded: the snapshot, the per-parity flags and the partial sums start clean
+static int reset_day_scratch(dys_handle* h)
+{
+    DevCtx& c = h->c;
+    for (int k = 0; k < 2; ++k) {
+        CK(h, cudaMemsetAsync(h->d_hh_flag[k], 0, (size_t)c.H + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->d_hh_qflag[k], 0, (size_t)c.H + 16, h->stream));
+    }
+    CK(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 2 * DF_LEN, h->stream));
+    CK(h, cudaMemsetAsync(c.part, 0, sizeof(unsigned long long) * N_SLOTS * N_STATS, h->stream));
+    CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
+    h->ib_day = -1;
+    h->begun = false;
     return DYS_OK;
 }
 
@@ -252,7 +284,7 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
     if (rc != DYS_OK) return rc;
     h->have_pop = true;
     h->have_graph = false;
-    return DYS_OK;
+    return reset_day_scratch(h);
 }
 
 extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
@@ -270,7 +302,7 @@ extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int3
     if (rc != DYS_OK) return rc;
     for (int i = 0; i < DYS_STATS_RING; ++i) h->ring_day[i] = -1;
     h->last_day = -1;
-    return DYS_OK;
+    return reset_day_scratch(h);
 }
 
 extern "C" int dys_set_run(dys_handle* h, double norm_factor, double compliance, uint64_t seed)
@@ -289,7 +321,7 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
     int64_t* d_rowptr = nullptr;
-    int rc = dev_alloc(h, &d_rowptr, c.n_pad + 1);
+    int rc = dev_alloc(h, &d_rowptr, c.n_pad + 8);
     if (rc != DYS_OK) return rc;
     rc = copy_in(h, d_rowptr, rowptr, sizeof(int64_t) * (size_t)(c.n_loc + 1));
     if (rc != DYS_OK) return rc;
@@ -300,8 +332,8 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
     if (ends[0] != 0 || ends[1] < 0) return fail(h, DYS_ERR_RANGE, "dys_load_graph: rowptr[0] must be 0 and rowptr[N] >= 0");
     const int64_t nnz = ends[1];
     if (nnz > 0 && (!col || !val)) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_graph: null col/val");
-    if (c.n_pad > c.n_loc) {   // padded rows are empty
-        std::vector<int64_t> tail((size_t)(c.n_pad - c.n_loc), nnz);
+    {   // padded rows are empty (the tile copies of k_day read two entries past n_pad)
+        std::vector<int64_t> tail((size_t)(c.n_pad - c.n_loc) + 7, nnz);
         CK(h, cudaMemcpyAsync(d_rowptr + c.n_loc + 1, tail.data(), sizeof(int64_t) * tail.size(), cudaMemcpyHostToDevice, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
     }
@@ -380,8 +412,8 @@ extern "C" int dys_set_open(dys_handle* h, const uint8_t* open_flags)
     DevCtx& c = h->c;
     int rc = copy_in(h, (void*)c.open, open_flags, (size_t)c.B);
     if (rc != DYS_OK) return rc;
-    CK(h, cudaMemsetAsync(c.day_flags + 2, 0, sizeof(int32_t), h->stream));
-    k_count_closed<<<grid_for(c.B, 256), 256, 0, h->stream>>>(c.open, c.B, c.day_flags + 2);
+    CK(h, cudaMemsetAsync((void*)c.n_closed, 0, sizeof(int32_t), h->stream));
+    k_count_closed<<<grid_for(c.B, 256), 256, 0, h->stream>>>(c.open, c.B, (int32_t*)c.n_closed);
     CK(h, cudaGetLastError());
     return DYS_OK;
 }
@@ -422,7 +454,10 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     }
     if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
     tick(h, 0);
-    k_day_start<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    if (h->ib_day != day) {      // first day after a load / set_state, or a day skipped: phase A on its own
+        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+        h->ib_day = day;
+    }
     tick(h, 1);
     CK(h, cudaGetLastError());
     h->begun = true;
@@ -434,8 +469,12 @@ static int step_end(dys_handle* h, int32_t day)
     if (!h->begun) return fail(h, DYS_ERR_STATE, "dys_step_end without dys_step_begin");
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
-    const unsigned g = (unsigned)(c.n_pad / TILE);
-    k_contagion<<<g, TILE, 0, h->stream>>>(c, day);
+    const int par = (int)(h->steps & 1);
+    c.hh_flag = h->d_hh_flag[par]; c.hh_qflag = h->d_hh_qflag[par];
+    c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
+    c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
+    h->last_parity = par;
+    k_day<<<(unsigned)h->day_grid, TILE, K_DAY_SMEM, h->stream>>>(c, day);
     tick(h, 2);
     k_household_stats<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
@@ -445,6 +484,7 @@ static int step_end(dys_handle* h, int32_t day)
     CK(h, cudaEventRecord(h->ring_ev[slot], h->stream));
     h->ring_day[slot] = day;
     h->last_day = day;
+    h->ib_day = day + 1;         // k_household_stats wrote tomorrow's snapshot
     ++h->steps;
     if (!h->tev.empty()) ++h->t_end;
     h->begun = false;
@@ -518,7 +558,7 @@ extern "C" int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_
     if (!h || !n) return DYS_ERR_INVALID_ARG;
     int rc = need_last_day(h, day, h->c.ev_agent, "events");
     if (rc != DYS_OK) return rc;
-    rc = copy_out(h, h->h_small + 1, h->c.day_flags + 1, sizeof(int32_t));
+    rc = copy_out(h, h->h_small + 1, h->d_flags + h->last_parity * DF_LEN + DF_N_EVENTS, sizeof(int32_t));
     if (rc != DYS_OK) return rc;
     const int64_t cnt = h->h_small[1];
     *n = cnt;

@@ -1,12 +1,15 @@
 // Hand-written sm_100a kernels for one day of DySTUrbD's epidemic step (contagious3.py:176-366).
 //
-//   k_day_start        phase A snapshot + B hospitalisation + C mortality          (contagious3.py:181-227)
-//   k_contagion        phase D pairwise infection + E state transitions            (contagious3.py:230-259)
-//   k_household_stats  phase F household quarantine + G integer statistics         (contagious3.py:261-366)
-//   k_edge_classes     load-time: static shared-building class of every interaction_prob non-zero
+//   k_day              phases B hospitalisation, C mortality, D pairwise infection, E transitions (contagious3.py:205-259)
+//                      persistent CTAs; every tile's inputs arrive by TMA bulk copies (cp.async.bulk + mbarrier),
+//                      double buffered, so the only global loads left in the loop are the infectious-byte gathers
+//   k_household_stats  phase F household quarantine + G integer statistics (contagious3.py:261-366); also writes
+//                      TOMORROW's day-start snapshot (phase A, :181-202), so a day is two launches
+//   k_snapshot         phase A on its own (first day after a load / set_state)
+//   k_edge_classes     load time: static shared-building class of every interaction_prob non-zero
 //
-// All three day kernels are HBM-bound integer/byte streaming passes: nothing here is a dense contraction, so
-// there is no tensor-core path.  Layout and roofline reasoning: DESIGN.md.
+// Everything here is HBM-bound integer/byte streaming: nothing is a dense contraction, so there is no tensor-core
+// path.  Layout and roofline reasoning: DESIGN.md.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,9 +20,25 @@ namespace dys {
 
 enum : uint8_t { ST_PAD = 0, ST_S = 2, ST_I = 4, ST_QH = 6, ST_QI = 7, ST_D = 8, ST_H = 10, ST_R = 12, ST_X = 14 };
 
+// status sets as bit masks over the code: membership is one shift
+constexpr uint32_t sbit(int s) { return 1u << s; }
+constexpr uint32_t M_SUS = sbit(ST_S) | sbit(ST_QH);                                  // `uninfected`, contagious3.py:197
+constexpr uint32_t M_INF = sbit(ST_I) | sbit(ST_QI) | sbit(ST_D);                     // `infected`,   contagious3.py:196
+constexpr uint32_t M_ISO = sbit(ST_QH) | sbit(ST_QI) | sbit(ST_D);                    // home slot only, :184
+constexpr uint32_t M_ACTIVE = M_INF | sbit(ST_H);                                     // loop condition, :176
+constexpr uint32_t M_EVER = M_ACTIVE | sbit(ST_R) | sbit(ST_X);                       // status not in {1, 3}
+__device__ __forceinline__ bool in_set(uint32_t mask, uint32_t st) { return (mask >> st) & 1u; }
+
 // day-start "infectious byte" of an agent: bit7 infectious today (status 2 / 3.5 / 4 at day start), bit6 isolated
 // (3.5 / 4: only the home slot is visited), bits0-5 days since infection (index into the pdf table)
 constexpr uint8_t IB_INF = 0x80, IB_ISO = 0x40, IB_DAYS = 0x3F;
+__device__ __forceinline__ uint8_t infectious_byte(uint32_t st, int day, int t_inf)
+{
+    if (!in_set(M_INF, st)) return 0;
+    int n = day - t_inf;
+    n = n < 0 ? 0 : (n > 63 ? 63 : n);
+    return (uint8_t)(IB_INF | (st != ST_I ? IB_ISO : 0) | n);
+}
 
 // interaction_prob column word: bits0-26 column agent (global index), bits28-31 static shared-building class
 constexpr uint32_t COL_MASK = 0x07FFFFFFu;
@@ -32,6 +51,8 @@ enum {
     ST_DAILY_DEATHS, ST_EVER_INFECTED, ST_NEW_DIAG, ST_N_EVENTS, ST_SUS0, ST_INF0, ST_EDGES_SCANNED, ST_CANDIDATES,
     ST_EXPOSED, ST_HITS, ST_CHANGED
 };
+// per-step flag block (double buffered by step parity): [0] a diagnosis happened today, [1] events claimed today
+constexpr int DF_ANY_ND = 0, DF_N_EVENTS = 1, DF_LEN = 4;
 
 struct DevCtx {
     int64_t n_loc, n_pad, n_glob, lo;    // owned agents, padded count (multiple of 1024), global agents, first owned
@@ -49,17 +70,19 @@ struct DevCtx {
     const int32_t *hh, *home, *sa;
     const double *risk, *p_adm, *p_death;
     const int32_t* routine;              // [rt_n * V] building index or -1 (owned agents + halo: neighbours' rows are read)
-    const int64_t* rowptr;               // [n_pad + 1]
+    const int64_t* rowptr;               // [n_pad + 8]
     const uint32_t* colx;                // [nnz (+pad)] column | class << 28
     const double* val;                   // [nnz]
     const double* pdf;                   // [64]
     uint8_t* ib;                         // [n_glob padded] day-start infectious bytes of ALL agents
     const uint8_t* open;                 // [B]
-    uint8_t *hh_flag, *hh_qflag;         // [H] today's diagnosed households / quirk households
+    const int32_t* n_closed;             // [1] closed buildings today
+    uint8_t *hh_flag, *hh_qflag;         // [H] this step's diagnosed households / quirk households
+    uint8_t *hh_flag_next, *hh_qflag_next;   // the other parity: cleared by k_household_stats for the next step
     const uint8_t* hh_always;            // [H] or null
     const int64_t* trig_ptr;             // [n_pad + 1] or null
     const int32_t* trig_hh;
-    int32_t* day_flags;                  // [0] any new diagnosis today, [1] events claimed today, [2] closed buildings
+    int32_t *df, *df_next;               // this / next step's flag block
     unsigned long long* part;            // [N_STATS][N_SLOTS] spread partial sums
     int64_t* stats;                      // [N_STATS]
     unsigned int* ticket;
@@ -77,18 +100,16 @@ __device__ __forceinline__ double draw(const double* inj, int64_t idx, uint64_t 
     return inj ? __ldg(inj + idx) : keyed_uniform(seed, day, stream, a, b);
 }
 
-// block-level: add per-thread counters into the spread partial-sum slots (one atomic per counter per block)
+// block-level: fold per-thread counters into the spread partial-sum slots; warp sums by redux, one global atomic per
+// counter per block, all issued by warp 0 so that a single fence orders them before the block's ticket
 template <int NC>
-__device__ __forceinline__ void block_accumulate(const DevCtx& c, const int (&idx)[NC], unsigned int (&v)[NC])
+__device__ __forceinline__ void block_accumulate(const DevCtx& c, const int (&idx)[NC], const unsigned int (&v)[NC],
+                                                 unsigned int* s_acc /* [>= NC], zeroed, block-synchronised */)
 {
-    __shared__ unsigned int s_acc[NC];
-    if (threadIdx.x < NC) s_acc[threadIdx.x] = 0;
-    __syncthreads();
+    static_assert(NC <= 32, "one warp publishes the counters");
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        unsigned int x = v[k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        const unsigned int x = __reduce_add_sync(0xffffffffu, v[k]);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(&s_acc[k], x);
     }
     __syncthreads();
@@ -104,67 +125,40 @@ __device__ __forceinline__ void grid_clear(T* p, int64_t n)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = T(0);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// k_day_start: 4 agents per thread, vector loads.  Writes the day-start snapshot byte of every owned agent and
-// applies the two per-agent draws.  Also clears the per-day scratch (nothing else touches it during this kernel).
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_day_start(const DevCtx c, const int day)
+// 16 bytes at a time for the byte arrays (sizes are padded to 16 by the host)
+__device__ __forceinline__ void grid_clear16(uint8_t* p, int64_t n_bytes)
 {
-    grid_clear(c.hh_flag, c.H);
-    grid_clear(c.hh_qflag, c.H);
-    grid_clear(c.sa_hist, c.S * HIST_LEN);
-    grid_clear(c.bcount, c.B);
-    grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
-    if (blockIdx.x == 0 && threadIdx.x < 2) c.day_flags[threadIdx.x] = 0;
+    if (!p) return;
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const int64_t n = (n_bytes + 15) >> 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        q[i] = make_uint4(0, 0, 0, 0);
+}
 
-    const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    unsigned int cnt[4] = {0, 0, 0, 0};   // sus0, inf0, admissions, deaths
-    if (a0 < c.n_pad) {
-        uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
-        uint8_t s[4] = {sv.x, sv.y, sv.z, sv.w};
-        bool anyinf = false, anyh = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            anyinf |= (s[j] == ST_I) | (s[j] == ST_QI) | (s[j] == ST_D);
-            anyh |= (s[j] == ST_H);
-        }
-        short4 ti4 = make_short4(0, 0, 0, 0), ta4 = make_short4(0, 0, 0, 0);
-        if (anyinf) ti4 = *reinterpret_cast<const short4*>(c.t_inf + a0);
-        if (anyh) ta4 = *reinterpret_cast<const short4*>(c.t_adm + a0);
-        const int16_t ti[4] = {ti4.x, ti4.y, ti4.z, ti4.w}, ta[4] = {ta4.x, ta4.y, ta4.z, ta4.w};
-        uint8_t ibv[4];
-        bool changed = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t a = a0 + j;
-            const uint8_t st = s[j];
-            ibv[j] = 0;
-            cnt[0] += (st == ST_S) | (st == ST_QH);
-            if ((st == ST_I) | (st == ST_QI) | (st == ST_D)) {
-                ++cnt[1];
-                int n = day - ti[j];
-                n = n < 0 ? 0 : (n > 63 ? 63 : n);
-                ibv[j] = IB_INF | (st != ST_I ? IB_ISO : 0) | (uint8_t)n;
-                if (ti[j] >= c.adm_min && ti[j] <= c.adm_max) {        // contagious3.py:205 (absolute infection day)
-                    const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
-                    if (c.p_adm[a] > u) {                               // :213
-                        s[j] = ST_H; c.t_adm[a] = (int16_t)day; ++cnt[2]; changed = true;
-                    }
-                }
-            } else if (st == ST_H) {
-                if (ta[j] >= c.death_min) {                             // :219
-                    const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
-                    if (c.p_death[a] > u) {                             // :225
-                        s[j] = ST_X; c.t_adm[a] = 0; ++cnt[3]; changed = true;   // :259 resets col 24 for the dead
-                    }
-                }
-            }
-        }
-        *reinterpret_cast<uchar4*>(c.ib + c.lo + a0) = make_uchar4(ibv[0], ibv[1], ibv[2], ibv[3]);
-        if (changed) *reinterpret_cast<uchar4*>(c.status + a0) = make_uchar4(s[0], s[1], s[2], s[3]);
-    }
-    const int idx[4] = {ST_SUS0, ST_INF0, ST_DAILY_HOSP, ST_DAILY_DEATHS};
-    block_accumulate<4>(c, idx, cnt);
+// ---- TMA bulk copy + mbarrier (PTX ISA 8.x; SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // exact exposure test for days with closed buildings (contagious3.py:181-189, :230-231): a shared building must be
@@ -186,169 +180,245 @@ __device__ __noinline__ bool exposed_slow(const int32_t* __restrict__ routine, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_contagion: a block owns a tile of 256 consecutive agents = one CONTIGUOUS run of interaction_prob column words.
-// The run is streamed in lock step with aligned 128-bit loads (two chunks = 8 edges per thread in flight), each
-// column's day-start infectious byte is gathered (L1/L2 resident: neighbours live in the same community), and only
-// for an infectious column is the row looked up (binary search over the tile's row offsets staged in shared
-// memory).  The infector of a newly infected agent is the LARGEST infecting row index (contagious3.py:248) = a max,
-// kept per row with shared-memory atomicMax (order independent, no global atomics).
+// k_day.  A tile = 256 consecutive agents = one contiguous run of interaction_prob column words.  Persistent CTAs
+// walk tiles blockIdx.x, +gridDim.x, ...; while tile t is processed, thread 0 has already issued the bulk copies of
+// tile t+1 (column run, row pointers, status, the three day columns) into the other shared-memory stage.
+// Scan: the column run is read in lock step from shared memory (LDS.128), the day-start infectious byte of each
+// column agent is gathered (L1/L2 resident: neighbours live in the same community), and only for an infectious
+// column is the row looked up (binary search over the tile's row offsets).  The infector of a newly infected agent is
+// the LARGEST infecting row index (contagious3.py:248): shared-memory atomicMax, order independent.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TILE = 256;
+constexpr int CH = 5632;                 // column words staged per tile (22 KB); longer runs spill to direct loads
 
-__global__ void __launch_bounds__(TILE, 4) k_contagion(const DevCtx c, const int day)
+struct __align__(128) TileStage {
+    uint32_t col[CH];
+    int64_t rp[TILE + 2];
+    int16_t t_inf[TILE], t_q[TILE], t_adm[TILE];
+    uint8_t st[TILE];
+};
+constexpr size_t K_DAY_SMEM = 2 * sizeof(TileStage);
+
+__device__ __forceinline__ void issue_tile(const DevCtx& c, int64_t tile, TileStage* stg, uint64_t* bar)
 {
+    const int64_t t0 = tile * TILE;
+    const int64_t e0 = __ldg(c.rowptr + t0), e1 = __ldg(c.rowptr + t0 + TILE);
+    const int64_t al0 = e0 & ~3LL;
+    int64_t words = ((e1 - al0) + 3) & ~3LL;
+    if (words > CH) words = CH;
+    const uint32_t bcol = (uint32_t)words * 4u;
+    constexpr uint32_t b_rp = (TILE + 2) * 8, b_day = TILE * 2, b_st = TILE;
+    mbar_expect_tx(bar, bcol + b_rp + 3 * b_day + b_st);
+    if (bcol) bulk_g2s(stg->col, c.colx + al0, bcol, bar);
+    bulk_g2s(stg->rp, c.rowptr + t0, b_rp, bar);
+    bulk_g2s(stg->t_inf, c.t_inf + t0, b_day, bar);
+    bulk_g2s(stg->t_q, c.t_q + t0, b_day, bar);
+    bulk_g2s(stg->t_adm, c.t_adm + t0, b_day, bar);
+    bulk_g2s(stg->st, c.status + t0, b_st, bar);
+}
+
+__global__ void __launch_bounds__(TILE, 4) k_day(const DevCtx c, const int day)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileStage* stages = reinterpret_cast<TileStage*>(smem_raw);
+    __shared__ uint64_t s_bar[2];
     __shared__ int s_rp[TILE + 1];
     __shared__ int s_best[TILE];
-    __shared__ uint8_t s_st[TILE];
     __shared__ double s_pdf[64];
-    __shared__ int s_nev, s_evbase;
+    __shared__ unsigned int s_acc[16];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t tile0 = (int64_t)blockIdx.x * TILE;     // n_pad is a multiple of 1024
-    const int64_t a = tile0 + tid;
-    const int64_t e0 = c.rowptr[tile0];
-    const uint8_t st0 = c.status[a];
-    const bool sus = (st0 == ST_S) | (st0 == ST_QH);
-    s_rp[tid + 1] = (int)(c.rowptr[a + 1] - e0);
-    s_st[tid] = st0;
-    s_best[tid] = -1;
-    if (tid == 0) { s_rp[0] = 0; s_nev = 0; }
+    const int64_t n_tiles = c.n_pad / TILE;
+
+    // scratch of k_household_stats (nothing else touches it while this kernel runs)
+    grid_clear(c.sa_hist, c.S * HIST_LEN);
+    grid_clear(c.bcount, c.B);
+    grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (tid < 64) s_pdf[tid] = c.pdf[tid];
-    const int any_sus = __syncthreads_or(sus);
-    const int T = s_rp[TILE];
-    unsigned int n_scan = sus ? (unsigned)(s_rp[tid + 1] - s_rp[tid]) : 0u, n_cand = 0, n_exp = 0, n_hit = 0;
-
-    if (any_sus && T > 0) {
-        const bool any_closed = c.day_flags[2] != 0;
-        const int64_t eend = e0 + T;
-        auto candidate = [&](const int64_t e, const uint32_t cw, const uint8_t ibv) {
-            const int rel = (int)(e - e0);
-            int lo = 0, hi = TILE;                         // s_rp[lo] <= rel < s_rp[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_rp[mid] <= rel) lo = mid; else hi = mid;
-            }
-            const uint8_t st_r = s_st[lo];
-            if (st_r != ST_S && st_r != ST_QH) return;
-            ++n_cand;
-            const int64_t ul = tile0 + lo, ug = c.lo + ul;
-            const uint32_t ig = cw & COL_MASK, cls = cw >> CLS_SHIFT;
-            const bool iso_u = (st_r == ST_QH), iso_i = ibv & IB_ISO;
-            bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
-                      ((cls & CLS_OO) && !iso_u && !iso_i);
-            if (ex && any_closed) ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, (int64_t)ig - c.rt_lo, iso_u, iso_i);
-            if (!ex) return;
-            ++n_exp;
-            // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
-            double p = __dmul_rn(__ldg(c.val + e), __ldg(c.risk + ul));
-            p = __dmul_rn(p, s_pdf[ibv & IB_DAYS]);
-            p = __dmul_rn(p, c.norm_factor);
-            if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
-            const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
-            if (p > u) { ++n_hit; atomicMax(&s_best[lo], (int)ig); }        // :240, :248
-        };
-        for (int64_t base = (e0 & ~3LL) + 4 * tid; base < eend; base += 8 * TILE) {
-            const int64_t base1 = base + 4 * TILE;
-            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(c.colx + base));
-            uint4 v1 = make_uint4(0, 0, 0, 0);
-            if (base1 < eend) v1 = __ldg(reinterpret_cast<const uint4*>(c.colx + base1));
-            const uint32_t cw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            uint8_t ibv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int64_t e = (j < 4 ? base : base1 - 4) + j;
-                ibv[j] = (e >= e0 && e < eend) ? __ldg(c.ib + (cw[j] & COL_MASK)) : (uint8_t)0;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (ibv[j] & IB_INF) candidate((j < 4 ? base : base1 - 4) + j, cw[j], ibv[j]);
-        }
-    }
+    if (tid < 16) s_acc[tid] = 0;
     __syncthreads();
+    if (tid == 0 && blockIdx.x < n_tiles) issue_tile(c, blockIdx.x, &stages[0], &s_bar[0]);
+    const bool any_closed = *c.n_closed != 0;
 
-    // ---- per-agent: apply infection (contagious3.py:241-248), then the ordered rules of :250-259 ----
-    const int best = s_best[tid];
-    uint8_t s = st0;
-    int tinf = 0, tq = 0;
-    bool w_tinf = false, w_tq = false, w_tadm = false;
-    if (s == ST_I || s == ST_QI || s == ST_D || s == ST_H) tinf = c.t_inf[a];
-    if (s == ST_QH || s == ST_QI) tq = c.t_q[a];
-    const bool infected_today = best >= 0;
-    if (infected_today) {
-        s = (st0 == ST_S) ? ST_I : ST_QI;
-        tinf = day; w_tinf = true;
-        c.src[a] = best;
-    }
-    const int n_inf = day - tinf, n_q = day - tq;
-    if (s == ST_QH && n_q == c.quarantine) s = ST_S;                                   // :250
-    if (s == ST_QI && n_q == c.quarantine) s = ST_I;                                   // :252
-    if (s == ST_I && n_inf == c.diagnosis) { tq = day; w_tq = true; }                  // :253
-    if ((s == ST_I || s == ST_QI) && n_inf == c.diagnosis) s = ST_D;                   // :254
-    if (s == ST_D && n_inf == c.recover) s = ST_R;                                     // :255
-    if (s == ST_H && n_inf == c.hospital_recover) { s = ST_R; w_tadm = true; }         // :256, :259
-    const bool new_diag = (s == ST_D && n_inf == c.diagnosis);                         // :261
-    if (w_tinf) c.t_inf[a] = (int16_t)tinf;
-    if (w_tq) c.t_q[a] = (int16_t)tq;
-    if (w_tadm) c.t_adm[a] = 0;
-    if (s != st0) c.status[a] = s;
-    if (new_diag) {
-        c.hh_flag[c.hh[a]] = 1;                       // same-value stores: race-free in effect
-        if (c.trig_ptr)
-            for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) c.hh_qflag[c.trig_hh[t]] = 1;
-        c.day_flags[0] = 1;
-    }
+    // sus0, inf0, admissions, deaths, scanned, candidates, exposed, hits, events, new diagnoses, changed
+    unsigned int cnt[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-    // ---- today's infection events, block-compacted (order across blocks is arbitrary; hosts sort) ----
-    if (c.ev_agent || c.io_mat) {
-        const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
-        int woff = 0;
-        if (lane == 0 && evm) woff = atomicAdd(&s_nev, __popc(evm));
-        woff = __shfl_sync(0xffffffffu, woff, 0);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_nev) s_evbase = atomicAdd(&c.day_flags[1], s_nev);
-        __syncthreads();
-        if (infected_today) {
-            if (c.ev_agent) {
-                const int slot = s_evbase + woff + __popc(evm & ((1u << lane) - 1u));
-                c.ev_agent[slot] = (int)(c.lo + a);
-                c.ev_src[slot] = best;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int sidx = it & 1;
+        TileStage* stg = &stages[sidx];
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue_tile(c, tile + gridDim.x, &stages[sidx ^ 1], &s_bar[sidx ^ 1]);
+        mbar_wait(&s_bar[sidx], (uint32_t)((it >> 1) & 1));
+
+        const int64_t tile0 = tile * TILE;
+        const int64_t a = tile0 + tid;
+        const int64_t e0 = stg->rp[0];
+        const uint32_t st0 = stg->st[tid];
+        const bool sus = in_set(M_SUS, st0);
+        s_rp[tid] = (int)(stg->rp[tid] - e0);
+        if (tid == 0) s_rp[TILE] = (int)(stg->rp[TILE] - e0);
+        s_best[tid] = -1;
+        const int any_sus = __syncthreads_or(sus);
+        const int T = s_rp[TILE];
+        cnt[0] += sus;
+        cnt[4] += sus ? (unsigned)(s_rp[tid + 1] - s_rp[tid]) : 0u;
+
+        if (any_sus && T > 0) {
+            const int off = (int)(e0 & 3);            // word w of the staged run is edge (w - off) of the tile
+            auto candidate = [&](const int rel, const uint32_t cw, const uint32_t ibv) {
+                int lo = 0, hi = TILE;                 // s_rp[lo] <= rel < s_rp[hi]
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_rp[mid] <= rel) lo = mid; else hi = mid;
+                }
+                const uint32_t st_r = stg->st[lo];
+                if (!in_set(M_SUS, st_r)) return;
+                ++cnt[5];
+                const int64_t ul = tile0 + lo, ug = c.lo + ul;
+                const uint32_t ig = cw & COL_MASK, cls = cw >> CLS_SHIFT;
+                const bool iso_u = (st_r == ST_QH), iso_i = ibv & IB_ISO;
+                bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
+                          ((cls & CLS_OO) && !iso_u && !iso_i);
+                if (ex && any_closed)
+                    ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, (int64_t)ig - c.rt_lo, iso_u, iso_i);
+                if (!ex) return;
+                ++cnt[6];
+                // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
+                double p = __dmul_rn(__ldg(c.val + e0 + rel), __ldg(c.risk + ul));
+                p = __dmul_rn(p, s_pdf[ibv & IB_DAYS]);
+                p = __dmul_rn(p, c.norm_factor);
+                if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+                const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
+                if (p > u) { ++cnt[7]; atomicMax(&s_best[lo], (int)ig); }        // :240, :248
+            };
+            const int wend = off + T;                  // one past the last valid staged word
+            const int wstaged = wend < CH ? wend : CH;
+            for (int w = 4 * tid; w < wstaged; w += 8 * TILE) {
+                const int w1 = w + 4 * TILE;
+                const uint4 v0 = *reinterpret_cast<const uint4*>(&stg->col[w]);
+                uint4 v1 = make_uint4(0, 0, 0, 0);
+                if (w1 < wstaged) v1 = *reinterpret_cast<const uint4*>(&stg->col[w1]);
+                const uint32_t cw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t ibv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ww = (j < 4 ? w : w1 - 4) + j;
+                    ibv[j] = (ww >= off && ww < wend) ? (uint32_t)__ldg(c.ib + (cw[j] & COL_MASK)) : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (ibv[j] & IB_INF) candidate((j < 4 ? w : w1 - 4) + j - off, cw[j], ibv[j]);
             }
-            if (c.io_mat) {
-                // contagious3.py:356-366: row = area of the infected, column = area of the infector
-                const int sa_u = c.sa[a], sa_i = c.sa[best - c.lo];
-                if (sa_u >= 0 && sa_i >= 0) atomicAdd(&c.io_mat[(size_t)sa_u * c.S + sa_i], 1);
+            // runs longer than the staged window (fat rows): the rest straight from global memory
+            for (int64_t w = CH + tid; w < wend; w += TILE) {
+                const uint32_t cw = __ldg(c.colx + (e0 - off) + w);
+                const uint32_t ibv = __ldg(c.ib + (cw & COL_MASK));
+                if (ibv & IB_INF) candidate((int)(w - off), cw, ibv);
             }
         }
+        __syncthreads();
+
+        // ---- per agent: B, C on the day-start status, the infection found above, then the ordered rules of E ----
+        const int best = s_best[tid];
+        uint32_t s = st0;
+        int tinf = stg->t_inf[tid], tq = stg->t_q[tid];
+        const int tadm = stg->t_adm[tid];
+        bool w_tinf = false, w_tq = false, w_tadm = false;
+        if (in_set(M_INF, st0)) {
+            ++cnt[1];
+            if (tinf >= c.adm_min && tinf <= c.adm_max) {                   // contagious3.py:205 (absolute infection day)
+                const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
+                if (__ldg(c.p_adm + a) > u) { s = ST_H; c.t_adm[a] = (int16_t)day; ++cnt[2]; }   // :213-216
+            }
+        } else if (st0 == ST_H && tadm >= c.death_min) {                   // :219
+            const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
+            if (__ldg(c.p_death + a) > u) { s = ST_X; w_tadm = true; ++cnt[3]; }                 // :225-227, :259
+        }
+        const bool infected_today = best >= 0;
+        if (infected_today) {                                               // :241-248
+            s = (st0 == ST_S) ? ST_I : ST_QI;
+            tinf = day; w_tinf = true;
+            c.src[a] = best;
+        }
+        const int n_inf = day - tinf, n_q = day - tq;
+        if (s == ST_QH && n_q == c.quarantine) s = ST_S;                                   // :250
+        if (s == ST_QI && n_q == c.quarantine) s = ST_I;                                   // :252
+        if (s == ST_I && n_inf == c.diagnosis) { tq = day; w_tq = true; }                  // :253
+        if ((s == ST_I || s == ST_QI) && n_inf == c.diagnosis) s = ST_D;                   // :254
+        if (s == ST_D && n_inf == c.recover) s = ST_R;                                     // :255
+        if (s == ST_H && n_inf == c.hospital_recover) { s = ST_R; w_tadm = true; }         // :256, :259
+        const bool new_diag = (s == ST_D && n_inf == c.diagnosis);                         // :261
+        if (w_tinf) c.t_inf[a] = (int16_t)tinf;
+        if (w_tq) c.t_q[a] = (int16_t)tq;
+        if (w_tadm) c.t_adm[a] = 0;
+        if (s != st0) c.status[a] = (uint8_t)s;
+        if (new_diag) {
+            c.hh_flag[c.hh[a]] = 1;                   // same-value stores: race-free in effect
+            if (c.trig_ptr)
+                for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) c.hh_qflag[c.trig_hh[t]] = 1;
+            c.df[DF_ANY_ND] = 1;
+        }
+        cnt[8] += infected_today;
+        cnt[9] += new_diag;
+        cnt[10] += (s != st0) | w_tq;
+
+        // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
+        if (c.ev_agent) {
+            const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
+            if (evm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (infected_today) {
+                    const int slot = base + __popc(evm & ((1u << lane) - 1u));
+                    c.ev_agent[slot] = (int)(c.lo + a);
+                    c.ev_src[slot] = best;
+                }
+            }
+        }
+        __syncthreads();      // stage sidx and s_rp / s_best are free again
     }
-    unsigned int cnt[7] = {n_scan, n_cand, n_exp, n_hit, (unsigned)infected_today, (unsigned)new_diag,
-                           (unsigned)(s != st0 || w_tq)};
-    const int idx[7] = {ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED, ST_HITS, ST_N_EVENTS, ST_NEW_DIAG, ST_CHANGED};
-    block_accumulate<7>(c, idx, cnt);
+    const int idx[11] = {ST_SUS0, ST_INF0, ST_DAILY_HOSP, ST_DAILY_DEATHS, ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED,
+                         ST_HITS, ST_N_EVENTS, ST_NEW_DIAG, ST_CHANGED};
+    block_accumulate<11>(c, idx, cnt, s_acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_household_stats: phase F on the household flags raised by k_contagion, then the integer statistics of the
-// end-of-day state.  The last block to finish folds the spread partial sums into the stats block.
+// k_household_stats: phase F on the household flags raised by k_day, the integer statistics of the end-of-day
+// state (phase G), and tomorrow's day-start snapshot byte (phase A).  4 agents per thread, vector loads.  The last
+// block to finish folds the spread partial sums into the stats block.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_household_stats(const DevCtx c, const int day)
 {
     __shared__ unsigned int s_hist[HIST_LEN];
+    __shared__ unsigned int s_acc[16];
     __shared__ bool s_last;
     if (threadIdx.x < HIST_LEN) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 16) s_acc[threadIdx.x] = 0;
+    // the other parity's flags: last read by yesterday's launch of this kernel, next written by tomorrow's k_day
+    grid_clear16(c.hh_flag_next, c.H);
+    grid_clear16(c.hh_qflag_next, c.H);
+    if (blockIdx.x == 0 && threadIdx.x < DF_LEN) c.df_next[threadIdx.x] = 0;
     __syncthreads();
-    const bool any_nd = c.day_flags[0] != 0;
+    const bool any_nd = c.df[DF_ANY_ND] != 0;
     const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     // active, daily_inf, recovered, quarantined, daily_quar, hosp, dead, ever, changed
     unsigned int cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (a0 < c.n_pad) {
         const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
-        uint8_t s[4] = {sv.x, sv.y, sv.z, sv.w};
-        bool changed = false, any_ever = false, any_q = false;
-        bool newq[4] = {false, false, false, false};
+        uint32_t s[4] = {sv.x, sv.y, sv.z, sv.w};
+        uint32_t newq = 0;
         if (any_nd) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int64_t a = a0 + j;
                 if (s[j] != ST_S && s[j] != ST_I) continue;
+                const int64_t a = a0 + j;
                 const int h = c.hh[a];
                 bool hit = c.hh_flag[h];                                              // contagious3.py:263
                 if (s[j] == ST_I && !hit)                                             // :267 (whole-row isin)
@@ -358,60 +428,72 @@ __global__ void __launch_bounds__(256) k_household_stats(const DevCtx c, const i
                 if (hit) {
                     s[j] = (s[j] == ST_S) ? ST_QH : ST_QI;                            // :265, :269
                     c.t_q[a] = (int16_t)day;                                          // :266, :270
-                    newq[j] = true; changed = true; ++cnt[8];
+                    newq |= 1u << j;
                 }
             }
-            if (changed) *reinterpret_cast<uchar4*>(c.status + a0) = make_uchar4(s[0], s[1], s[2], s[3]);
+            if (newq) *reinterpret_cast<uchar4*>(c.status + a0) = make_uchar4(s[0], s[1], s[2], s[3]);
+            cnt[8] += __popc(newq);
         }
+        uint32_t m_ever = 0, m_q = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            any_ever |= !(s[j] == ST_S || s[j] == ST_QH || s[j] == ST_PAD);
-            any_q |= (s[j] == ST_QH || s[j] == ST_QI || s[j] == ST_D);
+            m_ever |= in_set(M_EVER, s[j]) << j;
+            m_q |= in_set(M_ISO, s[j]) << j;
         }
         short4 ti4 = make_short4(0, 0, 0, 0), tq4 = make_short4(0, 0, 0, 0);
-        if (any_ever) ti4 = *reinterpret_cast<const short4*>(c.t_inf + a0);
-        if (any_q) tq4 = *reinterpret_cast<const short4*>(c.t_q + a0);
-        const int16_t ti[4] = {ti4.x, ti4.y, ti4.z, ti4.w}, tq[4] = {tq4.x, tq4.y, tq4.z, tq4.w};
+        if (m_ever) ti4 = *reinterpret_cast<const short4*>(c.t_inf + a0);
+        if (m_q & ~newq) tq4 = *reinterpret_cast<const short4*>(c.t_q + a0);
+        const int ti[4] = {ti4.x, ti4.y, ti4.z, ti4.w}, tq[4] = {tq4.x, tq4.y, tq4.z, tq4.w};
+        uint8_t ibn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int64_t a = a0 + j;
-            const uint8_t st = s[j];
-            if (st == ST_PAD) continue;
-            const bool ever = !(st == ST_S || st == ST_QH);
-            const bool quar = (st == ST_QH || st == ST_QI || st == ST_D);
-            cnt[0] += (st == ST_I || st == ST_QI || st == ST_D || st == ST_H);
+            const uint32_t st = s[j];
+            ibn[j] = infectious_byte(st, day + 1, ti[j]);                  // tomorrow's phase A (contagious3.py:192-202)
+            cnt[0] += in_set(M_ACTIVE, st);
             cnt[2] += (st == ST_R);
-            cnt[3] += quar;
-            cnt[4] += quar && (newq[j] || tq[j] == day);
+            cnt[3] += (m_q >> j) & 1u;
+            cnt[4] += ((m_q >> j) & 1u) && (((newq >> j) & 1u) || tq[j] == day);
             cnt[5] += (st == ST_H);
             cnt[6] += (st == ST_X);
-            cnt[7] += ever;
-            if (ever) {
+            if ((m_ever >> j) & 1u) {
+                const int64_t a = a0 + j;
+                ++cnt[7];
                 const int k = day - ti[j];
                 cnt[1] += (k == 0);
                 if (k >= 0 && k < HIST_LEN) {
                     atomicAdd(&s_hist[k], 1u);
                     if (c.sa_hist) { const int sa = c.sa[a]; if (sa >= 0) atomicAdd(&c.sa_hist[(size_t)sa * HIST_LEN + k], 1); }
                 }
+                if (c.bcount && in_set(M_INF, st)) atomicAdd(&c.bcount[c.home[a]], 1);
+                if (c.io_mat && k == 0) {
+                    // contagious3.py:356-366: row = area of today's infected, column = area of the infector
+                    const int srci = c.src[a];
+                    if (srci >= 0) {
+                        const int sa_u = c.sa[a], sa_i = c.sa[srci - c.lo];
+                        if (sa_u >= 0 && sa_i >= 0) atomicAdd(&c.io_mat[(size_t)sa_u * c.S + sa_i], 1);
+                    }
+                }
             }
-            if (c.bcount && (st == ST_I || st == ST_QI || st == ST_D)) atomicAdd(&c.bcount[c.home[a]], 1);
         }
+        *reinterpret_cast<uchar4*>(c.ib + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
     }
     const int idx[9] = {ST_ACTIVE, ST_DAILY_INF, ST_RECOVERED, ST_QUARANTINED, ST_DAILY_QUAR, ST_HOSPITALIZED, ST_DEAD,
                         ST_EVER_INFECTED, ST_CHANGED};
-    block_accumulate<9>(c, idx, cnt);
-    if (threadIdx.x < HIST_LEN && s_hist[threadIdx.x])
-        atomicAdd(&c.part[(size_t)(HIST0 + threadIdx.x) * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))],
-                  (unsigned long long)s_hist[threadIdx.x]);
-
-    // last block folds the partial sums (threadfence reduction) and re-zeroes them for the next day
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(c.ticket, 1u) == gridDim.x - 1);
+    block_accumulate<9>(c, idx, cnt, s_acc);
+    if (threadIdx.x < 32) {
+        // warp 0 published the counters above; it also publishes the histogram, fences, and takes the ticket
+        if (threadIdx.x < HIST_LEN && s_hist[threadIdx.x])
+            atomicAdd(&c.part[(size_t)(HIST0 + threadIdx.x) * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))],
+                      (unsigned long long)s_hist[threadIdx.x]);
+        __threadfence();
+        __syncwarp();
+        if (threadIdx.x == 0) s_last = (atomicAdd(c.ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (s_last) {
         __threadfence();
-        // part[counter][slot]: a warp folds one counter with two coalesced loads and a shuffle tree
+        // part[counter][slot]: a warp folds one counter with two coalesced loads and a redux
         const int lane = threadIdx.x & 31;
         for (int k = threadIdx.x >> 5; k < N_STATS; k += 8) {
             unsigned long long* p = c.part + (size_t)k * N_SLOTS;
@@ -424,6 +506,18 @@ __global__ void __launch_bounds__(256) k_household_stats(const DevCtx c, const i
         }
         if (threadIdx.x == 0) *c.ticket = 0u;
     }
+}
+
+// phase A alone: the day-start snapshot byte of every owned agent (first day after a load / dys_set_state)
+__global__ void __launch_bounds__(256) k_snapshot(const DevCtx c, const int day)
+{
+    const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (a0 >= c.n_pad) return;
+    const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
+    const short4 ti = *reinterpret_cast<const short4*>(c.t_inf + a0);
+    *reinterpret_cast<uchar4*>(c.ib + c.lo + a0) =
+        make_uchar4(infectious_byte(sv.x, day, ti.x), infectious_byte(sv.y, day, ti.y), infectious_byte(sv.z, day, ti.z),
+                    infectious_byte(sv.w, day, ti.w));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
