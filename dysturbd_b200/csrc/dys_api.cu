@@ -157,12 +157,12 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     if (rc == DYS_OK) {
         int per_sm = 0, sms = 0;
         cudaError_t e2 = cudaFuncSetAttribute(k_day, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K_DAY_SMEM);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_day, TILE, K_DAY_SMEM);
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_day, WARPS * 32, K_DAY_SMEM);
         if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (e2 != cudaSuccess || per_sm < 1) { h->err = std::string("k_day occupancy: ") + cudaGetErrorString(e2); rc = DYS_ERR_CUDA; }
-        const int64_t n_tiles = c.n_pad / TILE;
+        const int64_t n_cta = (c.n_pad / SEG + WARPS - 1) / WARPS;      // never more CTAs than there are segments / 8
         const int64_t want = (int64_t)per_sm * sms;
-        h->day_grid = (int)(n_tiles < want ? n_tiles : want);
+        h->day_grid = (int)(n_cta < want ? n_cta : want);
     }
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -474,7 +474,7 @@ static int step_end(dys_handle* h, int32_t day)
     c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
     c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
     h->last_parity = par;
-    k_day<<<(unsigned)h->day_grid, TILE, K_DAY_SMEM, h->stream>>>(c, day);
+    k_day<<<(unsigned)h->day_grid, WARPS * 32, K_DAY_SMEM, h->stream>>>(c, day);
     tick(h, 2);
     k_household_stats<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);

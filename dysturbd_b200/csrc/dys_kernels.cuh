@@ -180,155 +180,221 @@ __device__ __noinline__ bool exposed_slow(const int32_t* __restrict__ routine, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_day.  A tile = 256 consecutive agents = one contiguous run of interaction_prob column words.  Persistent CTAs
-// walk tiles blockIdx.x, +gridDim.x, ...; while tile t is processed, thread 0 has already issued the bulk copies of
-// tile t+1 (column run, row pointers, status, the three day columns) into the other shared-memory stage.
-// Scan: the column run is read in lock step from shared memory (LDS.128), the day-start infectious byte of each
-// column agent is gathered (L1/L2 resident: neighbours live in the same community), and only for an infectious
-// column is the row looked up (binary search over the tile's row offsets).  The infector of a newly infected agent is
-// the LARGEST infecting row index (contagious3.py:248): shared-memory atomicMax, order independent.
+// k_day.  Every WARP is an autonomous worker: it walks segments of 32 consecutive agents (lane = agent); a segment's
+// interaction_prob column words are ONE contiguous run, fetched by a single TMA bulk copy into the warp's own
+// double-buffered shared-memory stage (the copy of segment k+1 is in flight while segment k is processed; per-agent
+// state of the next segment is prefetched into registers).  No block-level barrier exists in the loop.
+//   scan   : the run is read in lock step (LDS.128), the day-start infectious byte of each column agent is gathered
+//            (L1/L2 resident: neighbours live in the same community); infectious columns whose static class can
+//            still expose are compacted into a per-warp candidate list (ballot + prefix popcount)
+//   settle : the list is processed densely, one candidate per lane: row lookup (5-step binary search over the
+//            segment's row offsets), exact exposure, P = ((ip*risk)*pdf)*norm in float64, keyed Philox Bernoulli;
+//            the infector of a newly infected agent is the LARGEST infecting row index (contagious3.py:248) =
+//            shared-memory atomicMax, order independent
+//   agent  : B, C, E on the lane's own agent.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TILE = 256;
-constexpr int CH = 5632;                 // column words staged per tile (22 KB); longer runs spill to direct loads
+constexpr int WARPS = 8;                 // warps per CTA
+constexpr int SEG = 32;                  // agents per segment
+constexpr int CHW = 640;                 // column words staged per segment (2.5 KB); longer runs spill to direct loads
+constexpr int CAP = 256;                 // candidate list entries per warp
+constexpr uint32_t REL_MASK = 0x01FFFFFFu;   // candidate record: edge offset in the segment | iso << 25 | days << 26
 
-struct __align__(128) TileStage {
-    uint32_t col[CH];
-    int64_t rp[TILE + 2];
-    int16_t t_inf[TILE], t_q[TILE], t_adm[TILE];
-    uint8_t st[TILE];
+struct __align__(128) WarpSmem {
+    uint32_t col[2][CHW];
+    uint32_t cand[CAP];
+    int rel[SEG + 4];
+    int best[SEG];
+    uint64_t bar[2];
 };
-constexpr size_t K_DAY_SMEM = 2 * sizeof(TileStage);
+constexpr size_t K_DAY_SMEM = WARPS * sizeof(WarpSmem);
 
-__device__ __forceinline__ void issue_tile(const DevCtx& c, int64_t tile, TileStage* stg, uint64_t* bar)
+struct AgentRegs {                        // one lane's agent, prefetched a segment ahead
+    uint32_t st;
+    int tinf, tq, tadm;
+};
+
+__device__ __forceinline__ void load_agent(const DevCtx& c, int64_t a, AgentRegs& r)
 {
-    const int64_t t0 = tile * TILE;
-    const int64_t e0 = __ldg(c.rowptr + t0), e1 = __ldg(c.rowptr + t0 + TILE);
-    const int64_t al0 = e0 & ~3LL;
-    int64_t words = ((e1 - al0) + 3) & ~3LL;
-    if (words > CH) words = CH;
-    const uint32_t bcol = (uint32_t)words * 4u;
-    constexpr uint32_t b_rp = (TILE + 2) * 8, b_day = TILE * 2, b_st = TILE;
-    mbar_expect_tx(bar, bcol + b_rp + 3 * b_day + b_st);
-    if (bcol) bulk_g2s(stg->col, c.colx + al0, bcol, bar);
-    bulk_g2s(stg->rp, c.rowptr + t0, b_rp, bar);
-    bulk_g2s(stg->t_inf, c.t_inf + t0, b_day, bar);
-    bulk_g2s(stg->t_q, c.t_q + t0, b_day, bar);
-    bulk_g2s(stg->t_adm, c.t_adm + t0, b_day, bar);
-    bulk_g2s(stg->st, c.status + t0, b_st, bar);
+    r.st = c.status[a];
+    r.tinf = c.t_inf[a];
+    r.tq = c.t_q[a];
+    r.tadm = c.t_adm[a];
 }
 
-__global__ void __launch_bounds__(TILE, 4) k_day(const DevCtx c, const int day)
+__device__ __forceinline__ void issue_segment(const DevCtx& c, int64_t e0, int64_t e1, uint32_t* dst, uint64_t* bar)
+{
+    const int64_t al0 = e0 & ~3LL;
+    int64_t words = ((e1 - al0) + 3) & ~3LL;
+    if (words > CHW) words = CHW;
+    if (words > 0) {
+        mbar_expect_tx(bar, (uint32_t)words * 4u);
+        bulk_g2s(dst, c.colx + al0, (uint32_t)words * 4u, bar);
+    } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 4) k_day(const DevCtx c, const int day)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileStage* stages = reinterpret_cast<TileStage*>(smem_raw);
-    __shared__ uint64_t s_bar[2];
-    __shared__ int s_rp[TILE + 1];
-    __shared__ int s_best[TILE];
     __shared__ double s_pdf[64];
     __shared__ unsigned int s_acc[16];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t n_tiles = c.n_pad / TILE;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[wid];
+    const int64_t n_seg = c.n_pad / SEG;
+    const int64_t stride = (int64_t)gridDim.x * WARPS;
 
     // scratch of k_household_stats (nothing else touches it while this kernel runs)
     grid_clear(c.sa_hist, c.S * HIST_LEN);
     grid_clear(c.bcount, c.B);
     grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
 
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+    if (lane == 0) {
+        mbar_init(&ws.bar[0], 1);
+        mbar_init(&ws.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 64) s_pdf[tid] = c.pdf[tid];
     if (tid < 16) s_acc[tid] = 0;
     __syncthreads();
-    if (tid == 0 && blockIdx.x < n_tiles) issue_tile(c, blockIdx.x, &stages[0], &s_bar[0]);
     const bool any_closed = *c.n_closed != 0;
 
     // sus0, inf0, admissions, deaths, scanned, candidates, exposed, hits, events, new diagnoses, changed
     unsigned int cnt[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    int64_t seg = (int64_t)blockIdx.x * WARPS + wid;
+    AgentRegs cur{}, nxt{};
+    int64_t rp_cur = 0, rp_cur_hi = 0, rp_nxt = 0, rp_nxt_hi = 0;
+    if (seg < n_seg) {
+        const int64_t a = seg * SEG + lane;
+        rp_cur = c.rowptr[a]; rp_cur_hi = c.rowptr[a + 1];
+        load_agent(c, a, cur);
+        if (seg + stride < n_seg) {
+            const int64_t an = (seg + stride) * SEG + lane;
+            rp_nxt = c.rowptr[an]; rp_nxt_hi = c.rowptr[an + 1];
+            load_agent(c, an, nxt);
+        }
+        const int64_t e0 = __shfl_sync(0xffffffffu, rp_cur, 0), e1 = __shfl_sync(0xffffffffu, rp_cur_hi, 31);
+        if (lane == 0) issue_segment(c, e0, e1, ws.col[0], &ws.bar[0]);
+    }
+
+    for (int it = 0; seg < n_seg; seg += stride, ++it) {
         const int sidx = it & 1;
-        TileStage* stg = &stages[sidx];
-        if (tid == 0 && tile + gridDim.x < n_tiles) issue_tile(c, tile + gridDim.x, &stages[sidx ^ 1], &s_bar[sidx ^ 1]);
-        mbar_wait(&s_bar[sidx], (uint32_t)((it >> 1) & 1));
-
-        const int64_t tile0 = tile * TILE;
-        const int64_t a = tile0 + tid;
-        const int64_t e0 = stg->rp[0];
-        const uint32_t st0 = stg->st[tid];
-        const bool sus = in_set(M_SUS, st0);
-        s_rp[tid] = (int)(stg->rp[tid] - e0);
-        if (tid == 0) s_rp[TILE] = (int)(stg->rp[TILE] - e0);
-        s_best[tid] = -1;
-        const int any_sus = __syncthreads_or(sus);
-        const int T = s_rp[TILE];
-        cnt[0] += sus;
-        cnt[4] += sus ? (unsigned)(s_rp[tid + 1] - s_rp[tid]) : 0u;
-
-        if (any_sus && T > 0) {
-            const int off = (int)(e0 & 3);            // word w of the staged run is edge (w - off) of the tile
-            auto candidate = [&](const int rel, const uint32_t cw, const uint32_t ibv) {
-                int lo = 0, hi = TILE;                 // s_rp[lo] <= rel < s_rp[hi]
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_rp[mid] <= rel) lo = mid; else hi = mid;
-                }
-                const uint32_t st_r = stg->st[lo];
-                if (!in_set(M_SUS, st_r)) return;
-                ++cnt[5];
-                const int64_t ul = tile0 + lo, ug = c.lo + ul;
-                const uint32_t ig = cw & COL_MASK, cls = cw >> CLS_SHIFT;
-                const bool iso_u = (st_r == ST_QH), iso_i = ibv & IB_ISO;
-                bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
-                          ((cls & CLS_OO) && !iso_u && !iso_i);
-                if (ex && any_closed)
-                    ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, (int64_t)ig - c.rt_lo, iso_u, iso_i);
-                if (!ex) return;
-                ++cnt[6];
-                // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
-                double p = __dmul_rn(__ldg(c.val + e0 + rel), __ldg(c.risk + ul));
-                p = __dmul_rn(p, s_pdf[ibv & IB_DAYS]);
-                p = __dmul_rn(p, c.norm_factor);
-                if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
-                const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
-                if (p > u) { ++cnt[7]; atomicMax(&s_best[lo], (int)ig); }        // :240, :248
-            };
-            const int wend = off + T;                  // one past the last valid staged word
-            const int wstaged = wend < CH ? wend : CH;
-            for (int w = 4 * tid; w < wstaged; w += 8 * TILE) {
-                const int w1 = w + 4 * TILE;
-                const uint4 v0 = *reinterpret_cast<const uint4*>(&stg->col[w]);
-                uint4 v1 = make_uint4(0, 0, 0, 0);
-                if (w1 < wstaged) v1 = *reinterpret_cast<const uint4*>(&stg->col[w1]);
-                const uint32_t cw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                uint32_t ibv[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int ww = (j < 4 ? w : w1 - 4) + j;
-                    ibv[j] = (ww >= off && ww < wend) ? (uint32_t)__ldg(c.ib + (cw[j] & COL_MASK)) : 0u;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (ibv[j] & IB_INF) candidate((j < 4 ? w : w1 - 4) + j - off, cw[j], ibv[j]);
-            }
-            // runs longer than the staged window (fat rows): the rest straight from global memory
-            for (int64_t w = CH + tid; w < wend; w += TILE) {
-                const uint32_t cw = __ldg(c.colx + (e0 - off) + w);
-                const uint32_t ibv = __ldg(c.ib + (cw & COL_MASK));
-                if (ibv & IB_INF) candidate((int)(w - off), cw, ibv);
+        const int64_t seg0 = seg * SEG, a = seg0 + lane;
+        const bool have_next = seg + stride < n_seg;
+        // ---- pipeline: copy of the next segment, registers of the one after ----
+        AgentRegs nn{};
+        int64_t rp_nn = 0, rp_nn_hi = 0;
+        if (have_next) {
+            const int64_t ne0 = __shfl_sync(0xffffffffu, rp_nxt, 0), ne1 = __shfl_sync(0xffffffffu, rp_nxt_hi, 31);
+            if (lane == 0) issue_segment(c, ne0, ne1, ws.col[sidx ^ 1], &ws.bar[sidx ^ 1]);
+            if (seg + 2 * stride < n_seg) {
+                const int64_t ann = (seg + 2 * stride) * SEG + lane;
+                rp_nn = c.rowptr[ann]; rp_nn_hi = c.rowptr[ann + 1];
+                load_agent(c, ann, nn);
             }
         }
-        __syncthreads();
+        const int64_t e0 = __shfl_sync(0xffffffffu, rp_cur, 0);
+        const int T = (int)(__shfl_sync(0xffffffffu, rp_cur_hi, 31) - e0);
+        const int off = (int)(e0 & 3);                 // word w of the staged run is edge (w - off) of the segment
+        const uint32_t st0 = cur.st;
+        const bool sus = in_set(M_SUS, st0);
+        ws.rel[lane] = (int)(rp_cur - e0);
+        if (lane == 0) ws.rel[SEG] = T;
+        ws.best[lane] = -1;
+        cnt[0] += sus;
+        cnt[4] += sus ? (unsigned)(rp_cur_hi - rp_cur) : 0u;
+        const unsigned sus_rows = __ballot_sync(0xffffffffu, sus);     // also orders the shared writes above
+        mbar_wait(&ws.bar[sidx], (uint32_t)((it >> 1) & 1));
 
-        // ---- per agent: B, C on the day-start status, the infection found above, then the ordered rules of E ----
-        const int best = s_best[tid];
+        if (sus_rows && T > 0) {
+            const uint32_t* col = ws.col[sidx];
+            int n = 0;
+            auto settle = [&]() {
+                for (int k0 = 0; k0 < n; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool valid = k < n;
+                    const uint32_t rec = valid ? ws.cand[k] : 0u;
+                    const int rel = (int)(rec & REL_MASK);
+                    int lo = 0, hi = SEG;                      // ws.rel[lo] <= rel < ws.rel[hi]
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const int mid = (lo + hi) >> 1;
+                        if (ws.rel[mid] <= rel) lo = mid; else hi = mid;
+                    }
+                    const uint32_t st_r = __shfl_sync(0xffffffffu, st0, lo);
+                    if (!valid || !in_set(M_SUS, st_r)) continue;
+                    ++cnt[5];
+                    const int w = rel + off;
+                    const uint32_t cw = w < CHW ? col[w] : __ldg(c.colx + e0 + rel);
+                    const uint32_t ig = cw & COL_MASK, cls = cw >> CLS_SHIFT;
+                    const bool iso_u = (st_r == ST_QH), iso_i = (rec >> 25) & 1u;
+                    const int64_t ul = seg0 + lo, ug = c.lo + ul;
+                    bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
+                              ((cls & CLS_OO) && !iso_u && !iso_i);
+                    if (ex && any_closed)
+                        ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, (int64_t)ig - c.rt_lo, iso_u, iso_i);
+                    if (!ex) continue;
+                    ++cnt[6];
+                    // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
+                    double p = __dmul_rn(__ldg(c.val + e0 + rel), __ldg(c.risk + ul));
+                    p = __dmul_rn(p, s_pdf[rec >> 26]);
+                    p = __dmul_rn(p, c.norm_factor);
+                    if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+                    const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
+                    if (p > u) { ++cnt[7]; atomicMax(&ws.best[lo], (int)ig); }        // :240, :248
+                }
+                __syncwarp();
+                n = 0;
+            };
+            auto scan4 = [&](const uint32_t (&cw)[4], const uint32_t (&ibv)[4], const int rel0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // static pre-filter: classes that need a non-isolated column are dead if the column is isolated
+                    const uint32_t cls = cw[j] >> CLS_SHIFT, iso_i = (ibv[j] >> 6) & 1u;
+                    const bool cnd = (ibv[j] & IB_INF) && (cls & (iso_i ? (CLS_HH | CLS_OH) : 0xFu));
+                    const unsigned m = __ballot_sync(0xffffffffu, cnd);
+                    if (cnd) ws.cand[n + __popc(m & lt_mask)] = (uint32_t)(rel0 + j) | ((ibv[j] & 0x7Fu) << 25);
+                    n += __popc(m);
+                }
+            };
+            const int wend = off + T;                          // one past the last valid staged word
+            const int wstaged = wend < CHW ? wend : CHW;
+            for (int w0 = 0; w0 < wstaged; w0 += 4 * 32) {
+                if (n > CAP - 4 * 32) settle();
+                const int w = w0 + 4 * lane;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (w < wstaged) v = *reinterpret_cast<const uint4*>(&col[w]);
+                const uint32_t cw[4] = {v.x, v.y, v.z, v.w};
+                uint32_t ibv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    ibv[j] = (w + j >= off && w + j < wend) ? (uint32_t)__ldg(c.ib + (cw[j] & COL_MASK)) : 0u;
+                scan4(cw, ibv, w - off);
+            }
+            // runs longer than the staged window (fat rows): the rest straight from global memory
+            for (int64_t w0 = CHW; w0 < wend; w0 += 4 * 32) {
+                if (n > CAP - 4 * 32) settle();
+                const int64_t w = w0 + 4 * lane;
+                uint32_t cw[4] = {0, 0, 0, 0}, ibv[4] = {0, 0, 0, 0};
+                if (w < wend) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(c.colx + (e0 - off) + w));
+                    cw[0] = v.x; cw[1] = v.y; cw[2] = v.z; cw[3] = v.w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (w + j < wend) ibv[j] = __ldg(c.ib + (cw[j] & COL_MASK));
+                }
+                scan4(cw, ibv, (int)(w - off));
+            }
+            if (n > 0) settle();
+        }
+        __syncwarp();
+
+        // ---- the lane's own agent: B, C on the day-start status, the infection found above, then the rules of E ----
+        const int best = ws.best[lane];
         uint32_t s = st0;
-        int tinf = stg->t_inf[tid], tq = stg->t_q[tid];
-        const int tadm = stg->t_adm[tid];
+        int tinf = cur.tinf, tq = cur.tq;
         bool w_tinf = false, w_tq = false, w_tadm = false;
         if (in_set(M_INF, st0)) {
             ++cnt[1];
@@ -336,7 +402,7 @@ __global__ void __launch_bounds__(TILE, 4) k_day(const DevCtx c, const int day)
                 const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
                 if (__ldg(c.p_adm + a) > u) { s = ST_H; c.t_adm[a] = (int16_t)day; ++cnt[2]; }   // :213-216
             }
-        } else if (st0 == ST_H && tadm >= c.death_min) {                   // :219
+        } else if (st0 == ST_H && cur.tadm >= c.death_min) {               // :219
             const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
             if (__ldg(c.p_death + a) > u) { s = ST_X; w_tadm = true; ++cnt[3]; }                 // :225-227, :259
         }
@@ -376,16 +442,19 @@ __global__ void __launch_bounds__(TILE, 4) k_day(const DevCtx c, const int day)
                 if (lane == 0) base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (infected_today) {
-                    const int slot = base + __popc(evm & ((1u << lane) - 1u));
+                    const int slot = base + __popc(evm & lt_mask);
                     c.ev_agent[slot] = (int)(c.lo + a);
                     c.ev_src[slot] = best;
                 }
             }
         }
-        __syncthreads();      // stage sidx and s_rp / s_best are free again
+        __syncwarp();      // stage sidx, rel[] and best[] are free again
+        cur = nxt; nxt = nn;
+        rp_cur = rp_nxt; rp_cur_hi = rp_nxt_hi; rp_nxt = rp_nn; rp_nxt_hi = rp_nn_hi;
     }
     const int idx[11] = {ST_SUS0, ST_INF0, ST_DAILY_HOSP, ST_DAILY_DEATHS, ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED,
                          ST_HITS, ST_N_EVENTS, ST_NEW_DIAG, ST_CHANGED};
+    __syncthreads();
     block_accumulate<11>(c, idx, cnt, s_acc);
 }
 
