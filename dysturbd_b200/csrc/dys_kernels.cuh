@@ -197,7 +197,7 @@ constexpr int WARPS = 8;                 // warps per CTA
 constexpr int SEG = 32;                  // agents per segment
 constexpr int CHW = 640;                 // column words staged per segment (2.5 KB); longer runs spill to direct loads
 constexpr int CAP = 256;                 // candidate list entries per warp
-constexpr uint32_t REL_MASK = 0x01FFFFFFu;   // candidate record: edge offset in the segment | iso << 25 | days << 26
+constexpr uint32_t REL_MASK = 0x01FFFFFFu;   // candidate record: edge offset in the segment | days << 25 | iso << 31
 
 struct __align__(128) WarpSmem {
     uint32_t col[2][CHW];
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_day(const DevCtx c, const int
                     const int w = rel + off;
                     const uint32_t cw = w < CHW ? col[w] : __ldg(c.colx + e0 + rel);
                     const uint32_t ig = cw & COL_MASK, cls = cw >> CLS_SHIFT;
-                    const bool iso_u = (st_r == ST_QH), iso_i = (rec >> 25) & 1u;
+                    const bool iso_u = (st_r == ST_QH), iso_i = rec >> 31;
                     const int64_t ul = seg0 + lo, ug = c.lo + ul;
                     bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
                               ((cls & CLS_OO) && !iso_u && !iso_i);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_day(const DevCtx c, const int
                     ++cnt[6];
                     // contagious3.py:232-238, same association, separately rounded (no FMA can form: no adds)
                     double p = __dmul_rn(__ldg(c.val + e0 + rel), __ldg(c.risk + ul));
-                    p = __dmul_rn(p, s_pdf[rec >> 26]);
+                    p = __dmul_rn(p, s_pdf[(rec >> 25) & 0x3Fu]);
                     p = __dmul_rn(p, c.norm_factor);
                     if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
                     const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, ig);
