@@ -289,7 +289,7 @@ def run_ours(args):
                 "ms_per_step": s_e2e * 1e3 / K},
         "gpu_launches": int(sum(n_k)) if sum(n_k) else 3 * K,
         "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
-        "roofline": {"bound": "hbm", "kernel": "k_day", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_push", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms},

@@ -11,7 +11,8 @@
 #include <string>
 #include <vector>
 
-#include "dys_kernels.cuh"
+#include "dys_day.cuh"
+#include "dys_load.cuh"
 
 using namespace dys;
 
@@ -29,7 +30,6 @@ struct dys_handle {
     int64_t dev_bytes = 0;
     std::string err;
     bool have_pop = false, have_graph = false, begun = false;
-    int lpr = 4;
     int64_t nnz = 0;
     int32_t last_day = -1;
     int64_t steps = 0;
@@ -42,7 +42,7 @@ struct dys_handle {
     uint8_t *d_hh_flag[2] = {nullptr, nullptr}, *d_hh_qflag[2] = {nullptr, nullptr};
     int32_t* d_flags = nullptr;      // [2][DF_LEN] per-parity day flags, then [1] closed-building count
     int32_t ib_day = -1;             // the day the infectious bytes in c.ib are the day-start snapshot of
-    int day_grid = 0;                // persistent grid of k_day
+    int push_grid = 0;               // persistent grid of k_push
     int64_t last_parity = 0;
     double* d_pair_prob = nullptr;
     double *d_u_adm = nullptr, *d_u_death = nullptr, *d_u_pair = nullptr;   // staged injected draws
@@ -156,13 +156,12 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     c.n_closed = h->d_flags + 2 * DF_LEN;
     if (rc == DYS_OK) {
         int per_sm = 0, sms = 0;
-        cudaError_t e2 = cudaFuncSetAttribute(k_day, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K_DAY_SMEM);
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_day, WARPS * 32, K_DAY_SMEM);
+        cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, PUSH_WARPS * 32, 0);
         if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        if (e2 != cudaSuccess || per_sm < 1) { h->err = std::string("k_day occupancy: ") + cudaGetErrorString(e2); rc = DYS_ERR_CUDA; }
-        const int64_t n_cta = (c.n_pad / SEG + WARPS - 1) / WARPS;      // never more CTAs than there are segments / 8
-        const int64_t want = (int64_t)per_sm * sms;
-        h->day_grid = (int)(n_cta < want ? n_cta : want);
+        if (e2 != cudaSuccess || per_sm < 1) { h->err = std::string("k_push occupancy: ") + cudaGetErrorString(e2); rc = DYS_ERR_CUDA; }
+        const int64_t n_cta = ((c.rt_n + 31) / 32 + PUSH_WARPS - 1) / PUSH_WARPS;    // never more warps than groups
+        const int64_t want = (int64_t)per_sm * sms;                                     // persistent: a multiple of the SM count
+        h->push_grid = (int)(n_cta < want ? n_cta : want);
     }
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -227,7 +226,7 @@ static int check_bad(dys_handle* h, const char* what)
         CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int32_t), h->stream));
         return fail(h, DYS_ERR_RANGE, "%s: invalid input (flags 0x%x: 1 status code, 2 hh/home/sa index, 4 t_adm != 0 for a "
                     "never-admitted status, 8 src index, 16 routine building index, 32 rowptr not monotone, 64 column index, "
-                    "128 columns not strictly ascending, 256 day out of int16 range)", what, bad);
+                    "128 columns not strictly ascending, 256 day out of int16 range, 512 susceptible agent with an infector)", what, bad);
     }
     return DYS_OK;
 }
@@ -320,47 +319,54 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
     if (!rowptr) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_graph: null rowptr");
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
+    // staging copies of the caller's CSR (row = susceptible side); freed once the transposed form exists
     int64_t* d_rowptr = nullptr;
-    int rc = dev_alloc(h, &d_rowptr, c.n_pad + 8);
-    if (rc != DYS_OK) return rc;
-    rc = copy_in(h, d_rowptr, rowptr, sizeof(int64_t) * (size_t)(c.n_loc + 1));
-    if (rc != DYS_OK) return rc;
-    int64_t ends[2] = {0, 0};
-    CK(h, cudaMemcpyAsync(&ends[0], d_rowptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(&ends[1], d_rowptr + c.n_loc, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    if (ends[0] != 0 || ends[1] < 0) return fail(h, DYS_ERR_RANGE, "dys_load_graph: rowptr[0] must be 0 and rowptr[N] >= 0");
-    const int64_t nnz = ends[1];
-    if (nnz > 0 && (!col || !val)) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_graph: null col/val");
-    {   // padded rows are empty (the tile copies of k_day read two entries past n_pad)
-        std::vector<int64_t> tail((size_t)(c.n_pad - c.n_loc) + 7, nnz);
-        CK(h, cudaMemcpyAsync(d_rowptr + c.n_loc + 1, tail.data(), sizeof(int64_t) * tail.size(), cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-    }
-    uint32_t* d_colx = nullptr;
+    int32_t *d_col = nullptr, *d_cnt = nullptr;
     double* d_val = nullptr;
-    int32_t* d_col = nullptr;
-    rc = dev_alloc(h, &d_colx, nnz + 16);
-    if (rc == DYS_OK) rc = dev_alloc(h, &d_val, nnz + 2, false);
-    if (rc != DYS_OK) return rc;
-    CK(h, cudaMalloc((void**)&d_col, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    unsigned long long* d_cursor = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rowptr); cudaFree(d_col); cudaFree(d_val); cudaFree(d_cnt); cudaFree(d_cursor); };
+    CK(h, cudaMalloc((void**)&d_rowptr, sizeof(int64_t) * (size_t)(c.n_loc + 1)));
+    int rc = copy_in(h, d_rowptr, rowptr, sizeof(int64_t) * (size_t)(c.n_loc + 1));
+    int64_t ends[2] = {0, 0};
+    if (rc == DYS_OK && (cudaMemcpyAsync(&ends[0], d_rowptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                         cudaMemcpyAsync(&ends[1], d_rowptr + c.n_loc, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                         cudaStreamSynchronize(h->stream) != cudaSuccess))
+        rc = fail(h, DYS_ERR_CUDA, "dys_load_graph: reading rowptr failed");
+    if (rc == DYS_OK && (ends[0] != 0 || ends[1] < 0)) rc = fail(h, DYS_ERR_RANGE, "dys_load_graph: rowptr[0] must be 0 and rowptr[N] >= 0");
+    const int64_t nnz = ends[1];
+    if (rc == DYS_OK && nnz > 0 && (!col || !val)) rc = fail(h, DYS_ERR_INVALID_ARG, "dys_load_graph: null col/val");
+    if (rc != DYS_OK) { cleanup(); return rc; }
+    const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+    cudaError_t e = cudaMalloc((void**)&d_col, sizeof(int32_t) * nz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_val, sizeof(double) * nz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_cnt, sizeof(int32_t) * (size_t)c.rt_n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_cursor, sizeof(unsigned long long) * (size_t)c.rt_n);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * (size_t)c.rt_n, h->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(h, DYS_ERR_NOMEM, "dys_load_graph: %s", cudaGetErrorString(e)); }
     rc = copy_in(h, d_col, col, sizeof(int32_t) * (size_t)nnz);
     if (rc == DYS_OK) rc = copy_in(h, d_val, val, sizeof(double) * (size_t)nnz);
+    int64_t* d_tptr = nullptr;
+    uint32_t* d_tcolx = nullptr;
+    double* d_tval = nullptr;
+    if (rc == DYS_OK) rc = dev_alloc(h, &d_tptr, c.rt_n + 1);
+    if (rc == DYS_OK) rc = dev_alloc(h, &d_tcolx, nnz + 16);
+    if (rc == DYS_OK) rc = dev_alloc(h, &d_tval, nnz + 2, false);
     if (rc == DYS_OK) {
-        c.rowptr = d_rowptr; c.colx = d_colx; c.val = d_val;
-        k_validate_graph<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(d_rowptr, d_col, c.n_loc, c.rt_lo, c.rt_lo + c.rt_n, h->d_bad);
+        k_validate_graph_count<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(d_rowptr, d_col, c.n_loc, c.rt_lo, c.rt_lo + c.rt_n,
+                                                                             d_cnt, h->d_bad);
         rc = check_bad(h, "dys_load_graph");
     }
     if (rc == DYS_OK) {
-        k_edge_classes<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_col, d_colx);
+        // transpose: column counts -> offsets -> scatter with the static shared-building class of each pair
+        k_scan_counts<<<1, 1024, 0, h->stream>>>(d_cnt, c.rt_n, d_tptr, d_cursor);
+        k_fill_transpose<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_rowptr, d_col, d_val, d_cursor, d_tcolx, d_tval);
         if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
-            rc = fail(h, DYS_ERR_CUDA, "k_edge_classes failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = fail(h, DYS_ERR_CUDA, "building the transposed network failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    cudaFree(d_col);
+    cleanup();
     if (rc != DYS_OK) return rc;
+    c.tptr = d_tptr; c.tcolx = d_tcolx; c.tval = d_tval;
     h->nnz = nnz;
-    const double mean_deg = (double)nnz / (double)c.n_loc;
-    h->lpr = mean_deg <= 24.0 ? 4 : (mean_deg <= 96.0 ? 8 : 32);
     h->have_graph = true;
     return DYS_OK;
 }
@@ -453,9 +459,16 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
         }
     }
     if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
+    const int par = (int)(h->steps & 1);
     tick(h, 0);
-    if (h->ib_day != day) {      // first day after a load / set_state, or a day skipped: phase A on its own
-        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    if (h->ib_day != day || (inj && inj->u_adm)) {
+        // phase A on its own: first day after a load / set_state, a skipped day, or injected admission draws
+        // (tomorrow's diagnoses cannot be predicted from an array the caller has not handed over yet)
+        CK(h, cudaMemsetAsync(h->d_hh_flag[par], 0, (size_t)c.H + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->d_hh_qflag[par], 0, (size_t)c.H + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->d_flags + par * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
+        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day, h->d_hh_flag[par], h->d_hh_qflag[par],
+                                                                      h->d_flags + par * DF_LEN);
         h->ib_day = day;
     }
     tick(h, 1);
@@ -474,9 +487,9 @@ static int step_end(dys_handle* h, int32_t day)
     c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
     c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
     h->last_parity = par;
-    k_day<<<(unsigned)h->day_grid, WARPS * 32, K_DAY_SMEM, h->stream>>>(c, day);
+    k_push<<<(unsigned)h->push_grid, PUSH_WARPS * 32, 0, h->stream>>>(c, day);
     tick(h, 2);
-    k_household_stats<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
     CK(h, cudaGetLastError());
     const int slot = (int)(h->steps % DYS_STATS_RING);
@@ -484,7 +497,7 @@ static int step_end(dys_handle* h, int32_t day)
     CK(h, cudaEventRecord(h->ring_ev[slot], h->stream));
     h->ring_day[slot] = day;
     h->last_day = day;
-    h->ib_day = day + 1;         // k_household_stats wrote tomorrow's snapshot
+    h->ib_day = day + 1;         // k_agent wrote tomorrow's snapshot and household flags
     ++h->steps;
     if (!h->tev.empty()) ++h->t_end;
     h->begun = false;

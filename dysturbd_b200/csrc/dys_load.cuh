@@ -1,0 +1,152 @@
+// Load-time kernels: input validation, the int32 <-> int16 day columns, and the transposed, class-annotated
+// interaction_prob that k_push walks.  None of this runs per day.
+#pragma once
+#include "dys_common.cuh"
+
+namespace dys {
+
+// int32 -> int16 day columns with range check (days are < 32768)
+__global__ void k_narrow_days(const int32_t* __restrict__ in, int16_t* __restrict__ out, int64_t n, int32_t* bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = in[i];
+    if (v < -32768 || v > 32767) atomicOr(bad, 256);
+    out[i] = (int16_t)v;
+}
+
+__global__ void k_widen_days(const int16_t* __restrict__ in, int32_t* __restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// every index inside its range; t_adm == 0 wherever status is in {1, 2, 6, 7} (contagious3.py:259 keeps that invariant);
+// a susceptible agent has no infector yet (agents[:,21] == 0 until :248 writes it) -- k_push uses src[] as its mailbox
+__global__ void k_validate_population(const DevCtx c, int32_t* bad)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= c.n_loc) return;
+    const uint8_t s = c.status[a];
+    const bool known = s == ST_S || s == ST_I || s == ST_QH || s == ST_QI || s == ST_D || s == ST_H || s == ST_R || s == ST_X;
+    if (!known) atomicOr(bad, 1);
+    if (c.hh[a] < 0 || c.hh[a] >= c.H || c.home[a] < 0 || c.home[a] >= c.B || c.sa[a] < -1 || c.sa[a] >= c.S) atomicOr(bad, 2);
+    if ((s == ST_S || s == ST_I || s == ST_R || s == ST_X) && c.t_adm[a] != 0) atomicOr(bad, 4);
+    if (c.src[a] < -1 || c.src[a] >= c.n_glob) atomicOr(bad, 8);
+    if ((s == ST_S || s == ST_QH) && c.src[a] != -1) atomicOr(bad, 512);
+}
+
+__global__ void k_validate_routine(const int32_t* __restrict__ routine, int64_t n, int64_t B, int32_t* bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (routine[i] < -1 || routine[i] >= B)) atomicOr(bad, 16);
+}
+
+// rows monotone, columns inside the halo and strictly ascending; counts the non-zeros of every halo column
+__global__ void k_validate_graph_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_loc,
+                                       int64_t col_lo, int64_t col_hi, int32_t* __restrict__ col_count, int32_t* bad)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_loc) return;
+    if (rowptr[u + 1] < rowptr[u]) { atomicOr(bad, 32); return; }
+    int32_t prev = -1;
+    for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) {
+        const int32_t i = col[e];
+        if (i < col_lo || i >= col_hi) { atomicOr(bad, 64); continue; }
+        if (i <= prev) atomicOr(bad, 128);
+        prev = i;
+        atomicAdd(&col_count[i - col_lo], 1);
+    }
+}
+
+// exclusive prefix sum int32 counts -> int64 offsets (and a second copy used as the fill cursors); one block walks
+// the array in 1024-element chunks -- load time only
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int64_t n, int64_t* __restrict__ ptr,
+                                                      unsigned long long* __restrict__ cursor)
+{
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < n ? cnt[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            long long w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        const long long excl = carry + (wid ? s_warp[wid - 1] : 0) + incl - v;
+        if (i < n) { ptr[i] = excl; cursor[i] = (unsigned long long)excl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ptr[n] = s_carry;
+}
+
+// Routines are static (computed once per simulation, contagious3.py:139-170), so WHICH slots two agents share is static
+// too.  Four bits per interaction_prob non-zero (u = row = susceptible side, i = column = infectious side):
+//   HH  home(u) == home(i)                  HO  home(u) is a non-home stop of i
+//   OH  home(i) is a non-home stop of u     OO  they share a non-home stop
+// With every building open, exposure(u,i) = HH | HO&!iso(i) | OH&!iso(u) | OO&!iso(u)&!iso(i) exactly; with closed
+// buildings it is a superset that exposed_slow() re-checks.  One warp per row; each non-zero is appended to its
+// column's transposed list (the order inside a list is irrelevant: k_push reduces with max).
+__global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const int64_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                        unsigned long long* __restrict__ cursor, uint32_t* __restrict__ tcolx,
+                                                        double* __restrict__ tval)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t u = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (u >= c.n_loc) return;
+    const int V = c.V;
+    int32_t ru[16];
+    for (int s = 0; s < 16; ++s) ru[s] = s < V ? c.routine[(c.lo + u - c.rt_lo) * V + s] : -1;
+    for (int64_t e = rowptr[u] + lane; e < rowptr[u + 1]; e += 32) {
+        const int32_t i = col[e];
+        const int32_t* ri = c.routine + ((int64_t)i - c.rt_lo) * V;
+        uint32_t cls = 0;
+        for (int t = 0; t < V; ++t) {
+            const int32_t bi = ri[t];
+            if (bi < 0) continue;
+            for (int s = 0; s < V; ++s) {
+                if (ru[s] != bi) continue;
+                cls |= (s == 0) ? (t == 0 ? CLS_HH : CLS_HO) : (t == 0 ? CLS_OH : CLS_OO);
+            }
+        }
+        const unsigned long long pos = atomicAdd(&cursor[i - c.rt_lo], 1ull);
+        tcolx[pos] = (uint32_t)u | (cls << CLS_SHIFT);
+        tval[pos] = val[e];
+    }
+}
+
+__global__ void k_keyed_uniform(uint64_t seed, uint32_t day, uint32_t stream, const uint32_t* __restrict__ a,
+                                const uint32_t* __restrict__ b, int64_t n, double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = keyed_uniform(seed, day, stream, a[i], b[i]);
+}
+
+__global__ void k_count_closed(const uint8_t* __restrict__ open, int64_t B, int32_t* out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B && !open[i]) atomicAdd(out, 1);
+}
+
+}  // namespace dys

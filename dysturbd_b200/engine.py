@@ -18,7 +18,7 @@ N_STATS = 64
 HIST0 = 32
 HIST_LEN = 21
 N_KERNELS = 3
-KERNEL_NAMES = ("k_snapshot", "k_day", "k_household_stats")
+KERNEL_NAMES = ("k_snapshot", "k_push", "k_agent")
 STAT = {name: i for i, name in enumerate(
     ["active", "daily_inf", "recovered", "quarantined", "daily_quar", "hosp", "daily_hosp", "dead", "daily_deaths",
      "ever_infected", "new_diag", "n_events", "sus0", "inf0", "edges_scanned", "candidates", "exposed", "hits",

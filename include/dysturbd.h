@@ -160,7 +160,7 @@ int dys_get_pair_prob(dys_handle* h, double* out);
 
 int dys_sync(dys_handle* h);
 /* mean milliseconds per launch and launch counts since the last call, per kernel
- * (0 k_snapshot -- only launched on the first day after a load, 1 k_day, 2 k_household_stats); needs DYS_TIME_KERNELS */
+ * (0 k_snapshot -- only launched on the first day after a load, 1 k_push, 2 k_agent); needs DYS_TIME_KERNELS */
 #define DYS_N_KERNELS 3
 int dys_get_kernel_times(dys_handle* h, double* ms_total /* [DYS_N_KERNELS] */, int64_t* launches /* [DYS_N_KERNELS] */);
 /* raw device pointers for zero-copy interop (torch / DLPack / NCCL): which = one of dys_buffer */
