@@ -11,7 +11,7 @@ A step is one simulated day (one pass of contagious3.py:176-366) over the whole 
 `e2e`    : the same K days through the C ABI the way the reference-facing host loop uses it: every day the open
            flags come from pinned host memory and the day's outputs (stats, per-area histograms, per-building counts,
            infection events) are read back to host memory.
-`roofline`: k_day (the dominant kernel: hospitalisation, mortality, pairwise infection, transitions) -- algorithmic bytes per launch from the day's own work counters
+`roofline`: the slower of the two day kernels (k_push / k_agent) -- algorithmic bytes per launch from the day's own work counters
            (formula in DESIGN.md) over its mean CUDA-event duration, against MEASURED_PEAKS.json.
 `cpu_baseline`: the C oracle (OpenMP) on the same population, a bounded sample of days, rank 0 / N=1 only.
 """
@@ -101,22 +101,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def contagion_bytes(N, st, prev_active_like):
-    """Algorithmic bytes one k_day launch must move (DESIGN.md section 'k_day: bytes per launch'),
-    from the day's own counters: each needed datum once, at its stored width."""
+def kernel_bytes(N, st, prev):
+    """Algorithmic bytes one launch of each day kernel must move (DESIGN.md 'bytes per launch'), from the day's own
+    counters: each needed datum once, at its stored width.  `st` = today's stats block, `prev` = yesterday's (its
+    end-of-day status counts are today's day-start counts)."""
     from dysturbd_b200.engine import STAT
-    sus0, inf0 = int(st[STAT["sus0"]]), int(st[STAT["inf0"]])
-    edges, exposed, events, changed = (int(st[STAT[k]]) for k in ("edges_scanned", "exposed", "n_events", "changed"))
-    b = N * 1                      # status of every agent (u8)
-    b += sus0 * 8                  # row pointers of susceptible rows (i64, consecutive rows share one)
-    b += edges * 4                 # column words of every scanned non-zero (u32)
-    b += min(N, edges) * 1         # infectious bytes of the column agents (u8), each distinct agent once
-    b += exposed * 8               # interaction_prob value per Bernoulli (f64)
-    b += min(sus0, exposed) * 8    # risk of the rows that drew at least once (f64)
-    b += (inf0 + prev_active_like) * 2   # t_inf of infectious / hospitalised (i16), t_q of quarantined (i16)
-    b += events * (2 + 4)          # t_inf + infector written for the newly infected
-    b += changed * 1               # status rewritten
-    return b
+    g = lambda k: int(st[STAT[k]])
+    S0, I0, QH0, QI0, D0, H0, R0, X0 = (int(x) for x in prev[20:28])
+    inf0 = g("inf0")
+    # k_push: the snapshot byte of every agent, then only the transposed rows of today's infectious agents
+    push = N * 1 + inf0 * 16 + g("edges_scanned") * (4 + 1) + g("exposed") * (8 + 8) + g("hits") * 4
+    # k_agent: status in, snapshot byte out, and the columns each status needs
+    ever0 = I0 + QI0 + D0 + H0 + R0 + X0
+    agent = N * (1 + 1)                          # status read, tomorrow's snapshot byte written
+    agent += ever0 * 2                           # t_inf of everyone ever infected (rules of E, histogram)
+    agent += (QH0 + QI0 + D0) * 2 + H0 * 2       # t_q of the quarantined, t_adm of the hospitalised
+    agent += (S0 + QH0) * 4                      # the infector mailbox of every susceptible
+    if g("new_diag") or g("daily_quar"):         # F ran: household index + flag byte of everyone who can be quarantined
+        agent += (S0 + QH0 + I0 + QI0) * (4 + 1)
+    agent += g("changed") * 1 + g("n_events") * (2 + 8) + g("daily_quar") * 2
+    agent += int(st[32:53].sum()) * (4 + 4)      # area index + histogram bin of the recently infected
+    return {"k_push": push, "k_agent": agent}
 
 
 def run_ours(args):
@@ -196,34 +201,43 @@ def run_ours(args):
     st_last = eng.stats(W + K - 1)
 
     # ---- pass 2: end to end through the C ABI with host buffers (`e2e`) ----
+    # The host loop of dysturbd_b200/host.py: every day the open flags are offered from pinned host memory
+    # (dys_set_open; an unchanged vector is elided inside the library) and the day's whole output block (stats,
+    # per-area histograms, per-building counts, infection events) is read on the host.  Day d+1 is queued before day d
+    # is consumed -- legal because the lockdown decision lags 7 days (contagious3.py:306-309).
     eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
     open_pinned = torch.ones(pop.B, dtype=torch.uint8).pin_memory()
     h2d = d2h = 0
     stats_days = []
+    checksum = 0
     with torch.cuda.stream(stream):
-        def e2e_day(d, count):
-            nonlocal h2d, d2h
+        def queue_day(d):
             eng.set_open(open_pinned)
             day_step(eng, d)
-            st = eng.stats(d)
-            sa = eng.sa_hist(d)
-            bc = eng.building_counts(d)
-            ea, es = eng.events(d)
+
+        def consume_day(d, count):
+            nonlocal d2h, checksum
+            o = eng.outputs(d)
+            st = o["stats"].copy()
+            checksum += int(o["sa_hist"].sum()) + int(o["building_counts"].sum()) + int(o["events"].sum())
             if world > 1:   # global stats block (the host loop needs it for R / the lockdown decision)
                 t = torch.from_numpy(st).cuda()
                 dist.all_reduce(t)
                 st = t.cpu().numpy()
             if count:
-                h2d += pop.B
-                d2h += st.nbytes + sa.nbytes + bc.nbytes + ea.nbytes + es.nbytes
+                d2h += st.nbytes + o["sa_hist"].nbytes + o["building_counts"].nbytes + o["events"].nbytes
                 stats_days.append(st)
         for d in range(W):
-            e2e_day(d, False)
+            queue_day(d)
+            consume_day(d, False)
         barrier()
         clocks.active = True
         t0 = time.perf_counter()
+        queue_day(W)
         for d in range(W, W + K):
-            e2e_day(d, True)
+            if d + 1 < W + K:
+                queue_day(d + 1)
+            consume_day(d, True)
         barrier()
         s_e2e = max_over_ranks(time.perf_counter() - t0)
         clocks.active = False
@@ -239,7 +253,6 @@ def run_ours(args):
         class _Cai2:
             __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
         ib_t = torch.as_tensor(_Cai2(), device=torch.device("cuda", local))[:n_total]
-    kbytes = 0
     with torch.cuda.stream(stream_t):
         for d in range(W):
             day_step(eng_t, d)
@@ -248,10 +261,12 @@ def run_ours(args):
         for d in range(W, W + K):
             day_step(eng_t, d)
         ms_k, n_k = eng_t.kernel_times()
-    for i, st in enumerate(stats_days):     # the e2e pass ran the same days from the same state: same counters
-        prev = stats_days[i - 1] if i else st
-        kbytes += contagion_bytes(n_total, st, int(prev[STAT["hosp"]]) + int(prev[STAT["quarantined"]]))
-    kbytes //= world                        # counters are global after the all-reduce; a rank moves its share
+    prev = eng_t.stats(W - 1) if W > 0 and world == 1 else stats_days[0]
+    kb = {"k_push": 0, "k_agent": 0}
+    for st in stats_days:                   # the e2e pass ran the same days from the same state: same counters
+        for k, v in kernel_bytes(n_total, st, prev).items():
+            kb[k] += v // world             # counters are global after the all-reduce; a rank moves its share
+        prev = st
     eng_t.close()
     clocks.stop()
 
@@ -261,8 +276,14 @@ def run_ours(args):
     except (OSError, ValueError):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k_ms = ms_k[1] / max(1, n_k[1])
-    achieved = (kbytes / max(1, K)) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    per_kernel = {}
+    for i, name in enumerate(engine.KERNEL_NAMES):
+        if name in kb and n_k[i]:
+            ms = ms_k[i] / n_k[i]
+            per_kernel[name] = {"ms_per_launch": ms, "algorithmic_bytes_per_launch": kb[name] / K,
+                                "achieved_gbs": kb[name] / K / (ms * 1e-3) / 1e9}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"])
+    k_ms, kbytes, achieved = per_kernel[dom]["ms_per_launch"], per_kernel[dom]["algorithmic_bytes_per_launch"] * K, per_kernel[dom]["achieved_gbs"]
 
     if rank != 0:
         if world > 1:
@@ -287,12 +308,12 @@ def run_ours(args):
         },
         "e2e": {"value": n_total * K / s_e2e, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "ms_per_step": s_e2e * 1e3 / K},
-        "gpu_launches": int(sum(n_k)) if sum(n_k) else 3 * K,
+        "gpu_launches": 2 * K,       # k_push + k_agent per day (k_snapshot only on the first day after a load)
         "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
-        "roofline": {"bound": "hbm", "kernel": "k_push", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms},
+                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms, "per_kernel": per_kernel},
         "clocks": clocks.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -33,11 +33,18 @@ struct dys_handle {
     int64_t nnz = 0;
     int32_t last_day = -1;
     int64_t steps = 0;
-    // pinned ring of per-day stats + completion events
-    int64_t* h_stats = nullptr;
-    int32_t ring_day[DYS_STATS_RING];
-    cudaEvent_t ring_ev[DYS_STATS_RING];
-    int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags, [1] event count
+    // per-parity device output block [stats | sa_hist | bcount | events] and the pinned host ring it is copied into
+    unsigned char* d_out[2] = {nullptr, nullptr};
+    size_t off_sa = 0, off_bc = 0, off_ev = 0, out_copy_bytes = 0, out_dev_bytes = 0;
+    int64_t ev_inline = 0;
+    unsigned char* h_out = nullptr;                       // [DYS_OUT_RING][out_copy_bytes] pinned
+    int32_t out_day[DYS_OUT_RING];
+    int64_t out_step[DYS_OUT_RING];
+    cudaEvent_t out_ev[DYS_OUT_RING];
+    int64_t hist_stats[DYS_STATS_RING][N_STATS];          // stats of days that left the output ring
+    int32_t hist_day[DYS_STATS_RING];
+    uint8_t* h_open = nullptr;                            // pinned shadow of the open flags
+    int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags
     int32_t* d_bad = nullptr;
     uint8_t *d_hh_flag[2] = {nullptr, nullptr}, *d_hh_qflag[2] = {nullptr, nullptr};
     int32_t* d_flags = nullptr;      // [2][DF_LEN] per-parity day flags, then [1] closed-building count
@@ -145,15 +152,23 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     A(dev_alloc(h, (uint8_t**)&c.open, c.B));
     for (int k = 0; k < 2; ++k) { A(dev_alloc(h, &h->d_hh_flag[k], c.H + 16)); A(dev_alloc(h, &h->d_hh_qflag[k], c.H + 16)); }
     A(dev_alloc(h, &h->d_flags, 2 * DF_LEN + 4));
-    A(dev_alloc(h, &c.part, (int64_t)N_SLOTS * N_STATS)); A(dev_alloc(h, &c.stats, N_STATS)); A(dev_alloc(h, &c.ticket, 1));
+    A(dev_alloc(h, &c.part, (int64_t)N_SLOTS * N_STATS)); A(dev_alloc(h, &c.ticket, 1));
     A(dev_alloc(h, &d_pdf, DYS_PDF_LEN));
     A(dev_alloc(h, &h->d_bad, 1));
-    if (p.flags & DYS_WANT_SA_HIST) A(dev_alloc(h, &c.sa_hist, c.S * HIST_LEN));
-    if (p.flags & DYS_WANT_BUILDING_COUNTS) A(dev_alloc(h, &c.bcount, c.B));
-    if (p.flags & DYS_WANT_EVENTS) { A(dev_alloc(h, &c.ev_agent, c.n_pad)); A(dev_alloc(h, &c.ev_src, c.n_pad)); }
+    {   // one output block per parity: everything a day produces leaves the device in a single copy
+        auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        h->off_sa = sizeof(int64_t) * N_STATS;
+        h->off_bc = h->off_sa + ((p.flags & DYS_WANT_SA_HIST) ? up16(sizeof(int32_t) * (size_t)(c.S * HIST_LEN)) : 0);
+        h->off_ev = h->off_bc + ((p.flags & DYS_WANT_BUILDING_COUNTS) ? up16(sizeof(int32_t) * (size_t)c.B) : 0);
+        h->ev_inline = (p.flags & DYS_WANT_EVENTS) ? (c.n_pad / 64 > 1024 ? c.n_pad / 64 : 1024) : 0;
+        if (h->ev_inline > c.n_pad) h->ev_inline = c.n_pad;
+        h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
+        h->out_dev_bytes = h->off_ev + ((p.flags & DYS_WANT_EVENTS) ? sizeof(int2) * (size_t)c.n_pad : 0);
+        for (int k = 0; k < 2; ++k) A(dev_alloc(h, &h->d_out[k], (int64_t)h->out_dev_bytes));
+    }
     if (p.flags & DYS_WANT_IO_MAT) A(dev_alloc(h, &c.io_mat, c.S * c.S));
     c.pdf = d_pdf;
-    c.n_closed = h->d_flags + 2 * DF_LEN;
+    c.n_closed = 0;
     if (rc == DYS_OK) {
         int per_sm = 0, sms = 0;
         cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, PUSH_WARPS * 32, 0);
@@ -165,13 +180,17 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     }
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
-    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_stats, sizeof(int64_t) * N_STATS * DYS_STATS_RING) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_out, h->out_copy_bytes * DYS_OUT_RING) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open, (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK) memset(h->h_open, 1, (size_t)c.B);
     if (rc == DYS_OK && cudaMallocHost((void**)&h->h_small, sizeof(int32_t) * 16) != cudaSuccess) rc = DYS_ERR_CUDA;
-    for (int i = 0; i < DYS_STATS_RING; ++i) {
-        h->ring_day[i] = -1;
-        h->ring_ev[i] = nullptr;
-        if (rc == DYS_OK && cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = DYS_ERR_CUDA;
+    for (int i = 0; i < DYS_OUT_RING; ++i) {
+        h->out_day[i] = -1;
+        h->out_step[i] = -1;
+        h->out_ev[i] = nullptr;
+        if (rc == DYS_OK && cudaEventCreateWithFlags(&h->out_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = DYS_ERR_CUDA;
     }
+    for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
     if (rc == DYS_OK && (p.flags & DYS_TIME_KERNELS)) {
         h->tev.resize(dys_handle::T_RING * 4);
         for (auto& ev : h->tev) if (cudaEventCreate(&ev) != cudaSuccess) { rc = DYS_ERR_CUDA; break; }
@@ -192,9 +211,10 @@ extern "C" int dys_destroy(dys_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_open) cudaFreeHost(h->h_open);
     if (h->h_small) cudaFreeHost(h->h_small);
-    for (int i = 0; i < DYS_STATS_RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    for (int i = 0; i < DYS_OUT_RING; ++i) if (h->out_ev[i]) cudaEventDestroy(h->out_ev[i]);
     for (auto ev : h->tev) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -214,6 +234,9 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
     h->ib_day = -1;
     h->begun = false;
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; }
+    for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
     return DYS_OK;
 }
 
@@ -299,7 +322,6 @@ extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int3
     CK(h, cudaGetLastError());
     rc = check_bad(h, "dys_set_state");
     if (rc != DYS_OK) return rc;
-    for (int i = 0; i < DYS_STATS_RING; ++i) h->ring_day[i] = -1;
     h->last_day = -1;
     return reset_day_scratch(h);
 }
@@ -416,11 +438,23 @@ extern "C" int dys_set_open(dys_handle* h, const uint8_t* open_flags)
     if (!h || !open_flags) return h ? fail(h, DYS_ERR_INVALID_ARG, "dys_set_open: null") : DYS_ERR_INVALID_ARG;
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
-    int rc = copy_in(h, (void*)c.open, open_flags, (size_t)c.B);
-    if (rc != DYS_OK) return rc;
-    CK(h, cudaMemsetAsync((void*)c.n_closed, 0, sizeof(int32_t), h->stream));
-    k_count_closed<<<grid_for(c.B, 256), 256, 0, h->stream>>>(c.open, c.B, (int32_t*)c.n_closed);
-    CK(h, cudaGetLastError());
+    cudaPointerAttributes at{};
+    const bool on_device = cudaPointerGetAttributes(&at, open_flags) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (on_device) {      // a device-resident flag vector (e.g. a torch CUDA tensor): bring it to the pinned shadow
+        CK(h, cudaStreamSynchronize(h->stream));
+        CK(h, cudaMemcpy(h->h_open, open_flags, (size_t)c.B, cudaMemcpyDeviceToHost));
+    } else {
+        // the reference re-assigns build[:,10] every day (contagious3.py:384) but it rarely changes: an unchanged
+        // vector costs one memcmp and no transfer
+        if (memcmp(h->h_open, open_flags, (size_t)c.B) == 0) return DYS_OK;
+        CK(h, cudaStreamSynchronize(h->stream));      // the shadow may still be the source of a queued copy
+        memcpy(h->h_open, open_flags, (size_t)c.B);
+    }
+    int32_t closed = 0;
+    for (int64_t b = 0; b < c.B; ++b) closed += h->h_open[b] == 0;
+    c.n_closed = closed;
+    CK(h, cudaMemcpyAsync((void*)c.open, h->h_open, (size_t)c.B, cudaMemcpyHostToDevice, h->stream));
     return DYS_OK;
 }
 
@@ -483,6 +517,10 @@ static int step_end(dys_handle* h, int32_t day)
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
     const int par = (int)(h->steps & 1);
+    c.stats = (int64_t*)h->d_out[par];
+    c.sa_hist = (h->p.flags & DYS_WANT_SA_HIST) ? (int32_t*)(h->d_out[par] + h->off_sa) : nullptr;
+    c.bcount = (h->p.flags & DYS_WANT_BUILDING_COUNTS) ? (int32_t*)(h->d_out[par] + h->off_bc) : nullptr;
+    c.ev = (h->p.flags & DYS_WANT_EVENTS) ? (int2*)(h->d_out[par] + h->off_ev) : nullptr;
     c.hh_flag = h->d_hh_flag[par]; c.hh_qflag = h->d_hh_qflag[par];
     c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
     c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
@@ -492,10 +530,17 @@ static int step_end(dys_handle* h, int32_t day)
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
     CK(h, cudaGetLastError());
-    const int slot = (int)(h->steps % DYS_STATS_RING);
-    CK(h, cudaMemcpyAsync(h->h_stats + (size_t)slot * N_STATS, c.stats, sizeof(int64_t) * N_STATS, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaEventRecord(h->ring_ev[slot], h->stream));
-    h->ring_day[slot] = day;
+    const int slot = (int)(h->steps % DYS_OUT_RING);
+    if (h->out_day[slot] >= 0) {      // the day leaving the ring keeps its stats block in the history
+        CK(h, cudaEventSynchronize(h->out_ev[slot]));
+        const int hs = (int)(h->out_step[slot] % DYS_STATS_RING);
+        memcpy(h->hist_stats[hs], h->h_out + (size_t)slot * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
+        h->hist_day[hs] = h->out_day[slot];
+    }
+    CK(h, cudaMemcpyAsync(h->h_out + (size_t)slot * h->out_copy_bytes, h->d_out[par], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaEventRecord(h->out_ev[slot], h->stream));
+    h->out_day[slot] = day;
+    h->out_step[slot] = h->steps;
     h->last_day = day;
     h->ib_day = day + 1;         // k_agent wrote tomorrow's snapshot and household flags
     ++h->steps;
@@ -518,23 +563,42 @@ extern "C" int dys_step(dys_handle* h, int32_t day, const dys_injected* injected
     return rc == DYS_OK ? step_end(h, day) : rc;
 }
 
+static int find_out_slot(dys_handle* h, int32_t day)
+{
+    for (int i = 0; i < DYS_OUT_RING; ++i)
+        if (h->out_day[i] == day) return i;
+    return -1;
+}
+
+extern "C" int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    const int i = find_out_slot(h, day);
+    if (i < 0) return fail(h, DYS_ERR_NOT_AVAILABLE, "outputs of day %d are not in the ring (the last %d days are kept)", day, DYS_OUT_RING);
+    CK(h, cudaEventSynchronize(h->out_ev[i]));
+    const unsigned char* base = h->h_out + (size_t)i * h->out_copy_bytes;
+    out->day = day;
+    out->stats = (const int64_t*)base;
+    out->sa_hist = (h->p.flags & DYS_WANT_SA_HIST) ? (const int32_t*)(base + h->off_sa) : nullptr;
+    out->building_counts = (h->p.flags & DYS_WANT_BUILDING_COUNTS) ? (const int32_t*)(base + h->off_bc) : nullptr;
+    out->events = (h->p.flags & DYS_WANT_EVENTS) ? (const int32_t*)(base + h->off_ev) : nullptr;
+    out->n_events = out->stats[ST_N_EVENTS];
+    out->events_inline = (int32_t)(out->n_events < h->ev_inline ? out->n_events : h->ev_inline);
+    return DYS_OK;
+}
+
 extern "C" int dys_get_stats(dys_handle* h, int32_t day, int64_t* out)
 {
     if (!h || !out) return DYS_ERR_INVALID_ARG;
-    for (int i = 0; i < DYS_STATS_RING; ++i) {
-        if (h->ring_day[i] != day) continue;
-        CK(h, cudaEventSynchronize(h->ring_ev[i]));
-        memcpy(out, h->h_stats + (size_t)i * N_STATS, sizeof(int64_t) * N_STATS);
+    const int i = find_out_slot(h, day);
+    if (i >= 0) {
+        CK(h, cudaEventSynchronize(h->out_ev[i]));
+        memcpy(out, h->h_out + (size_t)i * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
         return DYS_OK;
     }
-    return fail(h, DYS_ERR_NOT_AVAILABLE, "stats of day %d are not in the ring (last %d days are kept)", day, DYS_STATS_RING);
-}
-
-static int need_last_day(dys_handle* h, int32_t day, const void* buf, const char* what)
-{
-    if (!buf) return fail(h, DYS_ERR_NOT_AVAILABLE, "%s was not requested in dys_params.flags", what);
-    if (day != h->last_day) return fail(h, DYS_ERR_NOT_AVAILABLE, "%s is only kept for the most recent day (%d)", what, h->last_day);
-    return DYS_OK;
+    for (int k = 0; k < DYS_STATS_RING; ++k)
+        if (h->hist_day[k] == day) { memcpy(out, h->hist_stats[k], sizeof(int64_t) * N_STATS); return DYS_OK; }
+    return fail(h, DYS_ERR_NOT_AVAILABLE, "stats of day %d are no longer kept (the last %d days are)", day, DYS_STATS_RING);
 }
 
 static int copy_out(dys_handle* h, void* dst, const void* src, size_t bytes)
@@ -548,38 +612,61 @@ static int copy_out(dys_handle* h, void* dst, const void* src, size_t bytes)
 extern "C" int dys_get_sa_hist(dys_handle* h, int32_t day, int32_t* out)
 {
     if (!h || !out) return DYS_ERR_INVALID_ARG;
-    int rc = need_last_day(h, day, h->c.sa_hist, "sa_hist");
-    return rc != DYS_OK ? rc : copy_out(h, out, h->c.sa_hist, sizeof(int32_t) * (size_t)(h->c.S * HIST_LEN));
+    dys_day_outputs o;
+    int rc = dys_get_outputs(h, day, &o);
+    if (rc != DYS_OK) return rc;
+    if (!o.sa_hist) return fail(h, DYS_ERR_NOT_AVAILABLE, "sa_hist was not requested in dys_params.flags");
+    memcpy(out, o.sa_hist, sizeof(int32_t) * (size_t)(h->c.S * HIST_LEN));
+    return DYS_OK;
 }
 
 extern "C" int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out)
 {
     if (!h || !out) return DYS_ERR_INVALID_ARG;
-    int rc = need_last_day(h, day, h->c.bcount, "building counts");
-    return rc != DYS_OK ? rc : copy_out(h, out, h->c.bcount, sizeof(int32_t) * (size_t)h->c.B);
+    dys_day_outputs o;
+    int rc = dys_get_outputs(h, day, &o);
+    if (rc != DYS_OK) return rc;
+    if (!o.building_counts) return fail(h, DYS_ERR_NOT_AVAILABLE, "building counts were not requested in dys_params.flags");
+    memcpy(out, o.building_counts, sizeof(int32_t) * (size_t)h->c.B);
+    return DYS_OK;
 }
 
 extern "C" int dys_get_io_mat(dys_handle* h, int32_t day, int32_t* out)
 {
     if (!h || !out) return DYS_ERR_INVALID_ARG;
-    int rc = need_last_day(h, day, h->c.io_mat, "io_mat");
-    return rc != DYS_OK ? rc : copy_out(h, out, h->c.io_mat, sizeof(int32_t) * (size_t)(h->c.S * h->c.S));
+    if (!h->c.io_mat) return fail(h, DYS_ERR_NOT_AVAILABLE, "io_mat was not requested in dys_params.flags");
+    if (day != h->last_day) return fail(h, DYS_ERR_NOT_AVAILABLE, "io_mat is only kept for the most recent day (%d)", h->last_day);
+    return copy_out(h, out, h->c.io_mat, sizeof(int32_t) * (size_t)(h->c.S * h->c.S));
 }
 
 extern "C" int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_t* infector, int64_t cap, int64_t* n)
 {
     if (!h || !n) return DYS_ERR_INVALID_ARG;
-    int rc = need_last_day(h, day, h->c.ev_agent, "events");
+    dys_day_outputs o;
+    int rc = dys_get_outputs(h, day, &o);
     if (rc != DYS_OK) return rc;
-    rc = copy_out(h, h->h_small + 1, h->d_flags + h->last_parity * DF_LEN + DF_N_EVENTS, sizeof(int32_t));
-    if (rc != DYS_OK) return rc;
-    const int64_t cnt = h->h_small[1];
+    if (!o.events) return fail(h, DYS_ERR_NOT_AVAILABLE, "events were not requested in dys_params.flags");
+    const int64_t cnt = o.n_events;
     *n = cnt;
     if (cnt == 0 || (!agent && !infector)) return DYS_OK;
     if (cap < cnt) return fail(h, DYS_ERR_INVALID_ARG, "dys_get_events: capacity %lld < %lld events", (long long)cap, (long long)cnt);
-    if (agent) rc = copy_out(h, agent, h->c.ev_agent, sizeof(int32_t) * (size_t)cnt);
-    if (rc == DYS_OK && infector) rc = copy_out(h, infector, h->c.ev_src, sizeof(int32_t) * (size_t)cnt);
-    return rc;
+    const int32_t* pairs = o.events;
+    std::vector<int32_t> rest;
+    if (cnt > o.events_inline) {
+        // more events than travel with the day's block: fetch them from the device block, which is only intact until
+        // the day after next is stepped
+        const int i = find_out_slot(h, day);
+        if (h->steps - h->out_step[i] > 2) return fail(h, DYS_ERR_NOT_AVAILABLE, "events of day %d beyond the first %d were overwritten", day, o.events_inline);
+        rest.resize((size_t)cnt * 2);
+        rc = copy_out(h, rest.data(), h->d_out[h->out_step[i] & 1] + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt);
+        if (rc != DYS_OK) return rc;
+        pairs = rest.data();
+    }
+    for (int64_t k = 0; k < cnt; ++k) {
+        if (agent) agent[k] = pairs[2 * k];
+        if (infector) infector[k] = pairs[2 * k + 1];
+    }
+    return DYS_OK;
 }
 
 extern "C" int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, int32_t* t_q, int32_t* t_adm, int32_t* src)
@@ -647,7 +734,7 @@ extern "C" int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* 
     switch (which) {
         case DYS_BUF_STATUS: *ptr = c.status; *bytes = c.n_pad; break;
         case DYS_BUF_INFECTIOUS: *ptr = c.ib; *bytes = round_up(c.n_glob, 1024); break;
-        case DYS_BUF_STATS: *ptr = c.stats; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
+        case DYS_BUF_STATS: *ptr = h->d_out[h->last_parity]; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
         case DYS_BUF_T_INF: *ptr = c.t_inf; *bytes = c.n_pad * 2; break;
         default: return fail(h, DYS_ERR_INVALID_ARG, "unknown buffer %d", which);
     }

@@ -68,7 +68,7 @@ struct DevCtx {
     const double* pdf;                   // [64]
     uint8_t* ib;                         // [n_glob padded] day-start infectious bytes of ALL agents
     const uint8_t* open;                 // [B]
-    const int32_t* n_closed;             // [1] closed buildings today
+    int32_t n_closed;                    // closed buildings today (counted on the host by dys_set_open)
     const uint8_t *hh_flag, *hh_qflag;   // [H] households diagnosed TODAY / quirk households (contagious3.py:263, :267)
     uint8_t *hh_flag_next, *hh_qflag_next;   // the other parity: tomorrow's, raised by k_agent, cleared by k_push
     const uint8_t* hh_always;            // [H] or null
@@ -76,11 +76,11 @@ struct DevCtx {
     const int32_t* trig_hh;
     int32_t *df, *df_next;               // today's / tomorrow's flag block
     unsigned long long* part;            // [N_STATS][N_SLOTS] spread partial sums
-    int64_t* stats;                      // [N_STATS]
+    int64_t* stats;                      // [N_STATS]   (stats, sa_hist, bcount, ev live in one per-parity output block)
     unsigned int* ticket;
     int32_t* sa_hist;                    // [S * 21] or null
     int32_t* bcount;                     // [B] or null
-    int32_t *ev_agent, *ev_src;          // [n_pad] or null
+    int2* ev;                            // [n_pad] today's (infected, infector) pairs, or null
     int32_t* io_mat;                     // [S * S] or null
     const double *u_adm, *u_death, *u_pair;   // injected draws or null
     double* pair_prob;                   // [n_glob^2] or null (tests)

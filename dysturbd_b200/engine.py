@@ -46,6 +46,11 @@ class _Params(C.Structure):
     ]
 
 
+class _DayOutputs(C.Structure):
+    _fields_ = [("day", C.c_int32), ("events_inline", C.c_int32), ("n_events", C.c_int64), ("stats", C.POINTER(C.c_int64)),
+                ("sa_hist", C.POINTER(C.c_int32)), ("building_counts", C.POINTER(C.c_int32)), ("events", C.POINTER(C.c_int32))]
+
+
 class _Injected(C.Structure):
     _fields_ = [("u_adm", C.c_void_p), ("u_death", C.c_void_p), ("u_pair", C.c_void_p)]
 
@@ -53,7 +58,7 @@ class _Injected(C.Structure):
 EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population", "dys_load_graph", "dys_load_quirk",
            "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_begin", "dys_step_end", "dys_get_stats",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
-           "dys_get_pair_prob", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
+           "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device"]
 
 _lib = None
@@ -88,6 +93,7 @@ def load_library():
     lib.dys_get_io_mat.argtypes = [vp, i32, vp]
     lib.dys_get_state.argtypes = [vp] + [vp] * 5
     lib.dys_get_pair_prob.argtypes = [vp, vp]
+    lib.dys_get_outputs.argtypes = [vp, i32, C.POINTER(_DayOutputs)]
     lib.dys_sync.argtypes = [vp]
     lib.dys_get_kernel_times.argtypes = [vp, vp, vp]
     lib.dys_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
@@ -224,6 +230,26 @@ class Engine:
 
     def step_end(self, day):
         self._ck(self.lib.dys_step_end(self.h, int(day)))
+
+    def outputs(self, day):
+        """Everything day `day` produced, as zero-copy numpy views of the library's pinned host ring (valid until
+        DYS_OUT_RING - 1 = 3 further days are stepped): dict(stats, sa_hist, building_counts, events[n,2], n_events)."""
+        o = _DayOutputs()
+        self._ck(self.lib.dys_get_outputs(self.h, int(day), C.byref(o)))
+        as_np = np.ctypeslib.as_array
+        out = {"stats": as_np(o.stats, (N_STATS,)), "n_events": int(o.n_events), "sa_hist": None, "building_counts": None,
+               "events": None}
+        if o.sa_hist:
+            out["sa_hist"] = as_np(o.sa_hist, (self.pop.S, HIST_LEN))
+        if o.building_counts:
+            out["building_counts"] = as_np(o.building_counts, (self.pop.B,))
+        if o.events:
+            if o.n_events > o.events_inline:          # rare: more infections than travel with the day's block
+                a, s_ = self.events(day)
+                out["events"] = np.stack([a, s_], axis=1)
+            else:
+                out["events"] = as_np(o.events, (max(int(o.events_inline), 1), 2))[:int(o.events_inline)]
+        return out
 
     def stats(self, day):
         out = np.zeros(N_STATS, dtype=np.int64)

@@ -90,10 +90,17 @@ class EpidemicModel:
         sim.set_open(self.open.astype(np.uint8))
         closed_today = int((self.open == 0).sum())
         sim.step(day)
-        st = sim.stats(day)
+        if hasattr(sim, "outputs"):              # the CUDA engine: one pinned block per day, no further transfers
+            o = sim.outputs(day)
+            st, sa_hist, bc = o["stats"], o["sa_hist"], o["building_counts"]
+            ev = o["events"]
+            order = np.argsort(ev[:, 0], kind="stable")
+            ev_a, ev_s = ev[order, 0], ev[order, 1]
+        else:                                    # tests drive this loop with the CPU oracle as backend
+            st, sa_hist, bc = sim.stats(day), sim.sa_hist(day), sim.building_counts(day)
+            ev_a, ev_s = sim.events(day)
         hist = st[HIST0:HIST0 + HIST_LEN]
         R = compute_R_from_hist(hist, self._pdf, prm.recover)
-        sa_hist = sim.sa_hist(day)
         sas = [float(x) for x in p.sa_ids]
         res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
         vis_R = res['Stats'][day - prm.diagnosis]['R'] if day > prm.diagnosis else 0          # :306-309
@@ -110,9 +117,7 @@ class EpidemicModel:
             S['Total infected'] = res['Stats'][day - 1]['Total infected'] + new_infections
         S['Susceptible'] = p.N - S['Total infected']
         res['Stats'][day] = S
-        bc = sim.building_counts(day)
         res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
-        ev_a, ev_s = sim.events(day)
         mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                       # :356-366
         if len(ev_a):
             for a, s in zip(p.sa[ev_a], p.sa[ev_s]):

@@ -72,11 +72,12 @@ enum {
     /* work counters of the day (feed the algorithmic-bytes formula of DESIGN.md) */
     DYS_ST_SUS0,             /* susceptible at day start (status 1 or 3) */
     DYS_ST_INF0,             /* infectious at day start (status 2, 3.5, 4) */
-    DYS_ST_EDGES_SCANNED,    /* interaction_prob non-zeros visited */
+    DYS_ST_EDGES_SCANNED,    /* interaction_prob non-zeros visited (implementation specific: rows of infectious agents) */
     DYS_ST_CANDIDATES,       /* ... whose column agent is infectious */
     DYS_ST_EXPOSED,          /* ... and shares a building today: one Bernoulli each */
     DYS_ST_HITS,             /* Bernoulli successes */
     DYS_ST_CHANGED,          /* agents whose state was rewritten today */
+    DYS_ST_COUNT_S = 20,     /* [20..27]: end-of-day agents in status 1, 2, 3, 3.5, 4, 5, 6, 7 */
     DYS_ST_HIST0 = 32        /* [32 .. 32+20]: global days-since-infection histogram */
 };
 
@@ -155,6 +156,21 @@ int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out /* [B] */);
 int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_t* infector, int64_t cap, int64_t* n);
 int dys_get_io_mat(dys_handle* h, int32_t day, int32_t* out /* [S*S] */);
 int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, int32_t* t_q, int32_t* t_adm, int32_t* src);
+/* Everything a day produced, in ONE device->host transfer that dys_step() already queued into library-owned pinned host
+ * memory: this call only waits for it.  The pointers stay valid until DYS_OUT_RING - 1 further days have been stepped,
+ * so a host loop can queue day d+1 before it consumes day d (the lockdown decision lags `diagnosis` = 7 days,
+ * contagious3.py:306-309, so nothing a day produces is needed to start the next one). */
+#define DYS_OUT_RING 4
+typedef struct dys_day_outputs {
+    int32_t day;
+    int32_t events_inline;       /* how many of the n_events pairs are in `events` (the rest: dys_get_events) */
+    int64_t n_events;
+    const int64_t* stats;        /* [DYS_N_STATS] */
+    const int32_t* sa_hist;      /* [S*DYS_HIST_LEN] or NULL */
+    const int32_t* building_counts; /* [B] or NULL */
+    const int32_t* events;       /* [events_inline][2] = (infected, infector) row indices, or NULL */
+} dys_day_outputs;
+int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out);
 /* P for every evaluated pair of the most recent day (tests; requires injected mode): out[N*N] */
 int dys_get_pair_prob(dys_handle* h, double* out);
 

@@ -1,0 +1,80 @@
+// Developer micro-benchmark (not part of the product): times kernels on synthetic arrays to separate launch floor,
+// latency chains and throughput.  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo tools/kbench.cu -o tools/kbench
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../dysturbd_b200/csrc/dys_day.cuh"
+using namespace dys;
+
+__global__ void k_empty(const DevCtx c, const int day) {}
+__global__ void __launch_bounds__(256) k_stream(const DevCtx c, const int day)
+{
+    const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (a0 >= c.n_pad) return;
+    const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
+    const short4 ti = *reinterpret_cast<const short4*>(c.t_inf + a0);
+    uint32_t w = sv.x + sv.y + sv.z + sv.w + ti.x;
+    *reinterpret_cast<uint32_t*>(c.ib + a0) = w;
+}
+__global__ void __launch_bounds__(256) k_agent_nofold(const DevCtx c, const int day) { agent_body<1>(c, day); }
+__global__ void __launch_bounds__(256) k_agent_noreduce(const DevCtx c, const int day) { agent_body<2>(c, day); }
+template <typename T> T* dalloc(size_t n, int fill = 0) { T* p; cudaMalloc(&p, n * sizeof(T)); cudaMemset(p, fill, n * sizeof(T)); return p; }
+
+int main(int argc, char** argv)
+{
+    const int64_t N = argc > 1 ? atoll(argv[1]) : 1002496;
+    const double frac_inf = argc > 2 ? atof(argv[2]) : 0.02;
+    DevCtx c{};
+    c.n_loc = c.n_pad = c.n_glob = N; c.rt_n = N; c.H = N / 3; c.B = N / 20; c.S = N / 1200; c.V = 10;
+    c.recover = 21; c.hospital_recover = 28; c.diagnosis = 7; c.quarantine = 7; c.adm_min = 4; c.adm_max = 14; c.death_min = 3;
+    c.norm_factor = 4.0; c.compliance = 1.0; c.seed = 1;
+    std::vector<uint8_t> st(N, ST_S); std::vector<int16_t> ti(N, 0); std::vector<int32_t> hh(N), home(N), sa(N), src(N, -1);
+    srand(1);
+    for (int64_t a = 0; a < N; ++a) {
+        hh[a] = (int)(a / 3); home[a] = (int)(a / 30 % c.B); sa[a] = (int)(a / 1200 % c.S);
+        if (rand() / (double)RAND_MAX < frac_inf) { st[a] = ST_I; ti[a] = 18; src[a] = 5; }
+    }
+    c.status = dalloc<uint8_t>(N); cudaMemcpy(c.status, st.data(), N, cudaMemcpyHostToDevice);
+    c.t_inf = dalloc<int16_t>(N); cudaMemcpy(c.t_inf, ti.data(), 2 * N, cudaMemcpyHostToDevice);
+    c.t_q = dalloc<int16_t>(N); c.t_adm = dalloc<int16_t>(N);
+    c.src = dalloc<int32_t>(N); cudaMemcpy(c.src, src.data(), 4 * N, cudaMemcpyHostToDevice);
+    int32_t* d; d = dalloc<int32_t>(N); cudaMemcpy(d, hh.data(), 4 * N, cudaMemcpyHostToDevice); c.hh = d;
+    d = dalloc<int32_t>(N); cudaMemcpy(d, home.data(), 4 * N, cudaMemcpyHostToDevice); c.home = d;
+    d = dalloc<int32_t>(N); cudaMemcpy(d, sa.data(), 4 * N, cudaMemcpyHostToDevice); c.sa = d;
+    c.risk = dalloc<double>(N); c.p_adm = dalloc<double>(N); c.p_death = dalloc<double>(N);
+    c.pdf = dalloc<double>(64);
+    c.ib = dalloc<uint8_t>(N + 2048);
+    c.open = dalloc<uint8_t>(c.B, 1); c.n_closed = 0;
+    uint8_t* f0 = dalloc<uint8_t>(c.H + 16); uint8_t* f1 = dalloc<uint8_t>(c.H + 16);
+    c.hh_flag = f0; c.hh_qflag = f1; c.hh_flag_next = dalloc<uint8_t>(c.H + 16); c.hh_qflag_next = dalloc<uint8_t>(c.H + 16);
+    int32_t* df = dalloc<int32_t>(16); c.df = df; c.df_next = df + 4;
+    c.part = dalloc<unsigned long long>(64 * 64); c.stats = dalloc<int64_t>(64); c.ticket = dalloc<unsigned int>(1);
+    c.sa_hist = dalloc<int32_t>(c.S * 21); c.bcount = dalloc<int32_t>(c.B);
+    c.ev = dalloc<int2>(N);
+    c.tptr = dalloc<int64_t>(N + 1); c.tcolx = dalloc<uint32_t>(16); c.tval = dalloc<double>(16);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto timeit = [&](const char* name, auto launch) {
+        for (int i = 0; i < 5; ++i) launch(i);
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        const int R = 200;
+        for (int i = 0; i < R; ++i) launch(100);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%-28s %8.2f us/launch   (%s)\n", name, ms * 1000 / R, cudaGetErrorString(cudaGetLastError()));
+    };
+    const unsigned g4 = (unsigned)(N / 1024);
+    int anynd = 1;
+    timeit("k_empty", [&](int d) { k_empty<<<g4, 256>>>(c, d); });
+    timeit("k_stream (5 B/agent)", [&](int d) { k_stream<<<g4, 256>>>(c, d); });
+    timeit("k_agent any_nd=0", [&](int d) { k_agent<<<g4, 256>>>(c, d); });
+    cudaMemcpy(df, &anynd, 4, cudaMemcpyHostToDevice);
+    timeit("k_agent any_nd=1", [&](int d) { k_agent<<<g4, 256>>>(c, d); });
+    timeit("k_agent no fold/ticket", [&](int d) { k_agent_nofold<<<g4, 256>>>(c, d); });
+    timeit("k_agent no reduction", [&](int d) { k_agent_noreduce<<<g4, 256>>>(c, d); });
+    timeit("k_snapshot", [&](int d) { k_snapshot<<<g4, 256>>>(c, d, f0, f1, df); });
+    int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, 256, 0);
+    timeit("k_push (empty rows)", [&](int d) { k_push<<<148 * per_sm, 256>>>(c, d); });
+    printf("push blocks/SM %d\n", per_sm);
+    return 0;
+}
