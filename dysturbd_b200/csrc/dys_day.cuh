@@ -38,20 +38,34 @@ __device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, uint
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_push.  Persistent warps walk groups of 32 consecutive halo agents.  The infectious lanes' transposed rows are
-// flattened (warp prefix sum of their lengths) so that all 32 lanes work on consecutive entries regardless of how the
-// infectious agents are spread; each entry costs one coalesced 4-byte read and one 1-byte status gather.
+// k_push.  Persistent, warp-autonomous.  A warp scans the snapshot bytes of 128 halo agents per step (one 32-bit load
+// per lane, the next step's load already in flight), compacts the infectious ones into its own shared-memory frontier
+// queue, and whenever 32 rows are queued expands them together: the 32 transposed rows are flattened (warp prefix sum
+// of their lengths) so every lane works on consecutive entries however the infectious agents are spread; four entries
+// per lane are in flight (one coalesced 4-byte read + one 1-byte status gather each).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PUSH_WARPS = 8;
+constexpr int PUSH_CHUNK = 128;                    // halo agents scanned per warp step (4 snapshot bytes per lane): small
+                                                   // steps spread the infectious rows over all resident warps
+constexpr int PUSH_QCAP = PUSH_CHUNK + 32;
+constexpr int PUSH_PCAP = 256;
+
+struct PushWarpSmem {
+    uint32_t q_idx[PUSH_QCAP];                     // halo-relative index of a queued infectious agent
+    uint8_t q_ib[PUSH_QCAP];                       // its snapshot byte
+    int off[36];                                   // exclusive prefix of the 32 expanded rows' lengths
+    int64_t t0[32];
+    unsigned long long pairs[PUSH_PCAP];           // exposed pairs awaiting their Bernoulli: entry | row << 48 | iso_u << 56
+};
 
 __global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const int day)
 {
     __shared__ double s_pdf[64];
     __shared__ unsigned int s_acc[8];
-    __shared__ int s_off[PUSH_WARPS][36];
-    __shared__ int64_t s_t0[PUSH_WARPS][32];
-    __shared__ uint8_t s_ib[PUSH_WARPS][32];
+    __shared__ PushWarpSmem s_w[PUSH_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    PushWarpSmem& w = s_w[wid];
 
     // scratch that k_agent fills today, and the flags it raises for tomorrow
     grid_clear(c.sa_hist, c.S * HIST_LEN);
@@ -67,50 +81,20 @@ __global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const 
     const bool any_closed = c.n_closed != 0;
     unsigned int cnt[4] = {0, 0, 0, 0};   // entries scanned, candidates, exposed, hits
 
-    const int64_t n_groups = (c.rt_n + 31) >> 5;
-    for (int64_t g = (int64_t)blockIdx.x * PUSH_WARPS + wid; g < n_groups; g += (int64_t)gridDim.x * PUSH_WARPS) {
-        const int64_t il = g * 32 + lane;                 // halo-relative index of this lane's agent
-        const uint32_t ibv = il < c.rt_n ? (uint32_t)c.ib[c.rt_lo + il] : 0u;
-        const bool inf = ibv & IB_INF;
-        if (!__ballot_sync(0xffffffffu, inf)) continue;
-        int64_t t0 = 0;
-        int len = 0;
-        if (inf) { t0 = c.tptr[il]; len = (int)(c.tptr[il + 1] - t0); }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        s_off[wid][lane] = incl - len;
-        if (lane == 31) s_off[wid][32] = total;
-        s_t0[wid][lane] = t0;
-        s_ib[wid][lane] = (uint8_t)ibv;
-        __syncwarp();
-        cnt[0] += len;
-        for (int f0 = 0; f0 < total; f0 += 32) {
-            const int f = f0 + lane;
-            if (f >= total) continue;
-            int r = 0, hi = 32;                            // s_off[r] <= f < s_off[hi]; the last such r is the row
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const int mid = (r + hi) >> 1;
-                if (s_off[wid][mid] <= f) r = mid; else hi = mid;
-            }
-            const int64_t e = s_t0[wid][r] + (f - s_off[wid][r]);
-            const uint32_t cw = __ldg(c.tcolx + e);
-            const uint32_t ul = cw & COL_MASK, cls = cw >> CLS_SHIFT;
-            const uint32_t st_u = c.status[ul];           // day-start status: k_agent has not run yet today
-            if (!in_set(M_SUS, st_u)) continue;
-            ++cnt[1];
-            const uint32_t ib_i = s_ib[wid][r];
-            const bool iso_u = (st_u == ST_QH), iso_i = ib_i & IB_ISO;
-            const int64_t ig = c.rt_lo + g * 32 + r, ug = c.lo + ul;
-            bool ex = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
-                      ((cls & CLS_OO) && !iso_u && !iso_i);
-            if (ex && any_closed) ex = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
-            if (!ex) continue;
+    // settle the first n queued pairs (susceptible u, infectious i) that share a building: probability, Bernoulli, mailbox.
+    // Dense: one pair per lane, so the two 8-byte gathers and the Philox rounds are issued once per 32 pairs.
+    auto settle = [&](const int q0, const int n) {
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            if (k >= n) continue;
+            const unsigned long long rec = w.pairs[k];
+            const int64_t e = (int64_t)(rec & 0xFFFFFFFFFFFFull);
+            const int r = (int)((rec >> 48) & 0x3Fu);
+            const bool iso_u = (rec >> 56) & 1u;
+            const uint32_t cw = __ldg(c.tcolx + e), ib_i = w.q_ib[q0 + r];
+            const uint32_t ul = cw & COL_MASK;
+            const int64_t ug = c.lo + ul, ig = c.rt_lo + w.q_idx[q0 + r];
+            if (any_closed && !exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, (ib_i & IB_ISO) != 0)) continue;
             ++cnt[2];
             // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
             // rounded separately (no add follows, so no FMA can form)
@@ -119,216 +103,329 @@ __global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const 
             p = __dmul_rn(p, c.norm_factor);
             if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
             const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
-            if (p > u) { ++cnt[3]; atomicMax(&c.src[ul], (int)ig); }           // :240, :248
+            if (p > u) { ++cnt[3]; atomicMax(&c.src[ul], (int)ig); }               // :240, :248
         }
         __syncwarp();
+    };
+
+    // expand nb (<= 32) queued rows starting at queue position q0
+    auto expand = [&](const int q0, const int nb) {
+        int64_t t0 = 0;
+        int len = 0;
+        if (lane < nb) { const uint32_t il = w.q_idx[q0 + lane]; t0 = __ldg(c.tptr + il); len = (int)(__ldg(c.tptr + il + 1) - t0); }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        w.off[lane] = incl - len;
+        if (lane == 31) w.off[32] = total;
+        w.t0[lane] = t0;
+        __syncwarp();
+        cnt[0] += len;
+        int np = 0;                                        // queued pairs (warp-uniform)
+        for (int f0 = 0; f0 < total; f0 += 128) {
+            int64_t e[4];
+            int r[4];
+            uint32_t cw[4], st_u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int f = f0 + 32 * k + lane;
+                int lo = 0, hi = 32;                       // off[lo] <= f < off[hi]; the last such lo is the row
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int mid = (lo + hi) >> 1;
+                    if (w.off[mid] <= f) lo = mid; else hi = mid;
+                }
+                r[k] = lo;
+                e[k] = w.t0[lo] + (f - w.off[lo]);
+                cw[k] = f < total ? __ldg(c.tcolx + e[k]) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[cw[k] & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // cheap part of the exposure test (static class x today's isolation); survivors are queued
+                const bool sus = in_set(M_SUS, st_u[k]);
+                cnt[1] += sus;
+                const uint32_t cls = cw[k] >> CLS_SHIFT;
+                const bool iso_u = (st_u[k] == ST_QH), iso_i = w.q_ib[q0 + r[k]] & IB_ISO;
+                const bool ex = sus && ((cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
+                                        ((cls & CLS_OO) && !iso_u && !iso_i));
+                const unsigned m = __ballot_sync(0xffffffffu, ex);
+                if (ex) w.pairs[np + __popc(m & lt_mask)] = (unsigned long long)e[k] | ((unsigned long long)r[k] << 48) |
+                                                            ((unsigned long long)iso_u << 56);
+                np += __popc(m);
+            }
+            __syncwarp();
+            if (np > PUSH_PCAP - 128) { settle(q0, np); np = 0; }
+        }
+        if (np > 0) settle(q0, np);
+        __syncwarp();
+    };
+
+    const int64_t n_chunks = (c.rt_n + PUSH_CHUNK - 1) / PUSH_CHUNK;
+    const int64_t stride = (int64_t)gridDim.x * PUSH_WARPS;
+    int64_t ch = (int64_t)blockIdx.x * PUSH_WARPS + wid;
+    int nq = 0;                                            // queued rows (warp-uniform)
+    const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib + c.rt_lo);     // rt_lo is a multiple of 1024
+    uint32_t v = 0;
+    if (ch < n_chunks) v = ib4[ch * (PUSH_CHUNK / 4) + lane];
+    for (; ch < n_chunks; ch += stride) {
+        uint32_t vn = 0;
+        if (ch + stride < n_chunks) vn = ib4[(ch + stride) * (PUSH_CHUNK / 4) + lane];   // next step's bytes, in flight
+        const int mine = __popc(v & 0x80808080u);
+        if (__ballot_sync(0xffffffffu, mine != 0)) {
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pos = nq + incl - mine;
+            const uint32_t il0 = (uint32_t)(ch * PUSH_CHUNK + lane * 4);
+            if (mine) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t byte = (v >> (8 * b)) & 0xFFu;
+                    if ((byte & IB_INF) && il0 + b < (uint32_t)c.rt_n) { w.q_idx[pos] = il0 + b; w.q_ib[pos] = (uint8_t)byte; ++pos; }
+                }
+            }
+            nq += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            while (nq >= 32) {         // expand from the back of the queue: nothing has to move
+                nq -= 32;
+                expand(nq, 32);
+            }
+        }
+        v = vn;
     }
+    if (nq > 0) expand(0, nq);
     const int idx[4] = {ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED, ST_HITS};
     __syncthreads();
     block_accumulate<4>(c, idx, cnt, s_acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_agent.  4 agents per thread, vector loads, one pass; columns an agent's status cannot need are not loaded, and an
-// agent to whom nothing can happen today (susceptible, not infected, no household diagnosed anywhere; recovered;
-// dead) only feeds the counters.  Compartment counts are reduced as packed status histograms (two REDUX per warp);
-// rare events (admissions, deaths, diagnoses, infections, ...) go straight to shared-memory counters.
+// k_agent.  A block owns 1024 consecutive agents, in two phases.
+//   sweep  : 4 agents per thread, vector loads of the status word, the infector mailbox and (on days with a
+//            diagnosis) the household flags.  An agent to whom nothing can happen today -- susceptible, nobody infected
+//            it, household not flagged; or recovered -- only feeds the packed status histogram.  Every other agent's
+//            local index is compacted (ballot + prefix popcount) into a shared-memory work list.
+//   settle : the work list is processed densely, one agent per thread: B, C, applying D, the ordered rules of E, F, G,
+//            tomorrow's snapshot byte and household flags.  Divergent per-agent logic therefore costs instructions in
+//            proportion to the agents that need it, not to the population.
+// Compartment counts are reduced as packed 8-bit histograms (REDUX); rare events go to shared-memory counters; the last
+// block folds the spread partial sums into the day's stats block.
 // ---------------------------------------------------------------------------------------------------------------
 // packed 8-bit histogram field of a status code: QI S I QH | D H R X   (4 agents x 32 lanes = 128 < 256 per field)
-__device__ __forceinline__ void hist_add(uint32_t (&w)[2], uint32_t st)
-{
-    const uint32_t idx = (st == ST_QI) ? 0u : (st >> 1);
-    w[idx >> 2] += 1u << (8u * (idx & 3u));
-}
+__device__ __forceinline__ uint32_t hist_idx(uint32_t st) { return (st == ST_QI) ? 0u : (st >> 1); }
 constexpr uint32_t M_F = M_SUS | sbit(ST_I) | sbit(ST_QI);      // can be in status 1 or 2 when F runs
 enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS, EV_CHANGED, EV_LEN };
 // internal partial-sum rows (folded into the public stats by the last block)
-constexpr int RAW_END = 53;      // [53..60] end-of-day status counts in hist_add order
+constexpr int RAW_END = 53;      // [53..60] end-of-day status counts in hist_idx order
 constexpr int RAW_SUS0 = 61, RAW_INF0 = 62;
 constexpr int ST_COUNT0 = 20;    // public: stats[20..27] = end-of-day agents in S, I, QH, QI, D, H, R, X
+constexpr int AGENT_TILE = 1024;
+
+// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
+__device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
+                                             unsigned int* s_cnt, unsigned int* s_ev, unsigned int* s_hist, bool& infected_today,
+                                             int& infector)
+{
+    const uint32_t st = c.status[a];
+    uint32_t x = st;
+    int ti = in_set(M_EVER, st) ? (int)c.t_inf[a] : 0;
+    int tq = in_set(M_ISO, st) ? (int)c.t_q[a] : 0;
+    bool w_ti = false, w_tq = false;
+    infected_today = false;
+    // ---- B, C (contagious3.py:205-227) on the day-start status; D's result from the mailbox ----
+    if (in_set(M_INF, st)) {
+        atomicAdd(&s_cnt[9], 1u);
+        if (ti >= c.adm_min && ti <= c.adm_max) {                            // :205 window on the ABSOLUTE infection day
+            const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
+            if (__ldg(c.p_adm + a) > u) { x = ST_H; c.t_adm[a] = (int16_t)day; atomicAdd(&s_ev[EV_ADM], 1u); }   // :213-216
+        }
+    } else if (st == ST_H) {
+        if (c.t_adm[a] >= c.death_min) {                                     // :219
+            const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
+            if (__ldg(c.p_death + a) > u) { x = ST_X; c.t_adm[a] = 0; atomicAdd(&s_ev[EV_DEATH], 1u); }          // :225-227, :259
+        }
+    } else if (in_set(M_SUS, st)) {
+        atomicAdd(&s_cnt[8], 1u);
+        infector = c.src[a];
+        if (infector >= 0) {                                                 // :241-248: k_push found an infector
+            x = (st == ST_S) ? ST_I : ST_QI;
+            ti = day; w_ti = true;
+            infected_today = true;
+        }
+    }
+    // ---- E: the ordered rules of contagious3.py:250-259 ----
+    const int n_inf = day - ti, n_q = day - tq;
+    if (x == ST_QH && n_q == c.quarantine) x = ST_S;                                        // :250
+    if (x == ST_QI && n_q == c.quarantine) x = ST_I;                                        // :252
+    if (x == ST_I && n_inf == c.diagnosis) { tq = day; w_tq = true; }                       // :253
+    if ((x == ST_I || x == ST_QI) && n_inf == c.diagnosis) x = ST_D;                        // :254
+    if (x == ST_D && n_inf == c.recover) x = ST_R;                                          // :255
+    if (x == ST_H && n_inf == c.hospital_recover) { x = ST_R; c.t_adm[a] = 0; }             // :256, :259
+    if (x == ST_D && n_inf == c.diagnosis) atomicAdd(&s_ev[EV_NEW_DIAG], 1u);               // :261
+    // ---- F (contagious3.py:261-270): the households diagnosed today were flagged yesterday ----
+    if (any_nd && (x == ST_S || x == ST_I)) {
+        const int h = __ldg(c.hh + a);
+        bool hit = __ldg(c.hh_flag + h);                                                    // :263
+        if (x == ST_I && !hit) hit = __ldg(c.hh_qflag + h) || (c.hh_always && __ldg(c.hh_always + h));   // :267 whole-row isin
+        if (hit && c.compliance < 1.0)
+            hit = keyed_uniform(c.seed, day, STREAM_COMPLIANCE, (uint32_t)(c.lo + a), 0) < c.compliance;
+        if (hit) { x = (x == ST_S) ? ST_QH : ST_QI; tq = day; w_tq = true; }                // :265-270
+    }
+    if (w_ti) c.t_inf[a] = (int16_t)ti;
+    if (w_tq) c.t_q[a] = (int16_t)tq;
+    if (x != st) { c.status[a] = (uint8_t)x; atomicAdd(&s_ev[EV_CHANGED], 1u); }
+    if (in_set(M_ISO, x) && tq == day) atomicAdd(&s_ev[EV_DAILY_QUAR], 1u);
+    // ---- G: this agent's share of the integer statistics (contagious3.py:273-366) ----
+    atomicAdd(&s_cnt[hist_idx(x)], 1u);
+    if (in_set(M_EVER, x)) {
+        const int k = day - ti;
+        if (k >= 0 && k < HIST_LEN) {
+            if (k == 0) atomicAdd(&s_ev[EV_DAILY_INF], 1u);
+            atomicAdd(&s_hist[k], 1u);
+            if (c.sa_hist) { const int sa = __ldg(c.sa + a); if (sa >= 0) atomicAdd(&c.sa_hist[(size_t)sa * HIST_LEN + k], 1); }
+            if (c.io_mat && infected_today) {
+                // contagious3.py:356-366: row = area of today's infected, column = area of the infector
+                const int sa_u = __ldg(c.sa + a), sa_i = __ldg(c.sa + (infector - c.lo));
+                if (sa_u >= 0 && sa_i >= 0) atomicAdd(&c.io_mat[(size_t)sa_u * c.S + sa_i], 1);
+            }
+        }
+        if (c.bcount && in_set(M_INF, x)) atomicAdd(&c.bcount[__ldg(c.home + a)], 1);
+    }
+    // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
+    c.ib[c.lo + a] = infectious_byte(x, day + 1, ti);
+    if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.hh_flag_next, c.hh_qflag_next, c.df_next);
+}
 
 template <int VARIANT>   // 0 = product; 1, 2 = tools/kbench.cu ablations (no fold / no reduction at all)
 __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
 {
     __shared__ unsigned int s_hist[HIST_LEN];
     __shared__ unsigned int s_ev[EV_LEN];
-    __shared__ unsigned int s_cnt[10];            // 8 status counts, sus0, inf0
+    __shared__ unsigned int s_cnt[10];            // 8 end-of-day status counts (hist_idx order), sus0, inf0
+    __shared__ unsigned int s_nlist;
+    __shared__ unsigned short s_list[AGENT_TILE];
     __shared__ long long s_fold[N_STATS];
     __shared__ bool s_last;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < HIST_LEN) s_hist[threadIdx.x] = 0;
-    if (threadIdx.x < EV_LEN) s_ev[threadIdx.x] = 0;
-    if (threadIdx.x < 10) s_cnt[threadIdx.x] = 0;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    if (tid < HIST_LEN) s_hist[tid] = 0;
+    if (tid < EV_LEN) s_ev[tid] = 0;
+    if (tid < 10) s_cnt[tid] = 0;
+    if (tid == 0) s_nlist = 0;
     __syncthreads();
     const bool any_nd = c.df[DF_ANY_ND] != 0;
-    const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    uint32_t h_end[2] = {0, 0}, h_start = 0;      // h_start: sus0 | inf0 << 8
-    uint32_t ev_mask = 0;
-    int4 src4 = make_int4(-1, -1, -1, -1);
-    if (a0 < c.n_pad) {
+    const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN;   // a recovered agent left the histogram
+    const int64_t tile0 = (int64_t)blockIdx.x * AGENT_TILE;
+    const int64_t a0 = tile0 + tid * 4;
+
+    // ---- sweep ----
+    {
         const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
         const uint32_t st0[4] = {sv.x, sv.y, sv.z, sv.w};
-        uint32_t m_sus = 0, m_need_ti = 0, m_iso = 0, m_h = 0;
+        uint32_t m_s = 0, m_f = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            m_sus |= in_set(M_SUS, st0[j]) << j;
-            m_need_ti |= in_set(M_EVER, st0[j]) << j;
-            m_iso |= in_set(M_ISO, st0[j]) << j;
-            m_h |= (st0[j] == ST_H) << j;
+            m_s |= (uint32_t)(st0[j] == ST_S) << j;
+            m_f |= (uint32_t)(st0[j] == ST_S) << j;
         }
-        short4 ti4 = make_short4(0, 0, 0, 0), tq4 = make_short4(0, 0, 0, 0), ta4 = make_short4(0, 0, 0, 0);
-        if (m_need_ti) ti4 = *reinterpret_cast<const short4*>(c.t_inf + a0);
-        if (m_iso) tq4 = *reinterpret_cast<const short4*>(c.t_q + a0);
-        if (m_h) ta4 = *reinterpret_cast<const short4*>(c.t_adm + a0);
-        if (m_sus) src4 = *reinterpret_cast<const int4*>(c.src + a0);        // the mailbox k_push wrote into
-        int ti[4] = {ti4.x, ti4.y, ti4.z, ti4.w}, tq[4] = {tq4.x, tq4.y, tq4.z, tq4.w}, ta[4] = {ta4.x, ta4.y, ta4.z, ta4.w};
+        int4 src4 = make_int4(-1, -1, -1, -1);
+        if (m_s) src4 = *reinterpret_cast<const int4*>(c.src + a0);          // the mailbox k_push wrote into
         const int srcv[4] = {src4.x, src4.y, src4.z, src4.w};
-        uint32_t s[4];
-        bool w_st = false;
-        uint32_t w_ti = 0, w_tq = 0, w_ta = 0;     // per-agent write masks (columns are only loaded when needed)
-        uint32_t ibw = 0;                          // tomorrow's four snapshot bytes
-        // F needs the household flags of agents that can be in status 1 or 2 after E: fetch all four up front so
-        // the gathers overlap instead of serialising behind each agent's rules
-        uint32_t hflag[4] = {0, 0, 0, 0};          // bit0 household diagnosed today, bit1 quirk household
-        if (any_nd) {
-            uint32_t m_f = 0;
+        uint32_t flagged = 0;                      // susceptible agents whose household sees a diagnosis today
+        if (any_nd && m_f) {
+            const int4 hh4 = __ldg(reinterpret_cast<const int4*>(c.hh + a0));
+            const int hv[4] = {hh4.x, hh4.y, hh4.z, hh4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) m_f |= in_set(M_F, st0[j]) << j;
-            if (m_f) {
-                const int4 hh4 = __ldg(reinterpret_cast<const int4*>(c.hh + a0));
-                const int hv[4] = {hh4.x, hh4.y, hh4.z, hh4.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((m_f >> j) & 1u) {
-                        uint32_t f = __ldg(c.hh_flag + hv[j]);
-                        f |= (uint32_t)(__ldg(c.hh_qflag + hv[j]) | (c.hh_always ? __ldg(c.hh_always + hv[j]) : 0)) << 1;
-                        hflag[j] = f;
-                    }
-            }
+            for (int j = 0; j < 4; ++j)
+                if ((m_f >> j) & 1u) flagged |= (uint32_t)(__ldg(c.hh_flag + hv[j]) != 0) << j;
         }
+        uint32_t work = 0, n_idle_s = 0, n_idle_r = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t st = st0[j];
-            s[j] = st;
-            if (st == ST_PAD) continue;
-            const bool sus = (m_sus >> j) & 1u;
-            h_start += sus ? 1u : (in_set(M_INF, st) ? 0x100u : 0u);
-            // nothing can happen to: a susceptible agent nobody infected whose household is not flagged; recovered; dead
-            const bool idle = (st == ST_S) ? (srcv[j] < 0 && !any_nd) : (st == ST_R || st == ST_X);
-            uint32_t x = st;
-            if (!idle) {
-                const int64_t a = a0 + j;
-                // ---- B, C (contagious3.py:205-227) on the day-start status; D's result from the mailbox ----
-                if (in_set(M_INF, st)) {
-                    if (ti[j] >= c.adm_min && ti[j] <= c.adm_max) {              // :205 window on the ABSOLUTE infection day
-                        const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
-                        if (__ldg(c.p_adm + a) > u) { x = ST_H; ta[j] = day; w_ta |= 1u << j; atomicAdd(&s_ev[EV_ADM], 1u); }  // :213-216
-                    }
-                } else if (st == ST_H) {
-                    if (ta[j] >= c.death_min) {                                   // :219
-                        const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
-                        if (__ldg(c.p_death + a) > u) { x = ST_X; ta[j] = 0; w_ta |= 1u << j; atomicAdd(&s_ev[EV_DEATH], 1u); }  // :225-227, :259
-                    }
-                } else if (sus && srcv[j] >= 0) {                                 // :241-248: k_push found an infector
-                    x = (st == ST_S) ? ST_I : ST_QI;
-                    ti[j] = day; w_ti |= 1u << j;
-                    ev_mask |= 1u << j;
-                }
-                // ---- E: the ordered rules of contagious3.py:250-259 ----
-                const int n_inf = day - ti[j], n_q = day - tq[j];
-                if (x == ST_QH && n_q == c.quarantine) x = ST_S;                                        // :250
-                if (x == ST_QI && n_q == c.quarantine) x = ST_I;                                        // :252
-                if (x == ST_I && n_inf == c.diagnosis) { tq[j] = day; w_tq |= 1u << j; }              // :253
-                if ((x == ST_I || x == ST_QI) && n_inf == c.diagnosis) x = ST_D;                        // :254
-                if (x == ST_D && n_inf == c.recover) x = ST_R;                                          // :255
-                if (x == ST_H && n_inf == c.hospital_recover) { x = ST_R; ta[j] = 0; w_ta |= 1u << j; } // :256, :259
-                if (x == ST_D && n_inf == c.diagnosis) atomicAdd(&s_ev[EV_NEW_DIAG], 1u);               // :261
-                // ---- F (contagious3.py:261-270): the households diagnosed today were flagged yesterday ----
-                if (any_nd && (x == ST_S || x == ST_I)) {
-                    bool hit = hflag[j] & 1u;                                                           // :263
-                    if (x == ST_I && !hit) hit = hflag[j] >> 1;                                         // :267 whole-row isin
-                    if (hit && c.compliance < 1.0)
-                        hit = keyed_uniform(c.seed, day, STREAM_COMPLIANCE, (uint32_t)(c.lo + a), 0) < c.compliance;
-                    if (hit) { x = (x == ST_S) ? ST_QH : ST_QI; tq[j] = day; w_tq |= 1u << j; }         // :265-270
-                }
-                s[j] = x;
-                if (x != st) { w_st = true; atomicAdd(&s_ev[EV_CHANGED], 1u); }
-                if (in_set(M_ISO, x) && tq[j] == day) atomicAdd(&s_ev[EV_DAILY_QUAR], 1u);
-                // tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow
-                ibw |= (uint32_t)infectious_byte(x, day + 1, ti[j]) << (8 * j);
-                if (diagnosed_on(c, nullptr, a, x, ti[j], day + 1))
-                    raise_household(c, a, c.hh_flag_next, c.hh_qflag_next, c.df_next);
-            }
-            // ---- G: integer statistics of the end-of-day state (contagious3.py:273-366) ----
-            hist_add(h_end, x);
-            if (in_set(M_EVER, x)) {
-                const int k = day - ti[j];
-                if (k >= 0 && k < HIST_LEN) {
-                    const int64_t a = a0 + j;
-                    if (k == 0) atomicAdd(&s_ev[EV_DAILY_INF], 1u);
-                    atomicAdd(&s_hist[k], 1u);
-                    if (c.sa_hist) { const int sa = c.sa[a]; if (sa >= 0) atomicAdd(&c.sa_hist[(size_t)sa * HIST_LEN + k], 1); }
-                    if (c.io_mat && ((ev_mask >> j) & 1u)) {
-                        // contagious3.py:356-366: row = area of today's infected, column = area of the infector
-                        const int sa_u = c.sa[a], sa_i = c.sa[srcv[j] - c.lo];
-                        if (sa_u >= 0 && sa_i >= 0) atomicAdd(&c.io_mat[(size_t)sa_u * c.S + sa_i], 1);
-                    }
-                }
-                if (c.bcount && in_set(M_INF, x)) atomicAdd(&c.bcount[c.home[a0 + j]], 1);
+            const bool idle_s = (st == ST_S) && srcv[j] < 0 && !((flagged >> j) & 1u);
+            const bool idle_r = (st == ST_R) && r_idle;
+            n_idle_s += idle_s;
+            n_idle_r += idle_r;
+            work |= (uint32_t)(!idle_s && !idle_r && st != ST_PAD) << j;
+        }
+        // idle agents: end-of-day status == day-start status; their snapshot byte is 0
+        if (VARIANT != 2) {
+            const uint32_t packed = n_idle_s | (n_idle_r << 8);
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, packed);
+            if (lane == 0 && tot) {
+                if (tot & 0xFFu) { atomicAdd(&s_cnt[1], tot & 0xFFu); atomicAdd(&s_cnt[8], tot & 0xFFu); }
+                if (tot >> 8) atomicAdd(&s_cnt[6], tot >> 8);
             }
         }
-        *reinterpret_cast<uint32_t*>(c.ib + c.lo + a0) = ibw;
-        if (w_st) *reinterpret_cast<uchar4*>(c.status + a0) = make_uchar4(s[0], s[1], s[2], s[3]);
+        // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
+        *reinterpret_cast<uint32_t*>(c.ib + c.lo + a0) = 0u;
+        // compact the agents that need the settle phase
+        const int mine = __popc(work);
+        const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+        if (any) {
+            int incl = mine;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {              // rare, and only the agents that changed (their neighbours' columns may not be loaded)
-            if ((w_ti >> j) & 1u) c.t_inf[a0 + j] = (int16_t)ti[j];
-            if ((w_tq >> j) & 1u) c.t_q[a0 + j] = (int16_t)tq[j];
-            if ((w_ta >> j) & 1u) c.t_adm[a0 + j] = (int16_t)ta[j];
-        }
-    }
-    // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
-    const unsigned any_ev = __ballot_sync(0xffffffffu, ev_mask != 0);
-    if (any_ev) {
-        const int mine = __popc(ev_mask);
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) atomicAdd(&s_ev[EV_EVENTS], (unsigned)incl);
-        if (c.ev) {
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
             int base = 0;
-            if (lane == 31) base = atomicAdd(&c.df[DF_N_EVENTS], incl);
+            if (lane == 31) base = (int)atomicAdd(&s_nlist, (unsigned)incl);
             base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-            const int srcv[4] = {src4.x, src4.y, src4.z, src4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if ((ev_mask >> j) & 1u) {
-                    c.ev[base++] = make_int2((int)(c.lo + a0 + j), srcv[j]);
-                }
-        }
-    }
-    if (VARIANT == 2) return;
-    // ---- block reduction: packed histograms by REDUX, then one global atomic per non-zero counter ----
-    {
-        const uint32_t e0 = __reduce_add_sync(0xffffffffu, h_end[0]), e1 = __reduce_add_sync(0xffffffffu, h_end[1]);
-        const uint32_t b0 = __reduce_add_sync(0xffffffffu, h_start);
-        if (lane < 10) {
-            const uint32_t w = lane < 4 ? e0 : (lane < 8 ? e1 : b0);
-            const uint32_t v = (w >> (8 * (lane & 3))) & 0xFFu;
-            if (v) atomicAdd(&s_cnt[lane], v);
+                if ((work >> j) & 1u) s_list[base++] = (unsigned short)(tid * 4 + j);
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+
+    // ---- settle ----
+    const int n_list = (int)s_nlist;
+    for (int k0 = 0; k0 < n_list; k0 += 256) {
+        const int k = k0 + tid;
+        const bool valid = k < n_list;
+        bool infected_today = false;
+        int infector = -1;
+        int64_t a = 0;
+        if (valid) {
+            a = tile0 + s_list[k];
+            settle_agent(c, day, a, any_nd, s_cnt, s_ev, s_hist, infected_today, infector);
+        }
+        // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
+        const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
+        if (evm) {
+            if (lane == 0) atomicAdd(&s_ev[EV_EVENTS], (unsigned)__popc(evm));
+            if (c.ev) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (infected_today) c.ev[base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+            }
+        }
+    }
+    if (VARIANT == 2) return;
+    __syncthreads();
+    if (tid < 32) {
         // warp 0 publishes everything, fences, and takes the ticket
         const int slot = blockIdx.x & (N_SLOTS - 1);
         if (lane < 10 && s_cnt[lane])
             atomicAdd(&c.part[(size_t)(RAW_END + lane) * N_SLOTS + slot], (unsigned long long)s_cnt[lane]);
         if (lane < EV_LEN && s_ev[lane]) {
-            const int idx[EV_LEN] = {ST_DAILY_HOSP, ST_DAILY_DEATHS, ST_DAILY_INF, ST_DAILY_QUAR, ST_NEW_DIAG, ST_N_EVENTS, ST_CHANGED};
-            atomicAdd(&c.part[(size_t)idx[lane] * N_SLOTS + slot], (unsigned long long)s_ev[lane]);
+            const int row = lane == EV_ADM ? ST_DAILY_HOSP : lane == EV_DEATH ? ST_DAILY_DEATHS : lane == EV_DAILY_INF ? ST_DAILY_INF
+                          : lane == EV_DAILY_QUAR ? ST_DAILY_QUAR : lane == EV_NEW_DIAG ? ST_NEW_DIAG : lane == EV_EVENTS ? ST_N_EVENTS
+                          : ST_CHANGED;
+            atomicAdd(&c.part[(size_t)row * N_SLOTS + slot], (unsigned long long)s_ev[lane]);
         }
         if (lane < HIST_LEN && s_hist[lane])
             atomicAdd(&c.part[(size_t)(HIST0 + lane) * N_SLOTS + slot], (unsigned long long)s_hist[lane]);
@@ -346,7 +443,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
         unsigned long long t[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            unsigned long long* p = c.part + (size_t)((threadIdx.x >> 5) + 8 * q) * N_SLOTS;
+            unsigned long long* p = c.part + (size_t)((tid >> 5) + 8 * q) * N_SLOTS;
             t[q] = __ldcg(p + lane) + __ldcg(p + lane + 32);
             p[lane] = 0ull;
             p[lane + 32] = 0ull;
@@ -355,13 +452,13 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
         for (int q = 0; q < 8; ++q) {
 #pragma unroll
             for (int o = 16; o; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
-            if (lane == 0) s_fold[(threadIdx.x >> 5) + 8 * q] = (long long)t[q];
+            if (lane == 0) s_fold[(tid >> 5) + 8 * q] = (long long)t[q];
         }
         __syncthreads();
-        if (threadIdx.x < N_STATS) {
+        if (tid < N_STATS) {
             const long long* r = s_fold + RAW_END;        // QI S I QH D H R X
-            long long v = s_fold[threadIdx.x];
-            switch (threadIdx.x) {
+            long long v = s_fold[tid];
+            switch (tid) {
                 case ST_ACTIVE: v = r[2] + r[0] + r[4] + r[5]; break;
                 case ST_RECOVERED: v = r[6]; break;
                 case ST_QUARANTINED: v = r[3] + r[0] + r[4]; break;
@@ -380,10 +477,10 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
                 case ST_COUNT0 + 7: v = r[7]; break;
                 default: break;
             }
-            if (threadIdx.x >= RAW_END) v = 0;
-            c.stats[threadIdx.x] = v;
+            if (tid >= RAW_END) v = 0;
+            c.stats[tid] = v;
         }
-        if (threadIdx.x == 0) *c.ticket = 0u;
+        if (tid == 0) *c.ticket = 0u;
     }
 }
 

@@ -51,7 +51,25 @@ int main(int argc, char** argv)
     c.part = dalloc<unsigned long long>(64 * 64); c.stats = dalloc<int64_t>(64); c.ticket = dalloc<unsigned int>(1);
     c.sa_hist = dalloc<int32_t>(c.S * 21); c.bcount = dalloc<int32_t>(c.B);
     c.ev = dalloc<int2>(N);
-    c.tptr = dalloc<int64_t>(N + 1); c.tcolx = dalloc<uint32_t>(16); c.tval = dalloc<double>(16);
+    {   // a synthetic transposed network: 17 entries per column, rows within +-300 of the column (same community)
+        const int D = 17;
+        std::vector<int64_t> tp(N + 1);
+        std::vector<uint32_t> tc((size_t)N * D + 16);
+        std::vector<double> tv((size_t)N * D + 2, 0.97);
+        for (int64_t i = 0; i <= N; ++i) tp[i] = i * D;
+        for (int64_t i = 0; i < N; ++i)
+            for (int k = 0; k < D; ++k) {
+                int64_t u = i + (rand() % 601) - 300;
+                if (u < 0) u = 0; if (u >= N) u = N - 1;
+                tc[(size_t)i * D + k] = (uint32_t)u | ((rand() % 5 == 0 ? 1u : 0u) << 28);
+            }
+        int64_t* dp = dalloc<int64_t>(N + 1); cudaMemcpy(dp, tp.data(), 8 * (N + 1), cudaMemcpyHostToDevice); c.tptr = dp;
+        uint32_t* dc = dalloc<uint32_t>(tc.size()); cudaMemcpy(dc, tc.data(), 4 * tc.size(), cudaMemcpyHostToDevice); c.tcolx = dc;
+        double* dv = dalloc<double>(tv.size()); cudaMemcpy(dv, tv.data(), 8 * tv.size(), cudaMemcpyHostToDevice); c.tval = dv;
+        std::vector<double> rk(N, 0.1); cudaMemcpy((void*)c.risk, rk.data(), 8 * N, cudaMemcpyHostToDevice);
+        std::vector<double> pdf(64, 0.1); cudaMemcpy((void*)c.pdf, pdf.data(), 8 * 64, cudaMemcpyHostToDevice);
+        c.norm_factor = 1e-6;       // Bernoulli successes are rare: the mailbox stays (almost) untouched between launches
+    }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto timeit = [&](const char* name, auto launch) {
         for (int i = 0; i < 5; ++i) launch(i);
@@ -74,7 +92,12 @@ int main(int argc, char** argv)
     timeit("k_agent no reduction", [&](int d) { k_agent_noreduce<<<g4, 256>>>(c, d); });
     timeit("k_snapshot", [&](int d) { k_snapshot<<<g4, 256>>>(c, d, f0, f1, df); });
     int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, 256, 0);
-    timeit("k_push (empty rows)", [&](int d) { k_push<<<148 * per_sm, 256>>>(c, d); });
+    {   // snapshot bytes for the infectious agents
+        std::vector<uint8_t> ibh(N + 2048, 0);
+        for (int64_t a = 0; a < N; ++a) if (st[a] == ST_I) ibh[a] = 0x80 | 3;
+        cudaMemcpy(c.ib, ibh.data(), N, cudaMemcpyHostToDevice);
+    }
+    timeit("k_push", [&](int d) { k_push<<<148 * per_sm, 256>>>(c, d); });
     printf("push blocks/SM %d\n", per_sm);
     return 0;
 }
