@@ -72,7 +72,20 @@ def _banded_normal(r, age, table):
     return np.maximum(out, 0.0)
 
 
-def _community_agents(L, c):
+def _anchors(L, c):
+    """Anchor buildings (GLOBAL indices, -1 = none) of community c's agents before commuting is applied: non-residential
+    buildings with heavy-tailed popularity (the largest gets ~10 % of the community)."""
+    n, nb, nres, b0 = int(L.size[c]), int(L.nb[c]), int(L.nres[c]), int(L.b0[c])
+    r = _rng(L.seed, c, 4)
+    nnr = nb - nres
+    w = 1.0 / (np.arange(nnr) + 3.0)
+    w /= w.sum()
+    a1 = np.where(r.random(n) < 0.845, b0 + nres + r.choice(nnr, size=n, p=w), -1)
+    a2 = np.where(r.random(n) < 0.5, b0 + nres + r.choice(nnr, size=n, p=w), -1)
+    return a1, a2
+
+
+def _community_agents(L, c, degree=14, cross=0.02):
     """Static per-agent columns and routines of community c (local arrays, global indices)."""
     n, nb, nres, ns = int(L.size[c]), int(L.nb[c]), int(L.nres[c]), int(L.ns[c])
     a0, b0, s0, h0 = int(L.a0[c]), int(L.b0[c]), int(L.s0[c]), int(L.h0[c])
@@ -90,13 +103,18 @@ def _community_agents(L, c):
     risk = _banded_normal(r, age, INFECTION)
     p_adm = _banded_normal(r, age, ADMISSION)
     p_death = _banded_normal(r, age, MORTALITY)
-    # anchors: non-residential buildings, heavy-tailed popularity (largest ~10 % of the community)
-    nnr = nb - nres
-    w = 1.0 / (np.arange(nnr) + 3.0)
-    w /= w.sum()
-    anchor1 = np.where(r.random(n) < 0.845, nres + r.choice(nnr, size=n, p=w), -1)
-    anchor2 = np.where(r.random(n) < 0.5, nres + r.choice(nnr, size=n, p=w), -1)
-    anchors = np.stack([anchor1, anchor2, home_local], axis=1)                   # agents_reg[:, 2:] of contagious3.py:131
+    anchor1, anchor2 = _anchors(L, c)
+    if c + 1 < L.C and cross > 0:
+        # commuters: an agent with a contact in the next community works where that contact works, so cross-community
+        # (and, when sharded, cross-GPU) contacts really meet in a building
+        u, v, _ = _community_contacts(L, c, degree, cross)
+        far = v >= a0 + n
+        nxt_a1, _ = _anchors(L, c + 1)
+        uu, vv = u[far] - a0, v[far] - int(L.a0[c + 1])
+        ok = nxt_a1[vv] >= 0
+        anchor1 = anchor1.copy()
+        anchor1[uu[ok]] = nxt_a1[vv[ok]]
+    anchors = np.stack([anchor1, anchor2, home_local + b0], axis=1)              # agents_reg[:, 2:] of contagious3.py:131
     # flexible stops: k = 2 per anchor, each taken with probability 1/2, uniform over nearby buildings; a few
     # stops land in the next community so shards are genuinely coupled
     routine = np.full((n, V), -1, dtype=np.int64)
@@ -114,7 +132,7 @@ def _community_agents(L, c):
             routine[idx, fill[idx]] = stop[idx]
             fill[idx] += 1
         idx = np.nonzero(has)[0]
-        routine[idx, fill[idx]] = anchors[idx, j] + b0
+        routine[idx, fill[idx]] = anchors[idx, j]
         fill[idx] += 1
     return dict(n=n, hh=hh_local + h0, home=home_local + b0, sa=bld_area[home_local] + s0, risk=risk, p_adm=p_adm,
                 p_death=p_death, routine=routine.astype(np.int32), bld_area=bld_area + s0, age=age)
@@ -146,7 +164,7 @@ def synth_population(n_agents, seed=0, degree=14, cross=0.02, communities=None, 
     L = Layout(n_agents, seed)
     c_lo, c_hi = (0, L.C) if communities is None else communities
     h_lo, h_hi = max(0, c_lo - 1), min(L.C, c_hi + 1)
-    parts = {c: _community_agents(L, c) for c in range(h_lo, h_hi)}
+    parts = {c: _community_agents(L, c, degree, cross) for c in range(h_lo, h_hi)}
     own = [parts[c] for c in range(c_lo, c_hi)]
     cat = lambda k, dt: np.concatenate([p[k] for p in own]).astype(dt)
     lo, hi = int(L.a0[c_lo]), int(L.a0[c_hi])

@@ -111,17 +111,38 @@ typedef struct {
     int32_t* bld_infected;           /* [B] or NULL */
     int32_t *ev_agent, *ev_src;      /* [N] or NULL: today's infections in ascending agent order */
     double* pair_prob;               /* [N*N] or NULL: P written for every evaluated (u,i) pair (tests) */
+    /* sharded populations: this context owns global agents [lo, lo+N) of n_glob; `routine` covers global agents from
+     * rt_lo; interaction_prob columns, src, the random keys and the events are GLOBAL indices.  ib_global (when not
+     * NULL) is the all-gathered day-start infectious byte of every agent: bit7 infectious (status 2/3.5/4), bit6
+     * isolated (3.5/4), bits0-5 days since infection -- the only thing a day needs to know about a remote agent. */
+    int64_t lo, n_glob, rt_lo;
+    const uint8_t* ib_global;
 } orc_ctx;
 
 enum { O_ACTIVE, O_DAILY_INF, O_RECOVERED, O_QUARANTINED, O_DAILY_QUAR, O_HOSP, O_DAILY_HOSP, O_DEAD, O_DAILY_DEATHS,
        O_EVER_INFECTED, O_NEW_DIAG, O_N_EVENTS, O_SUS0, O_INF0, O_EDGES_SCANNED, O_CANDIDATES, O_EXPOSED, O_HITS };
 
-static int eff_list(const orc_ctx* c, int64_t a, uint8_t st0, int32_t* out)
+static uint8_t snapshot_byte(uint8_t st, int day, int t_inf)
+{
+    if (!(st == ST_I || st == ST_QI || st == ST_D)) return 0;
+    int n = day - t_inf;
+    if (n < 0) n = 0;
+    if (n > 63) n = 63;
+    return (uint8_t)(0x80 | (st != ST_I ? 0x40 : 0) | n);
+}
+
+/* day-start infectious bytes of the owned agents (what a shard contributes to the per-day exchange) */
+void orc_snapshot(const orc_ctx* c, int32_t day, uint8_t* out)
+{
+    for (int64_t a = 0; a < c->N; ++a) out[a] = snapshot_byte(c->status[a], day, c->t_inf[a]);
+}
+
+/* a = row of the routine table (global agent index - rt_lo); gone = admitted or dead; iso = keeps only the home slot */
+static int eff_list(const orc_ctx* c, int64_t a, int gone, int iso, int32_t* out)
 {
     /* contagious3.py:181-189: closed buildings removed; isolated agents keep slot 0; admitted/dead keep nothing */
     int n = 0;
-    if (st0 == ST_H || st0 == ST_X) return 0;
-    int iso = (st0 == ST_QH || st0 == ST_QI || st0 == ST_D);
+    if (gone) return 0;
     for (int s = 0; s < c->V; ++s) {
         int32_t b = c->routine[a * c->V + s];
         if (b < 0) continue;
@@ -148,11 +169,11 @@ int orc_day(orc_ctx* c, int32_t day)
         n_inf0 += inf0;
         n_sus0 += (s == ST_S || s == ST_QH);
         if (inf0 && c->t_inf[a] >= c->adm_min_day && c->t_inf[a] <= c->adm_max_day) {
-            double u = c->u_adm ? c->u_adm[a] : orc_keyed_uniform(c->seed, day, 0, (uint32_t)a, 0);
+            double u = c->u_adm ? c->u_adm[c->lo + a] : orc_keyed_uniform(c->seed, day, 0, (uint32_t)(c->lo + a), 0);
             if (c->p_adm[a] > u) { c->status[a] = ST_H; c->t_adm[a] = day; ++n_adm; }
         }
         if (s == ST_H && c->t_adm[a] >= c->death_min_adm_day) {
-            double u = c->u_death ? c->u_death[a] : orc_keyed_uniform(c->seed, day, 1, (uint32_t)a, 0);
+            double u = c->u_death ? c->u_death[c->lo + a] : orc_keyed_uniform(c->seed, day, 1, (uint32_t)(c->lo + a), 0);
             if (c->p_death[a] > u) { c->status[a] = ST_X; ++n_death; }
         }
     }
@@ -164,28 +185,37 @@ int orc_day(orc_ctx* c, int32_t day)
         uint8_t su = st0[u];
         if (!(su == ST_S || su == ST_QH)) continue;
         int32_t eu[16], ei[16];
-        int nu = eff_list(c, u, su, eu);
+        const int64_t ug = c->lo + u;
+        int nu = eff_list(c, ug - c->rt_lo, 0, su == ST_QH, eu);
         int32_t best = -1;
         for (int64_t e = c->rowptr[u]; e < c->rowptr[u + 1]; ++e) {
-            int32_t i = c->col[e];
+            int32_t i = c->col[e];                       /* GLOBAL index of the column agent */
             ++scanned;
-            uint8_t si = st0[i];
-            if (!(si == ST_I || si == ST_QI || si == ST_D)) continue;
+            int inf_i, iso_i, n_inf;
+            if (c->ib_global) {
+                uint8_t b = c->ib_global[i];
+                inf_i = b & 0x80; iso_i = (b & 0x40) != 0; n_inf = b & 63;
+            } else {
+                uint8_t si = st0[i];
+                inf_i = (si == ST_I || si == ST_QI || si == ST_D);
+                iso_i = (si == ST_QI || si == ST_D);
+                n_inf = day - c->t_inf[i];
+                if (n_inf > 63) n_inf = 63;
+            }
+            if (!inf_i) continue;
             ++cand;
-            int ni = eff_list(c, i, si, ei), share = 0;
+            int ni = eff_list(c, (int64_t)i - c->rt_lo, 0, iso_i, ei), share = 0;
             for (int x = 0; x < nu && !share; ++x)
                 for (int y = 0; y < ni; ++y)
                     if (eu[x] == ei[y]) { share = 1; break; }
-            int n_inf = day - c->t_inf[i];
-            if (n_inf > 63) n_inf = 63;
             double p = c->val[e] * c->risk[u];          /* :232-233 */
             p = p * c->pdf[n_inf];                      /* :234 */
             p = p * (share ? 1.0 : 0.0);                /* :237 */
             p = p * c->norm_factor;                     /* :238 */
-            if (c->pair_prob) c->pair_prob[u * N + i] = p;
+            if (c->pair_prob) c->pair_prob[ug * c->n_glob + i] = p;
             if (!share) continue;
             ++expo;
-            double r = c->u_pair ? c->u_pair[u * N + i] : orc_keyed_uniform(c->seed, day, 2, (uint32_t)u, (uint32_t)i);
+            double r = c->u_pair ? c->u_pair[ug * c->n_glob + i] : orc_keyed_uniform(c->seed, day, 2, (uint32_t)ug, (uint32_t)i);
             if (p > r) { ++hits; if (i > best) best = i; }   /* :240, :248 last writer = largest index */
         }
         if (best >= 0) {
@@ -226,7 +256,7 @@ int orc_day(orc_ctx* c, int32_t day)
             int32_t h = c->hh[a];
             uint8_t s = c->status[a];
             int obey = 1;
-            if (c->compliance < 1.0) obey = orc_keyed_uniform(c->seed, day, 3, (uint32_t)a, 0) < c->compliance;
+            if (c->compliance < 1.0) obey = orc_keyed_uniform(c->seed, day, 3, (uint32_t)(c->lo + a), 0) < c->compliance;
             if (s == ST_S && hh_hit[h] && obey) { c->status[a] = ST_QH; c->t_q[a] = day; }
             else if (s == ST_I && (hh_hit[h] || hh_quirk[h] || (c->hh_always && c->hh_always[h])) && obey) {
                 c->status[a] = ST_QI; c->t_q[a] = day;
@@ -260,7 +290,7 @@ int orc_day(orc_ctx* c, int32_t day)
         }
         if (c->bld_infected && (s == ST_I || s == ST_QI || s == ST_D)) c->bld_infected[c->home[a]] += 1;
         if (ever && c->t_inf[a] == day && st0[a] != s && (st0[a] == ST_S || st0[a] == ST_QH)) {
-            if (c->ev_agent) { c->ev_agent[nev] = (int32_t)a; c->ev_src[nev] = c->src[a]; }
+            if (c->ev_agent) { c->ev_agent[nev] = (int32_t)(c->lo + a); c->ev_src[nev] = c->src[a]; }
             ++nev;
         }
     }

@@ -43,6 +43,7 @@ class _Ctx(C.Structure):
         ("u_adm", C.c_void_p), ("u_death", C.c_void_p), ("u_pair", C.c_void_p),
         ("stats", C.c_void_p), ("sa_hist", C.c_void_p), ("bld_infected", C.c_void_p),
         ("ev_agent", C.c_void_p), ("ev_src", C.c_void_p), ("pair_prob", C.c_void_p),
+        ("lo", C.c_int64), ("n_glob", C.c_int64), ("rt_lo", C.c_int64), ("ib_global", C.c_void_p),
     ]
 
 
@@ -58,6 +59,7 @@ def lib():
         _lib.orc_keyed_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         _lib.orc_keyed_uniform.restype = C.c_double
         _lib.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_snapshot.argtypes = [C.POINTER(_Ctx), C.c_int32, C.c_void_p]
     return _lib
 
 
@@ -106,7 +108,7 @@ class OracleSim:
         self.bld_infected = np.zeros(pop.B, dtype=np.int32)
         self.ev_agent = np.zeros(pop.N, dtype=np.int32)
         self.ev_src = np.zeros(pop.N, dtype=np.int32)
-        self.pair_prob = np.zeros((pop.N, pop.N)) if capture_prob else None
+        self.pair_prob = np.zeros((pop.N_glob, pop.N_glob)) if capture_prob else None
         k = self._keep
         ctx = _Ctx()
         ctx.N, ctx.H, ctx.B, ctx.S, ctx.V = pop.N, pop.H, pop.B, pop.S, pop.V
@@ -123,6 +125,9 @@ class OracleSim:
         ctx.open = _p(self.open)
         ctx.stats, ctx.sa_hist, ctx.bld_infected = _p(self._stats), _p(self._sa_hist), _p(self.bld_infected)
         ctx.ev_agent, ctx.ev_src, ctx.pair_prob = _p(self.ev_agent), _p(self.ev_src), _p(self.pair_prob)
+        ctx.lo, ctx.n_glob, ctx.rt_lo = pop.lo, pop.N_glob, pop.halo[0]
+        ctx.ib_global = None
+        self._ib_global = None
         self.ctx = ctx
 
     def set_open(self, open_flags):
@@ -139,6 +144,22 @@ class OracleSim:
         if rc != 0:
             raise RuntimeError("orc_day failed")
         return self._stats.copy()
+
+    # sharded populations: the same two-half day as dys_step_begin / dys_step_end (include/dysturbd.h)
+    def step_begin(self, day):
+        self._ib_local = np.zeros(self.pop.N, dtype=np.uint8)
+        lib().orc_snapshot(C.byref(self.ctx), int(day), self._ib_local.ctypes.data)
+
+    def ib_local(self):
+        return self._ib_local
+
+    def set_ib_global(self, ib):
+        self._ib_global = np.ascontiguousarray(ib, dtype=np.uint8)
+        assert self._ib_global.size >= self.pop.N_glob
+        self.ctx.ib_global = self._ib_global.ctypes.data
+
+    def step_end(self, day):
+        return self.step(day)
 
     # the same read-out surface as dysturbd_b200.engine.Engine, so tests can drive either through one harness
     def stats(self, day=None):
