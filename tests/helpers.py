@@ -111,3 +111,77 @@ def compare_sims(a, b, days, open_fn=None):
         assert np.array_equal(a.building_counts(d), b.building_counts(d)), "building counts day %d" % d
         ea, eb = a.events(d), b.events(d)
         assert np.array_equal(ea[0], eb[0]) and np.array_equal(ea[1], eb[1]), "events day %d" % d
+
+
+# ---- config 1: the shipped city at full size (22 493 agents), literal reference run for 100 days ----
+REF_DIR = os.path.join(os.path.dirname(GOLDEN.rstrip("/")), "..", "oracle", "_ref")
+REF_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref"))
+CONFIG1_IP_CACHES = [os.path.join(REF_DIR, "local", "config1_ip_csr.npz"), "/tmp/dys_ref_local/config1_ip_csr.npz"]
+
+
+def config1_available():
+    return os.path.exists(os.path.join(REF_DIR, "config1_inputs.npz")) and \
+        os.path.exists(os.path.join(REF_DIR, "config1_noLockdown_golden.npz"))
+
+
+def config1_ip_cached():
+    return any(os.path.exists(p) for p in CONFIG1_IP_CACHES)
+
+
+def config1_interaction_prob(z, allow_recompute=True):
+    """interaction_prob of the shipped city as CSR.  The reference builds it from all-pairs shortest paths over the
+    communities.py graph (contagious3.py:124-130); agent->agent paths only run through agent nodes, so the same scipy
+    call on the shipped agent-agent edge list reproduces it BIT FOR BIT (verified against the reference's own matrix
+    when the fixture was generated: indptr, indices and data identical).  ~2 minutes, 4 GB."""
+    import scipy.sparse as sp
+    n = len(z["agents"])
+    for p in CONFIG1_IP_CACHES:
+        if os.path.exists(p):
+            c = np.load(p)
+            return sp.csr_matrix((c["data"], c["indices"], c["indptr"]), shape=(n, n))
+    if not allow_recompute:
+        return None
+    from scipy.sparse.csgraph import shortest_path
+    g = sp.csr_matrix((z["edge_w"], (z["edge_row"], z["edge_col"])), shape=(n, n))
+    d = shortest_path(g, directed=True, return_predecessors=False)
+    np.fill_diagonal(d, np.inf)
+    m = sp.csr_matrix(np.exp(-d))
+    del d
+    m.sort_indices()
+    try:
+        os.makedirs(os.path.dirname(CONFIG1_IP_CACHES[0]), exist_ok=True)
+        np.savez(CONFIG1_IP_CACHES[0], indptr=m.indptr.astype(np.int64), indices=m.indices.astype(np.int32), data=m.data)
+    except OSError:
+        pass
+    return m
+
+
+class Config1:
+    def __init__(self, allow_recompute=True):
+        z = np.load(os.path.join(REF_DIR, "config1_inputs.npz"))
+        g = np.load(os.path.join(REF_DIR, "config1_noLockdown_golden.npz"))
+        self.agents, self.build, self.visits = z["agents"], z["build"], z["bld_visits_by_agents"]
+        self.ip = config1_interaction_prob(z, allow_recompute)
+        self.pop = Population.from_reference(self.agents, self.build, self.visits, self.ip)
+        self.params = EpiParams(seed=int(g["philox_seed"]))
+        self.exp = {k: g[k] for k in ("status_x2", "t_inf", "t_q", "t_adm", "src_id", "open_next", "day_seconds")}
+        self.outputs = json.loads(str(g["outputs_json"]))
+        self.days = len(self.exp["status_x2"])
+        ids = {v: i for i, v in enumerate(self.pop.agent_ids)}
+        self._ids = ids
+
+    def expected_src(self, day):
+        return np.array([self._ids[v] if v != 0 else -1 for v in self.exp["src_id"][day]], dtype=np.int32)
+
+    def check_day(self, sim, d):
+        st = sim.state()
+        assert np.array_equal(st["status"], self.exp["status_x2"][d]), "status day %d" % d
+        for k in ("t_inf", "t_q", "t_adm"):
+            assert np.array_equal(st[k], self.exp[k][d]), "%s day %d" % (k, d)
+        assert np.array_equal(st["src"], self.expected_src(d)), "infector day %d" % d
+        S = self.outputs["Results"]["Stats"][str(d)]
+        s = sim.stats(d)
+        got = {"Active infected": s[0], "Daily infections": s[1], "Recovered": s[2], "Quarantined": s[3], "Daily quarantined": s[4],
+               "Hospitalized": s[5], "Daily hospitalizations": s[6], "Total Dead": s[7], "Daily deaths": s[8]}
+        for k, v in got.items():
+            assert S[k] == int(v), "%s day %d: %s != %s" % (k, d, S[k], v)
