@@ -37,11 +37,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--communities-per-gpu", type=int, default=89, help="89 x 11 264 = 1 002 496 agents per GPU")
-    ap.add_argument("--norm-factor", type=float, default=4.0)
+    ap.add_argument("--norm-factor", type=float, default=6.0,
+                    help="with the degree-16.7 synthetic network 6.0 gives a reference-like epidemic: peak near day 70, "
+                         "38 %% of the population infected, extinct near day 280")
     ap.add_argument("--seeds-per-22493", type=int, default=20)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused P2P stores of the snapshot bytes from k_agent (peer) or a per-day NCCL all-gather")
     return ap.parse_args()
 
 
@@ -144,29 +148,25 @@ def run_ours(args):
     prm = make_params(args)
     W, K = args.warmup, args.steps
     all_out = engine.WANT_SA_HIST | engine.WANT_BUILDING_COUNTS | engine.WANT_EVENTS
+    from dysturbd_b200.sharded import ShardedEngine
+
+    def make_engine(flags):
+        if world == 1:
+            return engine.Engine(pop, prm, device=local, flags=flags)
+        return ShardedEngine(pop, prm, device=local, mode=args.exchange, flags=flags)
+
+    def raw(e):                      # the ctypes Engine underneath
+        return e if world == 1 else e.sim
+
     t0 = time.perf_counter()
-    eng = engine.Engine(pop, prm, device=local, flags=all_out, rank=rank, world=world)
-    eng.sync()
+    eng = make_engine(all_out)
+    raw(eng).sync()
     load_s = time.perf_counter() - t0
-    stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=local)
+    stream = torch.cuda.ExternalStream(raw(eng).cuda_stream(), device=local)
     init = pop.copy_state()
 
-    ib_t = None
-    if world > 1:
-        ptr, nbytes = eng.device_buffer(engine.BUF_INFECTIOUS)
-
-        class _Cai:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-        ib_t = torch.as_tensor(_Cai(), device=torch.device("cuda", local))[:n_total]
-        shard = pop.N
-
     def day_step(e, day):
-        if world == 1:
-            e.step(day)
-        else:
-            e.step_begin(day)
-            dist.all_gather_into_tensor(ib_t, ib_t[rank * shard:(rank + 1) * shard])   # in place: day-start infectious bytes
-            e.step_end(day)
+        e.step(day)
 
     def barrier():
         if world > 1:
@@ -198,7 +198,7 @@ def run_ours(args):
         barrier()
         clocks.active = False
         ms_value = max_over_ranks(ev0.elapsed_time(ev1))
-    st_last = eng.stats(W + K - 1)
+    st_last = raw(eng).stats(W + K - 1)
 
     # ---- pass 2: end to end through the C ABI with host buffers (`e2e`) ----
     # The host loop of dysturbd_b200/host.py: every day the open flags are offered from pinned host memory
@@ -208,7 +208,7 @@ def run_ours(args):
     eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
     open_pinned = torch.ones(pop.B, dtype=torch.uint8).pin_memory()
     h2d = d2h = 0
-    stats_days = []
+    stats_days, pending = [], []
     checksum = 0
     with torch.cuda.stream(stream):
         def queue_day(d):
@@ -220,13 +220,19 @@ def run_ours(args):
             o = eng.outputs(d)
             st = o["stats"].copy()
             checksum += int(o["sa_hist"].sum()) + int(o["building_counts"].sum()) + int(o["events"].sum())
-            if world > 1:   # global stats block (the host loop needs it for R / the lockdown decision)
-                t = torch.from_numpy(st).cuda()
-                dist.all_reduce(t)
-                st = t.cpu().numpy()
             if count:
                 d2h += st.nbytes + o["sa_hist"].nbytes + o["building_counts"].nbytes + o["events"].nbytes
                 stats_days.append(st)
+                pending.append(st)
+            if world > 1 and pending and (len(pending) == 7 or d == W + K - 1):
+                # global stats (R, the lockdown decision) are only needed `diagnosis` = 7 days later
+                # (contagious3.py:306-309): one all-reduce per week of stacked 64-integer blocks
+                t = torch.from_numpy(np.stack(pending)).cuda()
+                dist.all_reduce(t)
+                g = t.cpu().numpy()
+                for k in range(len(pending)):
+                    stats_days[len(stats_days) - len(pending) + k] = g[k]
+                pending.clear()
         for d in range(W):
             queue_day(d)
             consume_day(d, False)
@@ -245,23 +251,17 @@ def run_ours(args):
 
     # ---- pass 3: per-kernel CUDA-event durations for the roofline (same days, same state) ----
     eng.close()
-    eng_t = engine.Engine(pop, prm, device=local, flags=all_out | engine.TIME_KERNELS, rank=rank, world=world)
-    stream_t = torch.cuda.ExternalStream(eng_t.cuda_stream(), device=local)
-    if world > 1:
-        ptr, nbytes = eng_t.device_buffer(engine.BUF_INFECTIOUS)
-
-        class _Cai2:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-        ib_t = torch.as_tensor(_Cai2(), device=torch.device("cuda", local))[:n_total]
+    eng_t = make_engine(all_out | engine.TIME_KERNELS)
+    stream_t = torch.cuda.ExternalStream(raw(eng_t).cuda_stream(), device=local)
     with torch.cuda.stream(stream_t):
         for d in range(W):
             day_step(eng_t, d)
-        eng_t.kernel_times()
+        raw(eng_t).kernel_times()
         barrier()
         for d in range(W, W + K):
             day_step(eng_t, d)
-        ms_k, n_k = eng_t.kernel_times()
-    prev = eng_t.stats(W - 1) if W > 0 and world == 1 else stats_days[0]
+        ms_k, n_k = raw(eng_t).kernel_times()
+    prev = raw(eng_t).stats(W - 1) if W > 0 and world == 1 else stats_days[0]
     kb = {"k_push": 0, "k_agent": 0}
     for st in stats_days:                   # the e2e pass ran the same days from the same state: same counters
         for k, v in kernel_bytes(n_total, st, prev).items():
@@ -300,7 +300,7 @@ def run_ours(args):
                         (pop.N, args.communities_per_gpu, W, W + K - 1),
             "agents_total": n_total, "edges_per_gpu": pop.nnz, "norm_factor": args.norm_factor,
             "seeds_per_22493": args.seeds_per_22493, "scenario": "noLockdown",
-            "parallelism": "1 GPU" if world == 1 else "sharded by community x%d, per-day NCCL all-gather of infectious bytes" % world,
+            "parallelism": "1 GPU" if world == 1 else "sharded by community x%d, exchange=%s (peer: snapshot bytes stored into every peer GPU by k_agent over NVLink; nccl: per-day all-gather)" % (world, args.exchange),
             "l2": "state + network of one day (%.0f MB) exceed L2 only partly; every day rewrites the state, no flush" %
                   (eng_bytes(pop) / 1e6),
             "ever_infected_at_end": int(st_last[STAT["ever_infected"]]) if world == 1 else None,

@@ -48,7 +48,13 @@ struct dys_handle {
     int32_t* d_bad = nullptr;
     uint8_t *d_hh_flag[2] = {nullptr, nullptr}, *d_hh_qflag[2] = {nullptr, nullptr};
     int32_t* d_flags = nullptr;      // [2][DF_LEN] per-parity day flags, then [1] closed-building count
-    int32_t ib_day = -1;             // the day the infectious bytes in c.ib are the day-start snapshot of
+    int32_t ib_day = -1;             // the day whose day-start snapshot bytes are complete in buffer ib_day & 1
+    uint8_t* d_ib = nullptr;         // [2][ib_stride] snapshot bytes of all agents, double buffered by day parity
+    int64_t ib_stride = 0;
+    int32_t* d_peer_flags = nullptr; // [8] peer mode: flags[r] = last day rank r's bytes are complete for (on this GPU)
+    uint8_t* peer_ib[8] = {};        // peer mode: every rank's d_ib (own included)
+    int32_t* peer_flags[8] = {};
+    int n_peers = 1;
     int push_grid = 0;               // persistent grid of k_push
     int64_t last_parity = 0;
     double* d_pair_prob = nullptr;
@@ -148,7 +154,9 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     A(dev_alloc(h, (int32_t**)&c.hh, c.n_pad)); A(dev_alloc(h, (int32_t**)&c.home, c.n_pad)); A(dev_alloc(h, (int32_t**)&c.sa, c.n_pad));
     A(dev_alloc(h, (double**)&c.risk, c.n_pad)); A(dev_alloc(h, (double**)&c.p_adm, c.n_pad)); A(dev_alloc(h, (double**)&c.p_death, c.n_pad));
     A(dev_alloc(h, (int32_t**)&c.routine, c.rt_n * c.V));
-    A(dev_alloc(h, &c.ib, round_up(c.n_glob, 1024) + 1024));
+    h->ib_stride = round_up(c.n_glob, 1024) + 1024;
+    A(dev_alloc(h, &h->d_ib, 2 * h->ib_stride));
+    A(dev_alloc(h, &h->d_peer_flags, 8));
     A(dev_alloc(h, (uint8_t**)&c.open, c.B));
     for (int k = 0; k < 2; ++k) { A(dev_alloc(h, &h->d_hh_flag[k], c.H + 16)); A(dev_alloc(h, &h->d_hh_qflag[k], c.H + 16)); }
     A(dev_alloc(h, &h->d_flags, 2 * DF_LEN + 4));
@@ -234,6 +242,7 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
     h->ib_day = -1;
     h->begun = false;
+    CK(h, cudaMemsetAsync(h->d_peer_flags, 0xFF, sizeof(int32_t) * 8, h->stream));   // -1: nothing complete yet
     CK(h, cudaStreamSynchronize(h->stream));
     for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; }
     for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
@@ -494,6 +503,17 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     }
     if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
     const int par = (int)(h->steps & 1);
+    auto ib_targets = [&](int parity) {       // where snapshot bytes of parity `parity` are written: own buffer, then peers
+        c.n_peers = h->n_peers; c.rank = h->p.rank;
+        c.flag_wait = h->d_peer_flags;
+        c.n_wr = 0;
+        c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
+        for (int r = 0; r < h->n_peers; ++r) {
+            c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
+            if (h->n_peers > 1 && r != h->p.rank) c.ib_wr[c.n_wr++] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
+        }
+    };
+    c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
     tick(h, 0);
     if (h->ib_day != day || (inj && inj->u_adm)) {
         // phase A on its own: first day after a load / set_state, a skipped day, or injected admission draws
@@ -501,8 +521,10 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
         CK(h, cudaMemsetAsync(h->d_hh_flag[par], 0, (size_t)c.H + 16, h->stream));
         CK(h, cudaMemsetAsync(h->d_hh_qflag[par], 0, (size_t)c.H + 16, h->stream));
         CK(h, cudaMemsetAsync(h->d_flags + par * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
+        ib_targets(day & 1);
         k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day, h->d_hh_flag[par], h->d_hh_qflag[par],
                                                                       h->d_flags + par * DF_LEN);
+        if (h->n_peers > 1) k_signal<<<1, 32, 0, h->stream>>>(c, day);
         h->ib_day = day;
     }
     tick(h, 1);
@@ -525,6 +547,17 @@ static int step_end(dys_handle* h, int32_t day)
     c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
     c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
     h->last_parity = par;
+    c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
+    c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
+    c.n_wr = 0;
+    {   // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
+        const int parity = (day + 1) & 1;
+        c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
+        for (int r = 0; r < h->n_peers; ++r) {
+            c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
+            if (h->n_peers > 1 && r != h->p.rank) c.ib_wr[c.n_wr++] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
+        }
+    }
     k_push<<<(unsigned)h->push_grid, PUSH_WARPS * 32, 0, h->stream>>>(c, day);
     tick(h, 2);
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
@@ -733,7 +766,7 @@ extern "C" int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* 
     const DevCtx& c = h->c;
     switch (which) {
         case DYS_BUF_STATUS: *ptr = c.status; *bytes = c.n_pad; break;
-        case DYS_BUF_INFECTIOUS: *ptr = c.ib; *bytes = round_up(c.n_glob, 1024); break;
+        case DYS_BUF_INFECTIOUS: *ptr = h->d_ib; *bytes = 2 * h->ib_stride; break;   /* [2][bytes/2]: buffer of day d is d & 1 */
         case DYS_BUF_STATS: *ptr = h->d_out[h->last_parity]; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
         case DYS_BUF_T_INF: *ptr = c.t_inf; *bytes = c.n_pad * 2; break;
         default: return fail(h, DYS_ERR_INVALID_ARG, "unknown buffer %d", which);
@@ -769,5 +802,37 @@ extern "C" int dys_keyed_uniform_device(int device, uint64_t seed, uint32_t day,
     if (e == cudaSuccess) e = cudaMemcpy(out, dout, 8 * (size_t)n, cudaMemcpyDeviceToHost);
     cudaFree(da); cudaFree(db); cudaFree(dout);
     if (e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "dys_keyed_uniform_device: %s", cudaGetErrorString(e));
+    return DYS_OK;
+}
+
+// ---- peer mode: the per-day exchange fused into k_agent (P2P stores over NVLink) ----
+extern "C" int dys_peer_export(dys_handle* h, void* out /* DYS_PEER_HANDLE_BYTES */)
+{
+    if (!h || !out) return DYS_ERR_INVALID_ARG;
+    CK(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hs[2];
+    CK(h, cudaIpcGetMemHandle(&hs[0], h->d_ib));
+    CK(h, cudaIpcGetMemHandle(&hs[1], h->d_peer_flags));
+    static_assert(sizeof(hs) == DYS_PEER_HANDLE_BYTES, "handle size");
+    memcpy(out, hs, sizeof hs);
+    return DYS_OK;
+}
+
+extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */)
+{
+    if (!h || !handles) return DYS_ERR_INVALID_ARG;
+    if (n_ranks < 2 || n_ranks > 8 || n_ranks != h->p.world) return fail(h, DYS_ERR_INVALID_ARG, "dys_peer_attach: 2..8 ranks, equal to dys_params.world");
+    CK(h, cudaSetDevice(h->device));
+    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)handles;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == h->p.rank) { h->peer_ib[r] = h->d_ib; h->peer_flags[r] = h->d_peer_flags; continue; }
+        void *pib = nullptr, *pfl = nullptr;
+        CK(h, cudaIpcOpenMemHandle(&pib, hs[2 * r], cudaIpcMemLazyEnablePeerAccess));
+        CK(h, cudaIpcOpenMemHandle(&pfl, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        h->peer_ib[r] = (uint8_t*)pib;
+        h->peer_flags[r] = (int32_t*)pfl;
+    }
+    h->n_peers = n_ranks;
+    h->ib_day = -1;
     return DYS_OK;
 }

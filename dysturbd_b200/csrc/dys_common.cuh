@@ -66,7 +66,15 @@ struct DevCtx {
     const uint32_t* tcolx;               // [nnz] u (local) | class << 28
     const double* tval;                  // [nnz] ip[u, i]
     const double* pdf;                   // [64]
-    uint8_t* ib;                         // [n_glob padded] day-start infectious bytes of ALL agents
+    // day-start snapshot bytes of ALL agents, double buffered by day parity: k_push(d) reads ib_rd = buffer d&1, k_agent(d)
+    // writes tomorrow's bytes of the owned agents into buffer (d+1)&1 -- of this GPU and, in peer mode, of every peer GPU
+    // (P2P stores over NVLink), so the per-day exchange is fused into the producing kernel
+    const uint8_t* ib_rd;
+    uint8_t* ib_wr[8];                   // [n_wr] write targets (own buffer first)
+    int32_t n_wr;
+    int32_t n_peers, rank;               // peer mode: n_peers > 1
+    const int32_t* flag_wait;            // [n_peers] on THIS GPU: flag_wait[r] = last day rank r's bytes are complete for
+    int32_t* flag_signal[8];             // [n_peers] &flags[rank] on every GPU (own included)
     const uint8_t* open;                 // [B]
     int32_t n_closed;                    // closed buildings today (counted on the host by dys_set_open)
     const uint8_t *hh_flag, *hh_qflag;   // [H] households diagnosed TODAY / quirk households (contagious3.py:263, :267)

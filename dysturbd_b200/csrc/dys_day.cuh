@@ -77,6 +77,13 @@ __global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const 
 
     if (tid < 64) s_pdf[tid] = c.pdf[tid];
     if (tid < 8) s_acc[tid] = 0;
+    if (c.n_peers > 1 && tid < c.n_peers) {
+        // peer mode: every rank's k_agent (or k_signal) stored its slice of today's snapshot bytes straight into this
+        // GPU's buffer and then raised flag[r] = day; the grid is persistent (all CTAs resident), so spinning is safe
+        const volatile int32_t* f = c.flag_wait + tid;
+        while (*f < day) __nanosleep(64);
+        __threadfence_system();
+    }
     __syncthreads();
     const bool any_closed = c.n_closed != 0;
     unsigned int cnt[4] = {0, 0, 0, 0};   // entries scanned, candidates, exposed, hits
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const 
     const int64_t stride = (int64_t)gridDim.x * PUSH_WARPS;
     int64_t ch = (int64_t)blockIdx.x * PUSH_WARPS + wid;
     int nq = 0;                                            // queued rows (warp-uniform)
-    const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib + c.rt_lo);     // rt_lo is a multiple of 1024
+    const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib_rd + c.rt_lo);  // rt_lo is a multiple of 1024
     uint32_t v = 0;
     if (ch < n_chunks) v = ib4[ch * (PUSH_CHUNK / 4) + lane];
     for (; ch < n_chunks; ch += stride) {
@@ -302,7 +309,8 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
         if (c.bcount && in_set(M_INF, x)) atomicAdd(&c.bcount[__ldg(c.home + a)], 1);
     }
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
-    c.ib[c.lo + a] = infectious_byte(x, day + 1, ti);
+    const uint8_t ibn = infectious_byte(x, day + 1, ti);
+    for (int p = 0; p < c.n_wr; ++p) c.ib_wr[p][c.lo + a] = ibn;
     if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.hh_flag_next, c.hh_qflag_next, c.df_next);
 }
 
@@ -369,7 +377,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
             }
         }
         // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
-        *reinterpret_cast<uint32_t*>(c.ib + c.lo + a0) = 0u;
+        for (int p = 0; p < c.n_wr; ++p) *reinterpret_cast<uint32_t*>(c.ib_wr[p] + c.lo + a0) = 0u;
         // compact the agents that need the settle phase
         const int mine = __popc(work);
         const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
@@ -415,6 +423,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
         }
     }
     if (VARIANT == 2) return;
+    if (c.n_peers > 1) __threadfence_system();     // this thread's peer stores are visible before the block's ticket
     __syncthreads();
     if (tid < 32) {
         // warp 0 publishes everything, fences, and takes the ticket
@@ -481,6 +490,11 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
             c.stats[tid] = v;
         }
         if (tid == 0) *c.ticket = 0u;
+        // every block fenced its peer stores before its ticket: tomorrow's bytes are complete on every GPU
+        if (c.n_peers > 1 && tid < c.n_peers) {
+            __threadfence_system();
+            *reinterpret_cast<volatile int32_t*>(c.flag_signal[tid]) = day + 1;
+        }
     }
 }
 
@@ -502,7 +516,17 @@ __global__ void __launch_bounds__(256) k_snapshot(const DevCtx c, const int day,
         ibn[j] = infectious_byte(st[j], day, ti[j]);
         if (diagnosed_on(c, c.u_adm, a0 + j, st[j], ti[j], day)) raise_household(c, a0 + j, hh_flag, hh_qflag, df);
     }
-    *reinterpret_cast<uchar4*>(c.ib + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
+    for (int p = 0; p < c.n_wr; ++p)
+        *reinterpret_cast<uchar4*>(c.ib_wr[p] + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
+}
+
+// peer mode: after a stand-alone k_snapshot, tell every GPU that this rank's bytes for `day` are complete
+__global__ void k_signal(const DevCtx c, const int day)
+{
+    if (threadIdx.x < c.n_peers) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int32_t*>(c.flag_signal[threadIdx.x]) = day;
+    }
 }
 
 }  // namespace dys

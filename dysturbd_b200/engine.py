@@ -26,6 +26,7 @@ STAT = {name: i for i, name in enumerate(
 
 WANT_SA_HIST, WANT_BUILDING_COUNTS, WANT_EVENTS, WANT_IO_MAT, TIME_KERNELS = 1, 2, 4, 8, 16
 BUF_STATUS, BUF_INFECTIOUS, BUF_STATS, BUF_T_INF = 0, 1, 2, 3
+PEER_HANDLE_BYTES = 128
 
 
 class DysError(RuntimeError):
@@ -59,7 +60,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_begin", "dys_step_end", "dys_get_stats",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
-           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device"]
+           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach"]
 
 _lib = None
 
@@ -102,6 +103,8 @@ def load_library():
     lib.dys_device_bytes.restype = i64
     lib.dys_version.restype = C.c_char_p
     lib.dys_keyed_uniform_device.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, i64, vp]
+    lib.dys_peer_export.argtypes = [vp, vp]
+    lib.dys_peer_attach.argtypes = [vp, C.c_int, vp]
     _lib = lib
     return lib
 
@@ -308,6 +311,17 @@ class Engine:
         p, b = C.c_void_p(), C.c_int64()
         self._ck(self.lib.dys_device_buffer(self.h, which, C.byref(p), C.byref(b)))
         return p.value, b.value
+
+    def peer_export(self):
+        """CUDA IPC handles (bytes) of this rank's snapshot buffer and flag array"""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._ck(self.lib.dys_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles):
+        """handles: list of every rank's peer_export() bytes, in rank order"""
+        blob = b"".join(handles)
+        self._ck(self.lib.dys_peer_attach(self.h, len(handles), blob))
 
     def cuda_stream(self):
         p = C.c_void_p()

@@ -184,6 +184,14 @@ typedef enum { DYS_BUF_STATUS = 0, DYS_BUF_INFECTIOUS = 1, DYS_BUF_STATS = 2, DY
 int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* bytes);
 int dys_cuda_stream(dys_handle* h, void** stream);
 int64_t dys_device_bytes(const dys_handle* h);
+/* Peer mode (sharded populations on one NVLink/NVSwitch node): every rank exports CUDA IPC handles of its snapshot
+ * buffer and flag array, gathers all ranks' handles (any host-side all-gather) and attaches them.  From then on the
+ * kernel that produces tomorrow's snapshot bytes stores them straight into every peer GPU's buffer and raises a flag
+ * there; the next day's first kernel waits for all flags.  dys_step() then needs no collective call at all.  After
+ * dys_set_state in peer mode the caller must barrier across ranks before the next dys_step. */
+#define DYS_PEER_HANDLE_BYTES 128
+int dys_peer_export(dys_handle* h, void* out /* [DYS_PEER_HANDLE_BYTES] */);
+int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */);
 /* evaluates the keyed uniform u(day, stream, a[k], b[k]) ON THE DEVICE for n host-side index pairs (known-answer
  * tests of the device Philox against oracle/philox_np.py) */
 int dys_keyed_uniform_device(int device, uint64_t seed, uint32_t day, uint32_t stream, const uint32_t* a,

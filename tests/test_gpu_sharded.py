@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_COMM, DAYS = 6, 35
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mode):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -29,7 +29,7 @@ def _worker(rank, world, port, out):
         cpr = N_COMM // world
         pop = synth_population(n, seed=33, communities=(rank * cpr, (rank + 1) * cpr), seeds_per_22493=150, cross=0.05)
         prm = EpiParams(norm_factor=6.0, seed=7)
-        sh = ShardedEngine(pop, prm, device=rank)
+        sh = ShardedEngine(pop, prm, device=rank, mode=mode)
         ref = engine.Engine(synth_population(n, seed=33, seeds_per_22493=150, cross=0.05), prm, device=rank) if rank == 0 else None
         ok, cross = True, 0
         for d in range(DAYS):
@@ -54,15 +54,16 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_equals_single_gpu():
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_two_gpu_sharded_equals_single_gpu(mode):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29700 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    port = 29700 + os.getpid() % 2000 + (7 if mode == "nccl" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, mode)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -28,7 +28,7 @@ def _worker(rank, world, port, out):
         cpr = N_COMM // world
         pop = synth_population(n, seed=21, communities=(rank * cpr, (rank + 1) * cpr), seeds_per_22493=150, cross=0.05)
         prm = EpiParams(norm_factor=6.0, seed=77)
-        sh = ShardedEngine(pop, prm, backend=oracle_port.OracleSim)
+        sh = ShardedEngine(pop, prm, backend=oracle_port.OracleSim)     # CPU stand-in -> mode "nccl" over gloo
         ref = oracle_port.OracleSim(synth_population(n, seed=21, seeds_per_22493=150, cross=0.05), prm) if rank == 0 else None
         ok, cross_events = True, 0
         for d in range(DAYS):

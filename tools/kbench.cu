@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) k_stream(const DevCtx c, const int day)
     const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
     const short4 ti = *reinterpret_cast<const short4*>(c.t_inf + a0);
     uint32_t w = sv.x + sv.y + sv.z + sv.w + ti.x;
-    *reinterpret_cast<uint32_t*>(c.ib + a0) = w;
+    *reinterpret_cast<uint32_t*>(c.ib_wr[0] + a0) = w;
 }
 __global__ void __launch_bounds__(256) k_agent_nofold(const DevCtx c, const int day) { agent_body<1>(c, day); }
 __global__ void __launch_bounds__(256) k_agent_noreduce(const DevCtx c, const int day) { agent_body<2>(c, day); }
@@ -43,7 +43,8 @@ int main(int argc, char** argv)
     d = dalloc<int32_t>(N); cudaMemcpy(d, sa.data(), 4 * N, cudaMemcpyHostToDevice); c.sa = d;
     c.risk = dalloc<double>(N); c.p_adm = dalloc<double>(N); c.p_death = dalloc<double>(N);
     c.pdf = dalloc<double>(64);
-    c.ib = dalloc<uint8_t>(N + 2048);
+    uint8_t* ibbuf = dalloc<uint8_t>(N + 2048); c.ib_rd = ibbuf; c.ib_wr[0] = ibbuf; c.n_wr = 1; c.n_peers = 1;
+    c.flag_wait = dalloc<int32_t>(8); c.flag_signal[0] = dalloc<int32_t>(8);
     c.open = dalloc<uint8_t>(c.B, 1); c.n_closed = 0;
     uint8_t* f0 = dalloc<uint8_t>(c.H + 16); uint8_t* f1 = dalloc<uint8_t>(c.H + 16);
     c.hh_flag = f0; c.hh_qflag = f1; c.hh_flag_next = dalloc<uint8_t>(c.H + 16); c.hh_qflag_next = dalloc<uint8_t>(c.H + 16);
@@ -95,7 +96,7 @@ int main(int argc, char** argv)
     {   // snapshot bytes for the infectious agents
         std::vector<uint8_t> ibh(N + 2048, 0);
         for (int64_t a = 0; a < N; ++a) if (st[a] == ST_I) ibh[a] = 0x80 | 3;
-        cudaMemcpy(c.ib, ibh.data(), N, cudaMemcpyHostToDevice);
+        cudaMemcpy(ibbuf, ibh.data(), N, cudaMemcpyHostToDevice);
     }
     timeit("k_push", [&](int d) { k_push<<<148 * per_sm, 256>>>(c, d); });
     printf("push blocks/SM %d\n", per_sm);
