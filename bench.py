@@ -64,45 +64,57 @@ def make_params(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clocks and throttle reasons DURING the timed regions.  The timed regions are tens of milliseconds long, so
+    the nvidia-smi loop of B200_PROFILING.md (200 ms period) would miss them: the same NVML counters are polled from a
+    thread every millisecond instead."""
 
     def __init__(self, gpu_index):
-        self.rows, self.gpu, self.proc = [], gpu_index, None
-        self.active = False
+        self.rows, self.gpu, self.active, self._stop = [], gpu_index, False, False
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
             return
-        threading.Thread(target=self._read, daemon=True).start()
+        threading.Thread(target=self._poll, daemon=True).start()
 
-    def _read(self):
-        for line in self.proc.stdout:
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
             if self.active:
-                self.rows.append([x.strip() for x in line.split(",")])
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((sm, rs))
+                except Exception:
+                    pass
+            time.sleep(0.001)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
+        self._stop = True
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80}
+        seen = set()
+        for _, rs in self.rows:
+            for n, bit in names.items():
+                if rs & bit:
+                    seen.add(n)
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(self.max_sm), "reasons": sorted(seen),
+                "samples": len(self.rows)}
 
 
 def kernel_bytes(N, st, prev):
@@ -219,7 +231,8 @@ def run_ours(args):
             nonlocal d2h, checksum
             o = eng.outputs(d)
             st = o["stats"].copy()
-            checksum += int(o["sa_hist"].sum()) + int(o["building_counts"].sum()) + int(o["events"].sum())
+            # the block is in host memory now (one D2H per day, queued by dys_step); touch each part
+            checksum += int(o["sa_hist"][-1, 0]) + int(o["building_counts"][-1]) + o["n_events"] + (int(o["events"][-1, 0]) if len(o["events"]) else 0)
             if count:
                 d2h += st.nbytes + o["sa_hist"].nbytes + o["building_counts"].nbytes + o["events"].nbytes
                 stats_days.append(st)
@@ -257,11 +270,12 @@ def run_ours(args):
         for d in range(W):
             day_step(eng_t, d)
         raw(eng_t).kernel_times()
+        prev_w = raw(eng_t).stats(W - 1) if W > 0 else None      # day-start compartment counts of the first timed day
         barrier()
         for d in range(W, W + K):
             day_step(eng_t, d)
         ms_k, n_k = raw(eng_t).kernel_times()
-    prev = raw(eng_t).stats(W - 1) if W > 0 and world == 1 else stats_days[0]
+    prev = prev_w if prev_w is not None and world == 1 else stats_days[0]
     kb = {"k_push": 0, "k_agent": 0}
     for st in stats_days:                   # the e2e pass ran the same days from the same state: same counters
         for k, v in kernel_bytes(n_total, st, prev).items():

@@ -26,6 +26,8 @@ struct dys_handle {
     DevCtx c{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // the day's output block leaves on its own stream, under the next day's kernels
+    cudaEvent_t day_done[2] = {nullptr, nullptr};   // per parity: k_agent finished writing the block
     std::vector<void*> allocs;
     int64_t dev_bytes = 0;
     std::string err;
@@ -55,6 +57,7 @@ struct dys_handle {
     uint8_t* peer_ib[8] = {};        // peer mode: every rank's d_ib (own included)
     int32_t* peer_flags[8] = {};
     int n_peers = 1;
+    cudaEvent_t out_parity_ev[2] = {nullptr, nullptr};   // the copy-done event of the last day that used block [parity]
     int push_grid = 0;               // persistent grid of k_push
     int64_t last_parity = 0;
     double* d_pair_prob = nullptr;
@@ -134,6 +137,8 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     h->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->day_done[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { fail(nullptr, DYS_ERR_CUDA, "cuda init: %s", cudaGetErrorString(e)); delete h; return DYS_ERR_CUDA; }
     DevCtx& c = h->c;
     c.n_loc = hi - lo; c.n_pad = round_up(c.n_loc, 1024); c.n_glob = p.n_agents; c.lo = lo;
@@ -224,6 +229,8 @@ extern "C" int dys_destroy(dys_handle* h)
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < DYS_OUT_RING; ++i) if (h->out_ev[i]) cudaEventDestroy(h->out_ev[i]);
     for (auto ev : h->tev) if (ev) cudaEventDestroy(ev);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int k = 0; k < 2; ++k) if (h->day_done[k]) cudaEventDestroy(h->day_done[k]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return DYS_OK;
@@ -244,6 +251,8 @@ static int reset_day_scratch(dys_handle* h)
     h->begun = false;
     CK(h, cudaMemsetAsync(h->d_peer_flags, 0xFF, sizeof(int32_t) * 8, h->stream));   // -1: nothing complete yet
     CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaStreamSynchronize(h->copy_stream));
+    h->out_parity_ev[0] = h->out_parity_ev[1] = nullptr;
     for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; }
     for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
     return DYS_OK;
@@ -547,6 +556,7 @@ static int step_end(dys_handle* h, int32_t day)
     c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
     c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
     h->last_parity = par;
+    if (h->out_parity_ev[par]) CK(h, cudaStreamWaitEvent(h->stream, h->out_parity_ev[par], 0));   // block `par` has left the device
     c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
     c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
     c.n_wr = 0;
@@ -570,8 +580,13 @@ static int step_end(dys_handle* h, int32_t day)
         memcpy(h->hist_stats[hs], h->h_out + (size_t)slot * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
         h->hist_day[hs] = h->out_day[slot];
     }
-    CK(h, cudaMemcpyAsync(h->h_out + (size_t)slot * h->out_copy_bytes, h->d_out[par], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaEventRecord(h->out_ev[slot], h->stream));
+    // the copy runs on its own stream so that the next day's kernels do not queue behind it; block `par` is written
+    // again two days from now, and that day's kernels wait for this copy (see step_end's cudaStreamWaitEvent)
+    CK(h, cudaEventRecord(h->day_done[par], h->stream));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->day_done[par], 0));
+    CK(h, cudaMemcpyAsync(h->h_out + (size_t)slot * h->out_copy_bytes, h->d_out[par], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(h, cudaEventRecord(h->out_ev[slot], h->copy_stream));
+    h->out_parity_ev[par] = h->out_ev[slot];
     h->out_day[slot] = day;
     h->out_step[slot] = h->steps;
     h->last_day = day;
@@ -739,6 +754,7 @@ extern "C" int dys_sync(dys_handle* h)
     if (!h) return DYS_ERR_INVALID_ARG;
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaStreamSynchronize(h->copy_stream));
     return DYS_OK;
 }
 
