@@ -213,25 +213,23 @@ def run_ours(args):
     st_last = raw(eng).stats(W + K - 1)
 
     # ---- pass 2: end to end through the C ABI with host buffers (`e2e`) ----
-    # The host loop of dysturbd_b200/host.py: every day the open flags are offered from pinned host memory
-    # (dys_set_open; an unchanged vector is elided inside the library) and the day's whole output block (stats,
-    # per-area histograms, per-building counts, infection events) is read on the host.  Day d+1 is queued before day d
-    # is consumed -- legal because the lockdown decision lags 7 days (contagious3.py:306-309).
+    # The host loop of dysturbd_b200/host.py (EpidemicModel.run): days are queued in windows of 3 with two windows in
+    # flight (exact for every scenario: the lockdown decision lags 7 days, contagious3.py:306-309).  Every window the
+    # open flags of its days are offered from pinned host memory (dys_step_many -> dys_set_open; an unchanged vector is
+    # elided inside the library) and every day's whole output block (stats, per-area histograms, per-building counts,
+    # infection events) is read on the host from the pinned ring the library copied it into.
+    WIN = 3
     eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
-    open_pinned = torch.ones(pop.B, dtype=torch.uint8).pin_memory()
+    open_pinned = torch.ones((WIN, pop.B), dtype=torch.uint8).pin_memory()
     h2d = d2h = 0
     stats_days, pending = [], []
     checksum = 0
     with torch.cuda.stream(stream):
-        def queue_day(d):
-            eng.set_open(open_pinned)
-            day_step(eng, d)
-
         def consume_day(d, count):
             nonlocal d2h, checksum
             o = eng.outputs(d)
             st = o["stats"].copy()
-            # the block is in host memory now (one D2H per day, queued by dys_step); touch each part
+            # the block is in host memory now (one D2H per day, queued by the library); touch each part
             checksum += int(o["sa_hist"][-1, 0]) + int(o["building_counts"][-1]) + o["n_events"] + (int(o["events"][-1, 0]) if len(o["events"]) else 0)
             if count:
                 d2h += st.nbytes + o["sa_hist"].nbytes + o["building_counts"].nbytes + o["events"].nbytes
@@ -246,17 +244,23 @@ def run_ours(args):
                 for k in range(len(pending)):
                     stats_days[len(stats_days) - len(pending) + k] = g[k]
                 pending.clear()
-        for d in range(W):
-            queue_day(d)
-            consume_day(d, False)
+
+        def run_days(first, last, count):
+            queued = consumed = first
+            while consumed < last:
+                while queued < min(last, consumed + 2 * WIN):
+                    n = min(WIN, last - queued)
+                    eng.step_many(queued, n, open_pinned[:n])
+                    queued += n
+                for _ in range(min(WIN, queued - consumed)):
+                    consume_day(consumed, count)
+                    consumed += 1
+
+        run_days(0, W, False)
         barrier()
         clocks.active = True
         t0 = time.perf_counter()
-        queue_day(W)
-        for d in range(W, W + K):
-            if d + 1 < W + K:
-                queue_day(d + 1)
-            consume_day(d, True)
+        run_days(W, W + K, True)
         barrier()
         s_e2e = max_over_ranks(time.perf_counter() - t0)
         clocks.active = False

@@ -618,6 +618,22 @@ static int find_out_slot(dys_handle* h, int32_t day)
     return -1;
 }
 
+extern "C" int dys_step_many(dys_handle* h, int32_t first_day, int32_t n_days, const uint8_t* open_flags)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (n_days < 1 || n_days > DYS_OUT_RING - 2) return fail(h, DYS_ERR_INVALID_ARG, "dys_step_many: 1..%d days", DYS_OUT_RING - 2);
+    for (int32_t k = 0; k < n_days; ++k) {
+        if (open_flags) {
+            int rc = dys_set_open(h, open_flags + (size_t)k * (size_t)h->c.B);
+            if (rc != DYS_OK) return rc;
+        }
+        int rc = step_begin(h, first_day + k, nullptr);
+        if (rc == DYS_OK) rc = step_end(h, first_day + k);
+        if (rc != DYS_OK) return rc;
+    }
+    return DYS_OK;
+}
+
 extern "C" int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out)
 {
     if (!h || !out) return DYS_ERR_INVALID_ARG;

@@ -57,7 +57,7 @@ class _Injected(C.Structure):
 
 
 EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population", "dys_load_graph", "dys_load_quirk",
-           "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_begin", "dys_step_end", "dys_get_stats",
+           "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_many", "dys_step_begin", "dys_step_end", "dys_get_stats",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach"]
@@ -85,6 +85,7 @@ def load_library():
     lib.dys_set_run.argtypes = [vp, C.c_double, C.c_double, C.c_uint64]
     lib.dys_set_state.argtypes = [vp] + [vp] * 5
     lib.dys_step.argtypes = [vp, i32, C.POINTER(_Injected)]
+    lib.dys_step_many.argtypes = [vp, i32, i32, vp]
     lib.dys_step_begin.argtypes = [vp, i32, C.POINTER(_Injected)]
     lib.dys_step_end.argtypes = [vp, i32]
     lib.dys_get_stats.argtypes = [vp, i32, vp]
@@ -228,6 +229,15 @@ class Engine:
         inj, keep = self._inj(u_adm, u_death, u_pair)
         self._ck(self.lib.dys_step(self.h, int(day), C.byref(inj) if inj is not None else None))
 
+    def step_many(self, first_day, n_days, open_flags=None):
+        """queue n_days (<= 14; <= 7 to stay exact under lockdown scenarios) consecutive days in one call;
+        open_flags: None or uint8 [n_days, B]"""
+        p = None
+        if open_flags is not None:
+            p, _keep = _ptr(np.ascontiguousarray(open_flags, dtype=np.uint8) if isinstance(open_flags, np.ndarray) else open_flags,
+                            None, n_days * self.pop.B)
+        self._ck(self.lib.dys_step_many(self.h, int(first_day), int(n_days), p))
+
     def step_begin(self, day):
         self._ck(self.lib.dys_step_begin(self.h, int(day), None))
 
@@ -236,7 +246,7 @@ class Engine:
 
     def outputs(self, day):
         """Everything day `day` produced, as zero-copy numpy views of the library's pinned host ring (valid until
-        DYS_OUT_RING - 1 = 3 further days are stepped): dict(stats, sa_hist, building_counts, events[n,2], n_events)."""
+        DYS_OUT_RING - 1 = 15 further days are stepped): dict(stats, sa_hist, building_counts, events[n,2], n_events)."""
         o = _DayOutputs()
         self._ck(self.lib.dys_get_outputs(self.h, int(day), C.byref(o)))
         as_np = np.ctypeslib.as_array

@@ -64,14 +64,21 @@ def building_lockdown(lu, usg, current, sc, vR, prevVR, choice):
 
 
 class EpidemicModel:
+    """contagious3.py:172-389 with the day on the GPU.
+
+    run() queues days in windows of WINDOW = 3 and keeps two windows in flight: the open flags of day d+1 depend on
+    `Known R` of days d and d-1, i.e. on R of days d-7 and d-8 (contagious3.py:306-309, 379-384), so the flags of two
+    3-day windows ahead only need days that have already been consumed -- exact for every scenario, while the host's
+    dictionary building overlaps the device's work."""
+    WINDOW = 3
+
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
                  device=0, choice_seed=None, backend=None, population=None):
         self.params = params or EpiParams()
         self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob)
         self.scenario = list(scenario)
         self.sim = backend(self.pop, self.params) if backend is not None else Engine(self.pop, self.params, device=device)
-        self.day = 0
-        self.open = self.pop.open.astype(float)
+        self.day = 0                 # next day to consume
         self.outputs = {'Results': {'Stats': {}, 'Buildings': {}, 'SAs': {}, 'IO_mat': {}}}
         self._choice = np.random.RandomState(choice_seed).choice
         p = self.pop
@@ -79,31 +86,69 @@ class EpidemicModel:
         self._inhabited = np.nonzero(self._bld_pop > 0)[0]
         self._pdf = [float(x) for x in self.params.pdf]
         self._active = int(np.isin(p.status, (4, 7, 8, 10)).sum())
+        self._R = {}                 # day -> R of that day (contagious3.py:281)
+        self._flags = {0: self.pop.open.astype(float)}      # day -> build[:,10] in force on that day
+        self._queued = 0             # next day to queue
+
+    @property
+    def open(self):
+        """build[:, 10] as the reference leaves it after the last consumed day (= the flags of the next day)"""
+        return self._flags_for(self.day)
 
     def active(self):
         """the `while` condition of contagious3.py:176"""
         return self._active > 0
 
-    def step(self):
+    def _known_R(self, day):
+        d = self.params.diagnosis
+        return self._R[day - d] if day > d else 0                                               # :306-309
+
+    def _flags_for(self, day):
+        """phase H (contagious3.py:368-385): the flags of `day` were decided at the end of day-1 from Known R"""
+        if day not in self._flags:
+            prev = day - 1
+            if 'DIFF' in self.scenario:
+                if prev != 0:
+                    raise KeyError('Vis_R')      # the reference reads a key it never writes (:371 vs :319)
+                self._flags[day] = np.ones(self.pop.B)
+            else:
+                cur = self._flags_for(prev)
+                prevVR = self._known_R(prev - 1) if prev != 0 else 0
+                self._flags[day] = building_lockdown(self.pop.bld_lu, self.pop.bld_usg, cur, self.scenario,
+                                                     self._known_R(prev), prevVR, self._choice)
+            self._flags.pop(day - 20, None)
+        return self._flags[day]
+
+    def _queue(self, n):
+        first = self._queued
+        flags = np.stack([self._flags_for(first + k) for k in range(n)]).astype(np.uint8)
+        if hasattr(self.sim, "step_many"):
+            self.sim.step_many(first, n, flags)
+        else:                                    # tests drive this loop with the CPU oracle as backend
+            assert n == 1
+            self.sim.set_open(flags[0])
+            self.sim.step(first)
+        self._queued += n
+
+    def _consume(self):
         p, sim, day, prm = self.pop, self.sim, self.day, self.params
         res = self.outputs['Results']
-        sim.set_open(self.open.astype(np.uint8))
-        closed_today = int((self.open == 0).sum())
-        sim.step(day)
+        closed_today = int((self._flags_for(day) == 0).sum())
         if hasattr(sim, "outputs"):              # the CUDA engine: one pinned block per day, no further transfers
             o = sim.outputs(day)
             st, sa_hist, bc = o["stats"], o["sa_hist"], o["building_counts"]
             ev = o["events"]
             order = np.argsort(ev[:, 0], kind="stable")
             ev_a, ev_s = ev[order, 0], ev[order, 1]
-        else:                                    # tests drive this loop with the CPU oracle as backend
+        else:
             st, sa_hist, bc = sim.stats(day), sim.sa_hist(day), sim.building_counts(day)
             ev_a, ev_s = sim.events(day)
         hist = st[HIST0:HIST0 + HIST_LEN]
         R = compute_R_from_hist(hist, self._pdf, prm.recover)
+        self._R[day] = R
         sas = [float(x) for x in p.sa_ids]
         res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
-        vis_R = res['Stats'][day - prm.diagnosis]['R'] if day > prm.diagnosis else 0          # :306-309
+        vis_R = self._known_R(day)
         res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
         new_infections = int(st[STAT['daily_inf']])
         S = {'Active infected': int(st[STAT['active']]), 'Daily infections': new_infections,
@@ -123,21 +168,36 @@ class EpidemicModel:
             for a, s in zip(p.sa[ev_a], p.sa[ev_s]):
                 mat[sas[a]][sas[s]] += 1
         res['IO_mat'][day] = mat
-        # phase H: tomorrow's open flags (contagious3.py:368-385)
-        if 'DIFF' in self.scenario:
-            if day != 0:
-                raise KeyError('Vis_R')          # the reference reads a key it never writes (:371 vs :319)
-            self.open = np.ones(p.B)
-        else:
-            prevVR = res['Stats'][day - 1]['Known R'] if day != 0 else 0
-            self.open = building_lockdown(p.bld_lu, p.bld_usg, self.open, self.scenario, vis_R, prevVR, self._choice)
         self._active = S['Active infected']
         self.day += 1
         return S
 
+    def step(self):
+        """one day, queued and consumed (contagious3.py:176-387)"""
+        if self._queued == self.day:
+            self._queue(1)
+        S = self._consume()
+        self._flags_for(self.day)        # phase H for tomorrow, in the reference's order of np.random.choice calls
+        return S
+
     def run(self, max_days=None):
-        while self.active() and (max_days is None or self.day < max_days):
-            self.step()
+        batched = hasattr(self.sim, "step_many")
+        w = self.WINDOW if batched else 1
+        limit = (lambda d: max_days is None or d < max_days)
+        while self.active() and limit(self.day):
+            while batched and self._queued < self.day + 2 * w and limit(self._queued):      # keep two windows in flight
+                n = w if max_days is None else min(w, max_days - self._queued)
+                self._queue(n)
+            if not batched:
+                self._queue(1)
+            for _ in range(self._queued - self.day if not batched else min(w, self._queued - self.day)):
+                if not (self.active() and limit(self.day)):
+                    break
+                self._consume()
+        # days queued beyond the end of the epidemic changed nothing the reference records (no infectious agent is
+        # left, so columns 16 and 21 are final), and their outputs are dropped
+        if hasattr(self.sim, "sync"):
+            self.sim.sync()
         st = self.sim.state()
         src_id = np.where(st['src'] >= 0, self.pop.agent_ids[np.maximum(st['src'], 0)], 0.0)
         self.outputs['Results']['Infections chain'] = np.stack(

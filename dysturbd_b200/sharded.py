@@ -73,6 +73,15 @@ class ShardedEngine:
             self.exchange(day)
             self.sim.step_end(day)
 
+    def step_many(self, first_day, n_days, open_flags=None):
+        if self.mode == "peer":
+            self.sim.step_many(first_day, n_days, open_flags)
+        else:
+            for k in range(n_days):
+                if open_flags is not None:
+                    self.sim.set_open(open_flags[k])
+                self.step(first_day + k)
+
     def set_open(self, open_flags):
         self.sim.set_open(open_flags)
 

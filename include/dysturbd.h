@@ -144,6 +144,10 @@ int dys_step(dys_handle* h, int32_t day, const dys_injected* injected /* nullabl
 /* the same day in two halves, for sharded populations: _begin writes this shard's slice of the day-start
  * infectious bytes (DYS_BUF_INFECTIOUS) and applies phases B, C; the caller exchanges the slices between ranks
  * (all-gather over NCCL); _end runs phases D-G.  dys_step == dys_step_begin + dys_step_end. */
+/* `n_days` consecutive days queued in one call.  open_flags is NULL (flags unchanged) or [n_days][B], one vector per
+ * day.  Exact for every scenario of the reference as long as n_days <= `diagnosis` (7): the lockdown decision for a day
+ * uses R of `diagnosis` days earlier (contagious3.py:306-309, 379-384), so a week's flags are known when it starts. */
+int dys_step_many(dys_handle* h, int32_t first_day, int32_t n_days, const uint8_t* open_flags /* nullable */);
 int dys_step_begin(dys_handle* h, int32_t day, const dys_injected* injected /* nullable */);
 int dys_step_end(dys_handle* h, int32_t day);
 
@@ -160,7 +164,7 @@ int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, int32_t* t_
  * memory: this call only waits for it.  The pointers stay valid until DYS_OUT_RING - 1 further days have been stepped,
  * so a host loop can queue day d+1 before it consumes day d (the lockdown decision lags `diagnosis` = 7 days,
  * contagious3.py:306-309, so nothing a day produces is needed to start the next one). */
-#define DYS_OUT_RING 4
+#define DYS_OUT_RING 16
 typedef struct dys_day_outputs {
     int32_t day;
     int32_t events_inline;       /* how many of the n_events pairs are in `events` (the rest: dys_get_events) */
