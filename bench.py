@@ -197,15 +197,21 @@ def run_ours(args):
         clocks.start()
 
     # ---- pass 1: resident throughput (`value`) ----
+    def run_resident(first, last):
+        # weeks of days per call: dys_step_many runs each window as ONE cooperative launch (k_days)
+        d = first
+        while d < last:
+            n = min(7, last - d)
+            eng.step_many(d, n)
+            d += n
+
     with torch.cuda.stream(stream):
-        for d in range(W):
-            day_step(eng, d)
+        run_resident(0, W)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clocks.active = True
         ev0.record(stream)
-        for d in range(W, W + K):
-            day_step(eng, d)
+        run_resident(W, W + K)
         ev1.record(stream)
         barrier()
         clocks.active = False
@@ -300,8 +306,12 @@ def run_ours(args):
             ms = ms_k[i] / n_k[i]
             per_kernel[name] = {"ms_per_launch": ms, "algorithmic_bytes_per_launch": kb[name] / K,
                                 "achieved_gbs": kb[name] / K / (ms * 1e-3) / 1e9}
-    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"])
-    k_ms, kbytes, achieved = per_kernel[dom]["ms_per_launch"], per_kernel[dom]["algorithmic_bytes_per_launch"] * K, per_kernel[dom]["achieved_gbs"]
+    # the product path runs a window of days as ONE cooperative launch (k_days = push_body + agent_body per day): its
+    # per-day duration is the resident pass above (CUDA events on the launching stream), its bytes the two bodies' sum
+    dom = "k_days (per simulated day; k_push + k_agent bodies fused, one cooperative launch per 7 days)"
+    k_ms = ms_value / K
+    kbytes = sum(kb.values())
+    achieved = kbytes / K / (k_ms * 1e-3) / 1e9
 
     if rank != 0:
         if world > 1:
@@ -326,7 +336,7 @@ def run_ours(args):
         },
         "e2e": {"value": n_total * K / s_e2e, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "ms_per_step": s_e2e * 1e3 / K},
-        "gpu_launches": 2 * K,       # k_push + k_agent per day (k_snapshot only on the first day after a load)
+        "gpu_launches": -(-K // 7),  # one cooperative k_days launch per 7-day window (k_snapshot only after a load)
         "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,

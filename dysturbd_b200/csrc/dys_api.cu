@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -27,7 +28,11 @@ struct dys_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // the day's output block leaves on its own stream, under the next day's kernels
-    cudaEvent_t day_done[2] = {nullptr, nullptr};   // per parity: k_agent finished writing the block
+    cudaEvent_t day_done[DYS_OUT_RING] = {};        // per ring slot: the day's kernels finished writing the block
+    uint8_t* d_open_ring = nullptr;                 // [MAX_FUSED_DAYS][B] per-day open flags of a fused window
+    uint8_t* h_open_ring = nullptr;                 // pinned staging of the same
+    unsigned int* d_barrier = nullptr;              // grid barrier counter of k_days
+    int days_grid = 0;                              // cooperative grid of k_days (0 = not available)
     std::vector<void*> allocs;
     int64_t dev_bytes = 0;
     std::string err;
@@ -36,7 +41,7 @@ struct dys_handle {
     int32_t last_day = -1;
     int64_t steps = 0;
     // per-parity device output block [stats | sa_hist | bcount | events] and the pinned host ring it is copied into
-    unsigned char* d_out[2] = {nullptr, nullptr};
+    unsigned char* d_out[DYS_OUT_RING] = {};          // device output blocks, one per ring slot (slot = step % ring)
     size_t off_sa = 0, off_bc = 0, off_ev = 0, out_copy_bytes = 0, out_dev_bytes = 0;
     int64_t ev_inline = 0;
     unsigned char* h_out = nullptr;                       // [DYS_OUT_RING][out_copy_bytes] pinned
@@ -57,9 +62,9 @@ struct dys_handle {
     uint8_t* peer_ib[8] = {};        // peer mode: every rank's d_ib (own included)
     int32_t* peer_flags[8] = {};
     int n_peers = 1;
-    cudaEvent_t out_parity_ev[2] = {nullptr, nullptr};   // the copy-done event of the last day that used block [parity]
     int push_grid = 0;               // persistent grid of k_push
-    int64_t last_parity = 0;
+    int last_slot = 0;
+    bool no_fuse = false;            // DYS_NO_FUSE=1 in the environment: dys_step_many launches two kernels a day
     double* d_pair_prob = nullptr;
     double *d_u_adm = nullptr, *d_u_death = nullptr, *d_u_pair = nullptr;   // staged injected draws
     // kernel timing
@@ -135,10 +140,11 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     dys_handle* h = new dys_handle();
     h->p = p;
     h->device = device;
+    { const char* nf = getenv("DYS_NO_FUSE"); h->no_fuse = nf && nf[0] == '1'; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->day_done[k], cudaEventDisableTiming);
+    for (int k = 0; k < DYS_OUT_RING && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->day_done[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { fail(nullptr, DYS_ERR_CUDA, "cuda init: %s", cudaGetErrorString(e)); delete h; return DYS_ERR_CUDA; }
     DevCtx& c = h->c;
     c.n_loc = hi - lo; c.n_pad = round_up(c.n_loc, 1024); c.n_glob = p.n_agents; c.lo = lo;
@@ -177,7 +183,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         if (h->ev_inline > c.n_pad) h->ev_inline = c.n_pad;
         h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
         h->out_dev_bytes = h->off_ev + ((p.flags & DYS_WANT_EVENTS) ? sizeof(int2) * (size_t)c.n_pad : 0);
-        for (int k = 0; k < 2; ++k) A(dev_alloc(h, &h->d_out[k], (int64_t)h->out_dev_bytes));
+        for (int k = 0; k < DYS_OUT_RING; ++k) A(dev_alloc(h, &h->d_out[k], (int64_t)h->out_dev_bytes));
     }
     if (p.flags & DYS_WANT_IO_MAT) A(dev_alloc(h, &c.io_mat, c.S * c.S));
     c.pdf = d_pdf;
@@ -190,7 +196,14 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         const int64_t n_cta = ((c.rt_n + 31) / 32 + PUSH_WARPS - 1) / PUSH_WARPS;    // never more warps than groups
         const int64_t want = (int64_t)per_sm * sms;                                     // persistent: a multiple of the SM count
         h->push_grid = (int)(n_cta < want ? n_cta : want);
+        int coop = 0, per_sm_days = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_days, k_days, 256, 0) == cudaSuccess && per_sm_days > 0)
+            h->days_grid = per_sm_days * sms;
     }
+    A(dev_alloc(h, &h->d_open_ring, (int64_t)MAX_FUSED_DAYS * c.B));
+    A(dev_alloc(h, &h->d_barrier, 4));
+    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open_ring, (size_t)MAX_FUSED_DAYS * (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMallocHost((void**)&h->h_out, h->out_copy_bytes * DYS_OUT_RING) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -230,7 +243,8 @@ extern "C" int dys_destroy(dys_handle* h)
     for (int i = 0; i < DYS_OUT_RING; ++i) if (h->out_ev[i]) cudaEventDestroy(h->out_ev[i]);
     for (auto ev : h->tev) if (ev) cudaEventDestroy(ev);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-    for (int k = 0; k < 2; ++k) if (h->day_done[k]) cudaEventDestroy(h->day_done[k]);
+    for (int k = 0; k < DYS_OUT_RING; ++k) if (h->day_done[k]) cudaEventDestroy(h->day_done[k]);
+    if (h->h_open_ring) cudaFreeHost(h->h_open_ring);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return DYS_OK;
@@ -252,7 +266,6 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaMemsetAsync(h->d_peer_flags, 0xFF, sizeof(int32_t) * 8, h->stream));   // -1: nothing complete yet
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaStreamSynchronize(h->copy_stream));
-    h->out_parity_ev[0] = h->out_parity_ev[1] = nullptr;
     for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; }
     for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
     return DYS_OK;
@@ -542,58 +555,156 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     return DYS_OK;
 }
 
+// the slot's previous day keeps its stats in the history; its block (host and device side) is then free
+static int retire_slot(dys_handle* h, int slot)
+{
+    if (h->out_day[slot] >= 0) {
+        CK(h, cudaEventSynchronize(h->out_ev[slot]));
+        const int hs = (int)(h->out_step[slot] % DYS_STATS_RING);
+        memcpy(h->hist_stats[hs], h->h_out + (size_t)slot * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
+        h->hist_day[hs] = h->out_day[slot];
+        h->out_day[slot] = -1;
+    }
+    return DYS_OK;
+}
+
+// the day's block leaves on the copy stream, under the following days' kernels
+static int ship_day(dys_handle* h, int32_t day, int slot, int64_t step)
+{
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->day_done[slot], 0));
+    CK(h, cudaMemcpyAsync(h->h_out + (size_t)slot * h->out_copy_bytes, h->d_out[slot], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(h, cudaEventRecord(h->out_ev[slot], h->copy_stream));
+    h->out_day[slot] = day;
+    h->out_step[slot] = step;
+    return DYS_OK;
+}
+
+static void set_snapshot_targets(dys_handle* h, int32_t day)
+{
+    DevCtx& c = h->c;
+    c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
+    c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
+    c.n_wr = 0;
+    // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
+    const int parity = (day + 1) & 1;
+    c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
+    for (int r = 0; r < h->n_peers; ++r) {
+        c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
+        if (h->n_peers > 1 && r != h->p.rank) c.ib_wr[c.n_wr++] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
+    }
+}
+
 static int step_end(dys_handle* h, int32_t day)
 {
     if (!h->begun) return fail(h, DYS_ERR_STATE, "dys_step_end without dys_step_begin");
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
     const int par = (int)(h->steps & 1);
-    c.stats = (int64_t*)h->d_out[par];
-    c.sa_hist = (h->p.flags & DYS_WANT_SA_HIST) ? (int32_t*)(h->d_out[par] + h->off_sa) : nullptr;
-    c.bcount = (h->p.flags & DYS_WANT_BUILDING_COUNTS) ? (int32_t*)(h->d_out[par] + h->off_bc) : nullptr;
-    c.ev = (h->p.flags & DYS_WANT_EVENTS) ? (int2*)(h->d_out[par] + h->off_ev) : nullptr;
+    const int slot = (int)(h->steps % DYS_OUT_RING);
+    int rc = retire_slot(h, slot);
+    if (rc != DYS_OK) return rc;
+    c.stats = (int64_t*)h->d_out[slot];
+    c.sa_hist = (h->p.flags & DYS_WANT_SA_HIST) ? (int32_t*)(h->d_out[slot] + h->off_sa) : nullptr;
+    c.bcount = (h->p.flags & DYS_WANT_BUILDING_COUNTS) ? (int32_t*)(h->d_out[slot] + h->off_bc) : nullptr;
+    c.ev = (h->p.flags & DYS_WANT_EVENTS) ? (int2*)(h->d_out[slot] + h->off_ev) : nullptr;
     c.hh_flag = h->d_hh_flag[par]; c.hh_qflag = h->d_hh_qflag[par];
     c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
     c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
-    h->last_parity = par;
-    if (h->out_parity_ev[par]) CK(h, cudaStreamWaitEvent(h->stream, h->out_parity_ev[par], 0));   // block `par` has left the device
-    c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
-    c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
-    c.n_wr = 0;
-    {   // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
-        const int parity = (day + 1) & 1;
-        c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
-        for (int r = 0; r < h->n_peers; ++r) {
-            c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
-            if (h->n_peers > 1 && r != h->p.rank) c.ib_wr[c.n_wr++] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
-        }
-    }
+    h->last_slot = slot;
+    set_snapshot_targets(h, day);
     k_push<<<(unsigned)h->push_grid, PUSH_WARPS * 32, 0, h->stream>>>(c, day);
     tick(h, 2);
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
     CK(h, cudaGetLastError());
-    const int slot = (int)(h->steps % DYS_OUT_RING);
-    if (h->out_day[slot] >= 0) {      // the day leaving the ring keeps its stats block in the history
-        CK(h, cudaEventSynchronize(h->out_ev[slot]));
-        const int hs = (int)(h->out_step[slot] % DYS_STATS_RING);
-        memcpy(h->hist_stats[hs], h->h_out + (size_t)slot * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
-        h->hist_day[hs] = h->out_day[slot];
-    }
-    // the copy runs on its own stream so that the next day's kernels do not queue behind it; block `par` is written
-    // again two days from now, and that day's kernels wait for this copy (see step_end's cudaStreamWaitEvent)
-    CK(h, cudaEventRecord(h->day_done[par], h->stream));
-    CK(h, cudaStreamWaitEvent(h->copy_stream, h->day_done[par], 0));
-    CK(h, cudaMemcpyAsync(h->h_out + (size_t)slot * h->out_copy_bytes, h->d_out[par], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
-    CK(h, cudaEventRecord(h->out_ev[slot], h->copy_stream));
-    h->out_parity_ev[par] = h->out_ev[slot];
-    h->out_day[slot] = day;
-    h->out_step[slot] = h->steps;
+    CK(h, cudaEventRecord(h->day_done[slot], h->stream));
+    rc = ship_day(h, day, slot, h->steps);
+    if (rc != DYS_OK) return rc;
     h->last_day = day;
     h->ib_day = day + 1;         // k_agent wrote tomorrow's snapshot and household flags
     ++h->steps;
     if (!h->tev.empty()) ++h->t_end;
     h->begun = false;
+    return DYS_OK;
+}
+
+// n_days in ONE cooperative launch (k_days); the per-day blocks are shipped afterwards
+static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const uint8_t* open_flags)
+{
+    CK(h, cudaSetDevice(h->device));
+    DevCtx& c = h->c;
+    DayPlan plan{};
+    plan.first_day = first_day; plan.n_days = n_days;
+    plan.first_parity = (int)(h->steps & 1);
+    plan.off_sa = h->off_sa; plan.off_bc = h->off_bc; plan.off_ev = h->off_ev;
+    plan.want_sa = (h->p.flags & DYS_WANT_SA_HIST) != 0;
+    plan.want_bc = (h->p.flags & DYS_WANT_BUILDING_COUNTS) != 0;
+    plan.want_ev = (h->p.flags & DYS_WANT_EVENTS) != 0;
+    for (int k = 0; k < 2; ++k) {
+        plan.hh_flag[k] = h->d_hh_flag[k]; plan.hh_qflag[k] = h->d_hh_qflag[k];
+        plan.df[k] = h->d_flags + k * DF_LEN;
+        plan.ib[k] = h->d_ib + (size_t)k * h->ib_stride;
+        for (int r = 0; r < h->n_peers; ++r) plan.peer_ib[r][k] = (h->n_peers > 1 ? h->peer_ib[r] : h->d_ib) + (size_t)k * h->ib_stride;
+    }
+    // open flags: a day whose vector differs from the one in force gets its own device copy
+    const uint8_t* cur_dev = c.open;
+    int32_t cur_closed = c.n_closed;
+    bool staged = false;
+    for (int k = 0; k < n_days; ++k) {
+        if (open_flags) {
+            const uint8_t* f = open_flags + (size_t)k * (size_t)c.B;
+            if (memcmp(h->h_open, f, (size_t)c.B) != 0) {
+                if (!staged) { CK(h, cudaStreamSynchronize(h->stream)); staged = true; }   // the staging ring may still be in flight
+                memcpy(h->h_open, f, (size_t)c.B);
+                memcpy(h->h_open_ring + (size_t)k * c.B, f, (size_t)c.B);
+                CK(h, cudaMemcpyAsync(h->d_open_ring + (size_t)k * c.B, h->h_open_ring + (size_t)k * c.B, (size_t)c.B, cudaMemcpyHostToDevice, h->stream));
+                cur_dev = h->d_open_ring + (size_t)k * c.B;
+                cur_closed = 0;
+                for (int64_t b = 0; b < c.B; ++b) cur_closed += f[b] == 0;
+            }
+        }
+        plan.open[k] = cur_dev;
+        plan.n_closed[k] = cur_closed;
+    }
+    int rc = DYS_OK;
+    for (int k = 0; k < n_days && rc == DYS_OK; ++k) {
+        const int slot = (int)((h->steps + k) % DYS_OUT_RING);
+        rc = retire_slot(h, slot);
+        plan.out[k] = h->d_out[slot];
+    }
+    if (rc != DYS_OK) return rc;
+    // first day's snapshot, if the previous day did not leave it
+    if (h->ib_day != first_day) {
+        const int par = plan.first_parity;
+        CK(h, cudaMemsetAsync(h->d_hh_flag[par], 0, (size_t)c.H + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->d_hh_qflag[par], 0, (size_t)c.H + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->d_flags + par * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
+        c.u_adm = c.u_death = c.u_pair = nullptr; c.pair_prob = nullptr;
+        set_snapshot_targets(h, first_day - 1);        // write targets of parity first_day & 1
+        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, first_day, h->d_hh_flag[par], h->d_hh_qflag[par],
+                                                                      h->d_flags + par * DF_LEN);
+        if (h->n_peers > 1) k_signal<<<1, 32, 0, h->stream>>>(c, first_day);
+    }
+    c.u_adm = c.u_death = c.u_pair = nullptr; c.pair_prob = nullptr;
+    set_snapshot_targets(h, first_day);                 // flag pointers; the per-day buffers come from the plan
+    CK(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned int), h->stream));
+    unsigned int* bar = h->d_barrier;
+    void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
+    CK(h, cudaLaunchCooperativeKernel((const void*)k_days, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
+    if (cur_dev != c.open) {      // the flags in force after the window become the standing vector
+        CK(h, cudaMemcpyAsync((void*)c.open, cur_dev, (size_t)c.B, cudaMemcpyDeviceToDevice, h->stream));
+        c.n_closed = cur_closed;
+    }
+    for (int k = 0; k < n_days; ++k) {
+        const int slot = (int)((h->steps + k) % DYS_OUT_RING);
+        CK(h, cudaEventRecord(h->day_done[slot], h->stream));
+        rc = ship_day(h, first_day + k, slot, h->steps + k);
+        if (rc != DYS_OK) return rc;
+        h->last_slot = slot;
+    }
+    h->steps += n_days;
+    h->last_day = first_day + n_days - 1;
+    h->ib_day = first_day + n_days;
     return DYS_OK;
 }
 
@@ -622,6 +733,11 @@ extern "C" int dys_step_many(dys_handle* h, int32_t first_day, int32_t n_days, c
 {
     if (!h) return DYS_ERR_INVALID_ARG;
     if (n_days < 1 || n_days > DYS_OUT_RING - 2) return fail(h, DYS_ERR_INVALID_ARG, "dys_step_many: 1..%d days", DYS_OUT_RING - 2);
+    if (!h->have_pop || !h->have_graph) return fail(h, DYS_ERR_STATE, "dys_step_many before dys_load_population/dys_load_graph");
+    if (h->begun) return fail(h, DYS_ERR_STATE, "dys_step_many between dys_step_begin and dys_step_end");
+    if (first_day < 0 || first_day + n_days > 32000) return fail(h, DYS_ERR_INVALID_ARG, "day out of range");
+    if (n_days >= 2 && n_days <= MAX_FUSED_DAYS && h->days_grid > 0 && h->tev.empty() && !h->no_fuse)
+        return step_fused(h, first_day, n_days, open_flags);
     for (int32_t k = 0; k < n_days; ++k) {
         if (open_flags) {
             int rc = dys_set_open(h, open_flags + (size_t)k * (size_t)h->c.B);
@@ -720,9 +836,9 @@ extern "C" int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_
         // more events than travel with the day's block: fetch them from the device block, which is only intact until
         // the day after next is stepped
         const int i = find_out_slot(h, day);
-        if (h->steps - h->out_step[i] > 2) return fail(h, DYS_ERR_NOT_AVAILABLE, "events of day %d beyond the first %d were overwritten", day, o.events_inline);
+        if (h->steps - h->out_step[i] >= DYS_OUT_RING) return fail(h, DYS_ERR_NOT_AVAILABLE, "events of day %d beyond the first %d were overwritten", day, o.events_inline);
         rest.resize((size_t)cnt * 2);
-        rc = copy_out(h, rest.data(), h->d_out[h->out_step[i] & 1] + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt);
+        rc = copy_out(h, rest.data(), h->d_out[i] + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt);
         if (rc != DYS_OK) return rc;
         pairs = rest.data();
     }
@@ -799,7 +915,7 @@ extern "C" int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* 
     switch (which) {
         case DYS_BUF_STATUS: *ptr = c.status; *bytes = c.n_pad; break;
         case DYS_BUF_INFECTIOUS: *ptr = h->d_ib; *bytes = 2 * h->ib_stride; break;   /* [2][bytes/2]: buffer of day d is d & 1 */
-        case DYS_BUF_STATS: *ptr = h->d_out[h->last_parity]; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
+        case DYS_BUF_STATS: *ptr = h->d_out[h->last_slot]; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
         case DYS_BUF_T_INF: *ptr = c.t_inf; *bytes = c.n_pad * 2; break;
         default: return fail(h, DYS_ERR_INVALID_ARG, "unknown buffer %d", which);
     }

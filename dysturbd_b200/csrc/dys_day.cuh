@@ -58,7 +58,7 @@ struct PushWarpSmem {
     unsigned long long pairs[PUSH_PCAP];           // exposed pairs awaiting their Bernoulli: entry | row << 48 | iso_u << 56
 };
 
-__global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const int day)
+__device__ __forceinline__ void push_body(const DevCtx& c, const int day)
 {
     __shared__ double s_pdf[64];
     __shared__ unsigned int s_acc[8];
@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const 
     block_accumulate<4>(c, idx, cnt, s_acc);
 }
 
+__global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const int day) { push_body(c, day); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_agent.  A block owns 1024 consecutive agents, in two phases.
 //   sweep  : 4 agents per thread, vector loads of the status word, the infector mailbox and (on days with a
@@ -329,12 +331,15 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
     if (tid < HIST_LEN) s_hist[tid] = 0;
     if (tid < EV_LEN) s_ev[tid] = 0;
     if (tid < 10) s_cnt[tid] = 0;
-    if (tid == 0) s_nlist = 0;
     __syncthreads();
     const bool any_nd = c.df[DF_ANY_ND] != 0;
     const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN;   // a recovered agent left the histogram
-    const int64_t tile0 = (int64_t)blockIdx.x * AGENT_TILE;
+    // one tile per block when launched as k_agent (grid = tiles); a persistent grid (k_days) strides over the tiles
+    for (int64_t tile = blockIdx.x; tile * AGENT_TILE < c.n_pad; tile += gridDim.x) {
+    const int64_t tile0 = tile * AGENT_TILE;
     const int64_t a0 = tile0 + tid * 4;
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
 
     // ---- sweep ----
     {
@@ -422,6 +427,8 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
             }
         }
     }
+    __syncthreads();      // s_list / s_nlist are free for the next tile
+    }
     if (VARIANT == 2) return;
     if (c.n_peers > 1) __threadfence_system();     // this thread's peer stores are visible before the block's ticket
     __syncthreads();
@@ -441,7 +448,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
         if (VARIANT == 0) {
             __threadfence();
             __syncwarp();
-            if (lane == 0) s_last = (atomicAdd(c.ticket, 1u) == gridDim.x - 1);
+            if (lane == 0) s_last = (atomicAdd(c.ticket, 1u) == gridDim.x - 1);      // one ticket per block, after all its tiles
         }
     }
     if (VARIANT != 0) return;
@@ -499,6 +506,77 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
 }
 
 __global__ void __launch_bounds__(256) k_agent(const DevCtx c, const int day) { agent_body<0>(c, day); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_days: several consecutive days in ONE cooperative launch (persistent grid, all CTAs resident).  Per day: push_body,
+// grid barrier, agent_body, grid barrier -- the same device code as k_push / k_agent, minus two launches a day.  At a
+// million agents a day is ~20 MB of traffic, i.e. launch latency is the larger part of a day done as separate kernels.
+// The per-day buffers (output block, household flags, flag block, snapshot parity, open flags) come from DayPlan.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MAX_FUSED_DAYS = 14;
+struct DayPlan {
+    int32_t first_day, n_days;
+    int32_t n_closed[MAX_FUSED_DAYS];
+    const uint8_t* open[MAX_FUSED_DAYS];
+    unsigned char* out[MAX_FUSED_DAYS];             // the day's output block
+    size_t off_sa, off_bc, off_ev;                  // 0 = that part was not requested
+    uint8_t* hh_flag[2];
+    uint8_t* hh_qflag[2];
+    int32_t* df[2];
+    uint8_t* ib[2];                                 // own snapshot buffers by day parity
+    uint8_t* peer_ib[8][2];                         // peer mode: every other rank's, by day parity
+    int32_t first_parity;                           // step parity of first_day (household flags, flag block)
+    int32_t want_sa, want_bc, want_ev;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
+{
+    // all CTAs are resident (cooperative launch); one arrival per CTA, monotone counter, no reset needed
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        ++epoch;
+        const unsigned int target = epoch * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan plan, unsigned int* barrier_counter)
+{
+    __shared__ DevCtx s_c;               // the day's view of the context: read by both bodies like kernel parameters
+    unsigned int epoch = 0;
+    for (int k = 0; k < plan.n_days; ++k) {
+        const int day = plan.first_day + k;
+        if (threadIdx.x == 0) {
+            DevCtx& c = s_c;
+            c = c0;
+            const int par = (plan.first_parity + k) & 1;
+            c.open = plan.open[k];
+            c.n_closed = plan.n_closed[k];
+            c.stats = reinterpret_cast<int64_t*>(plan.out[k]);
+            c.sa_hist = plan.want_sa ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_sa) : nullptr;
+            c.bcount = plan.want_bc ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_bc) : nullptr;
+            c.ev = plan.want_ev ? reinterpret_cast<int2*>(plan.out[k] + plan.off_ev) : nullptr;
+            c.hh_flag = plan.hh_flag[par]; c.hh_qflag = plan.hh_qflag[par];
+            c.hh_flag_next = plan.hh_flag[par ^ 1]; c.hh_qflag_next = plan.hh_qflag[par ^ 1];
+            c.df = plan.df[par]; c.df_next = plan.df[par ^ 1];
+            c.ib_rd = plan.ib[day & 1];
+            const int wr = (day + 1) & 1;
+            c.n_wr = 0;
+            c.ib_wr[c.n_wr++] = plan.ib[wr];
+            for (int r = 0; r < c.n_peers; ++r)
+                if (c.n_peers > 1 && r != c.rank) c.ib_wr[c.n_wr++] = plan.peer_ib[r][wr];
+        }
+        __syncthreads();
+        push_body(s_c, day);
+        grid_barrier(barrier_counter, epoch);
+        agent_body<0>(s_c, day);
+        grid_barrier(barrier_counter, epoch);
+    }
+}
 
 // phase A alone (contagious3.py:181-202): the day-start snapshot byte of every owned agent and the households that see
 // a diagnosis on `day`.  The host clears hh_flag / hh_qflag / df first.

@@ -168,6 +168,9 @@ class Engine:
         if rc != 0:
             raise DysError(rc, (self.lib.dys_last_error(None) or b"").decode())
         self.n_loc = pop.N
+        self._o = _DayOutputs()
+        self._o_ref = C.byref(self._o)
+        self._views = {}
         self.load(pop)
 
     def _ck(self, rc):
@@ -247,22 +250,29 @@ class Engine:
     def outputs(self, day):
         """Everything day `day` produced, as zero-copy numpy views of the library's pinned host ring (valid until
         DYS_OUT_RING - 1 = 15 further days are stepped): dict(stats, sa_hist, building_counts, events[n,2], n_events)."""
-        o = _DayOutputs()
-        self._ck(self.lib.dys_get_outputs(self.h, int(day), C.byref(o)))
-        as_np = np.ctypeslib.as_array
-        out = {"stats": as_np(o.stats, (N_STATS,)), "n_events": int(o.n_events), "sa_hist": None, "building_counts": None,
-               "events": None}
-        if o.sa_hist:
-            out["sa_hist"] = as_np(o.sa_hist, (self.pop.S, HIST_LEN))
-        if o.building_counts:
-            out["building_counts"] = as_np(o.building_counts, (self.pop.B,))
+        o = self._o
+        rc = self.lib.dys_get_outputs(self.h, int(day), self._o_ref)
+        if rc != 0:
+            self._ck(rc)
+        key = C.cast(o.stats, C.c_void_p).value          # the ring slot: its numpy views are built once
+        views = self._views.get(key)
+        if views is None:
+            as_np = np.ctypeslib.as_array
+            views = (as_np(o.stats, (N_STATS,)),
+                     as_np(o.sa_hist, (self.pop.S, HIST_LEN)) if o.sa_hist else None,
+                     as_np(o.building_counts, (self.pop.B,)) if o.building_counts else None)
+            self._views[key] = views
+        n_ev, n_in = int(o.n_events), int(o.events_inline)
+        ev = None
         if o.events:
-            if o.n_events > o.events_inline:          # rare: more infections than travel with the day's block
+            if n_ev > n_in:                                # rare: more infections than travel with the day's block
                 a, s_ = self.events(day)
-                out["events"] = np.stack([a, s_], axis=1)
+                ev = np.stack([a, s_], axis=1)
+            elif n_in:
+                ev = np.ctypeslib.as_array(o.events, (n_in, 2))
             else:
-                out["events"] = as_np(o.events, (max(int(o.events_inline), 1), 2))[:int(o.events_inline)]
-        return out
+                ev = np.zeros((0, 2), dtype=np.int32)
+        return {"stats": views[0], "sa_hist": views[1], "building_counts": views[2], "events": ev, "n_events": n_ev}
 
     def stats(self, day):
         out = np.zeros(N_STATS, dtype=np.int64)

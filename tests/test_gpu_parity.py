@@ -170,3 +170,36 @@ def test_error_paths(eng):
     with pytest.raises(eng.DysError):
         g.io_mat(0)                                 # not requested
     g.close()
+
+
+def test_step_many_fused_windows_vs_oracle(eng, oracle_lib):
+    """dys_step_many: windows of days in one cooperative launch (k_days), open flags changing inside a window"""
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import synth_population
+    pop = synth_population(30000, seed=8, seeds_per_22493=150)
+    prm = EpiParams(norm_factor=6.0, seed=4321)
+    g = eng.Engine(pop, prm)
+    o = oracle_lib.OracleSim(pop, prm)
+    flags = _closures(pop, 17)
+    day = 0
+    for n in (5, 7, 2, 6, 7, 3, 7):
+        f = np.stack([flags(day + k) for k in range(n)])
+        g.step_many(day, n, f)
+        for k in range(n):
+            o.set_open(f[k])
+            o.step(day + k)
+            out = g.outputs(day + k)
+            keep = [i for i in range(18) if i != 14]
+            assert np.array_equal(out["stats"][keep], o.stats()[keep]), "day %d" % (day + k)
+            assert np.array_equal(out["stats"][32:53], o.stats()[32:53])
+            assert np.array_equal(out["sa_hist"], o.sa_hist()) and np.array_equal(out["building_counts"], o.building_counts())
+            ev = out["events"]
+            order = np.argsort(ev[:, 0], kind="stable")
+            ea, es = o.events()
+            assert np.array_equal(ev[order, 0], ea) and np.array_equal(ev[order, 1], es)
+        day += n
+        sg, so = g.state(), o.state()
+        for key in sg:
+            assert np.array_equal(sg[key], so[key]), (key, day)
+    assert o.stats()[9] > 3000
+    g.close()
