@@ -44,6 +44,8 @@ __device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, uint
 // of their lengths) so every lane works on consecutive entries however the infectious agents are spread; four entries
 // per lane are in flight (one coalesced 4-byte read + one 1-byte status gather each).
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int PUSH_WARPS = 8;
 constexpr int PUSH_CHUNK = 128;                    // halo agents scanned per warp step (4 snapshot bytes per lane): small
                                                    // steps spread the infectious rows over all resident warps
@@ -163,8 +165,12 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
                 const bool ex = sus && ((cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
                                         ((cls & CLS_OO) && !iso_u && !iso_i));
                 const unsigned m = __ballot_sync(0xffffffffu, ex);
-                if (ex) w.pairs[np + __popc(m & lt_mask)] = (unsigned long long)e[k] | ((unsigned long long)r[k] << 48) |
-                                                            ((unsigned long long)iso_u << 56);
+                if (ex) {
+                    w.pairs[np + __popc(m & lt_mask)] = (unsigned long long)e[k] | ((unsigned long long)r[k] << 48) |
+                                                        ((unsigned long long)iso_u << 56);
+                    prefetch_l2(c.tval + e[k]);                 // both are read when the pair is settled
+                    prefetch_l2(c.risk + (cw[k] & COL_MASK));
+                }
                 np += __popc(m);
             }
             __syncwarp();
@@ -198,7 +204,10 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const uint32_t byte = (v >> (8 * b)) & 0xFFu;
-                    if ((byte & IB_INF) && il0 + b < (uint32_t)c.rt_n) { w.q_idx[pos] = il0 + b; w.q_ib[pos] = (uint8_t)byte; ++pos; }
+                    if ((byte & IB_INF) && il0 + b < (uint32_t)c.rt_n) {
+                        w.q_idx[pos] = il0 + b; w.q_ib[pos] = (uint8_t)byte; ++pos;
+                        prefetch_l2(c.tptr + il0 + b);          // the row extent is needed when the queue is expanded
+                    }
                 }
             }
             nq += __shfl_sync(0xffffffffu, incl, 31);
@@ -242,13 +251,23 @@ constexpr int AGENT_TILE = 1024;
 
 // one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
 __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
-                                             unsigned int* s_cnt, unsigned int* s_ev, unsigned int* s_hist, bool& infected_today,
-                                             int& infector)
+                                             const uint32_t st, const int mailbox, unsigned int* s_cnt, unsigned int* s_ev,
+                                             unsigned int* s_hist, bool& infected_today, int& infector)
 {
-    const uint32_t st = c.status[a];
+    // every column this agent can need is requested before any of it is used: the per-agent latency is two dependent
+    // round trips (columns, then the household flags) instead of one per rule
+    int ti = c.t_inf[a];
+    int tq = c.t_q[a];
+    const int h = any_nd ? __ldg(c.hh + a) : 0;
+    const int sa_a = c.sa_hist ? __ldg(c.sa + a) : -1;
+    const int home_a = c.bcount ? __ldg(c.home + a) : 0;
+    bool f_hh = false, f_q = false;
+    if (any_nd) {
+        f_hh = __ldg(c.hh_flag + h) != 0;
+        f_q = (__ldg(c.hh_qflag + h) != 0) || (c.hh_always && __ldg(c.hh_always + h));
+    }
     uint32_t x = st;
-    int ti = in_set(M_EVER, st) ? (int)c.t_inf[a] : 0;
-    int tq = in_set(M_ISO, st) ? (int)c.t_q[a] : 0;
+    if (!in_set(M_EVER, st)) ti = 0;
     bool w_ti = false, w_tq = false;
     infected_today = false;
     // ---- B, C (contagious3.py:205-227) on the day-start status; D's result from the mailbox ----
@@ -265,7 +284,7 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
         }
     } else if (in_set(M_SUS, st)) {
         atomicAdd(&s_cnt[8], 1u);
-        infector = c.src[a];
+        infector = mailbox;
         if (infector >= 0) {                                                 // :241-248: k_push found an infector
             x = (st == ST_S) ? ST_I : ST_QI;
             ti = day; w_ti = true;
@@ -283,9 +302,8 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
     if (x == ST_D && n_inf == c.diagnosis) atomicAdd(&s_ev[EV_NEW_DIAG], 1u);               // :261
     // ---- F (contagious3.py:261-270): the households diagnosed today were flagged yesterday ----
     if (any_nd && (x == ST_S || x == ST_I)) {
-        const int h = __ldg(c.hh + a);
-        bool hit = __ldg(c.hh_flag + h);                                                    // :263
-        if (x == ST_I && !hit) hit = __ldg(c.hh_qflag + h) || (c.hh_always && __ldg(c.hh_always + h));   // :267 whole-row isin
+        bool hit = f_hh;                                                                    // :263
+        if (x == ST_I && !hit) hit = f_q;                                                   // :267 whole-row isin
         if (hit && c.compliance < 1.0)
             hit = keyed_uniform(c.seed, day, STREAM_COMPLIANCE, (uint32_t)(c.lo + a), 0) < c.compliance;
         if (hit) { x = (x == ST_S) ? ST_QH : ST_QI; tq = day; w_tq = true; }                // :265-270
@@ -301,14 +319,14 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
         if (k >= 0 && k < HIST_LEN) {
             if (k == 0) atomicAdd(&s_ev[EV_DAILY_INF], 1u);
             atomicAdd(&s_hist[k], 1u);
-            if (c.sa_hist) { const int sa = __ldg(c.sa + a); if (sa >= 0) atomicAdd(&c.sa_hist[(size_t)sa * HIST_LEN + k], 1); }
+            if (c.sa_hist && sa_a >= 0) atomicAdd(&c.sa_hist[(size_t)sa_a * HIST_LEN + k], 1);
             if (c.io_mat && infected_today) {
                 // contagious3.py:356-366: row = area of today's infected, column = area of the infector
                 const int sa_u = __ldg(c.sa + a), sa_i = __ldg(c.sa + (infector - c.lo));
                 if (sa_u >= 0 && sa_i >= 0) atomicAdd(&c.io_mat[(size_t)sa_u * c.S + sa_i], 1);
             }
         }
-        if (c.bcount && in_set(M_INF, x)) atomicAdd(&c.bcount[__ldg(c.home + a)], 1);
+        if (c.bcount && in_set(M_INF, x)) atomicAdd(&c.bcount[home_a], 1);
     }
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
@@ -324,6 +342,8 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
     __shared__ unsigned int s_cnt[10];            // 8 end-of-day status counts (hist_idx order), sus0, inf0
     __shared__ unsigned int s_nlist;
     __shared__ unsigned short s_list[AGENT_TILE];
+    __shared__ uint32_t s_stw[AGENT_TILE / 4];      // the tile's status words, for the settle phase
+    __shared__ __align__(16) int s_src[AGENT_TILE]; // the tile's mailbox (infector) column (written 16 bytes at a time)
     __shared__ long long s_fold[N_STATS];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -343,20 +363,21 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
 
     // ---- sweep ----
     {
-        const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
-        const uint32_t st0[4] = {sv.x, sv.y, sv.z, sv.w};
-        uint32_t m_s = 0, m_f = 0;
+        // all three columns are requested at once (the mailbox and household index of a susceptible agent are needed
+        // on almost every day of an epidemic), then the household flags
+        const uint32_t sw = *reinterpret_cast<const uint32_t*>(c.status + a0);
+        const int4 src4 = *reinterpret_cast<const int4*>(c.src + a0);        // the mailbox k_push wrote into
+        int4 hh4 = make_int4(0, 0, 0, 0);
+        if (any_nd) hh4 = __ldg(reinterpret_cast<const int4*>(c.hh + a0));
+        const uint32_t st0[4] = {sw & 0xFFu, (sw >> 8) & 0xFFu, (sw >> 16) & 0xFFu, sw >> 24};
+        s_stw[tid] = sw;
+        *reinterpret_cast<int4*>(&s_src[tid * 4]) = src4;
+        uint32_t m_f = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            m_s |= (uint32_t)(st0[j] == ST_S) << j;
-            m_f |= (uint32_t)(st0[j] == ST_S) << j;
-        }
-        int4 src4 = make_int4(-1, -1, -1, -1);
-        if (m_s) src4 = *reinterpret_cast<const int4*>(c.src + a0);          // the mailbox k_push wrote into
+        for (int j = 0; j < 4; ++j) m_f |= (uint32_t)(st0[j] == ST_S) << j;
         const int srcv[4] = {src4.x, src4.y, src4.z, src4.w};
         uint32_t flagged = 0;                      // susceptible agents whose household sees a diagnosis today
         if (any_nd && m_f) {
-            const int4 hh4 = __ldg(reinterpret_cast<const int4*>(c.hh + a0));
             const int hv[4] = {hh4.x, hh4.y, hh4.z, hh4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -412,8 +433,10 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
         int infector = -1;
         int64_t a = 0;
         if (valid) {
-            a = tile0 + s_list[k];
-            settle_agent(c, day, a, any_nd, s_cnt, s_ev, s_hist, infected_today, infector);
+            const int li = s_list[k];
+            a = tile0 + li;
+            settle_agent(c, day, a, any_nd, (s_stw[li >> 2] >> (8 * (li & 3))) & 0xFFu, s_src[li], s_cnt, s_ev, s_hist,
+                         infected_today, infector);
         }
         // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
         const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
