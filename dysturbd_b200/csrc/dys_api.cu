@@ -546,7 +546,10 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
         ib_targets(day & 1);
         k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day, h->d_hh_flag[par], h->d_hh_qflag[par],
                                                                       h->d_flags + par * DF_LEN);
-        if (h->n_peers > 1) k_signal<<<1, 32, 0, h->stream>>>(c, day);
+        if (h->n_peers > 1) {
+            k_publish<<<(unsigned)h->push_grid, 256, 0, h->stream>>>(c);
+            k_signal<<<1, 32, 0, h->stream>>>(c, day);
+        }
         h->ib_day = day;
     }
     tick(h, 1);
@@ -616,6 +619,10 @@ static int step_end(dys_handle* h, int32_t day)
     tick(h, 2);
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
+    if (h->n_peers > 1) {        // tomorrow's bytes go to every peer GPU, then the flag
+        k_publish<<<(unsigned)h->push_grid, 256, 0, h->stream>>>(c);
+        k_signal<<<1, 32, 0, h->stream>>>(c, day + 1);
+    }
     CK(h, cudaGetLastError());
     CK(h, cudaEventRecord(h->day_done[slot], h->stream));
     rc = ship_day(h, day, slot, h->steps);
@@ -683,7 +690,10 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         set_snapshot_targets(h, first_day - 1);        // write targets of parity first_day & 1
         k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, first_day, h->d_hh_flag[par], h->d_hh_qflag[par],
                                                                       h->d_flags + par * DF_LEN);
-        if (h->n_peers > 1) k_signal<<<1, 32, 0, h->stream>>>(c, first_day);
+        if (h->n_peers > 1) {
+            k_publish<<<(unsigned)h->push_grid, 256, 0, h->stream>>>(c);
+            k_signal<<<1, 32, 0, h->stream>>>(c, first_day);
+        }
     }
     c.u_adm = c.u_death = c.u_pair = nullptr; c.pair_prob = nullptr;
     set_snapshot_targets(h, first_day);                 // flag pointers; the per-day buffers come from the plan

@@ -330,7 +330,7 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
     }
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
-    for (int p = 0; p < c.n_wr; ++p) c.ib_wr[p][c.lo + a] = ibn;
+    c.ib_wr[0][c.lo + a] = ibn;
     if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.hh_flag_next, c.hh_qflag_next, c.df_next);
 }
 
@@ -403,7 +403,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
             }
         }
         // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
-        for (int p = 0; p < c.n_wr; ++p) *reinterpret_cast<uint32_t*>(c.ib_wr[p] + c.lo + a0) = 0u;
+        *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
         // compact the agents that need the settle phase
         const int mine = __popc(work);
         const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
@@ -453,7 +453,6 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
     __syncthreads();      // s_list / s_nlist are free for the next tile
     }
     if (VARIANT == 2) return;
-    if (c.n_peers > 1) __threadfence_system();     // this thread's peer stores are visible before the block's ticket
     __syncthreads();
     if (tid < 32) {
         // warp 0 publishes everything, fences, and takes the ticket
@@ -520,11 +519,6 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
             c.stats[tid] = v;
         }
         if (tid == 0) *c.ticket = 0u;
-        // every block fenced its peer stores before its ticket: tomorrow's bytes are complete on every GPU
-        if (c.n_peers > 1 && tid < c.n_peers) {
-            __threadfence_system();
-            *reinterpret_cast<volatile int32_t*>(c.flag_signal[tid]) = day + 1;
-        }
     }
 }
 
@@ -536,6 +530,22 @@ __global__ void __launch_bounds__(256) k_agent(const DevCtx c, const int day) { 
 // million agents a day is ~20 MB of traffic, i.e. launch latency is the larger part of a day done as separate kernels.
 // The per-day buffers (output block, household flags, flag block, snapshot parity, open flags) come from DayPlan.
 // ---------------------------------------------------------------------------------------------------------------
+// peer mode: the owned slice of freshly written snapshot bytes (ib_wr[0]) is stored into the same place of every peer
+// GPU's buffer (ib_wr[1..]) with coalesced 16-byte P2P stores over NVLink; the flag is raised afterwards (k_signal, or
+// the tail of a k_days day) once every block's stores are fenced
+__device__ __forceinline__ void publish_body(const DevCtx& c)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(c.ib_wr[0] + c.lo);
+    const int64_t n16 = c.n_pad >> 4;
+    for (int p = 1; p < c.n_wr; ++p) {
+        uint4* dst = reinterpret_cast<uint4*>(c.ib_wr[p] + c.lo);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) k_publish(const DevCtx c) { publish_body(c); }
+
 constexpr int MAX_FUSED_DAYS = 14;
 struct DayPlan {
     int32_t first_day, n_days;
@@ -598,6 +608,14 @@ __global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan 
         grid_barrier(barrier_counter, epoch);
         agent_body<0>(s_c, day);
         grid_barrier(barrier_counter, epoch);
+        if (c0.n_peers > 1) {
+            publish_body(s_c);
+            grid_barrier(barrier_counter, epoch);
+            if (blockIdx.x == 0 && threadIdx.x < c0.n_peers) {
+                __threadfence_system();
+                *reinterpret_cast<volatile int32_t*>(c0.flag_signal[threadIdx.x]) = day + 1;
+            }
+        }
     }
 }
 
@@ -617,8 +635,7 @@ __global__ void __launch_bounds__(256) k_snapshot(const DevCtx c, const int day,
         ibn[j] = infectious_byte(st[j], day, ti[j]);
         if (diagnosed_on(c, c.u_adm, a0 + j, st[j], ti[j], day)) raise_household(c, a0 + j, hh_flag, hh_qflag, df);
     }
-    for (int p = 0; p < c.n_wr; ++p)
-        *reinterpret_cast<uchar4*>(c.ib_wr[p] + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
+    *reinterpret_cast<uchar4*>(c.ib_wr[0] + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
 }
 
 // peer mode: after a stand-alone k_snapshot, tell every GPU that this rank's bytes for `day` are complete
