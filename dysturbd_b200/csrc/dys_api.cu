@@ -62,6 +62,7 @@ struct dys_handle {
     uint8_t* peer_ib[8] = {};        // peer mode: every rank's d_ib (own included)
     int32_t* peer_flags[8] = {};
     int n_peers = 1;
+    int64_t peer_halo[8][2] = {};    // every rank's halo [lo, hi) in global agents
     int push_grid = 0;               // persistent grid of k_push
     int last_slot = 0;
     bool no_fuse = false;            // DYS_NO_FUSE=1 in the environment: dys_step_many launches two kernels a day
@@ -489,6 +490,20 @@ extern "C" int dys_set_open(dys_handle* h, const uint8_t* open_flags)
     return DYS_OK;
 }
 
+// peer r's buffer of parity `parity` becomes a write target; only the part of the owned slice inside r's halo travels
+static void add_peer_target(dys_handle* h, int r, int parity)
+{
+    DevCtx& c = h->c;
+    const int p = c.n_wr++;
+    c.ib_wr[p] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
+    int64_t lo = c.lo > h->peer_halo[r][0] ? c.lo : h->peer_halo[r][0];
+    int64_t hi = c.lo + c.n_pad < h->peer_halo[r][1] ? c.lo + c.n_pad : h->peer_halo[r][1];
+    lo &= ~(int64_t)15;
+    hi = (hi + 15) & ~(int64_t)15;
+    c.pub_lo[p] = lo;
+    c.pub_n[p] = hi > lo ? hi - lo : 0;
+}
+
 static void tick(dys_handle* h, int which)
 {
     if (h->tev.empty()) return;
@@ -532,7 +547,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
         c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
         for (int r = 0; r < h->n_peers; ++r) {
             c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
-            if (h->n_peers > 1 && r != h->p.rank) c.ib_wr[c.n_wr++] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
+            if (h->n_peers > 1 && r != h->p.rank) add_peer_target(h, r, parity);
         }
     };
     c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
@@ -547,7 +562,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
         k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day, h->d_hh_flag[par], h->d_hh_qflag[par],
                                                                       h->d_flags + par * DF_LEN);
         if (h->n_peers > 1) {
-            k_publish<<<(unsigned)h->push_grid, 256, 0, h->stream>>>(c);
+            k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
             k_signal<<<1, 32, 0, h->stream>>>(c, day);
         }
         h->ib_day = day;
@@ -587,13 +602,14 @@ static void set_snapshot_targets(dys_handle* h, int32_t day)
     DevCtx& c = h->c;
     c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
     c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
+    if (getenv("DYS_DEBUG_NO_PEER_WAIT")) c.n_peers = 1;     // timing experiment only: results are wrong
     c.n_wr = 0;
     // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
     const int parity = (day + 1) & 1;
     c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
     for (int r = 0; r < h->n_peers; ++r) {
         c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
-        if (h->n_peers > 1 && r != h->p.rank) c.ib_wr[c.n_wr++] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
+        if (h->n_peers > 1 && r != h->p.rank) add_peer_target(h, r, parity);
     }
 }
 
@@ -620,7 +636,7 @@ static int step_end(dys_handle* h, int32_t day)
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
     if (h->n_peers > 1) {        // tomorrow's bytes go to every peer GPU, then the flag
-        k_publish<<<(unsigned)h->push_grid, 256, 0, h->stream>>>(c);
+        k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
         k_signal<<<1, 32, 0, h->stream>>>(c, day + 1);
     }
     CK(h, cudaGetLastError());
@@ -691,13 +707,13 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, first_day, h->d_hh_flag[par], h->d_hh_qflag[par],
                                                                       h->d_flags + par * DF_LEN);
         if (h->n_peers > 1) {
-            k_publish<<<(unsigned)h->push_grid, 256, 0, h->stream>>>(c);
+            k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
             k_signal<<<1, 32, 0, h->stream>>>(c, first_day);
         }
     }
     c.u_adm = c.u_death = c.u_pair = nullptr; c.pair_prob = nullptr;
     set_snapshot_targets(h, first_day);                 // flag pointers; the per-day buffers come from the plan
-    CK(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned int), h->stream));
+    CK(h, cudaMemsetAsync(h->d_barrier, 0, 2 * sizeof(unsigned int), h->stream));
     unsigned int* bar = h->d_barrier;
     void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
     CK(h, cudaLaunchCooperativeKernel((const void*)k_days, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
@@ -976,9 +992,10 @@ extern "C" int dys_peer_export(dys_handle* h, void* out /* DYS_PEER_HANDLE_BYTES
     return DYS_OK;
 }
 
-extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */)
+extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */,
+                               const int64_t* halos /* [n_ranks][2] */)
 {
-    if (!h || !handles) return DYS_ERR_INVALID_ARG;
+    if (!h || !handles || !halos) return DYS_ERR_INVALID_ARG;
     if (n_ranks < 2 || n_ranks > 8 || n_ranks != h->p.world) return fail(h, DYS_ERR_INVALID_ARG, "dys_peer_attach: 2..8 ranks, equal to dys_params.world");
     CK(h, cudaSetDevice(h->device));
     const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)handles;
@@ -990,6 +1007,7 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
         h->peer_ib[r] = (uint8_t*)pib;
         h->peer_flags[r] = (int32_t*)pfl;
     }
+    for (int r = 0; r < n_ranks; ++r) { h->peer_halo[r][0] = halos[2 * r]; h->peer_halo[r][1] = halos[2 * r + 1]; }
     h->n_peers = n_ranks;
     h->ib_day = -1;
     return DYS_OK;

@@ -71,6 +71,7 @@ struct DevCtx {
     // (P2P stores over NVLink), so the per-day exchange is fused into the producing kernel
     const uint8_t* ib_rd;
     uint8_t* ib_wr[8];                   // [n_wr] write targets (own buffer first)
+    int64_t pub_lo[8], pub_n[8];         // peer mode: byte range of the owned slice that target p needs (its halo)
     int32_t n_wr;
     int32_t n_peers, rank;               // peer mode: n_peers > 1
     const int32_t* flag_wait;            // [n_peers] on THIS GPU: flag_wait[r] = last day rank r's bytes are complete for

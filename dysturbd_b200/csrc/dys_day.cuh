@@ -79,13 +79,6 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
 
     if (tid < 64) s_pdf[tid] = c.pdf[tid];
     if (tid < 8) s_acc[tid] = 0;
-    if (c.n_peers > 1 && tid < c.n_peers) {
-        // peer mode: every rank's k_agent (or k_signal) stored its slice of today's snapshot bytes straight into this
-        // GPU's buffer and then raised flag[r] = day; the grid is persistent (all CTAs resident), so spinning is safe
-        const volatile int32_t* f = c.flag_wait + tid;
-        while (*f < day) __nanosleep(64);
-        __threadfence_system();
-    }
     __syncthreads();
     const bool any_closed = c.n_closed != 0;
     unsigned int cnt[4] = {0, 0, 0, 0};   // entries scanned, candidates, exposed, hits
@@ -182,42 +175,62 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
 
     const int64_t n_chunks = (c.rt_n + PUSH_CHUNK - 1) / PUSH_CHUNK;
     const int64_t stride = (int64_t)gridDim.x * PUSH_WARPS;
-    int64_t ch = (int64_t)blockIdx.x * PUSH_WARPS + wid;
     int nq = 0;                                            // queued rows (warp-uniform)
     const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib_rd + c.rt_lo);  // rt_lo is a multiple of 1024
-    uint32_t v = 0;
-    if (ch < n_chunks) v = ib4[ch * (PUSH_CHUNK / 4) + lane];
-    for (; ch < n_chunks; ch += stride) {
-        uint32_t vn = 0;
-        if (ch + stride < n_chunks) vn = ib4[(ch + stride) * (PUSH_CHUNK / 4) + lane];   // next step's bytes, in flight
-        const int mine = __popc(v & 0x80808080u);
-        if (__ballot_sync(0xffffffffu, mine != 0)) {
-            int incl = mine;
+    // scan the snapshot bytes of halo agents [ch0, ch1) * 128, queueing the infectious ones
+    auto scan = [&](const int64_t ch0, const int64_t ch1) {
+        int64_t ch = ch0 + (int64_t)blockIdx.x * PUSH_WARPS + wid;
+        uint32_t v = 0;
+        if (ch < ch1) v = ib4[ch * (PUSH_CHUNK / 4) + lane];
+        for (; ch < ch1; ch += stride) {
+            uint32_t vn = 0;
+            if (ch + stride < ch1) vn = ib4[(ch + stride) * (PUSH_CHUNK / 4) + lane];   // next step's bytes, in flight
+            const int mine = __popc(v & 0x80808080u);
+            if (__ballot_sync(0xffffffffu, mine != 0)) {
+                int incl = mine;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            int pos = nq + incl - mine;
-            const uint32_t il0 = (uint32_t)(ch * PUSH_CHUNK + lane * 4);
-            if (mine) {
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int pos = nq + incl - mine;
+                const uint32_t il0 = (uint32_t)(ch * PUSH_CHUNK + lane * 4);
+                if (mine) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t byte = (v >> (8 * b)) & 0xFFu;
-                    if ((byte & IB_INF) && il0 + b < (uint32_t)c.rt_n) {
-                        w.q_idx[pos] = il0 + b; w.q_ib[pos] = (uint8_t)byte; ++pos;
-                        prefetch_l2(c.tptr + il0 + b);          // the row extent is needed when the queue is expanded
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t byte = (v >> (8 * b)) & 0xFFu;
+                        if ((byte & IB_INF) && il0 + b < (uint32_t)c.rt_n) {
+                            w.q_idx[pos] = il0 + b; w.q_ib[pos] = (uint8_t)byte; ++pos;
+                            prefetch_l2(c.tptr + il0 + b);      // the row extent is needed when the queue is expanded
+                        }
                     }
                 }
+                nq += __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+                while (nq >= 32) {     // expand from the back of the queue: nothing has to move
+                    nq -= 32;
+                    expand(nq, 32);
+                }
             }
-            nq += __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
-            while (nq >= 32) {         // expand from the back of the queue: nothing has to move
-                nq -= 32;
-                expand(nq, 32);
-            }
+            v = vn;
         }
-        v = vn;
+    };
+    if (c.n_peers > 1) {
+        // peer mode: the owned agents' bytes are local and final, so their rows are pushed first; the halo agents'
+        // bytes were stored into this GPU's buffer by their owners, who then raised flag[r] = day -- the exchange
+        // latency hides behind the local part of the push.  (Persistent grid: all CTAs resident, spinning is safe.)
+        const int64_t own0 = (c.lo - c.rt_lo) / PUSH_CHUNK, own1 = (c.lo - c.rt_lo + c.n_loc + PUSH_CHUNK - 1) / PUSH_CHUNK;
+        scan(own0, own1);
+        if (tid < c.n_peers) {
+            const volatile int32_t* f = c.flag_wait + tid;
+            while (*f < day) __nanosleep(32);
+            __threadfence_system();
+        }
+        __syncthreads();
+        scan(0, own0);
+        scan(own1, n_chunks);
+    } else {
+        scan(0, n_chunks);
     }
     if (nq > 0) expand(0, nq);
     const int idx[4] = {ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED, ST_HITS};
@@ -535,10 +548,11 @@ __global__ void __launch_bounds__(256) k_agent(const DevCtx c, const int day) { 
 // the tail of a k_days day) once every block's stores are fenced
 __device__ __forceinline__ void publish_body(const DevCtx& c)
 {
-    const uint4* src = reinterpret_cast<const uint4*>(c.ib_wr[0] + c.lo);
-    const int64_t n16 = c.n_pad >> 4;
+    // only the part of the owned slice that lies inside the peer's halo travels (pub_lo / pub_n, 16-byte granules)
     for (int p = 1; p < c.n_wr; ++p) {
-        uint4* dst = reinterpret_cast<uint4*>(c.ib_wr[p] + c.lo);
+        const uint4* src = reinterpret_cast<const uint4*>(c.ib_wr[0] + c.pub_lo[p]);
+        uint4* dst = reinterpret_cast<uint4*>(c.ib_wr[p] + c.pub_lo[p]);
+        const int64_t n16 = c.pub_n[p] >> 4;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
     }
     __threadfence_system();
@@ -547,6 +561,7 @@ __device__ __forceinline__ void publish_body(const DevCtx& c)
 __global__ void __launch_bounds__(256) k_publish(const DevCtx c) { publish_body(c); }
 
 constexpr int MAX_FUSED_DAYS = 14;
+constexpr int PUBLISH_BLOCKS = 64;
 struct DayPlan {
     int32_t first_day, n_days;
     int32_t n_closed[MAX_FUSED_DAYS];
@@ -608,13 +623,22 @@ __global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan 
         grid_barrier(barrier_counter, epoch);
         agent_body<0>(s_c, day);
         grid_barrier(barrier_counter, epoch);
-        if (c0.n_peers > 1) {
+        if (c0.n_peers > 1 && blockIdx.x < PUBLISH_BLOCKS) {
+            // a few CTAs ship tomorrow's bytes to the peers while the others already start the next day (whose push
+            // waits for the peers' flags anyway); the last shipper raises this rank's flag on every GPU
             publish_body(s_c);
-            grid_barrier(barrier_counter, epoch);
-            if (blockIdx.x == 0 && threadIdx.x < c0.n_peers) {
-                __threadfence_system();
-                *reinterpret_cast<volatile int32_t*>(c0.flag_signal[threadIdx.x]) = day + 1;
+            __syncthreads();
+            __shared__ bool s_pub_last;
+            if (threadIdx.x == 0) s_pub_last = (atomicAdd(barrier_counter + 1, 1u) == PUBLISH_BLOCKS - 1);
+            __syncthreads();
+            if (s_pub_last) {
+                if (threadIdx.x == 0) barrier_counter[1] = 0u;
+                if (threadIdx.x < c0.n_peers) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int32_t*>(c0.flag_signal[threadIdx.x]) = day + 1;
+                }
             }
+            __syncthreads();
         }
     }
 }

@@ -105,7 +105,7 @@ def load_library():
     lib.dys_version.restype = C.c_char_p
     lib.dys_keyed_uniform_device.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, i64, vp]
     lib.dys_peer_export.argtypes = [vp, vp]
-    lib.dys_peer_attach.argtypes = [vp, C.c_int, vp]
+    lib.dys_peer_attach.argtypes = [vp, C.c_int, vp, vp]
     _lib = lib
     return lib
 
@@ -338,10 +338,11 @@ class Engine:
         self._ck(self.lib.dys_peer_export(self.h, buf))
         return buf.raw
 
-    def peer_attach(self, handles):
-        """handles: list of every rank's peer_export() bytes, in rank order"""
+    def peer_attach(self, handles, halos):
+        """handles: every rank's peer_export() bytes, halos: every rank's (halo_lo, halo_hi), both in rank order"""
         blob = b"".join(handles)
-        self._ck(self.lib.dys_peer_attach(self.h, len(handles), blob))
+        hal = np.ascontiguousarray(halos, dtype=np.int64).reshape(len(handles), 2)
+        self._ck(self.lib.dys_peer_attach(self.h, len(handles), blob, hal.ctypes.data))
 
     def cuda_stream(self):
         p = C.c_void_p()
