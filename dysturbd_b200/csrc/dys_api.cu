@@ -602,7 +602,6 @@ static void set_snapshot_targets(dys_handle* h, int32_t day)
     DevCtx& c = h->c;
     c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
     c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
-    if (getenv("DYS_DEBUG_NO_PEER_WAIT")) c.n_peers = 1;     // timing experiment only: results are wrong
     c.n_wr = 0;
     // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
     const int parity = (day + 1) & 1;

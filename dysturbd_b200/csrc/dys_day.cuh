@@ -347,7 +347,57 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
     if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.hh_flag_next, c.hh_qflag_next, c.df_next);
 }
 
-template <int VARIANT>   // 0 = product; 1, 2 = tools/kbench.cu ablations (no fold / no reduction at all)
+// One block folds the spread partial sums (part[counter][slot]: one warp per counter, two coalesced loads, shuffle tree),
+// derives the compartment statistics from the status counts and re-zeroes the partials for the next day.
+__device__ __forceinline__ void fold_stats(const DevCtx& c)
+{
+    __shared__ long long s_fold[N_STATS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    __threadfence();
+    unsigned long long t[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        unsigned long long* p = c.part + (size_t)((tid >> 5) + 8 * q) * N_SLOTS;
+        t[q] = __ldcg(p + lane) + __ldcg(p + lane + 32);
+        p[lane] = 0ull;
+        p[lane + 32] = 0ull;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
+        if (lane == 0) s_fold[(tid >> 5) + 8 * q] = (long long)t[q];
+    }
+    __syncthreads();
+    if (tid < N_STATS) {
+        const long long* r = s_fold + RAW_END;        // QI S I QH D H R X
+        long long v = s_fold[tid];
+        switch (tid) {
+            case ST_ACTIVE: v = r[2] + r[0] + r[4] + r[5]; break;
+            case ST_RECOVERED: v = r[6]; break;
+            case ST_QUARANTINED: v = r[3] + r[0] + r[4]; break;
+            case ST_HOSPITALIZED: v = r[5]; break;
+            case ST_DEAD: v = r[7]; break;
+            case ST_EVER_INFECTED: v = r[2] + r[0] + r[4] + r[5] + r[6] + r[7]; break;
+            case ST_SUS0: v = s_fold[RAW_SUS0]; break;
+            case ST_INF0: v = s_fold[RAW_INF0]; break;
+            case ST_COUNT0 + 0: v = r[1]; break;
+            case ST_COUNT0 + 1: v = r[2]; break;
+            case ST_COUNT0 + 2: v = r[3]; break;
+            case ST_COUNT0 + 3: v = r[0]; break;
+            case ST_COUNT0 + 4: v = r[4]; break;
+            case ST_COUNT0 + 5: v = r[5]; break;
+            case ST_COUNT0 + 6: v = r[6]; break;
+            case ST_COUNT0 + 7: v = r[7]; break;
+            default: break;
+        }
+        if (tid >= RAW_END) v = 0;
+        c.stats[tid] = v;
+    }
+}
+
+template <int VARIANT>   // 0 = k_agent (last block folds); 3 = k_days (block 0 folds after the grid barrier);
+                         // 1, 2 = tools/kbench.cu ablations (no fold / no reduction at all)
 __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
 {
     __shared__ unsigned int s_hist[HIST_LEN];
@@ -357,7 +407,6 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
     __shared__ unsigned short s_list[AGENT_TILE];
     __shared__ uint32_t s_stw[AGENT_TILE / 4];      // the tile's status words, for the settle phase
     __shared__ __align__(16) int s_src[AGENT_TILE]; // the tile's mailbox (infector) column (written 16 bytes at a time)
-    __shared__ long long s_fold[N_STATS];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -489,48 +538,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
     if (VARIANT != 0) return;
     __syncthreads();
     if (s_last) {
-        // the last block folds the spread partial sums: part[counter][slot], one warp per counter, two coalesced loads
-        __threadfence();
-        unsigned long long t[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            unsigned long long* p = c.part + (size_t)((tid >> 5) + 8 * q) * N_SLOTS;
-            t[q] = __ldcg(p + lane) + __ldcg(p + lane + 32);
-            p[lane] = 0ull;
-            p[lane + 32] = 0ull;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
-            if (lane == 0) s_fold[(tid >> 5) + 8 * q] = (long long)t[q];
-        }
-        __syncthreads();
-        if (tid < N_STATS) {
-            const long long* r = s_fold + RAW_END;        // QI S I QH D H R X
-            long long v = s_fold[tid];
-            switch (tid) {
-                case ST_ACTIVE: v = r[2] + r[0] + r[4] + r[5]; break;
-                case ST_RECOVERED: v = r[6]; break;
-                case ST_QUARANTINED: v = r[3] + r[0] + r[4]; break;
-                case ST_HOSPITALIZED: v = r[5]; break;
-                case ST_DEAD: v = r[7]; break;
-                case ST_EVER_INFECTED: v = r[2] + r[0] + r[4] + r[5] + r[6] + r[7]; break;
-                case ST_SUS0: v = s_fold[RAW_SUS0]; break;
-                case ST_INF0: v = s_fold[RAW_INF0]; break;
-                case ST_COUNT0 + 0: v = r[1]; break;
-                case ST_COUNT0 + 1: v = r[2]; break;
-                case ST_COUNT0 + 2: v = r[3]; break;
-                case ST_COUNT0 + 3: v = r[0]; break;
-                case ST_COUNT0 + 4: v = r[4]; break;
-                case ST_COUNT0 + 5: v = r[5]; break;
-                case ST_COUNT0 + 6: v = r[6]; break;
-                case ST_COUNT0 + 7: v = r[7]; break;
-                default: break;
-            }
-            if (tid >= RAW_END) v = 0;
-            c.stats[tid] = v;
-        }
+        fold_stats(c);      // the last block to finish
         if (tid == 0) *c.ticket = 0u;
     }
 }
@@ -575,6 +583,7 @@ struct DayPlan {
     uint8_t* peer_ib[8][2];                         // peer mode: every other rank's, by day parity
     int32_t first_parity;                           // step parity of first_day (household flags, flag block)
     int32_t want_sa, want_bc, want_ev;
+    unsigned long long* trace;                      // developer tracing (tools/kbench.cu): globaltimer at phase boundaries, or null
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
@@ -619,10 +628,23 @@ __global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan 
                 if (c.n_peers > 1 && r != c.rank) c.ib_wr[c.n_wr++] = plan.peer_ib[r][wr];
         }
         __syncthreads();
+        auto stamp = [&](int i) {
+            if (plan.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                plan.trace[k * 8 + i] = t;
+            }
+        };
+        stamp(0);
         push_body(s_c, day);
+        stamp(1);
         grid_barrier(barrier_counter, epoch);
-        agent_body<0>(s_c, day);
+        stamp(2);
+        agent_body<3>(s_c, day);
+        stamp(3);
         grid_barrier(barrier_counter, epoch);
+        stamp(4);
+        if (blockIdx.x == gridDim.x - 1) fold_stats(s_c);      // every block's partial sums are in; the others move on
         if (c0.n_peers > 1 && blockIdx.x < PUBLISH_BLOCKS) {
             // a few CTAs ship tomorrow's bytes to the peers while the others already start the next day (whose push
             // waits for the peers' flags anyway); the last shipper raises this rank's flag on every GPU

@@ -143,10 +143,4 @@ __global__ void k_keyed_uniform(uint64_t seed, uint32_t day, uint32_t stream, co
     if (i < n) out[i] = keyed_uniform(seed, day, stream, a[i], b[i]);
 }
 
-__global__ void k_count_closed(const uint8_t* __restrict__ open, int64_t B, int32_t* out)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B && !open[i]) atomicAdd(out, 1);
-}
-
 }  // namespace dys

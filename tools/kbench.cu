@@ -100,5 +100,34 @@ int main(int argc, char** argv)
     }
     timeit("k_push", [&](int d) { k_push<<<148 * per_sm, 256>>>(c, d); });
     printf("push blocks/SM %d\n", per_sm);
+    {   // k_days: 7 days in one cooperative launch, with phase timestamps of block 0
+        DayPlan plan{};
+        plan.first_day = 100; plan.n_days = 7; plan.first_parity = 0;
+        plan.off_sa = 512; plan.off_bc = 512 + ((c.S * 21 * 4 + 15) & ~15ll); plan.off_ev = plan.off_bc + ((c.B * 4 + 15) & ~15ll);
+        plan.want_sa = plan.want_bc = plan.want_ev = 1;
+        const size_t blk = plan.off_ev + 8 * (size_t)N;
+        for (int k = 0; k < 7; ++k) { plan.out[k] = dalloc<unsigned char>(blk); plan.open[k] = c.open; plan.n_closed[k] = 0; }
+        plan.hh_flag[0] = f0; plan.hh_flag[1] = c.hh_flag_next; plan.hh_qflag[0] = f1; plan.hh_qflag[1] = c.hh_qflag_next;
+        plan.df[0] = df; plan.df[1] = df + 4;
+        plan.ib[0] = ibbuf; plan.ib[1] = dalloc<uint8_t>(N + 2048);
+        cudaMemcpy(plan.ib[1], ibbuf, N, cudaMemcpyDeviceToDevice);
+        plan.trace = dalloc<unsigned long long>(64);
+        unsigned int* bar = dalloc<unsigned int>(4);
+        int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_days, 256, 0);
+        void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaMemset(bar, 0, 16);
+            cudaMemcpy(df, &anynd, 4, cudaMemcpyHostToDevice);
+            cudaEventRecord(e0);
+            cudaError_t er = cudaLaunchCooperativeKernel((const void*)k_days, dim3(148 * occ), dim3(256), args, 0, 0);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("k_days 7 days: %.2f us/day (%s, %d CTAs/SM)\n", ms * 1000 / 7, cudaGetErrorString(er), occ);
+        }
+        unsigned long long tr[64]; cudaMemcpy(tr, plan.trace, sizeof tr, cudaMemcpyDeviceToHost);
+        for (int k = 1; k < 7; ++k)
+            printf("  day %d (block 0): push %.2f  barrier %.2f  agent %.2f  barrier %.2f us\n", k, (tr[k*8+1]-tr[k*8+0])/1e3,
+                   (tr[k*8+2]-tr[k*8+1])/1e3, (tr[k*8+3]-tr[k*8+2])/1e3, (tr[k*8+4]-tr[k*8+3])/1e3);
+    }
     return 0;
 }
