@@ -63,6 +63,8 @@ struct dys_handle {
     int32_t* peer_flags[8] = {};
     int n_peers = 1;
     int64_t peer_halo[8][2] = {};    // every rank's halo [lo, hi) in global agents
+    int64_t peer_own[8][2] = {};     // every rank's owned range
+    uint32_t wait_mask = 0, signal_mask = 0;
     int push_grid = 0;               // persistent grid of k_push
     int last_slot = 0;
     bool no_fuse = false;            // DYS_NO_FUSE=1 in the environment: dys_step_many launches two kernels a day
@@ -543,6 +545,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     auto ib_targets = [&](int parity) {       // where snapshot bytes of parity `parity` are written: own buffer, then peers
         c.n_peers = h->n_peers; c.rank = h->p.rank;
         c.flag_wait = h->d_peer_flags;
+        c.wait_mask = h->wait_mask; c.signal_mask = h->signal_mask;
         c.n_wr = 0;
         c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
         for (int r = 0; r < h->n_peers; ++r) {
@@ -602,6 +605,7 @@ static void set_snapshot_targets(dys_handle* h, int32_t day)
     DevCtx& c = h->c;
     c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
     c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
+    c.wait_mask = h->wait_mask; c.signal_mask = h->signal_mask;
     c.n_wr = 0;
     // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
     const int parity = (day + 1) & 1;
@@ -992,7 +996,7 @@ extern "C" int dys_peer_export(dys_handle* h, void* out /* DYS_PEER_HANDLE_BYTES
 }
 
 extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */,
-                               const int64_t* halos /* [n_ranks][2] */)
+                               const int64_t* halos /* [n_ranks][4] */)
 {
     if (!h || !handles || !halos) return DYS_ERR_INVALID_ARG;
     if (n_ranks < 2 || n_ranks > 8 || n_ranks != h->p.world) return fail(h, DYS_ERR_INVALID_ARG, "dys_peer_attach: 2..8 ranks, equal to dys_params.world");
@@ -1006,7 +1010,18 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
         h->peer_ib[r] = (uint8_t*)pib;
         h->peer_flags[r] = (int32_t*)pfl;
     }
-    for (int r = 0; r < n_ranks; ++r) { h->peer_halo[r][0] = halos[2 * r]; h->peer_halo[r][1] = halos[2 * r + 1]; }
+    h->wait_mask = h->signal_mask = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+        h->peer_own[r][0] = halos[4 * r]; h->peer_own[r][1] = halos[4 * r + 1];
+        h->peer_halo[r][0] = halos[4 * r + 2]; h->peer_halo[r][1] = halos[4 * r + 3];
+    }
+    const int me = h->p.rank;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == me) continue;
+        // r's agents inside my halo -> I wait for r; my agents inside r's halo -> r waits for me
+        if (h->peer_own[r][0] < h->peer_halo[me][1] && h->peer_own[r][1] > h->peer_halo[me][0]) h->wait_mask |= 1u << r;
+        if (h->peer_own[me][0] < h->peer_halo[r][1] && h->peer_own[me][1] > h->peer_halo[r][0]) h->signal_mask |= 1u << r;
+    }
     h->n_peers = n_ranks;
     h->ib_day = -1;
     return DYS_OK;

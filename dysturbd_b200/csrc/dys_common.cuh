@@ -74,6 +74,7 @@ struct DevCtx {
     int64_t pub_lo[8], pub_n[8];         // peer mode: byte range of the owned slice that target p needs (its halo)
     int32_t n_wr;
     int32_t n_peers, rank;               // peer mode: n_peers > 1
+    uint32_t wait_mask, signal_mask;     // ranks whose bytes this rank reads (waits for) / ranks that read this rank's bytes
     const int32_t* flag_wait;            // [n_peers] on THIS GPU: flag_wait[r] = last day rank r's bytes are complete for
     int32_t* flag_signal[8];             // [n_peers] &flags[rank] on every GPU (own included)
     const uint8_t* open;                 // [B]

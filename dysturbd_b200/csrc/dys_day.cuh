@@ -221,7 +221,7 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
         // latency hides behind the local part of the push.  (Persistent grid: all CTAs resident, spinning is safe.)
         const int64_t own0 = (c.lo - c.rt_lo) / PUSH_CHUNK, own1 = (c.lo - c.rt_lo + c.n_loc + PUSH_CHUNK - 1) / PUSH_CHUNK;
         scan(own0, own1);
-        if (tid < c.n_peers) {
+        if (tid < c.n_peers && ((c.wait_mask >> tid) & 1u)) {      // only the ranks whose agents are in this rank's halo
             const volatile int32_t* f = c.flag_wait + tid;
             while (*f < day) __nanosleep(32);
             __threadfence_system();
@@ -569,7 +569,7 @@ __device__ __forceinline__ void publish_body(const DevCtx& c)
 __global__ void __launch_bounds__(256) k_publish(const DevCtx c) { publish_body(c); }
 
 constexpr int MAX_FUSED_DAYS = 14;
-constexpr int PUBLISH_BLOCKS = 64;
+constexpr int PUBLISH_BLOCKS = 8;          // the halo part of a slice is small (one community per neighbour)
 struct DayPlan {
     int32_t first_day, n_days;
     int32_t n_closed[MAX_FUSED_DAYS];
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan 
             __syncthreads();
             if (s_pub_last) {
                 if (threadIdx.x == 0) barrier_counter[1] = 0u;
-                if (threadIdx.x < c0.n_peers) {
+                if (threadIdx.x < c0.n_peers && ((c0.signal_mask >> threadIdx.x) & 1u)) {
                     __threadfence_system();
                     *reinterpret_cast<volatile int32_t*>(c0.flag_signal[threadIdx.x]) = day + 1;
                 }
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(256) k_snapshot(const DevCtx c, const int day,
 // peer mode: after a stand-alone k_snapshot, tell every GPU that this rank's bytes for `day` are complete
 __global__ void k_signal(const DevCtx c, const int day)
 {
-    if (threadIdx.x < c.n_peers) {
+    if (threadIdx.x < c.n_peers && ((c.signal_mask >> threadIdx.x) & 1u)) {
         __threadfence_system();
         *reinterpret_cast<volatile int32_t*>(c.flag_signal[threadIdx.x]) = day;
     }

@@ -339,9 +339,9 @@ class Engine:
         return buf.raw
 
     def peer_attach(self, handles, halos):
-        """handles: every rank's peer_export() bytes, halos: every rank's (halo_lo, halo_hi), both in rank order"""
+        """handles: every rank's peer_export() bytes, halos: every rank's (shard_lo, shard_hi, halo_lo, halo_hi)"""
         blob = b"".join(handles)
-        hal = np.ascontiguousarray(halos, dtype=np.int64).reshape(len(handles), 2)
+        hal = np.ascontiguousarray(halos, dtype=np.int64).reshape(len(handles), 4)
         self._ck(self.lib.dys_peer_attach(self.h, len(handles), blob, hal.ctypes.data))
 
     def cuda_stream(self):

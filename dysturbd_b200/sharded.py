@@ -45,7 +45,7 @@ class ShardedEngine:
             self.stream = torch.cuda.ExternalStream(self.sim.cuda_stream(), device=device)
             if self.mode == "peer":
                 handles = [None] * self.world
-                dist.all_gather_object(handles, (self.sim.peer_export(), tuple(pop.halo)), group=group)
+                dist.all_gather_object(handles, (self.sim.peer_export(), (pop.lo, pop.lo + pop.N) + tuple(pop.halo)), group=group)
                 self.sim.peer_attach([x[0] for x in handles], [x[1] for x in handles])
                 self.sim.sync()
                 dist.barrier(group=group)          # nobody steps before every rank's flags are reset and attached

@@ -196,7 +196,8 @@ int64_t dys_device_bytes(const dys_handle* h);
 #define DYS_PEER_HANDLE_BYTES 128
 int dys_peer_export(dys_handle* h, void* out /* [DYS_PEER_HANDLE_BYTES] */);
 int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */,
-                    const int64_t* halos /* [n_ranks][2]: every rank's halo_lo, halo_hi -- only bytes a peer reads travel */);
+                    const int64_t* ranges /* [n_ranks][4]: every rank's shard_lo, shard_hi, halo_lo, halo_hi -- only the
+                                             bytes a peer reads travel, and only the ranks that exchange bytes synchronise */);
 /* evaluates the keyed uniform u(day, stream, a[k], b[k]) ON THE DEVICE for n host-side index pairs (known-answer
  * tests of the device Philox against oracle/philox_np.py) */
 int dys_keyed_uniform_device(int device, uint64_t seed, uint32_t day, uint32_t stream, const uint32_t* a,
