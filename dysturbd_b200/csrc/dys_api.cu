@@ -62,6 +62,7 @@ struct dys_handle {
     uint8_t* peer_ib[8] = {};        // peer mode: every rank's d_ib (own included)
     int32_t* peer_flags[8] = {};
     int n_peers = 1;
+    int64_t hh_lo = 0, bld_lo = 0, area_lo = 0;   // first owned household / building / area
     int64_t peer_halo[8][2] = {};    // every rank's halo [lo, hi) in global agents
     int64_t peer_own[8][2] = {};     // every rank's owned range
     uint32_t wait_mask = 0, signal_mask = 0;
@@ -157,6 +158,14 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         c.rt_lo = p.halo_lo; c.rt_n = p.halo_hi - p.halo_lo;
     }
     c.H = p.n_households; c.B = p.n_buildings; c.S = p.n_areas; c.V = p.n_slots;
+    c.B_out = c.B; c.S_out = c.S;
+    h->hh_lo = h->bld_lo = h->area_lo = 0;
+    if (p.hh_hi > p.hh_lo) { h->hh_lo = p.hh_lo; c.H = p.hh_hi - p.hh_lo; }
+    if (p.bld_hi > p.bld_lo) { h->bld_lo = p.bld_lo; c.B_out = p.bld_hi - p.bld_lo; }
+    if (p.area_hi > p.area_lo) { h->area_lo = p.area_lo; c.S_out = p.area_hi - p.area_lo; }
+    if (p.hh_hi > p.n_households || p.bld_hi > p.n_buildings || p.area_hi > p.n_areas || p.hh_lo < 0 || p.bld_lo < 0 || p.area_lo < 0) {
+        delete h; return fail(nullptr, DYS_ERR_INVALID_ARG, "owned household / building / area range outside the population");
+    }
     c.recover = p.recover; c.hospital_recover = p.hospital_recover; c.diagnosis = p.diagnosis; c.quarantine = p.quarantine;
     c.adm_min = p.adm_min_day; c.adm_max = p.adm_max_day; c.death_min = p.death_min_adm_day;
     c.norm_factor = p.norm_factor; c.compliance = p.compliance; c.seed = p.seed;
@@ -180,8 +189,8 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     {   // one output block per parity: everything a day produces leaves the device in a single copy
         auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
         h->off_sa = sizeof(int64_t) * N_STATS;
-        h->off_bc = h->off_sa + ((p.flags & DYS_WANT_SA_HIST) ? up16(sizeof(int32_t) * (size_t)(c.S * HIST_LEN)) : 0);
-        h->off_ev = h->off_bc + ((p.flags & DYS_WANT_BUILDING_COUNTS) ? up16(sizeof(int32_t) * (size_t)c.B) : 0);
+        h->off_bc = h->off_sa + ((p.flags & DYS_WANT_SA_HIST) ? up16(sizeof(int32_t) * (size_t)(c.S_out * HIST_LEN)) : 0);
+        h->off_ev = h->off_bc + ((p.flags & DYS_WANT_BUILDING_COUNTS) ? up16(sizeof(int32_t) * (size_t)c.B_out) : 0);
         h->ev_inline = (p.flags & DYS_WANT_EVENTS) ? (c.n_pad / 64 > 1024 ? c.n_pad / 64 : 1024) : 0;
         if (h->ev_inline > c.n_pad) h->ev_inline = c.n_pad;
         h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
@@ -333,6 +342,8 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
     A(copy_in(h, (void*)c.risk, risk, 8 * n)); A(copy_in(h, (void*)c.p_adm, p_adm, 8 * n)); A(copy_in(h, (void*)c.p_death, p_death, 8 * n));
     A(copy_in(h, (void*)c.routine, routine, 4 * (size_t)c.rt_n * c.V));
     if (rc != DYS_OK) return rc;
+    k_localize<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>((int32_t*)c.hh, (int32_t*)c.home, (int32_t*)c.sa, c.n_loc, (int32_t)h->hh_lo,
+                                                              (int32_t)h->bld_lo, (int32_t)h->area_lo);
     k_validate_population<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c, h->d_bad);
     k_validate_routine<<<grid_for(c.rt_n * c.V, 256), 256, 0, h->stream>>>(c.routine, c.rt_n * c.V, c.B, h->d_bad);
     CK(h, cudaGetLastError());
@@ -825,7 +836,7 @@ extern "C" int dys_get_sa_hist(dys_handle* h, int32_t day, int32_t* out)
     int rc = dys_get_outputs(h, day, &o);
     if (rc != DYS_OK) return rc;
     if (!o.sa_hist) return fail(h, DYS_ERR_NOT_AVAILABLE, "sa_hist was not requested in dys_params.flags");
-    memcpy(out, o.sa_hist, sizeof(int32_t) * (size_t)(h->c.S * HIST_LEN));
+    memcpy(out, o.sa_hist, sizeof(int32_t) * (size_t)(h->c.S_out * HIST_LEN));
     return DYS_OK;
 }
 
@@ -836,7 +847,7 @@ extern "C" int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out)
     int rc = dys_get_outputs(h, day, &o);
     if (rc != DYS_OK) return rc;
     if (!o.building_counts) return fail(h, DYS_ERR_NOT_AVAILABLE, "building counts were not requested in dys_params.flags");
-    memcpy(out, o.building_counts, sizeof(int32_t) * (size_t)h->c.B);
+    memcpy(out, o.building_counts, sizeof(int32_t) * (size_t)h->c.B_out);
     return DYS_OK;
 }
 

@@ -48,7 +48,8 @@ constexpr int DF_ANY_ND = 0, DF_N_EVENTS = 1, DF_LEN = 4;
 struct DevCtx {
     int64_t n_loc, n_pad, n_glob, lo;    // owned agents, padded count (multiple of 1024), global agents, first owned
     int64_t rt_lo, rt_n;                 // halo: global agents [rt_lo, rt_lo + rt_n) are the columns owned rows reference
-    int64_t H, B, S;
+    int64_t H, B, S;                     // OWNED households (hh[] is local to them), ALL buildings, ALL areas
+    int64_t B_out, S_out;                // owned buildings / areas: home[] and sa[] are local to them, and so are the outputs
     int32_t V;
     int32_t recover, hospital_recover, diagnosis, quarantine, adm_min, adm_max, death_min;
     double norm_factor, compliance;

@@ -70,8 +70,8 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
     PushWarpSmem& w = s_w[wid];
 
     // scratch that k_agent fills today, and the flags it raises for tomorrow
-    grid_clear(c.sa_hist, c.S * HIST_LEN);
-    grid_clear(c.bcount, c.B);
+    grid_clear(c.sa_hist, c.S_out * HIST_LEN);
+    grid_clear(c.bcount, c.B_out);
     grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
     grid_clear16(c.hh_flag_next, c.H);
     grid_clear16(c.hh_qflag_next, c.H);

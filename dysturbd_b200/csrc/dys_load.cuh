@@ -30,10 +30,21 @@ __global__ void k_validate_population(const DevCtx c, int32_t* bad)
     const uint8_t s = c.status[a];
     const bool known = s == ST_S || s == ST_I || s == ST_QH || s == ST_QI || s == ST_D || s == ST_H || s == ST_R || s == ST_X;
     if (!known) atomicOr(bad, 1);
-    if (c.hh[a] < 0 || c.hh[a] >= c.H || c.home[a] < 0 || c.home[a] >= c.B || c.sa[a] < -1 || c.sa[a] >= c.S) atomicOr(bad, 2);
+    if (c.hh[a] < 0 || c.hh[a] >= c.H || c.home[a] < 0 || c.home[a] >= c.B_out || c.sa[a] < -1 || c.sa[a] >= c.S_out) atomicOr(bad, 2);
     if ((s == ST_S || s == ST_I || s == ST_R || s == ST_X) && c.t_adm[a] != 0) atomicOr(bad, 4);
     if (c.src[a] < -1 || c.src[a] >= c.n_glob) atomicOr(bad, 8);
     if ((s == ST_S || s == ST_QH) && c.src[a] != -1) atomicOr(bad, 512);
+}
+
+// household / home building / area indices arrive global and are stored relative to the owned ranges
+__global__ void k_localize(int32_t* __restrict__ hh, int32_t* __restrict__ home, int32_t* __restrict__ sa, int64_t n, int32_t hh_lo,
+                           int32_t bld_lo, int32_t area_lo)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    hh[a] -= hh_lo;
+    home[a] -= bld_lo;
+    if (sa[a] >= 0) sa[a] = sa[a] >= area_lo ? sa[a] - area_lo : -2;     // -2: outside the owned areas -> rejected by validation
 }
 
 __global__ void k_validate_routine(const int32_t* __restrict__ routine, int64_t n, int64_t B, int32_t* bad)

@@ -44,6 +44,8 @@ class _Params(C.Structure):
         ("seed", C.c_uint64), ("flags", C.c_int32), ("reserved", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
         ("halo_lo", C.c_int64), ("halo_hi", C.c_int64),
+        ("hh_lo", C.c_int64), ("hh_hi", C.c_int64), ("bld_lo", C.c_int64), ("bld_hi", C.c_int64),
+        ("area_lo", C.c_int64), ("area_hi", C.c_int64),
     ]
 
 
@@ -162,6 +164,13 @@ class Engine:
         p.rank, p.world = rank, world
         p.shard_lo, p.shard_hi = pop.lo, pop.lo + pop.N
         p.halo_lo, p.halo_hi = pop.halo
+        self.hh_range = pop.hh_range or (0, pop.H)
+        self.bld_range = pop.bld_range or (0, pop.B)
+        self.sa_range = pop.sa_range or (0, pop.S)
+        p.hh_lo, p.hh_hi = self.hh_range
+        p.bld_lo, p.bld_hi = self.bld_range
+        p.area_lo, p.area_hi = self.sa_range
+        self.S_out, self.B_out = self.sa_range[1] - self.sa_range[0], self.bld_range[1] - self.bld_range[0]
         self.flags = flags
         self.h = C.c_void_p()
         rc = self.lib.dys_create(C.byref(p), device, C.byref(self.h))
@@ -188,7 +197,8 @@ class Engine:
         g = [a(pop.ip_rowptr, np.int64, n + 1), a(pop.ip_col, np.int32, None), a(pop.ip_val, np.float64, None)]
         self._ck(self.lib.dys_load_graph(self.h, *[k[0] for k in g]))
         if pop.hh_always is not None and (pop.hh_always.any() or len(pop.trig_hh)):
-            q = [a(pop.hh_always, np.uint8, pop.H), a(pop.trig_ptr, np.int64, n + 1), a(pop.trig_hh, np.int32, None)]
+            hl, hh_ = self.hh_range
+            q = [a(pop.hh_always[hl:hh_], np.uint8, hh_ - hl), a(pop.trig_ptr, np.int64, n + 1), a(pop.trig_hh - hl, np.int32, None)]
             self._ck(self.lib.dys_load_quirk(self.h, *[k[0] for k in q]))
         self.set_open(pop.open)
 
@@ -259,8 +269,8 @@ class Engine:
         if views is None:
             as_np = np.ctypeslib.as_array
             views = (as_np(o.stats, (N_STATS,)),
-                     as_np(o.sa_hist, (self.pop.S, HIST_LEN)) if o.sa_hist else None,
-                     as_np(o.building_counts, (self.pop.B,)) if o.building_counts else None)
+                     as_np(o.sa_hist, (self.S_out, HIST_LEN)) if o.sa_hist else None,
+                     as_np(o.building_counts, (self.B_out,)) if o.building_counts else None)
             self._views[key] = views
         n_ev, n_in = int(o.n_events), int(o.events_inline)
         ev = None
@@ -280,12 +290,12 @@ class Engine:
         return out
 
     def sa_hist(self, day):
-        out = np.zeros((self.pop.S, HIST_LEN), dtype=np.int32)
+        out = np.zeros((self.S_out, HIST_LEN), dtype=np.int32)
         self._ck(self.lib.dys_get_sa_hist(self.h, int(day), out.ctypes.data))
         return out
 
     def building_counts(self, day):
-        out = np.zeros(self.pop.B, dtype=np.int32)
+        out = np.zeros(self.B_out, dtype=np.int32)
         self._ck(self.lib.dys_get_building_counts(self.h, int(day), out.ctypes.data))
         return out
 

@@ -98,6 +98,9 @@ class Population:
     N_glob: int = None
     lo: int = 0
     halo: tuple = None
+    hh_range: tuple = None         # owned households / buildings / areas (index ranges); None = all
+    bld_range: tuple = None
+    sa_range: tuple = None
     age: np.ndarray = None
 
     def __post_init__(self):

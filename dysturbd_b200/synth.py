@@ -237,7 +237,9 @@ def synth_population(n_agents, seed=0, degree=14, cross=0.02, communities=None, 
         agent_ids=AGENT_ID0 + np.arange(lo, hi, dtype=np.float64), hh_ids=HH_ID0 + np.arange(L.H, dtype=np.float64),
         bld_ids=BLD_ID0 + np.arange(L.B, dtype=np.float64), sa_ids=np.arange(L.S, dtype=np.float64),
         bld_lu=bld_lu, bld_usg=bld_usg, bld_sa=bld_sa,
-        N_glob=L.N, lo=lo, halo=halo, age=cat("age", np.int32))
+        N_glob=L.N, lo=lo, halo=halo, age=cat("age", np.int32),
+        hh_range=(int(L.h0[c_lo]), int(L.h0[c_hi])), bld_range=(int(L.b0[c_lo]), int(L.b0[c_hi])),
+        sa_range=(int(L.s0[c_lo]), int(L.s0[c_hi])))
     return pop
 
 

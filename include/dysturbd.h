@@ -106,6 +106,11 @@ typedef struct dys_params {
     /* `routine` passed to dys_load_population covers global agents [halo_lo, halo_hi) -- the owned range plus every
      * agent an owned interaction_prob row references; 0, 0 means all n_agents */
     int64_t halo_lo, halo_hi;
+    /* the households / home buildings / statistical areas of the owned agents form these index ranges (0, 0 = all).
+     * hh / home / sa are passed as global indices; the per-household flags and the per-area / per-building OUTPUTS
+     * (dys_get_sa_hist, dys_get_building_counts, dys_get_outputs) only cover the owned ranges, so a shard's daily
+     * transfer does not grow with the total population.  hh_always / trig_hh of dys_load_quirk are relative to hh_lo. */
+    int64_t hh_lo, hh_hi, bld_lo, bld_hi, area_lo, area_hi;
 } dys_params;
 
 /* literal pre-drawn uniforms (small N only): replaces np.random.random at contagious3.py:212, :224, :239 */
@@ -155,8 +160,8 @@ int dys_step_end(dys_handle* h, int32_t day);
  * histograms, building counts, events and the IO matrix only for the most recent day. */
 #define DYS_STATS_RING 64
 int dys_get_stats(dys_handle* h, int32_t day, int64_t* out /* [DYS_N_STATS] */);
-int dys_get_sa_hist(dys_handle* h, int32_t day, int32_t* out /* [S*DYS_HIST_LEN] */);
-int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out /* [B] */);
+int dys_get_sa_hist(dys_handle* h, int32_t day, int32_t* out /* [(area_hi-area_lo)*DYS_HIST_LEN] */);
+int dys_get_building_counts(dys_handle* h, int32_t day, int32_t* out /* [bld_hi-bld_lo] */);
 int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_t* infector, int64_t cap, int64_t* n);
 int dys_get_io_mat(dys_handle* h, int32_t day, int32_t* out /* [S*S] */);
 int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, int32_t* t_q, int32_t* t_adm, int32_t* src);

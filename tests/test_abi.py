@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_params_struct_matches_header():
     from dysturbd_b200.engine import _Params
     # 4*8 + 8*4 + 2*8 + 64*8 + 8 + 2*4 + 2*4 + 2*8 + 2*8
-    assert ctypes.sizeof(_Params) == 32 + 32 + 16 + 512 + 8 + 8 + 8 + 16 + 16
+    assert ctypes.sizeof(_Params) == 32 + 32 + 16 + 512 + 8 + 8 + 8 + 16 + 16 + 48
 
 
 def test_no_gpu_means_loud_failure():

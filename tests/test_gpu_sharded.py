@@ -44,6 +44,10 @@ def _worker(rank, world, port, out, mode):
                 rs = ref.state()
                 for k in st:
                     ok &= bool(np.array_equal(st[k], rs[k][:pop.N]))
+                # per-area / per-building outputs only cover the owned ranges (the daily transfer must not grow with N)
+                o = sh.outputs(d)
+                ok &= bool(np.array_equal(o["sa_hist"], ref.sa_hist(d)[pop.sa_range[0]:pop.sa_range[1]]))
+                ok &= bool(np.array_equal(o["building_counts"], ref.building_counts(d)[pop.bld_range[0]:pop.bld_range[1]]))
             a, s_ = sh.sim.events(d)
             cross += int(((s_ < pop.lo) | (s_ >= pop.lo + pop.N)).sum())
         t = torch.tensor([cross], device="cuda")

@@ -25,7 +25,7 @@ int main(int argc, char** argv)
     const int64_t N = argc > 1 ? atoll(argv[1]) : 1002496;
     const double frac_inf = argc > 2 ? atof(argv[2]) : 0.02;
     DevCtx c{};
-    c.n_loc = c.n_pad = c.n_glob = N; c.rt_n = N; c.H = N / 3; c.B = N / 20; c.S = N / 1200; c.V = 10;
+    c.n_loc = c.n_pad = c.n_glob = N; c.rt_n = N; c.H = N / 3; c.B = N / 20; c.S = N / 1200; c.V = 10; c.B_out = c.B; c.S_out = c.S;
     c.recover = 21; c.hospital_recover = 28; c.diagnosis = 7; c.quarantine = 7; c.adm_min = 4; c.adm_max = 14; c.death_min = 3;
     c.norm_factor = 4.0; c.compliance = 1.0; c.seed = 1;
     std::vector<uint8_t> st(N, ST_S); std::vector<int16_t> ti(N, 0); std::vector<int32_t> hh(N), home(N), sa(N), src(N, -1);
