@@ -230,6 +230,7 @@ def run_ours(args):
     h2d = d2h = 0
     stats_days, pending = [], []
     checksum = 0
+    side = torch.cuda.Stream(device=local)
     with torch.cuda.stream(stream):
         def consume_day(d, count):
             nonlocal d2h, checksum
@@ -244,9 +245,10 @@ def run_ours(args):
             if world > 1 and pending and (len(pending) == 7 or d == W + K - 1):
                 # global stats (R, the lockdown decision) are only needed `diagnosis` = 7 days later
                 # (contagious3.py:306-309): one all-reduce per week of stacked 64-integer blocks
-                t = torch.from_numpy(np.stack(pending)).cuda()
-                dist.all_reduce(t)
-                g = t.cpu().numpy()
+                with torch.cuda.stream(side):          # not on the library's stream: the days keep flowing
+                    t = torch.from_numpy(np.stack(pending)).cuda()
+                    dist.all_reduce(t)
+                    g = t.cpu().numpy()
                 for k in range(len(pending)):
                     stats_days[len(stats_days) - len(pending) + k] = g[k]
                 pending.clear()
