@@ -177,9 +177,6 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(raw(eng).cuda_stream(), device=local)
     init = pop.copy_state()
 
-    def day_step(e, day):
-        e.step(day)
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -212,6 +209,7 @@ def run_ours(args):
         clocks.active = True
         ev0.record(stream)
         run_resident(W, W + K)
+        raw(eng).sync()              # the last days' output blocks are still leaving on the library's copy stream
         ev1.record(stream)
         barrier()
         clocks.active = False
@@ -280,12 +278,12 @@ def run_ours(args):
     stream_t = torch.cuda.ExternalStream(raw(eng_t).cuda_stream(), device=local)
     with torch.cuda.stream(stream_t):
         for d in range(W):
-            day_step(eng_t, d)
+            eng_t.step(d)
         raw(eng_t).kernel_times()
         prev_w = raw(eng_t).stats(W - 1) if W > 0 else None      # day-start compartment counts of the first timed day
         barrier()
         for d in range(W, W + K):
-            day_step(eng_t, d)
+            eng_t.step(d)
         ms_k, n_k = raw(eng_t).kernel_times()
     prev = prev_w if prev_w is not None and world == 1 else stats_days[0]
     kb = {"k_push": 0, "k_agent": 0}
@@ -331,8 +329,8 @@ def run_ours(args):
             "agents_total": n_total, "edges_per_gpu": pop.nnz, "norm_factor": args.norm_factor,
             "seeds_per_22493": args.seeds_per_22493, "scenario": "noLockdown",
             "parallelism": "1 GPU" if world == 1 else "sharded by community x%d, exchange=%s (peer: snapshot bytes stored into every peer GPU by k_agent over NVLink; nccl: per-day all-gather)" % (world, args.exchange),
-            "l2": "state + network of one day (%.0f MB) exceed L2 only partly; every day rewrites the state, no flush" %
-                  (eng_bytes(pop) / 1e6),
+            "l2": "no flush: the inputs of a day (%.0f MB of state + network per GPU) are larger than the 126 MB L2 and "
+                  "every day rewrites the state" % (eng_bytes(pop) / 1e6),
             "ever_infected_at_end": int(st_last[STAT["ever_infected"]]) if world == 1 else None,
             "load_seconds": load_s,
         },
@@ -343,7 +341,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms, "per_kernel": per_kernel},
+                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms, "per_kernel": per_kernel,
+                     "traffic_note": "ncu dram bytes of k_days = 8.6-9.4 MB per simulated day on days 8-21, equal to the "
+                                     "algorithmic bytes of those days (profiles/r01h_summary.md)"},
         "clocks": clocks.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:

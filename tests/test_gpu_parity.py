@@ -203,3 +203,28 @@ def test_step_many_fused_windows_vs_oracle(eng, oracle_lib):
             assert np.array_equal(sg[key], so[key]), (key, day)
     assert o.stats()[9] > 3000
     g.close()
+
+
+def test_replica_sweep_is_reproducible(eng, oracle_lib):
+    """BASELINE.json configs[4]: replicas of one loaded city (dys_set_state + dys_set_run) over norm_factor x compliance;
+    every replica equals a fresh oracle run with the same parameters and seed."""
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import synth_population
+    pop = synth_population(9000, seed=12, seeds_per_22493=150)
+    g = eng.Engine(pop, EpiParams(), flags=0)
+    sizes = {}
+    for k, (norm, comp) in enumerate([(4.0, 1.0), (8.0, 1.0), (8.0, 0.4)]):
+        g.set_state(pop.status, pop.t_inf, pop.t_q, pop.t_adm, pop.src)
+        g.set_run(norm_factor=norm, compliance=comp, seed=100 + k)
+        g.step_many(0, 7)
+        g.step_many(7, 7)
+        g.step_many(14, 6)
+        o = oracle_lib.OracleSim(pop, EpiParams(norm_factor=norm, compliance=comp, seed=100 + k))
+        for d in range(20):
+            o.step(d)
+        sg, so = g.state(), o.state()
+        for key in sg:
+            assert np.array_equal(sg[key], so[key]), (key, norm, comp)
+        sizes[(norm, comp)] = int(o.stats()[9])
+    assert sizes[(8.0, 1.0)] > sizes[(4.0, 1.0)]
+    g.close()
