@@ -172,6 +172,7 @@ def run_ours(args):
 
     t0 = time.perf_counter()
     eng = make_engine(all_out)
+    eng_mode = getattr(eng, "mode", "single")
     raw(eng).sync()
     load_s = time.perf_counter() - t0
     stream = torch.cuda.ExternalStream(raw(eng).cuda_stream(), device=local)
@@ -328,7 +329,7 @@ def run_ours(args):
                         (pop.N, args.communities_per_gpu, W, W + K - 1),
             "agents_total": n_total, "edges_per_gpu": pop.nnz, "norm_factor": args.norm_factor,
             "seeds_per_22493": args.seeds_per_22493, "scenario": "noLockdown",
-            "parallelism": "1 GPU" if world == 1 else "sharded by community x%d, exchange=%s (peer: snapshot bytes stored into every peer GPU by k_agent over NVLink; nccl: per-day all-gather)" % (world, args.exchange),
+            "parallelism": "1 GPU" if world == 1 else "sharded by community x%d, exchange=%s (peer: snapshot bytes stored into every peer GPU by k_agent over NVLink; nccl: per-day all-gather)" % (world, eng_mode),
             "l2": "no flush: the inputs of a day (%.0f MB of state + network per GPU) are larger than the 126 MB L2 and "
                   "every day rewrites the state" % (eng_bytes(pop) / 1e6),
             "ever_infected_at_end": int(st_last[STAT["ever_infected"]]) if world == 1 else None,

@@ -445,6 +445,9 @@ extern "C" int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
     int rc = DYS_OK;
+    if (hh_always && h->p.world > 1)
+        return fail(h, DYS_ERR_NOT_AVAILABLE, "hh_always (households quarantined whenever ANYONE is diagnosed, contagious3.py:267) "
+                    "needs a global diagnosis flag and is not available in sharded mode");
     if (hh_always) {
         uint8_t* d = nullptr;
         rc = dev_alloc(h, &d, c.H);
@@ -1006,6 +1009,8 @@ extern "C" int dys_peer_export(dys_handle* h, void* out /* DYS_PEER_HANDLE_BYTES
     return DYS_OK;
 }
 
+extern "C" int dys_peer_detach(dys_handle* h);
+
 extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */,
                                const int64_t* halos /* [n_ranks][4] */)
 {
@@ -1016,8 +1021,15 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
     for (int r = 0; r < n_ranks; ++r) {
         if (r == h->p.rank) { h->peer_ib[r] = h->d_ib; h->peer_flags[r] = h->d_peer_flags; continue; }
         void *pib = nullptr, *pfl = nullptr;
-        CK(h, cudaIpcOpenMemHandle(&pib, hs[2 * r], cudaIpcMemLazyEnablePeerAccess));
-        CK(h, cudaIpcOpenMemHandle(&pfl, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        cudaError_t e1 = cudaIpcOpenMemHandle(&pib, hs[2 * r], cudaIpcMemLazyEnablePeerAccess);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&pfl, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) : e1;
+        if (e2 != cudaSuccess) {
+            cudaGetLastError();
+            h->n_peers = r;               // so that dys_peer_detach closes what was opened
+            h->peer_ib[r] = (uint8_t*)pib;
+            dys_peer_detach(h);
+            return fail(h, DYS_ERR_NOT_AVAILABLE, "peer memory of rank %d is not reachable (%s): use the NCCL exchange", r, cudaGetErrorString(e2));
+        }
         h->peer_ib[r] = (uint8_t*)pib;
         h->peer_flags[r] = (int32_t*)pfl;
     }
@@ -1034,6 +1046,24 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
         if (h->peer_own[me][0] < h->peer_halo[r][1] && h->peer_own[me][1] > h->peer_halo[r][0]) h->signal_mask |= 1u << r;
     }
     h->n_peers = n_ranks;
+    h->ib_day = -1;
+    return DYS_OK;
+}
+
+extern "C" int dys_peer_detach(dys_handle* h)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->n_peers; ++r) {
+        if (r == h->p.rank) continue;
+        if (h->peer_ib[r]) cudaIpcCloseMemHandle(h->peer_ib[r]);
+        if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+        h->peer_ib[r] = nullptr; h->peer_flags[r] = nullptr;
+    }
+    cudaGetLastError();
+    h->n_peers = 1;
+    h->wait_mask = h->signal_mask = 0;
     h->ib_day = -1;
     return DYS_OK;
 }

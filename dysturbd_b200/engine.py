@@ -62,7 +62,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_many", "dys_step_begin", "dys_step_end", "dys_get_stats",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
-           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach"]
+           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach"]
 
 _lib = None
 
@@ -108,6 +108,7 @@ def load_library():
     lib.dys_keyed_uniform_device.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, i64, vp]
     lib.dys_peer_export.argtypes = [vp, vp]
     lib.dys_peer_attach.argtypes = [vp, C.c_int, vp, vp]
+    lib.dys_peer_detach.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -353,6 +354,9 @@ class Engine:
         blob = b"".join(handles)
         hal = np.ascontiguousarray(halos, dtype=np.int64).reshape(len(handles), 4)
         self._ck(self.lib.dys_peer_attach(self.h, len(handles), blob, hal.ctypes.data))
+
+    def peer_detach(self):
+        self._ck(self.lib.dys_peer_detach(self.h))
 
     def cuda_stream(self):
         p = C.c_void_p()

@@ -46,7 +46,16 @@ class ShardedEngine:
             if self.mode == "peer":
                 handles = [None] * self.world
                 dist.all_gather_object(handles, (self.sim.peer_export(), (pop.lo, pop.lo + pop.N) + tuple(pop.halo)), group=group)
-                self.sim.peer_attach([x[0] for x in handles], [x[1] for x in handles])
+                ok = 1
+                try:
+                    self.sim.peer_attach([x[0] for x in handles], [x[1] for x in handles])
+                except Exception:                  # no P2P path to some rank: every rank falls back together
+                    ok = 0
+                t = torch.tensor([ok], device=torch.device("cuda", device))
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+                if int(t.item()) == 0:
+                    self.sim.peer_detach()
+                    self.mode = "nccl"
                 self.sim.sync()
                 dist.barrier(group=group)          # nobody steps before every rank's flags are reset and attached
         else:                                   # tests: a CPU stand-in with the same two-half interface

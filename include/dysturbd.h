@@ -200,6 +200,7 @@ int64_t dys_device_bytes(const dys_handle* h);
  * dys_set_state in peer mode the caller must barrier across ranks before the next dys_step. */
 #define DYS_PEER_HANDLE_BYTES 128
 int dys_peer_export(dys_handle* h, void* out /* [DYS_PEER_HANDLE_BYTES] */);
+int dys_peer_detach(dys_handle* h);   /* back to the collective exchange (all ranks must do the same) */
 int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks][DYS_PEER_HANDLE_BYTES] */,
                     const int64_t* ranges /* [n_ranks][4]: every rank's shard_lo, shard_hi, halo_lo, halo_hi -- only the
                                              bytes a peer reads travel, and only the ranks that exchange bytes synchronise */);
