@@ -99,6 +99,21 @@ class ClockSampler:
                     pass
             time.sleep(0.001)
 
+    def sample_now(self):
+        """one synchronous sample (a timed region can be shorter than the polling period)"""
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((sm, rs))
+        except Exception:
+            pass
+
     def stop(self):
         self._stop = True
 
@@ -210,6 +225,7 @@ def run_ours(args):
         clocks.active = True
         ev0.record(stream)
         run_resident(W, W + K)
+        clocks.sample_now()          # queued, not finished: the GPU is inside the timed region here
         raw(eng).sync()              # the last days' output blocks are still leaving on the library's copy stream
         ev1.record(stream)
         barrier()
@@ -268,6 +284,7 @@ def run_ours(args):
         clocks.active = True
         t0 = time.perf_counter()
         run_days(W, W + K, True)
+        clocks.sample_now()
         barrier()
         s_e2e = max_over_ranks(time.perf_counter() - t0)
         clocks.active = False
