@@ -53,8 +53,7 @@ struct dys_handle {
     uint8_t* h_open = nullptr;                            // pinned shadow of the open flags
     int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags
     int32_t* d_bad = nullptr;
-    uint8_t *d_hh_flag[2] = {nullptr, nullptr}, *d_hh_qflag[2] = {nullptr, nullptr};
-    int32_t* d_flags = nullptr;      // [2][DF_LEN] per-parity day flags, then [1] closed-building count
+    DayBuffers buf{};                // attention bytes, mailboxes, quirk flags, flag blocks, partial sums: rings indexed by day
     int32_t ib_day = -1;             // the day whose day-start snapshot bytes are complete in buffer ib_day & 1
     uint8_t* d_ib = nullptr;         // [2][ib_stride] snapshot bytes of all agents, double buffered by day parity
     int64_t ib_stride = 0;
@@ -69,6 +68,8 @@ struct dys_handle {
     int push_grid = 0;               // persistent grid of k_push
     int last_slot = 0;
     bool no_fuse = false;            // DYS_NO_FUSE=1 in the environment: dys_step_many launches two kernels a day
+    const char* trace_path = nullptr;          // DYS_TRACE=<file> (developer): per-block phase timestamps of every fused window
+    unsigned long long* d_trace = nullptr;
     double* d_pair_prob = nullptr;
     double *d_u_adm = nullptr, *d_u_death = nullptr, *d_u_pair = nullptr;   // staged injected draws
     // kernel timing
@@ -145,6 +146,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     h->p = p;
     h->device = device;
     { const char* nf = getenv("DYS_NO_FUSE"); h->no_fuse = nf && nf[0] == '1'; }
+    h->trace_path = getenv("DYS_TRACE");
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -181,9 +183,18 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     A(dev_alloc(h, &h->d_ib, 2 * h->ib_stride));
     A(dev_alloc(h, &h->d_peer_flags, 8));
     A(dev_alloc(h, (uint8_t**)&c.open, c.B));
-    for (int k = 0; k < 2; ++k) { A(dev_alloc(h, &h->d_hh_flag[k], c.H + 16)); A(dev_alloc(h, &h->d_hh_qflag[k], c.H + 16)); }
-    A(dev_alloc(h, &h->d_flags, 2 * DF_LEN + 4));
-    A(dev_alloc(h, &c.part, (int64_t)N_SLOTS * N_STATS)); A(dev_alloc(h, &c.ticket, 1));
+    for (int k = 0; k < 2; ++k) {
+        A(dev_alloc(h, &h->buf.att[k], c.n_pad + 16));
+        A(dev_alloc(h, &h->buf.mb_any[k], c.n_pad)); A(dev_alloc(h, &h->buf.mb_iso[k], c.n_pad));
+        h->buf.ib[k] = h->d_ib + (size_t)k * h->ib_stride;
+        for (int r = 0; r < 8; ++r) h->buf.peer_ib[r][k] = h->buf.ib[k];
+    }
+    for (int k = 0; k < Q_RING; ++k) A(dev_alloc(h, &h->buf.qflag[k], c.H + 16));
+    A(dev_alloc(h, &h->buf.df, DF_RING * DF_LEN));
+    A(dev_alloc(h, &h->buf.part, (int64_t)PART_RING * N_SLOTS * N_STATS)); A(dev_alloc(h, &c.ticket, 1));
+    A(dev_alloc(h, (int64_t**)&c.hh_ptr, c.H + 1)); A(dev_alloc(h, (int32_t**)&c.hh_mem, c.n_pad));
+    c.n_peers = 1; c.rank = p.rank; c.flag_wait = h->d_peer_flags;
+    for (int r = 0; r < 8; ++r) c.flag_signal[r] = h->d_peer_flags ? h->d_peer_flags + p.rank : nullptr;
     A(dev_alloc(h, &d_pdf, DYS_PDF_LEN));
     A(dev_alloc(h, &h->d_bad, 1));
     {   // one output block per parity: everything a day produces leaves the device in a single copy
@@ -202,10 +213,10 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     c.n_closed = 0;
     if (rc == DYS_OK) {
         int per_sm = 0, sms = 0;
-        cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, PUSH_WARPS * 32, 0);
+        cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, BLOCK, 0);
         if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (e2 != cudaSuccess || per_sm < 1) { h->err = std::string("k_push occupancy: ") + cudaGetErrorString(e2); rc = DYS_ERR_CUDA; }
-        const int64_t n_cta = ((c.rt_n + 31) / 32 + PUSH_WARPS - 1) / PUSH_WARPS;    // never more warps than groups
+        const int64_t n_cta = (c.rt_n + 15) / 16;                                       // a block's share is at least 16 agents
         const int64_t want = (int64_t)per_sm * sms;                                     // persistent: a multiple of the SM count
         h->push_grid = (int)(n_cta < want ? n_cta : want);
         int coop = 0, per_sm_days = 0;
@@ -267,11 +278,13 @@ static int reset_day_scratch(dys_handle* h)
 {
     DevCtx& c = h->c;
     for (int k = 0; k < 2; ++k) {
-        CK(h, cudaMemsetAsync(h->d_hh_flag[k], 0, (size_t)c.H + 16, h->stream));
-        CK(h, cudaMemsetAsync(h->d_hh_qflag[k], 0, (size_t)c.H + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->buf.att[k], 0, (size_t)c.n_pad + 16, h->stream));
+        CK(h, cudaMemsetAsync(h->buf.mb_any[k], 0xFF, sizeof(int32_t) * (size_t)c.n_pad, h->stream));   // -1: empty mailbox
+        CK(h, cudaMemsetAsync(h->buf.mb_iso[k], 0xFF, sizeof(int32_t) * (size_t)c.n_pad, h->stream));
     }
-    CK(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 2 * DF_LEN, h->stream));
-    CK(h, cudaMemsetAsync(c.part, 0, sizeof(unsigned long long) * N_SLOTS * N_STATS, h->stream));
+    for (int k = 0; k < Q_RING; ++k) CK(h, cudaMemsetAsync(h->buf.qflag[k], 0, (size_t)c.H + 16, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.df, 0, sizeof(int32_t) * DF_RING * DF_LEN, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.part, 0, sizeof(unsigned long long) * PART_RING * N_SLOTS * N_STATS, h->stream));
     CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
     h->ib_day = -1;
     h->begun = false;
@@ -349,6 +362,22 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
     CK(h, cudaGetLastError());
     rc = check_bad(h, "dys_load_population");
     if (rc != DYS_OK) return rc;
+    {   // household -> members (phase F flags the MEMBERS of a diagnosed agent's household, contagious3.py:263)
+        int32_t* d_cnt = nullptr;
+        unsigned long long* d_cursor = nullptr;
+        cudaError_t e = cudaMalloc((void**)&d_cnt, sizeof(int32_t) * (size_t)c.H);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_cursor, sizeof(unsigned long long) * (size_t)c.H);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * (size_t)c.H, h->stream);
+        if (e == cudaSuccess) {
+            k_count_members<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c.hh, c.n_loc, d_cnt);
+            k_scan_counts<<<1, 1024, 0, h->stream>>>(d_cnt, c.H, (int64_t*)c.hh_ptr, d_cursor);
+            k_fill_members<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c.hh, c.n_loc, d_cursor, (int32_t*)c.hh_mem);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(d_cnt); cudaFree(d_cursor);
+        if (e != cudaSuccess) return fail(h, DYS_ERR_CUDA, "building the household index failed: %s", cudaGetErrorString(e));
+    }
     h->have_pop = true;
     h->have_graph = false;
     return reset_day_scratch(h);
@@ -506,18 +535,50 @@ extern "C" int dys_set_open(dys_handle* h, const uint8_t* open_flags)
     return DYS_OK;
 }
 
-// peer r's buffer of parity `parity` becomes a write target; only the part of the owned slice inside r's halo travels
-static void add_peer_target(dys_handle* h, int r, int parity)
+// the day-independent peer fields of the context: who waits for whom, and which part of the owned slice each write
+// target needs (only the bytes inside that rank's halo travel)
+static void bind_peers(dys_handle* h)
 {
     DevCtx& c = h->c;
-    const int p = c.n_wr++;
-    c.ib_wr[p] = h->peer_ib[r] + (size_t)parity * h->ib_stride;
-    int64_t lo = c.lo > h->peer_halo[r][0] ? c.lo : h->peer_halo[r][0];
-    int64_t hi = c.lo + c.n_pad < h->peer_halo[r][1] ? c.lo + c.n_pad : h->peer_halo[r][1];
-    lo &= ~(int64_t)15;
-    hi = (hi + 15) & ~(int64_t)15;
-    c.pub_lo[p] = lo;
-    c.pub_n[p] = hi > lo ? hi - lo : 0;
+    c.n_peers = h->n_peers; c.rank = h->p.rank;
+    c.flag_wait = h->d_peer_flags;
+    c.wait_mask = h->wait_mask; c.signal_mask = h->signal_mask;
+    int p = 1;
+    c.pub_lo[0] = 0; c.pub_n[0] = 0;
+    for (int r = 0; r < h->n_peers; ++r) {
+        c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
+        for (int k = 0; k < 2; ++k) h->buf.peer_ib[r][k] = (h->n_peers > 1 ? h->peer_ib[r] : h->d_ib) + (size_t)k * h->ib_stride;
+        if (h->n_peers > 1 && r != h->p.rank) {
+            int64_t lo = c.lo > h->peer_halo[r][0] ? c.lo : h->peer_halo[r][0];
+            int64_t hi = c.lo + c.n_pad < h->peer_halo[r][1] ? c.lo + c.n_pad : h->peer_halo[r][1];
+            lo &= ~(int64_t)15;
+            hi = (hi + 15) & ~(int64_t)15;
+            c.pub_lo[p] = lo;
+            c.pub_n[p] = hi > lo ? hi - lo : 0;
+            ++p;
+        }
+    }
+}
+
+// phase A on its own for `day`: the day's attention bytes / quirk flags / flag block start clean, k_snapshot raises
+// into them and writes the snapshot bytes of parity day & 1 (published to the peers in peer mode)
+static int run_snapshot(dys_handle* h, int32_t day)
+{
+    DevCtx& c = h->c;
+    CK(h, cudaMemsetAsync(h->buf.att[day & 1], 0, (size_t)c.n_pad + 16, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.qflag[day % Q_RING], 0, (size_t)c.H + 16, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.df + (day & (DF_RING - 1)) * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
+    bind_day(c, h->buf, day);
+    bind_ib_targets(c, h->buf, day & 1);
+    k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    if (h->n_peers > 1) {
+        k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
+        k_signal<<<1, 32, 0, h->stream>>>(c, day);
+    }
+    CK(h, cudaGetLastError());
+    bind_day(c, h->buf, day);
+    h->ib_day = day;
+    return DYS_OK;
 }
 
 static void tick(dys_handle* h, int which)
@@ -555,34 +616,14 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
         }
     }
     if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
-    const int par = (int)(h->steps & 1);
-    auto ib_targets = [&](int parity) {       // where snapshot bytes of parity `parity` are written: own buffer, then peers
-        c.n_peers = h->n_peers; c.rank = h->p.rank;
-        c.flag_wait = h->d_peer_flags;
-        c.wait_mask = h->wait_mask; c.signal_mask = h->signal_mask;
-        c.n_wr = 0;
-        c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
-        for (int r = 0; r < h->n_peers; ++r) {
-            c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
-            if (h->n_peers > 1 && r != h->p.rank) add_peer_target(h, r, parity);
-        }
-    };
-    c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
+    bind_peers(h);
+    bind_day(c, h->buf, day);
     tick(h, 0);
     if (h->ib_day != day || (inj && inj->u_adm)) {
-        // phase A on its own: first day after a load / set_state, a skipped day, or injected admission draws
-        // (tomorrow's diagnoses cannot be predicted from an array the caller has not handed over yet)
-        CK(h, cudaMemsetAsync(h->d_hh_flag[par], 0, (size_t)c.H + 16, h->stream));
-        CK(h, cudaMemsetAsync(h->d_hh_qflag[par], 0, (size_t)c.H + 16, h->stream));
-        CK(h, cudaMemsetAsync(h->d_flags + par * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
-        ib_targets(day & 1);
-        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day, h->d_hh_flag[par], h->d_hh_qflag[par],
-                                                                      h->d_flags + par * DF_LEN);
-        if (h->n_peers > 1) {
-            k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
-            k_signal<<<1, 32, 0, h->stream>>>(c, day);
-        }
-        h->ib_day = day;
+        // first day after a load / set_state, a skipped day, or injected admission draws (tomorrow's diagnoses cannot
+        // be predicted from an array the caller has not handed over yet)
+        int rc = run_snapshot(h, day);
+        if (rc != DYS_OK) return rc;
     }
     tick(h, 1);
     CK(h, cudaGetLastError());
@@ -614,28 +655,11 @@ static int ship_day(dys_handle* h, int32_t day, int slot, int64_t step)
     return DYS_OK;
 }
 
-static void set_snapshot_targets(dys_handle* h, int32_t day)
-{
-    DevCtx& c = h->c;
-    c.ib_rd = h->d_ib + (size_t)(day & 1) * h->ib_stride;
-    c.n_peers = h->n_peers; c.rank = h->p.rank; c.flag_wait = h->d_peer_flags;
-    c.wait_mask = h->wait_mask; c.signal_mask = h->signal_mask;
-    c.n_wr = 0;
-    // k_agent writes tomorrow's bytes (parity (day+1)&1) into its own buffer and, in peer mode, into every peer's
-    const int parity = (day + 1) & 1;
-    c.ib_wr[c.n_wr++] = h->d_ib + (size_t)parity * h->ib_stride;
-    for (int r = 0; r < h->n_peers; ++r) {
-        c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
-        if (h->n_peers > 1 && r != h->p.rank) add_peer_target(h, r, parity);
-    }
-}
-
 static int step_end(dys_handle* h, int32_t day)
 {
     if (!h->begun) return fail(h, DYS_ERR_STATE, "dys_step_end without dys_step_begin");
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
-    const int par = (int)(h->steps & 1);
     const int slot = (int)(h->steps % DYS_OUT_RING);
     int rc = retire_slot(h, slot);
     if (rc != DYS_OK) return rc;
@@ -643,12 +667,10 @@ static int step_end(dys_handle* h, int32_t day)
     c.sa_hist = (h->p.flags & DYS_WANT_SA_HIST) ? (int32_t*)(h->d_out[slot] + h->off_sa) : nullptr;
     c.bcount = (h->p.flags & DYS_WANT_BUILDING_COUNTS) ? (int32_t*)(h->d_out[slot] + h->off_bc) : nullptr;
     c.ev = (h->p.flags & DYS_WANT_EVENTS) ? (int2*)(h->d_out[slot] + h->off_ev) : nullptr;
-    c.hh_flag = h->d_hh_flag[par]; c.hh_qflag = h->d_hh_qflag[par];
-    c.hh_flag_next = h->d_hh_flag[par ^ 1]; c.hh_qflag_next = h->d_hh_qflag[par ^ 1];
-    c.df = h->d_flags + par * DF_LEN; c.df_next = h->d_flags + (par ^ 1) * DF_LEN;
     h->last_slot = slot;
-    set_snapshot_targets(h, day);
-    k_push<<<(unsigned)h->push_grid, PUSH_WARPS * 32, 0, h->stream>>>(c, day);
+    bind_peers(h);
+    bind_day(c, h->buf, day);
+    k_push<<<(unsigned)h->push_grid, BLOCK, 0, h->stream>>>(c, day);
     tick(h, 2);
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     tick(h, 3);
@@ -675,17 +697,12 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     DevCtx& c = h->c;
     DayPlan plan{};
     plan.first_day = first_day; plan.n_days = n_days;
-    plan.first_parity = (int)(h->steps & 1);
     plan.off_sa = h->off_sa; plan.off_bc = h->off_bc; plan.off_ev = h->off_ev;
     plan.want_sa = (h->p.flags & DYS_WANT_SA_HIST) != 0;
     plan.want_bc = (h->p.flags & DYS_WANT_BUILDING_COUNTS) != 0;
     plan.want_ev = (h->p.flags & DYS_WANT_EVENTS) != 0;
-    for (int k = 0; k < 2; ++k) {
-        plan.hh_flag[k] = h->d_hh_flag[k]; plan.hh_qflag[k] = h->d_hh_qflag[k];
-        plan.df[k] = h->d_flags + k * DF_LEN;
-        plan.ib[k] = h->d_ib + (size_t)k * h->ib_stride;
-        for (int r = 0; r < h->n_peers; ++r) plan.peer_ib[r][k] = (h->n_peers > 1 ? h->peer_ib[r] : h->d_ib) + (size_t)k * h->ib_stride;
-    }
+    bind_peers(h);
+    plan.buf = h->buf;
     // open flags: a day whose vector differs from the one in force gets its own device copy
     const uint8_t* cur_dev = c.open;
     int32_t cur_closed = c.n_closed;
@@ -713,27 +730,34 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         plan.out[k] = h->d_out[slot];
     }
     if (rc != DYS_OK) return rc;
-    // first day's snapshot, if the previous day did not leave it
-    if (h->ib_day != first_day) {
-        const int par = plan.first_parity;
-        CK(h, cudaMemsetAsync(h->d_hh_flag[par], 0, (size_t)c.H + 16, h->stream));
-        CK(h, cudaMemsetAsync(h->d_hh_qflag[par], 0, (size_t)c.H + 16, h->stream));
-        CK(h, cudaMemsetAsync(h->d_flags + par * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
-        c.u_adm = c.u_death = c.u_pair = nullptr; c.pair_prob = nullptr;
-        set_snapshot_targets(h, first_day - 1);        // write targets of parity first_day & 1
-        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, first_day, h->d_hh_flag[par], h->d_hh_qflag[par],
-                                                                      h->d_flags + par * DF_LEN);
-        if (h->n_peers > 1) {
-            k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
-            k_signal<<<1, 32, 0, h->stream>>>(c, first_day);
-        }
-    }
     c.u_adm = c.u_death = c.u_pair = nullptr; c.pair_prob = nullptr;
-    set_snapshot_targets(h, first_day);                 // flag pointers; the per-day buffers come from the plan
+    if (h->ib_day != first_day) {      // first day's snapshot, if the previous day did not leave it
+        rc = run_snapshot(h, first_day);
+        if (rc != DYS_OK) return rc;
+    }
+    bind_day(c, h->buf, first_day);    // (k_days binds every day's view itself)
     CK(h, cudaMemsetAsync(h->d_barrier, 0, 2 * sizeof(unsigned int), h->stream));
     unsigned int* bar = h->d_barrier;
     void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
+    const size_t trace_words = (size_t)MAX_FUSED_DAYS * (size_t)h->days_grid * 8;
+    if (h->trace_path && h->trace_path[0]) {
+        if (!h->d_trace) { rc = dev_alloc(h, &h->d_trace, (int64_t)trace_words); if (rc != DYS_OK) return rc; }
+        plan.trace = h->d_trace;
+    }
     CK(h, cudaLaunchCooperativeKernel((const void*)k_days, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
+    if (plan.trace) {      // developer tracing: synchronous, appended as text
+        std::vector<unsigned long long> tr(trace_words);
+        CK(h, cudaMemcpyAsync(tr.data(), h->d_trace, trace_words * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (FILE* f = fopen(h->trace_path, "a")) {
+            for (int k = 0; k < n_days; ++k)
+                for (int b = 0; b < h->days_grid; ++b) {
+                    const unsigned long long* t = &tr[((size_t)k * h->days_grid + b) * 8];
+                    fprintf(f, "%d %d %llu %llu %llu %llu %llu %llu %llu %llu\n", first_day + k, b, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+                }
+            fclose(f);
+        }
+    }
     if (cur_dev != c.open) {      // the flags in force after the window become the standing vector
         CK(h, cudaMemcpyAsync((void*)c.open, cur_dev, (size_t)c.B, cudaMemcpyDeviceToDevice, h->stream));
         c.n_closed = cur_closed;

@@ -42,8 +42,13 @@ enum {
     ST_DAILY_DEATHS, ST_EVER_INFECTED, ST_NEW_DIAG, ST_N_EVENTS, ST_SUS0, ST_INF0, ST_EDGES_SCANNED, ST_CANDIDATES,
     ST_EXPOSED, ST_HITS, ST_CHANGED
 };
-// per-day flag block (double buffered by day parity): [0] somebody is diagnosed on that day, [1] events claimed
-constexpr int DF_ANY_ND = 0, DF_N_EVENTS = 1, DF_LEN = 4;
+// per-day flag block, a ring of four indexed by day & 3: [0] somebody is diagnosed on that day, [1] events claimed
+constexpr int DF_ANY_ND = 0, DF_N_EVENTS = 1, DF_LEN = 4, DF_RING = 4;
+constexpr int Q_RING = 3, PART_RING = 3;         // quirk household flags and partial sums: rings indexed by day % 3
+// per-agent attention byte (double buffered by day parity): bit0 "k_push left an infector in your mailbox",
+// bit1 "somebody of your household is diagnosed today" (contagious3.py:263).  An agent whose byte is 0 and who is
+// susceptible (or long recovered) cannot change today: the sweep of agent_body reads two bytes for it and moves on.
+constexpr uint32_t ATT_HIT = 1u, ATT_HH = 2u;
 
 struct DevCtx {
     int64_t n_loc, n_pad, n_glob, lo;    // owned agents, padded count (multiple of 1024), global agents, first owned
@@ -62,40 +67,76 @@ struct DevCtx {
     const int32_t *hh, *home, *sa;
     const double *risk, *p_adm, *p_death;
     const int32_t* routine;              // [rt_n * V] building index or -1 (halo agents: both sides of a pair are read)
+    const int64_t* hh_ptr;               // [H + 1] household -> its members (local agent indices)
+    const int32_t* hh_mem;               // [n_loc]
     // interaction_prob TRANSPOSED over the halo columns: for infectious column i, the owned rows u with ip[u,i] != 0
     const int64_t* tptr;                 // [rt_n + 1]
     const uint32_t* tcolx;               // [nnz] u (local) | class << 28
     const double* tval;                  // [nnz] ip[u, i]
     const double* pdf;                   // [64]
-    // day-start snapshot bytes of ALL agents, double buffered by day parity: k_push(d) reads ib_rd = buffer d&1, k_agent(d)
-    // writes tomorrow's bytes of the owned agents into buffer (d+1)&1 -- of this GPU and, in peer mode, of every peer GPU
-    // (P2P stores over NVLink), so the per-day exchange is fused into the producing kernel
-    const uint8_t* ib_rd;
-    uint8_t* ib_wr[8];                   // [n_wr] write targets (own buffer first)
-    int64_t pub_lo[8], pub_n[8];         // peer mode: byte range of the owned slice that target p needs (its halo)
+    const uint8_t* hh_always;            // [H] or null   (quirk of contagious3.py:267, see dys_load_quirk)
+    const int64_t* trig_ptr;             // [n_pad + 1] or null
+    const int32_t* trig_hh;
+    // peer mode (n_peers > 1)
+    int64_t pub_lo[8], pub_n[8];         // byte range of the owned slice that write target p needs (its halo)
     int32_t n_wr;
-    int32_t n_peers, rank;               // peer mode: n_peers > 1
+    int32_t n_peers, rank;
     uint32_t wait_mask, signal_mask;     // ranks whose bytes this rank reads (waits for) / ranks that read this rank's bytes
     const int32_t* flag_wait;            // [n_peers] on THIS GPU: flag_wait[r] = last day rank r's bytes are complete for
     int32_t* flag_signal[8];             // [n_peers] &flags[rank] on every GPU (own included)
+    // ---- the view of ONE day (bind_day) ----
+    // day-start snapshot bytes of ALL agents, double buffered by day parity: the scan push of day d reads buffer d&1, the
+    // agent pass of day d writes tomorrow's bytes of the owned agents into buffer (d+1)&1
+    const uint8_t* ib_rd;
+    uint8_t* ib_wr[8];                   // [n_wr] write targets (own buffer first; peers' buffers are written by publish_body)
     const uint8_t* open;                 // [B]
-    int32_t n_closed;                    // closed buildings today (counted on the host by dys_set_open)
-    const uint8_t *hh_flag, *hh_qflag;   // [H] households diagnosed TODAY / quirk households (contagious3.py:263, :267)
-    uint8_t *hh_flag_next, *hh_qflag_next;   // the other parity: tomorrow's, raised by k_agent, cleared by k_push
-    const uint8_t* hh_always;            // [H] or null
-    const int64_t* trig_ptr;             // [n_pad + 1] or null
-    const int32_t* trig_hh;
-    int32_t *df, *df_next;               // today's / tomorrow's flag block
-    unsigned long long* part;            // [N_STATS][N_SLOTS] spread partial sums
-    int64_t* stats;                      // [N_STATS]   (stats, sa_hist, bcount, ev live in one per-parity output block)
+    int32_t n_closed;                    // closed buildings today (counted on the host)
+    uint8_t *att, *att_next;             // [n_pad] attention bytes of this day / of tomorrow
+    int32_t *mb_any, *mb_iso;            // [n_pad] this day's mailboxes: largest infecting i if u is free / if u is isolated
+    uint8_t *qflag, *qflag_next;         // [H] quirk households of this day / tomorrow (contagious3.py:267)
+    int32_t *df, *df_next;               // this day's / tomorrow's flag block
+    unsigned long long* part;            // [N_STATS][N_SLOTS] spread partial sums of this day
+    int64_t* stats;                      // [N_STATS]   (stats, sa_hist, bcount, ev live in one output block per day)
     unsigned int* ticket;
-    int32_t* sa_hist;                    // [S * 21] or null
-    int32_t* bcount;                     // [B] or null
+    int32_t* sa_hist;                    // [S_out * 21] or null
+    int32_t* bcount;                     // [B_out] or null
     int2* ev;                            // [n_pad] today's (infected, infector) pairs, or null
     int32_t* io_mat;                     // [S * S] or null
     const double *u_adm, *u_death, *u_pair;   // injected draws or null
     double* pair_prob;                   // [n_glob^2] or null (tests)
 };
+
+// the buffers behind the per-day view; bind_day() points a DevCtx at the ones of `day`
+struct DayBuffers {
+    uint8_t* att[2];
+    int32_t *mb_any[2], *mb_iso[2];
+    uint8_t* qflag[Q_RING];
+    int32_t* df;                         // [DF_RING][DF_LEN]
+    unsigned long long* part;            // [PART_RING][N_STATS][N_SLOTS]
+    uint8_t* ib[2];                      // own snapshot buffers by day parity
+    uint8_t* peer_ib[8][2];              // peer mode: every rank's, by day parity
+};
+
+// where snapshot bytes of parity `parity` are written: the own buffer, then (peer mode) every other rank's
+__host__ __device__ __forceinline__ void bind_ib_targets(DevCtx& c, const DayBuffers& b, const int parity)
+{
+    c.n_wr = 0;
+    c.ib_wr[c.n_wr++] = b.ib[parity];
+    for (int r = 0; r < c.n_peers; ++r)
+        if (c.n_peers > 1 && r != c.rank) c.ib_wr[c.n_wr++] = b.peer_ib[r][parity];
+}
+
+__host__ __device__ __forceinline__ void bind_day(DevCtx& c, const DayBuffers& b, const int day)
+{
+    const int p = day & 1;
+    c.att = b.att[p]; c.att_next = b.att[p ^ 1];
+    c.mb_any = b.mb_any[p]; c.mb_iso = b.mb_iso[p];
+    c.qflag = b.qflag[day % Q_RING]; c.qflag_next = b.qflag[(day + 1) % Q_RING];
+    c.df = b.df + (day & (DF_RING - 1)) * DF_LEN; c.df_next = b.df + ((day + 1) & (DF_RING - 1)) * DF_LEN;
+    c.part = b.part + (size_t)(day % PART_RING) * N_STATS * N_SLOTS;
+    c.ib_rd = b.ib[p];
+    bind_ib_targets(c, b, p ^ 1);        // the agent pass of `day` writes tomorrow's snapshot bytes
+}
 
 __device__ __forceinline__ double draw(const double* inj, int64_t idx, uint64_t seed, uint32_t day, uint32_t stream,
                                        uint32_t a, uint32_t b)
@@ -106,7 +147,7 @@ __device__ __forceinline__ double draw(const double* inj, int64_t idx, uint64_t 
 // block-level: fold per-thread counters into the spread partial-sum slots; warp sums by redux, one global atomic per
 // counter per block, all issued by warp 0 so that a single fence orders them before the block's ticket
 template <int NC>
-__device__ __forceinline__ void block_accumulate(const DevCtx& c, const int (&idx)[NC], const unsigned int (&v)[NC],
+__device__ __forceinline__ void block_accumulate(unsigned long long* part, const int (&idx)[NC], const unsigned int (&v)[NC],
                                                  unsigned int* s_acc /* [>= NC], zeroed, block-synchronised */)
 {
     static_assert(NC <= 32, "one warp publishes the counters");
@@ -117,7 +158,7 @@ __device__ __forceinline__ void block_accumulate(const DevCtx& c, const int (&id
     }
     __syncthreads();
     if (threadIdx.x < NC && s_acc[threadIdx.x])
-        atomicAdd(&c.part[(size_t)idx[threadIdx.x] * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))],
+        atomicAdd(&part[(size_t)idx[threadIdx.x] * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))],
                   (unsigned long long)s_acc[threadIdx.x]);
 }
 

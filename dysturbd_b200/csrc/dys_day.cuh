@@ -1,17 +1,22 @@
-// The two kernels of a simulated day (contagious3.py:176-366), plus the stand-alone snapshot.
+// The kernels of a simulated day (contagious3.py:176-366).
 //
-//   k_push   phase D, pairwise infection (contagious3.py:230-248), as a FRONTIER PUSH: only today's infectious agents
-//            do work.  For infectious i the transposed interaction_prob row lists every owned u with ip[u,i] != 0; a
-//            susceptible u that shares a building with i today draws one Bernoulli; a success does
-//            atomicMax(src[u], i) -- the reference's "last writer wins" is the LARGEST infecting row index (:248), an
-//            order-independent max, and src[u] is -1 for every susceptible, so the infector array itself is the mailbox.
-//   k_agent  everything that is per agent, one streaming pass: B hospitalisation, C mortality, applying D, the ordered
-//            rules of E, F household quarantine, G the integer statistics -- and tomorrow's phase A (snapshot byte and
-//            the households that WILL see a diagnosis tomorrow, which is a pure function of an agent's own state and
-//            its keyed admission draw), so a day is two launches.
-//   k_snapshot  phase A on its own: first day after a load / dys_set_state, and every day in injected-draw mode.
+//   push   phase D, pairwise infection (contagious3.py:230-248), as a FRONTIER PUSH: only today's infectious agents do
+//          work.  For infectious i the transposed interaction_prob row lists every owned u with ip[u,i] != 0; a pair that
+//          shares a building today draws one Bernoulli; a success does atomicMax(mailbox[u], i) -- the reference's "last
+//          writer wins" is the LARGEST infecting row index (:248), an order-independent max -- and raises u's attention
+//          byte.  Two mailboxes per agent: the infector if u moves freely, and the infector if u is isolated at home
+//          (status 3: only its home slot counts, :184), so the push does not have to know u's status.
+//   agent  everything that is per agent, one streaming pass: B hospitalisation, C mortality, applying D, the ordered
+//          rules of E, F household quarantine, G the integer statistics -- and tomorrow's phase A (snapshot byte and
+//          the households that WILL see a diagnosis tomorrow, a pure function of an agent's own state and its keyed
+//          admission draw).
 //
-// Both day kernels are HBM/L2-bound integer and byte work; there is no dense contraction, hence no tensor-core path.
+// Because the push of day d+1 only needs the infectious agents' OWN new state (their snapshot byte) and static data,
+// a thread block pushes the rows of its own newly infectious agents right after its agent pass of day d: a day of the
+// fused kernel (k_days) is  [agent(d) ; push(d+1)]  per block, then ONE grid barrier.  Stand-alone launches (k_push /
+// k_agent: injected draws, sharded NCCL mode, first day of a window) find the frontier by scanning the snapshot bytes.
+//
+// All of it is HBM/L2-bound integer and byte work; there is no dense contraction, hence no tensor-core path.
 #pragma once
 #include "dys_common.cuh"
 
@@ -29,92 +34,144 @@ __device__ __forceinline__ bool diagnosed_on(const DevCtx& c, const double* u_ad
     return true;
 }
 
-__device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, uint8_t* hh_flag, uint8_t* hh_qflag, int32_t* df)
+__device__ __forceinline__ void att_or(uint8_t* att, int64_t a, uint32_t bit)
 {
-    hh_flag[c.hh[a]] = 1;                             // same-value byte stores: race-free in effect
+    atomicOr(reinterpret_cast<unsigned int*>(att + (a & ~(int64_t)3)), bit << (8 * (int)(a & 3)));
+}
+
+// agent a is diagnosed on the day the three targets belong to: every member of its household gets the attention bit
+// (contagious3.py:263-265), the quirk households of :267 are flagged, and the day is marked as having a diagnosis
+__device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, uint8_t* att, uint8_t* qflag, int32_t* df)
+{
+    const int h = __ldg(c.hh + a);
+    for (int64_t t = __ldg(c.hh_ptr + h); t < __ldg(c.hh_ptr + h + 1); ++t) att_or(att, __ldg(c.hh_mem + t), ATT_HH);
     if (c.trig_ptr)
-        for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) hh_qflag[c.trig_hh[t]] = 1;
+        for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) qflag[c.trig_hh[t]] = 1;   // same-value byte stores
     df[DF_ANY_ND] = 1;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// k_push.  Persistent, warp-autonomous.  A warp scans the snapshot bytes of 128 halo agents per step (one 32-bit load
-// per lane, the next step's load already in flight), compacts the infectious ones into its own shared-memory frontier
-// queue, and whenever 32 rows are queued expands them together: the 32 transposed rows are flattened (warp prefix sum
-// of their lengths) so every lane works on consecutive entries however the infectious agents are spread; four entries
-// per lane are in flight (one coalesced 4-byte read + one 1-byte status gather each).
-// ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-constexpr int PUSH_WARPS = 8;
-constexpr int PUSH_CHUNK = 128;                    // halo agents scanned per warp step (4 snapshot bytes per lane): small
-                                                   // steps spread the infectious rows over all resident warps
-constexpr int PUSH_QCAP = PUSH_CHUNK + 32;
+// ---------------------------------------------------------------------------------------------------------------
+// Shared memory of a block (256 threads).  The frontier outlives the agent pass; the agent work list and the push
+// scratch are never live together.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BLOCK = 256, WARPS = BLOCK / 32;
+constexpr int FCAP = 4096;                         // frontier entries: index relative to the block's base | snapshot byte << 24
+constexpr int LCAP = 2048;                         // agent work list = one batch of the sweep (2 x 4 agents per thread)
 constexpr int PUSH_PCAP = 256;
+constexpr uint32_t REL_MASK = 0x00FFFFFFu;
 
-struct PushWarpSmem {
-    uint32_t q_idx[PUSH_QCAP];                     // halo-relative index of a queued infectious agent
-    uint8_t q_ib[PUSH_QCAP];                       // its snapshot byte
-    int off[36];                                   // exclusive prefix of the 32 expanded rows' lengths
-    int64_t t0[32];
-    unsigned long long pairs[PUSH_PCAP];           // exposed pairs awaiting their Bernoulli: entry | row << 48 | iso_u << 56
+// where a block's queued agents live: contiguous from `base` (scan push), or in pieces of 128 agents dealt round-robin
+// to the blocks (agent pass: piece q belongs to block q % stride and is that block's slot q / stride)
+struct FrontMap {
+    int64_t base;
+    int stride, blk;
+    __device__ __forceinline__ int64_t at(uint32_t rel) const
+    {
+        return stride ? base + ((int64_t)(rel >> 7) * stride + blk) * 128 + (rel & 127u) : base + rel;
+    }
 };
 
-__device__ __forceinline__ void push_body(const DevCtx& c, const int day)
+struct PushWarpScratch {
+    int off[36];                                   // exclusive prefix of the expanded rows' lengths
+    int64_t t0[32];
+    unsigned long long pairs[PUSH_PCAP];           // pairs awaiting their Bernoulli: entry | row << 48 | flags << 56
+};
+
+enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS, EV_CHANGED, EV_LEN };
+
+struct BlockScratch {
+    uint32_t front[FCAP];
+    union {
+        uint32_t list[LCAP];                       // local index | status << 24 | attention << 28
+        PushWarpScratch pw[WARPS];
+    };
+    double pdf[64];
+    unsigned int n_front, n_list;
+    unsigned int hist[HIST_LEN], ev[EV_LEN], cnt[10], acc[8];
+    bool last;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// push_frontier: the block's queued infectious agents (sm.front[0 .. n_front), halo-relative index = base + rel) push
+// along their transposed rows.  The rows are dealt to the warps in groups of <= 32; a group is flattened (warp prefix
+// sum of the row lengths) so every lane works on consecutive entries however long the rows are; four entries per lane
+// are in flight.  Pairs that pass the static class test are compacted and settled densely (two 8-byte gathers and the
+// Philox rounds once per 32 pairs).
+//   CHECK = true   the status column is final (stand-alone launch, or after a grid barrier): u must be susceptible, and
+//                  the hit goes to the mailbox that matches u's isolation -- the counters equal the reference's
+//                  candidate / exposed / success counts.
+//   CHECK = false  the push runs while other blocks still settle day d: nothing about u is read.  A hit is recorded
+//                  for both isolation cases; the agent pass of u picks the one that applies (and ignores it if u is
+//                  not susceptible).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool CHECK>
+__device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, BlockScratch& sm, const FrontMap fmap,
+                                              unsigned int (&cnt)[4])
 {
-    __shared__ double s_pdf[64];
-    __shared__ unsigned int s_acc[8];
-    __shared__ PushWarpSmem s_w[PUSH_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    PushWarpSmem& w = s_w[wid];
-
-    // scratch that k_agent fills today, and the flags it raises for tomorrow
-    grid_clear(c.sa_hist, c.S_out * HIST_LEN);
-    grid_clear(c.bcount, c.B_out);
-    grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
-    grid_clear16(c.hh_flag_next, c.H);
-    grid_clear16(c.hh_qflag_next, c.H);
-    if (blockIdx.x == 0 && tid < DF_LEN) c.df_next[tid] = 0;
-
-    if (tid < 64) s_pdf[tid] = c.pdf[tid];
-    if (tid < 8) s_acc[tid] = 0;
-    __syncthreads();
+    PushWarpScratch& w = sm.pw[wid];
+    const int n = (int)sm.n_front;
     const bool any_closed = c.n_closed != 0;
-    unsigned int cnt[4] = {0, 0, 0, 0};   // entries scanned, candidates, exposed, hits
+    int rpg = (n + WARPS - 1) / WARPS;
+    rpg = rpg < 1 ? 1 : (rpg > 32 ? 32 : rpg);
+    const int n_groups = (n + rpg - 1) / rpg;
 
-    // settle the first n queued pairs (susceptible u, infectious i) that share a building: probability, Bernoulli, mailbox.
-    // Dense: one pair per lane, so the two 8-byte gathers and the Philox rounds are issued once per 32 pairs.
-    auto settle = [&](const int q0, const int n) {
-        for (int k0 = 0; k0 < n; k0 += 32) {
+    // settle the first np queued pairs of this warp: probability, Bernoulli, mailbox
+    auto settle = [&](const int q0, const int np) {
+        for (int k0 = 0; k0 < np; k0 += 32) {
             const int k = k0 + lane;
-            if (k >= n) continue;
+            if (k >= np) continue;
             const unsigned long long rec = w.pairs[k];
             const int64_t e = (int64_t)(rec & 0xFFFFFFFFFFFFull);
             const int r = (int)((rec >> 48) & 0x3Fu);
-            const bool iso_u = (rec >> 56) & 1u;
-            const uint32_t cw = __ldg(c.tcolx + e), ib_i = w.q_ib[q0 + r];
+            const uint32_t fl = (uint32_t)(rec >> 56);                  // CHECK: bit0 = u is isolated; else bit0 = valid if u isolated
+            const uint32_t fe = sm.front[q0 + r];
+            const uint32_t cw = __ldg(c.tcolx + e), ib_i = fe >> 24;
             const uint32_t ul = cw & COL_MASK;
-            const int64_t ug = c.lo + ul, ig = c.rt_lo + w.q_idx[q0 + r];
-            if (any_closed && !exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, (ib_i & IB_ISO) != 0)) continue;
+            const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe & REL_MASK);
+            const bool iso_i = (ib_i & IB_ISO) != 0;
+            bool ok_free, ok_iso;
+            if (CHECK) {
+                const bool iso_u = fl & 1u;
+                const bool ok = !any_closed || exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
+                ok_free = ok && !iso_u;
+                ok_iso = ok && iso_u;
+            } else {
+                ok_free = !any_closed || exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
+                ok_iso = (fl & 1u) && (!any_closed || exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i));
+            }
+            if (!ok_free && !ok_iso) continue;
             ++cnt[2];
             // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
             // rounded separately (no add follows, so no FMA can form)
             double p = __dmul_rn(__ldg(c.tval + e), __ldg(c.risk + ul));
-            p = __dmul_rn(p, s_pdf[ib_i & IB_DAYS]);
+            p = __dmul_rn(p, sm.pdf[ib_i & IB_DAYS]);
             p = __dmul_rn(p, c.norm_factor);
-            if (c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+            if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
             const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
-            if (p > u) { ++cnt[3]; atomicMax(&c.src[ul], (int)ig); }               // :240, :248
+            if (p > u) {                                                           // :240, :248
+                ++cnt[3];
+                if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
+                if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
+                att_or(c.att, ul, ATT_HIT);
+            }
         }
         __syncwarp();
     };
 
-    // expand nb (<= 32) queued rows starting at queue position q0
-    auto expand = [&](const int q0, const int nb) {
+    for (int g = wid; g < n_groups; g += WARPS) {
+        const int q0 = g * rpg;
+        const int nb = (n - q0) < rpg ? (n - q0) : rpg;
         int64_t t0 = 0;
         int len = 0;
-        if (lane < nb) { const uint32_t il = w.q_idx[q0 + lane]; t0 = __ldg(c.tptr + il); len = (int)(__ldg(c.tptr + il + 1) - t0); }
+        if (lane < nb) {
+            const int64_t il = fmap.at(sm.front[q0 + lane] & REL_MASK);
+            t0 = __ldg(c.tptr + il);
+            len = (int)(__ldg(c.tptr + il + 1) - t0);
+        }
         int incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -145,22 +202,35 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
                 e[k] = w.t0[lo] + (f - w.off[lo]);
                 cw[k] = f < total ? __ldg(c.tcolx + e[k]) : 0u;
             }
+            if (CHECK) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[cw[k] & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
+                for (int k = 0; k < 4; ++k)
+                    st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[cw[k] & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 // cheap part of the exposure test (static class x today's isolation); survivors are queued
-                const bool sus = in_set(M_SUS, st_u[k]);
-                cnt[1] += sus;
-                const uint32_t cls = cw[k] >> CLS_SHIFT;
-                const bool iso_u = (st_u[k] == ST_QH), iso_i = w.q_ib[q0 + r[k]] & IB_ISO;
-                const bool ex = sus && ((cls & CLS_HH) | ((cls & CLS_HO) && !iso_i) | ((cls & CLS_OH) && !iso_u) |
-                                        ((cls & CLS_OO) && !iso_u && !iso_i));
+                const uint32_t cls = cw[k] >> CLS_SHIFT;                // 0 for the padding entries
+                const bool iso_i = (sm.front[q0 + r[k]] >> 24) & IB_ISO;
+                const bool x_iso = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i);                      // u isolated at home
+                const bool x_free = x_iso | ((cls & CLS_OH) != 0) | ((cls & CLS_OO) && !iso_i);      // u moves freely
+                bool ex;
+                uint32_t fl;
+                if (CHECK) {
+                    const bool sus = in_set(M_SUS, st_u[k]);
+                    const bool iso_u = (st_u[k] == ST_QH);
+                    cnt[1] += sus;
+                    ex = sus && (iso_u ? x_iso : x_free);
+                    fl = iso_u;
+                } else {
+                    ex = x_free;
+                    cnt[1] += ex;
+                    fl = x_iso;
+                }
                 const unsigned m = __ballot_sync(0xffffffffu, ex);
                 if (ex) {
                     w.pairs[np + __popc(m & lt_mask)] = (unsigned long long)e[k] | ((unsigned long long)r[k] << 48) |
-                                                        ((unsigned long long)iso_u << 56);
+                                                        ((unsigned long long)fl << 56);
                     prefetch_l2(c.tval + e[k]);                 // both are read when the pair is settled
                     prefetch_l2(c.risk + (cw[k] & COL_MASK));
                 }
@@ -171,55 +241,105 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
         }
         if (np > 0) settle(q0, np);
         __syncwarp();
-    };
+    }
+}
 
-    const int64_t n_chunks = (c.rt_n + PUSH_CHUNK - 1) / PUSH_CHUNK;
-    const int64_t stride = (int64_t)gridDim.x * PUSH_WARPS;
-    int nq = 0;                                            // queued rows (warp-uniform)
-    const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib_rd + c.rt_lo);  // rt_lo is a multiple of 1024
-    // scan the snapshot bytes of halo agents [ch0, ch1) * 128, queueing the infectious ones
-    auto scan = [&](const int64_t ch0, const int64_t ch1) {
-        int64_t ch = ch0 + (int64_t)blockIdx.x * PUSH_WARPS + wid;
+// what a push of day X clears before the agent pass of day X fills it / raises into it (grid-strided, any block)
+__device__ __forceinline__ void push_clear_duties(const DevCtx& c)
+{
+    grid_clear(c.sa_hist, c.S_out * HIST_LEN);
+    grid_clear(c.bcount, c.B_out);
+    grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
+    if (c.trig_ptr) grid_clear16(c.qflag_next, c.H);
+    if (blockIdx.x == 0 && threadIdx.x < DF_LEN) c.df_next[threadIdx.x] = 0;
+}
+
+__device__ __forceinline__ void publish_push_counters(const DevCtx& c, BlockScratch& sm, const unsigned int (&cnt)[4])
+{
+    const int idx[4] = {ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED, ST_HITS};
+    if (threadIdx.x < 8) sm.acc[threadIdx.x] = 0;
+    __syncthreads();
+    block_accumulate<4>(c.part, idx, cnt, sm.acc);
+}
+
+// the block's contiguous share [lo, hi) of n items, in granules of 16
+__device__ __forceinline__ void block_share(const int64_t n, const int n_blocks, int64_t& lo, int64_t& hi)
+{
+    int64_t span = (n + n_blocks - 1) / n_blocks;
+    span = (span + 15) & ~(int64_t)15;
+    lo = (int64_t)blockIdx.x * span;
+    hi = lo + span;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// push_scan_body: the push of `day` with the frontier found by scanning the snapshot bytes (c.ib_rd) of the halo
+// agents.  Every block scans a contiguous share, 1024 bytes a step (the next step's word already in flight).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    push_clear_duties(c);
+    if (tid < 64) sm.pdf[tid] = c.pdf[tid];
+    if (tid == 0) sm.n_front = 0;
+    __syncthreads();
+    unsigned int cnt[4] = {0, 0, 0, 0};   // entries scanned, candidates, Bernoulli draws, successes
+
+    // halo-relative agents [r0, r1): r0 is a multiple of 1024
+    auto scan = [&](const int64_t r0, const int64_t r1) {
+        int64_t lo, hi;
+        block_share(r1 - r0, n_blocks, lo, hi);
+        lo += r0; hi += r0;
+        int64_t base = lo;
+        const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib_rd + c.rt_lo);   // rt_lo is a multiple of 1024
         uint32_t v = 0;
-        if (ch < ch1) v = ib4[ch * (PUSH_CHUNK / 4) + lane];
-        for (; ch < ch1; ch += stride) {
+        if (lo + tid * 4 < hi) v = ib4[(lo >> 2) + tid];
+        for (int64_t s0 = lo; s0 < hi; s0 += BLOCK * 4) {
             uint32_t vn = 0;
-            if (ch + stride < ch1) vn = ib4[(ch + stride) * (PUSH_CHUNK / 4) + lane];   // next step's bytes, in flight
-            const int mine = __popc(v & 0x80808080u);
-            if (__ballot_sync(0xffffffffu, mine != 0)) {
+            if (s0 + BLOCK * 4 + tid * 4 < hi) vn = ib4[((s0 + BLOCK * 4) >> 2) + tid];   // next step's bytes, in flight
+            const int64_t il0 = s0 + tid * 4;
+            uint32_t vm = v & 0x80808080u;                          // bytes past the end of the share are not ours
+            if (il0 + 4 > hi) vm &= il0 >= hi ? 0u : (0xFFFFFFFFu >> (8 * (int)(il0 + 4 - hi)));
+            const int mine = __popc(vm);
+            const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+            if (any) {
                 int incl = mine;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int t = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += t;
                 }
-                int pos = nq + incl - mine;
-                const uint32_t il0 = (uint32_t)(ch * PUSH_CHUNK + lane * 4);
-                if (mine) {
+                int pos = 0;
+                if (lane == 31) pos = (int)atomicAdd(&sm.n_front, (unsigned)incl);
+                pos = __shfl_sync(0xffffffffu, pos, 31) + incl - mine;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const uint32_t byte = (v >> (8 * b)) & 0xFFu;
-                        if ((byte & IB_INF) && il0 + b < (uint32_t)c.rt_n) {
-                            w.q_idx[pos] = il0 + b; w.q_ib[pos] = (uint8_t)byte; ++pos;
-                            prefetch_l2(c.tptr + il0 + b);      // the row extent is needed when the queue is expanded
-                        }
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t byte = (v >> (8 * b)) & 0xFFu;
+                    if ((vm >> (8 * b)) & 0x80u) {
+                        sm.front[pos++] = (uint32_t)(il0 + b - base) | (byte << 24);
+                        prefetch_l2(c.tptr + il0 + b);          // the row extent is needed when the frontier is pushed
                     }
-                }
-                nq += __shfl_sync(0xffffffffu, incl, 31);
-                __syncwarp();
-                while (nq >= 32) {     // expand from the back of the queue: nothing has to move
-                    nq -= 32;
-                    expand(nq, 32);
                 }
             }
             v = vn;
+            __syncthreads();
+            const int64_t s1 = s0 + BLOCK * 4;
+            const unsigned nf = sm.n_front;        // read by everyone before the next step appends (barrier below)
+            if (nf > FCAP - BLOCK * 4 || s1 - base > (int64_t)REL_MASK - BLOCK * 4 || s1 >= hi) {
+                if (nf) push_frontier<true>(c, day, sm, FrontMap{base, 0, 0}, cnt);
+                __syncthreads();
+                if (tid == 0) sm.n_front = 0;
+                base = s1;
+            }
+            __syncthreads();
         }
     };
     if (c.n_peers > 1) {
         // peer mode: the owned agents' bytes are local and final, so their rows are pushed first; the halo agents'
         // bytes were stored into this GPU's buffer by their owners, who then raised flag[r] = day -- the exchange
         // latency hides behind the local part of the push.  (Persistent grid: all CTAs resident, spinning is safe.)
-        const int64_t own0 = (c.lo - c.rt_lo) / PUSH_CHUNK, own1 = (c.lo - c.rt_lo + c.n_loc + PUSH_CHUNK - 1) / PUSH_CHUNK;
+        const int64_t own0 = c.lo - c.rt_lo, own1 = own0 + c.n_pad < c.rt_n ? own0 + c.n_pad : c.rt_n;
         scan(own0, own1);
         if (tid < c.n_peers && ((c.wait_mask >> tid) & 1u)) {      // only the ranks whose agents are in this rank's halo
             const volatile int32_t* f = c.flag_wait + tid;
@@ -227,81 +347,86 @@ __device__ __forceinline__ void push_body(const DevCtx& c, const int day)
             __threadfence_system();
         }
         __syncthreads();
-        scan(0, own0);
-        scan(own1, n_chunks);
+        if (own0 > 0) scan(0, own0);
+        if (own1 < c.rt_n) scan(own1, c.rt_n);
     } else {
-        scan(0, n_chunks);
+        scan(0, c.rt_n);
     }
-    if (nq > 0) expand(0, nq);
-    const int idx[4] = {ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED, ST_HITS};
-    __syncthreads();
-    block_accumulate<4>(c, idx, cnt, s_acc);
+    publish_push_counters(c, sm, cnt);
 }
 
-__global__ void __launch_bounds__(PUSH_WARPS * 32) k_push(const DevCtx c, const int day) { push_body(c, day); }
+__global__ void __launch_bounds__(BLOCK) k_push(const DevCtx c, const int day)
+{
+    __shared__ BlockScratch sm;
+    push_scan_body(c, day, sm, (int)gridDim.x);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_agent.  A block owns 1024 consecutive agents, in two phases.
-//   sweep  : 4 agents per thread, vector loads of the status word, the infector mailbox and (on days with a
-//            diagnosis) the household flags.  An agent to whom nothing can happen today -- susceptible, nobody infected
-//            it, household not flagged; or recovered -- only feeds the packed status histogram.  Every other agent's
-//            local index is compacted (ballot + prefix popcount) into a shared-memory work list.
+// agent_body.  A block owns a contiguous share of the agents and walks it in batches of 2048, in two phases.
+//   sweep  : 4 agents per thread and round: one 32-bit load of the status bytes, one of the attention bytes.  An agent
+//            to whom nothing can happen today -- susceptible or long recovered, attention byte 0 -- only feeds the
+//            packed status histogram.  Every other agent is compacted (ballot + prefix popcount) into the work list.
 //   settle : the work list is processed densely, one agent per thread: B, C, applying D, the ordered rules of E, F, G,
-//            tomorrow's snapshot byte and household flags.  Divergent per-agent logic therefore costs instructions in
-//            proportion to the agents that need it, not to the population.
-// Compartment counts are reduced as packed 8-bit histograms (REDUX); rare events go to shared-memory counters; the last
-// block folds the spread partial sums into the day's stats block.
+//            tomorrow's snapshot byte and household flags; agents that are infectious tomorrow join the block's frontier.
+// Divergent per-agent logic therefore costs instructions in proportion to the agents that need it, not to the
+// population.  Compartment counts are reduced as packed 8-bit histograms (REDUX); rare events go to shared-memory
+// counters; one block folds the spread partial sums into the day's stats block.
 // ---------------------------------------------------------------------------------------------------------------
-// packed 8-bit histogram field of a status code: QI S I QH | D H R X   (4 agents x 32 lanes = 128 < 256 per field)
+// packed 8-bit histogram field of a status code: QI S I QH | D H R X
 __device__ __forceinline__ uint32_t hist_idx(uint32_t st) { return (st == ST_QI) ? 0u : (st >> 1); }
-constexpr uint32_t M_F = M_SUS | sbit(ST_I) | sbit(ST_QI);      // can be in status 1 or 2 when F runs
-enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS, EV_CHANGED, EV_LEN };
-// internal partial-sum rows (folded into the public stats by the last block)
+// internal partial-sum rows (folded into the public stats by fold_stats)
 constexpr int RAW_END = 53;      // [53..60] end-of-day status counts in hist_idx order
 constexpr int RAW_SUS0 = 61, RAW_INF0 = 62;
 constexpr int ST_COUNT0 = 20;    // public: stats[20..27] = end-of-day agents in S, I, QH, QI, D, H, R, X
-constexpr int AGENT_TILE = 1024;
 
-// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
-__device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
-                                             const uint32_t st, const int mailbox, unsigned int* s_cnt, unsigned int* s_ev,
-                                             unsigned int* s_hist, bool& infected_today, int& infector)
+// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366);
+// returns tomorrow's snapshot byte
+__device__ __forceinline__ uint8_t settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
+                                                const uint32_t st, const uint32_t att, BlockScratch& sm,
+                                                bool& infected_today, int& infector)
 {
-    // every column this agent can need is requested before any of it is used: the per-agent latency is two dependent
-    // round trips (columns, then the household flags) instead of one per rule
+    // every column this agent can need is requested before any of it is used
     int ti = c.t_inf[a];
     int tq = c.t_q[a];
-    const int h = any_nd ? __ldg(c.hh + a) : 0;
+    const bool quirk = any_nd && (c.trig_ptr || c.hh_always);
+    const int h = quirk ? __ldg(c.hh + a) : 0;
     const int sa_a = c.sa_hist ? __ldg(c.sa + a) : -1;
     const int home_a = c.bcount ? __ldg(c.home + a) : 0;
-    bool f_hh = false, f_q = false;
-    if (any_nd) {
-        f_hh = __ldg(c.hh_flag + h) != 0;
-        f_q = (__ldg(c.hh_qflag + h) != 0) || (c.hh_always && __ldg(c.hh_always + h));
+    int mb = -1;
+    if (att & ATT_HIT) {
+        // the mailbox that matches this agent's isolation; both are reset for the day after tomorrow
+        const int m_free = c.mb_any[a], m_iso = c.mb_iso[a];
+        mb = (st == ST_QH) ? m_iso : m_free;
+        c.mb_any[a] = -1;
+        c.mb_iso[a] = -1;
     }
+    const bool f_hh = (att & ATT_HH) != 0;                                                  // :263
+    bool f_q = false;
+    if (quirk) f_q = (c.trig_ptr && c.qflag[h] != 0) || (c.hh_always && __ldg(c.hh_always + h));   // qflag is written during k_days: no __ldg
     uint32_t x = st;
     if (!in_set(M_EVER, st)) ti = 0;
     bool w_ti = false, w_tq = false;
     infected_today = false;
     // ---- B, C (contagious3.py:205-227) on the day-start status; D's result from the mailbox ----
     if (in_set(M_INF, st)) {
-        atomicAdd(&s_cnt[9], 1u);
+        atomicAdd(&sm.cnt[9], 1u);
         if (ti >= c.adm_min && ti <= c.adm_max) {                            // :205 window on the ABSOLUTE infection day
             const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
-            if (__ldg(c.p_adm + a) > u) { x = ST_H; c.t_adm[a] = (int16_t)day; atomicAdd(&s_ev[EV_ADM], 1u); }   // :213-216
+            if (__ldg(c.p_adm + a) > u) { x = ST_H; c.t_adm[a] = (int16_t)day; atomicAdd(&sm.ev[EV_ADM], 1u); }   // :213-216
         }
     } else if (st == ST_H) {
         if (c.t_adm[a] >= c.death_min) {                                     // :219
             const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
-            if (__ldg(c.p_death + a) > u) { x = ST_X; c.t_adm[a] = 0; atomicAdd(&s_ev[EV_DEATH], 1u); }          // :225-227, :259
+            if (__ldg(c.p_death + a) > u) { x = ST_X; c.t_adm[a] = 0; atomicAdd(&sm.ev[EV_DEATH], 1u); }          // :225-227, :259
         }
     } else if (in_set(M_SUS, st)) {
-        atomicAdd(&s_cnt[8], 1u);
-        infector = mailbox;
-        if (infector >= 0) {                                                 // :241-248: k_push found an infector
+        atomicAdd(&sm.cnt[8], 1u);
+        infector = mb;
+        if (infector >= 0) {                                                 // :241-248: the push found an infector
             x = (st == ST_S) ? ST_I : ST_QI;
             ti = day; w_ti = true;
             infected_today = true;
+            c.src[a] = infector;
         }
     }
     // ---- E: the ordered rules of contagious3.py:250-259 ----
@@ -312,7 +437,7 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
     if ((x == ST_I || x == ST_QI) && n_inf == c.diagnosis) x = ST_D;                        // :254
     if (x == ST_D && n_inf == c.recover) x = ST_R;                                          // :255
     if (x == ST_H && n_inf == c.hospital_recover) { x = ST_R; c.t_adm[a] = 0; }             // :256, :259
-    if (x == ST_D && n_inf == c.diagnosis) atomicAdd(&s_ev[EV_NEW_DIAG], 1u);               // :261
+    if (x == ST_D && n_inf == c.diagnosis) atomicAdd(&sm.ev[EV_NEW_DIAG], 1u);              // :261
     // ---- F (contagious3.py:261-270): the households diagnosed today were flagged yesterday ----
     if (any_nd && (x == ST_S || x == ST_I)) {
         bool hit = f_hh;                                                                    // :263
@@ -323,15 +448,15 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
     }
     if (w_ti) c.t_inf[a] = (int16_t)ti;
     if (w_tq) c.t_q[a] = (int16_t)tq;
-    if (x != st) { c.status[a] = (uint8_t)x; atomicAdd(&s_ev[EV_CHANGED], 1u); }
-    if (in_set(M_ISO, x) && tq == day) atomicAdd(&s_ev[EV_DAILY_QUAR], 1u);
+    if (x != st) { c.status[a] = (uint8_t)x; atomicAdd(&sm.ev[EV_CHANGED], 1u); }
+    if (in_set(M_ISO, x) && tq == day) atomicAdd(&sm.ev[EV_DAILY_QUAR], 1u);
     // ---- G: this agent's share of the integer statistics (contagious3.py:273-366) ----
-    atomicAdd(&s_cnt[hist_idx(x)], 1u);
+    atomicAdd(&sm.cnt[hist_idx(x)], 1u);
     if (in_set(M_EVER, x)) {
         const int k = day - ti;
         if (k >= 0 && k < HIST_LEN) {
-            if (k == 0) atomicAdd(&s_ev[EV_DAILY_INF], 1u);
-            atomicAdd(&s_hist[k], 1u);
+            if (k == 0) atomicAdd(&sm.ev[EV_DAILY_INF], 1u);
+            atomicAdd(&sm.hist[k], 1u);
             if (c.sa_hist && sa_a >= 0) atomicAdd(&c.sa_hist[(size_t)sa_a * HIST_LEN + k], 1);
             if (c.io_mat && infected_today) {
                 // contagious3.py:356-366: row = area of today's infected, column = area of the infector
@@ -344,11 +469,12 @@ __device__ __forceinline__ void settle_agent(const DevCtx& c, const int day, con
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
     c.ib_wr[0][c.lo + a] = ibn;
-    if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.hh_flag_next, c.hh_qflag_next, c.df_next);
+    if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.att_next, c.qflag_next, c.df_next);
+    return ibn;
 }
 
 // One block folds the spread partial sums (part[counter][slot]: one warp per counter, two coalesced loads, shuffle tree),
-// derives the compartment statistics from the status counts and re-zeroes the partials for the next day.
+// derives the compartment statistics from the status counts and re-zeroes the partials (this day's ring entry).
 __device__ __forceinline__ void fold_stats(const DevCtx& c)
 {
     __shared__ long long s_fold[N_STATS];
@@ -394,162 +520,214 @@ __device__ __forceinline__ void fold_stats(const DevCtx& c)
         if (tid >= RAW_END) v = 0;
         c.stats[tid] = v;
     }
+    __syncthreads();
 }
 
-template <int VARIANT>   // 0 = k_agent (last block folds); 3 = k_days (block 0 folds after the grid barrier);
-                         // 1, 2 = tools/kbench.cu ablations (no fold / no reduction at all)
-__device__ __forceinline__ void agent_body(const DevCtx& c, const int day)
+// VARIANT 0 = k_agent (the last block to finish folds the statistics); 3 = k_days (one block folds after the grid
+// barrier); 1, 2 = tools/kbench.cu ablations (no fold / no reduction at all).
+// cn = tomorrow's view: the block pushes the rows of its own newly infectious agents (null: no push, e.g. k_agent).
+template <int VARIANT>
+__device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn,
+                                           unsigned int (&push_cnt)[4], const int n_blocks, unsigned long long* tr = nullptr)
 {
-    __shared__ unsigned int s_hist[HIST_LEN];
-    __shared__ unsigned int s_ev[EV_LEN];
-    __shared__ unsigned int s_cnt[10];            // 8 end-of-day status counts (hist_idx order), sus0, inf0
-    __shared__ unsigned int s_nlist;
-    __shared__ unsigned short s_list[AGENT_TILE];
-    __shared__ uint32_t s_stw[AGENT_TILE / 4];      // the tile's status words, for the settle phase
-    __shared__ __align__(16) int s_src[AGENT_TILE]; // the tile's mailbox (infector) column (written 16 bytes at a time)
-    __shared__ bool s_last;
+    auto stamp = [&](int i) {        // developer tracing: globaltimer at phase boundaries
+        if (tr && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tr[i] = t;
+        }
+    };
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    if (tid < HIST_LEN) s_hist[tid] = 0;
-    if (tid < EV_LEN) s_ev[tid] = 0;
-    if (tid < 10) s_cnt[tid] = 0;
+    if (tid < HIST_LEN) sm.hist[tid] = 0;
+    if (tid < EV_LEN) sm.ev[tid] = 0;
+    if (tid < 10) sm.cnt[tid] = 0;
+    if (tid == 0) { sm.n_list = 0; sm.n_front = 0; }
+    if (cn && tid < 64) sm.pdf[tid] = c.pdf[tid];
     __syncthreads();
     const bool any_nd = c.df[DF_ANY_ND] != 0;
     const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN;   // a recovered agent left the histogram
-    // one tile per block when launched as k_agent (grid = tiles); a persistent grid (k_days) strides over the tiles
-    for (int64_t tile = blockIdx.x; tile * AGENT_TILE < c.n_pad; tile += gridDim.x) {
-    const int64_t tile0 = tile * AGENT_TILE;
-    const int64_t a0 = tile0 + tid * 4;
-    if (tid == 0) s_nlist = 0;
-    __syncthreads();
+    // Pieces of 128 agents (one 4-byte word per lane) are dealt round-robin to the blocks: piece q is slot q / n_blocks
+    // of block q % n_blocks.  A block's share is thus spread over the whole population, which evens out the load when
+    // the epidemic is concentrated in some communities.  Warp w handles slot s0 + w (+ 8) of a batch of 16 slots.
+    const int wid = tid >> 5;
+    const int64_t n_pieces = c.n_pad >> 7;
+    const int64_t n_slots = (int)blockIdx.x < n_blocks ? (n_pieces - blockIdx.x + n_blocks - 1) / n_blocks : 0;
+    const FrontMap fmap{c.lo - c.rt_lo, n_blocks, (int)blockIdx.x};
+    auto agent_of = [&](uint32_t rel) { return ((int64_t)(rel >> 7) * n_blocks + blockIdx.x) * 128 + (rel & 127u); };
+    uint32_t n_idle_s = 0, n_idle_r = 0;
+    constexpr int SLOTS = LCAP / 128;             // slots per batch
 
-    // ---- sweep ----
-    {
-        // all three columns are requested at once (the mailbox and household index of a susceptible agent are needed
-        // on almost every day of an epidemic), then the household flags
-        const uint32_t sw = *reinterpret_cast<const uint32_t*>(c.status + a0);
-        const int4 src4 = *reinterpret_cast<const int4*>(c.src + a0);        // the mailbox k_push wrote into
-        int4 hh4 = make_int4(0, 0, 0, 0);
-        if (any_nd) hh4 = __ldg(reinterpret_cast<const int4*>(c.hh + a0));
-        const uint32_t st0[4] = {sw & 0xFFu, (sw >> 8) & 0xFFu, (sw >> 16) & 0xFFu, sw >> 24};
-        s_stw[tid] = sw;
-        *reinterpret_cast<int4*>(&s_src[tid * 4]) = src4;
-        uint32_t m_f = 0;
+    // first batch's words
+    uint32_t sw[2], aw[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m_f |= (uint32_t)(st0[j] == ST_S) << j;
-        const int srcv[4] = {src4.x, src4.y, src4.z, src4.w};
-        uint32_t flagged = 0;                      // susceptible agents whose household sees a diagnosis today
-        if (any_nd && m_f) {
-            const int hv[4] = {hh4.x, hh4.y, hh4.z, hh4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if ((m_f >> j) & 1u) flagged |= (uint32_t)(__ldg(c.hh_flag + hv[j]) != 0) << j;
-        }
-        uint32_t work = 0, n_idle_s = 0, n_idle_r = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t st = st0[j];
-            const bool idle_s = (st == ST_S) && srcv[j] < 0 && !((flagged >> j) & 1u);
-            const bool idle_r = (st == ST_R) && r_idle;
-            n_idle_s += idle_s;
-            n_idle_r += idle_r;
-            work |= (uint32_t)(!idle_s && !idle_r && st != ST_PAD) << j;
-        }
-        // idle agents: end-of-day status == day-start status; their snapshot byte is 0
-        if (VARIANT != 2) {
-            const uint32_t packed = n_idle_s | (n_idle_r << 8);
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, packed);
-            if (lane == 0 && tot) {
-                if (tot & 0xFFu) { atomicAdd(&s_cnt[1], tot & 0xFFu); atomicAdd(&s_cnt[8], tot & 0xFFu); }
-                if (tot >> 8) atomicAdd(&s_cnt[6], tot >> 8);
-            }
-        }
-        // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
-        *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
-        // compact the agents that need the settle phase
-        const int mine = __popc(work);
-        const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
-        if (any) {
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int base = 0;
-            if (lane == 31) base = (int)atomicAdd(&s_nlist, (unsigned)incl);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if ((work >> j) & 1u) s_list[base++] = (unsigned short)(tid * 4 + j);
+    for (int r = 0; r < 2; ++r) {
+        const int64_t sl = r * WARPS + wid;
+        sw[r] = aw[r] = 0;
+        if (sl < n_slots) {
+            const int64_t a0 = agent_of((uint32_t)(sl << 7) | (lane * 4));
+            sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
+            aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
         }
     }
-    __syncthreads();
-
-    // ---- settle ----
-    const int n_list = (int)s_nlist;
-    for (int k0 = 0; k0 < n_list; k0 += 256) {
-        const int k = k0 + tid;
-        const bool valid = k < n_list;
-        bool infected_today = false;
-        int infector = -1;
-        int64_t a = 0;
-        if (valid) {
-            const int li = s_list[k];
-            a = tile0 + li;
-            settle_agent(c, day, a, any_nd, (s_stw[li >> 2] >> (8 * (li & 3))) & 0xFFu, s_src[li], s_cnt, s_ev, s_hist,
-                         infected_today, infector);
-        }
-        // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
-        const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
-        if (evm) {
-            if (lane == 0) atomicAdd(&s_ev[EV_EVENTS], (unsigned)__popc(evm));
-            if (c.ev) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (infected_today) c.ev[base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+    for (int64_t s0 = 0; s0 < n_slots; s0 += SLOTS) {
+        // ---- sweep ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t sl = s0 + r * WARPS + wid;
+            const bool in = sl < n_slots;
+            const uint32_t rel0 = (uint32_t)(sl << 7) | (lane * 4);
+            const int64_t a0 = agent_of(rel0);
+            uint32_t work = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t st = (sw[r] >> (8 * j)) & 0xFFu, at = (aw[r] >> (8 * j)) & 0xFFu;
+                const bool idle_s = (st == ST_S) && at == 0;
+                const bool idle_r = (st == ST_R) && r_idle && at == 0;
+                n_idle_s += idle_s;
+                n_idle_r += idle_r;
+                work |= (uint32_t)(!idle_s && !idle_r && st != ST_PAD) << j;
+            }
+            if (in) {
+                if (aw[r]) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
+                // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
+                *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
+            }
+            const int mine = __popc(work);
+            const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+            if (any) {
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int pos = 0;
+                if (lane == 31) pos = (int)atomicAdd(&sm.n_list, (unsigned)incl);
+                pos = __shfl_sync(0xffffffffu, pos, 31) + incl - mine;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((work >> j) & 1u)
+                        sm.list[pos++] = (rel0 + j) | (((sw[r] >> (8 * j)) & 0xFu) << 24) | (((aw[r] >> (8 * j)) & 0x3u) << 28);
             }
         }
-    }
-    __syncthreads();      // s_list / s_nlist are free for the next tile
+        // the next batch's words are requested before this batch is settled
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t sl = s0 + SLOTS + r * WARPS + wid;
+            sw[r] = aw[r] = 0;
+            if (sl < n_slots) {
+                const int64_t a0 = agent_of((uint32_t)(sl << 7) | (lane * 4));
+                sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
+                aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
+            }
+        }
+        __syncthreads();
+        stamp(5);
+
+        // ---- settle ----
+        const int n_list = (int)sm.n_list;
+        for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
+            const int k = k0 + tid;
+            bool infected_today = false;
+            int infector = -1;
+            int64_t a = 0;
+            uint32_t ibn = 0, rel = 0;
+            if (k < n_list) {
+                const uint32_t le = sm.list[k];
+                rel = le & REL_MASK;
+                a = agent_of(rel);
+                ibn = settle_agent(c, day, a, any_nd, (le >> 24) & 0xFu, (le >> 28) & 0x3u, sm, infected_today, infector);
+            }
+            // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
+            const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
+            if (evm) {
+                if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
+                if (c.ev) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (infected_today) c.ev[base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+                }
+            }
+            if (cn) {
+                // infectious tomorrow: queue the agent's row for the block's push of day + 1
+                const bool f = (ibn & IB_INF) != 0;
+                const unsigned fm = __ballot_sync(0xffffffffu, f);
+                if (fm) {
+                    int base = 0;
+                    if (lane == 0) base = (int)atomicAdd(&sm.n_front, (unsigned)__popc(fm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (f) {
+                        sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
+                        prefetch_l2(cn->tptr + fmap.base + a);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // the work list is free; the frontier count is final for this batch
+        stamp(6);
+        if (tid == 0) sm.n_list = 0;
+        if (cn && sm.n_front && (sm.n_front > FCAP - LCAP || s0 + SLOTS >= n_slots)) {
+            push_frontier<false>(*cn, day + 1, sm, fmap, push_cnt);      // (the work list's memory is the push scratch)
+            __syncthreads();
+            if (tid == 0) sm.n_front = 0;
+        }
+        __syncthreads();
     }
     if (VARIANT == 2) return;
+    {
+        // idle agents: end-of-day status == day-start status
+        const uint32_t tot_s = __reduce_add_sync(0xffffffffu, n_idle_s), tot_r = __reduce_add_sync(0xffffffffu, n_idle_r);
+        if (lane == 0) {
+            if (tot_s) { atomicAdd(&sm.cnt[1], tot_s); atomicAdd(&sm.cnt[8], tot_s); }
+            if (tot_r) atomicAdd(&sm.cnt[6], tot_r);
+        }
+    }
     __syncthreads();
     if (tid < 32) {
         // warp 0 publishes everything, fences, and takes the ticket
         const int slot = blockIdx.x & (N_SLOTS - 1);
-        if (lane < 10 && s_cnt[lane])
-            atomicAdd(&c.part[(size_t)(RAW_END + lane) * N_SLOTS + slot], (unsigned long long)s_cnt[lane]);
-        if (lane < EV_LEN && s_ev[lane]) {
+        stamp(7);
+        if (lane < 10 && sm.cnt[lane])
+            atomicAdd(&c.part[(size_t)(RAW_END + lane) * N_SLOTS + slot], (unsigned long long)sm.cnt[lane]);
+        if (lane < EV_LEN && sm.ev[lane]) {
             const int row = lane == EV_ADM ? ST_DAILY_HOSP : lane == EV_DEATH ? ST_DAILY_DEATHS : lane == EV_DAILY_INF ? ST_DAILY_INF
                           : lane == EV_DAILY_QUAR ? ST_DAILY_QUAR : lane == EV_NEW_DIAG ? ST_NEW_DIAG : lane == EV_EVENTS ? ST_N_EVENTS
                           : ST_CHANGED;
-            atomicAdd(&c.part[(size_t)row * N_SLOTS + slot], (unsigned long long)s_ev[lane]);
+            atomicAdd(&c.part[(size_t)row * N_SLOTS + slot], (unsigned long long)sm.ev[lane]);
         }
-        if (lane < HIST_LEN && s_hist[lane])
-            atomicAdd(&c.part[(size_t)(HIST0 + lane) * N_SLOTS + slot], (unsigned long long)s_hist[lane]);
+        if (lane < HIST_LEN && sm.hist[lane])
+            atomicAdd(&c.part[(size_t)(HIST0 + lane) * N_SLOTS + slot], (unsigned long long)sm.hist[lane]);
         if (VARIANT == 0) {
             __threadfence();
             __syncwarp();
-            if (lane == 0) s_last = (atomicAdd(c.ticket, 1u) == gridDim.x - 1);      // one ticket per block, after all its tiles
+            if (lane == 0) sm.last = (atomicAdd(c.ticket, 1u) == gridDim.x - 1);      // one ticket per block
         }
     }
     if (VARIANT != 0) return;
     __syncthreads();
-    if (s_last) {
+    if (sm.last) {
         fold_stats(c);      // the last block to finish
         if (tid == 0) *c.ticket = 0u;
     }
 }
 
-__global__ void __launch_bounds__(256) k_agent(const DevCtx c, const int day) { agent_body<0>(c, day); }
+__global__ void __launch_bounds__(BLOCK) k_agent(const DevCtx c, const int day)
+{
+    __shared__ BlockScratch sm;
+    unsigned int none[4] = {0, 0, 0, 0};
+    agent_body<0>(c, day, sm, nullptr, none, (int)gridDim.x);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_days: several consecutive days in ONE cooperative launch (persistent grid, all CTAs resident).  Per day: push_body,
-// grid barrier, agent_body, grid barrier -- the same device code as k_push / k_agent, minus two launches a day.  At a
-// million agents a day is ~20 MB of traffic, i.e. launch latency is the larger part of a day done as separate kernels.
-// The per-day buffers (output block, household flags, flag block, snapshot parity, open flags) come from DayPlan.
+// k_days: several consecutive days in ONE cooperative launch (persistent grid, all CTAs resident).
+//   single GPU :  scan push of the first day, barrier; then per day  [agent(d) ; push(d+1) of the block's own
+//                 frontier], ONE barrier.  (The last day of the window does not push: tomorrow's open flags arrive
+//                 with the next call.)
+//   peer mode  :  per day  scan push (own rows, wait for the peers' flags, halo rows), barrier, agent, barrier,
+//                 publish the halo part of tomorrow's snapshot bytes to the peers and raise the flag.
+// The per-day buffers come from DayPlan; each block keeps today's and tomorrow's view of the context in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 // peer mode: the owned slice of freshly written snapshot bytes (ib_wr[0]) is stored into the same place of every peer
 // GPU's buffer (ib_wr[1..]) with coalesced 16-byte P2P stores over NVLink; the flag is raised afterwards (k_signal, or
@@ -566,7 +744,7 @@ __device__ __forceinline__ void publish_body(const DevCtx& c)
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(256) k_publish(const DevCtx c) { publish_body(c); }
+__global__ void __launch_bounds__(BLOCK) k_publish(const DevCtx c) { publish_body(c); }
 
 constexpr int MAX_FUSED_DAYS = 14;
 constexpr int PUBLISH_BLOCKS = 8;          // the halo part of a slice is small (one community per neighbour)
@@ -576,15 +754,22 @@ struct DayPlan {
     const uint8_t* open[MAX_FUSED_DAYS];
     unsigned char* out[MAX_FUSED_DAYS];             // the day's output block
     size_t off_sa, off_bc, off_ev;                  // 0 = that part was not requested
-    uint8_t* hh_flag[2];
-    uint8_t* hh_qflag[2];
-    int32_t* df[2];
-    uint8_t* ib[2];                                 // own snapshot buffers by day parity
-    uint8_t* peer_ib[8][2];                         // peer mode: every other rank's, by day parity
-    int32_t first_parity;                           // step parity of first_day (household flags, flag block)
+    DayBuffers buf;
     int32_t want_sa, want_bc, want_ev;
-    unsigned long long* trace;                      // developer tracing (tools/kbench.cu): globaltimer at phase boundaries, or null
+    unsigned long long* trace;                      // developer tracing: [n_days][grid][8] globaltimer at phase boundaries, or null
 };
+
+__device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const DayPlan& plan, const int k)
+{
+    c = c0;
+    bind_day(c, plan.buf, plan.first_day + k);
+    c.open = plan.open[k];
+    c.n_closed = plan.n_closed[k];
+    c.stats = reinterpret_cast<int64_t*>(plan.out[k]);
+    c.sa_hist = plan.want_sa ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_sa) : nullptr;
+    c.bcount = plan.want_bc ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_bc) : nullptr;
+    c.ev = plan.want_ev ? reinterpret_cast<int2*>(plan.out[k] + plan.off_ev) : nullptr;
+}
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
 {
@@ -601,56 +786,55 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan plan, unsigned int* barrier_counter)
+__global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPlan plan, unsigned int* barrier_counter)
 {
-    __shared__ DevCtx s_c;               // the day's view of the context: read by both bodies like kernel parameters
+    __shared__ BlockScratch sm;
+    __shared__ DevCtx s_c[2];            // today's and tomorrow's view of the context (read like kernel parameters)
+    __shared__ bool s_pub_last;
     unsigned int epoch = 0;
+    const bool peers = c0.n_peers > 1;
+    // io_mat is one buffer for the latest day: the push of day + 1 must not clear it under the agent pass of day
+    const bool two_phase = peers || c0.io_mat != nullptr;
+    // the last block owns no agents: it folds each day's statistics after the barrier while the others are already in
+    // the next day, and is never the one they wait for
+    const int n_work = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
+    if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0);
+    __syncthreads();
     for (int k = 0; k < plan.n_days; ++k) {
         const int day = plan.first_day + k;
-        if (threadIdx.x == 0) {
-            DevCtx& c = s_c;
-            c = c0;
-            const int par = (plan.first_parity + k) & 1;
-            c.open = plan.open[k];
-            c.n_closed = plan.n_closed[k];
-            c.stats = reinterpret_cast<int64_t*>(plan.out[k]);
-            c.sa_hist = plan.want_sa ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_sa) : nullptr;
-            c.bcount = plan.want_bc ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_bc) : nullptr;
-            c.ev = plan.want_ev ? reinterpret_cast<int2*>(plan.out[k] + plan.off_ev) : nullptr;
-            c.hh_flag = plan.hh_flag[par]; c.hh_qflag = plan.hh_qflag[par];
-            c.hh_flag_next = plan.hh_flag[par ^ 1]; c.hh_qflag_next = plan.hh_qflag[par ^ 1];
-            c.df = plan.df[par]; c.df_next = plan.df[par ^ 1];
-            c.ib_rd = plan.ib[day & 1];
-            const int wr = (day + 1) & 1;
-            c.n_wr = 0;
-            c.ib_wr[c.n_wr++] = plan.ib[wr];
-            for (int r = 0; r < c.n_peers; ++r)
-                if (c.n_peers > 1 && r != c.rank) c.ib_wr[c.n_wr++] = plan.peer_ib[r][wr];
-        }
+        const DevCtx& c = s_c[k & 1];
+        const bool local_push = !two_phase && k + 1 < plan.n_days;
+        if (threadIdx.x == 0 && k + 1 < plan.n_days) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1);
         __syncthreads();
+        unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * 8 : nullptr;
         auto stamp = [&](int i) {
-            if (plan.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+            if (tr && threadIdx.x == 0) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                plan.trace[k * 8 + i] = t;
+                tr[i] = t;
             }
         };
         stamp(0);
-        push_body(s_c, day);
-        stamp(1);
-        grid_barrier(barrier_counter, epoch);
+        if (k == 0 || two_phase) {
+            push_scan_body(c, day, sm, n_work);
+            stamp(1);
+            grid_barrier(barrier_counter, epoch);
+        }
         stamp(2);
-        agent_body<3>(s_c, day);
+        unsigned int push_cnt[4] = {0, 0, 0, 0};
+        const DevCtx* cn = local_push ? &s_c[(k + 1) & 1] : nullptr;
+        if (cn) push_clear_duties(*cn);
+        agent_body<3>(c, day, sm, cn, push_cnt, n_work, tr);
+        if (cn) { __syncthreads(); publish_push_counters(*cn, sm, push_cnt); }
         stamp(3);
         grid_barrier(barrier_counter, epoch);
         stamp(4);
-        if (blockIdx.x == gridDim.x - 1) fold_stats(s_c);      // every block's partial sums are in; the others move on
-        if (c0.n_peers > 1 && blockIdx.x < PUBLISH_BLOCKS) {
+        if (blockIdx.x == gridDim.x - 1) fold_stats(c);      // every block's partial sums are in; the others move on
+        if (peers && blockIdx.x < PUBLISH_BLOCKS) {
             // a few CTAs ship tomorrow's bytes to the peers while the others already start the next day (whose push
             // waits for the peers' flags anyway); the last shipper raises this rank's flag on every GPU
-            publish_body(s_c);
+            publish_body(c);
             __syncthreads();
-            __shared__ bool s_pub_last;
             if (threadIdx.x == 0) s_pub_last = (atomicAdd(barrier_counter + 1, 1u) == PUBLISH_BLOCKS - 1);
             __syncthreads();
             if (s_pub_last) {
@@ -662,14 +846,15 @@ __global__ void __launch_bounds__(256, 4) k_days(const DevCtx c0, const DayPlan 
             }
             __syncthreads();
         }
+        __syncthreads();      // the fold (and tomorrow's bind) are done with today's view
     }
 }
 
 // phase A alone (contagious3.py:181-202): the day-start snapshot byte of every owned agent and the households that see
-// a diagnosis on `day`.  The host clears hh_flag / hh_qflag / df first.
-__global__ void __launch_bounds__(256) k_snapshot(const DevCtx c, const int day, uint8_t* hh_flag, uint8_t* hh_qflag, int32_t* df)
+// a diagnosis on `day` (raised into the day's own attention bytes / quirk flags / flag block, which the host cleared).
+__global__ void __launch_bounds__(BLOCK) k_snapshot(const DevCtx c, const int day)
 {
-    const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    const int64_t a0 = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * 4;
     if (a0 >= c.n_pad) return;
     const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
     const short4 ti4 = *reinterpret_cast<const short4*>(c.t_inf + a0);
@@ -679,8 +864,9 @@ __global__ void __launch_bounds__(256) k_snapshot(const DevCtx c, const int day,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         ibn[j] = infectious_byte(st[j], day, ti[j]);
-        if (diagnosed_on(c, c.u_adm, a0 + j, st[j], ti[j], day)) raise_household(c, a0 + j, hh_flag, hh_qflag, df);
+        if (diagnosed_on(c, c.u_adm, a0 + j, st[j], ti[j], day)) raise_household(c, a0 + j, c.att, c.qflag, c.df);
     }
+    // (k_snapshot of `day` is bound like day - 1's agent pass would be: ib_wr[0] is the buffer of `day`)
     *reinterpret_cast<uchar4*>(c.ib_wr[0] + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
 }
 

@@ -22,7 +22,7 @@ __global__ void k_widen_days(const int16_t* __restrict__ in, int32_t* __restrict
 }
 
 // every index inside its range; t_adm == 0 wherever status is in {1, 2, 6, 7} (contagious3.py:259 keeps that invariant);
-// a susceptible agent has no infector yet (agents[:,21] == 0 until :248 writes it) -- k_push uses src[] as its mailbox
+// a susceptible agent has no infector yet (agents[:,21] == 0 until :248 writes it)
 __global__ void k_validate_population(const DevCtx c, int32_t* bad)
 {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,6 +45,20 @@ __global__ void k_localize(int32_t* __restrict__ hh, int32_t* __restrict__ home,
     hh[a] -= hh_lo;
     home[a] -= bld_lo;
     if (sa[a] >= 0) sa[a] = sa[a] >= area_lo ? sa[a] - area_lo : -2;     // -2: outside the owned areas -> rejected by validation
+}
+
+// household -> members: counts, then (after k_scan_counts) the member lists; order inside a household is irrelevant
+__global__ void k_count_members(const int32_t* __restrict__ hh, int64_t n, int32_t* __restrict__ cnt)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) atomicAdd(&cnt[hh[a]], 1);
+}
+
+__global__ void k_fill_members(const int32_t* __restrict__ hh, int64_t n, unsigned long long* __restrict__ cursor,
+                               int32_t* __restrict__ mem)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) mem[atomicAdd(&cursor[hh[a]], 1ull)] = (int32_t)a;
 }
 
 __global__ void k_validate_routine(const int32_t* __restrict__ routine, int64_t n, int64_t B, int32_t* bad)

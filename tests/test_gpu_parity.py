@@ -189,7 +189,9 @@ def test_step_many_fused_windows_vs_oracle(eng, oracle_lib):
             o.set_open(f[k])
             o.step(day + k)
             out = g.outputs(day + k)
-            keep = [i for i in range(18) if i != 14]
+            # 14..17 (entries scanned / candidates / draws / successes of the push) are implementation specific inside
+            # a fused window: the push of day d+1 runs before other blocks finished day d and does not read u's status
+            keep = list(range(14))
             assert np.array_equal(out["stats"][keep], o.stats()[keep]), "day %d" % (day + k)
             assert np.array_equal(out["stats"][32:53], o.stats()[32:53])
             assert np.array_equal(out["sa_hist"], o.sa_hist()) and np.array_equal(out["building_counts"], o.building_counts())

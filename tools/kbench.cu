@@ -16,8 +16,18 @@ __global__ void __launch_bounds__(256) k_stream(const DevCtx c, const int day)
     uint32_t w = sv.x + sv.y + sv.z + sv.w + ti.x;
     *reinterpret_cast<uint32_t*>(c.ib_wr[0] + a0) = w;
 }
-__global__ void __launch_bounds__(256) k_agent_nofold(const DevCtx c, const int day) { agent_body<1>(c, day); }
-__global__ void __launch_bounds__(256) k_agent_noreduce(const DevCtx c, const int day) { agent_body<2>(c, day); }
+__global__ void __launch_bounds__(256) k_agent_nofold(const DevCtx c, const int day)
+{
+    __shared__ BlockScratch sm;
+    unsigned int none[4] = {0, 0, 0, 0};
+    agent_body<1>(c, day, sm, nullptr, none, (int)gridDim.x);
+}
+__global__ void __launch_bounds__(256) k_agent_noreduce(const DevCtx c, const int day)
+{
+    __shared__ BlockScratch sm;
+    unsigned int none[4] = {0, 0, 0, 0};
+    agent_body<2>(c, day, sm, nullptr, none, (int)gridDim.x);
+}
 template <typename T> T* dalloc(size_t n, int fill = 0) { T* p; cudaMalloc(&p, n * sizeof(T)); cudaMemset(p, fill, n * sizeof(T)); return p; }
 
 int main(int argc, char** argv)
@@ -43,13 +53,28 @@ int main(int argc, char** argv)
     d = dalloc<int32_t>(N); cudaMemcpy(d, sa.data(), 4 * N, cudaMemcpyHostToDevice); c.sa = d;
     c.risk = dalloc<double>(N); c.p_adm = dalloc<double>(N); c.p_death = dalloc<double>(N);
     c.pdf = dalloc<double>(64);
-    uint8_t* ibbuf = dalloc<uint8_t>(N + 2048); c.ib_rd = ibbuf; c.ib_wr[0] = ibbuf; c.n_wr = 1; c.n_peers = 1;
+    DayBuffers buf{};
+    c.n_peers = 1;
     c.flag_wait = dalloc<int32_t>(8); c.flag_signal[0] = dalloc<int32_t>(8);
     c.open = dalloc<uint8_t>(c.B, 1); c.n_closed = 0;
-    uint8_t* f0 = dalloc<uint8_t>(c.H + 16); uint8_t* f1 = dalloc<uint8_t>(c.H + 16);
-    c.hh_flag = f0; c.hh_qflag = f1; c.hh_flag_next = dalloc<uint8_t>(c.H + 16); c.hh_qflag_next = dalloc<uint8_t>(c.H + 16);
-    int32_t* df = dalloc<int32_t>(16); c.df = df; c.df_next = df + 4;
-    c.part = dalloc<unsigned long long>(64 * 64); c.stats = dalloc<int64_t>(64); c.ticket = dalloc<unsigned int>(1);
+    for (int k = 0; k < 2; ++k) {
+        buf.att[k] = dalloc<uint8_t>(N + 16); buf.mb_any[k] = dalloc<int32_t>(N, 0xFF); buf.mb_iso[k] = dalloc<int32_t>(N, 0xFF);
+        buf.ib[k] = dalloc<uint8_t>(N + 2048);
+    }
+    for (int k = 0; k < Q_RING; ++k) buf.qflag[k] = dalloc<uint8_t>(c.H + 16);
+    buf.df = dalloc<int32_t>(DF_RING * DF_LEN);
+    buf.part = dalloc<unsigned long long>(PART_RING * 64 * 64);
+    int32_t* df = buf.df;
+    uint8_t* ibbuf = buf.ib[0];
+    c.stats = dalloc<int64_t>(64); c.ticket = dalloc<unsigned int>(1);
+    {
+        std::vector<int64_t> hp(c.H + 2); std::vector<int32_t> hm(N);
+        for (int64_t h = 0; h <= c.H + 1; ++h) hp[h] = h * 3 < N ? h * 3 : N;
+        for (int64_t a = 0; a < N; ++a) hm[a] = (int)a;
+        int64_t* dp = dalloc<int64_t>(c.H + 2); cudaMemcpy(dp, hp.data(), 8 * (c.H + 2), cudaMemcpyHostToDevice); c.hh_ptr = dp;
+        int32_t* dm = dalloc<int32_t>(N); cudaMemcpy(dm, hm.data(), 4 * N, cudaMemcpyHostToDevice); c.hh_mem = dm;
+    }
+    bind_day(c, buf, 100);
     c.sa_hist = dalloc<int32_t>(c.S * 21); c.bcount = dalloc<int32_t>(c.B);
     c.ev = dalloc<int2>(N);
     {   // a synthetic transposed network: 17 entries per column, rows within +-300 of the column (same community)
@@ -91,7 +116,7 @@ int main(int argc, char** argv)
     timeit("k_agent any_nd=1", [&](int d) { k_agent<<<g4, 256>>>(c, d); });
     timeit("k_agent no fold/ticket", [&](int d) { k_agent_nofold<<<g4, 256>>>(c, d); });
     timeit("k_agent no reduction", [&](int d) { k_agent_noreduce<<<g4, 256>>>(c, d); });
-    timeit("k_snapshot", [&](int d) { k_snapshot<<<g4, 256>>>(c, d, f0, f1, df); });
+    timeit("k_snapshot", [&](int d) { k_snapshot<<<g4, 256>>>(c, d); });
     int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_push, 256, 0);
     {   // snapshot bytes for the infectious agents
         std::vector<uint8_t> ibh(N + 2048, 0);
@@ -102,32 +127,43 @@ int main(int argc, char** argv)
     printf("push blocks/SM %d\n", per_sm);
     {   // k_days: 7 days in one cooperative launch, with phase timestamps of block 0
         DayPlan plan{};
-        plan.first_day = 100; plan.n_days = 7; plan.first_parity = 0;
+        plan.first_day = 100; plan.n_days = 7;
         plan.off_sa = 512; plan.off_bc = 512 + ((c.S * 21 * 4 + 15) & ~15ll); plan.off_ev = plan.off_bc + ((c.B * 4 + 15) & ~15ll);
         plan.want_sa = plan.want_bc = plan.want_ev = 1;
         const size_t blk = plan.off_ev + 8 * (size_t)N;
         for (int k = 0; k < 7; ++k) { plan.out[k] = dalloc<unsigned char>(blk); plan.open[k] = c.open; plan.n_closed[k] = 0; }
-        plan.hh_flag[0] = f0; plan.hh_flag[1] = c.hh_flag_next; plan.hh_qflag[0] = f1; plan.hh_qflag[1] = c.hh_qflag_next;
-        plan.df[0] = df; plan.df[1] = df + 4;
-        plan.ib[0] = ibbuf; plan.ib[1] = dalloc<uint8_t>(N + 2048);
-        cudaMemcpy(plan.ib[1], ibbuf, N, cudaMemcpyDeviceToDevice);
-        plan.trace = dalloc<unsigned long long>(64);
+        cudaMemcpy(buf.ib[1], ibbuf, N, cudaMemcpyDeviceToDevice);
+        plan.buf = buf;
+        plan.trace = dalloc<unsigned long long>((size_t)7 * 148 * 8 * 8);
         unsigned int* bar = dalloc<unsigned int>(4);
         int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_days, 256, 0);
         void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
         for (int rep = 0; rep < 3; ++rep) {
             cudaMemset(bar, 0, 16);
-            cudaMemcpy(df, &anynd, 4, cudaMemcpyHostToDevice);
+            for (int q = 0; q < DF_RING; ++q) cudaMemcpy(df + q * DF_LEN, &anynd, 4, cudaMemcpyHostToDevice);
             cudaEventRecord(e0);
             cudaError_t er = cudaLaunchCooperativeKernel((const void*)k_days, dim3(148 * occ), dim3(256), args, 0, 0);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             printf("k_days 7 days: %.2f us/day (%s, %d CTAs/SM)\n", ms * 1000 / 7, cudaGetErrorString(er), occ);
         }
-        unsigned long long tr[64]; cudaMemcpy(tr, plan.trace, sizeof tr, cudaMemcpyDeviceToHost);
-        for (int k = 1; k < 7; ++k)
-            printf("  day %d (block 0): push %.2f  barrier %.2f  agent %.2f  barrier %.2f us\n", k, (tr[k*8+1]-tr[k*8+0])/1e3,
-                   (tr[k*8+2]-tr[k*8+1])/1e3, (tr[k*8+3]-tr[k*8+2])/1e3, (tr[k*8+4]-tr[k*8+3])/1e3);
+        const int G = 148 * occ;
+        std::vector<unsigned long long> tr((size_t)7 * G * 8);
+        cudaMemcpy(tr.data(), plan.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 7; ++k) {
+            // per phase: mean over the working blocks, and the latest block relative to the earliest day start
+            double sw = 0, se = 0, pu = 0, late = 0; unsigned long long t_first = ~0ull, t_last = 0;
+            for (int b = 0; b < G - 1; ++b) {
+                const unsigned long long* t = &tr[((size_t)k * G + b) * 8];
+                sw += (t[5] - t[2]) / 1e3; se += (t[6] - t[5]) / 1e3; pu += (t[7] - t[6]) / 1e3;
+                if (t[2] < t_first) t_first = t[2];
+                if (t[3] > t_last) t_last = t[3];
+            }
+            (void)late;
+            const unsigned long long* t0 = &tr[((size_t)k * G) * 8];
+            printf("  day %d: sweep %.2f  settle %.2f  push %.2f us (means)   first start -> last block done %.2f   block 0 barrier wait %.2f\n",
+                   k, sw / (G - 1), se / (G - 1), pu / (G - 1), (t_last - t_first) / 1e3, (t0[4] - t0[3]) / 1e3);
+        }
     }
     return 0;
 }
