@@ -174,9 +174,8 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     int rc = DYS_OK;
     auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
     double* d_pdf = nullptr;
-    A(dev_alloc(h, &c.status, c.n_pad)); A(dev_alloc(h, &c.t_inf, c.n_pad)); A(dev_alloc(h, &c.t_q, c.n_pad));
-    A(dev_alloc(h, &c.t_adm, c.n_pad)); A(dev_alloc(h, &c.src, c.n_pad));
-    A(dev_alloc(h, (int32_t**)&c.hh, c.n_pad)); A(dev_alloc(h, (int32_t**)&c.home, c.n_pad)); A(dev_alloc(h, (int32_t**)&c.sa, c.n_pad));
+    A(dev_alloc(h, &c.status, c.n_pad)); A(dev_alloc(h, &c.rec, c.n_pad)); A(dev_alloc(h, &c.src, c.n_pad));
+    A(dev_alloc(h, (int32_t**)&c.hh, c.n_pad));
     A(dev_alloc(h, (double**)&c.risk, c.n_pad)); A(dev_alloc(h, (double**)&c.p_adm, c.n_pad)); A(dev_alloc(h, (double**)&c.p_death, c.n_pad));
     A(dev_alloc(h, (int32_t**)&c.routine, c.rt_n * c.V));
     h->ib_stride = round_up(c.n_glob, 1024) + 1024;
@@ -310,11 +309,11 @@ static int check_bad(dys_handle* h, const char* what)
     return DYS_OK;
 }
 
-static int load_days(dys_handle* h, int16_t* dst, const int32_t* src, int32_t* tmp, int64_t n)
+static int load_days(dys_handle* h, int field, const int32_t* src, int32_t* tmp, int64_t n)
 {
     int rc = copy_in(h, tmp, src, sizeof(int32_t) * (size_t)n);
     if (rc != DYS_OK) return rc;
-    k_narrow_days<<<grid_for(n, 256), 256, 0, h->stream>>>(tmp, dst, n, h->d_bad);
+    k_narrow_days<<<grid_for(n, 256), 256, 0, h->stream>>>(tmp, h->c.rec, field, n, h->d_bad);
     CK(h, cudaGetLastError());
     return DYS_OK;
 }
@@ -329,9 +328,9 @@ static int load_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_
     int rc = DYS_OK;
     auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
     A(copy_in(h, c.status, status_x2, (size_t)n));
-    A(load_days(h, c.t_inf, t_inf, tmp, n));
-    A(load_days(h, c.t_q, t_q, tmp, n));
-    A(load_days(h, c.t_adm, t_adm, tmp, n));
+    A(load_days(h, 0, t_inf, tmp, n));
+    A(load_days(h, 1, t_q, tmp, n));
+    A(load_days(h, 2, t_adm, tmp, n));
     A(copy_in(h, c.src, src, sizeof(int32_t) * (size_t)n));
     cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
@@ -351,12 +350,20 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
     const size_t n = (size_t)c.n_loc;
     int rc = load_state(h, status_x2, t_inf, t_q, t_adm, src);
     auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
-    A(copy_in(h, (void*)c.hh, hh, 4 * n)); A(copy_in(h, (void*)c.home, home, 4 * n)); A(copy_in(h, (void*)c.sa, sa, 4 * n));
+    int32_t *d_home = nullptr, *d_sa = nullptr;      // staging: both end up inside the agent records
+    if (cudaMalloc((void**)&d_home, 4 * n) != cudaSuccess || cudaMalloc((void**)&d_sa, 4 * n) != cudaSuccess) {
+        cudaFree(d_home);
+        return fail(h, DYS_ERR_NOMEM, "dys_load_population: staging allocation failed");
+    }
+    A(copy_in(h, (void*)c.hh, hh, 4 * n)); A(copy_in(h, d_home, home, 4 * n)); A(copy_in(h, d_sa, sa, 4 * n));
     A(copy_in(h, (void*)c.risk, risk, 8 * n)); A(copy_in(h, (void*)c.p_adm, p_adm, 8 * n)); A(copy_in(h, (void*)c.p_death, p_death, 8 * n));
     A(copy_in(h, (void*)c.routine, routine, 4 * (size_t)c.rt_n * c.V));
+    if (rc == DYS_OK)
+        k_localize<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>((int32_t*)c.hh, d_home, d_sa, c.rec, c.n_loc, (int32_t)h->hh_lo,
+                                                                  (int32_t)h->bld_lo, (int32_t)h->area_lo);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_home); cudaFree(d_sa);
     if (rc != DYS_OK) return rc;
-    k_localize<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>((int32_t*)c.hh, (int32_t*)c.home, (int32_t*)c.sa, c.n_loc, (int32_t)h->hh_lo,
-                                                              (int32_t)h->bld_lo, (int32_t)h->area_lo);
     k_validate_population<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c, h->d_bad);
     k_validate_routine<<<grid_for(c.rt_n * c.V, 256), 256, 0, h->stream>>>(c.routine, c.rt_n * c.V, c.B, h->d_bad);
     CK(h, cudaGetLastError());
@@ -442,11 +449,9 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
     rc = copy_in(h, d_col, col, sizeof(int32_t) * (size_t)nnz);
     if (rc == DYS_OK) rc = copy_in(h, d_val, val, sizeof(double) * (size_t)nnz);
     int64_t* d_tptr = nullptr;
-    uint32_t* d_tcolx = nullptr;
-    double* d_tval = nullptr;
+    TEdge* d_tedge = nullptr;
     if (rc == DYS_OK) rc = dev_alloc(h, &d_tptr, c.rt_n + 1);
-    if (rc == DYS_OK) rc = dev_alloc(h, &d_tcolx, nnz + 16);
-    if (rc == DYS_OK) rc = dev_alloc(h, &d_tval, nnz + 2, false);
+    if (rc == DYS_OK) rc = dev_alloc(h, &d_tedge, nnz + 4);
     if (rc == DYS_OK) {
         k_validate_graph_count<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(d_rowptr, d_col, c.n_loc, c.rt_lo, c.rt_lo + c.rt_n,
                                                                              d_cnt, h->d_bad);
@@ -455,13 +460,13 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
     if (rc == DYS_OK) {
         // transpose: column counts -> offsets -> scatter with the static shared-building class of each pair
         k_scan_counts<<<1, 1024, 0, h->stream>>>(d_cnt, c.rt_n, d_tptr, d_cursor);
-        k_fill_transpose<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_rowptr, d_col, d_val, d_cursor, d_tcolx, d_tval);
+        k_fill_transpose<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_rowptr, d_col, d_val, d_cursor, d_tedge);
         if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
             rc = fail(h, DYS_ERR_CUDA, "building the transposed network failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cleanup();
     if (rc != DYS_OK) return rc;
-    c.tptr = d_tptr; c.tcolx = d_tcolx; c.tval = d_tval;
+    c.tptr = d_tptr; c.tedge = d_tedge;
     h->nnz = nnz;
     h->have_graph = true;
     return DYS_OK;
@@ -925,13 +930,12 @@ extern "C" int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, 
     const int64_t n = c.n_loc;
     if (status_x2) CK(h, cudaMemcpyAsync(status_x2, c.status, (size_t)n, cudaMemcpyDefault, h->stream));
     if (src) CK(h, cudaMemcpyAsync(src, c.src, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, h->stream));
-    const int16_t* cols[3] = {c.t_inf, c.t_q, c.t_adm};
     int32_t* outs[3] = {t_inf, t_q, t_adm};
     int32_t* tmp = nullptr;
     for (int k = 0; k < 3; ++k) {
         if (!outs[k]) continue;
         if (!tmp) CK(h, cudaMalloc((void**)&tmp, sizeof(int32_t) * (size_t)n));
-        k_widen_days<<<grid_for(n, 256), 256, 0, h->stream>>>(cols[k], tmp, n);
+        k_widen_days<<<grid_for(n, 256), 256, 0, h->stream>>>(c.rec, k, tmp, n);
         cudaError_t e = cudaMemcpyAsync(outs[k], tmp, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { cudaFree(tmp); return fail(h, DYS_ERR_CUDA, "dys_get_state: %s", cudaGetErrorString(e)); }
@@ -983,7 +987,7 @@ extern "C" int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* 
         case DYS_BUF_STATUS: *ptr = c.status; *bytes = c.n_pad; break;
         case DYS_BUF_INFECTIOUS: *ptr = h->d_ib; *bytes = 2 * h->ib_stride; break;   /* [2][bytes/2]: buffer of day d is d & 1 */
         case DYS_BUF_STATS: *ptr = h->d_out[h->last_slot]; *bytes = (int64_t)sizeof(int64_t) * N_STATS; break;
-        case DYS_BUF_T_INF: *ptr = c.t_inf; *bytes = c.n_pad * 2; break;
+        case DYS_BUF_AGENT_REC: *ptr = c.rec; *bytes = c.n_pad * (int64_t)sizeof(AgentRec); break;
         default: return fail(h, DYS_ERR_INVALID_ARG, "unknown buffer %d", which);
     }
     return DYS_OK;

@@ -35,6 +35,14 @@ __device__ __forceinline__ uint8_t infectious_byte(uint32_t st, int day, int t_i
 constexpr uint32_t COL_MASK = 0x07FFFFFFu;
 constexpr int CLS_SHIFT = 28;
 constexpr uint32_t CLS_HH = 1u, CLS_HO = 2u, CLS_OH = 4u, CLS_OO = 8u;
+// one non-zero of the transposed interaction_prob, 16 bytes so that a lane fetches it with one 128-bit load.  The first
+// product of contagious3.py:232 -- interaction_prob[u,i] * agents[u,14] -- only involves static data, so it is formed once
+// at load time (same IEEE multiply, same rounding) and the push never gathers risk[u].
+struct __align__(16) TEdge {
+    uint32_t colx;                       // u | class << 28
+    uint32_t pad;
+    double val;                          // ip[u,i] * risk[u]
+};
 
 constexpr int N_STATS = 64, N_SLOTS = 64, HIST0 = 32, HIST_LEN = 21;
 enum {
@@ -50,6 +58,15 @@ constexpr int Q_RING = 3, PART_RING = 3;         // quirk household flags and pa
 // susceptible (or long recovered) cannot change today: the sweep of agent_body reads two bytes for it and moves on.
 constexpr uint32_t ATT_HIT = 1u, ATT_HH = 2u;
 
+// Everything the settle phase needs about one agent besides its status byte, in ONE 16-byte record: a divergent
+// gather costs the load/store unit one pass per distinct 32-byte sector, so four 2- and 4-byte columns cost four times
+// what this record does.
+struct __align__(16) AgentRec {
+    int16_t t_inf, t_q, t_adm, pad;      // agents[:,16], agents[:,19], agents[:,24] (contagious3.py:115-118); 0 = never
+    int32_t sa;                          // statistical area (local to the owned areas), -1 = none
+    int32_t home;                        // home building (local to the owned buildings)
+};
+
 struct DevCtx {
     int64_t n_loc, n_pad, n_glob, lo;    // owned agents, padded count (multiple of 1024), global agents, first owned
     int64_t rt_lo, rt_n;                 // halo: global agents [rt_lo, rt_lo + rt_n) are the columns owned rows reference
@@ -61,18 +78,17 @@ struct DevCtx {
     uint64_t seed;
     // mutable state, owned agents
     uint8_t* status;
-    int16_t *t_inf, *t_q, *t_adm;
+    AgentRec* rec;                       // days in state (mutable) + area and home building (static)
     int32_t* src;                        // infector (global index), -1 = never infected
     // static per owned agent
-    const int32_t *hh, *home, *sa;
+    const int32_t* hh;
     const double *risk, *p_adm, *p_death;
     const int32_t* routine;              // [rt_n * V] building index or -1 (halo agents: both sides of a pair are read)
     const int64_t* hh_ptr;               // [H + 1] household -> its members (local agent indices)
     const int32_t* hh_mem;               // [n_loc]
     // interaction_prob TRANSPOSED over the halo columns: for infectious column i, the owned rows u with ip[u,i] != 0
     const int64_t* tptr;                 // [rt_n + 1]
-    const uint32_t* tcolx;               // [nnz] u (local) | class << 28
-    const double* tval;                  // [nnz] ip[u, i]
+    const TEdge* tedge;                  // [nnz]
     const double* pdf;                   // [64]
     const uint8_t* hh_always;            // [H] or null   (quirk of contagious3.py:267, see dys_load_quirk)
     const int64_t* trig_ptr;             // [n_pad + 1] or null

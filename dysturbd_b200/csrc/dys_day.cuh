@@ -59,7 +59,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 constexpr int BLOCK = 256, WARPS = BLOCK / 32;
 constexpr int FCAP = 4096;                         // frontier entries: index relative to the block's base | snapshot byte << 24
 constexpr int LCAP = 2048;                         // agent work list = one batch of the sweep (2 x 4 agents per thread)
-constexpr int PUSH_PCAP = 256;
 constexpr uint32_t REL_MASK = 0x00FFFFFFu;
 
 // where a block's queued agents live: contiguous from `base` (scan push), or in pieces of 128 agents dealt round-robin
@@ -73,6 +72,7 @@ struct FrontMap {
     }
 };
 
+constexpr int PUSH_PCAP = 256;
 struct PushWarpScratch {
     int off[36];                                   // exclusive prefix of the expanded rows' lengths
     int64_t t0[32];
@@ -118,37 +118,32 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
     int rpg = (n + WARPS - 1) / WARPS;
     rpg = rpg < 1 ? 1 : (rpg > 32 ? 32 : rpg);
     const int n_groups = (n + rpg - 1) / rpg;
+    const uint4* edges = reinterpret_cast<const uint4*>(c.tedge);
 
-    // settle the first np queued pairs of this warp: probability, Bernoulli, mailbox
+    // settle the first np queued pairs of this warp, one pair per lane: probability, Bernoulli, mailbox.  The Philox
+    // rounds are the expensive part of a push; they run on full warps because the pairs were compacted first.
     auto settle = [&](const int q0, const int np) {
         for (int k0 = 0; k0 < np; k0 += 32) {
             const int k = k0 + lane;
             if (k >= np) continue;
-            const unsigned long long rec = w.pairs[k];
-            const int64_t e = (int64_t)(rec & 0xFFFFFFFFFFFFull);
-            const int r = (int)((rec >> 48) & 0x3Fu);
-            const uint32_t fl = (uint32_t)(rec >> 56);                  // CHECK: bit0 = u is isolated; else bit0 = valid if u isolated
+            const unsigned long long q = w.pairs[k];
+            const int r = (int)((q >> 48) & 0x3Fu);
+            const uint32_t fl = (uint32_t)(q >> 56);                    // bit0 valid if u moves freely, bit1 valid if u is isolated
+            const uint4 rec = __ldg(edges + (int64_t)(q & 0xFFFFFFFFFFFFull));   // fetched a moment ago: an L1 hit
             const uint32_t fe = sm.front[q0 + r];
-            const uint32_t cw = __ldg(c.tcolx + e), ib_i = fe >> 24;
-            const uint32_t ul = cw & COL_MASK;
+            const uint32_t ul = rec.x & COL_MASK, ib_i = fe >> 24;
             const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe & REL_MASK);
-            const bool iso_i = (ib_i & IB_ISO) != 0;
-            bool ok_free, ok_iso;
-            if (CHECK) {
-                const bool iso_u = fl & 1u;
-                const bool ok = !any_closed || exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
-                ok_free = ok && !iso_u;
-                ok_iso = ok && iso_u;
-            } else {
-                ok_free = !any_closed || exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
-                ok_iso = (fl & 1u) && (!any_closed || exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i));
+            bool ok_free = fl & 1u, ok_iso = (fl & 2u) != 0;
+            if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
+                const bool iso_i = (ib_i & IB_ISO) != 0;
+                if (ok_free) ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
+                if (ok_iso) ok_iso = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
+                if (!ok_free && !ok_iso) continue;
             }
-            if (!ok_free && !ok_iso) continue;
             ++cnt[2];
             // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
-            // rounded separately (no add follows, so no FMA can form)
-            double p = __dmul_rn(__ldg(c.tval + e), __ldg(c.risk + ul));
-            p = __dmul_rn(p, sm.pdf[ib_i & IB_DAYS]);
+            // rounded separately (no add follows, so no FMA can form); the first product comes with the record
+            double p = __dmul_rn(__hiloint2double((int)rec.w, (int)rec.z), sm.pdf[ib_i & IB_DAYS]);
             p = __dmul_rn(p, c.norm_factor);
             if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
             const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
@@ -186,9 +181,9 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
         cnt[0] += len;
         int np = 0;                                        // queued pairs (warp-uniform)
         for (int f0 = 0; f0 < total; f0 += 128) {
-            int64_t e[4];
             int r[4];
-            uint32_t cw[4], st_u[4];
+            int64_t e[4];
+            uint32_t cx[4], st_u[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int f = f0 + 32 * k + lane;
@@ -200,40 +195,37 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
                 }
                 r[k] = lo;
                 e[k] = w.t0[lo] + (f - w.off[lo]);
-                cw[k] = f < total ? __ldg(c.tcolx + e[k]) : 0u;
+                // the whole 16-byte record comes in (the value is used when the pair is settled); class 0 = padding lane
+                cx[k] = f < total ? __ldg(edges + e[k]).x : 0u;
             }
             if (CHECK) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[cw[k] & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
+                    st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[cx[k] & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                // cheap part of the exposure test (static class x today's isolation); survivors are queued
-                const uint32_t cls = cw[k] >> CLS_SHIFT;                // 0 for the padding entries
+                // the cheap part of the exposure test: static class x today's isolation; survivors are queued
+                const uint32_t cls = cx[k] >> CLS_SHIFT;
                 const bool iso_i = (sm.front[q0 + r[k]] >> 24) & IB_ISO;
                 const bool x_iso = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i);                      // u isolated at home
                 const bool x_free = x_iso | ((cls & CLS_OH) != 0) | ((cls & CLS_OO) && !iso_i);      // u moves freely
-                bool ex;
-                uint32_t fl;
+                bool ok_free, ok_iso;
                 if (CHECK) {
-                    const bool sus = in_set(M_SUS, st_u[k]);
-                    const bool iso_u = (st_u[k] == ST_QH);
+                    const bool sus = in_set(M_SUS, st_u[k]), iso_u = (st_u[k] == ST_QH);
                     cnt[1] += sus;
-                    ex = sus && (iso_u ? x_iso : x_free);
-                    fl = iso_u;
+                    ok_free = sus && !iso_u && x_free;
+                    ok_iso = sus && iso_u && x_iso;
                 } else {
-                    ex = x_free;
-                    cnt[1] += ex;
-                    fl = x_iso;
+                    cnt[1] += x_free;
+                    ok_free = x_free;
+                    ok_iso = x_iso;
                 }
+                const bool ex = ok_free || ok_iso;
                 const unsigned m = __ballot_sync(0xffffffffu, ex);
-                if (ex) {
+                if (ex)
                     w.pairs[np + __popc(m & lt_mask)] = (unsigned long long)e[k] | ((unsigned long long)r[k] << 48) |
-                                                        ((unsigned long long)fl << 56);
-                    prefetch_l2(c.tval + e[k]);                 // both are read when the pair is settled
-                    prefetch_l2(c.risk + (cw[k] & COL_MASK));
-                }
+                                                        ((unsigned long long)((ok_free ? 1u : 0u) | (ok_iso ? 2u : 0u)) << 56);
                 np += __popc(m);
             }
             __syncwarp();
@@ -379,19 +371,31 @@ constexpr int RAW_END = 53;      // [53..60] end-of-day status counts in hist_id
 constexpr int RAW_SUS0 = 61, RAW_INF0 = 62;
 constexpr int ST_COUNT0 = 20;    // public: stats[20..27] = end-of-day agents in S, I, QH, QI, D, H, R, X
 
-// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366);
-// returns tomorrow's snapshot byte
-__device__ __forceinline__ uint8_t settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
-                                                const uint32_t st, const uint32_t att, BlockScratch& sm,
-                                                bool& infected_today, int& infector)
+// what one settled agent contributes to the day's counters (accumulated per warp, see agent_body)
+enum : uint32_t { EVB_ADM = 1u, EVB_DEATH = 2u, EVB_DAILY_INF = 4u, EVB_DAILY_QUAR = 8u, EVB_NEW_DIAG = 16u, EVB_CHANGED = 32u,
+                  EVB_SUS0 = 64u, EVB_INF0 = 128u };
+struct Settled {
+    uint32_t x;          // end-of-day status
+    uint32_t ev;         // EVB_* flags
+    int k;               // days-since-infection histogram bin, or -1
+    uint32_t ibn;        // tomorrow's snapshot byte
+};
+
+// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
+__device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
+                                                const uint32_t st, const uint32_t att, bool& infected_today, int& infector)
 {
-    // every column this agent can need is requested before any of it is used
-    int ti = c.t_inf[a];
-    int tq = c.t_q[a];
+    uint32_t evb = 0;
+    // everything this agent can need is requested before any of it is used; its days in state, area and home building
+    // arrive together in one 16-byte record
+    const int4 rv = *reinterpret_cast<const int4*>(c.rec + a);
+    int16_t* const rdays = reinterpret_cast<int16_t*>(c.rec + a);       // [0] t_inf, [1] t_q, [2] t_adm
+    int ti = (int16_t)(rv.x & 0xFFFF);
+    int tq = rv.x >> 16;
+    const int tadm = (int16_t)(rv.y & 0xFFFF);
+    const int sa_a = rv.z, home_a = rv.w;
     const bool quirk = any_nd && (c.trig_ptr || c.hh_always);
     const int h = quirk ? __ldg(c.hh + a) : 0;
-    const int sa_a = c.sa_hist ? __ldg(c.sa + a) : -1;
-    const int home_a = c.bcount ? __ldg(c.home + a) : 0;
     int mb = -1;
     if (att & ATT_HIT) {
         // the mailbox that matches this agent's isolation; both are reset for the day after tomorrow
@@ -409,18 +413,18 @@ __device__ __forceinline__ uint8_t settle_agent(const DevCtx& c, const int day, 
     infected_today = false;
     // ---- B, C (contagious3.py:205-227) on the day-start status; D's result from the mailbox ----
     if (in_set(M_INF, st)) {
-        atomicAdd(&sm.cnt[9], 1u);
+        evb |= EVB_INF0;
         if (ti >= c.adm_min && ti <= c.adm_max) {                            // :205 window on the ABSOLUTE infection day
             const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
-            if (__ldg(c.p_adm + a) > u) { x = ST_H; c.t_adm[a] = (int16_t)day; atomicAdd(&sm.ev[EV_ADM], 1u); }   // :213-216
+            if (__ldg(c.p_adm + a) > u) { x = ST_H; rdays[2] = (int16_t)day; evb |= EVB_ADM; }     // :213-216
         }
     } else if (st == ST_H) {
-        if (c.t_adm[a] >= c.death_min) {                                     // :219
+        if (tadm >= c.death_min) {                                           // :219
             const double u = draw(c.u_death, c.lo + a, c.seed, day, STREAM_DEATH, (uint32_t)(c.lo + a), 0);
-            if (__ldg(c.p_death + a) > u) { x = ST_X; c.t_adm[a] = 0; atomicAdd(&sm.ev[EV_DEATH], 1u); }          // :225-227, :259
+            if (__ldg(c.p_death + a) > u) { x = ST_X; rdays[2] = 0; evb |= EVB_DEATH; }            // :225-227, :259
         }
     } else if (in_set(M_SUS, st)) {
-        atomicAdd(&sm.cnt[8], 1u);
+        evb |= EVB_SUS0;
         infector = mb;
         if (infector >= 0) {                                                 // :241-248: the push found an infector
             x = (st == ST_S) ? ST_I : ST_QI;
@@ -436,8 +440,8 @@ __device__ __forceinline__ uint8_t settle_agent(const DevCtx& c, const int day, 
     if (x == ST_I && n_inf == c.diagnosis) { tq = day; w_tq = true; }                       // :253
     if ((x == ST_I || x == ST_QI) && n_inf == c.diagnosis) x = ST_D;                        // :254
     if (x == ST_D && n_inf == c.recover) x = ST_R;                                          // :255
-    if (x == ST_H && n_inf == c.hospital_recover) { x = ST_R; c.t_adm[a] = 0; }             // :256, :259
-    if (x == ST_D && n_inf == c.diagnosis) atomicAdd(&sm.ev[EV_NEW_DIAG], 1u);              // :261
+    if (x == ST_H && n_inf == c.hospital_recover) { x = ST_R; rdays[2] = 0; }               // :256, :259
+    if (x == ST_D && n_inf == c.diagnosis) evb |= EVB_NEW_DIAG;                             // :261
     // ---- F (contagious3.py:261-270): the households diagnosed today were flagged yesterday ----
     if (any_nd && (x == ST_S || x == ST_I)) {
         bool hit = f_hh;                                                                    // :263
@@ -446,21 +450,21 @@ __device__ __forceinline__ uint8_t settle_agent(const DevCtx& c, const int day, 
             hit = keyed_uniform(c.seed, day, STREAM_COMPLIANCE, (uint32_t)(c.lo + a), 0) < c.compliance;
         if (hit) { x = (x == ST_S) ? ST_QH : ST_QI; tq = day; w_tq = true; }                // :265-270
     }
-    if (w_ti) c.t_inf[a] = (int16_t)ti;
-    if (w_tq) c.t_q[a] = (int16_t)tq;
-    if (x != st) { c.status[a] = (uint8_t)x; atomicAdd(&sm.ev[EV_CHANGED], 1u); }
-    if (in_set(M_ISO, x) && tq == day) atomicAdd(&sm.ev[EV_DAILY_QUAR], 1u);
+    if (w_ti) rdays[0] = (int16_t)ti;
+    if (w_tq) rdays[1] = (int16_t)tq;
+    if (x != st) { c.status[a] = (uint8_t)x; evb |= EVB_CHANGED; }
+    if (in_set(M_ISO, x) && tq == day) evb |= EVB_DAILY_QUAR;
     // ---- G: this agent's share of the integer statistics (contagious3.py:273-366) ----
-    atomicAdd(&sm.cnt[hist_idx(x)], 1u);
+    int kbin = -1;
     if (in_set(M_EVER, x)) {
         const int k = day - ti;
         if (k >= 0 && k < HIST_LEN) {
-            if (k == 0) atomicAdd(&sm.ev[EV_DAILY_INF], 1u);
-            atomicAdd(&sm.hist[k], 1u);
+            if (k == 0) evb |= EVB_DAILY_INF;
+            kbin = k;
             if (c.sa_hist && sa_a >= 0) atomicAdd(&c.sa_hist[(size_t)sa_a * HIST_LEN + k], 1);
             if (c.io_mat && infected_today) {
                 // contagious3.py:356-366: row = area of today's infected, column = area of the infector
-                const int sa_u = __ldg(c.sa + a), sa_i = __ldg(c.sa + (infector - c.lo));
+                const int sa_u = sa_a, sa_i = c.rec[infector - c.lo].sa;
                 if (sa_u >= 0 && sa_i >= 0) atomicAdd(&c.io_mat[(size_t)sa_u * c.S + sa_i], 1);
             }
         }
@@ -468,9 +472,9 @@ __device__ __forceinline__ uint8_t settle_agent(const DevCtx& c, const int day, 
     }
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
-    c.ib_wr[0][c.lo + a] = ibn;
+    if (ibn) c.ib_wr[0][c.lo + a] = ibn;      // (the sweep already stored 0 for everybody)
     if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.att_next, c.qflag_next, c.df_next);
-    return ibn;
+    return Settled{x, evb, kbin, ibn};
 }
 
 // One block folds the spread partial sums (part[counter][slot]: one warp per counter, two coalesced loads, shuffle tree),
@@ -633,11 +637,41 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             int infector = -1;
             int64_t a = 0;
             uint32_t ibn = 0, rel = 0;
+            uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
+            int kbin = -1;
             if (k < n_list) {
                 const uint32_t le = sm.list[k];
                 rel = le & REL_MASK;
                 a = agent_of(rel);
-                ibn = settle_agent(c, day, a, any_nd, (le >> 24) & 0xFu, (le >> 28) & 0x3u, sm, infected_today, infector);
+                const Settled r = settle_agent(c, day, a, any_nd, (le >> 24) & 0xFu, (le >> 28) & 0x3u, infected_today, infector);
+                ibn = r.ibn;
+                kbin = r.k;
+                const uint32_t hi = hist_idx(r.x);
+                h0 = hi < 4 ? 1u << (8 * hi) : 0u;
+                h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
+                eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
+                     ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
+                eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
+                     ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
+            }
+            {
+                // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per
+                // non-zero counter from distinct lanes -- not 32 colliding atomics per counter
+                h0 = __reduce_add_sync(0xffffffffu, h0);
+                h1 = __reduce_add_sync(0xffffffffu, h1);
+                eA = __reduce_add_sync(0xffffffffu, eA);
+                eB = __reduce_add_sync(0xffffffffu, eB);
+                const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
+                const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
+                if (v) {
+                    unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
+                                      : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
+                                      : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
+                                      : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
+                    atomicAdd(dst, v);
+                }
+                const unsigned km = __match_any_sync(0xffffffffu, kbin);
+                if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
             }
             // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
             const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
@@ -857,9 +891,8 @@ __global__ void __launch_bounds__(BLOCK) k_snapshot(const DevCtx c, const int da
     const int64_t a0 = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * 4;
     if (a0 >= c.n_pad) return;
     const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
-    const short4 ti4 = *reinterpret_cast<const short4*>(c.t_inf + a0);
     const uint32_t st[4] = {sv.x, sv.y, sv.z, sv.w};
-    const int ti[4] = {ti4.x, ti4.y, ti4.z, ti4.w};
+    const int ti[4] = {c.rec[a0].t_inf, c.rec[a0 + 1].t_inf, c.rec[a0 + 2].t_inf, c.rec[a0 + 3].t_inf};
     uint8_t ibn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

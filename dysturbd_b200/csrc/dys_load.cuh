@@ -5,20 +5,20 @@
 
 namespace dys {
 
-// int32 -> int16 day columns with range check (days are < 32768)
-__global__ void k_narrow_days(const int32_t* __restrict__ in, int16_t* __restrict__ out, int64_t n, int32_t* bad)
+// int32 day column -> int16 field `field` (0 t_inf, 1 t_q, 2 t_adm) of the agent records, with range check
+__global__ void k_narrow_days(const int32_t* __restrict__ in, AgentRec* __restrict__ rec, int field, int64_t n, int32_t* bad)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t v = in[i];
     if (v < -32768 || v > 32767) atomicOr(bad, 256);
-    out[i] = (int16_t)v;
+    reinterpret_cast<int16_t*>(rec + i)[field] = (int16_t)v;
 }
 
-__global__ void k_widen_days(const int16_t* __restrict__ in, int32_t* __restrict__ out, int64_t n)
+__global__ void k_widen_days(const AgentRec* __restrict__ rec, int field, int32_t* __restrict__ out, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i];
+    if (i < n) out[i] = reinterpret_cast<const int16_t*>(rec + i)[field];
 }
 
 // every index inside its range; t_adm == 0 wherever status is in {1, 2, 6, 7} (contagious3.py:259 keeps that invariant);
@@ -30,21 +30,23 @@ __global__ void k_validate_population(const DevCtx c, int32_t* bad)
     const uint8_t s = c.status[a];
     const bool known = s == ST_S || s == ST_I || s == ST_QH || s == ST_QI || s == ST_D || s == ST_H || s == ST_R || s == ST_X;
     if (!known) atomicOr(bad, 1);
-    if (c.hh[a] < 0 || c.hh[a] >= c.H || c.home[a] < 0 || c.home[a] >= c.B_out || c.sa[a] < -1 || c.sa[a] >= c.S_out) atomicOr(bad, 2);
-    if ((s == ST_S || s == ST_I || s == ST_R || s == ST_X) && c.t_adm[a] != 0) atomicOr(bad, 4);
+    const AgentRec r = c.rec[a];
+    if (c.hh[a] < 0 || c.hh[a] >= c.H || r.home < 0 || r.home >= c.B_out || r.sa < -1 || r.sa >= c.S_out) atomicOr(bad, 2);
+    if ((s == ST_S || s == ST_I || s == ST_R || s == ST_X) && r.t_adm != 0) atomicOr(bad, 4);
     if (c.src[a] < -1 || c.src[a] >= c.n_glob) atomicOr(bad, 8);
     if ((s == ST_S || s == ST_QH) && c.src[a] != -1) atomicOr(bad, 512);
 }
 
 // household / home building / area indices arrive global and are stored relative to the owned ranges
-__global__ void k_localize(int32_t* __restrict__ hh, int32_t* __restrict__ home, int32_t* __restrict__ sa, int64_t n, int32_t hh_lo,
-                           int32_t bld_lo, int32_t area_lo)
+__global__ void k_localize(int32_t* __restrict__ hh, const int32_t* __restrict__ home, const int32_t* __restrict__ sa,
+                           AgentRec* __restrict__ rec, int64_t n, int32_t hh_lo, int32_t bld_lo, int32_t area_lo)
 {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     hh[a] -= hh_lo;
-    home[a] -= bld_lo;
-    if (sa[a] >= 0) sa[a] = sa[a] >= area_lo ? sa[a] - area_lo : -2;     // -2: outside the owned areas -> rejected by validation
+    rec[a].home = home[a] - bld_lo;
+    const int32_t s = sa[a];
+    rec[a].sa = s >= 0 ? (s >= area_lo ? s - area_lo : -2) : s;         // -2: outside the owned areas -> rejected by validation
 }
 
 // household -> members: counts, then (after k_scan_counts) the member lists; order inside a household is irrelevant
@@ -134,8 +136,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
 // column's transposed list (the order inside a list is irrelevant: k_push reduces with max).
 __global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const int64_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ col, const double* __restrict__ val,
-                                                        unsigned long long* __restrict__ cursor, uint32_t* __restrict__ tcolx,
-                                                        double* __restrict__ tval)
+                                                        unsigned long long* __restrict__ cursor, TEdge* __restrict__ tedge)
 {
     const int lane = threadIdx.x & 31;
     const int64_t u = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -156,8 +157,11 @@ __global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const in
             }
         }
         const unsigned long long pos = atomicAdd(&cursor[i - c.rt_lo], 1ull);
-        tcolx[pos] = (uint32_t)u | (cls << CLS_SHIFT);
-        tval[pos] = val[e];
+        TEdge t;
+        t.colx = (uint32_t)u | (cls << CLS_SHIFT);
+        t.pad = 0u;
+        t.val = __dmul_rn(val[e], c.risk[u]);      // contagious3.py:232, first product (both factors are static)
+        tedge[pos] = t;
     }
 }
 

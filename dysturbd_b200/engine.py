@@ -25,7 +25,7 @@ STAT = {name: i for i, name in enumerate(
      "changed"])}
 
 WANT_SA_HIST, WANT_BUILDING_COUNTS, WANT_EVENTS, WANT_IO_MAT, TIME_KERNELS = 1, 2, 4, 8, 16
-BUF_STATUS, BUF_INFECTIOUS, BUF_STATS, BUF_T_INF = 0, 1, 2, 3
+BUF_STATUS, BUF_INFECTIOUS, BUF_STATS, BUF_AGENT_REC = 0, 1, 2, 3
 PEER_HANDLE_BYTES = 128
 
 

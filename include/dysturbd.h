@@ -189,7 +189,8 @@ int dys_sync(dys_handle* h);
 #define DYS_N_KERNELS 3
 int dys_get_kernel_times(dys_handle* h, double* ms_total /* [DYS_N_KERNELS] */, int64_t* launches /* [DYS_N_KERNELS] */);
 /* raw device pointers for zero-copy interop (torch / DLPack / NCCL): which = one of dys_buffer */
-typedef enum { DYS_BUF_STATUS = 0, DYS_BUF_INFECTIOUS = 1, DYS_BUF_STATS = 2, DYS_BUF_T_INF = 3 } dys_buffer;
+/* DYS_BUF_AGENT_REC: [n_pad] 16-byte records {int16 t_inf, t_q, t_adm, pad; int32 area (local), home building (local)} */
+typedef enum { DYS_BUF_STATUS = 0, DYS_BUF_INFECTIOUS = 1, DYS_BUF_STATS = 2, DYS_BUF_AGENT_REC = 3 } dys_buffer;
 int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* bytes);
 int dys_cuda_stream(dys_handle* h, void** stream);
 int64_t dys_device_bytes(const dys_handle* h);

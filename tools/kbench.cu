@@ -12,8 +12,7 @@ __global__ void __launch_bounds__(256) k_stream(const DevCtx c, const int day)
     const int64_t a0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (a0 >= c.n_pad) return;
     const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
-    const short4 ti = *reinterpret_cast<const short4*>(c.t_inf + a0);
-    uint32_t w = sv.x + sv.y + sv.z + sv.w + ti.x;
+    uint32_t w = sv.x + sv.y + sv.z + sv.w + c.rec[a0].t_inf;
     *reinterpret_cast<uint32_t*>(c.ib_wr[0] + a0) = w;
 }
 __global__ void __launch_bounds__(256) k_agent_nofold(const DevCtx c, const int day)
@@ -45,12 +44,13 @@ int main(int argc, char** argv)
         if (rand() / (double)RAND_MAX < frac_inf) { st[a] = ST_I; ti[a] = 18; src[a] = 5; }
     }
     c.status = dalloc<uint8_t>(N); cudaMemcpy(c.status, st.data(), N, cudaMemcpyHostToDevice);
-    c.t_inf = dalloc<int16_t>(N); cudaMemcpy(c.t_inf, ti.data(), 2 * N, cudaMemcpyHostToDevice);
-    c.t_q = dalloc<int16_t>(N); c.t_adm = dalloc<int16_t>(N);
+    {
+        std::vector<AgentRec> rc(N);
+        for (int64_t a = 0; a < N; ++a) rc[a] = AgentRec{ti[a], 0, 0, 0, sa[a], home[a]};
+        c.rec = dalloc<AgentRec>(N); cudaMemcpy(c.rec, rc.data(), sizeof(AgentRec) * N, cudaMemcpyHostToDevice);
+    }
     c.src = dalloc<int32_t>(N); cudaMemcpy(c.src, src.data(), 4 * N, cudaMemcpyHostToDevice);
     int32_t* d; d = dalloc<int32_t>(N); cudaMemcpy(d, hh.data(), 4 * N, cudaMemcpyHostToDevice); c.hh = d;
-    d = dalloc<int32_t>(N); cudaMemcpy(d, home.data(), 4 * N, cudaMemcpyHostToDevice); c.home = d;
-    d = dalloc<int32_t>(N); cudaMemcpy(d, sa.data(), 4 * N, cudaMemcpyHostToDevice); c.sa = d;
     c.risk = dalloc<double>(N); c.p_adm = dalloc<double>(N); c.p_death = dalloc<double>(N);
     c.pdf = dalloc<double>(64);
     DayBuffers buf{};
@@ -90,8 +90,9 @@ int main(int argc, char** argv)
                 tc[(size_t)i * D + k] = (uint32_t)u | ((rand() % 5 == 0 ? 1u : 0u) << 28);
             }
         int64_t* dp = dalloc<int64_t>(N + 1); cudaMemcpy(dp, tp.data(), 8 * (N + 1), cudaMemcpyHostToDevice); c.tptr = dp;
-        uint32_t* dc = dalloc<uint32_t>(tc.size()); cudaMemcpy(dc, tc.data(), 4 * tc.size(), cudaMemcpyHostToDevice); c.tcolx = dc;
-        double* dv = dalloc<double>(tv.size()); cudaMemcpy(dv, tv.data(), 8 * tv.size(), cudaMemcpyHostToDevice); c.tval = dv;
+        std::vector<TEdge> te((size_t)N * D + 4);
+        for (size_t e = 0; e < (size_t)N * D; ++e) { te[e].colx = tc[e]; te[e].pad = 0; te[e].val = tv[e] * 0.1; }
+        TEdge* de = dalloc<TEdge>(te.size()); cudaMemcpy(de, te.data(), sizeof(TEdge) * te.size(), cudaMemcpyHostToDevice); c.tedge = de;
         std::vector<double> rk(N, 0.1); cudaMemcpy((void*)c.risk, rk.data(), 8 * N, cudaMemcpyHostToDevice);
         std::vector<double> pdf(64, 0.1); cudaMemcpy((void*)c.pdf, pdf.data(), 8 * 64, cudaMemcpyHostToDevice);
         c.norm_factor = 1e-6;       // Bernoulli successes are rare: the mailbox stays (almost) untouched between launches
