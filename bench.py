@@ -11,8 +11,9 @@ A step is one simulated day (one pass of contagious3.py:176-366) over the whole 
 `e2e`    : the same K days through the C ABI the way the reference-facing host loop uses it: every day the open
            flags come from pinned host memory and the day's outputs (stats, per-area histograms, per-building counts,
            infection events) are read back to host memory.
-`roofline`: the slower of the two day kernels (k_push / k_agent) -- algorithmic bytes per launch from the day's own work counters
-           (formula in DESIGN.md) over its mean CUDA-event duration, against MEASURED_PEAKS.json.
+`roofline`: k_days (the fused day kernel) -- algorithmic bytes per simulated day from the day's own work counters
+           (formula in DESIGN.md) over its mean duration (CUDA events around the resident pass), against
+           MEASURED_PEAKS.json; `survey_8d` evaluates SURVEY.md 8(d)'s formula with the same counters.
 `cpu_baseline`: the C oracle (OpenMP) on the same population, a bounded sample of days, rank 0 / N=1 only.
 """
 import argparse
@@ -132,27 +133,39 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def kernel_bytes(N, st, prev):
-    """Algorithmic bytes one launch of each day kernel must move (DESIGN.md 'bytes per launch'), from the day's own
+def kernel_bytes(N, st, prev, window=7):
+    """Algorithmic bytes one simulated day must move in this design (DESIGN.md 'bytes per day'), from the day's own
     counters: each needed datum once, at its stored width.  `st` = today's stats block, `prev` = yesterday's (its
     end-of-day status counts are today's day-start counts)."""
     from dysturbd_b200.engine import STAT
     g = lambda k: int(st[STAT[k]])
     S0, I0, QH0, QI0, D0, H0, R0, X0 = (int(x) for x in prev[20:28])
-    inf0 = g("inf0")
-    # k_push: the snapshot byte of every agent, then only the transposed rows of today's infectious agents
-    push = N * 1 + inf0 * 16 + g("edges_scanned") * (4 + 1) + g("exposed") * (8 + 8) + g("hits") * 4
-    # k_agent: status in, snapshot byte out, and the columns each status needs
-    ever0 = I0 + QI0 + D0 + H0 + R0 + X0
-    agent = N * (1 + 1)                          # status read, tomorrow's snapshot byte written
-    agent += ever0 * 2                           # t_inf of everyone ever infected (rules of E, histogram)
-    agent += (QH0 + QI0 + D0) * 2 + H0 * 2       # t_q of the quarantined, t_adm of the hospitalised
-    agent += (S0 + QH0) * 4                      # the infector mailbox of every susceptible
-    if g("new_diag") or g("daily_quar"):         # F ran: household index + flag byte of everyone who can be quarantined
-        agent += (S0 + QH0 + I0 + QI0) * (4 + 1)
-    agent += g("changed") * 1 + g("n_events") * (2 + 8) + g("daily_quar") * 2
-    agent += int(st[32:53].sum()) * (4 + 4)      # area index + histogram bin of the recently infected
+    rows = g("inf0")
+    # push: the row extent of every infectious agent, its kept network entries (16-byte records), a mailbox + attention
+    # byte per success; the snapshot bytes are only scanned on the first day of a window
+    push = rows * 16 + g("edges_scanned") * 16 + g("hits") * (4 + 4 + 1) + N // window
+    # agent: status + attention byte of everybody; the 16-byte record half of every agent that is not idle; state writes
+    listed = I0 + QI0 + D0 + H0 + X0 + QH0 + g("hits") + g("daily_quar")
+    agent = N * (1 + 1) + listed * 16
+    agent += g("changed") * (1 + 2) + g("n_events") * (8 + 4) + g("daily_quar") * 2
+    agent += int(st[32:53].sum()) * 4 + (I0 + QI0 + D0) * 4      # per-area histogram bin, per-building count
+    agent += 2 * N // window                                    # tomorrow's snapshot bytes: last day of a window only
     return {"k_push": push, "k_agent": agent}
+
+
+def survey_8d_bytes(N, st, prev, mean_degree):
+    """SURVEY.md section 8(d)'s per-day byte formula (a straightforward pull over compact SoA columns), evaluated with
+    the same counters -- what the PROBLEM would cost an implementation that re-reads routines and gates rows every day."""
+    from dysturbd_b200.engine import STAT
+    g = lambda k: int(st[STAT[k]])
+    S0, I0, QH0, QI0, D0, H0, R0, X0 = (int(x) for x in prev[20:28])
+    n_live = S0 + I0 + QH0 + QI0 + D0
+    e_scanned = int(g("inf0") * mean_degree)                     # every interaction_prob non-zero of an infectious agent
+    u_gated = min(S0 + QH0, g("exposed"))
+    b = N * 2 + N * 6 + n_live * 40 + (I0 + QI0 + D0) * 8 + H0 * 8 + u_gated * 16 + e_scanned * 12
+    b += N * 4 if (g("new_diag") or g("daily_quar")) else 0
+    b += N * 6 + g("changed") * 11
+    return b
 
 
 def run_ours(args):
@@ -234,12 +247,13 @@ def run_ours(args):
     st_last = raw(eng).stats(W + K - 1)
 
     # ---- pass 2: end to end through the C ABI with host buffers (`e2e`) ----
-    # The host loop of dysturbd_b200/host.py (EpidemicModel.run): days are queued in windows of 3 with two windows in
-    # flight (exact for every scenario: the lockdown decision lags 7 days, contagious3.py:306-309).  Every window the
-    # open flags of its days are offered from pinned host memory (dys_step_many -> dys_set_open; an unchanged vector is
-    # elided inside the library) and every day's whole output block (stats, per-area histograms, per-building counts,
-    # infection events) is read on the host from the pinned ring the library copied it into.
-    WIN = 3
+    # The host loop of dysturbd_b200/host.py (EpidemicModel.run): days are queued in windows with two windows in flight
+    # (week-long for a scenario that closes nothing, as here; (diagnosis + 1) // 2 = 4 days under a lockdown scenario,
+    # whose decision lags `diagnosis` days, contagious3.py:306-309).  Every window the open flags of its days are offered
+    # from pinned host memory (dys_step_many compares them with the vector in force and only transfers a changed one) and
+    # every day's whole output block (stats, per-area histograms, per-building counts, infection events) is read on the
+    # host from the pinned ring the library copied it into.
+    WIN = 7
     eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
     open_pinned = torch.ones((WIN, pop.B), dtype=torch.uint8).pin_memory()
     h2d = d2h = 0
@@ -305,9 +319,11 @@ def run_ours(args):
         ms_k, n_k = raw(eng_t).kernel_times()
     prev = prev_w if prev_w is not None and world == 1 else stats_days[0]
     kb = {"k_push": 0, "k_agent": 0}
+    survey_bytes = 0
     for st in stats_days:                   # the e2e pass ran the same days from the same state: same counters
         for k, v in kernel_bytes(n_total, st, prev).items():
             kb[k] += v // world             # counters are global after the all-reduce; a rank moves its share
+        survey_bytes += survey_8d_bytes(n_total, st, prev, pop.nnz / pop.N) // world
         prev = st
     eng_t.close()
     clocks.stop()
@@ -326,7 +342,7 @@ def run_ours(args):
                                 "achieved_gbs": kb[name] / K / (ms * 1e-3) / 1e9}
     # the product path runs a window of days as ONE cooperative launch (k_days = push_body + agent_body per day): its
     # per-day duration is the resident pass above (CUDA events on the launching stream), its bytes the two bodies' sum
-    dom = "k_days (per simulated day; k_push + k_agent bodies fused, one cooperative launch per 7 days)"
+    dom = "k_days (per simulated day: agent pass + push of the block's own frontier, one grid barrier; one cooperative launch per 7 days)"
     k_ms = ms_value / K
     kbytes = sum(kb.values())
     achieved = kbytes / K / (k_ms * 1e-3) / 1e9
@@ -353,15 +369,26 @@ def run_ours(args):
             "load_seconds": load_s,
         },
         "e2e": {"value": n_total * K / s_e2e, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-                "ms_per_step": s_e2e * 1e3 / K},
+                "ms_per_step": s_e2e * 1e3 / K,
+                "h2d_note": "the only per-day input of this path is the building open-flag vector (%d bytes), offered every "
+                            "day from pinned host memory and transferred when it differs from the one in force -- never "
+                            "under noLockdown; the population is resident by construction (it is the simulation state)" % pop.B},
         "gpu_launches": -(-K // 7),  # one cooperative k_days launch per 7-day window (k_snapshot only after a load)
         "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms, "per_kernel": per_kernel,
-                     "traffic_note": "ncu dram bytes of k_days = 8.6-9.4 MB per simulated day on days 8-21, equal to the "
-                                     "algorithmic bytes of those days (profiles/r01h_summary.md)"},
+                     "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms,
+                     "note": "algorithmic bytes = what THIS design must move per day (bench.py kernel_bytes, DESIGN.md); a "
+                             "1 M-agent day is a chain of dependent memory round trips and one grid barrier, not a bandwidth "
+                             "problem -- see profiles/ for the per-phase trace",
+                     "survey_8d": {"bytes_per_day": survey_bytes / max(1, K),
+                                   "achieved": survey_bytes / max(1, K) / (k_ms * 1e-3) / 1e9,
+                                   "frac": survey_bytes / max(1, K) / (k_ms * 1e-3) / 1e9 / peak if peak else None,
+                                   "what": "SURVEY.md 8(d)'s per-day formula (daily routine rows, gated pull over every "
+                                           "interaction_prob non-zero) with the same counters: the bytes the problem costs a "
+                                           "straightforward SoA pull, which this design avoids moving"},
+                     "per_kernel_standalone": per_kernel},
         "clocks": clocks.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -37,7 +37,7 @@ struct dys_handle {
     int64_t dev_bytes = 0;
     std::string err;
     bool have_pop = false, have_graph = false, begun = false;
-    int64_t nnz = 0;
+    int64_t nnz = 0, nnz_kept = 0;
     int32_t last_day = -1;
     int64_t steps = 0;
     // per-parity device output block [stats | sa_hist | bcount | events] and the pinned host ring it is copied into
@@ -223,6 +223,11 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_days, k_days, 256, 0) == cudaSuccess && per_sm_days > 0)
             h->days_grid = per_sm_days * sms;
     }
+    if (rc == DYS_OK && h->days_grid > 1)
+        for (int k = 0; k < 2; ++k) {      // the daily equal-work cut of k_days (see plan_cut)
+            A(dev_alloc(h, &h->buf.bounds[k], h->days_grid + 1));
+            A(dev_alloc(h, &h->buf.piece_work[k], c.n_pad / 128));
+        }
     A(dev_alloc(h, &h->d_open_ring, (int64_t)MAX_FUSED_DAYS * c.B));
     A(dev_alloc(h, &h->d_barrier, 4));
     if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open_ring, (size_t)MAX_FUSED_DAYS * (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -285,6 +290,17 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaMemsetAsync(h->buf.df, 0, sizeof(int32_t) * DF_RING * DF_LEN, h->stream));
     CK(h, cudaMemsetAsync(h->buf.part, 0, sizeof(unsigned long long) * PART_RING * N_SLOTS * N_STATS, h->stream));
     CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
+    if (h->buf.bounds[0]) {      // until measured costs exist the blocks of k_days get equal runs of pieces
+        const int n_work = h->days_grid - 1;
+        const int64_t n_pieces = c.n_pad / 128, per = (n_pieces + n_work - 1) / n_work;
+        std::vector<int32_t> cut((size_t)n_work + 1);
+        for (int b = 0; b <= n_work; ++b) cut[(size_t)b] = (int32_t)((int64_t)b * per < n_pieces ? (int64_t)b * per : n_pieces);
+        for (int k = 0; k < 2; ++k) {
+            CK(h, cudaMemcpyAsync(h->buf.bounds[k], cut.data(), sizeof(int32_t) * cut.size(), cudaMemcpyHostToDevice, h->stream));
+            CK(h, cudaMemsetAsync(h->buf.piece_work[k], 0, sizeof(uint32_t) * (size_t)n_pieces, h->stream));
+        }
+        CK(h, cudaStreamSynchronize(h->stream));      // `cut` leaves scope
+    }
     h->ib_day = -1;
     h->begun = false;
     CK(h, cudaMemsetAsync(h->d_peer_flags, 0xFF, sizeof(int32_t) * 8, h->stream));   // -1: nothing complete yet
@@ -304,7 +320,8 @@ static int check_bad(dys_handle* h, const char* what)
         CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int32_t), h->stream));
         return fail(h, DYS_ERR_RANGE, "%s: invalid input (flags 0x%x: 1 status code, 2 hh/home/sa index, 4 t_adm != 0 for a "
                     "never-admitted status, 8 src index, 16 routine building index, 32 rowptr not monotone, 64 column index, "
-                    "128 columns not strictly ascending, 256 day out of int16 range, 512 susceptible agent with an infector)", what, bad);
+                    "128 columns not strictly ascending, 256 day out of int16 range, 512 susceptible agent with an infector, "
+                    "1024 household with more than 32767 members)", what, bad);
     }
     return DYS_OK;
 }
@@ -379,11 +396,14 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
             k_count_members<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c.hh, c.n_loc, d_cnt);
             k_scan_counts<<<1, 1024, 0, h->stream>>>(d_cnt, c.H, (int64_t*)c.hh_ptr, d_cursor);
             k_fill_members<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c.hh, c.n_loc, d_cursor, (int32_t*)c.hh_mem);
+            k_pack_records<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c.hh, c.hh_ptr, c.p_adm, c.rec, c.n_loc, h->d_bad);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         cudaFree(d_cnt); cudaFree(d_cursor);
         if (e != cudaSuccess) return fail(h, DYS_ERR_CUDA, "building the household index failed: %s", cudaGetErrorString(e));
+        rc = check_bad(h, "dys_load_population");
+        if (rc != DYS_OK) return rc;
     }
     h->have_pop = true;
     h->have_graph = false;
@@ -451,15 +471,21 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
     int64_t* d_tptr = nullptr;
     TEdge* d_tedge = nullptr;
     if (rc == DYS_OK) rc = dev_alloc(h, &d_tptr, c.rt_n + 1);
-    if (rc == DYS_OK) rc = dev_alloc(h, &d_tedge, nnz + 4);
     if (rc == DYS_OK) {
-        k_validate_graph_count<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(d_rowptr, d_col, c.n_loc, c.rt_lo, c.rt_lo + c.rt_n,
-                                                                             d_cnt, h->d_bad);
+        k_validate_graph_count<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_rowptr, d_col, d_cnt, h->d_bad);
         rc = check_bad(h, "dys_load_graph");
     }
     if (rc == DYS_OK) {
         // transpose: column counts -> offsets -> scatter with the static shared-building class of each pair
         k_scan_counts<<<1, 1024, 0, h->stream>>>(d_cnt, c.rt_n, d_tptr, d_cursor);
+        int64_t kept = 0;      // the non-zeros whose pair can ever share a building
+        if (cudaMemcpyAsync(&kept, d_tptr + c.rt_n, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess)
+            rc = fail(h, DYS_ERR_CUDA, "dys_load_graph: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc == DYS_OK) rc = dev_alloc(h, &d_tedge, kept + 4);
+        h->nnz_kept = kept;
+    }
+    if (rc == DYS_OK) {
         k_fill_transpose<<<grid_for(c.n_loc * 32, 256), 256, 0, h->stream>>>(c, d_rowptr, d_col, d_val, d_cursor, d_tedge);
         if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
             rc = fail(h, DYS_ERR_CUDA, "building the transposed network failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -573,7 +599,7 @@ static int run_snapshot(dys_handle* h, int32_t day)
     CK(h, cudaMemsetAsync(h->buf.att[day & 1], 0, (size_t)c.n_pad + 16, h->stream));
     CK(h, cudaMemsetAsync(h->buf.qflag[day % Q_RING], 0, (size_t)c.H + 16, h->stream));
     CK(h, cudaMemsetAsync(h->buf.df + (day & (DF_RING - 1)) * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
-    bind_day(c, h->buf, day);
+    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     bind_ib_targets(c, h->buf, day & 1);
     k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     if (h->n_peers > 1) {
@@ -581,7 +607,7 @@ static int run_snapshot(dys_handle* h, int32_t day)
         k_signal<<<1, 32, 0, h->stream>>>(c, day);
     }
     CK(h, cudaGetLastError());
-    bind_day(c, h->buf, day);
+    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     h->ib_day = day;
     return DYS_OK;
 }
@@ -622,7 +648,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     }
     if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
     bind_peers(h);
-    bind_day(c, h->buf, day);
+    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     tick(h, 0);
     if (h->ib_day != day || (inj && inj->u_adm)) {
         // first day after a load / set_state, a skipped day, or injected admission draws (tomorrow's diagnoses cannot
@@ -674,7 +700,7 @@ static int step_end(dys_handle* h, int32_t day)
     c.ev = (h->p.flags & DYS_WANT_EVENTS) ? (int2*)(h->d_out[slot] + h->off_ev) : nullptr;
     h->last_slot = slot;
     bind_peers(h);
-    bind_day(c, h->buf, day);
+    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     k_push<<<(unsigned)h->push_grid, BLOCK, 0, h->stream>>>(c, day);
     tick(h, 2);
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
@@ -744,7 +770,7 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     CK(h, cudaMemsetAsync(h->d_barrier, 0, 2 * sizeof(unsigned int), h->stream));
     unsigned int* bar = h->d_barrier;
     void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
-    const size_t trace_words = (size_t)MAX_FUSED_DAYS * (size_t)h->days_grid * 8;
+    const size_t trace_words = (size_t)MAX_FUSED_DAYS * (size_t)h->days_grid * TRACE_SLOTS;
     if (h->trace_path && h->trace_path[0]) {
         if (!h->d_trace) { rc = dev_alloc(h, &h->d_trace, (int64_t)trace_words); if (rc != DYS_OK) return rc; }
         plan.trace = h->d_trace;
@@ -757,8 +783,10 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         if (FILE* f = fopen(h->trace_path, "a")) {
             for (int k = 0; k < n_days; ++k)
                 for (int b = 0; b < h->days_grid; ++b) {
-                    const unsigned long long* t = &tr[((size_t)k * h->days_grid + b) * 8];
-                    fprintf(f, "%d %d %llu %llu %llu %llu %llu %llu %llu %llu\n", first_day + k, b, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+                    const unsigned long long* t = &tr[((size_t)k * h->days_grid + b) * TRACE_SLOTS];
+                    fprintf(f, "%d %d", first_day + k, b);
+                    for (int i = 0; i < TRACE_SLOTS; ++i) fprintf(f, " %llu", t[i]);
+                    fprintf(f, "\n");
                 }
             fclose(f);
         }

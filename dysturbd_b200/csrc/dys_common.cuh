@@ -57,15 +57,21 @@ constexpr int Q_RING = 3, PART_RING = 3;         // quirk household flags and pa
 // bit1 "somebody of your household is diagnosed today" (contagious3.py:263).  An agent whose byte is 0 and who is
 // susceptible (or long recovered) cannot change today: the sweep of agent_body reads two bytes for it and moves on.
 constexpr uint32_t ATT_HIT = 1u, ATT_HH = 2u;
+constexpr int TRACE_SLOTS = 12;                  // developer tracing (DYS_TRACE): timestamps per block and day
 
-// Everything the settle phase needs about one agent besides its status byte, in ONE 16-byte record: a divergent
-// gather costs the load/store unit one pass per distinct 32-byte sector, so four 2- and 4-byte columns cost four times
-// what this record does.
+// Everything the settle phase needs about one agent besides its status byte, in ONE 32-byte record = one memory sector:
+// a gather costs a round trip per dependent access and a sector per distinct column, so the agent's days in state, its
+// area, home building, household (with where its members are listed) and admission probability arrive together.
 struct __align__(16) AgentRec {
-    int16_t t_inf, t_q, t_adm, pad;      // agents[:,16], agents[:,19], agents[:,24] (contagious3.py:115-118); 0 = never
+    int16_t t_inf, t_q, t_adm;           // agents[:,16], agents[:,19], agents[:,24] (contagious3.py:115-118); 0 = never
+    int16_t hh_size;                     // members of the agent's household ...
     int32_t sa;                          // statistical area (local to the owned areas), -1 = none
     int32_t home;                        // home building (local to the owned buildings)
+    int32_t hh;                          // household (local to the owned households)
+    int32_t hh_slot;                     // ... listed at hh_mem[hh_slot .. hh_slot + hh_size)
+    double p_adm;                        // agents[:,23]
 };
+static_assert(sizeof(AgentRec) == 32, "one sector");
 
 struct DevCtx {
     int64_t n_loc, n_pad, n_glob, lo;    // owned agents, padded count (multiple of 1024), global agents, first owned
@@ -105,6 +111,7 @@ struct DevCtx {
     // agent pass of day d writes tomorrow's bytes of the owned agents into buffer (d+1)&1
     const uint8_t* ib_rd;
     uint8_t* ib_wr[8];                   // [n_wr] write targets (own buffer first; peers' buffers are written by publish_body)
+    int32_t write_ib;                    // 0: nobody will scan tomorrow's bytes (a middle day of a single-GPU k_days window)
     const uint8_t* open;                 // [B]
     int32_t n_closed;                    // closed buildings today (counted on the host)
     uint8_t *att, *att_next;             // [n_pad] attention bytes of this day / of tomorrow
@@ -118,6 +125,10 @@ struct DevCtx {
     int32_t* bcount;                     // [B_out] or null
     int2* ev;                            // [n_pad] today's (infected, infector) pairs, or null
     int32_t* io_mat;                     // [S * S] or null
+    // k_days only: the agents are dealt to the blocks in contiguous runs of 128-agent pieces, re-cut every day so that
+    // every block gets the same MEASURED work (the epidemic is never evenly spread over the population)
+    const int32_t* bounds;               // [n_work + 1] today's cut, or null (equal runs)
+    uint32_t* piece_work;                // [n_pad / 128] today's cost of each piece, written by the sweep, or null
     const double *u_adm, *u_death, *u_pair;   // injected draws or null
     double* pair_prob;                   // [n_glob^2] or null (tests)
 };
@@ -131,6 +142,8 @@ struct DayBuffers {
     unsigned long long* part;            // [PART_RING][N_STATS][N_SLOTS]
     uint8_t* ib[2];                      // own snapshot buffers by day parity
     uint8_t* peer_ib[8][2];              // peer mode: every rank's, by day parity
+    int32_t* bounds[2];                  // k_days: the cut of day d is bounds[d & 1] (made from the work of day d - 2), or null
+    uint32_t* piece_work[2];             // k_days: the piece costs measured on day d are piece_work[d & 1]
 };
 
 // where snapshot bytes of parity `parity` are written: the own buffer, then (peer mode) every other rank's
@@ -150,7 +163,9 @@ __host__ __device__ __forceinline__ void bind_day(DevCtx& c, const DayBuffers& b
     c.qflag = b.qflag[day % Q_RING]; c.qflag_next = b.qflag[(day + 1) % Q_RING];
     c.df = b.df + (day & (DF_RING - 1)) * DF_LEN; c.df_next = b.df + ((day + 1) & (DF_RING - 1)) * DF_LEN;
     c.part = b.part + (size_t)(day % PART_RING) * N_STATS * N_SLOTS;
+    c.bounds = b.bounds[p]; c.piece_work = b.piece_work[p];
     c.ib_rd = b.ib[p];
+    c.write_ib = 1;
     bind_ib_targets(c, b, p ^ 1);        // the agent pass of `day` writes tomorrow's snapshot bytes
 }
 

@@ -18,18 +18,21 @@
 //
 // All of it is HBM/L2-bound integer and byte work; there is no dense contraction, hence no tensor-core path.
 #pragma once
+#include <cstddef>
+
 #include "dys_common.cuh"
 
 namespace dys {
 
 // Will agent a (day-start status st, infection day tinf) be among `new_diagnosed_agents` (contagious3.py:261) on
 // `day`?  Yes iff it is infectious, day - tinf == diagnosis (rule :254 fires) and phase B does not hospitalise it first.
-__device__ __forceinline__ bool diagnosed_on(const DevCtx& c, const double* u_adm, int64_t a, uint32_t st, int tinf, int day)
+__device__ __forceinline__ bool diagnosed_on(const DevCtx& c, const double* u_adm, int64_t a, uint32_t st, int tinf, int day,
+                                             const double p_adm)
 {
     if (!in_set(M_INF, st) || day - tinf != c.diagnosis) return false;
     if (tinf >= c.adm_min && tinf <= c.adm_max) {
         const double u = draw(u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
-        if (__ldg(c.p_adm + a) > u) return false;
+        if (p_adm > u) return false;
     }
     return true;
 }
@@ -41,10 +44,10 @@ __device__ __forceinline__ void att_or(uint8_t* att, int64_t a, uint32_t bit)
 
 // agent a is diagnosed on the day the three targets belong to: every member of its household gets the attention bit
 // (contagious3.py:263-265), the quirk households of :267 are flagged, and the day is marked as having a diagnosis
-__device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, uint8_t* att, uint8_t* qflag, int32_t* df)
+__device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, int hh_slot, int hh_size, uint8_t* att, uint8_t* qflag,
+                                                int32_t* df)
 {
-    const int h = __ldg(c.hh + a);
-    for (int64_t t = __ldg(c.hh_ptr + h); t < __ldg(c.hh_ptr + h + 1); ++t) att_or(att, __ldg(c.hh_mem + t), ATT_HH);
+    for (int t = 0; t < hh_size; ++t) att_or(att, __ldg(c.hh_mem + hh_slot + t), ATT_HH);
     if (c.trig_ptr)
         for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) qflag[c.trig_hh[t]] = 1;   // same-value byte stores
     df[DF_ANY_ND] = 1;
@@ -58,25 +61,19 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BLOCK = 256, WARPS = BLOCK / 32;
 constexpr int FCAP = 4096;                         // frontier entries: index relative to the block's base | snapshot byte << 24
-constexpr int LCAP = 2048;                         // agent work list = one batch of the sweep (2 x 4 agents per thread)
+constexpr int LCAP = 2048;                         // one batch of the sweep (2 x 4 agents per thread) adds at most this many
+constexpr int LTOT = 4096;                         // agent work list: batches accumulate until the next one might not fit
 constexpr uint32_t REL_MASK = 0x00FFFFFFu;
 
-// where a block's queued agents live: contiguous from `base` (scan push), or in pieces of 128 agents dealt round-robin
-// to the blocks (agent pass: piece q belongs to block q % stride and is that block's slot q / stride)
+// where a block's queued agents live: halo-relative index = base + rel
 struct FrontMap {
     int64_t base;
-    int stride, blk;
-    __device__ __forceinline__ int64_t at(uint32_t rel) const
-    {
-        return stride ? base + ((int64_t)(rel >> 7) * stride + blk) * 128 + (rel & 127u) : base + rel;
-    }
+    __device__ __forceinline__ int64_t at(uint32_t rel) const { return base + rel; }
 };
 
-constexpr int PUSH_PCAP = 256;
 struct PushWarpScratch {
     int off[36];                                   // exclusive prefix of the expanded rows' lengths
     int64_t t0[32];
-    unsigned long long pairs[PUSH_PCAP];           // pairs awaiting their Bernoulli: entry | row << 48 | flags << 56
 };
 
 enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS, EV_CHANGED, EV_LEN };
@@ -84,7 +81,7 @@ enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS
 struct BlockScratch {
     uint32_t front[FCAP];
     union {
-        uint32_t list[LCAP];                       // local index | status << 24 | attention << 28
+        uint32_t list[LTOT];                       // local index | status << 24 | attention << 28
         PushWarpScratch pw[WARPS];
     };
     double pdf[64];
@@ -111,7 +108,6 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
                                               unsigned int (&cnt)[4])
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     PushWarpScratch& w = sm.pw[wid];
     const int n = (int)sm.n_front;
     const bool any_closed = c.n_closed != 0;
@@ -119,43 +115,6 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
     rpg = rpg < 1 ? 1 : (rpg > 32 ? 32 : rpg);
     const int n_groups = (n + rpg - 1) / rpg;
     const uint4* edges = reinterpret_cast<const uint4*>(c.tedge);
-
-    // settle the first np queued pairs of this warp, one pair per lane: probability, Bernoulli, mailbox.  The Philox
-    // rounds are the expensive part of a push; they run on full warps because the pairs were compacted first.
-    auto settle = [&](const int q0, const int np) {
-        for (int k0 = 0; k0 < np; k0 += 32) {
-            const int k = k0 + lane;
-            if (k >= np) continue;
-            const unsigned long long q = w.pairs[k];
-            const int r = (int)((q >> 48) & 0x3Fu);
-            const uint32_t fl = (uint32_t)(q >> 56);                    // bit0 valid if u moves freely, bit1 valid if u is isolated
-            const uint4 rec = __ldg(edges + (int64_t)(q & 0xFFFFFFFFFFFFull));   // fetched a moment ago: an L1 hit
-            const uint32_t fe = sm.front[q0 + r];
-            const uint32_t ul = rec.x & COL_MASK, ib_i = fe >> 24;
-            const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe & REL_MASK);
-            bool ok_free = fl & 1u, ok_iso = (fl & 2u) != 0;
-            if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
-                const bool iso_i = (ib_i & IB_ISO) != 0;
-                if (ok_free) ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
-                if (ok_iso) ok_iso = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
-                if (!ok_free && !ok_iso) continue;
-            }
-            ++cnt[2];
-            // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
-            // rounded separately (no add follows, so no FMA can form); the first product comes with the record
-            double p = __dmul_rn(__hiloint2double((int)rec.w, (int)rec.z), sm.pdf[ib_i & IB_DAYS]);
-            p = __dmul_rn(p, c.norm_factor);
-            if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
-            const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
-            if (p > u) {                                                           // :240, :248
-                ++cnt[3];
-                if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
-                if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
-                att_or(c.att, ul, ATT_HIT);
-            }
-        }
-        __syncwarp();
-    };
 
     for (int g = wid; g < n_groups; g += WARPS) {
         const int q0 = g * rpg;
@@ -179,13 +138,14 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
         w.t0[lane] = t0;
         __syncwarp();
         cnt[0] += len;
-        int np = 0;                                        // queued pairs (warp-uniform)
-        for (int f0 = 0; f0 < total; f0 += 128) {
-            int r[4];
-            int64_t e[4];
-            uint32_t cx[4], st_u[4];
+        // two entries per lane and step: every entry of the transposed network can be exposed (the others were left
+        // out at load time), so nearly every lane draws its Bernoulli and the Philox rounds run on full warps
+        for (int f0 = 0; f0 < total; f0 += 64) {
+            int r[2];
+            uint4 rec[2];
+            uint32_t st_u[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 const int f = f0 + 32 * k + lane;
                 int lo = 0, hi = 32;                       // off[lo] <= f < off[hi]; the last such lo is the row
 #pragma unroll
@@ -194,25 +154,26 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
                     if (w.off[mid] <= f) lo = mid; else hi = mid;
                 }
                 r[k] = lo;
-                e[k] = w.t0[lo] + (f - w.off[lo]);
-                // the whole 16-byte record comes in (the value is used when the pair is settled); class 0 = padding lane
-                cx[k] = f < total ? __ldg(edges + e[k]).x : 0u;
+                rec[k] = make_uint4(0u, 0u, 0u, 0u);       // class 0: a padding lane never passes the exposure test
+                if (f < total) rec[k] = __ldg(edges + (w.t0[lo] + (f - w.off[lo])));
             }
             if (CHECK) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[cx[k] & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
+                for (int k = 0; k < 2; ++k)
+                    st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[rec[k].x & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // the cheap part of the exposure test: static class x today's isolation; survivors are queued
-                const uint32_t cls = cx[k] >> CLS_SHIFT;
-                const bool iso_i = (sm.front[q0 + r[k]] >> 24) & IB_ISO;
+            for (int k = 0; k < 2; ++k) {
+                // the exposure test: static class x today's isolation
+                const uint32_t fe = sm.front[q0 + r[k]];
+                const uint32_t cls = rec[k].x >> CLS_SHIFT, ib_i = fe >> 24;
+                const bool iso_i = (ib_i & IB_ISO) != 0;
                 const bool x_iso = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i);                      // u isolated at home
                 const bool x_free = x_iso | ((cls & CLS_OH) != 0) | ((cls & CLS_OO) && !iso_i);      // u moves freely
-                bool ok_free, ok_iso;
+                bool ok_free, ok_iso, iso_u = false;
                 if (CHECK) {
-                    const bool sus = in_set(M_SUS, st_u[k]), iso_u = (st_u[k] == ST_QH);
+                    const bool sus = in_set(M_SUS, st_u[k]);
+                    iso_u = (st_u[k] == ST_QH);
                     cnt[1] += sus;
                     ok_free = sus && !iso_u && x_free;
                     ok_iso = sus && iso_u && x_iso;
@@ -221,17 +182,35 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
                     ok_free = x_free;
                     ok_iso = x_iso;
                 }
-                const bool ex = ok_free || ok_iso;
-                const unsigned m = __ballot_sync(0xffffffffu, ex);
-                if (ex)
-                    w.pairs[np + __popc(m & lt_mask)] = (unsigned long long)e[k] | ((unsigned long long)r[k] << 48) |
-                                                        ((unsigned long long)((ok_free ? 1u : 0u) | (ok_iso ? 2u : 0u)) << 56);
-                np += __popc(m);
+                if (!ok_free && !ok_iso) continue;
+                const uint32_t ul = rec[k].x & COL_MASK;
+                const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe & REL_MASK);
+                if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
+                    if (CHECK) {
+                        const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
+                        ok_free = ok_free && ok;
+                        ok_iso = ok_iso && ok;
+                    } else {
+                        ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
+                        ok_iso = ok_iso && exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
+                    }
+                    if (!ok_free && !ok_iso) continue;
+                }
+                ++cnt[2];
+                // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
+                // rounded separately (no add follows, so no FMA can form); the first product comes with the record
+                double p = __dmul_rn(__hiloint2double((int)rec[k].w, (int)rec[k].z), sm.pdf[ib_i & IB_DAYS]);
+                p = __dmul_rn(p, c.norm_factor);
+                if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+                const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
+                if (p > u) {                                                           // :240, :248
+                    ++cnt[3];
+                    if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
+                    if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
+                    att_or(c.att, ul, ATT_HIT);
+                }
             }
-            __syncwarp();
-            if (np > PUSH_PCAP - 128) { settle(q0, np); np = 0; }
         }
-        if (np > 0) settle(q0, np);
         __syncwarp();
     }
 }
@@ -255,11 +234,12 @@ __device__ __forceinline__ void publish_push_counters(const DevCtx& c, BlockScra
 }
 
 // the block's contiguous share [lo, hi) of n items, in granules of 16
-__device__ __forceinline__ void block_share(const int64_t n, const int n_blocks, int64_t& lo, int64_t& hi)
+__device__ __forceinline__ void block_share(const int64_t n, const int n_blocks, const int wb, int64_t& lo, int64_t& hi)
 {
+    if (wb < 0) { lo = hi = 0; return; }
     int64_t span = (n + n_blocks - 1) / n_blocks;
     span = (span + 15) & ~(int64_t)15;
-    lo = (int64_t)blockIdx.x * span;
+    lo = (int64_t)wb * span;
     hi = lo + span;
     if (lo > n) lo = n;
     if (hi > n) hi = n;
@@ -269,7 +249,8 @@ __device__ __forceinline__ void block_share(const int64_t n, const int n_blocks,
 // push_scan_body: the push of `day` with the frontier found by scanning the snapshot bytes (c.ib_rd) of the halo
 // agents.  Every block scans a contiguous share, 1024 bytes a step (the next step's word already in flight).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks)
+// wb = the block's index among the n_blocks working blocks (-1: a block without a share)
+__device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     push_clear_duties(c);
@@ -281,7 +262,7 @@ __device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, B
     // halo-relative agents [r0, r1): r0 is a multiple of 1024
     auto scan = [&](const int64_t r0, const int64_t r1) {
         int64_t lo, hi;
-        block_share(r1 - r0, n_blocks, lo, hi);
+        block_share(r1 - r0, n_blocks, wb, lo, hi);
         lo += r0; hi += r0;
         int64_t base = lo;
         const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib_rd + c.rt_lo);   // rt_lo is a multiple of 1024
@@ -319,7 +300,7 @@ __device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, B
             const int64_t s1 = s0 + BLOCK * 4;
             const unsigned nf = sm.n_front;        // read by everyone before the next step appends (barrier below)
             if (nf > FCAP - BLOCK * 4 || s1 - base > (int64_t)REL_MASK - BLOCK * 4 || s1 >= hi) {
-                if (nf) push_frontier<true>(c, day, sm, FrontMap{base, 0, 0}, cnt);
+                if (nf) push_frontier<true>(c, day, sm, FrontMap{base}, cnt);
                 __syncthreads();
                 if (tid == 0) sm.n_front = 0;
                 base = s1;
@@ -350,7 +331,7 @@ __device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, B
 __global__ void __launch_bounds__(BLOCK) k_push(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
-    push_scan_body(c, day, sm, (int)gridDim.x);
+    push_scan_body(c, day, sm, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -381,29 +362,45 @@ struct Settled {
     uint32_t ibn;        // tomorrow's snapshot byte
 };
 
-// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
-__device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
-                                                const uint32_t st, const uint32_t att, bool& infected_today, int& infector)
+// what the settle phase fetches for one agent, all of it requested before any of it is used
+struct Loaded {
+    int4 rv;             // first half of the agent record: days in state, household size, area, home building
+    int mb;              // the infector the push left for this agent, or -1
+};
+
+__device__ __forceinline__ Loaded load_agent(const DevCtx& c, const int64_t a, const uint32_t st, const uint32_t att)
 {
-    uint32_t evb = 0;
-    // everything this agent can need is requested before any of it is used; its days in state, area and home building
-    // arrive together in one 16-byte record
-    const int4 rv = *reinterpret_cast<const int4*>(c.rec + a);
-    int16_t* const rdays = reinterpret_cast<int16_t*>(c.rec + a);       // [0] t_inf, [1] t_q, [2] t_adm
-    int ti = (int16_t)(rv.x & 0xFFFF);
-    int tq = rv.x >> 16;
-    const int tadm = (int16_t)(rv.y & 0xFFFF);
-    const int sa_a = rv.z, home_a = rv.w;
-    const bool quirk = any_nd && (c.trig_ptr || c.hh_always);
-    const int h = quirk ? __ldg(c.hh + a) : 0;
-    int mb = -1;
+    Loaded L;
+    L.rv = reinterpret_cast<const int4*>(c.rec + a)[0];
+    L.mb = -1;
     if (att & ATT_HIT) {
         // the mailbox that matches this agent's isolation; both are reset for the day after tomorrow
         const int m_free = c.mb_any[a], m_iso = c.mb_iso[a];
-        mb = (st == ST_QH) ? m_iso : m_free;
+        L.mb = (st == ST_QH) ? m_iso : m_free;
         c.mb_any[a] = -1;
         c.mb_iso[a] = -1;
     }
+    return L;
+}
+
+// one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
+__device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
+                                                const uint32_t st, const uint32_t att, const Loaded& L, bool& infected_today,
+                                                int& infector)
+{
+    uint32_t evb = 0;
+    const int4 rv = L.rv;
+    int16_t* const rdays = reinterpret_cast<int16_t*>(c.rec + a);       // [0] t_inf, [1] t_q, [2] t_adm
+    int ti = (int16_t)(rv.x & 0xFFFF);
+    int tq = rv.x >> 16;
+    const int tadm = (int16_t)(rv.y & 0xFFFF), hh_size = rv.y >> 16;
+    const int sa_a = rv.z, home_a = rv.w;
+    // the second half of the record (household, where its members are listed, admission probability) is only needed on
+    // the few days of an agent's life when it can be admitted or diagnosed
+    auto second_half = [&]() { return reinterpret_cast<const int4*>(c.rec + a)[1]; };
+    const bool quirk = any_nd && (c.trig_ptr || c.hh_always);
+    const int h = quirk ? second_half().x : 0;
+    const int mb = L.mb;
     const bool f_hh = (att & ATT_HH) != 0;                                                  // :263
     bool f_q = false;
     if (quirk) f_q = (c.trig_ptr && c.qflag[h] != 0) || (c.hh_always && __ldg(c.hh_always + h));   // qflag is written during k_days: no __ldg
@@ -416,7 +413,8 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
         evb |= EVB_INF0;
         if (ti >= c.adm_min && ti <= c.adm_max) {                            // :205 window on the ABSOLUTE infection day
             const double u = draw(c.u_adm, c.lo + a, c.seed, day, STREAM_ADMISSION, (uint32_t)(c.lo + a), 0);
-            if (__ldg(c.p_adm + a) > u) { x = ST_H; rdays[2] = (int16_t)day; evb |= EVB_ADM; }     // :213-216
+            const int4 rw = second_half();
+            if (__hiloint2double(rw.w, rw.z) > u) { x = ST_H; rdays[2] = (int16_t)day; evb |= EVB_ADM; }   // :213-216
         }
     } else if (st == ST_H) {
         if (tadm >= c.death_min) {                                           // :219
@@ -472,8 +470,12 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
     }
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
-    if (ibn) c.ib_wr[0][c.lo + a] = ibn;      // (the sweep already stored 0 for everybody)
-    if (diagnosed_on(c, nullptr, a, x, ti, day + 1)) raise_household(c, a, c.att_next, c.qflag_next, c.df_next);
+    if (ibn && c.write_ib) c.ib_wr[0][c.lo + a] = ibn;      // (the sweep already stored 0 for everybody)
+    if (in_set(M_INF, x) && day + 1 - ti == c.diagnosis) {
+        const int4 rw = second_half();
+        if (diagnosed_on(c, nullptr, a, x, ti, day + 1, __hiloint2double(rw.w, rw.z)))
+            raise_household(c, a, rw.y, hh_size, c.att_next, c.qflag_next, c.df_next);
+    }
     return Settled{x, evb, kbin, ibn};
 }
 
@@ -532,7 +534,8 @@ __device__ __forceinline__ void fold_stats(const DevCtx& c)
 // cn = tomorrow's view: the block pushes the rows of its own newly infectious agents (null: no push, e.g. k_agent).
 template <int VARIANT>
 __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn,
-                                           unsigned int (&push_cnt)[4], const int n_blocks, unsigned long long* tr = nullptr)
+                                           unsigned int (&push_cnt)[4], const int n_blocks, const int wb,
+                                           unsigned long long* tr = nullptr)
 {
     auto stamp = [&](int i) {        // developer tracing: globaltimer at phase boundaries
         if (tr && threadIdx.x == 0) {
@@ -551,16 +554,25 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
     __syncthreads();
     const bool any_nd = c.df[DF_ANY_ND] != 0;
     const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN;   // a recovered agent left the histogram
-    // Pieces of 128 agents (one 4-byte word per lane) are dealt round-robin to the blocks: piece q is slot q / n_blocks
-    // of block q % n_blocks.  A block's share is thus spread over the whole population, which evens out the load when
-    // the epidemic is concentrated in some communities.  Warp w handles slot s0 + w (+ 8) of a batch of 16 slots.
+    // The block owns a contiguous run of 128-agent pieces (one 4-byte word per lane): an equal share, or -- in k_days --
+    // today's cut of equal measured work.  Warp w handles slot s0 + w (+ 8) of a batch of 16 slots.
     const int wid = tid >> 5;
     const int64_t n_pieces = c.n_pad >> 7;
-    const int64_t n_slots = (int)blockIdx.x < n_blocks ? (n_pieces - blockIdx.x + n_blocks - 1) / n_blocks : 0;
-    const FrontMap fmap{c.lo - c.rt_lo, n_blocks, (int)blockIdx.x};
-    auto agent_of = [&](uint32_t rel) { return ((int64_t)(rel >> 7) * n_blocks + blockIdx.x) * 128 + (rel & 127u); };
+    int64_t p_first, p_last;
+    if (wb < 0 || wb >= n_blocks) p_first = p_last = 0;
+    else if (c.bounds) { p_first = c.bounds[wb]; p_last = c.bounds[wb + 1]; }
+    else {
+        const int64_t per = (n_pieces + n_blocks - 1) / n_blocks;
+        p_first = wb * per < n_pieces ? wb * per : n_pieces;
+        p_last = p_first + per < n_pieces ? p_first + per : n_pieces;
+    }
+    const int64_t n_slots = p_last - p_first;
+    const int64_t a_first = p_first << 7;
+    const FrontMap fmap{c.lo - c.rt_lo + a_first};
+    auto agent_of = [&](uint32_t rel) { return a_first + rel; };
     uint32_t n_idle_s = 0, n_idle_r = 0;
     constexpr int SLOTS = LCAP / 128;             // slots per batch
+    if (tr && tid == 0) tr[1] = 0;
 
     // first batch's words
     uint32_t sw[2], aw[2];
@@ -582,20 +594,25 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             const bool in = sl < n_slots;
             const uint32_t rel0 = (uint32_t)(sl << 7) | (lane * 4);
             const int64_t a0 = agent_of(rel0);
-            uint32_t work = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t st = (sw[r] >> (8 * j)) & 0xFFu, at = (aw[r] >> (8 * j)) & 0xFFu;
-                const bool idle_s = (st == ST_S) && at == 0;
-                const bool idle_r = (st == ST_R) && r_idle && at == 0;
-                n_idle_s += idle_s;
-                n_idle_r += idle_r;
-                work |= (uint32_t)(!idle_s && !idle_r && st != ST_PAD) << j;
+            // four agents at once, byte-parallel: zb(x) has 0x80 in every byte of x that is zero (exact, no borrows)
+            auto zb = [](uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };
+            const uint32_t at0 = zb(aw[r]);                                           // attention byte == 0
+            const uint32_t idle_s = zb(sw[r] ^ (0x01010101u * ST_S)) & at0;           // susceptible, nothing pending
+            const uint32_t idle_r = r_idle ? zb(sw[r] ^ (0x01010101u * ST_R)) & at0 : 0u;
+            n_idle_s += __popc(idle_s);
+            n_idle_r += __popc(idle_r);
+            const uint32_t wk = ~(idle_s | idle_r | zb(sw[r])) & 0x80808080u;         // 0x80 per agent that must be settled
+            const uint32_t work = ((wk >> 7) | (wk >> 14) | (wk >> 21) | (wk >> 28)) & 0xFu;
+            if (c.piece_work) {
+                // what this piece costs a block (ns, measured with DYS_TRACE): ~50 for the sweep and ~65 per agent that is
+                // settled (most of them are infectious and push a row tomorrow as well)
+                const uint32_t cost = __reduce_add_sync(0xffffffffu, 65u * __popc(work));
+                if (in && lane == 0) c.piece_work[p_first + sl] = 50u + cost;
             }
             if (in) {
                 if (aw[r]) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
                 // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
-                *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
+                if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
             }
             const int mine = __popc(work);
             const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
@@ -627,10 +644,14 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             }
         }
         __syncthreads();
-        stamp(5);
+        if (s0 == 0) stamp(5);
 
-        // ---- settle ----
+        // ---- settle: once the list might not take another batch, or after the last batch.  A block in a quiet part of
+        // the city sweeps all its pieces back to back and settles once ----
         const int n_list = (int)sm.n_list;
+        const bool do_settle = n_list > LTOT - LCAP || s0 + SLOTS >= n_slots;
+        if (do_settle) {
+        if (tr && tid == 0) tr[1] += (unsigned long long)n_list << 32;      // tracing: settled agents | pushed rows
         for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
             const int k = k0 + tid;
             bool infected_today = false;
@@ -639,11 +660,26 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             uint32_t ibn = 0, rel = 0;
             uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
             int kbin = -1;
-            if (k < n_list) {
+            const bool valid = k < n_list;
+            uint32_t st = ST_PAD, att = 0;
+            Loaded L;
+            L.mb = -1;
+            if (valid) {
                 const uint32_t le = sm.list[k];
                 rel = le & REL_MASK;
                 a = agent_of(rel);
-                const Settled r = settle_agent(c, day, a, any_nd, (le >> 24) & 0xFu, (le >> 28) & 0x3u, infected_today, infector);
+                st = (le >> 24) & 0xFu;
+                att = (le >> 28) & 0x3u;
+                L = load_agent(c, a, st, att);
+            }
+            // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim
+            // is issued as soon as the mailboxes are in, its answer is only needed when the events are written
+            const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
+            if (k0 == 0) stamp(8);      // (the ballot needed the mailboxes: first round's loads are in)
+            int ev_base = 0;
+            if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+            if (valid) {
+                const Settled r = settle_agent(c, day, a, any_nd, st, att, L, infected_today, infector);
                 ibn = r.ibn;
                 kbin = r.k;
                 const uint32_t hi = hist_idx(r.x);
@@ -654,6 +690,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                 eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
                      ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
             }
+            if (k0 == 0) stamp(9);      // first round settled
             {
                 // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per
                 // non-zero counter from distinct lanes -- not 32 colliding atomics per counter
@@ -673,17 +710,14 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                 const unsigned km = __match_any_sync(0xffffffffu, kbin);
                 if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
             }
-            // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort)
-            const unsigned evm = __ballot_sync(0xffffffffu, infected_today);
             if (evm) {
                 if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
                 if (c.ev) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (infected_today) c.ev[base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+                    ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
+                    if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
                 }
             }
+            if (k0 == 0) stamp(10);     // counters and events done
             if (cn) {
                 // infectious tomorrow: queue the agent's row for the block's push of day + 1
                 const bool f = (ibn & IB_INF) != 0;
@@ -694,18 +728,20 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (f) {
                         sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
-                        prefetch_l2(cn->tptr + fmap.base + a);
+                        prefetch_l2(cn->tptr + fmap.at(rel));
                     }
                 }
             }
         }
-        __syncthreads();      // the work list is free; the frontier count is final for this batch
+        __syncthreads();      // the work list is free; the frontier count is final
         stamp(6);
         if (tid == 0) sm.n_list = 0;
-        if (cn && sm.n_front && (sm.n_front > FCAP - LCAP || s0 + SLOTS >= n_slots)) {
+        if (tr && tid == 0 && cn) tr[1] += sm.n_front;
+        if (cn && sm.n_front) {      // (a settle can add as many rows as the frontier holds: push after each)
             push_frontier<false>(*cn, day + 1, sm, fmap, push_cnt);      // (the work list's memory is the push scratch)
             __syncthreads();
             if (tid == 0) sm.n_front = 0;
+        }
         }
         __syncthreads();
     }
@@ -751,7 +787,7 @@ __global__ void __launch_bounds__(BLOCK) k_agent(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
     unsigned int none[4] = {0, 0, 0, 0};
-    agent_body<0>(c, day, sm, nullptr, none, (int)gridDim.x);
+    agent_body<0>(c, day, sm, nullptr, none, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -803,6 +839,110 @@ __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const
     c.sa_hist = plan.want_sa ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_sa) : nullptr;
     c.bcount = plan.want_bc ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_bc) : nullptr;
     c.ev = plan.want_ev ? reinterpret_cast<int2*>(plan.out[k] + plan.off_ev) : nullptr;
+    // tomorrow's snapshot bytes are only scanned by a stand-alone push: every day in peer / two-phase mode, else only
+    // after the last day of the window (the next call starts with a scan)
+    c.write_ib = (c0.n_peers > 1 || c0.io_mat != nullptr || k == plan.n_days - 1) ? 1 : 0;
+}
+
+// The service block re-cuts the population for the day after tomorrow: contiguous runs of pieces with equal measured
+// cost.  Piece q goes to block floor(prefix(q) * n_work / total); bounds[b] = the first piece of block b.  The piece
+// costs are staged in the block's (otherwise idle) frontier + work-list shared memory, 8192 at a time, so that every
+// global load is coalesced and all of them are in flight together; up to a million agents that is a single chunk and
+// the total falls out of the same scan.
+__device__ __forceinline__ void plan_cut(const uint32_t* __restrict__ work, int32_t* __restrict__ bounds, const int64_t n_pieces,
+                                         const int n_work, BlockScratch& sm, unsigned long long* tr = nullptr)
+{
+    auto stamp = [&](int i) {
+        if (tr && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tr[i] = t;
+        }
+    };
+    stamp(8);
+    __shared__ unsigned long long s_sum[BLOCK];
+    __shared__ unsigned long long s_carry, s_total;
+    static_assert(offsetof(BlockScratch, list) == sizeof(uint32_t) * FCAP, "front and list are contiguous");
+    const int tid = threadIdx.x;
+    constexpr int CHUNK = FCAP + LTOT, PER = CHUNK / BLOCK;      // 32 consecutive pieces per thread and chunk
+    uint32_t* const stage = sm.front;
+    // thread t walks 32 consecutive words: XOR the word's low index with t so that the 32 lanes of a warp hit 32 banks
+    auto at = [](int i) { return (i & ~31) | ((i & 31) ^ ((i >> 5) & 31)); };
+    const bool single = n_pieces <= CHUNK;
+    if (!single) {      // a first pass for the total
+        unsigned long long s = 0;
+        for (int64_t q = tid; q < n_pieces; q += BLOCK) s += __ldcg(work + q);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((tid & 31) == 0) s_sum[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t = 0;
+            for (int w = 0; w < WARPS; ++w) t += s_sum[w];
+            s_total = t;
+        }
+    }
+    if (tid == 0) { s_carry = 0; bounds[0] = 0; bounds[n_work] = (int32_t)n_pieces; }
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < n_pieces; c0 += CHUNK) {
+        {
+            uint32_t v[PER];                                 // all of the thread's loads are issued before the first store
+#pragma unroll
+            for (int j = 0; j < PER; ++j) v[j] = c0 + tid + j * BLOCK < n_pieces ? __ldcg(work + c0 + tid + j * BLOCK) : 0u;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) stage[at(tid + j * BLOCK)] = v[j];
+        }
+        __syncthreads();
+        stamp(9);
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) mine += stage[at(tid * PER + k)];
+        s_sum[tid] = mine;
+        __syncthreads();
+        if (tid < 32) {      // exclusive scan of the 256 thread sums: 8 per lane, then a warp scan
+            unsigned long long v[8], run = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[k] = s_sum[tid * 8 + k]; run += v[k]; }
+            unsigned long long incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            unsigned long long ex = s_carry + incl - run;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s_sum[tid * 8 + k] = ex; ex += v[k]; }
+            __syncwarp();
+            if (tid == 31) { s_carry += incl; if (single) s_total = incl; }
+        }
+        __syncthreads();
+        stamp(10);
+        // floor(before * n_work / total) with one division per thread instead of one per piece: (before * M) >> 32 with
+        // M = floor(2^32 * n_work / total).  Any monotone function of `before` that every thread evaluates identically
+        // gives a valid cut.  (total < 2^40 and n_work < 2^11: no overflow.)
+        const unsigned long long M = (((unsigned long long)n_work) << 32) / (s_total ? s_total : 1ull);
+        auto block_of = [&](unsigned long long before) {
+            const int b = (int)((before * M) >> 32);
+            return b < n_work - 1 ? b : n_work - 1;
+        };
+        unsigned long long cum = s_sum[tid];                 // cost of all pieces before this thread's first
+        const int64_t q0 = c0 + tid * PER;
+        int prev = 0;
+        if (q0 > 0 && q0 < n_pieces) prev = block_of(cum - (tid ? stage[at(tid * PER - 1)] : __ldcg(work + q0 - 1)));
+#pragma unroll 4
+        for (int k = 0; k < PER; ++k) {
+            const int64_t q = q0 + k;
+            if (q < n_pieces) {
+                const int b = block_of(cum);
+                for (int j = prev + 1; j <= b; ++j) bounds[j] = (int32_t)q;
+                prev = b;
+                cum += stage[at(tid * PER + k)];
+                if (q == n_pieces - 1)
+                    for (int j = prev + 1; j < n_work; ++j) bounds[j] = (int32_t)n_pieces;      // blocks left without pieces
+            }
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
@@ -829,9 +969,12 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     const bool peers = c0.n_peers > 1;
     // io_mat is one buffer for the latest day: the push of day + 1 must not clear it under the agent pass of day
     const bool two_phase = peers || c0.io_mat != nullptr;
-    // the last block owns no agents: it folds each day's statistics after the barrier while the others are already in
-    // the next day, and is never the one they wait for
+    // Block 0 owns no agents: it folds each day's statistics and re-cuts the population after the barrier while the
+    // others are already in the next day.  (The FIRST block, because the warp schedulers favour the oldest warps of an
+    // SM: as the youngest block it was starved by its three busy neighbours and became the one everybody waited for.)
+    const bool service = gridDim.x > 1 && blockIdx.x == 0;
     const int n_work = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
+    const int wb = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
     if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0);
     __syncthreads();
     for (int k = 0; k < plan.n_days; ++k) {
@@ -840,7 +983,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         const bool local_push = !two_phase && k + 1 < plan.n_days;
         if (threadIdx.x == 0 && k + 1 < plan.n_days) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1);
         __syncthreads();
-        unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * 8 : nullptr;
+        unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * TRACE_SLOTS : nullptr;
         auto stamp = [&](int i) {
             if (tr && threadIdx.x == 0) {
                 unsigned long long t;
@@ -850,7 +993,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         };
         stamp(0);
         if (k == 0 || two_phase) {
-            push_scan_body(c, day, sm, n_work);
+            push_scan_body(c, day, sm, n_work, wb);
             stamp(1);
             grid_barrier(barrier_counter, epoch);
         }
@@ -858,13 +1001,20 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         unsigned int push_cnt[4] = {0, 0, 0, 0};
         const DevCtx* cn = local_push ? &s_c[(k + 1) & 1] : nullptr;
         if (cn) push_clear_duties(*cn);
-        agent_body<3>(c, day, sm, cn, push_cnt, n_work, tr);
+        agent_body<3>(c, day, sm, cn, push_cnt, n_work, wb, tr);
         if (cn) { __syncthreads(); publish_push_counters(*cn, sm, push_cnt); }
         stamp(3);
         grid_barrier(barrier_counter, epoch);
         stamp(4);
-        if (blockIdx.x == gridDim.x - 1) fold_stats(c);      // every block's partial sums are in; the others move on
-        if (peers && blockIdx.x < PUBLISH_BLOCKS) {
+        if (service || gridDim.x == 1) {                      // every block's partial sums are in; the others move on
+            fold_stats(c);
+            // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
+            // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a
+            // quiet day.  Days = 0, 1 mod 4 refresh the even- and the odd-day cut.)
+            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, const_cast<int32_t*>(c.bounds), c.n_pad >> 7, n_work, sm, tr);
+            stamp(11);
+        }
+        if (peers && wb >= 0 && wb < PUBLISH_BLOCKS) {      // (not the service block: it is busy folding)
             // a few CTAs ship tomorrow's bytes to the peers while the others already start the next day (whose push
             // waits for the peers' flags anyway); the last shipper raises this rank's flag on every GPU
             publish_body(c);
@@ -892,12 +1042,12 @@ __global__ void __launch_bounds__(BLOCK) k_snapshot(const DevCtx c, const int da
     if (a0 >= c.n_pad) return;
     const uchar4 sv = *reinterpret_cast<const uchar4*>(c.status + a0);
     const uint32_t st[4] = {sv.x, sv.y, sv.z, sv.w};
-    const int ti[4] = {c.rec[a0].t_inf, c.rec[a0 + 1].t_inf, c.rec[a0 + 2].t_inf, c.rec[a0 + 3].t_inf};
     uint8_t ibn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        ibn[j] = infectious_byte(st[j], day, ti[j]);
-        if (diagnosed_on(c, c.u_adm, a0 + j, st[j], ti[j], day)) raise_household(c, a0 + j, c.att, c.qflag, c.df);
+        const AgentRec r = c.rec[a0 + j];
+        ibn[j] = infectious_byte(st[j], day, r.t_inf);
+        if (diagnosed_on(c, c.u_adm, a0 + j, st[j], r.t_inf, day, r.p_adm)) raise_household(c, a0 + j, r.hh_slot, r.hh_size, c.att, c.qflag, c.df);
     }
     // (k_snapshot of `day` is bound like day - 1's agent pass would be: ib_wr[0] is the buffer of `day`)
     *reinterpret_cast<uchar4*>(c.ib_wr[0] + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);

@@ -63,26 +63,67 @@ __global__ void k_fill_members(const int32_t* __restrict__ hh, int64_t n, unsign
     if (a < n) mem[atomicAdd(&cursor[hh[a]], 1ull)] = (int32_t)a;
 }
 
+// household, member list position and admission probability into the agent records
+__global__ void k_pack_records(const int32_t* __restrict__ hh, const int64_t* __restrict__ hh_ptr, const double* __restrict__ p_adm,
+                               AgentRec* __restrict__ rec, int64_t n, int32_t* bad)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int32_t h = hh[a];
+    const int64_t first = hh_ptr[h], size = hh_ptr[h + 1] - first;
+    if (size > 32767) atomicOr(bad, 1024);
+    rec[a].hh = h;
+    rec[a].hh_slot = (int32_t)first;
+    rec[a].hh_size = (int16_t)size;
+    rec[a].p_adm = p_adm[a];
+}
+
 __global__ void k_validate_routine(const int32_t* __restrict__ routine, int64_t n, int64_t B, int32_t* bad)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && (routine[i] < -1 || routine[i] >= B)) atomicOr(bad, 16);
 }
 
-// rows monotone, columns inside the halo and strictly ascending; counts the non-zeros of every halo column
-__global__ void k_validate_graph_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_loc,
-                                       int64_t col_lo, int64_t col_hi, int32_t* __restrict__ col_count, int32_t* bad)
+// Routines are static (computed once per simulation, contagious3.py:139-170), so WHICH slots two agents share is static
+// too.  Four bits per interaction_prob non-zero (u = row = susceptible side, i = column = infectious side):
+//   HH  home(u) == home(i)                  HO  home(u) is a non-home stop of i
+//   OH  home(i) is a non-home stop of u     OO  they share a non-home stop
+// With every building open, exposure(u,i) = HH | HO&!iso(i) | OH&!iso(u) | OO&!iso(u)&!iso(i) exactly; with closed
+// buildings it is a superset that exposed_slow() re-checks.  Class 0 = the pair never shares a building: its exposure
+// factor (contagious3.py:230-236) is 0 on every day, so P = 0 and `P > U` can never hold -- such non-zeros are left out
+// of the transposed network altogether (three quarters of the synthetic city's, most of the shipped city's).
+__device__ __forceinline__ uint32_t pair_class(const int32_t* __restrict__ ru /* [V] routine of u */,
+                                               const int32_t* __restrict__ ri /* [V] routine of i */, const int V)
 {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_loc) return;
-    if (rowptr[u + 1] < rowptr[u]) { atomicOr(bad, 32); return; }
-    int32_t prev = -1;
-    for (int64_t e = rowptr[u]; e < rowptr[u + 1]; ++e) {
+    uint32_t cls = 0;
+    for (int t = 0; t < V; ++t) {
+        const int32_t bi = ri[t];
+        if (bi < 0) continue;
+        for (int s = 0; s < V; ++s)
+            if (ru[s] == bi) cls |= (s == 0) ? (t == 0 ? CLS_HH : CLS_HO) : (t == 0 ? CLS_OH : CLS_OO);
+    }
+    return cls;
+}
+
+// rows monotone, columns inside the halo and strictly ascending; counts, for every halo column, the non-zeros whose
+// pair can ever share a building.  One warp per row.
+__global__ void __launch_bounds__(256) k_validate_graph_count(const DevCtx c, const int64_t* __restrict__ rowptr,
+                                                              const int32_t* __restrict__ col, int32_t* __restrict__ col_count,
+                                                              int32_t* bad)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t u = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (u >= c.n_loc) return;
+    const int64_t e0 = rowptr[u], e1 = rowptr[u + 1];
+    if (e1 < e0) { if (lane == 0) atomicOr(bad, 32); return; }
+    const int V = c.V;
+    int32_t ru[16];
+    for (int s = 0; s < 16; ++s) ru[s] = s < V ? c.routine[(c.lo + u - c.rt_lo) * V + s] : -1;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
         const int32_t i = col[e];
-        if (i < col_lo || i >= col_hi) { atomicOr(bad, 64); continue; }
-        if (i <= prev) atomicOr(bad, 128);
-        prev = i;
-        atomicAdd(&col_count[i - col_lo], 1);
+        if (i < c.rt_lo || i >= c.rt_lo + c.rt_n) { atomicOr(bad, 64); continue; }
+        if (e > e0 && i <= col[e - 1]) atomicOr(bad, 128);
+        if (pair_class(ru, c.routine + ((int64_t)i - c.rt_lo) * V, V)) atomicAdd(&col_count[i - c.rt_lo], 1);
     }
 }
 
@@ -127,13 +168,8 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
     if (threadIdx.x == 0) ptr[n] = s_carry;
 }
 
-// Routines are static (computed once per simulation, contagious3.py:139-170), so WHICH slots two agents share is static
-// too.  Four bits per interaction_prob non-zero (u = row = susceptible side, i = column = infectious side):
-//   HH  home(u) == home(i)                  HO  home(u) is a non-home stop of i
-//   OH  home(i) is a non-home stop of u     OO  they share a non-home stop
-// With every building open, exposure(u,i) = HH | HO&!iso(i) | OH&!iso(u) | OO&!iso(u)&!iso(i) exactly; with closed
-// buildings it is a superset that exposed_slow() re-checks.  One warp per row; each non-zero is appended to its
-// column's transposed list (the order inside a list is irrelevant: k_push reduces with max).
+// One warp per row; each non-zero whose pair can share a building is appended to its column's transposed list (the order
+// inside a list is irrelevant: the push reduces with max).
 __global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const int64_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ col, const double* __restrict__ val,
                                                         unsigned long long* __restrict__ cursor, TEdge* __restrict__ tedge)
@@ -146,16 +182,8 @@ __global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const in
     for (int s = 0; s < 16; ++s) ru[s] = s < V ? c.routine[(c.lo + u - c.rt_lo) * V + s] : -1;
     for (int64_t e = rowptr[u] + lane; e < rowptr[u + 1]; e += 32) {
         const int32_t i = col[e];
-        const int32_t* ri = c.routine + ((int64_t)i - c.rt_lo) * V;
-        uint32_t cls = 0;
-        for (int t = 0; t < V; ++t) {
-            const int32_t bi = ri[t];
-            if (bi < 0) continue;
-            for (int s = 0; s < V; ++s) {
-                if (ru[s] != bi) continue;
-                cls |= (s == 0) ? (t == 0 ? CLS_HH : CLS_HO) : (t == 0 ? CLS_OH : CLS_OO);
-            }
-        }
+        const uint32_t cls = pair_class(ru, c.routine + ((int64_t)i - c.rt_lo) * V, V);
+        if (!cls) continue;
         const unsigned long long pos = atomicAdd(&cursor[i - c.rt_lo], 1ull);
         TEdge t;
         t.colx = (uint32_t)u | (cls << CLS_SHIFT);

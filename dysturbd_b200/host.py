@@ -66,11 +66,13 @@ def building_lockdown(lu, usg, current, sc, vR, prevVR, choice):
 class EpidemicModel:
     """contagious3.py:172-389 with the day on the GPU.
 
-    run() queues days in windows of WINDOW = 3 and keeps two windows in flight: the open flags of day d+1 depend on
-    `Known R` of days d and d-1, i.e. on R of days d-7 and d-8 (contagious3.py:306-309, 379-384), so the flags of two
-    3-day windows ahead only need days that have already been consumed -- exact for every scenario, while the host's
-    dictionary building overlaps the device's work."""
-    WINDOW = 3
+    run() queues days in windows (one cooperative launch each) and keeps two windows in flight.  The open flags of day
+    d+1 depend on `Known R` of days d and d-1, i.e. on R of days d-`diagnosis` and d-`diagnosis`-1 (contagious3.py:306-309,
+    379-384): with c days consumed, the flags of every day <= c + diagnosis are already determined.  Two windows of
+    (diagnosis + 1) // 2 days therefore never need a day that has not been consumed -- exact for every scenario, while the
+    host's dictionary building overlaps the device's work.  A scenario that closes nothing (no ALL / EDU / REL keyword)
+    has constant flags and uses week-long windows."""
+    MAX_WINDOW = 7
 
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
                  device=0, choice_seed=None, backend=None, population=None):
@@ -89,6 +91,8 @@ class EpidemicModel:
         self._R = {}                 # day -> R of that day (contagious3.py:281)
         self._flags = {0: self.pop.open.astype(float)}      # day -> build[:,10] in force on that day
         self._queued = 0             # next day to queue
+        closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
+        self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
 
     @property
     def open(self):
@@ -182,7 +186,7 @@ class EpidemicModel:
 
     def run(self, max_days=None):
         batched = hasattr(self.sim, "step_many")
-        w = self.WINDOW if batched else 1
+        w = self.window if batched else 1
         limit = (lambda d: max_days is None or d < max_days)
         while self.active() and limit(self.day):
             while batched and self._queued < self.day + 2 * w and limit(self._queued):      # keep two windows in flight

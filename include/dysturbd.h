@@ -72,8 +72,12 @@ enum {
     /* work counters of the day (feed the algorithmic-bytes formula of DESIGN.md) */
     DYS_ST_SUS0,             /* susceptible at day start (status 1 or 3) */
     DYS_ST_INF0,             /* infectious at day start (status 2, 3.5, 4) */
-    DYS_ST_EDGES_SCANNED,    /* interaction_prob non-zeros visited (implementation specific: rows of infectious agents) */
-    DYS_ST_CANDIDATES,       /* ... whose column agent is infectious */
+    /* 14..17 are diagnostics of the push.  Only non-zeros whose pair can ever share a building are kept (the others have
+     * exposure 0 on every day).  dys_step: 16 and 17 equal the reference's count of P > 0 pairs and of P > U successes.
+     * Inside a dys_step_many window the push of day d+1 runs before day d is finished everywhere and does not read the
+     * row agent's status, so all four count pairs regardless of whether the row agent is still susceptible. */
+    DYS_ST_EDGES_SCANNED,    /* kept non-zeros in the columns of today's infectious agents */
+    DYS_ST_CANDIDATES,       /* ... whose row agent is susceptible */
     DYS_ST_EXPOSED,          /* ... and shares a building today: one Bernoulli each */
     DYS_ST_HITS,             /* Bernoulli successes */
     DYS_ST_CHANGED,          /* agents whose state was rewritten today */

@@ -104,7 +104,7 @@ def compare_sims(a, b, days, open_fn=None):
         for k in ("status", "t_inf", "t_q", "t_adm", "src"):
             assert np.array_equal(sa[k], sb[k]), "%s differs on day %d (%d agents)" % (k, d, int((sa[k] != sb[k]).sum()))
         xa, xb = a.stats(d), b.stats(d)
-        keep = [i for i in range(18) if i != 14]    # 14 = entries scanned: implementation-specific (the oracle pulls, the GPU pushes)
+        keep = [i for i in range(18) if i not in (14, 15)]    # 14, 15 = network entries visited / with a susceptible row: implementation-specific (the oracle pulls every non-zero, the GPU pushes and keeps only pairs that can share a building)
         assert np.array_equal(xa[keep], xb[keep]), "counters differ on day %d: %s vs %s" % (d, xa[:18], xb[:18])
         assert np.array_equal(xa[32:53], xb[32:53]), "histogram differs on day %d" % d
         assert np.array_equal(a.sa_hist(d), b.sa_hist(d)), "sa_hist day %d" % d

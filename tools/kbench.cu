@@ -19,13 +19,13 @@ __global__ void __launch_bounds__(256) k_agent_nofold(const DevCtx c, const int 
 {
     __shared__ BlockScratch sm;
     unsigned int none[4] = {0, 0, 0, 0};
-    agent_body<1>(c, day, sm, nullptr, none, (int)gridDim.x);
+    agent_body<1>(c, day, sm, nullptr, none, (int)gridDim.x, (int)blockIdx.x);
 }
 __global__ void __launch_bounds__(256) k_agent_noreduce(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
     unsigned int none[4] = {0, 0, 0, 0};
-    agent_body<2>(c, day, sm, nullptr, none, (int)gridDim.x);
+    agent_body<2>(c, day, sm, nullptr, none, (int)gridDim.x, (int)blockIdx.x);
 }
 template <typename T> T* dalloc(size_t n, int fill = 0) { T* p; cudaMalloc(&p, n * sizeof(T)); cudaMemset(p, fill, n * sizeof(T)); return p; }
 
@@ -46,7 +46,7 @@ int main(int argc, char** argv)
     c.status = dalloc<uint8_t>(N); cudaMemcpy(c.status, st.data(), N, cudaMemcpyHostToDevice);
     {
         std::vector<AgentRec> rc(N);
-        for (int64_t a = 0; a < N; ++a) rc[a] = AgentRec{ti[a], 0, 0, 0, sa[a], home[a]};
+        for (int64_t a = 0; a < N; ++a) rc[a] = AgentRec{ti[a], 0, 0, 3, sa[a], home[a], hh[a], (int32_t)(a / 3 * 3), 0.5};
         c.rec = dalloc<AgentRec>(N); cudaMemcpy(c.rec, rc.data(), sizeof(AgentRec) * N, cudaMemcpyHostToDevice);
     }
     c.src = dalloc<int32_t>(N); cudaMemcpy(c.src, src.data(), 4 * N, cudaMemcpyHostToDevice);
@@ -135,7 +135,7 @@ int main(int argc, char** argv)
         for (int k = 0; k < 7; ++k) { plan.out[k] = dalloc<unsigned char>(blk); plan.open[k] = c.open; plan.n_closed[k] = 0; }
         cudaMemcpy(buf.ib[1], ibbuf, N, cudaMemcpyDeviceToDevice);
         plan.buf = buf;
-        plan.trace = dalloc<unsigned long long>((size_t)7 * 148 * 8 * 8);
+        plan.trace = dalloc<unsigned long long>((size_t)7 * 148 * 8 * TRACE_SLOTS);
         unsigned int* bar = dalloc<unsigned int>(4);
         int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_days, 256, 0);
         void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
@@ -149,19 +149,19 @@ int main(int argc, char** argv)
             printf("k_days 7 days: %.2f us/day (%s, %d CTAs/SM)\n", ms * 1000 / 7, cudaGetErrorString(er), occ);
         }
         const int G = 148 * occ;
-        std::vector<unsigned long long> tr((size_t)7 * G * 8);
+        std::vector<unsigned long long> tr((size_t)7 * G * TRACE_SLOTS);
         cudaMemcpy(tr.data(), plan.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
         for (int k = 0; k < 7; ++k) {
             // per phase: mean over the working blocks, and the latest block relative to the earliest day start
             double sw = 0, se = 0, pu = 0, late = 0; unsigned long long t_first = ~0ull, t_last = 0;
             for (int b = 0; b < G - 1; ++b) {
-                const unsigned long long* t = &tr[((size_t)k * G + b) * 8];
+                const unsigned long long* t = &tr[((size_t)k * G + b) * TRACE_SLOTS];
                 sw += (t[5] - t[2]) / 1e3; se += (t[6] - t[5]) / 1e3; pu += (t[7] - t[6]) / 1e3;
                 if (t[2] < t_first) t_first = t[2];
                 if (t[3] > t_last) t_last = t[3];
             }
             (void)late;
-            const unsigned long long* t0 = &tr[((size_t)k * G) * 8];
+            const unsigned long long* t0 = &tr[((size_t)k * G) * TRACE_SLOTS];
             printf("  day %d: sweep %.2f  settle %.2f  push %.2f us (means)   first start -> last block done %.2f   block 0 barrier wait %.2f\n",
                    k, sw / (G - 1), se / (G - 1), pu / (G - 1), (t_last - t_first) / 1e3, (t0[4] - t0[3]) / 1e3);
         }

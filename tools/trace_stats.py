@@ -17,14 +17,14 @@ for d in sorted(set(rows[:, 0])):
     starts[d] = r[0, 2]
     if d not in sel:
         continue
-    w = r[:-1]                      # working blocks (the last one only folds)
+    w = r[1:]                       # working blocks (block 0 only folds and plans)
     t = w[:, 2:].astype(float) / 1e3
     ok = t[:, 5] > 0
     sweep = (t[ok, 5] - t[ok, 2]).mean() if ok.any() else 0
     settle = (t[ok, 6] - t[ok, 5]).mean() if ok.any() else 0
     push = (t[ok, 7] - t[ok, 6]).mean() if ok.any() else 0
     span = t[:, 3].max() - t[:, 2].min()
-    bw = t[0, 4] - t[0, 3]
+    bw = t[0, 4] - t[0, 3]          # the first working block's wait at the barrier
     nxt = (starts.get(d + 1, 0))
     print("%4d %6.2f %6.2f %6.2f | %6.2f  (agent phase p50 %.2f p99 %.2f max %.2f) | %6.2f" %
           (d, sweep, settle, push, span, np.percentile(t[:, 3] - t[:, 2], 50), np.percentile(t[:, 3] - t[:, 2], 99),
