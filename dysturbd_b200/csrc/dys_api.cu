@@ -224,9 +224,9 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
             h->days_grid = per_sm_days * sms;
     }
     if (rc == DYS_OK && h->days_grid > 1)
-        for (int k = 0; k < 2; ++k) {      // the daily equal-work cut of k_days (see plan_cut)
+        for (int k = 0; k < 3; ++k) {      // the daily equal-work cut of k_days (see plan_cut)
             A(dev_alloc(h, &h->buf.bounds[k], h->days_grid + 1));
-            A(dev_alloc(h, &h->buf.piece_work[k], c.n_pad / 128));
+            if (k < 2) A(dev_alloc(h, &h->buf.piece_work[k], c.n_pad / 128));
         }
     A(dev_alloc(h, &h->d_open_ring, (int64_t)MAX_FUSED_DAYS * c.B));
     A(dev_alloc(h, &h->d_barrier, 4));
@@ -295,9 +295,9 @@ static int reset_day_scratch(dys_handle* h)
         const int64_t n_pieces = c.n_pad / 128, per = (n_pieces + n_work - 1) / n_work;
         std::vector<int32_t> cut((size_t)n_work + 1);
         for (int b = 0; b <= n_work; ++b) cut[(size_t)b] = (int32_t)((int64_t)b * per < n_pieces ? (int64_t)b * per : n_pieces);
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 3; ++k) {
             CK(h, cudaMemcpyAsync(h->buf.bounds[k], cut.data(), sizeof(int32_t) * cut.size(), cudaMemcpyHostToDevice, h->stream));
-            CK(h, cudaMemsetAsync(h->buf.piece_work[k], 0, sizeof(uint32_t) * (size_t)n_pieces, h->stream));
+            if (k < 2) CK(h, cudaMemsetAsync(h->buf.piece_work[k], 0, sizeof(uint32_t) * (size_t)n_pieces, h->stream));
         }
         CK(h, cudaStreamSynchronize(h->stream));      // `cut` leaves scope
     }
@@ -599,7 +599,7 @@ static int run_snapshot(dys_handle* h, int32_t day)
     CK(h, cudaMemsetAsync(h->buf.att[day & 1], 0, (size_t)c.n_pad + 16, h->stream));
     CK(h, cudaMemsetAsync(h->buf.qflag[day % Q_RING], 0, (size_t)c.H + 16, h->stream));
     CK(h, cudaMemsetAsync(h->buf.df + (day & (DF_RING - 1)) * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
-    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
+    bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     bind_ib_targets(c, h->buf, day & 1);
     k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
     if (h->n_peers > 1) {
@@ -607,7 +607,7 @@ static int run_snapshot(dys_handle* h, int32_t day)
         k_signal<<<1, 32, 0, h->stream>>>(c, day);
     }
     CK(h, cudaGetLastError());
-    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
+    bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     h->ib_day = day;
     return DYS_OK;
 }
@@ -648,7 +648,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     }
     if (!h->tev.empty() && h->t_end - h->t_begin >= dys_handle::T_RING) h->t_begin = h->t_end - dys_handle::T_RING + 1;
     bind_peers(h);
-    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
+    bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     tick(h, 0);
     if (h->ib_day != day || (inj && inj->u_adm)) {
         // first day after a load / set_state, a skipped day, or injected admission draws (tomorrow's diagnoses cannot
@@ -700,7 +700,7 @@ static int step_end(dys_handle* h, int32_t day)
     c.ev = (h->p.flags & DYS_WANT_EVENTS) ? (int2*)(h->d_out[slot] + h->off_ev) : nullptr;
     h->last_slot = slot;
     bind_peers(h);
-    bind_day(c, h->buf, day); c.bounds = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
+    bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     k_push<<<(unsigned)h->push_grid, BLOCK, 0, h->stream>>>(c, day);
     tick(h, 2);
     k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);

@@ -127,7 +127,8 @@ struct DevCtx {
     int32_t* io_mat;                     // [S * S] or null
     // k_days only: the agents are dealt to the blocks in contiguous runs of 128-agent pieces, re-cut every day so that
     // every block gets the same MEASURED work (the epidemic is never evenly spread over the population)
-    const int32_t* bounds;               // [n_work + 1] today's cut, or null (equal runs)
+    int32_t* bounds_plan;                // [n_work + 1] where the cut made from today's costs goes (used in three days), or null
+    int32_t cut_first, cut_last;         // this block's run of pieces today, or cut_first < 0: an equal share
     uint32_t* piece_work;                // [n_pad / 128] today's cost of each piece, written by the sweep, or null
     const double *u_adm, *u_death, *u_pair;   // injected draws or null
     double* pair_prob;                   // [n_glob^2] or null (tests)
@@ -142,7 +143,9 @@ struct DayBuffers {
     unsigned long long* part;            // [PART_RING][N_STATS][N_SLOTS]
     uint8_t* ib[2];                      // own snapshot buffers by day parity
     uint8_t* peer_ib[8][2];              // peer mode: every rank's, by day parity
-    int32_t* bounds[2];                  // k_days: the cut of day d is bounds[d & 1] (made from the work of day d - 2), or null
+    int32_t* bounds[3];                  // k_days: the cut of day d is bounds[d % 3], made from the costs of day d - 3 or
+                                         // earlier -- complete a whole day before it is used, so that a block can fetch its
+                                         // run while it builds tomorrow's view; or null
     uint32_t* piece_work[2];             // k_days: the piece costs measured on day d are piece_work[d & 1]
 };
 
@@ -163,7 +166,8 @@ __host__ __device__ __forceinline__ void bind_day(DevCtx& c, const DayBuffers& b
     c.qflag = b.qflag[day % Q_RING]; c.qflag_next = b.qflag[(day + 1) % Q_RING];
     c.df = b.df + (day & (DF_RING - 1)) * DF_LEN; c.df_next = b.df + ((day + 1) & (DF_RING - 1)) * DF_LEN;
     c.part = b.part + (size_t)(day % PART_RING) * N_STATS * N_SLOTS;
-    c.bounds = b.bounds[p]; c.piece_work = b.piece_work[p];
+    c.bounds_plan = b.bounds[day % 3]; c.piece_work = b.piece_work[p];      // (day + 3) % 3
+    c.cut_first = c.cut_last = -1;
     c.ib_rd = b.ib[p];
     c.write_ib = 1;
     bind_ib_targets(c, b, p ^ 1);        // the agent pass of `day` writes tomorrow's snapshot bytes

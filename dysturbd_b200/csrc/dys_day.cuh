@@ -363,8 +363,11 @@ struct Settled {
 };
 
 // what the settle phase fetches for one agent, all of it requested before any of it is used
+#ifndef DYS_EAGER_REC
+#define DYS_EAGER_REC 0
+#endif
 struct Loaded {
-    int4 rv;             // first half of the agent record: days in state, household size, area, home building
+    int4 rv, rw;         // the agent record: days in state, household size, area, home building | household, members, p_adm
     int mb;              // the infector the push left for this agent, or -1
 };
 
@@ -372,6 +375,11 @@ __device__ __forceinline__ Loaded load_agent(const DevCtx& c, const int64_t a, c
 {
     Loaded L;
     L.rv = reinterpret_cast<const int4*>(c.rec + a)[0];
+#if DYS_EAGER_REC
+    // (measured: fetching both halves for everybody is 4 % slower than the dependent load on the few days of an agent's
+    // life when it is admitted or diagnosed -- the four extra live registers cost more than the round trip)
+    L.rw = reinterpret_cast<const int4*>(c.rec + a)[1];
+#endif
     L.mb = -1;
     if (att & ATT_HIT) {
         // the mailbox that matches this agent's isolation; both are reset for the day after tomorrow
@@ -395,9 +403,11 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
     int tq = rv.x >> 16;
     const int tadm = (int16_t)(rv.y & 0xFFFF), hh_size = rv.y >> 16;
     const int sa_a = rv.z, home_a = rv.w;
-    // the second half of the record (household, where its members are listed, admission probability) is only needed on
-    // the few days of an agent's life when it can be admitted or diagnosed
+#if DYS_EAGER_REC
+    auto second_half = [&]() { return L.rw; };
+#else
     auto second_half = [&]() { return reinterpret_cast<const int4*>(c.rec + a)[1]; };
+#endif
     const bool quirk = any_nd && (c.trig_ptr || c.hh_always);
     const int h = quirk ? second_half().x : 0;
     const int mb = L.mb;
@@ -560,7 +570,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
     const int64_t n_pieces = c.n_pad >> 7;
     int64_t p_first, p_last;
     if (wb < 0 || wb >= n_blocks) p_first = p_last = 0;
-    else if (c.bounds) { p_first = c.bounds[wb]; p_last = c.bounds[wb + 1]; }
+    else if (c.cut_first >= 0) { p_first = c.cut_first; p_last = c.cut_last; }
     else {
         const int64_t per = (n_pieces + n_blocks - 1) / n_blocks;
         p_first = wb * per < n_pieces ? wb * per : n_pieces;
@@ -842,6 +852,10 @@ __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const
     // tomorrow's snapshot bytes are only scanned by a stand-alone push: every day in peer / two-phase mode, else only
     // after the last day of the window (the next call starts with a scan)
     c.write_ib = (c0.n_peers > 1 || c0.io_mat != nullptr || k == plan.n_days - 1) ? 1 : 0;
+    // this block's run of pieces on that day: its cut was finished at least a day ago (plan_cut runs three days ahead), so
+    // fetching it here -- while the view is built, a day early for every day but the window's first -- costs no round trip later
+    const int32_t* cut = plan.buf.bounds[(plan.first_day + k) % 3];
+    if (cut && gridDim.x > 1 && blockIdx.x > 0) { c.cut_first = __ldcg(cut + blockIdx.x - 1); c.cut_last = __ldcg(cut + blockIdx.x); }
 }
 
 // The service block re-cuts the population for the day after tomorrow: contiguous runs of pieces with equal measured
@@ -1010,8 +1024,8 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             fold_stats(c);
             // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
             // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a
-            // quiet day.  Days = 0, 1 mod 4 refresh the even- and the odd-day cut.)
-            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, const_cast<int32_t*>(c.bounds), c.n_pad >> 7, n_work, sm, tr);
+            // quiet day.  The cut made after day d is the one of day d + 3.)
+            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, c.n_pad >> 7, n_work, sm, tr);
             stamp(11);
         }
         if (peers && wb >= 0 && wb < PUBLISH_BLOCKS) {      // (not the service block: it is busy folding)
