@@ -250,7 +250,10 @@ __device__ __forceinline__ void block_share(const int64_t n, const int n_blocks,
 // agents.  Every block scans a contiguous share, 1024 bytes a step (the next step's word already in flight).
 // ---------------------------------------------------------------------------------------------------------------
 // wb = the block's index among the n_blocks working blocks (-1: a block without a share)
-__device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb)
+// skip_own (peer mode inside a window): the owned agents' rows were already pushed by their blocks after yesterday's
+// agent pass; only the halo agents' bytes, which arrive from the peers, are scanned
+__device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb,
+                                               const bool skip_own = false)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     push_clear_duties(c);
@@ -313,7 +316,7 @@ __device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, B
         // bytes were stored into this GPU's buffer by their owners, who then raised flag[r] = day -- the exchange
         // latency hides behind the local part of the push.  (Persistent grid: all CTAs resident, spinning is safe.)
         const int64_t own0 = c.lo - c.rt_lo, own1 = own0 + c.n_pad < c.rt_n ? own0 + c.n_pad : c.rt_n;
-        scan(own0, own1);
+        if (!skip_own) scan(own0, own1);
         if (tid < c.n_peers && ((c.wait_mask >> tid) & 1u)) {      // only the ranks whose agents are in this rank's halo
             const volatile int32_t* f = c.flag_wait + tid;
             while (*f < day) __nanosleep(32);
@@ -805,26 +808,28 @@ __global__ void __launch_bounds__(BLOCK) k_agent(const DevCtx c, const int day)
 //   single GPU :  scan push of the first day, barrier; then per day  [agent(d) ; push(d+1) of the block's own
 //                 frontier], ONE barrier.  (The last day of the window does not push: tomorrow's open flags arrive
 //                 with the next call.)
-//   peer mode  :  per day  scan push (own rows, wait for the peers' flags, halo rows), barrier, agent, barrier,
-//                 publish the halo part of tomorrow's snapshot bytes to the peers and raise the flag.
+//   peer mode  :  per day  wait for the peers' flags and push the HALO agents' rows (scan of their snapshot bytes), barrier,
+//                 [agent(d) ; push(d+1) of the block's own frontier], barrier, publish the halo part of tomorrow's
+//                 snapshot bytes to the peers and raise the flag.
 // The per-day buffers come from DayPlan; each block keeps today's and tomorrow's view of the context in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 // peer mode: the owned slice of freshly written snapshot bytes (ib_wr[0]) is stored into the same place of every peer
 // GPU's buffer (ib_wr[1..]) with coalesced 16-byte P2P stores over NVLink; the flag is raised afterwards (k_signal, or
 // the tail of a k_days day) once every block's stores are fenced
-__device__ __forceinline__ void publish_body(const DevCtx& c)
+// (pub_idx of n_pub blocks share the copy)
+__device__ __forceinline__ void publish_body(const DevCtx& c, const int pub_idx, const int n_pub)
 {
     // only the part of the owned slice that lies inside the peer's halo travels (pub_lo / pub_n, 16-byte granules)
     for (int p = 1; p < c.n_wr; ++p) {
         const uint4* src = reinterpret_cast<const uint4*>(c.ib_wr[0] + c.pub_lo[p]);
         uint4* dst = reinterpret_cast<uint4*>(c.ib_wr[p] + c.pub_lo[p]);
         const int64_t n16 = c.pub_n[p] >> 4;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+        for (int64_t i = (int64_t)pub_idx * blockDim.x + threadIdx.x; i < n16; i += (int64_t)n_pub * blockDim.x) dst[i] = src[i];
     }
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(BLOCK) k_publish(const DevCtx c) { publish_body(c); }
+__global__ void __launch_bounds__(BLOCK) k_publish(const DevCtx c) { publish_body(c, (int)blockIdx.x, (int)gridDim.x); }
 
 constexpr int MAX_FUSED_DAYS = 14;
 constexpr int PUBLISH_BLOCKS = 8;          // the halo part of a slice is small (one community per neighbour)
@@ -994,7 +999,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     for (int k = 0; k < plan.n_days; ++k) {
         const int day = plan.first_day + k;
         const DevCtx& c = s_c[k & 1];
-        const bool local_push = !two_phase && k + 1 < plan.n_days;
+        const bool local_push = c0.io_mat == nullptr && k + 1 < plan.n_days;
         if (threadIdx.x == 0 && k + 1 < plan.n_days) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1);
         __syncthreads();
         unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * TRACE_SLOTS : nullptr;
@@ -1007,7 +1012,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         };
         stamp(0);
         if (k == 0 || two_phase) {
-            push_scan_body(c, day, sm, n_work, wb);
+            push_scan_body(c, day, sm, n_work, wb, peers && k > 0);
             stamp(1);
             grid_barrier(barrier_counter, epoch);
         }
@@ -1028,12 +1033,13 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, c.n_pad >> 7, n_work, sm, tr);
             stamp(11);
         }
-        if (peers && wb >= 0 && wb < PUBLISH_BLOCKS) {      // (not the service block: it is busy folding)
+        const int n_pub = PUBLISH_BLOCKS < n_work ? PUBLISH_BLOCKS : n_work;
+        if (peers && wb >= 0 && wb < n_pub) {      // (not the service block: it is busy folding)
             // a few CTAs ship tomorrow's bytes to the peers while the others already start the next day (whose push
             // waits for the peers' flags anyway); the last shipper raises this rank's flag on every GPU
-            publish_body(c);
+            publish_body(c, wb, n_pub);
             __syncthreads();
-            if (threadIdx.x == 0) s_pub_last = (atomicAdd(barrier_counter + 1, 1u) == PUBLISH_BLOCKS - 1);
+            if (threadIdx.x == 0) s_pub_last = (atomicAdd(barrier_counter + 1, 1u) == (unsigned)n_pub - 1u);
             __syncthreads();
             if (s_pub_last) {
                 if (threadIdx.x == 0) barrier_counter[1] = 0u;
