@@ -1,5 +1,5 @@
 // C ABI of the B200-native epidemic step (include/dysturbd.h).  Host-side bookkeeping only: owns the device
-// structure-of-arrays, launches the kernels of dys_kernels.cuh on one stream, and moves the small per-day
+// device arrays, launches the kernels of dys_day.cuh / dys_load.cuh on one stream, and moves the small per-day
 // integer outputs to pinned host memory.  No CPU implementation of any phase lives here.
 #include "../../include/dysturbd.h"
 
@@ -40,7 +40,7 @@ struct dys_handle {
     int64_t nnz = 0, nnz_kept = 0;
     int32_t last_day = -1;
     int64_t steps = 0;
-    // per-parity device output block [stats | sa_hist | bcount | events] and the pinned host ring it is copied into
+    // one device output block [stats | sa_hist | bcount | events] per ring slot and the pinned host ring it is copied into
     unsigned char* d_out[DYS_OUT_RING] = {};          // device output blocks, one per ring slot (slot = step % ring)
     size_t off_sa = 0, off_bc = 0, off_ev = 0, out_copy_bytes = 0, out_dev_bytes = 0;
     int64_t ev_inline = 0;
@@ -277,7 +277,7 @@ extern "C" int dys_destroy(dys_handle* h)
     return DYS_OK;
 }
 
-// state was (re)loaded: the snapshot, the per-parity flags and the partial sums start clean
+// state was (re)loaded: the snapshot, attention bytes, mailboxes, flag rings, partial sums and the cut start clean
 static int reset_day_scratch(dys_handle* h)
 {
     DevCtx& c = h->c;

@@ -57,3 +57,36 @@ def test_one_million_agents_properties():
         assert (st["t_inf"][src] < d).all() if len(a) else True
     assert ever_prev > 20_000
     g.close()
+
+
+def test_fused_windows_equal_single_days_at_scale():
+    """The product path (dys_step_many: k_days, one grid barrier per day, blocks pushing their own frontier, the daily
+    equal-work cut over more than one staging chunk of pieces) against the two-launch path (dys_step, itself checked
+    against the oracle above) on a population larger than BASELINE.json's: state, counts, histograms, per-area and
+    per-building outputs and the set of infection events must be identical on every day."""
+    from dysturbd_b200 import engine
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import COMMUNITY, synth_population
+    pop = synth_population(COMMUNITY * 107, seed=3, seeds_per_22493=120)      # 1.2 M agents: 9 416 pieces of 128
+    prm = EpiParams(norm_factor=8.0, seed=11)
+    a = engine.Engine(pop, prm)      # windows
+    b = engine.Engine(pop, prm)      # single days
+    day = 0
+    for n in (7, 7, 3, 7, 5, 7, 7, 2, 7, 7):
+        a.step_many(day, n)
+        for k in range(n):
+            d = day + k
+            b.step(d)
+            oa, sb = a.outputs(d), b.stats(d)
+            assert np.array_equal(oa["stats"][:14], sb[:14]), "day %d: %s vs %s" % (d, oa["stats"][:14], sb[:14])
+            assert np.array_equal(oa["stats"][18:28], sb[18:28]) and np.array_equal(oa["stats"][32:53], sb[32:53]), "day %d" % d
+            assert np.array_equal(oa["sa_hist"], b.sa_hist(d)) and np.array_equal(oa["building_counts"], b.building_counts(d)), "day %d" % d
+            ea, eb = a.events(d), b.events(d)
+            assert np.array_equal(ea[0], eb[0]) and np.array_equal(ea[1], eb[1]), "events day %d" % d
+        sa, sb = a.state(), b.state()
+        for key in sa:
+            assert np.array_equal(sa[key], sb[key]), "%s after day %d" % (key, day + n - 1)
+        day += n
+    assert int(b.stats(day - 1)[9]) > 50_000      # a real epidemic: blocks settle and push unevenly
+    a.close()
+    b.close()
