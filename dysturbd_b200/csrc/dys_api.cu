@@ -864,6 +864,7 @@ extern "C" int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out)
     out->events = (h->p.flags & DYS_WANT_EVENTS) ? (const int32_t*)(base + h->off_ev) : nullptr;
     out->n_events = out->stats[ST_N_EVENTS];
     out->events_inline = (int32_t)(out->n_events < h->ev_inline ? out->n_events : h->ev_inline);
+    out->events_capacity = h->ev_inline;
     return DYS_OK;
 }
 

@@ -51,7 +51,8 @@ class _Params(C.Structure):
 
 class _DayOutputs(C.Structure):
     _fields_ = [("day", C.c_int32), ("events_inline", C.c_int32), ("n_events", C.c_int64), ("stats", C.POINTER(C.c_int64)),
-                ("sa_hist", C.POINTER(C.c_int32)), ("building_counts", C.POINTER(C.c_int32)), ("events", C.POINTER(C.c_int32))]
+                ("sa_hist", C.POINTER(C.c_int32)), ("building_counts", C.POINTER(C.c_int32)), ("events", C.POINTER(C.c_int32)),
+                ("events_capacity", C.c_int64)]
 
 
 class _Injected(C.Structure):
@@ -271,7 +272,8 @@ class Engine:
             as_np = np.ctypeslib.as_array
             views = (as_np(o.stats, (N_STATS,)),
                      as_np(o.sa_hist, (self.S_out, HIST_LEN)) if o.sa_hist else None,
-                     as_np(o.building_counts, (self.B_out,)) if o.building_counts else None)
+                     as_np(o.building_counts, (self.B_out,)) if o.building_counts else None,
+                     as_np(o.events, (int(o.events_capacity), 2)) if o.events and o.events_capacity else None)
             self._views[key] = views
         n_ev, n_in = int(o.n_events), int(o.events_inline)
         ev = None
@@ -279,8 +281,8 @@ class Engine:
             if n_ev > n_in:                                # rare: more infections than travel with the day's block
                 a, s_ = self.events(day)
                 ev = np.stack([a, s_], axis=1)
-            elif n_in:
-                ev = np.ctypeslib.as_array(o.events, (n_in, 2))
+            elif views[3] is not None:
+                ev = views[3][:n_in]                       # (a slice of the slot's cached view: no per-day ctypes cast)
             else:
                 ev = np.zeros((0, 2), dtype=np.int32)
         return {"stats": views[0], "sa_hist": views[1], "building_counts": views[2], "events": ev, "n_events": n_ev}

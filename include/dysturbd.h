@@ -182,6 +182,7 @@ typedef struct dys_day_outputs {
     const int32_t* sa_hist;      /* [S*DYS_HIST_LEN] or NULL */
     const int32_t* building_counts; /* [B] or NULL */
     const int32_t* events;       /* [events_inline][2] = (infected, infector) row indices, or NULL */
+    int64_t events_capacity;     /* pairs the block can carry: events[0 .. events_capacity) is addressable on every day */
 } dys_day_outputs;
 int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out);
 /* P for every evaluated pair of the most recent day (tests; requires injected mode): out[N*N] */
