@@ -176,6 +176,47 @@ class EpidemicModel:
         self.day += 1
         return S
 
+    # ---- the reference's output file and a resumable snapshot ----
+    def write_json(self, path, total_time=None):
+        """outputs as contagious3.py:389-392 writes them (`json.dump(outputs)`; the day and area keys become strings
+        exactly as they do there), so create_figures.py reads a run of this library unchanged"""
+        import json
+        out = dict(self.outputs)
+        if total_time is not None:
+            out['Total_time'] = float(total_time)                                                # :390
+        with open(path, 'w') as f:
+            json.dump(out, f)
+
+    def checkpoint(self):
+        """everything needed to continue this run in another process: the agent columns the day mutates, the host's
+        R history (the lockdown decision lags `diagnosis` days), the flags in force, the np.random.choice stream and the
+        outputs so far.  Only valid between days (nothing queued ahead of the consumed day)."""
+        import copy
+        if self._queued != self.day:
+            raise RuntimeError("checkpoint() with days in flight: call it from step(), not inside run()")
+        if hasattr(self.sim, "sync"):
+            self.sim.sync()
+        return {'day': self.day, 'state': {k: np.array(v) for k, v in self.sim.state().items()}, 'R': dict(self._R),
+                'flags': {d: np.array(f) for d, f in self._flags.items()}, 'active': self._active,
+                'choice_state': self._choice.__self__.get_state(), 'outputs': copy.deepcopy(self.outputs),
+                'scenario': list(self.scenario)}
+
+    def restore(self, ck):
+        """continue from checkpoint(): the population (static columns, network) must be the one the run started with"""
+        import copy
+        if list(ck['scenario']) != self.scenario:
+            raise ValueError("checkpoint of scenario %s restored into %s" % (ck['scenario'], self.scenario))
+        st = ck['state']
+        self.sim.set_state(st['status'], st['t_inf'], st['t_q'], st['t_adm'], st['src'])
+        self.day = self._queued = int(ck['day'])
+        self._R = dict(ck['R'])
+        self._flags = {d: np.array(f) for d, f in ck['flags'].items()}
+        self._active = int(ck['active'])
+        self._choice.__self__.set_state(ck['choice_state'])
+        self.outputs = copy.deepcopy(ck['outputs'])
+        if hasattr(self.sim, "set_open"):
+            self.sim.set_open(self._flags_for(self.day).astype(np.uint8))
+
     def step(self):
         """one day, queued and consumed (contagious3.py:176-387)"""
         if self._queued == self.day:

@@ -133,6 +133,14 @@ class OracleSim:
     def set_open(self, open_flags):
         self.open[:] = np.asarray(open_flags, dtype=np.uint8)
 
+    def set_state(self, status, t_inf, t_q, t_adm, src):
+        """the mutable agent columns, in place (same surface as Engine.set_state)"""
+        self.status[:] = np.asarray(status, dtype=np.uint8)
+        self.t_inf[:] = np.asarray(t_inf, dtype=np.int32)
+        self.t_q[:] = np.asarray(t_q, dtype=np.int32)
+        self.t_adm[:] = np.asarray(t_adm, dtype=np.int32)
+        self.src[:] = np.asarray(src, dtype=np.int32)
+
     def step(self, day, u_adm=None, u_death=None, u_pair=None):
         keep = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None for x in (u_adm, u_death, u_pair)]
         self.ctx.u_adm, self.ctx.u_death, self.ctx.u_pair = map(_p, keep)

@@ -67,6 +67,28 @@ def test_epidemic_model_outputs_match_reference(name, eng):
     assert np.array_equal(chain[:, 1], fx.exp["t_inf"][fx.days - 1]) and np.array_equal(chain[:, 2], fx.exp["src_id"][fx.days - 1])
 
 
+def test_checkpoint_resume_and_json_on_gpu(eng, tmp_path):
+    """stop after 9 days, continue from checkpoint() in a new model on the GPU (dys_set_state), finish with run() (fused
+    windows): the reference's outputs, and the JSON file create_figures.py would read"""
+    import json
+    from dysturbd_b200.host import EpidemicModel
+    fx = Fixture("city300_philox_gradual_all")
+    mk = lambda: EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
+                               choice_seed=fx.meta["choice_seed"])
+    a = mk()
+    for _ in range(9):
+        a.step()
+    ck = a.checkpoint()
+    b = mk()
+    b.restore(ck)
+    out = b.run(max_days=fx.days)
+    compare_outputs(out, fx.outputs, fx.days)
+    path = tmp_path / "sim0.json"
+    b.write_json(path)
+    got = json.load(open(path))
+    assert got["Results"]["Stats"] == fx.outputs["Results"]["Stats"] and got["Results"]["IO_mat"] == fx.outputs["Results"]["IO_mat"]
+
+
 def _closures(pop, seed):
     rs = np.random.RandomState(seed)
 

@@ -42,3 +42,43 @@ def test_quirk_household_zero_fires(oracle_lib):
     sim = oracle_lib.OracleSim(pop, fx.params)
     with pytest.raises(AssertionError):
         run_against_fixture(sim, fx)
+
+
+def test_written_json_is_the_reference_file(oracle_lib, tmp_path):
+    """EpidemicModel.write_json == what contagious3.py:389-392 dumps: the golden `outputs` were stored after a JSON round
+    trip of the reference's dict, so the file this library writes must load to exactly that (every key, every float)."""
+    import json
+    from dysturbd_b200.host import EpidemicModel
+    fx = Fixture("city300_philox_gradual_all")
+    m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
+                      choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim)
+    m.run(max_days=fx.days)
+    path = tmp_path / "sim0.json"
+    m.write_json(path, total_time=1.5)
+    got = json.load(open(path))
+    assert got["Total_time"] == 1.5
+    for key in ("Stats", "SAs", "Buildings", "IO_mat"):
+        assert got["Results"][key] == {d: fx.outputs["Results"][key][d] for d in got["Results"][key]}, key
+        assert len(got["Results"][key]) == fx.days
+    assert len(got["Results"]["Infections chain"]) == fx.pop.N
+
+
+def test_checkpoint_and_resume(oracle_lib):
+    """a run stopped after 9 days and continued from checkpoint() in a NEW model equals the uninterrupted run: agent
+    state, the host's R history (the lockdown decision lags 7 days), the flags and the np.random.choice stream all travel"""
+    from dysturbd_b200.host import EpidemicModel
+    fx = Fixture("city300_philox_gradual_all")
+    mk = lambda: EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
+                               choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim)
+    a = mk()
+    for _ in range(9):
+        a.step()
+    ck = a.checkpoint()
+    b = mk()
+    b.restore(ck)
+    while b.day < fx.days and b.active():
+        b.step()
+    compare_outputs(b.outputs, fx.outputs, fx.days)
+    assert np.array_equal(b.open.astype(np.uint8), fx.exp["open_next"][fx.days - 1])
+    st = b.sim.state()
+    assert np.array_equal(st["status"], fx.exp["status_x2"][fx.days - 1]) and np.array_equal(st["t_q"], fx.exp["t_q"][fx.days - 1])
