@@ -376,7 +376,12 @@ def run_ours(args):
         "gpu_launches": -(-K // 7),  # one cooperative k_days launch per 7-day window (k_snapshot only after a load)
         "kernels_ms_per_step": {n: ms_k[i] / max(1, n_k[i]) for i, n in enumerate(engine.KERNEL_NAMES)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_days launch / its 7 simulated days, from the
+                     # committed ncu --set full capture (profiles/r01k_summary.md: days 66-72, the peak week, whose
+                     # algorithmic bytes are ~8 MB per day); not measured live
+                     "traffic": (49410560 + 2254080) / 7 if world == 1 and args.communities_per_gpu == 89 else None,
+                     "traffic_note": "per simulated day, peak week of the epidemic (ncu capture of 2026-10-20, profiles/r01k_summary.md)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": kbytes / max(1, K), "ms_per_launch": k_ms,
                      "note": "algorithmic bytes = what THIS design must move per day (bench.py kernel_bytes, DESIGN.md); a "
