@@ -238,6 +238,7 @@ def run_ours(args):
         # the K timed days are days 0 .. W+K-1 of the real run.
         run_resident(0, min(W + K, 150))
         raw(eng).sync()
+        barrier()                    # (peer mode: no rank resets its flags while a slower peer still signals spin-up days)
         eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
         barrier()                    # (peer mode: nobody steps before every rank has reset its flags)
         run_resident(0, W)
