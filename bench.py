@@ -232,15 +232,6 @@ def run_ours(args):
             d += n
 
     with torch.cuda.stream(stream):
-        # Clock spin-up (untimed, results discarded): the GPU idled while the population was generated on the host, and the
-        # first milliseconds after idle run far below the boost clock (a 30-day run measured 106 us per day instead of 21).
-        # A throw-away replica of the first days brings the clocks up; the state is then reset, so the W warm-up days and
-        # the K timed days are days 0 .. W+K-1 of the real run.
-        run_resident(0, min(W + K, 150))
-        raw(eng).sync()
-        barrier()                    # (peer mode: no rank resets its flags while a slower peer still signals spin-up days)
-        eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
-        barrier()                    # (peer mode: nobody steps before every rank has reset its flags)
         run_resident(0, W)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
