@@ -97,3 +97,22 @@ def test_synth_layout_and_shards_agree():
     assert abs(m - m.T).max() == 0
     same = full.hh[np.repeat(np.arange(n), np.diff(full.ip_rowptr))] == full.hh[full.ip_col]
     assert (full.ip_val[same] == 1.0).all()
+
+
+def test_window_length_follows_the_lockdown_lag():
+    """EpidemicModel queues days in windows it can decide the open flags for: Known R lags `diagnosis` days
+    (contagious3.py:306-309), so two windows of (diagnosis + 1) // 2 days never need an unconsumed day; a scenario that
+    closes nothing has constant flags and takes week-long windows."""
+    from dysturbd_b200.host import EpidemicModel
+
+    class Dummy:                                   # no device: only the constructor logic is exercised
+        def __init__(self, pop, params):
+            pass
+    pop = synth_population(2000, seed=2)
+    agents, build, visits, ip = to_reference(pop)
+    mk = lambda sc, **kw: EpidemicModel(agents, build, visits, ip, scenario=sc, params=EpiParams(**kw), backend=Dummy, population=pop)
+    assert mk(['noLockdown']).window == 7
+    assert mk(['GRADUAL', 'ALL']).window == 4
+    assert mk(['EDU', 'REL']).window == 4
+    assert mk(['ALL'], diagnosis=3).window == 2
+    assert mk(['ALL'], diagnosis=1).window == 1
