@@ -27,6 +27,15 @@ def compute_R_from_hist(hist, pdf, recover):
     return new_infections / sum_I if sum_I > 0 else 0
 
 
+def compute_R_rows(sa_hist, pdf, recover):
+    """compute_R_from_hist for every row of a [S, 21] histogram at once, bit for bit: np.cumsum accumulates sequentially
+    (np.sum would not: it sums pairwise), which is the reference's `sum_I += n * pdf(i)` order; 0.0 + x is exact."""
+    prod = sa_hist[:, 1:recover].astype(np.float64) * np.asarray(pdf[1:recover], dtype=np.float64)
+    sum_I = np.cumsum(prod, axis=1)[:, -1] if prod.shape[1] else np.zeros(len(sa_hist))
+    new = sa_hist[:, 0].astype(np.float64)
+    return np.where(sum_I > 0, new / np.where(sum_I > 0, sum_I, 1.0), 0.0)
+
+
 def building_lockdown(lu, usg, current, sc, vR, prevVR, choice):
     """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
     (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice."""
@@ -75,11 +84,16 @@ class EpidemicModel:
     MAX_WINDOW = 7
 
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
-                 device=0, choice_seed=None, backend=None, population=None):
+                 device=0, choice_seed=None, backend=None, population=None, compact=False):
         self.params = params or EpiParams()
         self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob)
         self.scenario = list(scenario)
         self.sim = backend(self.pop, self.params) if backend is not None else Engine(self.pop, self.params, device=device)
+        # compact=True: 'SAs', 'Buildings' and 'IO_mat' hold numpy arrays instead of the reference's nested dicts and
+        # lists (same numbers: per-area R [S], vis_R [S]; per inhabited building count and fraction [n, 2]; the day's
+        # (infected, infector) area indices [n_events, 2]).  The reference's schema costs O(S^2 + B) Python objects per
+        # day -- fine for its 19 areas, 50 ms per day for a million agents.  'Stats' is always the reference's dict.
+        self.compact = bool(compact)
         self.day = 0                 # next day to consume
         self.outputs = {'Results': {'Stats': {}, 'Buildings': {}, 'SAs': {}, 'IO_mat': {}}}
         self._choice = np.random.RandomState(choice_seed).choice
@@ -150,10 +164,14 @@ class EpidemicModel:
         hist = st[HIST0:HIST0 + HIST_LEN]
         R = compute_R_from_hist(hist, self._pdf, prm.recover)
         self._R[day] = R
-        sas = [float(x) for x in p.sa_ids]
-        res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
         vis_R = self._known_R(day)
-        res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
+        if self.compact:
+            R_sa = compute_R_rows(np.asarray(sa_hist)[:p.S], self._pdf, prm.recover)
+            res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - prm.diagnosis]['R'] if day > prm.diagnosis else np.zeros(p.S)}
+        else:
+            sas = [float(x) for x in p.sa_ids]
+            res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
+            res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
         new_infections = int(st[STAT['daily_inf']])
         S = {'Active infected': int(st[STAT['active']]), 'Daily infections': new_infections,
              'Recovered': int(st[STAT['recovered']]), 'Quarantined': int(st[STAT['quarantined']]),
@@ -166,12 +184,17 @@ class EpidemicModel:
             S['Total infected'] = res['Stats'][day - 1]['Total infected'] + new_infections
         S['Susceptible'] = p.N - S['Total infected']
         res['Stats'][day] = S
-        res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
-        mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                       # :356-366
-        if len(ev_a):
-            for a, s in zip(p.sa[ev_a], p.sa[ev_s]):
-                mat[sas[a]][sas[s]] += 1
-        res['IO_mat'][day] = mat
+        if self.compact:
+            cnt = np.asarray(bc)[self._inhabited].astype(np.float64)
+            res['Buildings'][day] = np.stack([cnt, cnt / self._bld_pop[self._inhabited]], axis=1)
+            res['IO_mat'][day] = np.stack([p.sa[ev_a], p.sa[ev_s]], axis=1) if len(ev_a) else np.zeros((0, 2), dtype=p.sa.dtype)
+        else:
+            res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
+            mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                   # :356-366
+            if len(ev_a):
+                for a, s in zip(p.sa[ev_a], p.sa[ev_s]):
+                    mat[sas[a]][sas[s]] += 1
+            res['IO_mat'][day] = mat
         self._active = S['Active infected']
         self.day += 1
         return S
@@ -181,6 +204,8 @@ class EpidemicModel:
         """outputs as contagious3.py:389-392 writes them (`json.dump(outputs)`; the day and area keys become strings
         exactly as they do there), so create_figures.py reads a run of this library unchanged"""
         import json
+        if self.compact:
+            raise ValueError("write_json writes the reference's schema: run the model with compact=False")
         out = dict(self.outputs)
         if total_time is not None:
             out['Total_time'] = float(total_time)                                                # :390

@@ -82,3 +82,29 @@ def test_checkpoint_and_resume(oracle_lib):
     assert np.array_equal(b.open.astype(np.uint8), fx.exp["open_next"][fx.days - 1])
     st = b.sim.state()
     assert np.array_equal(st["status"], fx.exp["status_x2"][fx.days - 1]) and np.array_equal(st["t_q"], fx.exp["t_q"][fx.days - 1])
+
+
+def test_compact_outputs_hold_the_same_numbers(oracle_lib):
+    """compact=True (arrays instead of the reference's nested dicts, for populations with hundreds of areas) carries
+    exactly the reference's values: per-area R and vis_R (floats compared with ==), building counts and fractions, and
+    the origin matrix rebuilt from the day's (infected area, infector area) pairs."""
+    from dysturbd_b200.host import EpidemicModel
+    fx = Fixture("city800_philox_edu_rel")
+    m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
+                      choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim, compact=True)
+    out = m.run(max_days=fx.days)["Results"]
+    sas = [float(x) for x in m.pop.sa_ids]
+    for d in range(fx.days):
+        exp = fx.outputs["Results"]
+        assert out["Stats"][d] == exp["Stats"][str(d)]
+        for k, sa in enumerate(sas):
+            assert out["SAs"][d]["R"][k] == exp["SAs"][str(d)]["R"][str(sa)], (d, sa)
+            assert out["SAs"][d]["vis_R"][k] == exp["SAs"][str(d)]["vis_R"][str(sa)], (d, sa)
+        eb = exp["Buildings"][str(d)]
+        assert len(eb) == len(out["Buildings"][d])
+        for row, (bid, cnt, frac) in zip(out["Buildings"][d], eb):
+            assert row[0] == cnt and row[1] == frac
+        mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}
+        for a, s in out["IO_mat"][d]:
+            mat[sas[a]][sas[s]] += 1
+        assert {str(a): {str(b): v for b, v in r.items()} for a, r in mat.items()} == exp["IO_mat"][str(d)]
