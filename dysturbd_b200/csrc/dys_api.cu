@@ -29,8 +29,20 @@ struct dys_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // the day's output block leaves on its own stream, under the next day's kernels
     cudaEvent_t day_done[DYS_OUT_RING] = {};        // per ring slot: the day's kernels finished writing the block
-    uint8_t* d_open_ring = nullptr;                 // [MAX_FUSED_DAYS][B] per-day open flags of a fused window
-    uint8_t* h_open_ring = nullptr;                 // pinned staging of the same
+    // per-day open flags of a fused window: two staging rings by window parity, uploaded on their own stream so that the
+    // flags of window w + 1 travel while window w runs
+    uint8_t* d_open_ring[2] = {};                   // [MAX_FUSED_DAYS][B]
+    uint8_t* h_open_ring[2] = {};                   // pinned staging of the same
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t up_done[2] = {}, ring_free[2] = {};
+    bool ring_used[2] = {false, false};
+    int64_t windows = 0;
+    int R = 1;                                      // replicas
+    int sel = -1;                                   // dys_select_replica
+    std::vector<RepParam> rep;                      // host copy of the per-replica parameters
+    RepParam* d_rep = nullptr;
+    volatile int32_t* h_abort = nullptr;            // pinned + mapped: the kernels poll it in their spin loops
+    int64_t h2d_bytes = 0;                          // flag bytes uploaded so far (bench accounting)
     unsigned int* d_barrier = nullptr;              // grid barrier counter of k_days
     int days_grid = 0;                              // cooperative grid of k_days (0 = not available)
     std::vector<void*> allocs;
@@ -48,10 +60,10 @@ struct dys_handle {
     int32_t out_day[DYS_OUT_RING];
     int64_t out_step[DYS_OUT_RING];
     cudaEvent_t out_ev[DYS_OUT_RING];
-    int64_t hist_stats[DYS_STATS_RING][N_STATS];          // stats of days that left the output ring
+    std::vector<int64_t> hist_stats;                      // [DYS_STATS_RING][R][N_STATS] stats of days that left the output ring
     int32_t hist_day[DYS_STATS_RING];
     uint8_t* h_open = nullptr;                            // pinned shadow of the open flags
-    int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags
+    int32_t* h_small = nullptr;      // pinned scratch: [0] validation flags, [1] r_idle_day
     int32_t* d_bad = nullptr;
     DayBuffers buf{};                // attention bytes, mailboxes, quirk flags, flag blocks, partial sums: rings indexed by day
     int32_t ib_day = -1;             // the day whose day-start snapshot bytes are complete in buffer ib_day & 1
@@ -108,6 +120,23 @@ static int dev_alloc(dys_handle* h, T** out, int64_t count, bool zero = true)
     return DYS_OK;
 }
 
+// release one tracked allocation early (a re-loaded network / quirk table)
+static void dev_free(dys_handle* h, const void* p)
+{
+    if (!p) return;
+    for (size_t i = 0; i < h->allocs.size(); ++i)
+        if (h->allocs[i] == p) { h->allocs.erase(h->allocs.begin() + (long)i); break; }
+    cudaFree(const_cast<void*>(p));
+}
+
+static int check_abort(dys_handle* h)
+{
+    if (h->h_abort && *h->h_abort)
+        return fail(h, DYS_ERR_ABORTED, "a launch was abandoned (%s); reload the state with dys_set_state",
+                    *h->h_abort == 2 ? "a grid barrier or peer wait timed out: DYS_SPIN_TIMEOUT_MS" : "dys_abort");
+    return DYS_OK;
+}
+
 static int copy_in(dys_handle* h, void* dst, const void* src, size_t bytes)
 {
     if (bytes == 0) return DYS_OK;
@@ -129,7 +158,16 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     if (p.n_agents <= 0 || p.n_agents > (int64_t)COL_MASK + 1) return fail(nullptr, DYS_ERR_INVALID_ARG, "n_agents must be in [1, 2^27]");
     if (p.n_households <= 0 || p.n_buildings <= 0 || p.n_areas < 0) return fail(nullptr, DYS_ERR_INVALID_ARG, "bad H/B/S");
     if (p.n_slots < 1 || p.n_slots > 16) return fail(nullptr, DYS_ERR_INVALID_ARG, "n_slots must be in [1,16]");
+    // the day-ahead household prediction needs diagnosis >= 1; compute_R (contagious3.py:29-42) sums bins 1..recover-1 of
+    // the 21-bin days-since-infection histogram
+    if (p.diagnosis < 1 || p.quarantine < 1 || p.recover < 1 || p.recover > HIST_LEN || p.hospital_recover < 1)
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "need diagnosis >= 1, quarantine >= 1, 1 <= recover <= %d, hospital_recover >= 1", HIST_LEN);
+    if (!(p.compliance >= 0.0 && p.compliance <= 1.0)) return fail(nullptr, DYS_ERR_INVALID_ARG, "compliance must be in [0, 1]");
     const int world = p.world > 1 ? p.world : 1;
+    const int R = p.n_replicas > 1 ? p.n_replicas : 1;
+    if (R > 4096) return fail(nullptr, DYS_ERR_INVALID_ARG, "n_replicas must be <= 4096");
+    if (R > 1 && (world > 1 || (p.flags & (DYS_WANT_IO_MAT | DYS_TIME_KERNELS))))
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "replicas are single-GPU (spread handles over GPUs) and exclude DYS_WANT_IO_MAT / DYS_TIME_KERNELS");
     int64_t lo = 0, hi = p.n_agents;
     if (world > 1) {
         lo = p.shard_lo; hi = p.shard_hi;
@@ -138,65 +176,83 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     }
     if ((p.flags & DYS_WANT_IO_MAT) && p.n_areas * p.n_areas > (int64_t)1 << 26)
         return fail(nullptr, DYS_ERR_INVALID_ARG, "DYS_WANT_IO_MAT needs S*S <= 2^26; use dys_get_events");
+    if (p.halo_hi > p.halo_lo && (p.halo_lo < 0 || p.halo_hi > p.n_agents || p.halo_lo > lo || p.halo_hi < hi))
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "halo must contain the owned range");
+    if (p.hh_hi > p.n_households || p.bld_hi > p.n_buildings || p.area_hi > p.n_areas || p.hh_lo < 0 || p.bld_lo < 0 || p.area_lo < 0)
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "owned household / building / area range outside the population");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, DYS_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(nullptr, DYS_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
-    dys_handle* h = new dys_handle();
+    dys_handle* h = new dys_handle();      // (from here on every failure goes through dys_destroy)
     h->p = p;
     h->device = device;
+    h->R = R;
+    for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; h->out_ev[i] = nullptr; }
+    for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
+    h->hist_stats.assign((size_t)DYS_STATS_RING * R * N_STATS, 0);
+    h->rep.assign((size_t)R, RepParam{p.norm_factor, p.compliance, p.seed});
     { const char* nf = getenv("DYS_NO_FUSE"); h->no_fuse = nf && nf[0] == '1'; }
     h->trace_path = getenv("DYS_TRACE");
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking);
     for (int k = 0; k < DYS_OUT_RING && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&h->day_done[k], cudaEventDisableTiming);
-    if (e != cudaSuccess) { fail(nullptr, DYS_ERR_CUDA, "cuda init: %s", cudaGetErrorString(e)); delete h; return DYS_ERR_CUDA; }
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&h->up_done[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ring_free[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { fail(nullptr, DYS_ERR_CUDA, "cuda init: %s", cudaGetErrorString(e)); dys_destroy(h); return DYS_ERR_CUDA; }
     DevCtx& c = h->c;
     c.n_loc = hi - lo; c.n_pad = round_up(c.n_loc, 1024); c.n_glob = p.n_agents; c.lo = lo;
     c.rt_lo = 0; c.rt_n = p.n_agents;
-    if (p.halo_hi > p.halo_lo) {
-        if (p.halo_lo < 0 || p.halo_hi > p.n_agents || p.halo_lo > lo || p.halo_hi < hi) { delete h; return fail(nullptr, DYS_ERR_INVALID_ARG, "halo must contain the owned range"); }
-        c.rt_lo = p.halo_lo; c.rt_n = p.halo_hi - p.halo_lo;
-    }
+    if (p.halo_hi > p.halo_lo) { c.rt_lo = p.halo_lo; c.rt_n = p.halo_hi - p.halo_lo; }
     c.H = p.n_households; c.B = p.n_buildings; c.S = p.n_areas; c.V = p.n_slots;
     c.B_out = c.B; c.S_out = c.S;
     h->hh_lo = h->bld_lo = h->area_lo = 0;
     if (p.hh_hi > p.hh_lo) { h->hh_lo = p.hh_lo; c.H = p.hh_hi - p.hh_lo; }
     if (p.bld_hi > p.bld_lo) { h->bld_lo = p.bld_lo; c.B_out = p.bld_hi - p.bld_lo; }
     if (p.area_hi > p.area_lo) { h->area_lo = p.area_lo; c.S_out = p.area_hi - p.area_lo; }
-    if (p.hh_hi > p.n_households || p.bld_hi > p.n_buildings || p.area_hi > p.n_areas || p.hh_lo < 0 || p.bld_lo < 0 || p.area_lo < 0) {
-        delete h; return fail(nullptr, DYS_ERR_INVALID_ARG, "owned household / building / area range outside the population");
-    }
     c.recover = p.recover; c.hospital_recover = p.hospital_recover; c.diagnosis = p.diagnosis; c.quarantine = p.quarantine;
     c.adm_min = p.adm_min_day; c.adm_max = p.adm_max_day; c.death_min = p.death_min_adm_day;
     c.norm_factor = p.norm_factor; c.compliance = p.compliance; c.seed = p.seed;
+    c.n_rep = R; c.rep = 0; c.r_idle_day = 0;
+    {
+        const char* t = getenv("DYS_SPIN_TIMEOUT_MS");
+        const double ms = t ? atof(t) : 20000.0;
+        c.spin_timeout_ns = ms > 0 ? (unsigned long long)(ms * 1e6) : 0ull;
+    }
     int rc = DYS_OK;
     auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
     double* d_pdf = nullptr;
-    A(dev_alloc(h, &c.status, c.n_pad)); A(dev_alloc(h, &c.rec, c.n_pad)); A(dev_alloc(h, &c.src, c.n_pad));
+    // everything mutable exists once per replica, replica r at r * stride (shift_replica)
+    A(dev_alloc(h, &c.status, c.n_pad * R)); A(dev_alloc(h, &c.rec, c.n_pad * R)); A(dev_alloc(h, &c.src, c.n_pad * R));
     A(dev_alloc(h, (int32_t**)&c.hh, c.n_pad));
     A(dev_alloc(h, (double**)&c.risk, c.n_pad)); A(dev_alloc(h, (double**)&c.p_adm, c.n_pad)); A(dev_alloc(h, (double**)&c.p_death, c.n_pad));
     A(dev_alloc(h, (int32_t**)&c.routine, c.rt_n * c.V));
     h->ib_stride = round_up(c.n_glob, 1024) + 1024;
-    A(dev_alloc(h, &h->d_ib, 2 * h->ib_stride));
+    c.ib_stride = h->ib_stride;
+    A(dev_alloc(h, &h->d_ib, 2 * h->ib_stride * R));
     A(dev_alloc(h, &h->d_peer_flags, 8));
     A(dev_alloc(h, (uint8_t**)&c.open, c.B));
     for (int k = 0; k < 2; ++k) {
-        A(dev_alloc(h, &h->buf.att[k], c.n_pad + 16));
-        A(dev_alloc(h, &h->buf.mb_any[k], c.n_pad)); A(dev_alloc(h, &h->buf.mb_iso[k], c.n_pad));
-        h->buf.ib[k] = h->d_ib + (size_t)k * h->ib_stride;
+        A(dev_alloc(h, &h->buf.att[k], (c.n_pad + 16) * R));
+        A(dev_alloc(h, &h->buf.mb_any[k], c.n_pad * R)); A(dev_alloc(h, &h->buf.mb_iso[k], c.n_pad * R));
+        h->buf.ib[k] = h->d_ib + (size_t)k * h->ib_stride * R;
         for (int r = 0; r < 8; ++r) h->buf.peer_ib[r][k] = h->buf.ib[k];
     }
-    for (int k = 0; k < Q_RING; ++k) A(dev_alloc(h, &h->buf.qflag[k], c.H + 16));
-    A(dev_alloc(h, &h->buf.df, DF_RING * DF_LEN));
-    A(dev_alloc(h, &h->buf.part, (int64_t)PART_RING * N_SLOTS * N_STATS)); A(dev_alloc(h, &c.ticket, 1));
+    for (int k = 0; k < Q_RING; ++k) A(dev_alloc(h, &h->buf.qflag[k], (c.H + 16) * R));
+    A(dev_alloc(h, &h->buf.df, (int64_t)DF_RING * DF_LEN * R));
+    A(dev_alloc(h, &h->buf.part, (int64_t)PART_RING * N_SLOTS * N_STATS * R)); A(dev_alloc(h, &c.ticket, 1));
     A(dev_alloc(h, (int64_t**)&c.hh_ptr, c.H + 1)); A(dev_alloc(h, (int32_t**)&c.hh_mem, c.n_pad));
+    A(dev_alloc(h, &h->d_rep, R));
+    c.rep_params = R > 1 ? h->d_rep : nullptr;
     c.n_peers = 1; c.rank = p.rank; c.flag_wait = h->d_peer_flags;
     for (int r = 0; r < 8; ++r) c.flag_signal[r] = h->d_peer_flags ? h->d_peer_flags + p.rank : nullptr;
     A(dev_alloc(h, &d_pdf, DYS_PDF_LEN));
-    A(dev_alloc(h, &h->d_bad, 1));
-    {   // one output block per parity: everything a day produces leaves the device in a single copy
+    A(dev_alloc(h, &h->d_bad, 4));
+    {   // one output block per ring slot and replica: everything a day produces leaves the device in a single copy
         auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
         h->off_sa = sizeof(int64_t) * N_STATS;
         h->off_bc = h->off_sa + ((p.flags & DYS_WANT_SA_HIST) ? up16(sizeof(int32_t) * (size_t)(c.S_out * HIST_LEN)) : 0);
@@ -205,7 +261,8 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         if (h->ev_inline > c.n_pad) h->ev_inline = c.n_pad;
         h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
         h->out_dev_bytes = h->off_ev + ((p.flags & DYS_WANT_EVENTS) ? sizeof(int2) * (size_t)c.n_pad : 0);
-        for (int k = 0; k < DYS_OUT_RING; ++k) A(dev_alloc(h, &h->d_out[k], (int64_t)h->out_dev_bytes));
+        c.out_stride = (int64_t)h->out_dev_bytes;
+        for (int k = 0; k < DYS_OUT_RING; ++k) A(dev_alloc(h, &h->d_out[k], (int64_t)h->out_dev_bytes * R));
     }
     if (p.flags & DYS_WANT_IO_MAT) A(dev_alloc(h, &c.io_mat, c.S * c.S));
     c.pdf = d_pdf;
@@ -222,28 +279,38 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_days, k_days, 256, 0) == cudaSuccess && per_sm_days > 0)
             h->days_grid = per_sm_days * sms;
+        if (R > 1 && h->days_grid < 2) { h->err = "replicas need the cooperative k_days launch"; rc = DYS_ERR_NOT_AVAILABLE; }
     }
     if (rc == DYS_OK && h->days_grid > 1)
-        for (int k = 0; k < 3; ++k) {      // the daily equal-work cut of k_days (see plan_cut)
+        for (int k = 0; k < 3; ++k) {      // the daily equal-work cut of k_days (see plan_cut), over [replica][piece]
             A(dev_alloc(h, &h->buf.bounds[k], h->days_grid + 1));
-            if (k < 2) A(dev_alloc(h, &h->buf.piece_work[k], c.n_pad / 128));
+            if (k < 2) A(dev_alloc(h, &h->buf.piece_work[k], c.n_pad / 128 * R));
         }
-    A(dev_alloc(h, &h->d_open_ring, (int64_t)MAX_FUSED_DAYS * c.B));
+    for (int k = 0; k < 2; ++k) {
+        A(dev_alloc(h, &h->d_open_ring[k], (int64_t)MAX_FUSED_DAYS * c.B));
+        if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open_ring[k], (size_t)MAX_FUSED_DAYS * (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
+    }
     A(dev_alloc(h, &h->d_barrier, 4));
-    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open_ring, (size_t)MAX_FUSED_DAYS * (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK) {
+        void* ab = nullptr;
+        if (cudaHostAlloc(&ab, 64, cudaHostAllocMapped) != cudaSuccess) rc = DYS_ERR_CUDA;
+        else {
+            h->h_abort = (volatile int32_t*)ab;
+            *h->h_abort = 0;
+            void* dab = nullptr;
+            if (cudaHostGetDevicePointer(&dab, ab, 0) != cudaSuccess) rc = DYS_ERR_CUDA;
+            c.abort_word = (volatile int32_t*)dab;
+        }
+    }
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMemcpyAsync(h->d_rep, h->rep.data(), sizeof(RepParam) * (size_t)R, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMemsetAsync((void*)c.open, 1, (size_t)c.B, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
-    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_out, h->out_copy_bytes * DYS_OUT_RING) != cudaSuccess) rc = DYS_ERR_CUDA;
+    if (rc == DYS_OK && cudaMallocHost((void**)&h->h_out, h->out_copy_bytes * DYS_OUT_RING * (size_t)R) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open, (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
     if (rc == DYS_OK) memset(h->h_open, 1, (size_t)c.B);
     if (rc == DYS_OK && cudaMallocHost((void**)&h->h_small, sizeof(int32_t) * 16) != cudaSuccess) rc = DYS_ERR_CUDA;
-    for (int i = 0; i < DYS_OUT_RING; ++i) {
-        h->out_day[i] = -1;
-        h->out_step[i] = -1;
-        h->out_ev[i] = nullptr;
+    for (int i = 0; i < DYS_OUT_RING; ++i)
         if (rc == DYS_OK && cudaEventCreateWithFlags(&h->out_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = DYS_ERR_CUDA;
-    }
-    for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
     if (rc == DYS_OK && (p.flags & DYS_TIME_KERNELS)) {
         h->tev.resize(dys_handle::T_RING * 4);
         for (auto& ev : h->tev) if (cudaEventCreate(&ev) != cudaSuccess) { rc = DYS_ERR_CUDA; break; }
@@ -262,7 +329,9 @@ extern "C" int dys_destroy(dys_handle* h)
 {
     if (!h) return DYS_OK;
     cudaSetDevice(h->device);
+    if (h->h_abort) *h->h_abort = 1;      // a launch that is still spinning ends
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamDestroy(h->up_stream); }
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_open) cudaFreeHost(h->h_open);
@@ -271,7 +340,12 @@ extern "C" int dys_destroy(dys_handle* h)
     for (auto ev : h->tev) if (ev) cudaEventDestroy(ev);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int k = 0; k < DYS_OUT_RING; ++k) if (h->day_done[k]) cudaEventDestroy(h->day_done[k]);
-    if (h->h_open_ring) cudaFreeHost(h->h_open_ring);
+    for (int k = 0; k < 2; ++k) {
+        if (h->h_open_ring[k]) cudaFreeHost(h->h_open_ring[k]);
+        if (h->up_done[k]) cudaEventDestroy(h->up_done[k]);
+        if (h->ring_free[k]) cudaEventDestroy(h->ring_free[k]);
+    }
+    if (h->h_abort) cudaFreeHost((void*)h->h_abort);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return DYS_OK;
@@ -281,18 +355,19 @@ extern "C" int dys_destroy(dys_handle* h)
 static int reset_day_scratch(dys_handle* h)
 {
     DevCtx& c = h->c;
+    const size_t R = (size_t)h->R;
     for (int k = 0; k < 2; ++k) {
-        CK(h, cudaMemsetAsync(h->buf.att[k], 0, (size_t)c.n_pad + 16, h->stream));
-        CK(h, cudaMemsetAsync(h->buf.mb_any[k], 0xFF, sizeof(int32_t) * (size_t)c.n_pad, h->stream));   // -1: empty mailbox
-        CK(h, cudaMemsetAsync(h->buf.mb_iso[k], 0xFF, sizeof(int32_t) * (size_t)c.n_pad, h->stream));
+        CK(h, cudaMemsetAsync(h->buf.att[k], 0, ((size_t)c.n_pad + 16) * R, h->stream));
+        CK(h, cudaMemsetAsync(h->buf.mb_any[k], 0xFF, sizeof(int32_t) * (size_t)c.n_pad * R, h->stream));   // -1: empty mailbox
+        CK(h, cudaMemsetAsync(h->buf.mb_iso[k], 0xFF, sizeof(int32_t) * (size_t)c.n_pad * R, h->stream));
     }
-    for (int k = 0; k < Q_RING; ++k) CK(h, cudaMemsetAsync(h->buf.qflag[k], 0, (size_t)c.H + 16, h->stream));
-    CK(h, cudaMemsetAsync(h->buf.df, 0, sizeof(int32_t) * DF_RING * DF_LEN, h->stream));
-    CK(h, cudaMemsetAsync(h->buf.part, 0, sizeof(unsigned long long) * PART_RING * N_SLOTS * N_STATS, h->stream));
+    for (int k = 0; k < Q_RING; ++k) CK(h, cudaMemsetAsync(h->buf.qflag[k], 0, ((size_t)c.H + 16) * R, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.df, 0, sizeof(int32_t) * DF_RING * DF_LEN * R, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.part, 0, sizeof(unsigned long long) * PART_RING * N_SLOTS * N_STATS * R, h->stream));
     CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
     if (h->buf.bounds[0]) {      // until measured costs exist the blocks of k_days get equal runs of pieces
         const int n_work = h->days_grid - 1;
-        const int64_t n_pieces = c.n_pad / 128, per = (n_pieces + n_work - 1) / n_work;
+        const int64_t n_pieces = c.n_pad / 128 * (int64_t)R, per = (n_pieces + n_work - 1) / n_work;
         std::vector<int32_t> cut((size_t)n_work + 1);
         for (int b = 0; b <= n_work; ++b) cut[(size_t)b] = (int32_t)((int64_t)b * per < n_pieces ? (int64_t)b * per : n_pieces);
         for (int k = 0; k < 3; ++k) {
@@ -306,52 +381,83 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaMemsetAsync(h->d_peer_flags, 0xFF, sizeof(int32_t) * 8, h->stream));   // -1: nothing complete yet
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaStreamSynchronize(h->copy_stream));
+    CK(h, cudaStreamSynchronize(h->up_stream));
     for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; }
     for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
+    if (h->h_abort) *h->h_abort = 0;
     return DYS_OK;
 }
 
 static int check_bad(dys_handle* h, const char* what)
 {
-    CK(h, cudaMemcpyAsync(h->h_small, h->d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->h_small, h->d_bad, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     const int bad = h->h_small[0];
     if (bad) {
-        CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int32_t), h->stream));
+        CK(h, cudaMemsetAsync(h->d_bad, 0, 2 * sizeof(int32_t), h->stream));
         return fail(h, DYS_ERR_RANGE, "%s: invalid input (flags 0x%x: 1 status code, 2 hh/home/sa index, 4 t_adm != 0 for a "
                     "never-admitted status, 8 src index, 16 routine building index, 32 rowptr not monotone, 64 column index, "
                     "128 columns not strictly ascending, 256 day out of int16 range, 512 susceptible agent with an infector, "
-                    "1024 household with more than 32767 members)", what, bad);
+                    "1024 household with more than 32767 members, 2048 trig_ptr not monotone, 4096 trig_hh outside the owned "
+                    "households)", what, bad);
     }
     return DYS_OK;
 }
 
-static int load_days(dys_handle* h, int field, const int32_t* src, int32_t* tmp, int64_t n)
+static int load_days(dys_handle* h, AgentRec* rec, int field, const int32_t* src, int32_t* tmp, int64_t n)
 {
     int rc = copy_in(h, tmp, src, sizeof(int32_t) * (size_t)n);
     if (rc != DYS_OK) return rc;
-    k_narrow_days<<<grid_for(n, 256), 256, 0, h->stream>>>(tmp, h->c.rec, field, n, h->d_bad);
+    k_narrow_days<<<grid_for(n, 256), 256, 0, h->stream>>>(tmp, rec, field, n, h->d_bad);
     CK(h, cudaGetLastError());
     return DYS_OK;
 }
 
+// the state columns of ONE replica (the context's pointers are replica 0's)
 static int load_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q, const int32_t* t_adm,
-                      const int32_t* src)
+                      const int32_t* src, int r = 0)
 {
-    DevCtx& c = h->c;
+    DevCtx c = h->c;
+    c.status += (size_t)c.n_pad * r; c.rec += (size_t)c.n_pad * r; c.src += (size_t)c.n_pad * r;
     const int64_t n = c.n_loc;
     int32_t* tmp = nullptr;
     CK(h, cudaMalloc((void**)&tmp, sizeof(int32_t) * (size_t)n));
     int rc = DYS_OK;
     auto A = [&](int r) { if (rc == DYS_OK) rc = r; };
     A(copy_in(h, c.status, status_x2, (size_t)n));
-    A(load_days(h, 0, t_inf, tmp, n));
-    A(load_days(h, 1, t_q, tmp, n));
-    A(load_days(h, 2, t_adm, tmp, n));
+    A(load_days(h, c.rec, 0, t_inf, tmp, n));
+    A(load_days(h, c.rec, 1, t_q, tmp, n));
+    A(load_days(h, c.rec, 2, t_adm, tmp, n));
     A(copy_in(h, c.src, src, sizeof(int32_t) * (size_t)n));
     cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
     return rc;
+}
+
+// replica 0 -> every other replica (state and the static half of the agent records)
+static int replicate_state(dys_handle* h)
+{
+    DevCtx& c = h->c;
+    for (int r = 1; r < h->R; ++r) {
+        CK(h, cudaMemcpyAsync(c.status + (size_t)c.n_pad * r, c.status, (size_t)c.n_pad, cudaMemcpyDeviceToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(c.rec + (size_t)c.n_pad * r, c.rec, sizeof(AgentRec) * (size_t)c.n_pad, cudaMemcpyDeviceToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(c.src + (size_t)c.n_pad * r, c.src, sizeof(int32_t) * (size_t)c.n_pad, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return DYS_OK;
+}
+
+// validation of the loaded state; also when every loaded recovered agent has left the days-since-infection histogram
+static int validate_state(dys_handle* h, const char* what, int r = 0)
+{
+    DevCtx c = h->c;
+    c.status += (size_t)c.n_pad * r; c.rec += (size_t)c.n_pad * r; c.src += (size_t)c.n_pad * r;
+    k_validate_population<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c, h->d_bad);
+    CK(h, cudaGetLastError());
+    int rc = check_bad(h, what);
+    if (rc != DYS_OK) return rc;
+    if (h->h_small[1] > h->c.r_idle_day) h->c.r_idle_day = h->h_small[1];
+    CK(h, cudaMemsetAsync(h->d_bad, 0, 2 * sizeof(int32_t), h->stream));
+    return DYS_OK;
 }
 
 extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
@@ -381,10 +487,10 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
     cudaStreamSynchronize(h->stream);
     cudaFree(d_home); cudaFree(d_sa);
     if (rc != DYS_OK) return rc;
-    k_validate_population<<<grid_for(c.n_loc, 256), 256, 0, h->stream>>>(c, h->d_bad);
     k_validate_routine<<<grid_for(c.rt_n * c.V, 256), 256, 0, h->stream>>>(c.routine, c.rt_n * c.V, c.B, h->d_bad);
     CK(h, cudaGetLastError());
-    rc = check_bad(h, "dys_load_population");
+    c.r_idle_day = 0;
+    rc = validate_state(h, "dys_load_population");
     if (rc != DYS_OK) return rc;
     {   // household -> members (phase F flags the MEMBERS of a diagnosed agent's household, contagious3.py:263)
         int32_t* d_cnt = nullptr;
@@ -407,7 +513,8 @@ extern "C" int dys_load_population(dys_handle* h, const uint8_t* status_x2, cons
     }
     h->have_pop = true;
     h->have_graph = false;
-    return reset_day_scratch(h);
+    rc = replicate_state(h);
+    return rc == DYS_OK ? reset_day_scratch(h) : rc;
 }
 
 extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
@@ -417,12 +524,14 @@ extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int3
     if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_set_state before dys_load_population");
     if (!status_x2 || !t_inf || !t_q || !t_adm || !src) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_state: null array");
     CK(h, cudaSetDevice(h->device));
-    int rc = load_state(h, status_x2, t_inf, t_q, t_adm, src);
+    CK(h, cudaStreamSynchronize(h->stream));
+    const int r = h->sel >= 0 ? h->sel : 0;
+    if (h->sel < 0) h->c.r_idle_day = 0;      // (a single replica's reload can only push the day later)
+    int rc = load_state(h, status_x2, t_inf, t_q, t_adm, src, r);
     if (rc != DYS_OK) return rc;
-    k_validate_population<<<grid_for(h->c.n_loc, 256), 256, 0, h->stream>>>(h->c, h->d_bad);
-    CK(h, cudaGetLastError());
-    rc = check_bad(h, "dys_set_state");
+    rc = validate_state(h, "dys_set_state", r);
     if (rc != DYS_OK) return rc;
+    if (h->sel < 0) { rc = replicate_state(h); if (rc != DYS_OK) return rc; }
     h->last_day = -1;
     return reset_day_scratch(h);
 }
@@ -430,8 +539,42 @@ extern "C" int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int3
 extern "C" int dys_set_run(dys_handle* h, double norm_factor, double compliance, uint64_t seed)
 {
     if (!h) return DYS_ERR_INVALID_ARG;
+    if (!(compliance >= 0.0 && compliance <= 1.0)) return fail(h, DYS_ERR_INVALID_ARG, "compliance must be in [0, 1]");
     h->c.norm_factor = norm_factor; h->c.compliance = compliance; h->c.seed = seed;
     h->p.norm_factor = norm_factor; h->p.compliance = compliance; h->p.seed = seed;
+    if (h->R == 1) h->rep[0] = RepParam{norm_factor, compliance, seed};
+    return DYS_OK;
+}
+
+extern "C" int dys_set_replica_params(dys_handle* h, const double* norm_factor, const double* compliance, const uint64_t* seed)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->R; ++r) {
+        if (compliance && !(compliance[r] >= 0.0 && compliance[r] <= 1.0)) return fail(h, DYS_ERR_INVALID_ARG, "compliance must be in [0, 1]");
+        if (norm_factor) h->rep[(size_t)r].norm_factor = norm_factor[r];
+        if (compliance) h->rep[(size_t)r].compliance = compliance[r];
+        if (seed) h->rep[(size_t)r].seed = seed[r];
+    }
+    CK(h, cudaMemcpyAsync(h->d_rep, h->rep.data(), sizeof(RepParam) * (size_t)h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->R == 1) { h->c.norm_factor = h->rep[0].norm_factor; h->c.compliance = h->rep[0].compliance; h->c.seed = h->rep[0].seed; }
+    return DYS_OK;
+}
+
+extern "C" int dys_select_replica(dys_handle* h, int32_t r)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (r < -1 || r >= h->R) return fail(h, DYS_ERR_INVALID_ARG, "replica %d out of range (%d replicas)", r, h->R);
+    h->sel = r;
+    return DYS_OK;
+}
+
+extern "C" int dys_abort(dys_handle* h)
+{
+    if (!h || !h->h_abort) return DYS_ERR_INVALID_ARG;
+    *h->h_abort = 1;
     return DYS_OK;
 }
 
@@ -491,7 +634,8 @@ extern "C" int dys_load_graph(dys_handle* h, const int64_t* rowptr, const int32_
             rc = fail(h, DYS_ERR_CUDA, "building the transposed network failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cleanup();
-    if (rc != DYS_OK) return rc;
+    if (rc != DYS_OK) { dev_free(h, d_tptr); dev_free(h, d_tedge); return rc; }
+    dev_free(h, c.tptr); dev_free(h, c.tedge);      // a previously loaded network
     c.tptr = d_tptr; c.tedge = d_tedge;
     h->nnz = nnz;
     h->have_graph = true;
@@ -503,18 +647,21 @@ extern "C" int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int
     if (!h) return DYS_ERR_INVALID_ARG;
     if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_load_quirk before dys_load_population");
     CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
     DevCtx& c = h->c;
     int rc = DYS_OK;
     if (hh_always && h->p.world > 1)
         return fail(h, DYS_ERR_NOT_AVAILABLE, "hh_always (households quarantined whenever ANYONE is diagnosed, contagious3.py:267) "
                     "needs a global diagnosis flag and is not available in sharded mode");
+    dev_free(h, c.hh_always); dev_free(h, c.trig_ptr); dev_free(h, c.trig_hh);      // previously loaded tables
+    c.hh_always = nullptr; c.trig_ptr = nullptr; c.trig_hh = nullptr;
     if (hh_always) {
         uint8_t* d = nullptr;
         rc = dev_alloc(h, &d, c.H);
         if (rc == DYS_OK) rc = copy_in(h, d, hh_always, (size_t)c.H);
         if (rc != DYS_OK) return rc;
         c.hh_always = d;
-    } else c.hh_always = nullptr;
+    }
     if (trig_ptr) {
         int64_t* d = nullptr;
         rc = dev_alloc(h, &d, c.n_pad + 1);
@@ -523,9 +670,9 @@ extern "C" int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int
         int64_t nt = 0;
         CK(h, cudaMemcpyAsync(&nt, d + c.n_loc, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
-        if (nt < 0) return fail(h, DYS_ERR_RANGE, "dys_load_quirk: negative trigger count");
-        if (nt == 0) { c.trig_ptr = nullptr; c.trig_hh = nullptr; return DYS_OK; }
-        if (!trig_hh) return fail(h, DYS_ERR_INVALID_ARG, "dys_load_quirk: null trig_hh");
+        if (nt < 0) { dev_free(h, d); return fail(h, DYS_ERR_RANGE, "dys_load_quirk: negative trigger count"); }
+        if (nt == 0) { dev_free(h, d); return DYS_OK; }
+        if (!trig_hh) { dev_free(h, d); return fail(h, DYS_ERR_INVALID_ARG, "dys_load_quirk: null trig_hh"); }
         if (c.n_pad > c.n_loc) {
             std::vector<int64_t> tail((size_t)(c.n_pad - c.n_loc), nt);
             CK(h, cudaMemcpyAsync(d + c.n_loc + 1, tail.data(), sizeof(int64_t) * tail.size(), cudaMemcpyHostToDevice, h->stream));
@@ -534,9 +681,14 @@ extern "C" int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int
         int32_t* t = nullptr;
         rc = dev_alloc(h, &t, nt);
         if (rc == DYS_OK) rc = copy_in(h, t, trig_hh, sizeof(int32_t) * (size_t)nt);
-        if (rc != DYS_OK) return rc;
+        if (rc == DYS_OK) {
+            const int64_t m = c.n_loc > nt ? c.n_loc : nt;
+            k_validate_quirk<<<grid_for(m, 256), 256, 0, h->stream>>>(d, t, c.n_loc, nt, c.H, h->d_bad);
+            rc = check_bad(h, "dys_load_quirk");
+        }
+        if (rc != DYS_OK) { dev_free(h, d); dev_free(h, t); return rc; }
         c.trig_ptr = d; c.trig_hh = t;
-    } else { c.trig_ptr = nullptr; c.trig_hh = nullptr; }
+    }
     CK(h, cudaStreamSynchronize(h->stream));
     return DYS_OK;
 }
@@ -596,12 +748,19 @@ static void bind_peers(dys_handle* h)
 static int run_snapshot(dys_handle* h, int32_t day)
 {
     DevCtx& c = h->c;
-    CK(h, cudaMemsetAsync(h->buf.att[day & 1], 0, (size_t)c.n_pad + 16, h->stream));
-    CK(h, cudaMemsetAsync(h->buf.qflag[day % Q_RING], 0, (size_t)c.H + 16, h->stream));
-    CK(h, cudaMemsetAsync(h->buf.df + (day & (DF_RING - 1)) * DF_LEN, 0, sizeof(int32_t) * DF_LEN, h->stream));
+    const size_t R = (size_t)h->R;
+    CK(h, cudaMemsetAsync(h->buf.att[day & 1], 0, ((size_t)c.n_pad + 16) * R, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.qflag[day % Q_RING], 0, ((size_t)c.H + 16) * R, h->stream));
+    CK(h, cudaMemsetAsync(h->buf.df + (size_t)(day & (DF_RING - 1)) * DF_LEN * R, 0, sizeof(int32_t) * DF_LEN * R, h->stream));
     bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
     bind_ib_targets(c, h->buf, day & 1);
-    k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    c.stats = nullptr; c.sa_hist = nullptr; c.bcount = nullptr; c.ev = nullptr;
+    for (int r = 0; r < h->R; ++r) {
+        DevCtx cr = c;
+        shift_replica(cr, r);
+        cr.norm_factor = h->rep[(size_t)r].norm_factor; cr.compliance = h->rep[(size_t)r].compliance; cr.seed = h->rep[(size_t)r].seed;
+        k_snapshot<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(cr, day);
+    }
     if (h->n_peers > 1) {
         k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
         k_signal<<<1, 32, 0, h->stream>>>(c, day);
@@ -623,6 +782,8 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     if (!h->have_pop || !h->have_graph) return fail(h, DYS_ERR_STATE, "dys_step before dys_load_population/dys_load_graph");
     if (h->begun) return fail(h, DYS_ERR_STATE, "dys_step_begin called twice without dys_step_end");
     if (day < 0 || day > 32000) return fail(h, DYS_ERR_INVALID_ARG, "day out of range");
+    if (h->R > 1) return fail(h, DYS_ERR_NOT_AVAILABLE, "replicas advance through dys_step_many");
+    { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
     c.u_adm = c.u_death = c.u_pair = nullptr;
@@ -668,18 +829,23 @@ static int retire_slot(dys_handle* h, int slot)
     if (h->out_day[slot] >= 0) {
         CK(h, cudaEventSynchronize(h->out_ev[slot]));
         const int hs = (int)(h->out_step[slot] % DYS_STATS_RING);
-        memcpy(h->hist_stats[hs], h->h_out + (size_t)slot * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
+        for (int r = 0; r < h->R; ++r)
+            memcpy(&h->hist_stats[((size_t)hs * h->R + r) * N_STATS], h->h_out + ((size_t)slot * h->R + r) * h->out_copy_bytes,
+                   sizeof(int64_t) * N_STATS);
         h->hist_day[hs] = h->out_day[slot];
         h->out_day[slot] = -1;
     }
     return DYS_OK;
 }
 
-// the day's block leaves on the copy stream, under the following days' kernels
+// the day's block (one per replica) leaves on the copy stream, under the following days' kernels
 static int ship_day(dys_handle* h, int32_t day, int slot, int64_t step)
 {
     CK(h, cudaStreamWaitEvent(h->copy_stream, h->day_done[slot], 0));
-    CK(h, cudaMemcpyAsync(h->h_out + (size_t)slot * h->out_copy_bytes, h->d_out[slot], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    unsigned char* dst = h->h_out + (size_t)slot * h->R * h->out_copy_bytes;
+    if (h->R == 1) CK(h, cudaMemcpyAsync(dst, h->d_out[slot], h->out_copy_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    else CK(h, cudaMemcpy2DAsync(dst, h->out_copy_bytes, h->d_out[slot], h->out_dev_bytes, h->out_copy_bytes, (size_t)h->R,
+                                 cudaMemcpyDeviceToHost, h->copy_stream));
     CK(h, cudaEventRecord(h->out_ev[slot], h->copy_stream));
     h->out_day[slot] = day;
     h->out_step[slot] = step;
@@ -732,27 +898,36 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     plan.want_sa = (h->p.flags & DYS_WANT_SA_HIST) != 0;
     plan.want_bc = (h->p.flags & DYS_WANT_BUILDING_COUNTS) != 0;
     plan.want_ev = (h->p.flags & DYS_WANT_EVENTS) != 0;
+    { const char* t = getenv("DYS_TEST_HANG_BLOCK"); plan.test_hang_block = t ? atoi(t) : -1; }
     bind_peers(h);
     plan.buf = h->buf;
-    // open flags: a day whose vector differs from the one in force gets its own device copy
+    // Open flags: the caller's vectors are this window's host input.  They are staged in one of two pinned rings (by
+    // window parity) and uploaded on their own stream, so the flags of window w + 1 travel while window w runs; the
+    // kernels of this window wait for the upload, the upload waits for the launch that last read the ring.
     const uint8_t* cur_dev = c.open;
     int32_t cur_closed = c.n_closed;
-    bool staged = false;
-    for (int k = 0; k < n_days; ++k) {
-        if (open_flags) {
-            const uint8_t* f = open_flags + (size_t)k * (size_t)c.B;
-            if (memcmp(h->h_open, f, (size_t)c.B) != 0) {
-                if (!staged) { CK(h, cudaStreamSynchronize(h->stream)); staged = true; }   // the staging ring may still be in flight
-                memcpy(h->h_open, f, (size_t)c.B);
-                memcpy(h->h_open_ring + (size_t)k * c.B, f, (size_t)c.B);
-                CK(h, cudaMemcpyAsync(h->d_open_ring + (size_t)k * c.B, h->h_open_ring + (size_t)k * c.B, (size_t)c.B, cudaMemcpyHostToDevice, h->stream));
-                cur_dev = h->d_open_ring + (size_t)k * c.B;
-                cur_closed = 0;
-                for (int64_t b = 0; b < c.B; ++b) cur_closed += f[b] == 0;
-            }
+    const int wp = (int)(h->windows & 1);
+    if (open_flags) {
+        const size_t B = (size_t)c.B;
+        if (h->ring_used[wp]) CK(h, cudaEventSynchronize(h->up_done[wp]));      // (two windows ago: long done)
+        memcpy(h->h_open_ring[wp], open_flags, (size_t)n_days * B);
+        if (h->ring_used[wp]) CK(h, cudaStreamWaitEvent(h->up_stream, h->ring_free[wp], 0));
+        CK(h, cudaMemcpyAsync(h->d_open_ring[wp], h->h_open_ring[wp], (size_t)n_days * B, cudaMemcpyHostToDevice, h->up_stream));
+        CK(h, cudaEventRecord(h->up_done[wp], h->up_stream));
+        CK(h, cudaStreamWaitEvent(h->stream, h->up_done[wp], 0));
+        h->h2d_bytes += (int64_t)n_days * (int64_t)B;
+        for (int k = 0; k < n_days; ++k) {
+            const uint8_t* f = open_flags + (size_t)k * B;
+            int32_t closed = 0;
+            for (size_t b = 0; b < B; ++b) closed += f[b] == 0;
+            plan.open[k] = h->d_open_ring[wp] + (size_t)k * B;
+            plan.n_closed[k] = closed;
         }
-        plan.open[k] = cur_dev;
-        plan.n_closed[k] = cur_closed;
+        cur_dev = plan.open[n_days - 1];
+        cur_closed = plan.n_closed[n_days - 1];
+        memcpy(h->h_open, open_flags + (size_t)(n_days - 1) * B, B);
+    } else {
+        for (int k = 0; k < n_days; ++k) { plan.open[k] = cur_dev; plan.n_closed[k] = cur_closed; }
     }
     int rc = DYS_OK;
     for (int k = 0; k < n_days && rc == DYS_OK; ++k) {
@@ -776,6 +951,11 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         plan.trace = h->d_trace;
     }
     CK(h, cudaLaunchCooperativeKernel((const void*)k_days, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
+    if (open_flags) {
+        CK(h, cudaEventRecord(h->ring_free[wp], h->stream));
+        h->ring_used[wp] = true;
+        ++h->windows;
+    }
     if (plan.trace) {      // developer tracing: synchronous, appended as text
         std::vector<unsigned long long> tr(trace_words);
         CK(h, cudaMemcpyAsync(tr.data(), h->d_trace, trace_words * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -836,7 +1016,8 @@ extern "C" int dys_step_many(dys_handle* h, int32_t first_day, int32_t n_days, c
     if (!h->have_pop || !h->have_graph) return fail(h, DYS_ERR_STATE, "dys_step_many before dys_load_population/dys_load_graph");
     if (h->begun) return fail(h, DYS_ERR_STATE, "dys_step_many between dys_step_begin and dys_step_end");
     if (first_day < 0 || first_day + n_days > 32000) return fail(h, DYS_ERR_INVALID_ARG, "day out of range");
-    if (n_days >= 2 && n_days <= MAX_FUSED_DAYS && h->days_grid > 0 && h->tev.empty() && !h->no_fuse)
+    { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
+    if ((n_days >= 2 || h->R > 1) && n_days <= MAX_FUSED_DAYS && h->days_grid > 0 && h->tev.empty() && (!h->no_fuse || h->R > 1))
         return step_fused(h, first_day, n_days, open_flags);
     for (int32_t k = 0; k < n_days; ++k) {
         if (open_flags) {
@@ -850,13 +1031,16 @@ extern "C" int dys_step_many(dys_handle* h, int32_t first_day, int32_t n_days, c
     return DYS_OK;
 }
 
+static inline int sel_rep(const dys_handle* h) { return h->sel >= 0 ? h->sel : 0; }
+
 extern "C" int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out)
 {
     if (!h || !out) return DYS_ERR_INVALID_ARG;
     const int i = find_out_slot(h, day);
     if (i < 0) return fail(h, DYS_ERR_NOT_AVAILABLE, "outputs of day %d are not in the ring (the last %d days are kept)", day, DYS_OUT_RING);
     CK(h, cudaEventSynchronize(h->out_ev[i]));
-    const unsigned char* base = h->h_out + (size_t)i * h->out_copy_bytes;
+    { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
+    const unsigned char* base = h->h_out + ((size_t)i * h->R + sel_rep(h)) * h->out_copy_bytes;
     out->day = day;
     out->stats = (const int64_t*)base;
     out->sa_hist = (h->p.flags & DYS_WANT_SA_HIST) ? (const int32_t*)(base + h->off_sa) : nullptr;
@@ -874,11 +1058,15 @@ extern "C" int dys_get_stats(dys_handle* h, int32_t day, int64_t* out)
     const int i = find_out_slot(h, day);
     if (i >= 0) {
         CK(h, cudaEventSynchronize(h->out_ev[i]));
-        memcpy(out, h->h_out + (size_t)i * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
+        { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
+        memcpy(out, h->h_out + ((size_t)i * h->R + sel_rep(h)) * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
         return DYS_OK;
     }
     for (int k = 0; k < DYS_STATS_RING; ++k)
-        if (h->hist_day[k] == day) { memcpy(out, h->hist_stats[k], sizeof(int64_t) * N_STATS); return DYS_OK; }
+        if (h->hist_day[k] == day) {
+            memcpy(out, &h->hist_stats[((size_t)k * h->R + sel_rep(h)) * N_STATS], sizeof(int64_t) * N_STATS);
+            return DYS_OK;
+        }
     return fail(h, DYS_ERR_NOT_AVAILABLE, "stats of day %d are no longer kept (the last %d days are)", day, DYS_STATS_RING);
 }
 
@@ -939,7 +1127,7 @@ extern "C" int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_
         const int i = find_out_slot(h, day);
         if (h->steps - h->out_step[i] >= DYS_OUT_RING) return fail(h, DYS_ERR_NOT_AVAILABLE, "events of day %d beyond the first %d were overwritten", day, o.events_inline);
         rest.resize((size_t)cnt * 2);
-        rc = copy_out(h, rest.data(), h->d_out[i] + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt);
+        rc = copy_out(h, rest.data(), h->d_out[i] + (size_t)sel_rep(h) * h->out_dev_bytes + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt);
         if (rc != DYS_OK) return rc;
         pairs = rest.data();
     }
@@ -955,7 +1143,8 @@ extern "C" int dys_get_state(dys_handle* h, uint8_t* status_x2, int32_t* t_inf, 
     if (!h) return DYS_ERR_INVALID_ARG;
     if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_get_state before dys_load_population");
     CK(h, cudaSetDevice(h->device));
-    DevCtx& c = h->c;
+    DevCtx c = h->c;
+    { const size_t o = (size_t)c.n_pad * sel_rep(h); c.status += o; c.rec += o; c.src += o; }
     const int64_t n = c.n_loc;
     if (status_x2) CK(h, cudaMemcpyAsync(status_x2, c.status, (size_t)n, cudaMemcpyDefault, h->stream));
     if (src) CK(h, cudaMemcpyAsync(src, c.src, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, h->stream));
@@ -987,8 +1176,10 @@ extern "C" int dys_sync(dys_handle* h)
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaStreamSynchronize(h->copy_stream));
-    return DYS_OK;
+    return check_abort(h);
 }
+
+extern "C" int64_t dys_h2d_bytes(const dys_handle* h) { return h ? h->h2d_bytes : 0; }
 
 extern "C" int dys_get_kernel_times(dys_handle* h, double* ms_total, int64_t* launches)
 {

@@ -73,6 +73,12 @@ struct __align__(16) AgentRec {
 };
 static_assert(sizeof(AgentRec) == 32, "one sector");
 
+// Monte-Carlo replicas of one loaded city (BASELINE.json configs[4]): the parameters that differ between them
+struct RepParam {
+    double norm_factor, compliance;
+    uint64_t seed;
+};
+
 struct DevCtx {
     int64_t n_loc, n_pad, n_glob, lo;    // owned agents, padded count (multiple of 1024), global agents, first owned
     int64_t rt_lo, rt_n;                 // halo: global agents [rt_lo, rt_lo + rt_n) are the columns owned rows reference
@@ -82,6 +88,16 @@ struct DevCtx {
     int32_t recover, hospital_recover, diagnosis, quarantine, adm_min, adm_max, death_min;
     double norm_factor, compliance;
     uint64_t seed;
+    int32_t r_idle_day;                  // from this day on every recovered agent has left the 21-bin histogram (see k_validate_population)
+    // Replicas: n_rep independent epidemics on the SAME city in one launch.  Everything mutable (and the per-day buffers and
+    // output blocks) exists n_rep times, replica r at `r * stride` behind replica 0; the network, routines, households and
+    // probabilities are shared.  shift_replica() turns a replica-0 view into replica r's.
+    int32_t n_rep, rep;
+    int64_t ib_stride, out_stride;       // bytes between two replicas' snapshot buffers / output blocks
+    const RepParam* rep_params;          // [n_rep] or null (n_rep == 1: the fields above)
+    // spinning loops (grid barrier, peer waits) give up when *abort_word != 0 or after spin_timeout_ns (then they set it)
+    volatile int32_t* abort_word;        // pinned host memory mapped into the device: the host can read and set it at any time
+    unsigned long long spin_timeout_ns;
     // mutable state, owned agents
     uint8_t* status;
     AgentRec* rec;                       // days in state (mutable) + area and home building (static)
@@ -163,14 +179,42 @@ __host__ __device__ __forceinline__ void bind_day(DevCtx& c, const DayBuffers& b
     const int p = day & 1;
     c.att = b.att[p]; c.att_next = b.att[p ^ 1];
     c.mb_any = b.mb_any[p]; c.mb_iso = b.mb_iso[p];
+    const int R = c.n_rep > 1 ? c.n_rep : 1;
     c.qflag = b.qflag[day % Q_RING]; c.qflag_next = b.qflag[(day + 1) % Q_RING];
-    c.df = b.df + (day & (DF_RING - 1)) * DF_LEN; c.df_next = b.df + ((day + 1) & (DF_RING - 1)) * DF_LEN;
-    c.part = b.part + (size_t)(day % PART_RING) * N_STATS * N_SLOTS;
+    c.df = b.df + (size_t)(day & (DF_RING - 1)) * R * DF_LEN; c.df_next = b.df + (size_t)((day + 1) & (DF_RING - 1)) * R * DF_LEN;
+    c.part = b.part + (size_t)(day % PART_RING) * R * N_STATS * N_SLOTS;
     c.bounds_plan = b.bounds[day % 3]; c.piece_work = b.piece_work[p];      // (day + 3) % 3
     c.cut_first = c.cut_last = -1;
     c.ib_rd = b.ib[p];
     c.write_ib = 1;
     bind_ib_targets(c, b, p ^ 1);        // the agent pass of `day` writes tomorrow's snapshot bytes
+}
+
+// replica 0's view of a day -> replica r's (every per-replica array is [n_rep][stride])
+__host__ __device__ __forceinline__ void shift_replica(DevCtx& c, const int r)
+{
+    c.rep = r;
+    if (c.n_rep <= 1) return;
+    const size_t n = (size_t)c.n_pad * r;
+    c.status += n; c.rec += n; c.src += n;
+    c.att += (size_t)(c.n_pad + 16) * r; c.att_next += (size_t)(c.n_pad + 16) * r;
+    c.mb_any += n; c.mb_iso += n;
+    c.qflag += (size_t)(c.H + 16) * r; c.qflag_next += (size_t)(c.H + 16) * r;
+    c.df += DF_LEN * r; c.df_next += DF_LEN * r;
+    c.part += (size_t)N_STATS * N_SLOTS * r;
+    c.ib_rd += (size_t)c.ib_stride * r; c.ib_wr[0] += (size_t)c.ib_stride * r;
+    const size_t o = (size_t)c.out_stride * r;
+    if (c.stats) c.stats = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(c.stats) + o);
+    if (c.sa_hist) c.sa_hist = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(c.sa_hist) + o);
+    if (c.bcount) c.bcount = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(c.bcount) + o);
+    if (c.ev) c.ev = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(c.ev) + o);
+    if (c.piece_work) c.piece_work += (size_t)(c.n_pad >> 7) * r;
+    if (c.rep_params) {
+#ifdef __CUDA_ARCH__
+        const RepParam p = c.rep_params[r];
+        c.norm_factor = p.norm_factor; c.compliance = p.compliance; c.seed = p.seed;
+#endif
+    }
 }
 
 __device__ __forceinline__ double draw(const double* inj, int64_t idx, uint64_t seed, uint32_t day, uint32_t stream,

@@ -55,14 +55,49 @@ __device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, int 
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Spinning loops (the grid barrier of k_days, the waits for peer GPUs) give
+// up when the abort word is set (by the host, or by a peer wait that timed out) or after spin_timeout_ns, so that a
+// faulted CTA or a dead peer process ends the launch instead of hanging the GPU.  Returns true when the launch must end.
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <typename Cond>
+__device__ __forceinline__ bool spin_until(const DevCtx& c, Cond done)
+{
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (!done()) {
+        __nanosleep(32);
+        if ((++spins & 255u) == 0u) {
+            if (c.abort_word && *c.abort_word) return true;
+            const unsigned long long t = global_ns();
+            if (!t0) t0 = t;
+            else if (c.spin_timeout_ns && t - t0 > c.spin_timeout_ns) {
+                if (c.abort_word) *c.abort_word = 2;      // timed out: everybody else gives up too
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// Shared memory of a block (256 threads).  The frontier outlives the agent pass; the agent work list and the push
-// scratch are never live together.
+// Shared memory of a block (256 threads = 8 warps).
+//   agent pass : every WARP keeps its own work list and its own frontier -- the warps of a block never wait for each
+//                other inside a day (no __syncthreads between the sweep, the settle rounds and the pushes), so an SM
+//                always has 32 independent chains of memory round trips in flight instead of 4 block-wide phases.
+//   scan push  : a block-wide frontier (first day of a window, stand-alone k_push).
+//   plan_cut   : the same memory staged as 8192 piece costs.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BLOCK = 256, WARPS = BLOCK / 32;
-constexpr int FCAP = 4096;                         // frontier entries: index relative to the block's base | snapshot byte << 24
-constexpr int LCAP = 2048;                         // one batch of the sweep (2 x 4 agents per thread) adds at most this many
-constexpr int LTOT = 4096;                         // agent work list: batches accumulate until the next one might not fit
+constexpr int FCAP = 4096;                         // scan-push frontier entries: index relative to the block's base | snapshot byte << 24
+constexpr int LTOT = 4096;                         // (with `front`: the staging area of plan_cut)
+constexpr int WL_CAP = 160;                        // a warp's work list: < 32 left over + one 128-agent piece
+constexpr int WF_CAP = 64;                         // a warp's frontier: < 32 left over + one settle round
 constexpr uint32_t REL_MASK = 0x00FFFFFFu;
 
 // where a block's queued agents live: halo-relative index = base + rel
@@ -72,30 +107,37 @@ struct FrontMap {
 };
 
 struct PushWarpScratch {
-    int off[36];                                   // exclusive prefix of the expanded rows' lengths
-    int64_t t0[32];
+    int off[32];                                   // first flat index of each (non-empty) row of the group
+    uint32_t fe[32];                               // its frontier entry
+    int64_t t0[32];                                // where its transposed row starts
 };
 
 enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS, EV_CHANGED, EV_LEN };
 
 struct BlockScratch {
-    uint32_t front[FCAP];
     union {
-        uint32_t list[LTOT];                       // local index | status << 24 | attention << 28
-        PushWarpScratch pw[WARPS];
+        struct {
+            uint32_t front[FCAP];
+            uint32_t list[LTOT];
+        };
+        struct {
+            uint32_t wlist[WARPS][WL_CAP];         // local index | status << 24 | attention << 28
+            uint32_t wfront[WARPS][WF_CAP];
+        };
     };
+    PushWarpScratch pw[WARPS];
     double pdf[64];
-    unsigned int n_front, n_list;
+    unsigned int n_front;
     unsigned int hist[HIST_LEN], ev[EV_LEN], cnt[10], acc[8];
     bool last;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// push_frontier: the block's queued infectious agents (sm.front[0 .. n_front), halo-relative index = base + rel) push
-// along their transposed rows.  The rows are dealt to the warps in groups of <= 32; a group is flattened (warp prefix
-// sum of the row lengths) so every lane works on consecutive entries however long the rows are; four entries per lane
-// are in flight.  Pairs that pass the static class test are compacted and settled densely (two 8-byte gathers and the
-// Philox rounds once per 32 pairs).
+// push_group: ONE WARP pushes the transposed rows of <= 32 queued infectious agents (ent[0 .. nb), halo-relative index =
+// fmap.at(entry & REL_MASK), snapshot byte = entry >> 24).  Empty rows are dropped, the others are flattened (warp prefix
+// sum of the row lengths) so that every lane works on consecutive 16-byte records however long the rows are, two per
+// lane in flight.  The row of a flat index is found with one ballot and one REDUX per 32 entries (rows that end at or
+// before the chunk + a bit mask of the row ends inside it), not a search per entry.
 //   CHECK = true   the status column is final (stand-alone launch, or after a grid barrier): u must be susceptible, and
 //                  the hit goes to the mailbox that matches u's isolation -- the counters equal the reference's
 //                  candidate / exposed / success counts.
@@ -104,125 +146,148 @@ struct BlockScratch {
 //                  not susceptible).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool CHECK>
+__device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushWarpScratch& w, const double* __restrict__ s_pdf,
+                                           const uint32_t* ent, const int nb, const FrontMap fmap, unsigned int (&cnt)[4])
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool any_closed = c.n_closed != 0;
+    const uint4* edges = reinterpret_cast<const uint4*>(c.tedge);
+    int64_t t0 = 0;
+    int len = 0;
+    uint32_t fe0 = 0;
+    if (lane < nb) {
+        fe0 = ent[lane];
+        const int64_t il = fmap.at(fe0 & REL_MASK);
+        t0 = __ldg(c.tptr + il);
+        len = (int)(__ldg(c.tptr + il + 1) - t0);
+    }
+    const unsigned nz = __ballot_sync(0xffffffffu, len > 0);
+    const int nr = __popc(nz);
+    if (nr == 0) return;
+    __syncwarp();                                    // (the previous group's readers are done with the scratch)
+    if (len > 0) {
+        const int slot = __popc(nz & lt_mask);
+        w.t0[slot] = t0;
+        w.fe[slot] = fe0;
+        w.off[slot] = len;
+    }
+    __syncwarp();
+    const int mylen = lane < nr ? w.off[lane] : 0;
+    int end = mylen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, end, o);
+        if (lane >= o) end += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, end, 31);
+    __syncwarp();
+    w.off[lane] = end - mylen;
+    __syncwarp();
+    cnt[0] += mylen;
+    // two entries per lane and step: every entry of the transposed network can be exposed (the others were left out at
+    // load time), so nearly every lane draws its Bernoulli and the Philox rounds run on full warps
+    for (int f0 = 0; f0 < total; f0 += 64) {
+        uint32_t fe[2];
+        uint4 rec[2];
+        uint32_t st_u[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int base = f0 + 32 * k, f = base + lane;
+            // row of f = #rows that end at or before f (row ends are strictly increasing: empty rows were dropped)
+            const int before = __popc(__ballot_sync(0xffffffffu, lane < nr && end <= base));
+            const unsigned ends = __reduce_or_sync(0xffffffffu, (lane < nr && end > base && end <= base + 31) ? 1u << (end - base) : 0u);
+            const int row = before + __popc(ends & ((2u << lane) - 1u));
+            rec[k] = make_uint4(0u, 0u, 0u, 0u);       // class 0: a padding lane never passes the exposure test
+            fe[k] = 0u;
+            if (f < total) {
+                rec[k] = __ldg(edges + (w.t0[row] + (f - w.off[row])));
+                fe[k] = w.fe[row];
+            }
+        }
+        if (CHECK) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[rec[k].x & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            // the exposure test: static class x today's isolation
+            const uint32_t cls = rec[k].x >> CLS_SHIFT, ib_i = fe[k] >> 24;
+            const bool iso_i = (ib_i & IB_ISO) != 0;
+            const bool x_iso = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i);                      // u isolated at home
+            const bool x_free = x_iso | ((cls & CLS_OH) != 0) | ((cls & CLS_OO) && !iso_i);      // u moves freely
+            bool ok_free, ok_iso, iso_u = false;
+            if (CHECK) {
+                const bool sus = in_set(M_SUS, st_u[k]);
+                iso_u = (st_u[k] == ST_QH);
+                cnt[1] += sus;
+                ok_free = sus && !iso_u && x_free;
+                ok_iso = sus && iso_u && x_iso;
+            } else {
+                cnt[1] += x_free;
+                ok_free = x_free;
+                ok_iso = x_iso;
+            }
+            if (!ok_free && !ok_iso) continue;
+            const uint32_t ul = rec[k].x & COL_MASK;
+            const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe[k] & REL_MASK);
+            if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
+                if (CHECK) {
+                    const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
+                    ok_free = ok_free && ok;
+                    ok_iso = ok_iso && ok;
+                } else {
+                    ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
+                    ok_iso = ok_iso && exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
+                }
+                if (!ok_free && !ok_iso) continue;
+            }
+            ++cnt[2];
+            // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
+            // rounded separately (no add follows, so no FMA can form); the first product comes with the record
+            double p = __dmul_rn(__hiloint2double((int)rec[k].w, (int)rec[k].z), s_pdf[ib_i & IB_DAYS]);
+            p = __dmul_rn(p, c.norm_factor);
+            if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+            const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
+            if (p > u) {                                                           // :240, :248
+                ++cnt[3];
+                if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
+                if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
+                att_or(c.att, ul, ATT_HIT);
+            }
+        }
+    }
+}
+
+// the block-wide frontier of a scan push (sm.front[0 .. n_front)), dealt to the warps in groups of <= 32 rows
+template <bool CHECK>
 __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, BlockScratch& sm, const FrontMap fmap,
                                               unsigned int (&cnt)[4])
 {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    PushWarpScratch& w = sm.pw[wid];
+    const int wid = threadIdx.x >> 5;
     const int n = (int)sm.n_front;
-    const bool any_closed = c.n_closed != 0;
     int rpg = (n + WARPS - 1) / WARPS;
     rpg = rpg < 1 ? 1 : (rpg > 32 ? 32 : rpg);
     const int n_groups = (n + rpg - 1) / rpg;
-    const uint4* edges = reinterpret_cast<const uint4*>(c.tedge);
-
     for (int g = wid; g < n_groups; g += WARPS) {
         const int q0 = g * rpg;
         const int nb = (n - q0) < rpg ? (n - q0) : rpg;
-        int64_t t0 = 0;
-        int len = 0;
-        if (lane < nb) {
-            const int64_t il = fmap.at(sm.front[q0 + lane] & REL_MASK);
-            t0 = __ldg(c.tptr + il);
-            len = (int)(__ldg(c.tptr + il + 1) - t0);
-        }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        w.off[lane] = incl - len;
-        if (lane == 31) w.off[32] = total;
-        w.t0[lane] = t0;
-        __syncwarp();
-        cnt[0] += len;
-        // two entries per lane and step: every entry of the transposed network can be exposed (the others were left
-        // out at load time), so nearly every lane draws its Bernoulli and the Philox rounds run on full warps
-        for (int f0 = 0; f0 < total; f0 += 64) {
-            int r[2];
-            uint4 rec[2];
-            uint32_t st_u[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int f = f0 + 32 * k + lane;
-                int lo = 0, hi = 32;                       // off[lo] <= f < off[hi]; the last such lo is the row
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const int mid = (lo + hi) >> 1;
-                    if (w.off[mid] <= f) lo = mid; else hi = mid;
-                }
-                r[k] = lo;
-                rec[k] = make_uint4(0u, 0u, 0u, 0u);       // class 0: a padding lane never passes the exposure test
-                if (f < total) rec[k] = __ldg(edges + (w.t0[lo] + (f - w.off[lo])));
-            }
-            if (CHECK) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    st_u[k] = (f0 + 32 * k + lane) < total ? (uint32_t)c.status[rec[k].x & COL_MASK] : (uint32_t)ST_PAD;   // day-start status
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                // the exposure test: static class x today's isolation
-                const uint32_t fe = sm.front[q0 + r[k]];
-                const uint32_t cls = rec[k].x >> CLS_SHIFT, ib_i = fe >> 24;
-                const bool iso_i = (ib_i & IB_ISO) != 0;
-                const bool x_iso = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i);                      // u isolated at home
-                const bool x_free = x_iso | ((cls & CLS_OH) != 0) | ((cls & CLS_OO) && !iso_i);      // u moves freely
-                bool ok_free, ok_iso, iso_u = false;
-                if (CHECK) {
-                    const bool sus = in_set(M_SUS, st_u[k]);
-                    iso_u = (st_u[k] == ST_QH);
-                    cnt[1] += sus;
-                    ok_free = sus && !iso_u && x_free;
-                    ok_iso = sus && iso_u && x_iso;
-                } else {
-                    cnt[1] += x_free;
-                    ok_free = x_free;
-                    ok_iso = x_iso;
-                }
-                if (!ok_free && !ok_iso) continue;
-                const uint32_t ul = rec[k].x & COL_MASK;
-                const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe & REL_MASK);
-                if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
-                    if (CHECK) {
-                        const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
-                        ok_free = ok_free && ok;
-                        ok_iso = ok_iso && ok;
-                    } else {
-                        ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
-                        ok_iso = ok_iso && exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
-                    }
-                    if (!ok_free && !ok_iso) continue;
-                }
-                ++cnt[2];
-                // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
-                // rounded separately (no add follows, so no FMA can form); the first product comes with the record
-                double p = __dmul_rn(__hiloint2double((int)rec[k].w, (int)rec[k].z), sm.pdf[ib_i & IB_DAYS]);
-                p = __dmul_rn(p, c.norm_factor);
-                if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
-                const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
-                if (p > u) {                                                           // :240, :248
-                    ++cnt[3];
-                    if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
-                    if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
-                    att_or(c.att, ul, ATT_HIT);
-                }
-            }
-        }
-        __syncwarp();
+        push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, sm.front + q0, nb, fmap, cnt);
     }
 }
 
 // what a push of day X clears before the agent pass of day X fills it / raises into it (grid-strided, any block)
-__device__ __forceinline__ void push_clear_duties(const DevCtx& c)
+// (c = the view of replica c.rep; r = another replica of the same day, addressed relative to it)
+__device__ __forceinline__ void push_clear_duties(const DevCtx& c, const int r = -1)
 {
-    grid_clear(c.sa_hist, c.S_out * HIST_LEN);
-    grid_clear(c.bcount, c.B_out);
+    const int dr = r < 0 ? 0 : r - c.rep;
+    const ptrdiff_t o = (ptrdiff_t)c.out_stride * dr;
+    if (c.sa_hist) grid_clear(reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(c.sa_hist) + o), c.S_out * HIST_LEN);
+    if (c.bcount) grid_clear(reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(c.bcount) + o), c.B_out);
     grid_clear(c.io_mat, c.io_mat ? c.S * c.S : 0);
-    if (c.trig_ptr) grid_clear16(c.qflag_next, c.H);
-    if (blockIdx.x == 0 && threadIdx.x < DF_LEN) c.df_next[threadIdx.x] = 0;
+    if (c.trig_ptr) grid_clear16(c.qflag_next + (ptrdiff_t)(c.H + 16) * dr, c.H);
+    if (blockIdx.x == 0 && threadIdx.x < DF_LEN) c.df_next[DF_LEN * dr + (int)threadIdx.x] = 0;
 }
 
 __device__ __forceinline__ void publish_push_counters(const DevCtx& c, BlockScratch& sm, const unsigned int (&cnt)[4])
@@ -252,9 +317,11 @@ __device__ __forceinline__ void block_share(const int64_t n, const int n_blocks,
 // wb = the block's index among the n_blocks working blocks (-1: a block without a share)
 // skip_own (peer mode inside a window): the owned agents' rows were already pushed by their blocks after yesterday's
 // agent pass; only the halo agents' bytes, which arrive from the peers, are scanned
-__device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb,
+// returns true when a wait for a peer GPU was abandoned (abort word / timeout): the launch must end
+__device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb,
                                                const bool skip_own = false)
 {
+    __shared__ int s_gave_up;
     const int tid = threadIdx.x, lane = tid & 31;
     push_clear_duties(c);
     if (tid < 64) sm.pdf[tid] = c.pdf[tid];
@@ -317,18 +384,22 @@ __device__ __forceinline__ void push_scan_body(const DevCtx& c, const int day, B
         // latency hides behind the local part of the push.  (Persistent grid: all CTAs resident, spinning is safe.)
         const int64_t own0 = c.lo - c.rt_lo, own1 = own0 + c.n_pad < c.rt_n ? own0 + c.n_pad : c.rt_n;
         if (!skip_own) scan(own0, own1);
+        if (tid == 0) s_gave_up = 0;
+        __syncthreads();
         if (tid < c.n_peers && ((c.wait_mask >> tid) & 1u)) {      // only the ranks whose agents are in this rank's halo
             const volatile int32_t* f = c.flag_wait + tid;
-            while (*f < day) __nanosleep(32);
+            if (spin_until(c, [&]() { return *f >= day; })) s_gave_up = 1;
             __threadfence_system();
         }
         __syncthreads();
+        if (s_gave_up) return true;
         if (own0 > 0) scan(0, own0);
         if (own1 < c.rt_n) scan(own1, c.rt_n);
     } else {
         scan(0, c.rt_n);
     }
     publish_push_counters(c, sm, cnt);
+    return false;
 }
 
 __global__ void __launch_bounds__(BLOCK) k_push(const DevCtx c, const int day)
@@ -366,23 +437,17 @@ struct Settled {
 };
 
 // what the settle phase fetches for one agent, all of it requested before any of it is used
-#ifndef DYS_EAGER_REC
-#define DYS_EAGER_REC 0
-#endif
 struct Loaded {
-    int4 rv, rw;         // the agent record: days in state, household size, area, home building | household, members, p_adm
+    int4 rv;             // first half of the agent record: days in state, household size, area, home building
     int mb;              // the infector the push left for this agent, or -1
 };
 
 __device__ __forceinline__ Loaded load_agent(const DevCtx& c, const int64_t a, const uint32_t st, const uint32_t att)
 {
     Loaded L;
+    // (the second half -- household, member list, p_adm -- is a dependent load on the few days of an agent's life when it
+    // can be admitted or diagnosed: fetching both halves for everybody measured 4 % slower)
     L.rv = reinterpret_cast<const int4*>(c.rec + a)[0];
-#if DYS_EAGER_REC
-    // (measured: fetching both halves for everybody is 4 % slower than the dependent load on the few days of an agent's
-    // life when it is admitted or diagnosed -- the four extra live registers cost more than the round trip)
-    L.rw = reinterpret_cast<const int4*>(c.rec + a)[1];
-#endif
     L.mb = -1;
     if (att & ATT_HIT) {
         // the mailbox that matches this agent's isolation; both are reset for the day after tomorrow
@@ -406,11 +471,7 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
     int tq = rv.x >> 16;
     const int tadm = (int16_t)(rv.y & 0xFFFF), hh_size = rv.y >> 16;
     const int sa_a = rv.z, home_a = rv.w;
-#if DYS_EAGER_REC
-    auto second_half = [&]() { return L.rw; };
-#else
     auto second_half = [&]() { return reinterpret_cast<const int4*>(c.rec + a)[1]; };
-#endif
     const bool quirk = any_nd && (c.trig_ptr || c.hh_always);
     const int h = quirk ? second_half().x : 0;
     const int mb = L.mb;
@@ -494,7 +555,7 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
 
 // One block folds the spread partial sums (part[counter][slot]: one warp per counter, two coalesced loads, shuffle tree),
 // derives the compartment statistics from the status counts and re-zeroes the partials (this day's ring entry).
-__device__ __forceinline__ void fold_stats(const DevCtx& c)
+__device__ __forceinline__ void fold_stats(unsigned long long* __restrict__ part, int64_t* __restrict__ stats)
 {
     __shared__ long long s_fold[N_STATS];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -502,7 +563,7 @@ __device__ __forceinline__ void fold_stats(const DevCtx& c)
     unsigned long long t[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        unsigned long long* p = c.part + (size_t)((tid >> 5) + 8 * q) * N_SLOTS;
+        unsigned long long* p = part + (size_t)((tid >> 5) + 8 * q) * N_SLOTS;
         t[q] = __ldcg(p + lane) + __ldcg(p + lane + 32);
         p[lane] = 0ull;
         p[lane + 32] = 0ull;
@@ -537,228 +598,205 @@ __device__ __forceinline__ void fold_stats(const DevCtx& c)
             default: break;
         }
         if (tid >= RAW_END) v = 0;
-        c.stats[tid] = v;
+        stats[tid] = v;
     }
     __syncthreads();
 }
 
-// VARIANT 0 = k_agent (the last block to finish folds the statistics); 3 = k_days (one block folds after the grid
-// barrier); 1, 2 = tools/kbench.cu ablations (no fold / no reduction at all).
-// cn = tomorrow's view: the block pushes the rows of its own newly infectious agents (null: no push, e.g. k_agent).
+// settle_round: ONE WARP settles <= 32 agents of its work list, one per lane -- record + mailbox loads issued together, B,
+// C, applying D, the ordered rules of E, F, G, tomorrow's snapshot byte and household flags.  The warp's counter
+// contributions are reduced with four REDUX + MATCH.ANY and added to the block's shared counters from distinct lanes.
+// Agents that are infectious tomorrow are appended to the warp's frontier wf[0 .. n_front).
+__device__ __forceinline__ void settle_round(const DevCtx& c, const int day, BlockScratch& sm, const uint32_t* entries, const int n,
+                                             const int64_t a_first, const bool any_nd, const DevCtx* cn, const FrontMap fmap,
+                                             uint32_t* wf, int& n_front)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool infected_today = false;
+    int infector = -1;
+    int64_t a = 0;
+    uint32_t ibn = 0, rel = 0;
+    uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
+    int kbin = -1;
+    const bool valid = lane < n;
+    uint32_t st = ST_PAD, att = 0;
+    Loaded L;
+    L.mb = -1;
+    if (valid) {
+        const uint32_t le = entries[lane];
+        rel = le & REL_MASK;
+        a = a_first + rel;
+        st = (le >> 24) & 0xFu;
+        att = (le >> 28) & 0x3u;
+        L = load_agent(c, a, st, att);
+    }
+    // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim is issued
+    // as soon as the mailboxes are in, its answer is only needed when the events are written
+    const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
+    int ev_base = 0;
+    if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+    if (valid) {
+        const Settled r = settle_agent(c, day, a, any_nd, st, att, L, infected_today, infector);
+        ibn = r.ibn;
+        kbin = r.k;
+        const uint32_t hi = hist_idx(r.x);
+        h0 = hi < 4 ? 1u << (8 * hi) : 0u;
+        h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
+        eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
+             ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
+        eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
+             ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
+    }
+    {
+        // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per non-zero
+        // counter from distinct lanes -- not 32 colliding atomics per counter
+        h0 = __reduce_add_sync(0xffffffffu, h0);
+        h1 = __reduce_add_sync(0xffffffffu, h1);
+        eA = __reduce_add_sync(0xffffffffu, eA);
+        eB = __reduce_add_sync(0xffffffffu, eB);
+        const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
+        const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
+        if (v) {
+            unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
+                              : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
+                              : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
+                              : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
+            atomicAdd(dst, v);
+        }
+        const unsigned km = __match_any_sync(0xffffffffu, kbin);
+        if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
+    }
+    if (evm) {
+        if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
+        if (c.ev) {
+            ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
+            if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+        }
+    }
+    if (cn) {
+        // infectious tomorrow: queue the agent's row for the warp's push of day + 1
+        const bool f = (ibn & IB_INF) != 0;
+        const unsigned fm = __ballot_sync(0xffffffffu, f);
+        if (f) {
+            wf[n_front + __popc(fm & lt_mask)] = rel | (ibn << 24);
+            prefetch_l2(cn->tptr + fmap.at(rel));
+        }
+        n_front += __popc(fm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// agent_body: the block owns the 128-agent pieces [p_first, p_last) of the view `c`; warp w takes pieces p_first + w,
+// p_first + w + 8, ... and runs on its own from there:
+//   sweep  : 4 agents per lane: one 32-bit load of the status bytes, one of the attention bytes (the next piece's words
+//            are requested before this piece is processed).  An agent to whom nothing can happen today -- susceptible
+//            or long recovered, attention byte 0 -- only feeds packed counters.  Every other agent is compacted
+//            (ballot + prefix popcount) into the warp's work list.
+//   settle : whenever the list holds 32 agents (and at the end) a settle_round() handles them, one per lane.
+//   push   : (cn != null) whenever the warp's frontier holds 32 rows (and at the end) push_group() pushes them along the
+//            transposed network for day + 1.
+// Divergent per-agent logic therefore costs instructions in proportion to the agents that need it, not to the
+// population, and no warp ever waits for another one of its block until the block's counters are published.
+// VARIANT 0 = k_agent (the last block to finish folds the statistics); 3 = k_days (one block folds after the grid barrier).
+// ---------------------------------------------------------------------------------------------------------------
 template <int VARIANT>
 __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn,
-                                           unsigned int (&push_cnt)[4], const int n_blocks, const int wb,
-                                           unsigned long long* tr = nullptr)
+                                           unsigned int (&push_cnt)[4], const int64_t p_first, const int64_t p_last)
 {
-    auto stamp = [&](int i) {        // developer tracing: globaltimer at phase boundaries
-        if (tr && threadIdx.x == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            tr[i] = t;
-        }
-    };
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < HIST_LEN) sm.hist[tid] = 0;
     if (tid < EV_LEN) sm.ev[tid] = 0;
     if (tid < 10) sm.cnt[tid] = 0;
-    if (tid == 0) { sm.n_list = 0; sm.n_front = 0; }
     if (cn && tid < 64) sm.pdf[tid] = c.pdf[tid];
     __syncthreads();
     const bool any_nd = c.df[DF_ANY_ND] != 0;
-    const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN;   // a recovered agent left the histogram
-    // The block owns a contiguous run of 128-agent pieces (one 4-byte word per lane): an equal share, or -- in k_days --
-    // today's cut of equal measured work.  Warp w handles slot s0 + w (+ 8) of a batch of 16 slots.
-    const int wid = tid >> 5;
-    const int64_t n_pieces = c.n_pad >> 7;
-    int64_t p_first, p_last;
-    if (wb < 0 || wb >= n_blocks) p_first = p_last = 0;
-    else if (c.cut_first >= 0) { p_first = c.cut_first; p_last = c.cut_last; }
-    else {
-        const int64_t per = (n_pieces + n_blocks - 1) / n_blocks;
-        p_first = wb * per < n_pieces ? wb * per : n_pieces;
-        p_last = p_first + per < n_pieces ? p_first + per : n_pieces;
-    }
-    const int64_t n_slots = p_last - p_first;
+    // a recovered agent left the histogram (see k_validate_population for agents LOADED as recovered)
+    const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN && day >= c.r_idle_day;
     const int64_t a_first = p_first << 7;
     const FrontMap fmap{c.lo - c.rt_lo + a_first};
-    auto agent_of = [&](uint32_t rel) { return a_first + rel; };
+    uint32_t* const wl = sm.wlist[wid];
+    uint32_t* const wf = sm.wfront[wid];
+    int n_list = 0, n_front = 0;                  // warp-uniform
     uint32_t n_idle_s = 0, n_idle_r = 0;
-    constexpr int SLOTS = LCAP / 128;             // slots per batch
-    if (tr && tid == 0) tr[1] = 0;
 
-    // first batch's words
-    uint32_t sw[2], aw[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int64_t sl = r * WARPS + wid;
-        sw[r] = aw[r] = 0;
-        if (sl < n_slots) {
-            const int64_t a0 = agent_of((uint32_t)(sl << 7) | (lane * 4));
-            sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
-            aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
-        }
+    int64_t p = p_first + wid;
+    uint32_t sw = 0, aw = 0;
+    if (p < p_last) {
+        const int64_t a0 = (p << 7) + lane * 4;
+        sw = *reinterpret_cast<const uint32_t*>(c.status + a0);
+        aw = *reinterpret_cast<const uint32_t*>(c.att + a0);
     }
-    for (int64_t s0 = 0; s0 < n_slots; s0 += SLOTS) {
+    for (; p < p_last; p += WARPS) {
+        // the next piece's words are requested before this piece is swept and settled
+        uint32_t sw_n = 0, aw_n = 0;
+        if (p + WARPS < p_last) {
+            const int64_t an = ((p + WARPS) << 7) + lane * 4;
+            sw_n = *reinterpret_cast<const uint32_t*>(c.status + an);
+            aw_n = *reinterpret_cast<const uint32_t*>(c.att + an);
+        }
         // ---- sweep ----
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int64_t sl = s0 + r * WARPS + wid;
-            const bool in = sl < n_slots;
-            const uint32_t rel0 = (uint32_t)(sl << 7) | (lane * 4);
-            const int64_t a0 = agent_of(rel0);
-            // four agents at once, byte-parallel: zb(x) has 0x80 in every byte of x that is zero (exact, no borrows)
-            auto zb = [](uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };
-            const uint32_t at0 = zb(aw[r]);                                           // attention byte == 0
-            const uint32_t idle_s = zb(sw[r] ^ (0x01010101u * ST_S)) & at0;           // susceptible, nothing pending
-            const uint32_t idle_r = r_idle ? zb(sw[r] ^ (0x01010101u * ST_R)) & at0 : 0u;
-            n_idle_s += __popc(idle_s);
-            n_idle_r += __popc(idle_r);
-            const uint32_t wk = ~(idle_s | idle_r | zb(sw[r])) & 0x80808080u;         // 0x80 per agent that must be settled
-            const uint32_t work = ((wk >> 7) | (wk >> 14) | (wk >> 21) | (wk >> 28)) & 0xFu;
-            if (c.piece_work) {
-                // what this piece costs a block (ns, measured with DYS_TRACE): ~50 for the sweep and ~65 per agent that is
-                // settled (most of them are infectious and push a row tomorrow as well)
-                const uint32_t cost = __reduce_add_sync(0xffffffffu, 65u * __popc(work));
-                if (in && lane == 0) c.piece_work[p_first + sl] = 50u + cost;
-            }
-            if (in) {
-                if (aw[r]) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
-                // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
-                if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
-            }
-            const int mine = __popc(work);
-            const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
-            if (any) {
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                int pos = 0;
-                if (lane == 31) pos = (int)atomicAdd(&sm.n_list, (unsigned)incl);
-                pos = __shfl_sync(0xffffffffu, pos, 31) + incl - mine;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((work >> j) & 1u)
-                        sm.list[pos++] = (rel0 + j) | (((sw[r] >> (8 * j)) & 0xFu) << 24) | (((aw[r] >> (8 * j)) & 0x3u) << 28);
-            }
+        const uint32_t rel0 = (uint32_t)((p - p_first) << 7) | (lane * 4);
+        const int64_t a0 = a_first + rel0;
+        // four agents at once, byte-parallel: zb(x) has 0x80 in every byte of x that is zero (exact, no borrows)
+        auto zb = [](uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };
+        const uint32_t at0 = zb(aw);                                              // attention byte == 0
+        const uint32_t idle_s = zb(sw ^ (0x01010101u * ST_S)) & at0;              // susceptible, nothing pending
+        const uint32_t idle_r = r_idle ? zb(sw ^ (0x01010101u * ST_R)) & at0 : 0u;
+        n_idle_s += __popc(idle_s);
+        n_idle_r += __popc(idle_r);
+        const uint32_t wk = ~(idle_s | idle_r | zb(sw)) & 0x80808080u;            // 0x80 per agent that must be settled
+        const uint32_t work = ((wk >> 7) | (wk >> 14) | (wk >> 21) | (wk >> 28)) & 0xFu;
+        const int mine = __popc(work);
+        if (c.piece_work) {
+            // what this piece costs a block (ns, measured with DYS_TRACE): ~50 for the sweep and ~65 per agent that is
+            // settled (most of them are infectious and push a row tomorrow as well)
+            const uint32_t cost = __reduce_add_sync(0xffffffffu, 65u * mine);
+            if (lane == 0) c.piece_work[p] = 50u + cost;
         }
-        // the next batch's words are requested before this batch is settled
+        if (aw) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
+        // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
+        if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
+        const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+        if (any) {
+            int incl = mine;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int64_t sl = s0 + SLOTS + r * WARPS + wid;
-            sw[r] = aw[r] = 0;
-            if (sl < n_slots) {
-                const int64_t a0 = agent_of((uint32_t)(sl << 7) | (lane * 4));
-                sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
-                aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-        }
-        __syncthreads();
-        if (s0 == 0) stamp(5);
-
-        // ---- settle: once the list might not take another batch, or after the last batch.  A block in a quiet part of
-        // the city sweeps all its pieces back to back and settles once ----
-        const int n_list = (int)sm.n_list;
-        const bool do_settle = n_list > LTOT - LCAP || s0 + SLOTS >= n_slots;
-        if (do_settle) {
-        if (tr && tid == 0) tr[1] += (unsigned long long)n_list << 32;      // tracing: settled agents | pushed rows
-        for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
-            const int k = k0 + tid;
-            bool infected_today = false;
-            int infector = -1;
-            int64_t a = 0;
-            uint32_t ibn = 0, rel = 0;
-            uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
-            int kbin = -1;
-            const bool valid = k < n_list;
-            uint32_t st = ST_PAD, att = 0;
-            Loaded L;
-            L.mb = -1;
-            if (valid) {
-                const uint32_t le = sm.list[k];
-                rel = le & REL_MASK;
-                a = agent_of(rel);
-                st = (le >> 24) & 0xFu;
-                att = (le >> 28) & 0x3u;
-                L = load_agent(c, a, st, att);
-            }
-            // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim
-            // is issued as soon as the mailboxes are in, its answer is only needed when the events are written
-            const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
-            if (k0 == 0) stamp(8);      // (the ballot needed the mailboxes: first round's loads are in)
-            int ev_base = 0;
-            if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
-            if (valid) {
-                const Settled r = settle_agent(c, day, a, any_nd, st, att, L, infected_today, infector);
-                ibn = r.ibn;
-                kbin = r.k;
-                const uint32_t hi = hist_idx(r.x);
-                h0 = hi < 4 ? 1u << (8 * hi) : 0u;
-                h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
-                eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
-                     ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
-                eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
-                     ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
-            }
-            if (k0 == 0) stamp(9);      // first round settled
-            {
-                // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per
-                // non-zero counter from distinct lanes -- not 32 colliding atomics per counter
-                h0 = __reduce_add_sync(0xffffffffu, h0);
-                h1 = __reduce_add_sync(0xffffffffu, h1);
-                eA = __reduce_add_sync(0xffffffffu, eA);
-                eB = __reduce_add_sync(0xffffffffu, eB);
-                const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
-                const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
-                if (v) {
-                    unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
-                                      : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
-                                      : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
-                                      : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
-                    atomicAdd(dst, v);
-                }
-                const unsigned km = __match_any_sync(0xffffffffu, kbin);
-                if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
-            }
-            if (evm) {
-                if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
-                if (c.ev) {
-                    ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
-                    if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
-                }
-            }
-            if (k0 == 0) stamp(10);     // counters and events done
-            if (cn) {
-                // infectious tomorrow: queue the agent's row for the block's push of day + 1
-                const bool f = (ibn & IB_INF) != 0;
-                const unsigned fm = __ballot_sync(0xffffffffu, f);
-                if (fm) {
-                    int base = 0;
-                    if (lane == 0) base = (int)atomicAdd(&sm.n_front, (unsigned)__popc(fm));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (f) {
-                        sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
-                        prefetch_l2(cn->tptr + fmap.at(rel));
-                    }
+            int pos = n_list + incl - mine;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((work >> j) & 1u)
+                    wl[pos++] = (rel0 + j) | (((sw >> (8 * j)) & 0xFu) << 24) | (((aw >> (8 * j)) & 0x3u) << 28);
+            n_list += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            // ---- settle (and push) whenever a full warp of work is queued ----
+            while (n_list >= 32) {
+                n_list -= 32;
+                settle_round(c, day, sm, wl + n_list, 32, a_first, any_nd, cn, fmap, wf, n_front);
+                __syncwarp();
+                if (n_front >= 32) {
+                    n_front -= 32;
+                    push_group<false>(*cn, day + 1, sm.pw[wid], sm.pdf, wf + n_front, 32, fmap, push_cnt);
+                    __syncwarp();
                 }
             }
         }
-        __syncthreads();      // the work list is free; the frontier count is final
-        stamp(6);
-        if (tid == 0) sm.n_list = 0;
-        if (tr && tid == 0 && cn) tr[1] += sm.n_front;
-        if (cn && sm.n_front) {      // (a settle can add as many rows as the frontier holds: push after each)
-            push_frontier<false>(*cn, day + 1, sm, fmap, push_cnt);      // (the work list's memory is the push scratch)
-            __syncthreads();
-            if (tid == 0) sm.n_front = 0;
-        }
-        }
-        __syncthreads();
+        sw = sw_n;
+        aw = aw_n;
     }
-    if (VARIANT == 2) return;
+    if (n_list) {
+        settle_round(c, day, sm, wl, n_list, a_first, any_nd, cn, fmap, wf, n_front);
+        __syncwarp();
+    }
+    while (n_front > 0) {
+        const int nb = n_front < 32 ? n_front : 32;
+        n_front -= nb;
+        push_group<false>(*cn, day + 1, sm.pw[wid], sm.pdf, wf + n_front, nb, fmap, push_cnt);
+        __syncwarp();
+    }
     {
         // idle agents: end-of-day status == day-start status
         const uint32_t tot_s = __reduce_add_sync(0xffffffffu, n_idle_s), tot_r = __reduce_add_sync(0xffffffffu, n_idle_r);
@@ -771,7 +809,6 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
     if (tid < 32) {
         // warp 0 publishes everything, fences, and takes the ticket
         const int slot = blockIdx.x & (N_SLOTS - 1);
-        stamp(7);
         if (lane < 10 && sm.cnt[lane])
             atomicAdd(&c.part[(size_t)(RAW_END + lane) * N_SLOTS + slot], (unsigned long long)sm.cnt[lane]);
         if (lane < EV_LEN && sm.ev[lane]) {
@@ -791,7 +828,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
     if (VARIANT != 0) return;
     __syncthreads();
     if (sm.last) {
-        fold_stats(c);      // the last block to finish
+        fold_stats(c.part, c.stats);      // the last block to finish
         if (tid == 0) *c.ticket = 0u;
     }
 }
@@ -800,7 +837,11 @@ __global__ void __launch_bounds__(BLOCK) k_agent(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
     unsigned int none[4] = {0, 0, 0, 0};
-    agent_body<0>(c, day, sm, nullptr, none, (int)gridDim.x, (int)blockIdx.x);
+    const int64_t n_pieces = c.n_pad >> 7;
+    const int64_t per = (n_pieces + gridDim.x - 1) / gridDim.x;
+    const int64_t p0 = (int64_t)blockIdx.x * per < n_pieces ? (int64_t)blockIdx.x * per : n_pieces;
+    const int64_t p1 = p0 + per < n_pieces ? p0 + per : n_pieces;
+    agent_body<0>(c, day, sm, nullptr, none, p0, p1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -842,6 +883,7 @@ struct DayPlan {
     DayBuffers buf;
     int32_t want_sa, want_bc, want_ev;
     unsigned long long* trace;                      // developer tracing: [n_days][grid][8] globaltimer at phase boundaries, or null
+    int32_t test_hang_block;                        // tests (DYS_TEST_HANG_BLOCK): this block leaves before the first barrier; -1 = none
 };
 
 __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const DayPlan& plan, const int k)
@@ -964,28 +1006,32 @@ __device__ __forceinline__ void plan_cut(const uint32_t* __restrict__ work, int3
     }
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
+// All CTAs are resident (cooperative launch): one arrival per CTA on a monotone counter, no reset needed.
+__device__ __forceinline__ bool grid_barrier(const DevCtx& c, unsigned int* counter, unsigned int& epoch)
 {
-    // all CTAs are resident (cooperative launch); one arrival per CTA, monotone counter, no reset needed
+    __shared__ int s_abort;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
         ++epoch;
         const unsigned int target = epoch * gridDim.x;
-        while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(32);
+        s_abort = spin_until(c, [&]() { return *reinterpret_cast<volatile unsigned int*>(counter) >= target; }) ? 1 : 0;
         __threadfence();
     }
     __syncthreads();
+    return s_abort != 0;
 }
 
 __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPlan plan, unsigned int* barrier_counter)
 {
     __shared__ BlockScratch sm;
     __shared__ DevCtx s_c[2];            // today's and tomorrow's view of the context (read like kernel parameters)
+    __shared__ DevCtx s_r[2];            // replicas: the same two views shifted to the replica the block is working on
     __shared__ bool s_pub_last;
     unsigned int epoch = 0;
     const bool peers = c0.n_peers > 1;
+    const int n_rep = c0.n_rep > 1 ? c0.n_rep : 1;
     // io_mat is one buffer for the latest day: the push of day + 1 must not clear it under the agent pass of day
     const bool two_phase = peers || c0.io_mat != nullptr;
     // Block 0 owns no agents: it folds each day's statistics and re-cuts the population after the barrier while the
@@ -994,8 +1040,18 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     const bool service = gridDim.x > 1 && blockIdx.x == 0;
     const int n_work = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
     const int wb = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+    const int64_t n_pieces = c0.n_pad >> 7, n_pieces_all = n_pieces * n_rep;
     if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0);
     __syncthreads();
+    if ((int)blockIdx.x == plan.test_hang_block) return;      // (tests: the others must time out at the barrier, not hang)
+    // the view of replica r of a day: with one replica the day's view itself, no copy
+    auto replica_view = [&](const DevCtx& day_view, const int slot, const int r) -> const DevCtx& {
+        if (n_rep == 1) return day_view;
+        __syncthreads();                       // (everybody is done with the previous occupant of the slot)
+        if (threadIdx.x == 0) { s_r[slot] = day_view; shift_replica(s_r[slot], r); }
+        __syncthreads();
+        return s_r[slot];
+    };
     for (int k = 0; k < plan.n_days; ++k) {
         const int day = plan.first_day + k;
         const DevCtx& c = s_c[k & 1];
@@ -1004,33 +1060,57 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         __syncthreads();
         unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * TRACE_SLOTS : nullptr;
         auto stamp = [&](int i) {
-            if (tr && threadIdx.x == 0) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                tr[i] = t;
-            }
+            if (tr && threadIdx.x == 0) tr[i] = global_ns();
         };
         stamp(0);
         if (k == 0 || two_phase) {
-            push_scan_body(c, day, sm, n_work, wb, peers && k > 0);
+            for (int r = 0; r < n_rep; ++r) {
+                const DevCtx& cr = replica_view(c, 0, r);
+                if (push_scan_body(cr, day, sm, n_work, wb, peers && k > 0)) return;
+                __syncthreads();
+            }
             stamp(1);
-            grid_barrier(barrier_counter, epoch);
+            if (grid_barrier(c, barrier_counter, epoch)) return;
         }
         stamp(2);
-        unsigned int push_cnt[4] = {0, 0, 0, 0};
         const DevCtx* cn = local_push ? &s_c[(k + 1) & 1] : nullptr;
-        if (cn) push_clear_duties(*cn);
-        agent_body<3>(c, day, sm, cn, push_cnt, n_work, wb, tr);
-        if (cn) { __syncthreads(); publish_push_counters(*cn, sm, push_cnt); }
+        if (cn)
+            for (int r = 0; r < n_rep; ++r) push_clear_duties(*cn, r);
+        {
+            // the block's run of pieces in the unified piece space [replica][piece]: today's cut of equal measured work,
+            // or an equal share; one agent_body per replica the run touches
+            int64_t P0, P1;
+            if (wb < 0 || wb >= n_work) P0 = P1 = 0;
+            else if (c.cut_first >= 0) { P0 = c.cut_first; P1 = c.cut_last; }
+            else {
+                const int64_t per = (n_pieces_all + n_work - 1) / n_work;
+                P0 = wb * per < n_pieces_all ? wb * per : n_pieces_all;
+                P1 = P0 + per < n_pieces_all ? P0 + per : n_pieces_all;
+            }
+            for (int64_t P = P0; P < P1;) {
+                const int r = (int)(P / n_pieces);
+                const int64_t p0 = P - (int64_t)r * n_pieces;
+                const int64_t p1 = P1 - (int64_t)r * n_pieces < n_pieces ? P1 - (int64_t)r * n_pieces : n_pieces;
+                unsigned int push_cnt[4] = {0, 0, 0, 0};
+                const DevCtx& cr = replica_view(c, 0, r);
+                const DevCtx* cnr = cn ? &replica_view(*cn, 1, r) : nullptr;
+                agent_body<3>(cr, day, sm, cnr, push_cnt, p0, p1);
+                if (cnr) { __syncthreads(); publish_push_counters(*cnr, sm, push_cnt); }
+                __syncthreads();
+                P += p1 - p0;
+            }
+        }
         stamp(3);
-        grid_barrier(barrier_counter, epoch);
+        if (grid_barrier(c, barrier_counter, epoch)) return;
         stamp(4);
         if (service || gridDim.x == 1) {                      // every block's partial sums are in; the others move on
-            fold_stats(c);
+            for (int r = 0; r < n_rep; ++r)
+                fold_stats(c.part + (size_t)r * N_STATS * N_SLOTS,
+                           reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(c.stats) + (size_t)r * c.out_stride));
             // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
             // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a
             // quiet day.  The cut made after day d is the one of day d + 3.)
-            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, c.n_pad >> 7, n_work, sm, tr);
+            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
             stamp(11);
         }
         const int n_pub = PUBLISH_BLOCKS < n_work ? PUBLISH_BLOCKS : n_work;

@@ -35,6 +35,19 @@ __global__ void k_validate_population(const DevCtx c, int32_t* bad)
     if ((s == ST_S || s == ST_I || s == ST_R || s == ST_X) && r.t_adm != 0) atomicOr(bad, 4);
     if (c.src[a] < -1 || c.src[a] >= c.n_glob) atomicOr(bad, 8);
     if ((s == ST_S || s == ST_QH) && c.src[a] != -1) atomicOr(bad, 512);
+    // a recovered agent is only idle (skipped by the sweep) once it has left the 21-bin days-since-infection histogram;
+    // agents that recover during the run always have (recover >= 21), agents LOADED as recovered may not
+    if (s == ST_R) atomicMax(bad + 1, (int32_t)r.t_inf + HIST_LEN);
+}
+
+// dys_load_quirk: trigger lists must be monotone and name owned households (raise_household stores qflag[trig_hh[t]])
+__global__ void k_validate_quirk(const int64_t* __restrict__ trig_ptr, const int32_t* __restrict__ trig_hh, int64_t n, int64_t nt,
+                                 int64_t H, int32_t* bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && trig_ptr[0] != 0) atomicOr(bad, 2048);
+    if (i < n && (trig_ptr[i + 1] < trig_ptr[i] || trig_ptr[i + 1] > nt)) atomicOr(bad, 2048);
+    if (i < nt && (trig_hh[i] < 0 || trig_hh[i] >= H)) atomicOr(bad, 4096);
 }
 
 // household / home building / area indices arrive global and are stored relative to the owned ranges

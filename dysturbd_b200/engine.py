@@ -41,7 +41,7 @@ class _Params(C.Structure):
         ("n_slots", C.c_int32), ("recover", C.c_int32), ("hospital_recover", C.c_int32), ("diagnosis", C.c_int32),
         ("quarantine", C.c_int32), ("adm_min_day", C.c_int32), ("adm_max_day", C.c_int32), ("death_min_adm_day", C.c_int32),
         ("norm_factor", C.c_double), ("compliance", C.c_double), ("pdf_table", C.c_double * 64),
-        ("seed", C.c_uint64), ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("seed", C.c_uint64), ("flags", C.c_int32), ("n_replicas", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
         ("halo_lo", C.c_int64), ("halo_hi", C.c_int64),
         ("hh_lo", C.c_int64), ("hh_hi", C.c_int64), ("bld_lo", C.c_int64), ("bld_hi", C.c_int64),
@@ -63,7 +63,8 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_set_open", "dys_set_run", "dys_set_state", "dys_step", "dys_step_many", "dys_step_begin", "dys_step_end", "dys_get_stats",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
-           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach"]
+           "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach",
+           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes"]
 
 _lib = None
 
@@ -110,6 +111,11 @@ def load_library():
     lib.dys_peer_export.argtypes = [vp, vp]
     lib.dys_peer_attach.argtypes = [vp, C.c_int, vp, vp]
     lib.dys_peer_detach.argtypes = [vp]
+    lib.dys_set_replica_params.argtypes = [vp, vp, vp, vp]
+    lib.dys_select_replica.argtypes = [vp, i32]
+    lib.dys_abort.argtypes = [vp]
+    lib.dys_h2d_bytes.argtypes = [vp]
+    lib.dys_h2d_bytes.restype = i64
     _lib = lib
     return lib
 
@@ -152,7 +158,7 @@ class Engine:
     `step(day)` is one pass of the reference's day loop; outputs are the integer arrays behind contagious3.py:326-366."""
 
     def __init__(self, pop: Population, params: EpiParams, device=0, flags=WANT_SA_HIST | WANT_BUILDING_COUNTS | WANT_EVENTS,
-                 rank=0, world=1):
+                 rank=0, world=1, replicas=1):
         self.lib = load_library()
         self.pop, self.params = pop, params
         self.N_glob = pop.N_glob
@@ -164,6 +170,7 @@ class Engine:
         for i in range(64):
             p.pdf_table[i] = float(params.pdf[i])
         p.rank, p.world = rank, world
+        p.n_replicas = self.replicas = int(replicas)
         p.shard_lo, p.shard_hi = pop.lo, pop.lo + pop.N
         p.halo_lo, p.halo_hi = pop.halo
         self.hh_range = pop.hh_range or (0, pop.H)
@@ -218,6 +225,23 @@ class Engine:
         if seed is not None:
             pr.seed = seed
         self._ck(self.lib.dys_set_run(self.h, pr.norm_factor, pr.compliance, pr.seed))
+
+    def set_replica_params(self, norm_factor=None, compliance=None, seed=None):
+        """per-replica run parameters (arrays of `replicas`); None keeps the current values"""
+        arr = lambda x, dt: None if x is None else np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dt), (self.replicas,)))
+        nf, cp, sd = arr(norm_factor, np.float64), arr(compliance, np.float64), arr(seed, np.uint64)
+        self._ck(self.lib.dys_set_replica_params(self.h, *[None if x is None else x.ctypes.data for x in (nf, cp, sd)]))
+
+    def select_replica(self, r):
+        """point the getters (outputs, stats, state, events ...) and set_state at replica r (-1: all / replica 0)"""
+        self._ck(self.lib.dys_select_replica(self.h, int(r)))
+        self._views = {}
+
+    def abort(self):
+        self._ck(self.lib.dys_abort(self.h))
+
+    def h2d_bytes(self):
+        return int(self.lib.dys_h2d_bytes(self.h))
 
     def set_state(self, status, t_inf, t_q, t_adm, src):
         n = self.n_loc

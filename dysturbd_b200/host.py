@@ -86,7 +86,8 @@ class EpidemicModel:
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
                  device=0, choice_seed=None, backend=None, population=None, compact=False):
         self.params = params or EpiParams()
-        self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob)
+        self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob,
+                                                                   diagnosis=self.params.diagnosis)
         self.scenario = list(scenario)
         self.sim = backend(self.pop, self.params) if backend is not None else Engine(self.pop, self.params, device=device)
         # compact=True: 'SAs', 'Buildings' and 'IO_mat' hold numpy arrays instead of the reference's nested dicts and

@@ -117,7 +117,7 @@ class Population:
         return {k: getattr(self, k).copy() for k in ("status", "t_inf", "t_q", "t_adm", "src")}
 
     @staticmethod
-    def from_reference(agents, build, bld_visits_by_agents, interaction_prob):
+    def from_reference(agents, build, bld_visits_by_agents, interaction_prob, diagnosis=7):
         agents = np.asarray(agents, dtype=np.float64)
         build = np.asarray(build, dtype=np.float64)
         N, B = agents.shape[0], build.shape[0]
@@ -156,7 +156,7 @@ class Population:
         if ip.shape != (N, N):
             raise ValueError("interaction_prob must be [N,N]")
 
-        hh_always, trig_ptr, trig_hh = quirk_sets(agents, hh_ids, hh.astype(np.int32))
+        hh_always, trig_ptr, trig_hh = quirk_sets(agents, hh_ids, hh.astype(np.int32), diagnosis)
         return Population(
             N=N, H=len(hh_ids), B=B, S=len(sa_ids), V=V,
             status=status, t_inf=agents[:, 16].astype(np.int32), t_q=agents[:, 19].astype(np.int32),
@@ -183,7 +183,7 @@ class Population:
         return agents
 
 
-def quirk_sets(agents, hh_ids, hh):
+def quirk_sets(agents, hh_ids, hh, diagnosis=7):
     """Reproduce `np.isin(agents[:, 1], new_diagnosed_agents)` (contagious3.py:267): the household id of a
     status-2 agent is tested against EVERY value in the newly diagnosed agents' full rows, not just their
     household column.  Returns
@@ -195,7 +195,7 @@ def quirk_sets(agents, hh_ids, hh):
     N = agents.shape[0]
     H = len(hh_ids)
     static_cols = [c for c in range(agents.shape[1]) if c not in DYNAMIC_COLS and c != 1]
-    always_vals = np.array([0.0, 4.0, 7.0])
+    always_vals = np.array([0.0, 4.0, float(diagnosis)])
     hh_always = np.isin(hh_ids, always_vals).astype(np.uint8)
     small = (hh_ids == np.round(hh_ids)) & (hh_ids >= 1) & (hh_ids < 100000) & (hh_always == 0)
     if small.any():

@@ -37,7 +37,8 @@ typedef enum {
     DYS_ERR_STATE = -3,     /* call order (e.g. step before load) */
     DYS_ERR_NOMEM = -4,
     DYS_ERR_RANGE = -5,     /* index out of range in an input array */
-    DYS_ERR_NOT_AVAILABLE = -6
+    DYS_ERR_NOT_AVAILABLE = -6,
+    DYS_ERR_ABORTED = -7    /* a launch was abandoned: dys_abort(), or a grid barrier / peer wait timed out (DYS_SPIN_TIMEOUT_MS) */
 } dys_status;
 
 enum { DYS_S = 2, DYS_I = 4, DYS_QH = 6, DYS_QI = 7, DYS_D = 8, DYS_H = 10, DYS_R = 12, DYS_X = 14 };
@@ -103,7 +104,9 @@ typedef struct dys_params {
     double pdf_table[DYS_PDF_LEN]; /* contagious_risk_day.pdf(0..63), host-computed (parameters.py:44) */
     uint64_t seed;               /* Philox key; counter = (a, b, day, stream) */
     int32_t flags;
-    int32_t reserved;
+    int32_t n_replicas;          /* Monte-Carlo replicas held by this handle (0 or 1 = a single run).  Replicas share the city
+                                  * (network, routines, households) and differ in state, seed, norm_factor and compliance;
+                                  * dys_step_many advances ALL of them in one launch.  Not with world > 1 / DYS_WANT_IO_MAT. */
     /* sharded mode (world > 1): this handle owns agents [shard_lo, shard_hi) of the n_agents global agents */
     int32_t rank, world;
     int64_t shard_lo, shard_hi;
@@ -145,6 +148,15 @@ int dys_load_quirk(dys_handle* h, const uint8_t* hh_always, const int64_t* trig_
 int dys_set_open(dys_handle* h, const uint8_t* open_flags);
 /* parameter sweeps / Monte-Carlo replicas on a loaded population */
 int dys_set_run(dys_handle* h, double norm_factor, double compliance, uint64_t seed);
+/* n_replicas > 1: the per-replica run parameters (arrays of n_replicas; NULL = keep).  dys_load_population / dys_set_state
+ * give every replica the same initial state; dys_select_replica(r) points the getters (dys_get_outputs, dys_get_stats,
+ * dys_get_sa_hist, dys_get_building_counts, dys_get_events, dys_get_state) and dys_set_state at replica r
+ * (r = -1: dys_set_state writes all replicas, getters read replica 0). */
+int dys_set_replica_params(dys_handle* h, const double* norm_factor, const double* compliance, const uint64_t* seed);
+int dys_select_replica(dys_handle* h, int32_t r);
+/* asks a running launch to end at its next spin check (grid barrier / peer wait); the handle then reports
+ * DYS_ERR_ABORTED until dys_set_state / dys_load_population.  Safe to call from another host thread. */
+int dys_abort(dys_handle* h);
 int dys_set_state(dys_handle* h, const uint8_t* status_x2, const int32_t* t_inf, const int32_t* t_q,
                   const int32_t* t_adm, const int32_t* src);
 
@@ -199,6 +211,8 @@ typedef enum { DYS_BUF_STATUS = 0, DYS_BUF_INFECTIOUS = 1, DYS_BUF_STATS = 2, DY
 int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* bytes);
 int dys_cuda_stream(dys_handle* h, void** stream);
 int64_t dys_device_bytes(const dys_handle* h);
+/* bytes of open flags uploaded host -> device by dys_step_many so far (benchmark accounting) */
+int64_t dys_h2d_bytes(const dys_handle* h);
 /* Peer mode (sharded populations on one NVLink/NVSwitch node): every rank exports CUDA IPC handles of its snapshot
  * buffer and flag array, gathers all ranks' handles (any host-side all-gather) and attaches them.  From then on the
  * kernel that produces tomorrow's snapshot bytes stores them straight into every peer GPU's buffer and raises a flag

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE (oracle) -- generates the config-1 (shipped city) reference artefacts.
 
-Runs ONLY in the authoring container (needs /root/reference).  Produces, under oracle/_ref/ (git-ignored):
+Runs ONLY in the authoring container (needs /root/reference).  Produces, under tests/golden/config1/ (committed; the
+8 GB-class interaction_prob cache goes to oracle/_ref/local/, git-ignored):
   config1_inputs.npz          agents[N,29], build[B,15], bld_visits_by_agents[N,10], agent-agent edge list of
                               the communities.py graph (so interaction_prob can be rebuilt without the reference)
   config1_<scenario>_golden.npz   per-day state columns + the reference's own Stats/SAs/Buildings/IO_mat output,
@@ -20,6 +21,7 @@ from . import literal
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
+OUT = os.path.normpath(os.path.join(HERE, "..", "tests", "golden", "config1"))
 
 
 def agent_edges(G, agents):
@@ -40,13 +42,14 @@ def main():
     ap.add_argument("--scenario", default="noLockdown")
     args = ap.parse_args()
     os.makedirs(os.path.join(REF, "local"), exist_ok=True)
+    os.makedirs(OUT, exist_ok=True)
     ind = os.path.join(literal.REFERENCE_DIR, "Data", "civ_withCar_bldg_np.csv")
     bld = os.path.join(literal.REFERENCE_DIR, "Data", "bldg_with_inst_orig.csv")
     t0 = time.time()
     s = literal.reference_setup(ind, bld, seed=args.seed, verbose=True)
     print("setup", time.time() - t0, s["timings"], flush=True)
     er, ec, ew = agent_edges(s["G"], s["agents"])
-    np.savez_compressed(os.path.join(REF, "config1_inputs.npz"), agents=s["agents"], build=s["build"],
+    np.savez_compressed(os.path.join(OUT, "config1_inputs.npz"), agents=s["agents"], build=s["build"],
                         bld_visits_by_agents=s["bld_visits_by_agents"], households=np.asarray(s["households"], np.float64),
                         edge_row=er, edge_col=ec, edge_w=ew, seed=args.seed,
                         timings=json.dumps(s["timings"]))
@@ -73,7 +76,7 @@ def main():
         "philox_seed": args.philox_seed,
         "outputs_json": json.dumps(r["outputs"], default=lambda o: o.item() if hasattr(o, "item") else str(o)),
     }
-    np.savez_compressed(os.path.join(REF, "config1_%s_golden.npz" % args.scenario), **out)
+    np.savez_compressed(os.path.join(OUT, "config1_%s_golden.npz" % args.scenario), **out)
     print("done", flush=True)
 
 

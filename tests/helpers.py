@@ -114,9 +114,9 @@ def compare_sims(a, b, days, open_fn=None):
 
 
 # ---- config 1: the shipped city at full size (22 493 agents), literal reference run for 100 days ----
-REF_DIR = os.path.join(os.path.dirname(GOLDEN.rstrip("/")), "..", "oracle", "_ref")
-REF_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref"))
-CONFIG1_IP_CACHES = [os.path.join(REF_DIR, "local", "config1_ip_csr.npz"), "/tmp/dys_ref_local/config1_ip_csr.npz"]
+REF_DIR = os.path.join(GOLDEN, "config1")          # committed: the only full-size pin of the reference
+_REF_LOCAL = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "local"))
+CONFIG1_IP_CACHES = [os.path.join(_REF_LOCAL, "config1_ip_csr.npz"), "/tmp/dys_ref_local/config1_ip_csr.npz"]
 
 
 def config1_available():

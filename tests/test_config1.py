@@ -1,15 +1,18 @@
 """BASELINE.json configs[0]: the repo's shipped city (22 493 agents, 1 015 buildings, interaction_prob with 162.5 M
 non-zeros) against the UNMODIFIED contagious3.py loop run for 100 days under keyed Philox draws
-(oracle/make_config1_ref.py -> oracle/_ref/, git-ignored, shipped to the GPU box).  Bit-exact agent state and Stats."""
+(oracle/make_config1_ref.py -> tests/golden/config1/, committed).  Bit-exact agent state and Stats."""
 import numpy as np
 import pytest
 
 from helpers import Config1, config1_available, config1_ip_cached
 
-needs_ref = pytest.mark.skipif(not config1_available(), reason="oracle/_ref/config1_* not generated (oracle/make_config1_ref.py)")
 
 
-@needs_ref
+def test_config1_fixture_is_committed():
+    """the only full-size pin of the reference: its absence is a failure, not a skip"""
+    assert config1_available(), "tests/golden/config1/config1_*.npz missing (oracle/make_config1_ref.py generates them)"
+
+
 @pytest.mark.skipif(not config1_ip_cached(), reason="interaction_prob cache absent (rebuilding it takes minutes; the GPU test does)")
 def test_oracle_matches_reference_on_shipped_city(oracle_lib):
     c1 = Config1(allow_recompute=False)
@@ -19,7 +22,6 @@ def test_oracle_matches_reference_on_shipped_city(oracle_lib):
         c1.check_day(sim, d)
 
 
-@needs_ref
 @pytest.mark.gpu
 def test_engine_matches_reference_on_shipped_city_100_days():
     from dysturbd_b200 import engine
