@@ -43,7 +43,8 @@ struct dys_handle {
     RepParam* d_rep = nullptr;
     volatile int32_t* h_abort = nullptr;            // pinned + mapped: the kernels poll it in their spin loops
     int64_t h2d_bytes = 0;                          // flag bytes uploaded so far (bench accounting)
-    unsigned int* d_barrier = nullptr;              // grid barrier counter of k_days
+    unsigned int* d_barrier = nullptr;              // grid barrier counter of k_days, publish ticket, blocks done with their run
+    unsigned long long* d_work = nullptr;           // [grid] work words of k_days (dynamic batches, stealing)
     int days_grid = 0;                              // cooperative grid of k_days (0 = not available)
     std::vector<void*> allocs;
     int64_t dev_bytes = 0;
@@ -291,6 +292,8 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open_ring[k], (size_t)MAX_FUSED_DAYS * (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
     }
     A(dev_alloc(h, &h->d_barrier, 4));
+    A(dev_alloc(h, &h->d_work, h->days_grid > 0 ? h->days_grid : 1));
+    { const char* t = getenv("DYS_NO_STEAL"); if (t && t[0] == '1') h->d_work = nullptr; }      // (developer: ablation)
     if (rc == DYS_OK) {
         void* ab = nullptr;
         if (cudaHostAlloc(&ab, 64, cudaHostAllocMapped) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -942,7 +945,9 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         if (rc != DYS_OK) return rc;
     }
     bind_day(c, h->buf, first_day);    // (k_days binds every day's view itself)
-    CK(h, cudaMemsetAsync(h->d_barrier, 0, 2 * sizeof(unsigned int), h->stream));
+    CK(h, cudaMemsetAsync(h->d_barrier, 0, 4 * sizeof(unsigned int), h->stream));
+    if (h->d_work) CK(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned long long) * (size_t)h->days_grid, h->stream));
+    plan.work = h->d_work;
     unsigned int* bar = h->d_barrier;
     void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
     const size_t trace_words = (size_t)MAX_FUSED_DAYS * (size_t)h->days_grid * TRACE_SLOTS;
@@ -1180,6 +1185,27 @@ extern "C" int dys_sync(dys_handle* h)
 }
 
 extern "C" int64_t dys_h2d_bytes(const dys_handle* h) { return h ? h->h2d_bytes : 0; }
+
+// compute_R (contagious3.py:29-42) for `rows` days-since-infection histograms in HOST memory: the float epilogue of the
+// integer outputs, in the reference's order of operations (sum_I += n_i * pdf(i) for i = 1 .. recover-1, ascending; IEEE
+// double, no contraction), so the values compare with == against the reference's.
+extern "C" int dys_compute_R_rows(const void* hist, int32_t elem_bytes, int64_t rows, int64_t row_stride, const double* pdf,
+                                  int32_t recover, double* out)
+{
+    if (!hist || !pdf || !out || rows < 0 || (elem_bytes != 4 && elem_bytes != 8) || recover < 1 || recover > HIST_LEN) return DYS_ERR_INVALID_ARG;
+    for (int64_t r = 0; r < rows; ++r) {
+        volatile double sum_I = 0.0;      // (volatile: every product and every sum is rounded to double on its own)
+        double first = 0.0;
+        for (int i = 0; i < recover; ++i) {
+            const double n = elem_bytes == 4 ? (double)((const int32_t*)hist)[r * row_stride + i] : (double)((const int64_t*)hist)[r * row_stride + i];
+            if (i == 0) { first = n; continue; }
+            volatile double prod = n * pdf[i];
+            sum_I = sum_I + prod;
+        }
+        out[r] = sum_I > 0.0 ? first / sum_I : 0.0;
+    }
+    return DYS_OK;
+}
 
 extern "C" int dys_get_kernel_times(dys_handle* h, double* ms_total, int64_t* launches)
 {

@@ -86,18 +86,12 @@ __device__ __forceinline__ bool spin_until(const DevCtx& c, Cond done)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Shared memory of a block (256 threads = 8 warps).
-//   agent pass : every WARP keeps its own work list and its own frontier -- the warps of a block never wait for each
-//                other inside a day (no __syncthreads between the sweep, the settle rounds and the pushes), so an SM
-//                always has 32 independent chains of memory round trips in flight instead of 4 block-wide phases.
-//   scan push  : a block-wide frontier (first day of a window, stand-alone k_push).
-//   plan_cut   : the same memory staged as 8192 piece costs.
+// Shared memory of a block (256 threads = 8 warps).  The frontier outlives the agent pass; plan_cut stages 8192 piece
+// costs in front + list.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BLOCK = 256, WARPS = BLOCK / 32;
 constexpr int FCAP = 4096;                         // scan-push frontier entries: index relative to the block's base | snapshot byte << 24
 constexpr int LTOT = 4096;                         // (with `front`: the staging area of plan_cut)
-constexpr int WL_CAP = 160;                        // a warp's work list: < 32 left over + one 128-agent piece
-constexpr int WF_CAP = 64;                         // a warp's frontier: < 32 left over + one settle round
 constexpr uint32_t REL_MASK = 0x00FFFFFFu;
 
 // where a block's queued agents live: halo-relative index = base + rel
@@ -115,19 +109,13 @@ struct PushWarpScratch {
 enum { EV_ADM = 0, EV_DEATH, EV_DAILY_INF, EV_DAILY_QUAR, EV_NEW_DIAG, EV_EVENTS, EV_CHANGED, EV_LEN };
 
 struct BlockScratch {
-    union {
-        struct {
-            uint32_t front[FCAP];
-            uint32_t list[LTOT];
-        };
-        struct {
-            uint32_t wlist[WARPS][WL_CAP];         // local index | status << 24 | attention << 28
-            uint32_t wfront[WARPS][WF_CAP];
-        };
-    };
+    uint32_t front[FCAP];                          // (front + list: the staging area of plan_cut)
+    uint32_t list[LTOT];                           // index relative to the block's base | status << 24 | attention << 28
     PushWarpScratch pw[WARPS];
     double pdf[64];
-    unsigned int n_front;
+    long long b_lo[2];                             // the batch being swept and the one after it (first piece, pieces)
+    int b_n[2];
+    unsigned int n_front, n_list;
     unsigned int hist[HIST_LEN], ev[EV_LEN], cnt[10], acc[8];
     bool last;
 };
@@ -603,199 +591,264 @@ __device__ __forceinline__ void fold_stats(unsigned long long* __restrict__ part
     __syncthreads();
 }
 
-// settle_round: ONE WARP settles <= 32 agents of its work list, one per lane -- record + mailbox loads issued together, B,
-// C, applying D, the ordered rules of E, F, G, tomorrow's snapshot byte and household flags.  The warp's counter
-// contributions are reduced with four REDUX + MATCH.ANY and added to the block's shared counters from distinct lanes.
-// Agents that are infectious tomorrow are appended to the warp's frontier wf[0 .. n_front).
-__device__ __forceinline__ void settle_round(const DevCtx& c, const int day, BlockScratch& sm, const uint32_t* entries, const int n,
-                                             const int64_t a_first, const bool any_nd, const DevCtx* cn, const FrontMap fmap,
-                                             uint32_t* wf, int& n_front)
+// ---------------------------------------------------------------------------------------------------------------
+// Where a block's pieces come from.
+//   static  (word == null): the pieces [next, end) of the view, in batches of <= 16 (k_agent; a stolen chunk in k_days).
+//   dynamic (k_days, the block's own run): `word` = (end << 32 | next) in UNIFIED piece indices ([replica][piece], local =
+//           unified - rep_off) lives in global memory.  The owner takes batches from the head with a compare-and-swap; blocks
+//           that finished their own run take batches from the same word (work stealing, see k_days).  Batch sizes follow
+//           guided self-scheduling -- a quarter of what is left, between 2 and 16 pieces -- so that whoever takes the last
+//           pieces of a run holds little work when everybody else is done.
+// ---------------------------------------------------------------------------------------------------------------
+struct WorkSrc {
+    unsigned long long* word;
+    int64_t rep_off;
+    int64_t next, end;                   // static mode: local piece indices
+};
+
+__device__ __forceinline__ unsigned long long pack_work(const int64_t next, const int64_t end)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    bool infected_today = false;
-    int infector = -1;
-    int64_t a = 0;
-    uint32_t ibn = 0, rel = 0;
-    uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
-    int kbin = -1;
-    const bool valid = lane < n;
-    uint32_t st = ST_PAD, att = 0;
-    Loaded L;
-    L.mb = -1;
-    if (valid) {
-        const uint32_t le = entries[lane];
-        rel = le & REL_MASK;
-        a = a_first + rel;
-        st = (le >> 24) & 0xFu;
-        att = (le >> 28) & 0x3u;
-        L = load_agent(c, a, st, att);
+    return ((unsigned long long)(uint32_t)end << 32) | (unsigned long long)(uint32_t)next;
+}
+
+// one thread: take the next batch; returns its first local piece and writes its size (0 = nothing left)
+__device__ __forceinline__ int64_t take_batch(WorkSrc& ws, int& n, const int cap = 16)
+{
+    if (!ws.word) {
+        const int64_t lo = ws.next;
+        n = (int)(ws.end - lo < cap ? ws.end - lo : cap);
+        if (n < 0) n = 0;
+        ws.next = lo + n;
+        return lo;
     }
-    // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim is issued
-    // as soon as the mailboxes are in, its answer is only needed when the events are written
-    const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
-    int ev_base = 0;
-    if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
-    if (valid) {
-        const Settled r = settle_agent(c, day, a, any_nd, st, att, L, infected_today, infector);
-        ibn = r.ibn;
-        kbin = r.k;
-        const uint32_t hi = hist_idx(r.x);
-        h0 = hi < 4 ? 1u << (8 * hi) : 0u;
-        h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
-        eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
-             ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
-        eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
-             ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
-    }
-    {
-        // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per non-zero
-        // counter from distinct lanes -- not 32 colliding atomics per counter
-        h0 = __reduce_add_sync(0xffffffffu, h0);
-        h1 = __reduce_add_sync(0xffffffffu, h1);
-        eA = __reduce_add_sync(0xffffffffu, eA);
-        eB = __reduce_add_sync(0xffffffffu, eB);
-        const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
-        const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
-        if (v) {
-            unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
-                              : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
-                              : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
-                              : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
-            atomicAdd(dst, v);
-        }
-        const unsigned km = __match_any_sync(0xffffffffu, kbin);
-        if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
-    }
-    if (evm) {
-        if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
-        if (c.ev) {
-            ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
-            if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
-        }
-    }
-    if (cn) {
-        // infectious tomorrow: queue the agent's row for the warp's push of day + 1
-        const bool f = (ibn & IB_INF) != 0;
-        const unsigned fm = __ballot_sync(0xffffffffu, f);
-        if (f) {
-            wf[n_front + __popc(fm & lt_mask)] = rel | (ibn << 24);
-            prefetch_l2(cn->tptr + fmap.at(rel));
-        }
-        n_front += __popc(fm);
+    unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(ws.word);
+    for (;;) {
+        const uint32_t nx = (uint32_t)w, en = (uint32_t)(w >> 32);
+        if (nx >= en) { n = 0; return 0; }
+        int g = (int)((en - nx + 3u) >> 2);
+        g = g < 2 ? 2 : (g > cap ? cap : g);
+        if ((uint32_t)g > en - nx) g = (int)(en - nx);
+        const unsigned long long seen = atomicCAS(ws.word, w, w + (unsigned long long)g);
+        if (seen == w) { n = g; return (int64_t)nx - ws.rep_off; }
+        w = seen;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// agent_body: the block owns the 128-agent pieces [p_first, p_last) of the view `c`; warp w takes pieces p_first + w,
-// p_first + w + 8, ... and runs on its own from there:
-//   sweep  : 4 agents per lane: one 32-bit load of the status bytes, one of the attention bytes (the next piece's words
-//            are requested before this piece is processed).  An agent to whom nothing can happen today -- susceptible
-//            or long recovered, attention byte 0 -- only feeds packed counters.  Every other agent is compacted
-//            (ballot + prefix popcount) into the warp's work list.
-//   settle : whenever the list holds 32 agents (and at the end) a settle_round() handles them, one per lane.
-//   push   : (cn != null) whenever the warp's frontier holds 32 rows (and at the end) push_group() pushes them along the
-//            transposed network for day + 1.
-// Divergent per-agent logic therefore costs instructions in proportion to the agents that need it, not to the
-// population, and no warp ever waits for another one of its block until the block's counters are published.
+// agent_body.  A block walks pieces of 128 agents in batches of <= 16 (two per warp), in two phases.
+//   sweep  : 4 agents per lane: one 32-bit load of the status bytes, one of the attention bytes.  An agent to whom nothing
+//            can happen today -- susceptible or long recovered, attention byte 0 -- only feeds packed counters.  Every other
+//            agent is compacted (ballot + prefix popcount) into the block's work list, which accumulates over batches.
+//   settle : once the list might not take another batch (or after the last batch) it is processed densely, one agent per
+//            thread whatever piece it came from: B, C, applying D, the ordered rules of E, F, G, tomorrow's snapshot byte and
+//            household flags; the next round's records are prefetched while a round is settled.  Agents that are infectious
+//            tomorrow join the block's frontier, which is pushed (cn != null) right after the settle.
+// Divergent per-agent logic therefore costs instructions in proportion to the agents that need it, not to the population,
+// and the work of a batch is spread evenly over the block's warps however unevenly the epidemic is spread over the pieces.
 // VARIANT 0 = k_agent (the last block to finish folds the statistics); 3 = k_days (one block folds after the grid barrier).
+// `a_base` = first agent the block may meet (rel indices of the list and the frontier are relative to it).
 // ---------------------------------------------------------------------------------------------------------------
 template <int VARIANT>
 __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn,
-                                           unsigned int (&push_cnt)[4], const int64_t p_first, const int64_t p_last)
+                                           unsigned int (&push_cnt)[4], WorkSrc ws, const int64_t a_base)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (tid < HIST_LEN) sm.hist[tid] = 0;
     if (tid < EV_LEN) sm.ev[tid] = 0;
     if (tid < 10) sm.cnt[tid] = 0;
+    if (tid == 0) {
+        sm.n_list = 0; sm.n_front = 0;
+        int n;
+        const int64_t lo = take_batch(ws, n);
+        sm.b_lo[0] = lo; sm.b_n[0] = n;
+    }
     if (cn && tid < 64) sm.pdf[tid] = c.pdf[tid];
     __syncthreads();
     const bool any_nd = c.df[DF_ANY_ND] != 0;
     // a recovered agent left the histogram (see k_validate_population for agents LOADED as recovered)
     const bool r_idle = c.recover >= HIST_LEN && c.hospital_recover >= HIST_LEN && day >= c.r_idle_day;
-    const int64_t a_first = p_first << 7;
-    const FrontMap fmap{c.lo - c.rt_lo + a_first};
-    uint32_t* const wl = sm.wlist[wid];
-    uint32_t* const wf = sm.wfront[wid];
-    int n_list = 0, n_front = 0;                  // warp-uniform
+    const FrontMap fmap{c.lo - c.rt_lo + a_base};
     uint32_t n_idle_s = 0, n_idle_r = 0;
+    constexpr int SLOTS = 2 * WARPS;              // pieces per batch
 
-    int64_t p = p_first + wid;
-    uint32_t sw = 0, aw = 0;
-    if (p < p_last) {
-        const int64_t a0 = (p << 7) + lane * 4;
-        sw = *reinterpret_cast<const uint32_t*>(c.status + a0);
-        aw = *reinterpret_cast<const uint32_t*>(c.att + a0);
+    // first batch's words
+    int64_t b_lo = sm.b_lo[0];
+    int b_n = sm.b_n[0];
+    uint32_t sw[2], aw[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int sl = r * WARPS + wid;
+        sw[r] = aw[r] = 0;
+        if (sl < b_n) {
+            const int64_t a0 = ((b_lo + sl) << 7) + lane * 4;
+            sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
+            aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
+        }
     }
-    for (; p < p_last; p += WARPS) {
-        // the next piece's words are requested before this piece is swept and settled
-        uint32_t sw_n = 0, aw_n = 0;
-        if (p + WARPS < p_last) {
-            const int64_t an = ((p + WARPS) << 7) + lane * 4;
-            sw_n = *reinterpret_cast<const uint32_t*>(c.status + an);
-            aw_n = *reinterpret_cast<const uint32_t*>(c.att + an);
+    for (int it = 0; b_n > 0; ++it) {
+        // the batch after this one is taken now (its words are requested before this batch is settled)
+        if (tid == 0) {
+            int n;
+            const int64_t lo = take_batch(ws, n);
+            sm.b_lo[(it + 1) & 1] = lo; sm.b_n[(it + 1) & 1] = n;
         }
         // ---- sweep ----
-        const uint32_t rel0 = (uint32_t)((p - p_first) << 7) | (lane * 4);
-        const int64_t a0 = a_first + rel0;
-        // four agents at once, byte-parallel: zb(x) has 0x80 in every byte of x that is zero (exact, no borrows)
-        auto zb = [](uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };
-        const uint32_t at0 = zb(aw);                                              // attention byte == 0
-        const uint32_t idle_s = zb(sw ^ (0x01010101u * ST_S)) & at0;              // susceptible, nothing pending
-        const uint32_t idle_r = r_idle ? zb(sw ^ (0x01010101u * ST_R)) & at0 : 0u;
-        n_idle_s += __popc(idle_s);
-        n_idle_r += __popc(idle_r);
-        const uint32_t wk = ~(idle_s | idle_r | zb(sw)) & 0x80808080u;            // 0x80 per agent that must be settled
-        const uint32_t work = ((wk >> 7) | (wk >> 14) | (wk >> 21) | (wk >> 28)) & 0xFu;
-        const int mine = __popc(work);
-        if (c.piece_work) {
-            // what this piece costs a block (ns, measured with DYS_TRACE): ~50 for the sweep and ~65 per agent that is
-            // settled (most of them are infectious and push a row tomorrow as well)
-            const uint32_t cost = __reduce_add_sync(0xffffffffu, 65u * mine);
-            if (lane == 0) c.piece_work[p] = 50u + cost;
-        }
-        if (aw) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
-        // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
-        if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
-        const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
-        if (any) {
-            int incl = mine;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+        for (int r = 0; r < 2; ++r) {
+            const int sl = r * WARPS + wid;
+            const bool in = sl < b_n;
+            const int64_t a0 = ((b_lo + sl) << 7) + lane * 4;
+            const uint32_t rel0 = (uint32_t)(a0 - a_base);
+            // four agents at once, byte-parallel: zb(x) has 0x80 in every byte of x that is zero (exact, no borrows)
+            auto zb = [](uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };
+            const uint32_t at0 = zb(aw[r]);                                           // attention byte == 0
+            const uint32_t idle_s = zb(sw[r] ^ (0x01010101u * ST_S)) & at0;           // susceptible, nothing pending
+            const uint32_t idle_r = r_idle ? zb(sw[r] ^ (0x01010101u * ST_R)) & at0 : 0u;
+            n_idle_s += __popc(idle_s);
+            n_idle_r += __popc(idle_r);
+            const uint32_t wk = ~(idle_s | idle_r | zb(sw[r])) & 0x80808080u;         // 0x80 per agent that must be settled
+            const uint32_t work = ((wk >> 7) | (wk >> 14) | (wk >> 21) | (wk >> 28)) & 0xFu;
+            const int mine = __popc(work);
+            if (c.piece_work) {
+                // what this piece costs a block (ns, measured with DYS_TRACE): ~50 for the sweep and ~65 per agent that is
+                // settled (most of them are infectious and push a row tomorrow as well)
+                const uint32_t cost = __reduce_add_sync(0xffffffffu, 65u * mine);
+                if (in && lane == 0) c.piece_work[b_lo + sl] = 50u + cost;
             }
-            int pos = n_list + incl - mine;
+            if (in) {
+                if (aw[r]) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
+                // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
+                if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
+            }
+            const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+            if (any) {
+                int incl = mine;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if ((work >> j) & 1u)
-                    wl[pos++] = (rel0 + j) | (((sw >> (8 * j)) & 0xFu) << 24) | (((aw >> (8 * j)) & 0x3u) << 28);
-            n_list += __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
-            // ---- settle (and push) whenever a full warp of work is queued ----
-            while (n_list >= 32) {
-                n_list -= 32;
-                settle_round(c, day, sm, wl + n_list, 32, a_first, any_nd, cn, fmap, wf, n_front);
-                __syncwarp();
-                if (n_front >= 32) {
-                    n_front -= 32;
-                    push_group<false>(*cn, day + 1, sm.pw[wid], sm.pdf, wf + n_front, 32, fmap, push_cnt);
-                    __syncwarp();
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int pos = 0;
+                if (lane == 31) pos = (int)atomicAdd(&sm.n_list, (unsigned)incl);
+                pos = __shfl_sync(0xffffffffu, pos, 31) + incl - mine;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((work >> j) & 1u) {
+                        sm.list[pos++] = (rel0 + j) | (((sw[r] >> (8 * j)) & 0xFu) << 24) | (((aw[r] >> (8 * j)) & 0x3u) << 28);
+                        prefetch_l2(c.rec + a0 + j);      // the record is needed when the list is settled
+                    }
+            }
+        }
+        __syncthreads();
+        // the next batch's words are requested before this batch is settled
+        const int64_t nb_lo = sm.b_lo[(it + 1) & 1];
+        const int nb_n = sm.b_n[(it + 1) & 1];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int sl = r * WARPS + wid;
+            sw[r] = aw[r] = 0;
+            if (sl < nb_n) {
+                const int64_t a0 = ((nb_lo + sl) << 7) + lane * 4;
+                sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
+                aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
+            }
+        }
+
+        // ---- settle: once the list might not take another batch, or after the last batch.  A block in a quiet part of
+        // the city sweeps all its pieces back to back and settles once ----
+        const int n_list = (int)sm.n_list;
+        const bool do_settle = n_list > LTOT - SLOTS * 128 || nb_n == 0;
+        if (do_settle) {
+            for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
+                const int k = k0 + tid;
+                bool infected_today = false;
+                int infector = -1;
+                int64_t a = 0;
+                uint32_t ibn = 0, rel = 0;
+                uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
+                int kbin = -1;
+                const bool valid = k < n_list;
+                uint32_t st = ST_PAD, att = 0;
+                Loaded L;
+                L.mb = -1;
+                if (valid) {
+                    const uint32_t le = sm.list[k];
+                    rel = le & REL_MASK;
+                    a = a_base + rel;
+                    st = (le >> 24) & 0xFu;
+                    att = (le >> 28) & 0x3u;
+                    L = load_agent(c, a, st, att);
+                }
+                // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim
+                // is issued as soon as the mailboxes are in, its answer is only needed when the events are written
+                const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
+                int ev_base = 0;
+                if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+                if (valid) {
+                    const Settled r = settle_agent(c, day, a, any_nd, st, att, L, infected_today, infector);
+                    ibn = r.ibn;
+                    kbin = r.k;
+                    const uint32_t hi = hist_idx(r.x);
+                    h0 = hi < 4 ? 1u << (8 * hi) : 0u;
+                    h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
+                    eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
+                         ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
+                    eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
+                         ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
+                }
+                {
+                    // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per
+                    // non-zero counter from distinct lanes -- not 32 colliding atomics per counter
+                    h0 = __reduce_add_sync(0xffffffffu, h0);
+                    h1 = __reduce_add_sync(0xffffffffu, h1);
+                    eA = __reduce_add_sync(0xffffffffu, eA);
+                    eB = __reduce_add_sync(0xffffffffu, eB);
+                    const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
+                    const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
+                    if (v) {
+                        unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
+                                          : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
+                                          : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
+                                          : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
+                        atomicAdd(dst, v);
+                    }
+                    const unsigned km = __match_any_sync(0xffffffffu, kbin);
+                    if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
+                }
+                if (evm) {
+                    if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
+                    if (c.ev) {
+                        ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
+                        if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+                    }
+                }
+                if (cn) {
+                    // infectious tomorrow: queue the agent's row for the block's push of day + 1
+                    const bool f = (ibn & IB_INF) != 0;
+                    const unsigned fm = __ballot_sync(0xffffffffu, f);
+                    if (fm) {
+                        int base = 0;
+                        if (lane == 0) base = (int)atomicAdd(&sm.n_front, (unsigned)__popc(fm));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (f) {
+                            sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
+                            prefetch_l2(cn->tptr + fmap.at(rel));
+                        }
+                    }
                 }
             }
+            __syncthreads();      // the work list is free; the frontier count is final
+            if (tid == 0) sm.n_list = 0;
+            if (cn && sm.n_front) {      // (a settle can add as many rows as the frontier holds: push after each)
+                push_frontier<false>(*cn, day + 1, sm, fmap, push_cnt);
+                __syncthreads();
+                if (tid == 0) sm.n_front = 0;
+            }
         }
-        sw = sw_n;
-        aw = aw_n;
-    }
-    if (n_list) {
-        settle_round(c, day, sm, wl, n_list, a_first, any_nd, cn, fmap, wf, n_front);
-        __syncwarp();
-    }
-    while (n_front > 0) {
-        const int nb = n_front < 32 ? n_front : 32;
-        n_front -= nb;
-        push_group<false>(*cn, day + 1, sm.pw[wid], sm.pdf, wf + n_front, nb, fmap, push_cnt);
-        __syncwarp();
+        __syncthreads();
+        b_lo = nb_lo;
+        b_n = nb_n;
     }
     {
         // idle agents: end-of-day status == day-start status
@@ -841,7 +894,7 @@ __global__ void __launch_bounds__(BLOCK) k_agent(const DevCtx c, const int day)
     const int64_t per = (n_pieces + gridDim.x - 1) / gridDim.x;
     const int64_t p0 = (int64_t)blockIdx.x * per < n_pieces ? (int64_t)blockIdx.x * per : n_pieces;
     const int64_t p1 = p0 + per < n_pieces ? p0 + per : n_pieces;
-    agent_body<0>(c, day, sm, nullptr, none, p0, p1);
+    agent_body<0>(c, day, sm, nullptr, none, WorkSrc{nullptr, 0, p0, p1}, p0 << 7);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -883,6 +936,7 @@ struct DayPlan {
     DayBuffers buf;
     int32_t want_sa, want_bc, want_ev;
     unsigned long long* trace;                      // developer tracing: [n_days][grid][8] globaltimer at phase boundaries, or null
+    unsigned long long* work;                       // [grid] the blocks' work words (see WorkSrc), or null: no stealing
     int32_t test_hang_block;                        // tests (DYS_TEST_HANG_BLOCK): this block leaves before the first barrier; -1 = none
 };
 
@@ -1041,6 +1095,8 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     const int n_work = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
     const int wb = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
     const int64_t n_pieces = c0.n_pad >> 7, n_pieces_all = n_pieces * n_rep;
+    // long runs are balanced dynamically (work words + stealing), short ones by the measured cut alone
+    const bool stealing = plan.work != nullptr && gridDim.x > 1 && n_pieces_all > 32ll * n_work;
     if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0);
     __syncthreads();
     if ((int)blockIdx.x == plan.test_hang_block) return;      // (tests: the others must time out at the barrier, not hang)
@@ -1077,8 +1133,10 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         if (cn)
             for (int r = 0; r < n_rep; ++r) push_clear_duties(*cn, r);
         {
-            // the block's run of pieces in the unified piece space [replica][piece]: today's cut of equal measured work,
-            // or an equal share; one agent_body per replica the run touches
+            // The block's run of pieces in the unified piece space [replica][piece] -- today's cut of equal measured work,
+            // or an equal share -- one agent_body per replica the run touches.  Long runs are consumed through the
+            // block's work word, from which blocks that are done take batches as well (work stealing): the epidemic is
+            // never evenly spread, and no cost model predicts an SM's speed.
             int64_t P0, P1;
             if (wb < 0 || wb >= n_work) P0 = P1 = 0;
             else if (c.cut_first >= 0) { P0 = c.cut_first; P1 = c.cut_last; }
@@ -1087,17 +1145,75 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 P0 = wb * per < n_pieces_all ? wb * per : n_pieces_all;
                 P1 = P0 + per < n_pieces_all ? P0 + per : n_pieces_all;
             }
-            for (int64_t P = P0; P < P1;) {
-                const int r = (int)(P / n_pieces);
-                const int64_t p0 = P - (int64_t)r * n_pieces;
-                const int64_t p1 = P1 - (int64_t)r * n_pieces < n_pieces ? P1 - (int64_t)r * n_pieces : n_pieces;
+            // (one loop, one call site of agent_body: first the segments of the own run, then stolen batches)
+            int64_t P = P0;
+            bool announced = false;
+            const unsigned int all_done = (unsigned)(k + 1) * (unsigned)n_work;
+            for (int round = 0;;) {
+                int r;
+                WorkSrc ws;
+                int64_t a_base;
+                if (P < P1) {
+                    r = (int)(P / n_pieces);
+                    const int64_t p0 = P - (int64_t)r * n_pieces;
+                    const int64_t p1 = P1 - (int64_t)r * n_pieces < n_pieces ? P1 - (int64_t)r * n_pieces : n_pieces;
+                    a_base = p0 << 7;
+                    if (stealing && p1 - p0 > 32) {
+                        if (threadIdx.x == 0) atomicExch(&plan.work[wb], pack_work(P, P + (p1 - p0)));
+                        ws = WorkSrc{&plan.work[wb], (int64_t)r * n_pieces, 0, 0};
+                    } else {
+                        ws = WorkSrc{nullptr, 0, p0, p1};
+                    }
+                    P += p1 - p0;
+                } else {
+                    if (!stealing || wb < 0 || wb >= n_work) break;
+                    // done with the own run: help whoever is not.  Warp 0 reads 32 blocks' work words at a time and takes a
+                    // batch from the one with the most pieces left; when every block has exhausted its own run there is
+                    // nothing left to take.
+                    if (!announced) {
+                        announced = true;
+                        if (threadIdx.x == 0) { __threadfence(); atomicAdd(barrier_counter + 2, 1u); }
+                    }
+                    if (threadIdx.x < 32) {
+                        const int lane = threadIdx.x;
+                        const int v = (int)(((long long)wb + 1 + lane + 32ll * round) % n_work);
+                        const unsigned long long w = __ldcg(plan.work + v);
+                        const uint32_t nx = (uint32_t)w, en = (uint32_t)(w >> 32);
+                        const uint32_t rem = (v != wb && en > nx) ? en - nx : 0u;
+                        const uint32_t best = __reduce_max_sync(0xffffffffu, rem);
+                        const unsigned who = __ballot_sync(0xffffffffu, rem == best && best > 0u);
+                        if (best > 0u && lane == __ffs(who) - 1) {
+                            WorkSrc vs{plan.work + v, 0, 0, 0};
+                            int n = 0;
+                            sm.b_lo[0] = take_batch(vs, n);
+                            sm.b_n[0] = n;
+                        }
+                        if (lane == 0) {
+                            if (best == 0u) sm.b_n[0] = 0;
+                            sm.b_n[1] = (int)(__ldcg(barrier_counter + 2) >= all_done);
+                        }
+                    }
+                    ++round;
+                    __syncthreads();
+                    const int n = sm.b_n[0];
+                    const int64_t Pst = sm.b_lo[0];
+                    const bool finished = sm.b_n[1] != 0;
+                    __syncthreads();
+                    if (n == 0) {
+                        if (finished) break;
+                        continue;
+                    }
+                    r = (int)(Pst / n_pieces);
+                    const int64_t p0 = Pst - (int64_t)r * n_pieces;
+                    a_base = p0 << 7;
+                    ws = WorkSrc{nullptr, 0, p0, p0 + n};
+                }
                 unsigned int push_cnt[4] = {0, 0, 0, 0};
                 const DevCtx& cr = replica_view(c, 0, r);
                 const DevCtx* cnr = cn ? &replica_view(*cn, 1, r) : nullptr;
-                agent_body<3>(cr, day, sm, cnr, push_cnt, p0, p1);
+                agent_body<3>(cr, day, sm, cnr, push_cnt, ws, a_base);
                 if (cnr) { __syncthreads(); publish_push_counters(*cnr, sm, push_cnt); }
                 __syncthreads();
-                P += p1 - p0;
             }
         }
         stamp(3);
@@ -1110,7 +1226,10 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
             // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a
             // quiet day.  The cut made after day d is the one of day d + 3.)
-            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
+            // (with more than two staging chunks of pieces the equal split + stealing balances well enough, and planning
+            // would make this block late for the next barrier)
+            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0 && n_pieces_all <= 2 * (FCAP + LTOT))
+                plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
             stamp(11);
         }
         const int n_pub = PUBLISH_BLOCKS < n_work ? PUBLISH_BLOCKS : n_work;

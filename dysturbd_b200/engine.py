@@ -64,7 +64,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach",
-           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes"]
+           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_R_rows"]
 
 _lib = None
 
@@ -116,6 +116,7 @@ def load_library():
     lib.dys_abort.argtypes = [vp]
     lib.dys_h2d_bytes.argtypes = [vp]
     lib.dys_h2d_bytes.restype = i64
+    lib.dys_compute_R_rows.argtypes = [vp, i32, i64, i64, vp, i32, vp]
     _lib = lib
     return lib
 
@@ -139,6 +140,22 @@ def _ptr(x, dtype=None, n=None):
             raise ValueError("expected %d elements, got %d" % (n, x.numel()))
         return x.data_ptr(), x
     raise TypeError("numpy array or torch tensor expected")
+
+
+def compute_R_rows(hist, pdf, recover, out=None):
+    """compute_R (contagious3.py:29-42) for every row of an int32 / int64 [rows, >=21] histogram (host memory), by the
+    library's C helper: the reference's order of float operations, bit for bit"""
+    lib = load_library()
+    hist = np.ascontiguousarray(hist)
+    if hist.ndim == 1:
+        hist = hist[None, :]
+    if out is None:
+        out = np.empty(hist.shape[0], dtype=np.float64)
+    rc = lib.dys_compute_R_rows(hist.ctypes.data, hist.dtype.itemsize, hist.shape[0], hist.shape[1], pdf.ctypes.data, int(recover),
+                                out.ctypes.data)
+    if rc != 0:
+        raise DysError(rc, "dys_compute_R_rows: bad argument")
+    return out
 
 
 def keyed_uniform_device(seed, day, stream, a, b, device=0):

@@ -84,7 +84,8 @@ class EpidemicModel:
     MAX_WINDOW = 7
 
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
-                 device=0, choice_seed=None, backend=None, population=None, compact=False):
+                 device=0, choice_seed=None, backend=None, population=None, compact=False, reduce_stats=None,
+                 upload_flags=True, keep_raw=False):
         self.params = params or EpiParams()
         self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob,
                                                                    diagnosis=self.params.diagnosis)
@@ -95,14 +96,27 @@ class EpidemicModel:
         # (infected, infector) area indices [n_events, 2]).  The reference's schema costs O(S^2 + B) Python objects per
         # day -- fine for its 19 areas, 50 ms per day for a million agents.  'Stats' is always the reference's dict.
         self.compact = bool(compact)
+        # sharded populations (one EpidemicModel per rank over a ShardedEngine): `reduce_stats` sums a [days, 64] block of
+        # stats over the ranks; R, Known R and the lockdown decision then use the GLOBAL counts while the per-area and
+        # per-building outputs stay local to the rank's areas / buildings
+        self._reduce = reduce_stats
+        self._gstats = {}
+        self._upload = bool(upload_flags)
+        # keep_raw: every day's raw 64-integer stats block (work counters included) and the flag vector it ran under
+        self.raw_stats = {} if keep_raw else None
+        self.flags_log = {} if keep_raw else None
         self.day = 0                 # next day to consume
         self.outputs = {'Results': {'Stats': {}, 'Buildings': {}, 'SAs': {}, 'IO_mat': {}}}
         self._choice = np.random.RandomState(choice_seed).choice
         p = self.pop
         self._bld_pop = np.bincount(p.home, minlength=p.B)
         self._inhabited = np.nonzero(self._bld_pop > 0)[0]
+        self._b0 = p.bld_range[0] if p.bld_range else 0          # outputs cover the owned buildings / areas only
+        self._s0, self._s1 = p.sa_range if p.sa_range else (0, p.S)
         self._pdf = [float(x) for x in self.params.pdf]
         self._active = int(np.isin(p.status, (4, 7, 8, 10)).sum())
+        if self._reduce is not None:
+            self._active = int(self._reduce(np.array([[self._active] + [0] * 63], dtype=np.int64))[0, 0])
         self._R = {}                 # day -> R of that day (contagious3.py:281)
         self._flags = {0: self.pop.open.astype(float)}      # day -> build[:,10] in force on that day
         self._queued = 0             # next day to queue
@@ -141,8 +155,16 @@ class EpidemicModel:
     def _queue(self, n):
         first = self._queued
         flags = np.stack([self._flags_for(first + k) for k in range(n)]).astype(np.uint8)
+        if self.flags_log is not None:
+            for k in range(n):
+                self.flags_log[first + k] = flags[k]
         if hasattr(self.sim, "step_many"):
-            self.sim.step_many(first, n, flags)
+            # the day's building flags are this path's only per-day host input (contagious3.py:384 re-assigns build[:,10]
+            # every day); upload_flags=False offers them only when they changed
+            changed = self._upload or any(not np.array_equal(flags[k], self._last_flags) for k in range(n)) \
+                if hasattr(self, "_last_flags") else True
+            self.sim.step_many(first, n, flags if changed else None)
+            self._last_flags = flags[-1]
         else:                                    # tests drive this loop with the CPU oracle as backend
             assert n == 1
             self.sim.set_open(flags[0])
@@ -156,19 +178,27 @@ class EpidemicModel:
         if hasattr(sim, "outputs"):              # the CUDA engine: one pinned block per day, no further transfers
             o = sim.outputs(day)
             st, sa_hist, bc = o["stats"], o["sa_hist"], o["building_counts"]
+            if self._reduce is not None:         # sharded: the counts behind R / Stats are sums over the ranks, one
+                if day not in self._gstats:      # all-reduce per window of queued days
+                    days = list(range(day, min(self._queued, day + self.window)))
+                    g = self._reduce(np.stack([sim.outputs(d)["stats"] for d in days]))
+                    self._gstats = dict(zip(days, g))
+                st = self._gstats.pop(day)
             ev = o["events"]
             order = np.argsort(ev[:, 0], kind="stable")
             ev_a, ev_s = ev[order, 0], ev[order, 1]
         else:
             st, sa_hist, bc = sim.stats(day), sim.sa_hist(day), sim.building_counts(day)
             ev_a, ev_s = sim.events(day)
+        if self.raw_stats is not None:
+            self.raw_stats[day] = np.array(st)
         hist = st[HIST0:HIST0 + HIST_LEN]
         R = compute_R_from_hist(hist, self._pdf, prm.recover)
         self._R[day] = R
         vis_R = self._known_R(day)
         if self.compact:
-            R_sa = compute_R_rows(np.asarray(sa_hist)[:p.S], self._pdf, prm.recover)
-            res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - prm.diagnosis]['R'] if day > prm.diagnosis else np.zeros(p.S)}
+            R_sa = compute_R_rows(np.asarray(sa_hist)[:self._s1 - self._s0], self._pdf, prm.recover)
+            res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - prm.diagnosis]['R'] if day > prm.diagnosis else np.zeros(len(R_sa))}
         else:
             sas = [float(x) for x in p.sa_ids]
             res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
@@ -183,12 +213,15 @@ class EpidemicModel:
             S['Total infected'] = S['Active infected']                                          # :347-348
         else:
             S['Total infected'] = res['Stats'][day - 1]['Total infected'] + new_infections
-        S['Susceptible'] = p.N - S['Total infected']
+        S['Susceptible'] = p.N_glob - S['Total infected']
         res['Stats'][day] = S
         if self.compact:
-            cnt = np.asarray(bc)[self._inhabited].astype(np.float64)
+            cnt = np.asarray(bc)[self._inhabited - self._b0].astype(np.float64)
             res['Buildings'][day] = np.stack([cnt, cnt / self._bld_pop[self._inhabited]], axis=1)
-            res['IO_mat'][day] = np.stack([p.sa[ev_a], p.sa[ev_s]], axis=1) if len(ev_a) else np.zeros((0, 2), dtype=p.sa.dtype)
+            if self._reduce is None:
+                res['IO_mat'][day] = np.stack([p.sa[ev_a], p.sa[ev_s]], axis=1) if len(ev_a) else np.zeros((0, 2), dtype=p.sa.dtype)
+            else:                                # sharded: the infector may live on another rank; keep agent indices
+                res['IO_mat'][day] = np.stack([ev_a, ev_s], axis=1)
         else:
             res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
             mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                   # :356-366
@@ -251,7 +284,9 @@ class EpidemicModel:
         self._flags_for(self.day)        # phase H for tomorrow, in the reference's order of np.random.choice calls
         return S
 
-    def run(self, max_days=None):
+    def run(self, max_days=None, finalize=True):
+        """the reference's `while` (contagious3.py:176); finalize=False skips the once-per-run 'Infections chain' read-back
+        (contagious3.py:389) so that a caller can continue the run"""
         batched = hasattr(self.sim, "step_many")
         w = self.window if batched else 1
         limit = (lambda d: max_days is None or d < max_days)
@@ -269,6 +304,8 @@ class EpidemicModel:
         # left, so columns 16 and 21 are final), and their outputs are dropped
         if hasattr(self.sim, "sync"):
             self.sim.sync()
+        if not finalize:
+            return self.outputs
         st = self.sim.state()
         src_id = np.where(st['src'] >= 0, self.pop.agent_ids[np.maximum(st['src'], 0)], 0.0)
         self.outputs['Results']['Infections chain'] = np.stack(

@@ -103,6 +103,10 @@ class ShardedEngine:
     def outputs(self, day):
         return self.sim.outputs(day)
 
+    def sync(self):
+        if hasattr(self.sim, "sync"):
+            self.sim.sync()
+
     def local_stats(self, day):
         return self.sim.stats(day)
 

@@ -211,6 +211,11 @@ typedef enum { DYS_BUF_STATUS = 0, DYS_BUF_INFECTIOUS = 1, DYS_BUF_STATS = 2, DY
 int dys_device_buffer(dys_handle* h, int which, void** ptr, int64_t* bytes);
 int dys_cuda_stream(dys_handle* h, void** stream);
 int64_t dys_device_bytes(const dys_handle* h);
+/* compute_R (contagious3.py:29-42) on `rows` histograms held in HOST memory (int32 or int64 elements, DYS_HIST_LEN used
+ * per row, rows `row_stride` elements apart): out[r] = hist[r][0] / sum_{i=1}^{recover-1} hist[r][i] * pdf[i], 0 if the sum
+ * is 0 -- the reference's order of float operations, so the results compare with ==. */
+int dys_compute_R_rows(const void* hist, int32_t elem_bytes, int64_t rows, int64_t row_stride, const double* pdf,
+                       int32_t recover, double* out);
 /* bytes of open flags uploaded host -> device by dys_step_many so far (benchmark accounting) */
 int64_t dys_h2d_bytes(const dys_handle* h);
 /* Peer mode (sharded populations on one NVLink/NVSwitch node): every rank exports CUDA IPC handles of its snapshot

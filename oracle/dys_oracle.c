@@ -4,7 +4,8 @@
  * legs may load this library; the product path (dysturbd_b200/) never does and has no CPU fallback.
  *
  * What it restates: /root/reference/contagious3.py:176-366 (the per-day `while` body), phase by phase, on a
- * structure-of-arrays state instead of the reference's agents[N,29] float64 matrix, and with the dense
+ * structure-of-arrays state instead of the reference's agents[N,29] float64 matrix, every per-agent loop an OpenMP
+ * loop (so that the CPU baseline of bench.py really uses the host cores it reports), and with the dense
  * U x I pair matrices of :230-248 replaced by a walk over the non-zeros of interaction_prob (a pair with
  * interaction_prob == 0 has P == 0 and `0 > u` is never true, so the sparse walk is exact).
  * Parity status: PINNED against the literal reference loop run under identical injected draws
@@ -162,7 +163,9 @@ int orc_day(orc_ctx* c, int32_t day)
     memset(c->stats, 0, 64 * sizeof(int64_t));
     int64_t n_adm = 0, n_death = 0, n_sus0 = 0, n_inf0 = 0;
 
-    /* phases B and C (contagious3.py:205-227), both on the day-start snapshot */
+    /* phases B and C (contagious3.py:205-227), both on the day-start snapshot.  (Every loop over agents is an OpenMP loop:
+     * agents are independent inside a phase, so the thread count changes nothing but the time.) */
+#pragma omp parallel for schedule(static) reduction(+ : n_adm, n_death, n_sus0, n_inf0)
     for (int64_t a = 0; a < N; ++a) {
         uint8_t s = st0[a];
         int inf0 = (s == ST_I || s == ST_QI || s == ST_D);
@@ -226,6 +229,7 @@ int orc_day(orc_ctx* c, int32_t day)
     }
 
     /* phase E (contagious3.py:250-259), rule by rule; day counters derived as day - start */
+#pragma omp parallel for schedule(static)
     for (int64_t a = 0; a < N; ++a) {
         uint8_t s = c->status[a];
         int n_inf = day - c->t_inf[a], n_q = day - c->t_q[a];
@@ -243,15 +247,21 @@ int orc_day(orc_ctx* c, int32_t day)
     int64_t n_diag = 0;
     uint8_t* hh_hit = (uint8_t*)calloc(c->H > 0 ? c->H : 1, 1);
     uint8_t* hh_quirk = (uint8_t*)calloc(c->H > 0 ? c->H : 1, 1);
+#pragma omp parallel for schedule(static) reduction(+ : n_diag)
     for (int64_t a = 0; a < N; ++a) {
         if (c->status[a] == ST_D && day - c->t_inf[a] == c->diagnosis) {
             ++n_diag;
+#pragma omp atomic write
             hh_hit[c->hh[a]] = 1;
             if (c->trig_ptr)
-                for (int64_t t = c->trig_ptr[a]; t < c->trig_ptr[a + 1]; ++t) hh_quirk[c->trig_hh[t]] = 1;
+                for (int64_t t = c->trig_ptr[a]; t < c->trig_ptr[a + 1]; ++t) {
+#pragma omp atomic write
+                    hh_quirk[c->trig_hh[t]] = 1;
+                }
         }
     }
     if (n_diag > 0) {
+#pragma omp parallel for schedule(static)
         for (int64_t a = 0; a < N; ++a) {
             int32_t h = c->hh[a];
             uint8_t s = c->status[a];
@@ -269,31 +279,69 @@ int orc_day(orc_ctx* c, int32_t day)
     int64_t* S = c->stats;
     if (c->sa_hist) memset(c->sa_hist, 0, sizeof(int32_t) * 21 * c->S);
     if (c->bld_infected) memset(c->bld_infected, 0, sizeof(int32_t) * c->B);
-    int64_t nev = 0;
-    for (int64_t a = 0; a < N; ++a) {
-        uint8_t s = c->status[a];
-        int ever = !(s == ST_S || s == ST_QH);
-        S[O_ACTIVE] += (s == ST_I || s == ST_QI || s == ST_D || s == ST_H);
-        S[O_DAILY_INF] += (ever && c->t_inf[a] == day);
-        S[O_RECOVERED] += (s == ST_R);
-        S[O_QUARANTINED] += (s == ST_QH || s == ST_QI || s == ST_D);
-        S[O_DAILY_QUAR] += ((s == ST_QH || s == ST_QI || s == ST_D) && c->t_q[a] == day);
-        S[O_HOSP] += (s == ST_H);
-        S[O_DEAD] += (s == ST_X);
-        S[O_EVER_INFECTED] += ever;
-        if (ever) {
-            int k = day - c->t_inf[a];
-            if (k >= 0 && k <= 20) {
-                S[32 + k] += 1;
-                if (c->sa_hist) c->sa_hist[c->sa[a] * 21 + k] += 1;
+    int64_t g_active = 0, g_dinf = 0, g_rec = 0, g_quar = 0, g_dquar = 0, g_hosp = 0, g_dead = 0, g_ever = 0;
+    int64_t hist[21];
+    memset(hist, 0, sizeof hist);
+    /* today's infections are listed in ascending agent order: count per chunk, prefix, fill */
+    enum { CHUNK = 1 << 15 };
+    const int64_t n_chunks = (N + CHUNK - 1) / CHUNK;
+    int64_t* chunk_ev = (int64_t*)calloc((size_t)n_chunks + 1, sizeof(int64_t));
+#pragma omp parallel for schedule(static) reduction(+ : g_active, g_dinf, g_rec, g_quar, g_dquar, g_hosp, g_dead, g_ever, hist[:21])
+    for (int64_t ch = 0; ch < n_chunks; ++ch) {
+        int64_t nev_c = 0;
+        const int64_t a1 = (ch + 1) * CHUNK < N ? (ch + 1) * CHUNK : N;
+        for (int64_t a = ch * CHUNK; a < a1; ++a) {
+            uint8_t s = c->status[a];
+            int ever = !(s == ST_S || s == ST_QH);
+            g_active += (s == ST_I || s == ST_QI || s == ST_D || s == ST_H);
+            g_dinf += (ever && c->t_inf[a] == day);
+            g_rec += (s == ST_R);
+            g_quar += (s == ST_QH || s == ST_QI || s == ST_D);
+            g_dquar += ((s == ST_QH || s == ST_QI || s == ST_D) && c->t_q[a] == day);
+            g_hosp += (s == ST_H);
+            g_dead += (s == ST_X);
+            g_ever += ever;
+            if (ever) {
+                int k = day - c->t_inf[a];
+                if (k >= 0 && k <= 20) {
+                    hist[k] += 1;
+                    if (c->sa_hist) {
+#pragma omp atomic
+                        c->sa_hist[c->sa[a] * 21 + k] += 1;
+                    }
+                }
+            }
+            if (c->bld_infected && (s == ST_I || s == ST_QI || s == ST_D)) {
+#pragma omp atomic
+                c->bld_infected[c->home[a]] += 1;
+            }
+            if (ever && c->t_inf[a] == day && st0[a] != s && (st0[a] == ST_S || st0[a] == ST_QH)) ++nev_c;
+        }
+        chunk_ev[ch + 1] = nev_c;
+    }
+    for (int64_t ch = 0; ch < n_chunks; ++ch) chunk_ev[ch + 1] += chunk_ev[ch];
+    const int64_t nev = chunk_ev[n_chunks];
+    if (c->ev_agent && nev > 0) {
+#pragma omp parallel for schedule(static)
+        for (int64_t ch = 0; ch < n_chunks; ++ch) {
+            int64_t k = chunk_ev[ch];
+            if (chunk_ev[ch + 1] == k) continue;
+            const int64_t a1 = (ch + 1) * CHUNK < N ? (ch + 1) * CHUNK : N;
+            for (int64_t a = ch * CHUNK; a < a1; ++a) {
+                uint8_t s = c->status[a];
+                int ever = !(s == ST_S || s == ST_QH);
+                if (ever && c->t_inf[a] == day && st0[a] != s && (st0[a] == ST_S || st0[a] == ST_QH)) {
+                    c->ev_agent[k] = (int32_t)(c->lo + a);
+                    c->ev_src[k] = c->src[a];
+                    ++k;
+                }
             }
         }
-        if (c->bld_infected && (s == ST_I || s == ST_QI || s == ST_D)) c->bld_infected[c->home[a]] += 1;
-        if (ever && c->t_inf[a] == day && st0[a] != s && (st0[a] == ST_S || st0[a] == ST_QH)) {
-            if (c->ev_agent) { c->ev_agent[nev] = (int32_t)(c->lo + a); c->ev_src[nev] = c->src[a]; }
-            ++nev;
-        }
     }
+    free(chunk_ev);
+    S[O_ACTIVE] = g_active; S[O_DAILY_INF] = g_dinf; S[O_RECOVERED] = g_rec; S[O_QUARANTINED] = g_quar;
+    S[O_DAILY_QUAR] = g_dquar; S[O_HOSP] = g_hosp; S[O_DEAD] = g_dead; S[O_EVER_INFECTED] = g_ever;
+    for (int k = 0; k < 21; ++k) S[32 + k] = hist[k];
     S[O_DAILY_HOSP] = n_adm;
     S[O_DAILY_DEATHS] = n_death;
     S[O_NEW_DIAG] = n_diag;
