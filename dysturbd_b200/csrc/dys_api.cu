@@ -41,6 +41,7 @@ struct dys_handle {
     int sel = -1;                                   // dys_select_replica
     std::vector<RepParam> rep;                      // host copy of the per-replica parameters
     RepParam* d_rep = nullptr;
+    LockdownPlan ld{};                              // device lockdown policy (dys_set_lockdown)
     volatile int32_t* h_abort = nullptr;            // pinned + mapped: the kernels poll it in their spin loops
     int64_t h2d_bytes = 0;                          // flag bytes uploaded so far (bench accounting)
     unsigned int* d_barrier = nullptr;              // grid barrier counter of k_days, publish ticket, blocks done with their run
@@ -70,14 +71,15 @@ struct dys_handle {
     int32_t ib_day = -1;             // the day whose day-start snapshot bytes are complete in buffer ib_day & 1
     uint8_t* d_ib = nullptr;         // [2][ib_stride] snapshot bytes of all agents, double buffered by day parity
     int64_t ib_stride = 0;
-    int32_t* d_peer_flags = nullptr; // [8] peer mode: flags[r] = last day rank r's bytes are complete for (on this GPU)
+    unsigned long long* d_arrive = nullptr;   // [8] peer mode: units (pieces + tokens) received from rank r on this GPU
+    unsigned long long pub_epoch = 0;         // publications of snapshot bytes so far (all ranks step the same days)
     uint8_t* peer_ib[8] = {};        // peer mode: every rank's d_ib (own included)
-    int32_t* peer_flags[8] = {};
+    unsigned long long* peer_arrive[8] = {};
     int n_peers = 1;
     int64_t hh_lo = 0, bld_lo = 0, area_lo = 0;   // first owned household / building / area
     int64_t peer_halo[8][2] = {};    // every rank's halo [lo, hi) in global agents
     int64_t peer_own[8][2] = {};     // every rank's owned range
-    uint32_t wait_mask = 0, signal_mask = 0;
+    uint32_t partner_mask = 0;       // ranks this rank exchanges bytes with (either direction)
     int push_grid = 0;               // persistent grid of k_push
     int last_slot = 0;
     bool no_fuse = false;            // DYS_NO_FUSE=1 in the environment: dys_step_many launches two kernels a day
@@ -235,7 +237,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     h->ib_stride = round_up(c.n_glob, 1024) + 1024;
     c.ib_stride = h->ib_stride;
     A(dev_alloc(h, &h->d_ib, 2 * h->ib_stride * R));
-    A(dev_alloc(h, &h->d_peer_flags, 8));
+    A(dev_alloc(h, &h->d_arrive, 8));
     A(dev_alloc(h, (uint8_t**)&c.open, c.B));
     for (int k = 0; k < 2; ++k) {
         A(dev_alloc(h, &h->buf.att[k], (c.n_pad + 16) * R));
@@ -249,8 +251,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     A(dev_alloc(h, (int64_t**)&c.hh_ptr, c.H + 1)); A(dev_alloc(h, (int32_t**)&c.hh_mem, c.n_pad));
     A(dev_alloc(h, &h->d_rep, R));
     c.rep_params = R > 1 ? h->d_rep : nullptr;
-    c.n_peers = 1; c.rank = p.rank; c.flag_wait = h->d_peer_flags;
-    for (int r = 0; r < 8; ++r) c.flag_signal[r] = h->d_peer_flags ? h->d_peer_flags + p.rank : nullptr;
+    c.n_peers = 1; c.rank = p.rank; c.arrive = h->d_arrive; c.n_wr = 1;
     A(dev_alloc(h, &d_pdf, DYS_PDF_LEN));
     A(dev_alloc(h, &h->d_bad, 4));
     {   // one output block per ring slot and replica: everything a day produces leaves the device in a single copy
@@ -354,6 +355,22 @@ extern "C" int dys_destroy(dys_handle* h)
     return DYS_OK;
 }
 
+// device lockdown policy at the start of a run: day 0 runs under the loaded flags, days 1 and 2 are decided from Known R = 0
+// (all open, contagious3.py:57-60 with vR = 0); no R history yet
+static int init_lockdown(dys_handle* h)
+{
+    DevCtx& c = h->c;
+    const size_t R = (size_t)h->R, B = (size_t)c.B;
+    CK(h, cudaMemsetAsync(h->ld.flags, 1, 4 * R * B, h->stream));
+    for (size_t r = 0; r < R; ++r) CK(h, cudaMemcpyAsync(h->ld.flags + r * B, c.open, B, cudaMemcpyDeviceToDevice, h->stream));
+    std::vector<int32_t> nc(4 * R, 0);
+    for (size_t r = 0; r < R; ++r) nc[r] = c.n_closed;
+    CK(h, cudaMemcpyAsync(h->ld.n_closed, nc.data(), sizeof(int32_t) * nc.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemsetAsync(h->ld.r_hist, 0, sizeof(double) * 16 * R, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return DYS_OK;
+}
+
 // state was (re)loaded: the snapshot, attention bytes, mailboxes, flag rings, partial sums and the cut start clean
 static int reset_day_scratch(dys_handle* h)
 {
@@ -379,9 +396,11 @@ static int reset_day_scratch(dys_handle* h)
         }
         CK(h, cudaStreamSynchronize(h->stream));      // `cut` leaves scope
     }
+    if (h->ld.mode) { int rl = init_lockdown(h); if (rl != DYS_OK) return rl; }
     h->ib_day = -1;
     h->begun = false;
-    CK(h, cudaMemsetAsync(h->d_peer_flags, 0xFF, sizeof(int32_t) * 8, h->stream));   // -1: nothing complete yet
+    CK(h, cudaMemsetAsync(h->d_arrive, 0, sizeof(unsigned long long) * 8, h->stream));   // (peer mode: the caller barriers across ranks before stepping)
+    h->pub_epoch = 0;
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaStreamSynchronize(h->copy_stream));
     CK(h, cudaStreamSynchronize(h->up_stream));
@@ -574,6 +593,38 @@ extern "C" int dys_select_replica(dys_handle* h, int32_t r)
     return DYS_OK;
 }
 
+extern "C" int dys_set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* bld_class)
+{
+    if (!h) return DYS_ERR_INVALID_ARG;
+    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_set_lockdown before dys_load_population");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (scenario == 0) { h->ld.mode = 0; return DYS_OK; }
+    if (!bld_class) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_lockdown: null bld_class");
+    if (scenario & ~(SC_GRADUAL | SC_ALL | SC_EDU | SC_REL)) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_lockdown: unknown scenario bits");
+    if (h->p.world > 1) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy needs the GLOBAL R: not in sharded mode (use the host policy)");
+    if (h->c.diagnosis < 2 || h->c.diagnosis > 12) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy needs 2 <= diagnosis <= 12");
+    if (h->steps != 0 && h->last_day >= 0) return fail(h, DYS_ERR_STATE, "dys_set_lockdown after the run has started: reload the state first");
+    if (h->days_grid < 2) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy needs the cooperative k_days launch");
+    DevCtx& c = h->c;
+    const int64_t R = h->R;
+    int rc = DYS_OK;
+    if (!h->ld.flags) {
+        uint8_t* cls = nullptr;
+        rc = dev_alloc(h, &cls, c.B);
+        if (rc == DYS_OK) rc = dev_alloc(h, &h->ld.flags, 4 * R * c.B);
+        if (rc == DYS_OK) rc = dev_alloc(h, &h->ld.n_closed, 4 * R);
+        if (rc == DYS_OK) rc = dev_alloc(h, &h->ld.r_hist, 16 * R);
+        if (rc != DYS_OK) return rc;
+        h->ld.bld_class = cls;
+    }
+    rc = copy_in(h, (void*)h->ld.bld_class, bld_class, (size_t)c.B);
+    if (rc != DYS_OK) return rc;
+    h->ld.scen = scenario;
+    h->ld.mode = 1;
+    return init_lockdown(h);
+}
+
 extern "C" int dys_abort(dys_handle* h)
 {
     if (!h || !h->h_abort) return DYS_ERR_INVALID_ARG;
@@ -723,27 +774,44 @@ extern "C" int dys_set_open(dys_handle* h, const uint8_t* open_flags)
 
 // the day-independent peer fields of the context: who waits for whom, and which part of the owned slice each write
 // target needs (only the bytes inside that rank's halo travel)
+static inline int64_t shard_pad(const int64_t lo, const int64_t hi) { return lo + round_up(hi - lo, 1024); }
+
+// global agents of rank `owner`'s slice (padded to its 1024 granule) that lie in rank `reader`'s halo, in whole pieces
+static void slice_in_halo(const dys_handle* h, int owner, int reader, int64_t& lo, int64_t& n)
+{
+    const int64_t o0 = h->peer_own[owner][0], o1 = shard_pad(h->peer_own[owner][0], h->peer_own[owner][1]);
+    int64_t a = o0 > h->peer_halo[reader][0] ? o0 : h->peer_halo[reader][0];
+    int64_t b = o1 < h->peer_halo[reader][1] ? o1 : h->peer_halo[reader][1];
+    if (b <= a) { lo = 0; n = 0; return; }
+    a &= ~(int64_t)127;
+    b = (b + 127) & ~(int64_t)127;
+    if (b > o1) b = o1;
+    lo = a; n = b - a;
+}
+
 static void bind_peers(dys_handle* h)
 {
     DevCtx& c = h->c;
     c.n_peers = h->n_peers; c.rank = h->p.rank;
-    c.flag_wait = h->d_peer_flags;
-    c.wait_mask = h->wait_mask; c.signal_mask = h->signal_mask;
+    c.arrive = h->d_arrive;
+    c.pub_lo[0] = 0; c.pub_n[0] = 0; c.units_out[0] = 0; c.arrive_at[0] = h->d_arrive;
+    for (int r = 0; r < 8; ++r) c.expect_in[r] = 0;
     int p = 1;
-    c.pub_lo[0] = 0; c.pub_n[0] = 0;
+    const int me = h->p.rank;
     for (int r = 0; r < h->n_peers; ++r) {
-        c.flag_signal[r] = (h->n_peers > 1 ? h->peer_flags[r] : h->d_peer_flags) + h->p.rank;
         for (int k = 0; k < 2; ++k) h->buf.peer_ib[r][k] = (h->n_peers > 1 ? h->peer_ib[r] : h->d_ib) + (size_t)k * h->ib_stride;
-        if (h->n_peers > 1 && r != h->p.rank) {
-            int64_t lo = c.lo > h->peer_halo[r][0] ? c.lo : h->peer_halo[r][0];
-            int64_t hi = c.lo + c.n_pad < h->peer_halo[r][1] ? c.lo + c.n_pad : h->peer_halo[r][1];
-            lo &= ~(int64_t)15;
-            hi = (hi + 15) & ~(int64_t)15;
-            c.pub_lo[p] = lo;
-            c.pub_n[p] = hi > lo ? hi - lo : 0;
+        if (h->n_peers > 1 && r != me && ((h->partner_mask >> r) & 1u)) {
+            int64_t lo, n;
+            slice_in_halo(h, me, r, lo, n);          // what this rank delivers to r
+            c.pub_lo[p] = lo; c.pub_n[p] = n;
+            c.units_out[p] = (uint32_t)(n >> 7) + 1u;
+            c.arrive_at[p] = h->peer_arrive[r] + me;
+            slice_in_halo(h, r, me, lo, n);          // what r delivers here
+            c.expect_in[r] = (uint32_t)(n >> 7) + 1u;
             ++p;
         }
     }
+    c.epoch = h->pub_epoch;
 }
 
 // phase A on its own for `day`: the day's attention bytes / quirk flags / flag block start clean, k_snapshot raises
@@ -766,10 +834,12 @@ static int run_snapshot(dys_handle* h, int32_t day)
     }
     if (h->n_peers > 1) {
         k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
-        k_signal<<<1, 32, 0, h->stream>>>(c, day);
+        k_signal<<<1, 32, 0, h->stream>>>(c);
+        ++h->pub_epoch;
     }
     CK(h, cudaGetLastError());
     bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
+    c.epoch = h->pub_epoch;
     h->ib_day = day;
     return DYS_OK;
 }
@@ -786,6 +856,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
     if (h->begun) return fail(h, DYS_ERR_STATE, "dys_step_begin called twice without dys_step_end");
     if (day < 0 || day > 32000) return fail(h, DYS_ERR_INVALID_ARG, "day out of range");
     if (h->R > 1) return fail(h, DYS_ERR_NOT_AVAILABLE, "replicas advance through dys_step_many");
+    if (h->ld.mode) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy advances through dys_step_many");
     { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
     CK(h, cudaSetDevice(h->device));
     DevCtx& c = h->c;
@@ -870,13 +941,19 @@ static int step_end(dys_handle* h, int32_t day)
     h->last_slot = slot;
     bind_peers(h);
     bind_day(c, h->buf, day); c.bounds_plan = nullptr; c.piece_work = nullptr;   // (the daily cut belongs to k_days)
+    c.epoch = h->pub_epoch;      // (the bytes of `day` are the latest publication)
     k_push<<<(unsigned)h->push_grid, BLOCK, 0, h->stream>>>(c, day);
     tick(h, 2);
-    k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(c, day);
+    {
+        DevCtx ca = c;
+        ca.n_wr = 1;             // (stand-alone: the agent pass writes its own buffer, k_publish ships the halo parts)
+        k_agent<<<(unsigned)(c.n_pad / 1024), 256, 0, h->stream>>>(ca, day);
+    }
     tick(h, 3);
-    if (h->n_peers > 1) {        // tomorrow's bytes go to every peer GPU, then the flag
+    if (h->n_peers > 1) {        // tomorrow's bytes go to every partner GPU, then the day's units
         k_publish<<<PUBLISH_BLOCKS, 256, 0, h->stream>>>(c);
-        k_signal<<<1, 32, 0, h->stream>>>(c, day + 1);
+        k_signal<<<1, 32, 0, h->stream>>>(c);
+        ++h->pub_epoch;
     }
     CK(h, cudaGetLastError());
     CK(h, cudaEventRecord(h->day_done[slot], h->stream));
@@ -910,6 +987,12 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     const uint8_t* cur_dev = c.open;
     int32_t cur_closed = c.n_closed;
     const int wp = (int)(h->windows & 1);
+    plan.ld = h->ld;
+    if (h->ld.mode) {
+        if (open_flags) return fail(h, DYS_ERR_INVALID_ARG, "the device lockdown policy decides the flags: open_flags must be NULL");
+        if (h->last_day < 0 && first_day != 0) return fail(h, DYS_ERR_STATE, "the device lockdown policy starts at day 0");
+        if (h->last_day >= 0 && first_day != h->last_day + 1) return fail(h, DYS_ERR_STATE, "the device lockdown policy needs consecutive days");
+    }
     if (open_flags) {
         const size_t B = (size_t)c.B;
         if (h->ring_used[wp]) CK(h, cudaEventSynchronize(h->up_done[wp]));      // (two windows ago: long done)
@@ -948,6 +1031,8 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     CK(h, cudaMemsetAsync(h->d_barrier, 0, 4 * sizeof(unsigned int), h->stream));
     if (h->d_work) CK(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned long long) * (size_t)h->days_grid, h->stream));
     plan.work = h->d_work;
+    plan.epoch0 = h->pub_epoch;
+    if (h->n_peers > 1) h->pub_epoch += (unsigned long long)n_days;      // every day of the window publishes tomorrow's bytes
     unsigned int* bar = h->d_barrier;
     void* args[] = {(void*)&c, (void*)&plan, (void*)&bar};
     const size_t trace_words = (size_t)MAX_FUSED_DAYS * (size_t)h->days_grid * TRACE_SLOTS;
@@ -1022,8 +1107,10 @@ extern "C" int dys_step_many(dys_handle* h, int32_t first_day, int32_t n_days, c
     if (h->begun) return fail(h, DYS_ERR_STATE, "dys_step_many between dys_step_begin and dys_step_end");
     if (first_day < 0 || first_day + n_days > 32000) return fail(h, DYS_ERR_INVALID_ARG, "day out of range");
     { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
-    if ((n_days >= 2 || h->R > 1) && n_days <= MAX_FUSED_DAYS && h->days_grid > 0 && h->tev.empty() && (!h->no_fuse || h->R > 1))
+    if ((n_days >= 2 || h->R > 1 || h->ld.mode) && n_days <= MAX_FUSED_DAYS && h->days_grid > 0 && h->tev.empty() &&
+        (!h->no_fuse || h->R > 1 || h->ld.mode))
         return step_fused(h, first_day, n_days, open_flags);
+    if (h->ld.mode) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy runs inside dys_step_many windows of <= %d days", MAX_FUSED_DAYS);
     for (int32_t k = 0; k < n_days; ++k) {
         if (open_flags) {
             int rc = dys_set_open(h, open_flags + (size_t)k * (size_t)h->c.B);
@@ -1189,7 +1276,7 @@ extern "C" int64_t dys_h2d_bytes(const dys_handle* h) { return h ? h->h2d_bytes 
 // compute_R (contagious3.py:29-42) for `rows` days-since-infection histograms in HOST memory: the float epilogue of the
 // integer outputs, in the reference's order of operations (sum_I += n_i * pdf(i) for i = 1 .. recover-1, ascending; IEEE
 // double, no contraction), so the values compare with == against the reference's.
-extern "C" int dys_compute_R_rows(const void* hist, int32_t elem_bytes, int64_t rows, int64_t row_stride, const double* pdf,
+extern "C" int dys_compute_r_rows(const void* hist, int32_t elem_bytes, int64_t rows, int64_t row_stride, const double* pdf,
                                   int32_t recover, double* out)
 {
     if (!hist || !pdf || !out || rows < 0 || (elem_bytes != 4 && elem_bytes != 8) || recover < 1 || recover > HIST_LEN) return DYS_ERR_INVALID_ARG;
@@ -1277,7 +1364,7 @@ extern "C" int dys_peer_export(dys_handle* h, void* out /* DYS_PEER_HANDLE_BYTES
     CK(h, cudaSetDevice(h->device));
     cudaIpcMemHandle_t hs[2];
     CK(h, cudaIpcGetMemHandle(&hs[0], h->d_ib));
-    CK(h, cudaIpcGetMemHandle(&hs[1], h->d_peer_flags));
+    CK(h, cudaIpcGetMemHandle(&hs[1], h->d_arrive));
     static_assert(sizeof(hs) == DYS_PEER_HANDLE_BYTES, "handle size");
     memcpy(out, hs, sizeof hs);
     return DYS_OK;
@@ -1293,7 +1380,7 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
     CK(h, cudaSetDevice(h->device));
     const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)handles;
     for (int r = 0; r < n_ranks; ++r) {
-        if (r == h->p.rank) { h->peer_ib[r] = h->d_ib; h->peer_flags[r] = h->d_peer_flags; continue; }
+        if (r == h->p.rank) { h->peer_ib[r] = h->d_ib; h->peer_arrive[r] = h->d_arrive; continue; }
         void *pib = nullptr, *pfl = nullptr;
         cudaError_t e1 = cudaIpcOpenMemHandle(&pib, hs[2 * r], cudaIpcMemLazyEnablePeerAccess);
         cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&pfl, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) : e1;
@@ -1305,9 +1392,9 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
             return fail(h, DYS_ERR_NOT_AVAILABLE, "peer memory of rank %d is not reachable (%s): use the NCCL exchange", r, cudaGetErrorString(e2));
         }
         h->peer_ib[r] = (uint8_t*)pib;
-        h->peer_flags[r] = (int32_t*)pfl;
+        h->peer_arrive[r] = (unsigned long long*)pfl;
     }
-    h->wait_mask = h->signal_mask = 0;
+    h->partner_mask = 0;
     for (int r = 0; r < n_ranks; ++r) {
         h->peer_own[r][0] = halos[4 * r]; h->peer_own[r][1] = halos[4 * r + 1];
         h->peer_halo[r][0] = halos[4 * r + 2]; h->peer_halo[r][1] = halos[4 * r + 3];
@@ -1315,9 +1402,12 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
     const int me = h->p.rank;
     for (int r = 0; r < n_ranks; ++r) {
         if (r == me) continue;
-        // r's agents inside my halo -> I wait for r; my agents inside r's halo -> r waits for me
-        if (h->peer_own[r][0] < h->peer_halo[me][1] && h->peer_own[r][1] > h->peer_halo[me][0]) h->wait_mask |= 1u << r;
-        if (h->peer_own[me][0] < h->peer_halo[r][1] && h->peer_own[me][1] > h->peer_halo[r][0]) h->signal_mask |= 1u << r;
+        // Partners = ranks whose agents lie in my halo OR whose halo holds mine.  The relation is made SYMMETRIC (both
+        // sides evaluate the same two tests): a rank that only delivers would otherwise never wait, run days ahead and
+        // overwrite the parity buffer its partner is still scanning; with the daily token both sides stay within a day.
+        const bool r_in_mine = h->peer_own[r][0] < h->peer_halo[me][1] && h->peer_own[r][1] > h->peer_halo[me][0];
+        const bool mine_in_r = h->peer_own[me][0] < h->peer_halo[r][1] && h->peer_own[me][1] > h->peer_halo[r][0];
+        if (r_in_mine || mine_in_r) h->partner_mask |= 1u << r;
     }
     h->n_peers = n_ranks;
     h->ib_day = -1;
@@ -1332,12 +1422,12 @@ extern "C" int dys_peer_detach(dys_handle* h)
     for (int r = 0; r < h->n_peers; ++r) {
         if (r == h->p.rank) continue;
         if (h->peer_ib[r]) cudaIpcCloseMemHandle(h->peer_ib[r]);
-        if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
-        h->peer_ib[r] = nullptr; h->peer_flags[r] = nullptr;
+        if (h->peer_arrive[r]) cudaIpcCloseMemHandle(h->peer_arrive[r]);
+        h->peer_ib[r] = nullptr; h->peer_arrive[r] = nullptr;
     }
     cudaGetLastError();
     h->n_peers = 1;
-    h->wait_mask = h->signal_mask = 0;
+    h->partner_mask = 0;
     h->ib_day = -1;
     return DYS_OK;
 }

@@ -115,13 +115,17 @@ struct DevCtx {
     const uint8_t* hh_always;            // [H] or null   (quirk of contagious3.py:267, see dys_load_quirk)
     const int64_t* trig_ptr;             // [n_pad + 1] or null
     const int32_t* trig_hh;
-    // peer mode (n_peers > 1)
-    int64_t pub_lo[8], pub_n[8];         // byte range of the owned slice that write target p needs (its halo)
+    // peer mode (n_peers > 1): every rank stores tomorrow's snapshot bytes straight into the buffers of the ranks whose halo
+    // contains them and counts what it delivered in a counter on the receiving GPU: one unit per 128-agent piece plus one
+    // token per day, so that partners stay within one day of each other even when no bytes travel in one direction
+    int64_t pub_lo[8], pub_n[8];         // write target p >= 1: GLOBAL agents [pub_lo, pub_lo + pub_n) of the owned slice lie in its halo
     int32_t n_wr;
     int32_t n_peers, rank;
-    uint32_t wait_mask, signal_mask;     // ranks whose bytes this rank reads (waits for) / ranks that read this rank's bytes
-    const int32_t* flag_wait;            // [n_peers] on THIS GPU: flag_wait[r] = last day rank r's bytes are complete for
-    int32_t* flag_signal[8];             // [n_peers] &flags[rank] on every GPU (own included)
+    const unsigned long long* arrive;    // [n_peers] on THIS GPU: units received from rank r so far
+    unsigned long long* arrive_at[8];    // write target p >= 1: the counter of this rank on that GPU
+    uint32_t expect_in[8];               // units per day from rank r (0: not a partner)
+    uint32_t units_out[8];               // write target p >= 1: units per day this rank delivers there (pieces + 1)
+    unsigned long long epoch;            // publications that preceded this day's own: the bytes this day READS were the epoch-th
     // ---- the view of ONE day (bind_day) ----
     // day-start snapshot bytes of ALL agents, double buffered by day parity: the scan push of day d reads buffer d&1, the
     // agent pass of day d writes tomorrow's bytes of the owned agents into buffer (d+1)&1
@@ -129,7 +133,9 @@ struct DevCtx {
     uint8_t* ib_wr[8];                   // [n_wr] write targets (own buffer first; peers' buffers are written by publish_body)
     int32_t write_ib;                    // 0: nobody will scan tomorrow's bytes (a middle day of a single-GPU k_days window)
     const uint8_t* open;                 // [B]
-    int32_t n_closed;                    // closed buildings today (counted on the host)
+    int32_t n_closed;                    // closed buildings today (counted on the host, or by the device policy)
+    int64_t open_stride;                 // device lockdown policy: every replica has its own flag vector, B bytes apart (else 0)
+    const int32_t* n_closed_ptr;         // ... and its own count (else null)
     uint8_t *att, *att_next;             // [n_pad] attention bytes of this day / of tomorrow
     int32_t *mb_any, *mb_iso;            // [n_pad] this day's mailboxes: largest infecting i if u is free / if u is isolated
     uint8_t *qflag, *qflag_next;         // [H] quirk households of this day / tomorrow (contagious3.py:267)
@@ -170,8 +176,8 @@ __host__ __device__ __forceinline__ void bind_ib_targets(DevCtx& c, const DayBuf
 {
     c.n_wr = 0;
     c.ib_wr[c.n_wr++] = b.ib[parity];
-    for (int r = 0; r < c.n_peers; ++r)
-        if (c.n_peers > 1 && r != c.rank) c.ib_wr[c.n_wr++] = b.peer_ib[r][parity];
+    for (int r = 0; r < c.n_peers; ++r)      // (partners only, in rank order: the order of pub_lo / arrive_at / units_out)
+        if (c.n_peers > 1 && r != c.rank && c.expect_in[r]) c.ib_wr[c.n_wr++] = b.peer_ib[r][parity];
 }
 
 __host__ __device__ __forceinline__ void bind_day(DevCtx& c, const DayBuffers& b, const int day)
@@ -209,12 +215,14 @@ __host__ __device__ __forceinline__ void shift_replica(DevCtx& c, const int r)
     if (c.bcount) c.bcount = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(c.bcount) + o);
     if (c.ev) c.ev = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(c.ev) + o);
     if (c.piece_work) c.piece_work += (size_t)(c.n_pad >> 7) * r;
-    if (c.rep_params) {
+    c.open += (size_t)c.open_stride * r;
 #ifdef __CUDA_ARCH__
+    if (c.n_closed_ptr) { c.n_closed_ptr += r; c.n_closed = __ldcg(c.n_closed_ptr); }
+    if (c.rep_params) {
         const RepParam p = c.rep_params[r];
         c.norm_factor = p.norm_factor; c.compliance = p.compliance; c.seed = p.seed;
-#endif
     }
+#endif
 }
 
 __device__ __forceinline__ double draw(const double* inj, int64_t idx, uint64_t seed, uint32_t day, uint32_t stream,

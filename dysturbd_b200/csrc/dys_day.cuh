@@ -20,6 +20,16 @@
 #pragma once
 #include <cstddef>
 
+// Software pipelining of the two gather loops (developer switches for ablation).  Measured on B200 (profiles/r02d_ab.txt):
+// requesting the next settle round's records a round early is neutral, requesting the next 64 edge records a step early
+// costs 4 % (register pressure under the 64-register cap of 4 CTAs per SM), both together 23 % -- so both are off.
+#ifndef DYS_PIPE_SETTLE
+#define DYS_PIPE_SETTLE 0
+#endif
+#ifndef DYS_PIPE_PUSH
+#define DYS_PIPE_PUSH 0
+#endif
+
 #include "dys_common.cuh"
 
 namespace dys {
@@ -54,6 +64,27 @@ __device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, int 
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// peer mode: tomorrow's snapshot bytes of the owned agents that lie in a peer's halo are stored straight into that peer's
+// buffer (P2P stores over NVLink), every byte exactly once per day: the sweep stores the bytes of the agents it does not
+// list (`listed` = 4-bit mask of the word's agents that go to the settle phase), the settle phase the byte of each agent
+// it handles -- so no two stores to one remote byte ever have to be ordered.
+__device__ __forceinline__ void remote_ib_word(const DevCtx& c, const int64_t ga0, const uint32_t listed)
+{
+    for (int p = 1; p < c.n_wr; ++p)
+        if (ga0 >= c.pub_lo[p] && ga0 < c.pub_lo[p] + c.pub_n[p]) {
+            if (!listed) *reinterpret_cast<uint32_t*>(c.ib_wr[p] + ga0) = 0u;
+            else
+                for (int j = 0; j < 4; ++j)
+                    if (!((listed >> j) & 1u)) c.ib_wr[p][ga0 + j] = 0;
+        }
+}
+
+__device__ __forceinline__ void remote_ib_byte(const DevCtx& c, const int64_t ga, const uint8_t ibn)
+{
+    for (int p = 1; p < c.n_wr; ++p)
+        if (ga >= c.pub_lo[p] && ga < c.pub_lo[p] + c.pub_n[p]) c.ib_wr[p][ga] = ibn;
+}
 
 // Spinning loops (the grid barrier of k_days, the waits for peer GPUs) give
 // up when the abort word is set (by the host, or by a peer wait that timed out) or after spin_timeout_ns, so that a
@@ -116,6 +147,7 @@ struct BlockScratch {
     long long b_lo[2];                             // the batch being swept and the one after it (first piece, pieces)
     int b_n[2];
     unsigned int n_front, n_list;
+    unsigned int pub_cnt[8];                       // peer mode: pieces of this call whose bytes went to write target p
     unsigned int hist[HIST_LEN], ev[EV_LEN], cnt[10], acc[8];
     bool last;
 };
@@ -133,23 +165,37 @@ struct BlockScratch {
 //                  for both isolation cases; the agent pass of u picks the one that applies (and ignores it if u is
 //                  not susceptible).
 // ---------------------------------------------------------------------------------------------------------------
+// one lane's row of a group: frontier entry, start and length of its transposed row
+struct RowRef {
+    uint32_t fe;
+    int len;
+    int64_t t0;
+};
+
+__device__ __forceinline__ RowRef load_row(const DevCtx& c, const uint32_t* ent, const int nb, const FrontMap fmap)
+{
+    RowRef r{0u, 0, 0};
+    const int lane = threadIdx.x & 31;
+    if (lane < nb) {
+        r.fe = ent[lane];
+        const int64_t il = fmap.at(r.fe & REL_MASK);
+        r.t0 = __ldg(c.tptr + il);
+        r.len = (int)(__ldg(c.tptr + il + 1) - r.t0);
+    }
+    return r;
+}
+
 template <bool CHECK>
 __device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushWarpScratch& w, const double* __restrict__ s_pdf,
-                                           const uint32_t* ent, const int nb, const FrontMap fmap, unsigned int (&cnt)[4])
+                                           const RowRef row0, const FrontMap fmap, unsigned int (&cnt)[4])
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool any_closed = c.n_closed != 0;
     const uint4* edges = reinterpret_cast<const uint4*>(c.tedge);
-    int64_t t0 = 0;
-    int len = 0;
-    uint32_t fe0 = 0;
-    if (lane < nb) {
-        fe0 = ent[lane];
-        const int64_t il = fmap.at(fe0 & REL_MASK);
-        t0 = __ldg(c.tptr + il);
-        len = (int)(__ldg(c.tptr + il + 1) - t0);
-    }
+    const int64_t t0 = row0.t0;
+    const int len = row0.len;
+    const uint32_t fe0 = row0.fe;
     const unsigned nz = __ballot_sync(0xffffffffu, len > 0);
     const int nr = __popc(nz);
     if (nr == 0) return;
@@ -175,10 +221,10 @@ __device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushW
     cnt[0] += mylen;
     // two entries per lane and step: every entry of the transposed network can be exposed (the others were left out at
     // load time), so nearly every lane draws its Bernoulli and the Philox rounds run on full warps
-    for (int f0 = 0; f0 < total; f0 += 64) {
-        uint32_t fe[2];
-        uint4 rec[2];
-        uint32_t st_u[2];
+    // the records of step f0 + 64 are requested before the pairs of step f0 are evaluated
+    uint32_t fe_n[2];
+    uint4 rec_n[2];
+    auto fetch = [&](const int f0, uint32_t (&fe)[2], uint4 (&rec)[2]) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int base = f0 + 32 * k, f = base + lane;
@@ -193,6 +239,21 @@ __device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushW
                 fe[k] = w.fe[row];
             }
         }
+    };
+#if DYS_PIPE_PUSH
+    fetch(0, fe_n, rec_n);
+#endif
+    for (int f0 = 0; f0 < total; f0 += 64) {
+#if DYS_PIPE_PUSH
+        uint32_t fe[2] = {fe_n[0], fe_n[1]};
+        uint4 rec[2] = {rec_n[0], rec_n[1]};
+        if (f0 + 64 < total) fetch(f0 + 64, fe_n, rec_n);
+#else
+        uint32_t fe[2];
+        uint4 rec[2];
+        fetch(f0, fe, rec);
+#endif
+        uint32_t st_u[2];
         if (CHECK) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
@@ -258,10 +319,16 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
     int rpg = (n + WARPS - 1) / WARPS;
     rpg = rpg < 1 ? 1 : (rpg > 32 ? 32 : rpg);
     const int n_groups = (n + rpg - 1) / rpg;
-    for (int g = wid; g < n_groups; g += WARPS) {
+    auto rows_of = [&](const int g) {
         const int q0 = g * rpg;
         const int nb = (n - q0) < rpg ? (n - q0) : rpg;
-        push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, sm.front + q0, nb, fmap, cnt);
+        return load_row(c, sm.front + q0, nb, fmap);
+    };
+    RowRef next = wid < n_groups ? rows_of(wid) : RowRef{0u, 0, 0};
+    for (int g = wid; g < n_groups; g += WARPS) {
+        const RowRef cur = next;
+        if (g + WARPS < n_groups) next = rows_of(g + WARPS);      // the next group's row extents, in flight under this group
+        push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, cur, fmap, cnt);
     }
 }
 
@@ -306,12 +373,16 @@ __device__ __forceinline__ void block_share(const int64_t n, const int n_blocks,
 // skip_own (peer mode inside a window): the owned agents' rows were already pushed by their blocks after yesterday's
 // agent pass; only the halo agents' bytes, which arrive from the peers, are scanned
 // returns true when a wait for a peer GPU was abandoned (abort word / timeout): the launch must end
-__device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb,
-                                               const bool skip_own = false)
+// HALO_ONLY (peer mode inside a window): the rows of the owned agents were pushed by their blocks after the agent pass; only
+// the halo agents' bytes, which the peers stored into this GPU's buffer, are scanned -- while other blocks may still be
+// settling the day before, hence CHECK = false and no clearing duties
+template <bool HALO_ONLY>
+__device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb)
 {
+    constexpr bool CHECK = !HALO_ONLY;
     __shared__ int s_gave_up;
     const int tid = threadIdx.x, lane = tid & 31;
-    push_clear_duties(c);
+    if (!HALO_ONLY) push_clear_duties(c);
     if (tid < 64) sm.pdf[tid] = c.pdf[tid];
     if (tid == 0) sm.n_front = 0;
     __syncthreads();
@@ -325,10 +396,11 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
         int64_t base = lo;
         const uint32_t* ib4 = reinterpret_cast<const uint32_t*>(c.ib_rd + c.rt_lo);   // rt_lo is a multiple of 1024
         uint32_t v = 0;
-        if (lo + tid * 4 < hi) v = ib4[(lo >> 2) + tid];
+        // (__ldcg: the bytes were written by other SMs or other GPUs since this SM last read the buffer; L1 is not coherent)
+        if (lo + tid * 4 < hi) v = __ldcg(ib4 + (lo >> 2) + tid);
         for (int64_t s0 = lo; s0 < hi; s0 += BLOCK * 4) {
             uint32_t vn = 0;
-            if (s0 + BLOCK * 4 + tid * 4 < hi) vn = ib4[((s0 + BLOCK * 4) >> 2) + tid];   // next step's bytes, in flight
+            if (s0 + BLOCK * 4 + tid * 4 < hi) vn = __ldcg(ib4 + ((s0 + BLOCK * 4) >> 2) + tid);   // next step's bytes, in flight
             const int64_t il0 = s0 + tid * 4;
             uint32_t vm = v & 0x80808080u;                          // bytes past the end of the share are not ours
             if (il0 + 4 > hi) vm &= il0 >= hi ? 0u : (0xFFFFFFFFu >> (8 * (int)(il0 + 4 - hi)));
@@ -358,7 +430,7 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
             const int64_t s1 = s0 + BLOCK * 4;
             const unsigned nf = sm.n_front;        // read by everyone before the next step appends (barrier below)
             if (nf > FCAP - BLOCK * 4 || s1 - base > (int64_t)REL_MASK - BLOCK * 4 || s1 >= hi) {
-                if (nf) push_frontier<true>(c, day, sm, FrontMap{base}, cnt);
+                if (nf) push_frontier<CHECK>(c, day, sm, FrontMap{base}, cnt);
                 __syncthreads();
                 if (tid == 0) sm.n_front = 0;
                 base = s1;
@@ -367,16 +439,18 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
         }
     };
     if (c.n_peers > 1) {
-        // peer mode: the owned agents' bytes are local and final, so their rows are pushed first; the halo agents'
-        // bytes were stored into this GPU's buffer by their owners, who then raised flag[r] = day -- the exchange
+        // peer mode: the owned agents' bytes are local and final, so their rows are pushed first; the halo agents' bytes
+        // were stored into this GPU's buffer by their owners, who counted what they delivered in arrive[r] (pieces + one
+        // token per day): the bytes of this day are complete once epoch x expect_in[r] units have arrived.  The exchange
         // latency hides behind the local part of the push.  (Persistent grid: all CTAs resident, spinning is safe.)
         const int64_t own0 = c.lo - c.rt_lo, own1 = own0 + c.n_pad < c.rt_n ? own0 + c.n_pad : c.rt_n;
-        if (!skip_own) scan(own0, own1);
+        if (!HALO_ONLY) scan(own0, own1);
         if (tid == 0) s_gave_up = 0;
         __syncthreads();
-        if (tid < c.n_peers && ((c.wait_mask >> tid) & 1u)) {      // only the ranks whose agents are in this rank's halo
-            const volatile int32_t* f = c.flag_wait + tid;
-            if (spin_until(c, [&]() { return *f >= day; })) s_gave_up = 1;
+        if (tid < c.n_peers && c.expect_in[tid]) {
+            const volatile unsigned long long* f = c.arrive + tid;
+            const unsigned long long need = c.epoch * (unsigned long long)c.expect_in[tid];
+            if (spin_until(c, [&]() { return *f >= need; })) s_gave_up = 1;
             __threadfence_system();
         }
         __syncthreads();
@@ -393,7 +467,7 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
 __global__ void __launch_bounds__(BLOCK) k_push(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
-    push_scan_body(c, day, sm, (int)gridDim.x, (int)blockIdx.x);
+    push_scan_body<false>(c, day, sm, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -533,6 +607,7 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
     if (ibn && c.write_ib) c.ib_wr[0][c.lo + a] = ibn;      // (the sweep already stored 0 for everybody)
+    if (c.n_wr > 1) remote_ib_byte(c, c.lo + a, ibn);
     if (in_set(M_INF, x) && day + 1 - ti == c.diagnosis) {
         const int4 rw = second_half();
         if (diagnosed_on(c, nullptr, a, x, ti, day + 1, __hiloint2double(rw.w, rw.z)))
@@ -596,9 +671,8 @@ __device__ __forceinline__ void fold_stats(unsigned long long* __restrict__ part
 //   static  (word == null): the pieces [next, end) of the view, in batches of <= 16 (k_agent; a stolen chunk in k_days).
 //   dynamic (k_days, the block's own run): `word` = (end << 32 | next) in UNIFIED piece indices ([replica][piece], local =
 //           unified - rep_off) lives in global memory.  The owner takes batches from the head with a compare-and-swap; blocks
-//           that finished their own run take batches from the same word (work stealing, see k_days).  Batch sizes follow
-//           guided self-scheduling -- a quarter of what is left, between 2 and 16 pieces -- so that whoever takes the last
-//           pieces of a run holds little work when everybody else is done.
+//           that finished their own run take batches from the same word (work stealing, see k_days): one atomicAdd per
+//           batch -- 16 pieces for the owner, 8 for a thief --, issued a whole sweep before its answer is needed.
 // ---------------------------------------------------------------------------------------------------------------
 struct WorkSrc {
     unsigned long long* word;
@@ -611,27 +685,38 @@ __device__ __forceinline__ unsigned long long pack_work(const int64_t next, cons
     return ((unsigned long long)(uint32_t)end << 32) | (unsigned long long)(uint32_t)next;
 }
 
-// one thread: take the next batch; returns its first local piece and writes its size (0 = nothing left)
-__device__ __forceinline__ int64_t take_batch(WorkSrc& ws, int& n, const int cap = 16)
+// peer mode, one thread: the pieces [lo, lo + n) of the view were taken by this block -- how many of them lie in each peer's halo
+__device__ __forceinline__ void count_pub(const DevCtx& c, BlockScratch& sm, const int64_t lo, const int n)
+{
+    const int64_t g0 = c.lo + (lo << 7), g1 = g0 + ((int64_t)n << 7);
+    for (int p = 1; p < c.n_wr; ++p) {
+        const int64_t a = g0 > c.pub_lo[p] ? g0 : c.pub_lo[p];
+        const int64_t b = g1 < c.pub_lo[p] + c.pub_n[p] ? g1 : c.pub_lo[p] + c.pub_n[p];
+        if (b > a) sm.pub_cnt[p] += (unsigned)((b - a) >> 7);
+    }
+}
+
+// one thread: take the next batch of <= g pieces.  The atomic is ISSUED by take_issue and its answer only looked at by
+// take_result, so that the round trip to the work word hides under whatever the caller does in between.
+__device__ __forceinline__ unsigned long long take_issue(WorkSrc& ws, const int g)
 {
     if (!ws.word) {
         const int64_t lo = ws.next;
-        n = (int)(ws.end - lo < cap ? ws.end - lo : cap);
-        if (n < 0) n = 0;
-        ws.next = lo + n;
-        return lo;
+        const int64_t n = ws.end - lo < g ? ws.end - lo : g;
+        ws.next = lo + (n > 0 ? n : 0);
+        return pack_work(lo, lo + (n > 0 ? n : 0));
     }
-    unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(ws.word);
-    for (;;) {
-        const uint32_t nx = (uint32_t)w, en = (uint32_t)(w >> 32);
-        if (nx >= en) { n = 0; return 0; }
-        int g = (int)((en - nx + 3u) >> 2);
-        g = g < 2 ? 2 : (g > cap ? cap : g);
-        if ((uint32_t)g > en - nx) g = (int)(en - nx);
-        const unsigned long long seen = atomicCAS(ws.word, w, w + (unsigned long long)g);
-        if (seen == w) { n = g; return (int64_t)nx - ws.rep_off; }
-        w = seen;
-    }
+    const unsigned long long old = atomicAdd(ws.word, (unsigned long long)g);
+    const uint32_t nx = (uint32_t)old, en = (uint32_t)(old >> 32);
+    const uint32_t hi = nx + (uint32_t)g < en ? nx + (uint32_t)g : en;
+    return nx < en ? pack_work((int64_t)nx - ws.rep_off, (int64_t)hi - ws.rep_off) : 0ull;      // local [lo, hi)
+}
+
+__device__ __forceinline__ int64_t take_result(const unsigned long long t, int& n)
+{
+    const uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+    n = hi > lo ? (int)(hi - lo) : 0;
+    return (int64_t)lo;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -659,9 +744,11 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
     if (tid < 10) sm.cnt[tid] = 0;
     if (tid == 0) {
         sm.n_list = 0; sm.n_front = 0;
+        for (int p = 0; p < 8; ++p) sm.pub_cnt[p] = 0;
         int n;
-        const int64_t lo = take_batch(ws, n);
+        const int64_t lo = take_result(take_issue(ws, 2 * WARPS), n);
         sm.b_lo[0] = lo; sm.b_n[0] = n;
+        if (c.n_wr > 1) count_pub(c, sm, lo, n);
     }
     if (cn && tid < 64) sm.pdf[tid] = c.pdf[tid];
     __syncthreads();
@@ -687,12 +774,10 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
         }
     }
     for (int it = 0; b_n > 0; ++it) {
-        // the batch after this one is taken now (its words are requested before this batch is settled)
-        if (tid == 0) {
-            int n;
-            const int64_t lo = take_batch(ws, n);
-            sm.b_lo[(it + 1) & 1] = lo; sm.b_n[(it + 1) & 1] = n;
-        }
+        // the batch after this one is taken now (its words are requested before this batch is settled); the answer of the
+        // atomic is only looked at after the sweep
+        unsigned long long taken = 0ull;
+        if (tid == 0) taken = take_issue(ws, SLOTS);
         // ---- sweep ----
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -720,6 +805,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                 if (aw[r]) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
                 // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
                 if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
+                if (c.n_wr > 1) remote_ib_word(c, c.lo + a0, work);
             }
             const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
             if (any) {
@@ -739,6 +825,12 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                         prefetch_l2(c.rec + a0 + j);      // the record is needed when the list is settled
                     }
             }
+        }
+        if (tid == 0) {
+            int n;
+            const int64_t lo = take_result(taken, n);
+            sm.b_lo[(it + 1) & 1] = lo; sm.b_n[(it + 1) & 1] = n;
+            if (c.n_wr > 1) count_pub(c, sm, lo, n);
         }
         __syncthreads();
         // the next batch's words are requested before this batch is settled
@@ -760,26 +852,37 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
         const int n_list = (int)sm.n_list;
         const bool do_settle = n_list > LTOT - SLOTS * 128 || nb_n == 0;
         if (do_settle) {
+            // the next round's records are requested before this round is settled
+            uint32_t le_n = tid < n_list ? sm.list[tid] : 0u;
+            Loaded L_n;
+            L_n.mb = -1;
+            if (tid < n_list) L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
             for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
                 const int k = k0 + tid;
+#if !DYS_PIPE_SETTLE
+                if (k0 > 0 && k < n_list) {
+                    le_n = sm.list[k];
+                    L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
+                }
+#endif
                 bool infected_today = false;
                 int infector = -1;
-                int64_t a = 0;
-                uint32_t ibn = 0, rel = 0;
+                uint32_t ibn = 0;
                 uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
                 int kbin = -1;
                 const bool valid = k < n_list;
-                uint32_t st = ST_PAD, att = 0;
-                Loaded L;
-                L.mb = -1;
-                if (valid) {
-                    const uint32_t le = sm.list[k];
-                    rel = le & REL_MASK;
-                    a = a_base + rel;
-                    st = (le >> 24) & 0xFu;
-                    att = (le >> 28) & 0x3u;
-                    L = load_agent(c, a, st, att);
+                const uint32_t le = le_n;
+                const Loaded L = L_n;
+                const uint32_t rel = le & REL_MASK;
+                const int64_t a = a_base + rel;
+                const uint32_t st = valid ? (le >> 24) & 0xFu : (uint32_t)ST_PAD, att = (le >> 28) & 0x3u;
+                L_n.mb = -1;
+#if DYS_PIPE_SETTLE
+                if (k + BLOCK < n_list) {
+                    le_n = sm.list[k + BLOCK];
+                    L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
                 }
+#endif
                 // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim
                 // is issued as soon as the mailboxes are in, its answer is only needed when the events are written
                 const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
@@ -859,6 +962,17 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
         }
     }
     __syncthreads();
+    if (VARIANT == 3 && c.n_wr > 1) {
+        // peer mode: every byte of the pieces this call took has been stored (here and in the peers).  Fence at system
+        // scope, then tell each peer how many pieces it received.
+        unsigned int any = 0;
+        for (int p = 1; p < c.n_wr; ++p) any |= sm.pub_cnt[p];
+        if (any) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid >= 1 && tid < c.n_wr && sm.pub_cnt[tid]) atomicAdd_system(c.arrive_at[tid], (unsigned long long)sm.pub_cnt[tid]);
+        }
+    }
     if (tid < 32) {
         // warp 0 publishes everything, fences, and takes the ticket
         const int slot = blockIdx.x & (N_SLOTS - 1);
@@ -925,8 +1039,23 @@ __device__ __forceinline__ void publish_body(const DevCtx& c, const int pub_idx,
 
 __global__ void __launch_bounds__(BLOCK) k_publish(const DevCtx c) { publish_body(c, (int)blockIdx.x, (int)gridDim.x); }
 
+// Phase H on the device (contagious3.py:57-107, 368-385): the service block of k_days forms R of the day it just folded
+// (compute_R, :29-42, in the reference's order of float operations) and decides the open flags THREE days ahead -- the
+// decision for day t uses `Known R` of days t-1 and t-2, i.e. R of days t-1-diagnosis and t-2-diagnosis (:306-309), which are
+// long known -- so a whole run needs no host round trip and no flag upload.
+constexpr int SC_GRADUAL = 1, SC_ALL = 2, SC_EDU = 4, SC_REL = 8;      // scenario keywords; building class bits = 2, 4, 8
+struct LockdownPlan {
+    int32_t mode;                                   // 0: the flags come from the host
+    int32_t scen;                                   // SC_* bits
+    const uint8_t* bld_class;                       // [B] 2: land use >= 3 (ALL), 4: EDU code, 8: REL code
+    uint8_t* flags;                                 // [4][n_rep][B] ring by day & 3
+    int32_t* n_closed;                              // [4][n_rep]
+    double* r_hist;                                 // [16][n_rep] ring by day & 15: R of that day
+};
+
 constexpr int MAX_FUSED_DAYS = 14;
 constexpr int PUBLISH_BLOCKS = 8;          // the halo part of a slice is small (one community per neighbour)
+constexpr int HALO_BLOCKS = 16;            // blocks that push the halo agents' rows inside a k_days window
 struct DayPlan {
     int32_t first_day, n_days;
     int32_t n_closed[MAX_FUSED_DAYS];
@@ -936,6 +1065,8 @@ struct DayPlan {
     DayBuffers buf;
     int32_t want_sa, want_bc, want_ev;
     unsigned long long* trace;                      // developer tracing: [n_days][grid][8] globaltimer at phase boundaries, or null
+    LockdownPlan ld;
+    unsigned long long epoch0;                      // peer mode: the bytes of first_day were the epoch0-th publication
     unsigned long long* work;                       // [grid] the blocks' work words (see WorkSrc), or null: no stealing
     int32_t test_hang_block;                        // tests (DYS_TEST_HANG_BLOCK): this block leaves before the first barrier; -1 = none
 };
@@ -946,6 +1077,15 @@ __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const
     bind_day(c, plan.buf, plan.first_day + k);
     c.open = plan.open[k];
     c.n_closed = plan.n_closed[k];
+    c.open_stride = 0; c.n_closed_ptr = nullptr;
+    if (plan.ld.mode) {      // (decided at least two grid barriers ago, see lockdown_service)
+        const int R = c0.n_rep > 1 ? c0.n_rep : 1;
+        const int slot = (plan.first_day + k) & 3;
+        c.open = plan.ld.flags + (size_t)slot * R * c0.B;
+        c.open_stride = c0.B;
+        c.n_closed_ptr = plan.ld.n_closed + slot * R;
+        c.n_closed = __ldcg(c.n_closed_ptr);
+    }
     c.stats = reinterpret_cast<int64_t*>(plan.out[k]);
     c.sa_hist = plan.want_sa ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_sa) : nullptr;
     c.bcount = plan.want_bc ? reinterpret_cast<int32_t*>(plan.out[k] + plan.off_bc) : nullptr;
@@ -953,6 +1093,7 @@ __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const
     // tomorrow's snapshot bytes are only scanned by a stand-alone push: every day in peer / two-phase mode, else only
     // after the last day of the window (the next call starts with a scan)
     c.write_ib = (c0.n_peers > 1 || c0.io_mat != nullptr || k == plan.n_days - 1) ? 1 : 0;
+    c.epoch = plan.epoch0 + (unsigned long long)k;
     // this block's run of pieces on that day: its cut was finished at least a day ago (plan_cut runs three days ahead), so
     // fetching it here -- while the view is built, a day early for every day but the window's first -- costs no round trip later
     const int32_t* cut = plan.buf.bounds[(plan.first_day + k) % 3];
@@ -1060,6 +1201,61 @@ __device__ __forceinline__ void plan_cut(const uint32_t* __restrict__ work, int3
     }
 }
 
+// after the fold of `day` for replica r: R(day) into the history, 'Closed buildings' / R / Known R into the day's stats block
+// (slots 28-30), and the flags of day + 3
+__device__ __noinline__ void lockdown_service(const LockdownPlan ld, const int64_t B, const int recover, const int diagnosis,
+                                              const double* __restrict__ pdf, const uint64_t seed, const int day, const int r,
+                                              const int n_rep, int64_t* __restrict__ stats)
+{
+    __shared__ double s_vr[2];
+    __shared__ int s_closed;
+    const int tid = threadIdx.x;
+    const int t = day + 3;
+    if (tid == 0) {
+        double sum_I = 0.0;                                                                     // compute_R, :29-42
+        for (int i = 1; i < recover; ++i) sum_I = __dadd_rn(sum_I, __dmul_rn((double)stats[HIST0 + i], pdf[i]));
+        const double R = sum_I > 0.0 ? __ddiv_rn((double)stats[HIST0], sum_I) : 0.0;
+        ld.r_hist[(day & 15) * n_rep + r] = R;
+        auto known = [&](const int d) { return d > diagnosis ? ld.r_hist[((d - diagnosis) & 15) * n_rep + r] : 0.0; };   // :306-309
+        s_vr[0] = known(t - 1);                                                                 // vR of the decision made on day t-1
+        s_vr[1] = (t - 1 != 0) ? known(t - 2) : 0.0;                                            // prevVR, :379-384
+        stats[28] = ld.n_closed[(day & 3) * n_rep + r];
+        stats[29] = __double_as_longlong(R);
+        stats[30] = __double_as_longlong(known(day));
+        s_closed = 0;
+    }
+    __syncthreads();
+    const double vR = s_vr[0], prevVR = s_vr[1];
+    enum { OPEN, FULL, HALF, KEEP };
+    int what = OPEN;                                                                            // building_lockdown, :57-107
+    if (ld.scen & SC_GRADUAL) {
+        if (vR > 1.0 && vR < 2.0) what = (prevVR <= 1.0 || prevVR >= 2.0) ? HALF : KEEP;
+        else if (vR >= 2.0) what = FULL;
+    } else if (vR > 1.0) what = FULL;
+    const uint32_t classes = (ld.scen & SC_ALL) ? (uint32_t)SC_ALL : (uint32_t)(ld.scen & (SC_EDU | SC_REL));
+    uint8_t* dst = ld.flags + ((size_t)(t & 3) * n_rep + r) * B;
+    const uint8_t* prev = ld.flags + ((size_t)((t - 1) & 3) * n_rep + r) * B;
+    int* const slot_closed = ld.n_closed + (t & 3) * n_rep + r;
+    if (what == OPEN && *slot_closed == 0) { __syncthreads(); return; }       // (the slot still holds an all-open vector)
+    int closed = 0;
+    for (int64_t b = tid; b < B; b += blockDim.x) {
+        uint8_t f = 1;
+        const bool in_class = (__ldg(ld.bld_class + b) & classes) != 0;
+        if (what == FULL) f = in_class ? 0 : 1;
+        // (the reference draws exactly half of each class with np.random.choice; the device policy closes each building of
+        // the class with probability 1/2 on a keyed draw -- host twin: host.building_lockdown(keyed=...))
+        else if (what == HALF) f = (in_class && keyed_uniform(seed, (uint32_t)(t - 1), STREAM_LOCKDOWN, (uint32_t)b, 0u) < 0.5) ? 0 : 1;
+        else if (what == KEEP) f = prev[b];
+        dst[b] = f;
+        closed += f == 0;
+    }
+    closed = __reduce_add_sync(0xffffffffu, closed);
+    if ((tid & 31) == 0 && closed) atomicAdd(&s_closed, closed);
+    __syncthreads();
+    if (tid == 0) *slot_closed = s_closed;
+    __syncthreads();
+}
+
 // All CTAs are resident (cooperative launch): one arrival per CTA on a monotone counter, no reset needed.
 __device__ __forceinline__ bool grid_barrier(const DevCtx& c, unsigned int* counter, unsigned int& epoch)
 {
@@ -1082,12 +1278,11 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     __shared__ BlockScratch sm;
     __shared__ DevCtx s_c[2];            // today's and tomorrow's view of the context (read like kernel parameters)
     __shared__ DevCtx s_r[2];            // replicas: the same two views shifted to the replica the block is working on
-    __shared__ bool s_pub_last;
     unsigned int epoch = 0;
     const bool peers = c0.n_peers > 1;
     const int n_rep = c0.n_rep > 1 ? c0.n_rep : 1;
     // io_mat is one buffer for the latest day: the push of day + 1 must not clear it under the agent pass of day
-    const bool two_phase = peers || c0.io_mat != nullptr;
+    const bool two_phase = c0.io_mat != nullptr;
     // Block 0 owns no agents: it folds each day's statistics and re-cuts the population after the barrier while the
     // others are already in the next day.  (The FIRST block, because the warp schedulers favour the oldest warps of an
     // SM: as the youngest block it was starved by its three busy neighbours and became the one everybody waited for.)
@@ -1122,7 +1317,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         if (k == 0 || two_phase) {
             for (int r = 0; r < n_rep; ++r) {
                 const DevCtx& cr = replica_view(c, 0, r);
-                if (push_scan_body(cr, day, sm, n_work, wb, peers && k > 0)) return;
+                if (push_scan_body<false>(cr, day, sm, n_work, wb)) return;
                 __syncthreads();
             }
             stamp(1);
@@ -1185,7 +1380,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                         if (best > 0u && lane == __ffs(who) - 1) {
                             WorkSrc vs{plan.work + v, 0, 0, 0};
                             int n = 0;
-                            sm.b_lo[0] = take_batch(vs, n);
+                            sm.b_lo[0] = take_result(take_issue(vs, WARPS), n);      // unified piece index (rep_off = 0)
                             sm.b_n[0] = n;
                         }
                         if (lane == 0) {
@@ -1216,38 +1411,31 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 __syncthreads();
             }
         }
+        if (peers) {
+            // One token per day and partner (the partners stay within a day of each other even if no bytes travel one way),
+            // then the push of the HALO agents' rows for tomorrow: their bytes arrive from the peers as those finish today's
+            // agent pass.  A few blocks share it -- the halo is a community or two -- and everybody meets at the barrier.
+            if (wb == 0 && threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr) atomicAdd_system(c.arrive_at[threadIdx.x], 1ull);
+            const int n_halo = HALO_BLOCKS < n_work ? HALO_BLOCKS : n_work;
+            if (cn && wb >= 0 && wb < n_halo) {
+                if (push_scan_body<true>(*cn, day + 1, sm, n_halo, wb)) return;
+            }
+        }
         stamp(3);
         if (grid_barrier(c, barrier_counter, epoch)) return;
         stamp(4);
         if (service || gridDim.x == 1) {                      // every block's partial sums are in; the others move on
-            for (int r = 0; r < n_rep; ++r)
-                fold_stats(c.part + (size_t)r * N_STATS * N_SLOTS,
-                           reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(c.stats) + (size_t)r * c.out_stride));
+            for (int r = 0; r < n_rep; ++r) {
+                int64_t* st = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(c.stats) + (size_t)r * c.out_stride);
+                fold_stats(c.part + (size_t)r * N_STATS * N_SLOTS, st);
+                if (plan.ld.mode)
+                    lockdown_service(plan.ld, c.B, c.recover, c.diagnosis, c.pdf, c.rep_params ? c.rep_params[r].seed : c.seed, day, r, n_rep, st);
+            }
             // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
             // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a
             // quiet day.  The cut made after day d is the one of day d + 3.)
-            // (with more than two staging chunks of pieces the equal split + stealing balances well enough, and planning
-            // would make this block late for the next barrier)
-            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0 && n_pieces_all <= 2 * (FCAP + LTOT))
-                plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
+            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
             stamp(11);
-        }
-        const int n_pub = PUBLISH_BLOCKS < n_work ? PUBLISH_BLOCKS : n_work;
-        if (peers && wb >= 0 && wb < n_pub) {      // (not the service block: it is busy folding)
-            // a few CTAs ship tomorrow's bytes to the peers while the others already start the next day (whose push
-            // waits for the peers' flags anyway); the last shipper raises this rank's flag on every GPU
-            publish_body(c, wb, n_pub);
-            __syncthreads();
-            if (threadIdx.x == 0) s_pub_last = (atomicAdd(barrier_counter + 1, 1u) == (unsigned)n_pub - 1u);
-            __syncthreads();
-            if (s_pub_last) {
-                if (threadIdx.x == 0) barrier_counter[1] = 0u;
-                if (threadIdx.x < c0.n_peers && ((c0.signal_mask >> threadIdx.x) & 1u)) {
-                    __threadfence_system();
-                    *reinterpret_cast<volatile int32_t*>(c0.flag_signal[threadIdx.x]) = day + 1;
-                }
-            }
-            __syncthreads();
         }
         __syncthreads();      // the fold (and tomorrow's bind) are done with today's view
     }
@@ -1272,12 +1460,12 @@ __global__ void __launch_bounds__(BLOCK) k_snapshot(const DevCtx c, const int da
     *reinterpret_cast<uchar4*>(c.ib_wr[0] + c.lo + a0) = make_uchar4(ibn[0], ibn[1], ibn[2], ibn[3]);
 }
 
-// peer mode: after a stand-alone k_snapshot, tell every GPU that this rank's bytes for `day` are complete
-__global__ void k_signal(const DevCtx c, const int day)
+// peer mode, stand-alone launches (k_snapshot / k_agent + k_publish): every partner receives the day's units at once
+__global__ void k_signal(const DevCtx c)
 {
-    if (threadIdx.x < c.n_peers && ((c.signal_mask >> threadIdx.x) & 1u)) {
+    if (threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr) {
         __threadfence_system();
-        *reinterpret_cast<volatile int32_t*>(c.flag_signal[threadIdx.x]) = day;
+        atomicAdd_system(c.arrive_at[threadIdx.x], (unsigned long long)c.units_out[threadIdx.x]);
     }
 }
 

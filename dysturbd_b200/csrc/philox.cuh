@@ -9,7 +9,7 @@
 
 namespace dys {
 
-enum : uint32_t { STREAM_ADMISSION = 0, STREAM_DEATH = 1, STREAM_INFECTION = 2, STREAM_COMPLIANCE = 3 };
+enum : uint32_t { STREAM_ADMISSION = 0, STREAM_DEATH = 1, STREAM_INFECTION = 2, STREAM_COMPLIANCE = 3, STREAM_LOCKDOWN = 4 };
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                         uint32_t k0, uint32_t k1, uint32_t& o0, uint32_t& o1,

@@ -12,7 +12,7 @@ import numpy as np
 from .population import EpiParams, Population
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdysturbd.so")
+LIB_PATH = os.environ.get("DYS_LIB") or os.path.join(HERE, "libdysturbd.so")      # (DYS_LIB: developer ablation builds)
 
 N_STATS = 64
 HIST0 = 32
@@ -25,6 +25,9 @@ STAT = {name: i for i, name in enumerate(
      "changed"])}
 
 WANT_SA_HIST, WANT_BUILDING_COUNTS, WANT_EVENTS, WANT_IO_MAT, TIME_KERNELS = 1, 2, 4, 8, 16
+SC_GRADUAL, SC_ALL, SC_EDU, SC_REL = 1, 2, 4, 8
+CLASS_NONRES, CLASS_EDU, CLASS_REL = 2, 4, 8
+ST_CLOSED, ST_R_BITS, ST_KNOWN_R_BITS = 28, 29, 30
 BUF_STATUS, BUF_INFECTIOUS, BUF_STATS, BUF_AGENT_REC = 0, 1, 2, 3
 PEER_HANDLE_BYTES = 128
 
@@ -64,7 +67,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach",
-           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_R_rows"]
+           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown"]
 
 _lib = None
 
@@ -114,9 +117,10 @@ def load_library():
     lib.dys_set_replica_params.argtypes = [vp, vp, vp, vp]
     lib.dys_select_replica.argtypes = [vp, i32]
     lib.dys_abort.argtypes = [vp]
+    lib.dys_set_lockdown.argtypes = [vp, i32, vp]
     lib.dys_h2d_bytes.argtypes = [vp]
     lib.dys_h2d_bytes.restype = i64
-    lib.dys_compute_R_rows.argtypes = [vp, i32, i64, i64, vp, i32, vp]
+    lib.dys_compute_r_rows.argtypes = [vp, i32, i64, i64, vp, i32, vp]
     _lib = lib
     return lib
 
@@ -151,10 +155,10 @@ def compute_R_rows(hist, pdf, recover, out=None):
         hist = hist[None, :]
     if out is None:
         out = np.empty(hist.shape[0], dtype=np.float64)
-    rc = lib.dys_compute_R_rows(hist.ctypes.data, hist.dtype.itemsize, hist.shape[0], hist.shape[1], pdf.ctypes.data, int(recover),
+    rc = lib.dys_compute_r_rows(hist.ctypes.data, hist.dtype.itemsize, hist.shape[0], hist.shape[1], pdf.ctypes.data, int(recover),
                                 out.ctypes.data)
     if rc != 0:
-        raise DysError(rc, "dys_compute_R_rows: bad argument")
+        raise DysError(rc, "dys_compute_r_rows: bad argument")
     return out
 
 
@@ -253,6 +257,13 @@ class Engine:
         """point the getters (outputs, stats, state, events ...) and set_state at replica r (-1: all / replica 0)"""
         self._ck(self.lib.dys_select_replica(self.h, int(r)))
         self._views = {}
+
+    def set_lockdown(self, scenario_bits, bld_class=None):
+        """decide the open flags on the device from now on (dys_set_lockdown); scenario_bits = 0 switches it off"""
+        p = None
+        if bld_class is not None:
+            p, _keep = _ptr(np.ascontiguousarray(bld_class, dtype=np.uint8), None, self.pop.B)
+        self._ck(self.lib.dys_set_lockdown(self.h, int(scenario_bits), p))
 
     def abort(self):
         self._ck(self.lib.dys_abort(self.h))

@@ -10,6 +10,7 @@ is O(B) bookkeeping and stays on the host.
 """
 import numpy as np
 
+from . import engine as _engine
 from .engine import HIST0, HIST_LEN, STAT, Engine
 from .population import EpiParams, Population
 
@@ -36,16 +37,21 @@ def compute_R_rows(sa_hist, pdf, recover):
     return np.where(sum_I > 0, new / np.where(sum_I > 0, sum_I, 1.0), 0.0)
 
 
-def building_lockdown(lu, usg, current, sc, vR, prevVR, choice):
+def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None):
     """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
-    (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice."""
+    (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice.
+    keyed = (seed, day): the half closures of GRADUAL close each building of the class with probability 1/2 on the keyed
+    draw u(day, STREAM_LOCKDOWN, building) instead -- the host twin of the device policy (dys_set_lockdown)."""
     lockdown = np.ones(len(lu))
     edu = np.where(np.isin(usg, EDU_CODES))[0]
     rel = np.where(np.isin(usg, REL_CODES))[0]
     non_res = np.where(lu >= 3)[0]
 
     def close(idx, half):
-        if half:
+        if half and keyed is not None:
+            from .philox_host import STREAM_LOCKDOWN, keyed_uniform
+            lockdown[idx[keyed_uniform(keyed[0], keyed[1], STREAM_LOCKDOWN, idx) < 0.5]] = 0
+        elif half:
             lockdown[choice(idx, replace=False, size=int(idx.size * 0.5))] = 0
         else:
             lockdown[idx] = 0
@@ -85,7 +91,7 @@ class EpidemicModel:
 
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
                  device=0, choice_seed=None, backend=None, population=None, compact=False, reduce_stats=None,
-                 upload_flags=True, keep_raw=False):
+                 upload_flags=True, keep_raw=False, lockdown='host'):
         self.params = params or EpiParams()
         self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob,
                                                                    diagnosis=self.params.diagnosis)
@@ -114,6 +120,13 @@ class EpidemicModel:
         self._b0 = p.bld_range[0] if p.bld_range else 0          # outputs cover the owned buildings / areas only
         self._s0, self._s1 = p.sa_range if p.sa_range else (0, p.S)
         self._pdf = [float(x) for x in self.params.pdf]
+        self._pdf_arr = np.ascontiguousarray(self.params.pdf, dtype=np.float64)
+        self._n_closed_cache = {}
+        try:                                     # the library's host-side helper (exact); numpy otherwise (also exact)
+            _engine.load_library()
+            self._R_rows = _engine.compute_R_rows
+        except Exception:
+            self._R_rows = lambda h, pdf, rec: compute_R_rows(np.atleast_2d(np.asarray(h)), pdf, rec)
         self._active = int(np.isin(p.status, (4, 7, 8, 10)).sum())
         if self._reduce is not None:
             self._active = int(self._reduce(np.array([[self._active] + [0] * 63], dtype=np.int64))[0, 0])
@@ -122,6 +135,21 @@ class EpidemicModel:
         self._queued = 0             # next day to queue
         closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
         self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
+        # lockdown = 'host'   phase H here, with the reference's np.random.choice (exact for every scenario)
+        #            'keyed'  phase H here, GRADUAL half closures on keyed draws (the host twin of the device policy)
+        #            'device' phase H inside the day kernel (dys_set_lockdown): no flags travel, week-long windows; exact
+        #                     for the deterministic scenarios, keyed half closures for GRADUAL
+        self.lockdown = lockdown
+        if lockdown == 'device':
+            bits = sum(b for k, b in (('GRADUAL', _engine.SC_GRADUAL), ('ALL', _engine.SC_ALL), ('EDU', _engine.SC_EDU),
+                                      ('REL', _engine.SC_REL)) if k in self.scenario)
+            cls = (np.where(p.bld_lu >= 3, _engine.CLASS_NONRES, 0) | np.where(np.isin(p.bld_usg, EDU_CODES), _engine.CLASS_EDU, 0) |
+                   np.where(np.isin(p.bld_usg, REL_CODES), _engine.CLASS_REL, 0)).astype(np.uint8)
+            if (bits & ~_engine.SC_GRADUAL) and 'DIFF' not in self.scenario:      # (DIFF: the host path mirrors the reference's KeyError)
+                self.sim.set_lockdown(bits, cls)
+                self.window = self.MAX_WINDOW
+            else:
+                self.lockdown = 'host'           # a scenario that closes nothing
 
     @property
     def open(self):
@@ -148,12 +176,17 @@ class EpidemicModel:
                 cur = self._flags_for(prev)
                 prevVR = self._known_R(prev - 1) if prev != 0 else 0
                 self._flags[day] = building_lockdown(self.pop.bld_lu, self.pop.bld_usg, cur, self.scenario,
-                                                     self._known_R(prev), prevVR, self._choice)
+                                                     self._known_R(prev), prevVR, self._choice,
+                                                     keyed=(self.params.seed, prev) if self.lockdown == 'keyed' else None)
             self._flags.pop(day - 20, None)
         return self._flags[day]
 
     def _queue(self, n):
         first = self._queued
+        if self.lockdown == 'device':            # the flags are decided inside the day kernel
+            self.sim.step_many(first, n, None)
+            self._queued += n
+            return
         flags = np.stack([self._flags_for(first + k) for k in range(n)]).astype(np.uint8)
         if self.flags_log is not None:
             for k in range(n):
@@ -172,9 +205,34 @@ class EpidemicModel:
         self._queued += n
 
     def _consume(self):
+        if self.compact:
+            return self._consume_compact()
         p, sim, day, prm = self.pop, self.sim, self.day, self.params
         res = self.outputs['Results']
-        closed_today = int((self._flags_for(day) == 0).sum())
+        st, sa_hist, bc, ev_a, ev_s = self._day_arrays(day, sort_events=True)
+        closed_today = int(st[_engine.ST_CLOSED]) if self.lockdown == 'device' else int((self._flags_for(day) == 0).sum())
+        hist = st[HIST0:HIST0 + HIST_LEN]
+        R = compute_R_from_hist(hist, self._pdf, prm.recover)
+        self._R[day] = R
+        vis_R = self._known_R(day)
+        sas = [float(x) for x in p.sa_ids]
+        res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
+        res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
+        S = self._stats_dict(st, R, vis_R, closed_today)
+        res['Stats'][day] = S
+        res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
+        mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                       # :356-366
+        if len(ev_a):
+            for a, s in zip(p.sa[ev_a], p.sa[ev_s]):
+                mat[sas[a]][sas[s]] += 1
+        res['IO_mat'][day] = mat
+        self._active = S['Active infected']
+        self.day += 1
+        return S
+
+    def _day_arrays(self, day, sort_events):
+        """the day's integer outputs: (stats[64], sa_hist[S,21], building_counts[B], infected agents, their infectors)"""
+        sim = self.sim
         if hasattr(sim, "outputs"):              # the CUDA engine: one pinned block per day, no further transfers
             o = sim.outputs(day)
             st, sa_hist, bc = o["stats"], o["sa_hist"], o["building_counts"]
@@ -185,53 +243,70 @@ class EpidemicModel:
                     self._gstats = dict(zip(days, g))
                 st = self._gstats.pop(day)
             ev = o["events"]
-            order = np.argsort(ev[:, 0], kind="stable")
-            ev_a, ev_s = ev[order, 0], ev[order, 1]
-        else:
-            st, sa_hist, bc = sim.stats(day), sim.sa_hist(day), sim.building_counts(day)
-            ev_a, ev_s = sim.events(day)
+            if sort_events:
+                order = np.argsort(ev[:, 0], kind="stable")
+                return st, sa_hist, bc, ev[order, 0], ev[order, 1]
+            return st, sa_hist, bc, ev[:, 0], ev[:, 1]
+        ev_a, ev_s = sim.events(day)
+        return sim.stats(day), sim.sa_hist(day), sim.building_counts(day), ev_a, ev_s
+
+    def _stats_dict(self, st, R, vis_R, closed_today):
+        day, res = self.day, self.outputs['Results']
         if self.raw_stats is not None:
             self.raw_stats[day] = np.array(st)
-        hist = st[HIST0:HIST0 + HIST_LEN]
-        R = compute_R_from_hist(hist, self._pdf, prm.recover)
-        self._R[day] = R
-        vis_R = self._known_R(day)
-        if self.compact:
-            R_sa = compute_R_rows(np.asarray(sa_hist)[:self._s1 - self._s0], self._pdf, prm.recover)
-            res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - prm.diagnosis]['R'] if day > prm.diagnosis else np.zeros(len(R_sa))}
-        else:
-            sas = [float(x) for x in p.sa_ids]
-            res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
-            res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
-        new_infections = int(st[STAT['daily_inf']])
-        S = {'Active infected': int(st[STAT['active']]), 'Daily infections': new_infections,
-             'Recovered': int(st[STAT['recovered']]), 'Quarantined': int(st[STAT['quarantined']]),
-             'Daily quarantined': int(st[STAT['daily_quar']]), 'Hospitalized': int(st[STAT['hosp']]),
-             'Daily hospitalizations': int(st[STAT['daily_hosp']]), 'Total Dead': int(st[STAT['dead']]),
-             'Daily deaths': int(st[STAT['daily_deaths']]), 'R': R, 'Known R': vis_R, 'Closed buildings': closed_today}
+        v = st[:9].tolist()
+        new_infections = v[STAT['daily_inf']]
+        S = {'Active infected': v[0], 'Daily infections': new_infections, 'Recovered': v[2], 'Quarantined': v[3],
+             'Daily quarantined': v[4], 'Hospitalized': v[5], 'Daily hospitalizations': v[6], 'Total Dead': v[7],
+             'Daily deaths': v[8], 'R': R, 'Known R': vis_R, 'Closed buildings': closed_today}
         if day == 0:
             S['Total infected'] = S['Active infected']                                          # :347-348
         else:
             S['Total infected'] = res['Stats'][day - 1]['Total infected'] + new_infections
-        S['Susceptible'] = p.N_glob - S['Total infected']
-        res['Stats'][day] = S
-        if self.compact:
-            cnt = np.asarray(bc)[self._inhabited - self._b0].astype(np.float64)
-            res['Buildings'][day] = np.stack([cnt, cnt / self._bld_pop[self._inhabited]], axis=1)
-            if self._reduce is None:
-                res['IO_mat'][day] = np.stack([p.sa[ev_a], p.sa[ev_s]], axis=1) if len(ev_a) else np.zeros((0, 2), dtype=p.sa.dtype)
-            else:                                # sharded: the infector may live on another rank; keep agent indices
-                res['IO_mat'][day] = np.stack([ev_a, ev_s], axis=1)
+        S['Susceptible'] = self.pop.N_glob - S['Total infected']
+        return S
+
+    def _consume_compact(self):
+        """compact=True: the same numbers as arrays -- 'SAs'[day] = {'R': float64[S], 'vis_R': float64[S]} (owned areas),
+        'Buildings'[day] = int32[B] infected residents per owned building (buildings_table() gives the reference's
+        [count, fraction] rows), 'IO_mat'[day] = int32[n, 2] (infected, infector) agent rows (io_pairs() gives the area
+        pairs the reference counts).  The floats are formed by the library's host-side helper in the reference's order of
+        operations (dys_compute_r_rows), a few microseconds per day whatever the number of areas."""
+        p, day, prm = self.pop, self.day, self.params
+        res = self.outputs['Results']
+        st, sa_hist, bc, ev_a, ev_s = self._day_arrays(day, sort_events=False)
+        if self.lockdown == 'device':
+            closed_today = int(st[_engine.ST_CLOSED])
         else:
-            res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
-            mat = {sa: {sa2: 0 for sa2 in sas} for sa in sas}                                   # :356-366
-            if len(ev_a):
-                for a, s in zip(p.sa[ev_a], p.sa[ev_s]):
-                    mat[sas[a]][sas[s]] += 1
-            res['IO_mat'][day] = mat
+            flags = self._flags_for(day)
+            closed_today = self._n_closed_cache.get(id(flags))
+            if closed_today is None:
+                closed_today = int((flags == 0).sum())
+                self._n_closed_cache = {id(flags): closed_today}
+        R = float(self._R_rows(st[HIST0:HIST0 + HIST_LEN], self._pdf_arr, prm.recover)[0])
+        self._R[day] = R
+        R_sa = self._R_rows(np.asarray(sa_hist)[:self._s1 - self._s0], self._pdf_arr, prm.recover)
+        dz = prm.diagnosis
+        res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - dz]['R'] if day > dz else np.zeros(len(R_sa))}
+        S = self._stats_dict(st, R, self._known_R(day), closed_today)
+        res['Stats'][day] = S
+        res['Buildings'][day] = np.array(bc, dtype=np.int32)
+        res['IO_mat'][day] = np.stack([ev_a, ev_s], axis=1) if len(ev_a) else np.zeros((0, 2), dtype=np.int32)
         self._active = S['Active infected']
         self.day += 1
         return S
+
+    def buildings_table(self, day):
+        """compact mode: the reference's 'Buildings'[day] rows (contagious3.py:339-346) as [n_inhabited, 2] = infected
+        residents, fraction of the building's residents, in build[] order"""
+        cnt = self.outputs['Results']['Buildings'][day][self._inhabited - self._b0].astype(np.float64)
+        return np.stack([cnt, cnt / self._bld_pop[self._inhabited]], axis=1)
+
+    def io_pairs(self, day):
+        """compact mode: (area of the infected agent, area of its infector) of the day's infections -- what the reference's
+        IO_mat counts (contagious3.py:356-366); single-GPU populations only (an infector may live on another rank)"""
+        ev = self.outputs['Results']['IO_mat'][day]
+        return np.stack([self.pop.sa[ev[:, 0]], self.pop.sa[ev[:, 1]]], axis=1) if len(ev) else np.zeros((0, 2), dtype=self.pop.sa.dtype)
 
     # ---- the reference's output file and a resumable snapshot (SURVEY.md section 8f-4) ----
     def write_json(self, path, total_time=None):
@@ -281,7 +356,8 @@ class EpidemicModel:
         if self._queued == self.day:
             self._queue(1)
         S = self._consume()
-        self._flags_for(self.day)        # phase H for tomorrow, in the reference's order of np.random.choice calls
+        if self.lockdown != 'device':
+            self._flags_for(self.day)    # phase H for tomorrow, in the reference's order of np.random.choice calls
         return S
 
     def run(self, max_days=None, finalize=True):

@@ -83,6 +83,9 @@ enum {
     DYS_ST_HITS,             /* Bernoulli successes */
     DYS_ST_CHANGED,          /* agents whose state was rewritten today */
     DYS_ST_COUNT_S = 20,     /* [20..27]: end-of-day agents in status 1, 2, 3, 3.5, 4, 5, 6, 7 */
+    DYS_ST_CLOSED = 28,      /* device lockdown policy only: closed buildings of the day, R and Known R as IEEE double bits */
+    DYS_ST_R_BITS = 29,
+    DYS_ST_KNOWN_R_BITS = 30,
     DYS_ST_HIST0 = 32        /* [32 .. 32+20]: global days-since-infection histogram */
 };
 
@@ -154,6 +157,16 @@ int dys_set_run(dys_handle* h, double norm_factor, double compliance, uint64_t s
  * (r = -1: dys_set_state writes all replicas, getters read replica 0). */
 int dys_set_replica_params(dys_handle* h, const double* norm_factor, const double* compliance, const uint64_t* seed);
 int dys_select_replica(dys_handle* h, int32_t r);
+/* Phase H on the device (contagious3.py:57-107, 368-385).  scenario = OR of DYS_SC_* (0 switches the device policy off
+ * again); bld_class[B] = OR of DYS_CLASS_NONRES (build[:,1] >= 3), DYS_CLASS_EDU, DYS_CLASS_REL (build[:,9] in the code lists
+ * of :67-74).  From then on dys_step_many decides every day's open flags on the device from the lagged R (open_flags must be
+ * NULL) and reports 'Closed buildings', R and Known R (IEEE double bits) in stats[28..30].  Exact for the deterministic
+ * scenarios (ALL / EDU / REL); DYS_SC_GRADUAL closes each building of the class with probability 1/2 on a keyed draw where
+ * the reference draws exactly half with np.random.choice (keep the host policy + dys_step_many(open_flags) for that).
+ * Call after dys_load_population / dys_set_state, before day 0; needs 2 <= diagnosis <= 12; not in sharded mode. */
+enum { DYS_SC_GRADUAL = 1, DYS_SC_ALL = 2, DYS_SC_EDU = 4, DYS_SC_REL = 8 };
+enum { DYS_CLASS_NONRES = 2, DYS_CLASS_EDU = 4, DYS_CLASS_REL = 8 };
+int dys_set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* bld_class);
 /* asks a running launch to end at its next spin check (grid barrier / peer wait); the handle then reports
  * DYS_ERR_ABORTED until dys_set_state / dys_load_population.  Safe to call from another host thread. */
 int dys_abort(dys_handle* h);
@@ -214,7 +227,7 @@ int64_t dys_device_bytes(const dys_handle* h);
 /* compute_R (contagious3.py:29-42) on `rows` histograms held in HOST memory (int32 or int64 elements, DYS_HIST_LEN used
  * per row, rows `row_stride` elements apart): out[r] = hist[r][0] / sum_{i=1}^{recover-1} hist[r][i] * pdf[i], 0 if the sum
  * is 0 -- the reference's order of float operations, so the results compare with ==. */
-int dys_compute_R_rows(const void* hist, int32_t elem_bytes, int64_t rows, int64_t row_stride, const double* pdf,
+int dys_compute_r_rows(const void* hist, int32_t elem_bytes, int64_t rows, int64_t row_stride, const double* pdf,
                        int32_t recover, double* out);
 /* bytes of open flags uploaded host -> device by dys_step_many so far (benchmark accounting) */
 int64_t dys_h2d_bytes(const dys_handle* h);

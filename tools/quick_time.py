@@ -29,7 +29,16 @@ def main():
     from dysturbd_b200.population import EpiParams
     from dysturbd_b200.synth import COMMUNITY, synth_population
     t0 = time.perf_counter()
-    pop = synth_population(COMMUNITY * a.communities, seed=1, seeds_per_22493=a.seeds)
+    import pickle
+    cache = "/tmp/dys_pop_%d_%d.pkl" % (a.communities, a.seeds)
+    if os.path.exists(cache):
+        pop = pickle.load(open(cache, "rb"))
+    else:
+        pop = synth_population(COMMUNITY * a.communities, seed=1, seeds_per_22493=a.seeds)
+        try:
+            pickle.dump(pop, open(cache, "wb"), protocol=4)
+        except Exception:
+            pass
     t1 = time.perf_counter()
     eng = engine.Engine(pop, EpiParams(norm_factor=a.norm, seed=20201019), flags=a.flags, replicas=a.replicas)
     if a.replicas > 1:
