@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dys_api.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "dys_common.cuh"), os.path.join(HERE, "csrc", "dys_day.cuh"),
-        os.path.join(HERE, "csrc", "dys_load.cuh"), os.path.join(HERE, "csrc", "philox.cuh"),
+        os.path.join(HERE, "csrc", "dys_load.cuh"), os.path.join(HERE, "csrc", "dys_routine.cuh"), os.path.join(HERE, "csrc", "philox.cuh"),
         os.path.join(HERE, "..", "include", "dysturbd.h")]
 LIB = os.path.join(HERE, "libdysturbd.so")
 
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     env.pop("CC", None)
     env.pop("CXX", None)
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or r.returncode != 0:
+    if verbose or r.returncode != 0 or "warning #" in r.stdout:      # (e.g. #940 missing return: never build silently over it)
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building %s" % LIB)

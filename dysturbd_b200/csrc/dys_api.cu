@@ -14,6 +14,7 @@
 
 #include "dys_day.cuh"
 #include "dys_load.cuh"
+#include "dys_routine.cuh"
 
 using namespace dys;
 
@@ -279,7 +280,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         h->push_grid = (int)(n_cta < want ? n_cta : want);
         int coop = 0, per_sm_days = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_days, k_days, 256, 0) == cudaSuccess && per_sm_days > 0)
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_days, k_days<true, true>, 256, 0) == cudaSuccess && per_sm_days > 0)
             h->days_grid = per_sm_days * sms;
         if (R > 1 && h->days_grid < 2) { h->err = "replicas need the cooperative k_days launch"; rc = DYS_ERR_NOT_AVAILABLE; }
     }
@@ -1031,6 +1032,9 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     CK(h, cudaMemsetAsync(h->d_barrier, 0, 4 * sizeof(unsigned int), h->stream));
     if (h->d_work) CK(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned long long) * (size_t)h->days_grid, h->stream));
     plan.work = h->d_work;
+    // (the service block plans the cut alone: beyond a few staging chunks of pieces it would be late for the next barrier,
+    // and the equal split + stealing balances as well -- profiles/r02e_ab.txt)
+    { const char* t = getenv("DYS_PLAN_MAX"); plan.plan_max_pieces = t ? atoll(t) : 16384; }
     plan.epoch0 = h->pub_epoch;
     if (h->n_peers > 1) h->pub_epoch += (unsigned long long)n_days;      // every day of the window publishes tomorrow's bytes
     unsigned int* bar = h->d_barrier;
@@ -1040,7 +1044,11 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         if (!h->d_trace) { rc = dev_alloc(h, &h->d_trace, (int64_t)trace_words); if (rc != DYS_OK) return rc; }
         plan.trace = h->d_trace;
     }
-    CK(h, cudaLaunchCooperativeKernel((const void*)k_days, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
+    // the kernel variant: PEERS carries the exchange code, MULTI the replica views and the work stealing of long runs
+    const bool multi = h->R > 1 || (h->d_work && (c.n_pad >> 7) > 32ll * (h->days_grid - 1));
+    const void* kern = h->n_peers > 1 ? (multi ? (const void*)k_days<true, true> : (const void*)k_days<true, false>)
+                                      : (multi ? (const void*)k_days<false, true> : (const void*)k_days<false, false>);
+    CK(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
     if (open_flags) {
         CK(h, cudaEventRecord(h->ring_free[wp], h->stream));
         h->ring_used[wp] = true;
@@ -1429,5 +1437,64 @@ extern "C" int dys_peer_detach(dys_handle* h)
     h->n_peers = 1;
     h->partner_mask = 0;
     h->ib_day = -1;
+    return DYS_OK;
+}
+
+// ---- routine generation (contagious3.py:139-170): no handle needed, host arrays in, host array out ----
+extern "C" int dys_generate_routines(int device, int64_t n_agents, int64_t n_bld, int32_t V, int32_t k, const int32_t* home,
+                                     const int32_t* anchors, const int64_t* out_ptr, const int32_t* out_idx,
+                                     const int64_t* in_ptr, const int32_t* in_idx, const int64_t* near_ptr,
+                                     const int32_t* near_idx, uint64_t seed, int32_t* routine)
+{
+    if (!home || !anchors || !out_ptr || !in_ptr || !near_ptr || !routine || n_agents <= 0 || n_bld <= 0)
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_generate_routines: null or empty argument");
+    if (k < 0 || V < 1 + 3 * (k + 1) || V > 64) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_generate_routines: need 1 + 3 (k + 1) <= V <= 64");
+    for (int64_t a = 0; a < n_agents; ++a) {
+        if (home[a] < 0 || home[a] >= n_bld) return fail(nullptr, DYS_ERR_RANGE, "dys_generate_routines: home building out of range");
+        for (int s = 0; s < 3; ++s)
+            if (anchors[a * 3 + s] < -1 || anchors[a * 3 + s] >= n_bld) return fail(nullptr, DYS_ERR_RANGE, "dys_generate_routines: anchor out of range");
+    }
+    const int64_t n_out = out_ptr[n_bld], n_in = in_ptr[n_bld], n_near = near_ptr[n_agents];
+    if (n_out < 0 || n_in < 0 || n_near < 0 || (n_out && !out_idx) || (n_in && !in_idx) || (n_near && !near_idx))
+        return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_generate_routines: bad list arrays");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, DYS_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, DYS_ERR_INVALID_ARG, "device %d out of range", device);
+    cudaError_t e = cudaSetDevice(device);
+    std::vector<void*> tmp;
+    auto up = [&](const void* src, size_t bytes) -> void* {
+        void* d = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&d, bytes ? bytes : 1);
+        if (e == cudaSuccess) { tmp.push_back(d); if (bytes) e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice); }
+        return d;
+    };
+    const int32_t* d_home = (const int32_t*)up(home, 4 * (size_t)n_agents);
+    const int32_t* d_anch = (const int32_t*)up(anchors, 12 * (size_t)n_agents);
+    const int64_t* d_op = (const int64_t*)up(out_ptr, 8 * (size_t)(n_bld + 1));
+    const int32_t* d_oi = (const int32_t*)up(out_idx, 4 * (size_t)n_out);
+    const int64_t* d_ip = (const int64_t*)up(in_ptr, 8 * (size_t)(n_bld + 1));
+    const int32_t* d_ii = (const int32_t*)up(in_idx, 4 * (size_t)n_in);
+    const int64_t* d_np = (const int64_t*)up(near_ptr, 8 * (size_t)(n_agents + 1));
+    const int32_t* d_ni = (const int32_t*)up(near_idx, 4 * (size_t)n_near);
+    int32_t* d_r = nullptr;
+    int32_t* d_bad = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_r, 4 * (size_t)n_agents * V);
+    if (e == cudaSuccess) { tmp.push_back(d_r); e = cudaMalloc((void**)&d_bad, 4); }
+    if (e == cudaSuccess) { tmp.push_back(d_bad); e = cudaMemset(d_bad, 0, 4); }
+    int32_t bad = 0;
+    if (e == cudaSuccess) {
+        k_validate_lists<<<grid_for(n_bld, 256), 256>>>(d_op, d_oi, n_bld, n_bld, d_bad);
+        k_validate_lists<<<grid_for(n_bld, 256), 256>>>(d_ip, d_ii, n_bld, n_bld, d_bad);
+        k_validate_lists<<<grid_for(n_agents, 256), 256>>>(d_np, d_ni, n_agents, n_bld, d_bad);
+        e = cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess && !bad) {
+        k_routines<<<grid_for(n_agents, 128), 128>>>(n_agents, V, k, d_home, d_anch, d_op, d_oi, d_ip, d_ii, d_np, d_ni, seed, d_r);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(routine, d_r, 4 * (size_t)n_agents * V, cudaMemcpyDeviceToHost);
+    }
+    for (void* p : tmp) cudaFree(p);
+    if (e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "dys_generate_routines: %s", cudaGetErrorString(e));
+    if (bad) return fail(nullptr, DYS_ERR_RANGE, "dys_generate_routines: invalid lists (flags 0x%x: 1 pointers not monotone, 2 index out of range, 4 list not strictly ascending)", bad);
     return DYS_OK;
 }

@@ -29,6 +29,46 @@
 #ifndef DYS_PIPE_PUSH
 #define DYS_PIPE_PUSH 0
 #endif
+// The two big per-item bodies (one settled agent, one group of pushed rows), or the two block-wide phases, as real
+// functions instead of inlined code (developer switches).  Measured on B200 (profiles/r02f_ab.txt, r02g_ab.txt): every
+// non-inlined variant is 8-10 % SLOWER than inlining everything, and an L2 prefetch of the records at sweep time buys
+// nothing -- all off.
+#ifndef DYS_NOINLINE_PUSH
+#define DYS_NOINLINE_PUSH 0
+#endif
+#ifndef DYS_NOINLINE_SETTLE
+#define DYS_NOINLINE_SETTLE 0
+#endif
+// ... or, coarser: the two block-wide PHASES (settle the work list, push the frontier) as real functions, called once per
+// flush, so that each gets its own register allocation and the sweep loop around them carries no state of theirs
+#ifndef DYS_BLOCK_FNS
+#define DYS_BLOCK_FNS 0
+#endif
+#ifndef DYS_PREFETCH_REC
+#define DYS_PREFETCH_REC 0
+#endif
+#ifndef DYS_ROW_REDUX
+#define DYS_ROW_REDUX 1
+#endif
+#if DYS_BLOCK_FNS
+#undef DYS_NOINLINE_PUSH
+#undef DYS_NOINLINE_SETTLE
+#define DYS_NOINLINE_PUSH 0
+#define DYS_NOINLINE_SETTLE 0
+#define DYS_BLOCK_FN __device__ __noinline__
+#else
+#define DYS_BLOCK_FN __device__ __forceinline__
+#endif
+#if DYS_NOINLINE_PUSH
+#define DYS_PUSH_FN __device__ __noinline__
+#else
+#define DYS_PUSH_FN __device__ __forceinline__
+#endif
+#if DYS_NOINLINE_SETTLE
+#define DYS_SETTLE_FN __device__ __noinline__
+#else
+#define DYS_SETTLE_FN __device__ __forceinline__
+#endif
 
 #include "dys_common.cuh"
 
@@ -147,6 +187,7 @@ struct BlockScratch {
     long long b_lo[2];                             // the batch being swept and the one after it (first piece, pieces)
     int b_n[2];
     unsigned int n_front, n_list;
+    unsigned int push_acc[4];                      // the block's push counters: entries scanned, candidates, Bernoulli draws, successes
     unsigned int pub_cnt[8];                       // peer mode: pieces of this call whose bytes went to write target p
     unsigned int hist[HIST_LEN], ev[EV_LEN], cnt[10], acc[8];
     bool last;
@@ -186,9 +227,10 @@ __device__ __forceinline__ RowRef load_row(const DevCtx& c, const uint32_t* ent,
 }
 
 template <bool CHECK>
-__device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushWarpScratch& w, const double* __restrict__ s_pdf,
-                                           const RowRef row0, const FrontMap fmap, unsigned int (&cnt)[4])
+DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w, const double* __restrict__ s_pdf,
+                             const RowRef row0, const FrontMap fmap)
 {
+    unsigned int cnt[4] = {0u, 0u, 0u, 0u};      // entries scanned, candidates, Bernoulli draws, successes
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool any_closed = c.n_closed != 0;
@@ -198,7 +240,7 @@ __device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushW
     const uint32_t fe0 = row0.fe;
     const unsigned nz = __ballot_sync(0xffffffffu, len > 0);
     const int nr = __popc(nz);
-    if (nr == 0) return;
+    if (nr == 0) return make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();                                    // (the previous group's readers are done with the scratch)
     if (len > 0) {
         const int slot = __popc(nz & lt_mask);
@@ -221,17 +263,29 @@ __device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushW
     cnt[0] += mylen;
     // two entries per lane and step: every entry of the transposed network can be exposed (the others were left out at
     // load time), so nearly every lane draws its Bernoulli and the Philox rounds run on full warps
-    // the records of step f0 + 64 are requested before the pairs of step f0 are evaluated
+    // (DYS_PIPE_PUSH: the records of step f0 + 64 are requested before the pairs of step f0 are evaluated)
+#if DYS_PIPE_PUSH
     uint32_t fe_n[2];
     uint4 rec_n[2];
+#endif
     auto fetch = [&](const int f0, uint32_t (&fe)[2], uint4 (&rec)[2]) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int base = f0 + 32 * k, f = base + lane;
+#if DYS_ROW_REDUX
             // row of f = #rows that end at or before f (row ends are strictly increasing: empty rows were dropped)
             const int before = __popc(__ballot_sync(0xffffffffu, lane < nr && end <= base));
             const unsigned ends = __reduce_or_sync(0xffffffffu, (lane < nr && end > base && end <= base + 31) ? 1u << (end - base) : 0u);
             const int row = before + __popc(ends & ((2u << lane) - 1u));
+#else
+            int lo = 0, hi = 32;                       // off[lo] <= f < off[hi]; the last such lo is the row
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int mid = (lo + hi) >> 1;
+                if (mid < nr && w.off[mid] <= f) lo = mid; else hi = mid;
+            }
+            const int row = lo;
+#endif
             rec[k] = make_uint4(0u, 0u, 0u, 0u);       // class 0: a padding lane never passes the exposure test
             fe[k] = 0u;
             if (f < total) {
@@ -307,14 +361,16 @@ __device__ __forceinline__ void push_group(const DevCtx& c, const int day, PushW
             }
         }
     }
+    return make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
 }
 
-// the block-wide frontier of a scan push (sm.front[0 .. n_front)), dealt to the warps in groups of <= 32 rows
+// the block-wide frontier (sm.front[0 .. n_front), halo-relative index = fmap_base + rel), dealt to the warps in groups of
+// <= 32 rows; the counters go to sm.push_acc
 template <bool CHECK>
-__device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, BlockScratch& sm, const FrontMap fmap,
-                                              unsigned int (&cnt)[4])
+DYS_BLOCK_FN void push_frontier(const DevCtx& c, const int day, BlockScratch& sm, const int64_t fmap_base)
 {
-    const int wid = threadIdx.x >> 5;
+    const FrontMap fmap{fmap_base};
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = (int)sm.n_front;
     int rpg = (n + WARPS - 1) / WARPS;
     rpg = rpg < 1 ? 1 : (rpg > 32 ? 32 : rpg);
@@ -324,11 +380,18 @@ __device__ __forceinline__ void push_frontier(const DevCtx& c, const int day, Bl
         const int nb = (n - q0) < rpg ? (n - q0) : rpg;
         return load_row(c, sm.front + q0, nb, fmap);
     };
+    unsigned int cnt[4] = {0u, 0u, 0u, 0u};
     RowRef next = wid < n_groups ? rows_of(wid) : RowRef{0u, 0, 0};
     for (int g = wid; g < n_groups; g += WARPS) {
         const RowRef cur = next;
         if (g + WARPS < n_groups) next = rows_of(g + WARPS);      // the next group's row extents, in flight under this group
-        push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, cur, fmap, cnt);
+        const uint4 d = push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, cur, fmap);
+        cnt[0] += d.x; cnt[1] += d.y; cnt[2] += d.z; cnt[3] += d.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned int x = __reduce_add_sync(0xffffffffu, cnt[k]);
+        if (lane == 0 && x) atomicAdd(&sm.push_acc[k], x);
     }
 }
 
@@ -345,12 +408,16 @@ __device__ __forceinline__ void push_clear_duties(const DevCtx& c, const int r =
     if (blockIdx.x == 0 && threadIdx.x < DF_LEN) c.df_next[DF_LEN * dr + (int)threadIdx.x] = 0;
 }
 
-__device__ __forceinline__ void publish_push_counters(const DevCtx& c, BlockScratch& sm, const unsigned int (&cnt)[4])
+// the block's push counters (sm.push_acc) into the day's spread partial sums; block-synchronising
+__device__ __forceinline__ void publish_push_counters(const DevCtx& c, BlockScratch& sm)
 {
-    const int idx[4] = {ST_EDGES_SCANNED, ST_CANDIDATES, ST_EXPOSED, ST_HITS};
-    if (threadIdx.x < 8) sm.acc[threadIdx.x] = 0;
     __syncthreads();
-    block_accumulate<4>(c.part, idx, cnt, sm.acc);
+    if (threadIdx.x < 4 && sm.push_acc[threadIdx.x]) {
+        const int idx = threadIdx.x == 0 ? ST_EDGES_SCANNED : threadIdx.x == 1 ? ST_CANDIDATES : threadIdx.x == 2 ? ST_EXPOSED : ST_HITS;
+        atomicAdd(&c.part[(size_t)idx * N_SLOTS + (blockIdx.x & (N_SLOTS - 1))], (unsigned long long)sm.push_acc[threadIdx.x]);
+        sm.push_acc[threadIdx.x] = 0u;
+    }
+    __syncthreads();
 }
 
 // the block's contiguous share [lo, hi) of n items, in granules of 16
@@ -376,7 +443,7 @@ __device__ __forceinline__ void block_share(const int64_t n, const int n_blocks,
 // HALO_ONLY (peer mode inside a window): the rows of the owned agents were pushed by their blocks after the agent pass; only
 // the halo agents' bytes, which the peers stored into this GPU's buffer, are scanned -- while other blocks may still be
 // settling the day before, hence CHECK = false and no clearing duties
-template <bool HALO_ONLY>
+template <bool HALO_ONLY, bool PEERS>
 __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, BlockScratch& sm, const int n_blocks, const int wb)
 {
     constexpr bool CHECK = !HALO_ONLY;
@@ -385,8 +452,8 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
     if (!HALO_ONLY) push_clear_duties(c);
     if (tid < 64) sm.pdf[tid] = c.pdf[tid];
     if (tid == 0) sm.n_front = 0;
+    if (tid < 4) sm.push_acc[tid] = 0u;
     __syncthreads();
-    unsigned int cnt[4] = {0, 0, 0, 0};   // entries scanned, candidates, Bernoulli draws, successes
 
     // halo-relative agents [r0, r1): r0 is a multiple of 1024
     auto scan = [&](const int64_t r0, const int64_t r1) {
@@ -430,7 +497,7 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
             const int64_t s1 = s0 + BLOCK * 4;
             const unsigned nf = sm.n_front;        // read by everyone before the next step appends (barrier below)
             if (nf > FCAP - BLOCK * 4 || s1 - base > (int64_t)REL_MASK - BLOCK * 4 || s1 >= hi) {
-                if (nf) push_frontier<CHECK>(c, day, sm, FrontMap{base}, cnt);
+                if (nf) push_frontier<CHECK>(c, day, sm, base);
                 __syncthreads();
                 if (tid == 0) sm.n_front = 0;
                 base = s1;
@@ -438,7 +505,7 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
             __syncthreads();
         }
     };
-    if (c.n_peers > 1) {
+    if (PEERS && c.n_peers > 1) {
         // peer mode: the owned agents' bytes are local and final, so their rows are pushed first; the halo agents' bytes
         // were stored into this GPU's buffer by their owners, who counted what they delivered in arrive[r] (pieces + one
         // token per day): the bytes of this day are complete once epoch x expect_in[r] units have arrived.  The exchange
@@ -460,14 +527,17 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
     } else {
         scan(0, c.rt_n);
     }
-    publish_push_counters(c, sm, cnt);
+    publish_push_counters(c, sm);
     return false;
 }
 
 __global__ void __launch_bounds__(BLOCK) k_push(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
-    push_scan_body<false>(c, day, sm, (int)gridDim.x, (int)blockIdx.x);
+    __shared__ DevCtx s_c;
+    if (threadIdx.x == 0) s_c = c;
+    __syncthreads();
+    push_scan_body<false, true>(s_c, day, sm, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -496,6 +566,7 @@ struct Settled {
     uint32_t ev;         // EVB_* flags
     int k;               // days-since-infection histogram bin, or -1
     uint32_t ibn;        // tomorrow's snapshot byte
+    int infector;        // >= 0: infected today by this agent (global index)
 };
 
 // what the settle phase fetches for one agent, all of it requested before any of it is used
@@ -522,10 +593,12 @@ __device__ __forceinline__ Loaded load_agent(const DevCtx& c, const int64_t a, c
 }
 
 // one non-idle agent, start to end of day (contagious3.py:205-270 for this agent, then its share of :273-366)
-__device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
-                                                const uint32_t st, const uint32_t att, const Loaded& L, bool& infected_today,
-                                                int& infector)
+template <bool PEERS>
+DYS_SETTLE_FN Settled settle_agent(const DevCtx& c, const int day, const int64_t a, const bool any_nd,
+                                   const uint32_t st, const uint32_t att, const Loaded L)
 {
+    bool infected_today = false;
+    int infector = -1;
     uint32_t evb = 0;
     const int4 rv = L.rv;
     int16_t* const rdays = reinterpret_cast<int16_t*>(c.rec + a);       // [0] t_inf, [1] t_q, [2] t_adm
@@ -607,13 +680,13 @@ __device__ __forceinline__ Settled settle_agent(const DevCtx& c, const int day, 
     // ---- tomorrow's phase A: snapshot byte, and the households that will see a diagnosis tomorrow ----
     const uint8_t ibn = infectious_byte(x, day + 1, ti);
     if (ibn && c.write_ib) c.ib_wr[0][c.lo + a] = ibn;      // (the sweep already stored 0 for everybody)
-    if (c.n_wr > 1) remote_ib_byte(c, c.lo + a, ibn);
+    if (PEERS && c.n_wr > 1) remote_ib_byte(c, c.lo + a, ibn);
     if (in_set(M_INF, x) && day + 1 - ti == c.diagnosis) {
         const int4 rw = second_half();
         if (diagnosed_on(c, nullptr, a, x, ti, day + 1, __hiloint2double(rw.w, rw.z)))
             raise_household(c, a, rw.y, hh_size, c.att_next, c.qflag_next, c.df_next);
     }
-    return Settled{x, evb, kbin, ibn};
+    return Settled{x, evb, kbin, ibn, infected_today ? infector : -1};
 }
 
 // One block folds the spread partial sums (part[counter][slot]: one warp per counter, two coalesced loads, shuffle tree),
@@ -719,6 +792,108 @@ __device__ __forceinline__ int64_t take_result(const unsigned long long t, int& 
     return (int64_t)lo;
 }
 
+// settle_list: the block's work list (sm.list[0 .. n_list)) processed densely, one agent per thread whatever piece it came
+// from; agents that are infectious tomorrow are appended to the block's frontier (cn != null)
+template <int VARIANT, bool PEERS>
+DYS_BLOCK_FN void settle_list(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn, const int64_t a_base, const bool any_nd)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const FrontMap fmap{c.lo - c.rt_lo + a_base};
+    const int n_list = (int)sm.n_list;
+    // the next round's records are requested before this round is settled
+    uint32_t le_n = tid < n_list ? sm.list[tid] : 0u;
+    Loaded L_n;
+    L_n.mb = -1;
+    if (tid < n_list) L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
+    for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
+        const int k = k0 + tid;
+#if !DYS_PIPE_SETTLE
+        if (k0 > 0 && k < n_list) {
+            le_n = sm.list[k];
+            L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
+        }
+#endif
+        bool infected_today = false;
+        int infector = -1;
+        uint32_t ibn = 0;
+        uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
+        int kbin = -1;
+        const bool valid = k < n_list;
+        const uint32_t le = le_n;
+        const Loaded L = L_n;
+        const uint32_t rel = le & REL_MASK;
+        const int64_t a = a_base + rel;
+        const uint32_t st = valid ? (le >> 24) & 0xFu : (uint32_t)ST_PAD, att = (le >> 28) & 0x3u;
+        L_n.mb = -1;
+#if DYS_PIPE_SETTLE
+        if (k + BLOCK < n_list) {
+            le_n = sm.list[k + BLOCK];
+            L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
+        }
+#endif
+        // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim
+        // is issued as soon as the mailboxes are in, its answer is only needed when the events are written
+        const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
+        int ev_base = 0;
+        if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
+        if (valid) {
+            const Settled r = settle_agent<PEERS>(c, day, a, any_nd, st, att, L);
+            infector = r.infector;
+            infected_today = infector >= 0;
+            ibn = r.ibn;
+            kbin = r.k;
+            const uint32_t hi = hist_idx(r.x);
+            h0 = hi < 4 ? 1u << (8 * hi) : 0u;
+            h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
+            eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
+                 ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
+            eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
+                 ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
+        }
+        {
+            // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per
+            // non-zero counter from distinct lanes -- not 32 colliding atomics per counter
+            h0 = __reduce_add_sync(0xffffffffu, h0);
+            h1 = __reduce_add_sync(0xffffffffu, h1);
+            eA = __reduce_add_sync(0xffffffffu, eA);
+            eB = __reduce_add_sync(0xffffffffu, eB);
+            const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
+            const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
+            if (v) {
+                unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
+                                  : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
+                                  : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
+                                  : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
+                atomicAdd(dst, v);
+            }
+            const unsigned km = __match_any_sync(0xffffffffu, kbin);
+            if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
+        }
+        if (evm) {
+            if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
+            if (c.ev) {
+                ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
+                if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
+            }
+        }
+        if (cn) {
+            // infectious tomorrow: queue the agent's row for the block's push of day + 1
+            const bool f = (ibn & IB_INF) != 0;
+            const unsigned fm = __ballot_sync(0xffffffffu, f);
+            if (fm) {
+                int base = 0;
+                if (lane == 0) base = (int)atomicAdd(&sm.n_front, (unsigned)__popc(fm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (f) {
+                    sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
+                    prefetch_l2(cn->tptr + fmap.at(rel));
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // agent_body.  A block walks pieces of 128 agents in batches of <= 16 (two per warp), in two phases.
 //   sweep  : 4 agents per lane: one 32-bit load of the status bytes, one of the attention bytes.  An agent to whom nothing
@@ -733,22 +908,22 @@ __device__ __forceinline__ int64_t take_result(const unsigned long long t, int& 
 // VARIANT 0 = k_agent (the last block to finish folds the statistics); 3 = k_days (one block folds after the grid barrier).
 // `a_base` = first agent the block may meet (rel indices of the list and the frontier are relative to it).
 // ---------------------------------------------------------------------------------------------------------------
-template <int VARIANT>
-__device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn,
-                                           unsigned int (&push_cnt)[4], WorkSrc ws, const int64_t a_base)
+template <int VARIANT, bool PEERS>
+__device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn, WorkSrc ws,
+                                           const int64_t a_base)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     if (tid < HIST_LEN) sm.hist[tid] = 0;
     if (tid < EV_LEN) sm.ev[tid] = 0;
     if (tid < 10) sm.cnt[tid] = 0;
     if (tid == 0) {
         sm.n_list = 0; sm.n_front = 0;
         for (int p = 0; p < 8; ++p) sm.pub_cnt[p] = 0;
+        for (int p = 0; p < 4; ++p) sm.push_acc[p] = 0;
         int n;
         const int64_t lo = take_result(take_issue(ws, 2 * WARPS), n);
         sm.b_lo[0] = lo; sm.b_n[0] = n;
-        if (c.n_wr > 1) count_pub(c, sm, lo, n);
+        if (PEERS && c.n_wr > 1) count_pub(c, sm, lo, n);
     }
     if (cn && tid < 64) sm.pdf[tid] = c.pdf[tid];
     __syncthreads();
@@ -805,7 +980,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                 if (aw[r]) *reinterpret_cast<uint32_t*>(c.att + a0) = 0u;      // consumed: clean for the day after tomorrow
                 // tomorrow's snapshot byte of an idle agent is 0; the settle phase overwrites the bytes of the agents it handles
                 if (c.write_ib) *reinterpret_cast<uint32_t*>(c.ib_wr[0] + c.lo + a0) = 0u;
-                if (c.n_wr > 1) remote_ib_word(c, c.lo + a0, work);
+                if (PEERS && c.n_wr > 1) remote_ib_word(c, c.lo + a0, work);
             }
             const unsigned any = __ballot_sync(0xffffffffu, mine != 0);
             if (any) {
@@ -822,7 +997,9 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
                 for (int j = 0; j < 4; ++j)
                     if ((work >> j) & 1u) {
                         sm.list[pos++] = (rel0 + j) | (((sw[r] >> (8 * j)) & 0xFu) << 24) | (((aw[r] >> (8 * j)) & 0x3u) << 28);
+#if DYS_PREFETCH_REC
                         prefetch_l2(c.rec + a0 + j);      // the record is needed when the list is settled
+#endif
                     }
             }
         }
@@ -830,7 +1007,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             int n;
             const int64_t lo = take_result(taken, n);
             sm.b_lo[(it + 1) & 1] = lo; sm.b_n[(it + 1) & 1] = n;
-            if (c.n_wr > 1) count_pub(c, sm, lo, n);
+            if (PEERS && c.n_wr > 1) count_pub(c, sm, lo, n);
         }
         __syncthreads();
         // the next batch's words are requested before this batch is settled
@@ -852,99 +1029,11 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
         const int n_list = (int)sm.n_list;
         const bool do_settle = n_list > LTOT - SLOTS * 128 || nb_n == 0;
         if (do_settle) {
-            // the next round's records are requested before this round is settled
-            uint32_t le_n = tid < n_list ? sm.list[tid] : 0u;
-            Loaded L_n;
-            L_n.mb = -1;
-            if (tid < n_list) L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
-            for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
-                const int k = k0 + tid;
-#if !DYS_PIPE_SETTLE
-                if (k0 > 0 && k < n_list) {
-                    le_n = sm.list[k];
-                    L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
-                }
-#endif
-                bool infected_today = false;
-                int infector = -1;
-                uint32_t ibn = 0;
-                uint32_t h0 = 0, h1 = 0, eA = 0, eB = 0;       // this agent's counter contributions, 8-bit fields
-                int kbin = -1;
-                const bool valid = k < n_list;
-                const uint32_t le = le_n;
-                const Loaded L = L_n;
-                const uint32_t rel = le & REL_MASK;
-                const int64_t a = a_base + rel;
-                const uint32_t st = valid ? (le >> 24) & 0xFu : (uint32_t)ST_PAD, att = (le >> 28) & 0x3u;
-                L_n.mb = -1;
-#if DYS_PIPE_SETTLE
-                if (k + BLOCK < n_list) {
-                    le_n = sm.list[k + BLOCK];
-                    L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
-                }
-#endif
-                // today's infection events: one slot claim per warp that has any (order is arbitrary; hosts sort).  The claim
-                // is issued as soon as the mailboxes are in, its answer is only needed when the events are written
-                const unsigned evm = __ballot_sync(0xffffffffu, valid && in_set(M_SUS, st) && L.mb >= 0);
-                int ev_base = 0;
-                if (evm && c.ev && lane == 0) ev_base = atomicAdd(&c.df[DF_N_EVENTS], __popc(evm));
-                if (valid) {
-                    const Settled r = settle_agent(c, day, a, any_nd, st, att, L, infected_today, infector);
-                    ibn = r.ibn;
-                    kbin = r.k;
-                    const uint32_t hi = hist_idx(r.x);
-                    h0 = hi < 4 ? 1u << (8 * hi) : 0u;
-                    h1 = hi < 4 ? 0u : 1u << (8 * (hi - 4));
-                    eA = ((r.ev & EVB_ADM) ? 1u : 0u) | ((r.ev & EVB_DEATH) ? 1u << 8 : 0u) | ((r.ev & EVB_DAILY_INF) ? 1u << 16 : 0u) |
-                         ((r.ev & EVB_DAILY_QUAR) ? 1u << 24 : 0u);
-                    eB = ((r.ev & EVB_NEW_DIAG) ? 1u : 0u) | ((r.ev & EVB_CHANGED) ? 1u << 8 : 0u) | ((r.ev & EVB_SUS0) ? 1u << 16 : 0u) |
-                         ((r.ev & EVB_INF0) ? 1u << 24 : 0u);
-                }
-                {
-                    // the warp's counters in four REDUX (at most 32 per 8-bit field), then one shared-memory atomic per
-                    // non-zero counter from distinct lanes -- not 32 colliding atomics per counter
-                    h0 = __reduce_add_sync(0xffffffffu, h0);
-                    h1 = __reduce_add_sync(0xffffffffu, h1);
-                    eA = __reduce_add_sync(0xffffffffu, eA);
-                    eB = __reduce_add_sync(0xffffffffu, eB);
-                    const uint32_t word = lane < 4 ? h0 : lane < 8 ? h1 : lane < 12 ? eA : eB;
-                    const uint32_t v = lane < 16 ? (word >> (8 * (lane & 3))) & 0xFFu : 0u;
-                    if (v) {
-                        unsigned int* dst = lane < 8 ? &sm.cnt[lane]                                 // end-of-day status counts
-                                          : lane < 12 ? &sm.ev[lane - 8]                             // EV_ADM .. EV_DAILY_QUAR
-                                          : lane == 12 ? &sm.ev[EV_NEW_DIAG] : lane == 13 ? &sm.ev[EV_CHANGED]
-                                          : lane == 14 ? &sm.cnt[8] : &sm.cnt[9];                    // susceptible / infectious at day start
-                        atomicAdd(dst, v);
-                    }
-                    const unsigned km = __match_any_sync(0xffffffffu, kbin);
-                    if (kbin >= 0 && lane == __ffs(km) - 1) atomicAdd(&sm.hist[kbin], (unsigned)__popc(km));
-                }
-                if (evm) {
-                    if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
-                    if (c.ev) {
-                        ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
-                        if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
-                    }
-                }
-                if (cn) {
-                    // infectious tomorrow: queue the agent's row for the block's push of day + 1
-                    const bool f = (ibn & IB_INF) != 0;
-                    const unsigned fm = __ballot_sync(0xffffffffu, f);
-                    if (fm) {
-                        int base = 0;
-                        if (lane == 0) base = (int)atomicAdd(&sm.n_front, (unsigned)__popc(fm));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (f) {
-                            sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
-                            prefetch_l2(cn->tptr + fmap.at(rel));
-                        }
-                    }
-                }
-            }
+            settle_list<VARIANT, PEERS>(c, day, sm, cn, a_base, any_nd);
             __syncthreads();      // the work list is free; the frontier count is final
             if (tid == 0) sm.n_list = 0;
             if (cn && sm.n_front) {      // (a settle can add as many rows as the frontier holds: push after each)
-                push_frontier<false>(*cn, day + 1, sm, fmap, push_cnt);
+                push_frontier<false>(*cn, day + 1, sm, fmap.base);
                 __syncthreads();
                 if (tid == 0) sm.n_front = 0;
             }
@@ -962,7 +1051,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
         }
     }
     __syncthreads();
-    if (VARIANT == 3 && c.n_wr > 1) {
+    if (PEERS && VARIANT == 3 && c.n_wr > 1) {
         // peer mode: every byte of the pieces this call took has been stored (here and in the peers).  Fence at system
         // scope, then tell each peer how many pieces it received.
         unsigned int any = 0;
@@ -1003,12 +1092,14 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
 __global__ void __launch_bounds__(BLOCK) k_agent(const DevCtx c, const int day)
 {
     __shared__ BlockScratch sm;
-    unsigned int none[4] = {0, 0, 0, 0};
+    __shared__ DevCtx s_c;               // (the phases are real functions: they take the context by address)
+    if (threadIdx.x == 0) s_c = c;
+    __syncthreads();
     const int64_t n_pieces = c.n_pad >> 7;
     const int64_t per = (n_pieces + gridDim.x - 1) / gridDim.x;
     const int64_t p0 = (int64_t)blockIdx.x * per < n_pieces ? (int64_t)blockIdx.x * per : n_pieces;
     const int64_t p1 = p0 + per < n_pieces ? p0 + per : n_pieces;
-    agent_body<0>(c, day, sm, nullptr, none, WorkSrc{nullptr, 0, p0, p1}, p0 << 7);
+    agent_body<0, false>(s_c, day, sm, nullptr, WorkSrc{nullptr, 0, p0, p1}, p0 << 7);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1066,6 +1157,7 @@ struct DayPlan {
     int32_t want_sa, want_bc, want_ev;
     unsigned long long* trace;                      // developer tracing: [n_days][grid][8] globaltimer at phase boundaries, or null
     LockdownPlan ld;
+    int64_t plan_max_pieces;                        // the equal-work cut is only planned up to this many pieces (beyond: equal split + stealing)
     unsigned long long epoch0;                      // peer mode: the bytes of first_day were the epoch0-th publication
     unsigned long long* work;                       // [grid] the blocks' work words (see WorkSrc), or null: no stealing
     int32_t test_hang_block;                        // tests (DYS_TEST_HANG_BLOCK): this block leaves before the first barrier; -1 = none
@@ -1273,14 +1365,17 @@ __device__ __forceinline__ bool grid_barrier(const DevCtx& c, unsigned int* coun
     return s_abort != 0;
 }
 
+// PEERS = false: the single-GPU kernel carries none of the exchange code (16 % faster than the generic one at 1 M agents)
+// MULTI = false: one replica and runs short enough for the planned cut alone -- no replica views, no work words, no stealing
+template <bool PEERS, bool MULTI>
 __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPlan plan, unsigned int* barrier_counter)
 {
     __shared__ BlockScratch sm;
     __shared__ DevCtx s_c[2];            // today's and tomorrow's view of the context (read like kernel parameters)
     __shared__ DevCtx s_r[2];            // replicas: the same two views shifted to the replica the block is working on
     unsigned int epoch = 0;
-    const bool peers = c0.n_peers > 1;
-    const int n_rep = c0.n_rep > 1 ? c0.n_rep : 1;
+    const bool peers = PEERS && c0.n_peers > 1;
+    const int n_rep = MULTI && c0.n_rep > 1 ? c0.n_rep : 1;
     // io_mat is one buffer for the latest day: the push of day + 1 must not clear it under the agent pass of day
     const bool two_phase = c0.io_mat != nullptr;
     // Block 0 owns no agents: it folds each day's statistics and re-cuts the population after the barrier while the
@@ -1291,13 +1386,13 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     const int wb = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
     const int64_t n_pieces = c0.n_pad >> 7, n_pieces_all = n_pieces * n_rep;
     // long runs are balanced dynamically (work words + stealing), short ones by the measured cut alone
-    const bool stealing = plan.work != nullptr && gridDim.x > 1 && n_pieces_all > 32ll * n_work;
+    const bool stealing = MULTI && plan.work != nullptr && gridDim.x > 1 && n_pieces_all > 32ll * n_work;
     if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0);
     __syncthreads();
     if ((int)blockIdx.x == plan.test_hang_block) return;      // (tests: the others must time out at the barrier, not hang)
     // the view of replica r of a day: with one replica the day's view itself, no copy
     auto replica_view = [&](const DevCtx& day_view, const int slot, const int r) -> const DevCtx& {
-        if (n_rep == 1) return day_view;
+        if (!MULTI || n_rep == 1) return day_view;
         __syncthreads();                       // (everybody is done with the previous occupant of the slot)
         if (threadIdx.x == 0) { s_r[slot] = day_view; shift_replica(s_r[slot], r); }
         __syncthreads();
@@ -1317,7 +1412,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         if (k == 0 || two_phase) {
             for (int r = 0; r < n_rep; ++r) {
                 const DevCtx& cr = replica_view(c, 0, r);
-                if (push_scan_body<false>(cr, day, sm, n_work, wb)) return;
+                if (push_scan_body<false, PEERS>(cr, day, sm, n_work, wb)) return;
                 __syncthreads();
             }
             stamp(1);
@@ -1403,22 +1498,21 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                     a_base = p0 << 7;
                     ws = WorkSrc{nullptr, 0, p0, p0 + n};
                 }
-                unsigned int push_cnt[4] = {0, 0, 0, 0};
                 const DevCtx& cr = replica_view(c, 0, r);
                 const DevCtx* cnr = cn ? &replica_view(*cn, 1, r) : nullptr;
-                agent_body<3>(cr, day, sm, cnr, push_cnt, ws, a_base);
-                if (cnr) { __syncthreads(); publish_push_counters(*cnr, sm, push_cnt); }
+                agent_body<3, PEERS>(cr, day, sm, cnr, ws, a_base);
+                if (cnr) publish_push_counters(*cnr, sm);
                 __syncthreads();
             }
         }
-        if (peers) {
+        if (PEERS && peers) {
             // One token per day and partner (the partners stay within a day of each other even if no bytes travel one way),
             // then the push of the HALO agents' rows for tomorrow: their bytes arrive from the peers as those finish today's
             // agent pass.  A few blocks share it -- the halo is a community or two -- and everybody meets at the barrier.
             if (wb == 0 && threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr) atomicAdd_system(c.arrive_at[threadIdx.x], 1ull);
             const int n_halo = HALO_BLOCKS < n_work ? HALO_BLOCKS : n_work;
             if (cn && wb >= 0 && wb < n_halo) {
-                if (push_scan_body<true>(*cn, day + 1, sm, n_halo, wb)) return;
+                if (push_scan_body<true, true>(*cn, day + 1, sm, n_halo, wb)) return;
             }
         }
         stamp(3);
@@ -1434,7 +1528,8 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
             // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a
             // quiet day.  The cut made after day d is the one of day d + 3.)
-            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0) plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
+            if (c.piece_work && gridDim.x > 1 && (day & 2) == 0 && n_pieces_all <= plan.plan_max_pieces)
+                plan_cut(c.piece_work, c.bounds_plan, n_pieces_all, n_work, sm, tr);
             stamp(11);
         }
         __syncthreads();      // the fold (and tomorrow's bind) are done with today's view

@@ -246,6 +246,18 @@ int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /* [n_ranks]
  * tests of the device Philox against oracle/philox_np.py) */
 int dys_keyed_uniform_device(int device, uint64_t seed, uint32_t day, uint32_t stream, const uint32_t* a,
                              const uint32_t* b, int64_t n, double* out);
+/* Routine generation (contagious3.py:139-170) on the device: every agent's static visit list [n_agents][V], -1 padded --
+ * home, then before each anchor (anchors[a][0..2] <- agents[:,12], agents[:,18], home; -1 = NaN) up to k flexible stops, each
+ * taken on a coin flip (:150) and drawn uniformly (:155) from (in[anchor] ∩ out[current position]) ∪ near[agent] in ascending
+ * building order.  Buildings are numbered by ASCENDING ID (the order np.union1d enumerates them in); out[b] / in[b] =
+ * buildings within bld_dist FROM / TO b, near[a] = buildings within a_dist of agent a, as CSR lists with ascending indices
+ * (dysturbd_b200/routines.py derives them from the reference's shortest-path matrix).  Draws are keyed:
+ * coin = u(seed, 0, 5, a, q) >= 0.5, choice = (int)(u(seed, 0, 6, a, q) * len), q = index of the coin among the agent's coins.
+ * All pointers are HOST pointers; V >= 1 + 3 (k + 1). */
+int dys_generate_routines(int device, int64_t n_agents, int64_t n_bld, int32_t V, int32_t k, const int32_t* home,
+                          const int32_t* anchors, const int64_t* out_ptr, const int32_t* out_idx, const int64_t* in_ptr,
+                          const int32_t* in_idx, const int64_t* near_ptr, const int32_t* near_idx, uint64_t seed,
+                          int32_t* routine);
 const char* dys_version(void);
 
 #ifdef __cplusplus

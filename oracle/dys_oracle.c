@@ -355,3 +355,66 @@ int orc_day(orc_ctx* c, int32_t day)
     free(st0);
     return 0;
 }
+
+/* ---- routine generation (contagious3.py:139-170), TEST INFRASTRUCTURE like the rest of this file ----
+ * The reference walks, for every agent, its anchors (agents[:,12], agents[:,18], home) and before each one takes up to k
+ * flexible stops: a coin (np.random.randint(2), :150), then a uniform choice (:155) from
+ *     (buildings within bld_dist TO the anchor  ∩  buildings within bld_dist FROM the current position)  ∪
+ *     (buildings within a_dist of the agent)
+ * in ascending building-id order (np.intersect1d / np.union1d sort).  Here the three sets are sorted index lists
+ * (buildings renumbered by ascending id) and the draws are keyed: coin = u(seed,0,5,agent,q) >= 0.5,
+ * choice index = (int)(u(seed,0,6,agent,q) * len), q = index of the coin among the agent's coins -- what
+ * oracle/literal.py injects into the unmodified reference code (tests/golden/routines_*.npz). */
+static int64_t orc_union_pick(const int32_t* A, int64_t na, const int32_t* B, int64_t nb, const int32_t* C, int64_t nc,
+                              int64_t pick /* -1: count only */, int32_t* out)
+{
+    int64_t pa = 0, pb = 0, pc = 0, count = 0;
+    for (;;) {
+        while (pa < na && pb < nb && A[pa] != B[pb]) { if (A[pa] < B[pb]) ++pa; else ++pb; }
+        const int64_t x = (pa < na && pb < nb) ? A[pa] : INT64_MAX;
+        const int64_t y = pc < nc ? C[pc] : INT64_MAX;
+        const int64_t v = x < y ? x : y;
+        if (v == INT64_MAX) break;
+        if (count == pick) { *out = (int32_t)v; return count; }
+        ++count;
+        if (x == v) { ++pa; ++pb; }
+        if (y == v) ++pc;
+    }
+    return count;
+}
+
+int orc_routines(int64_t N, int32_t V, int32_t k, const int32_t* home, const int32_t* anchors,
+                 const int64_t* out_ptr, const int32_t* out_idx, const int64_t* in_ptr, const int32_t* in_idx,
+                 const int64_t* near_ptr, const int32_t* near_idx, uint64_t seed, int32_t* routine)
+{
+    if (V < 1 + 3 * (k + 1)) return -1;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t a = 0; a < N; ++a) {
+        int32_t* r = routine + a * V;
+        for (int s = 0; s < V; ++s) r[s] = -1;
+        int32_t cur = home[a];
+        int nv = 0, q = 0;
+        r[nv++] = cur;
+        const int32_t* C = near_idx + near_ptr[a];
+        const int64_t nc = near_ptr[a + 1] - near_ptr[a];
+        for (int s = 0; s < 3; ++s) {
+            const int32_t i = anchors[a * 3 + s];
+            if (i < 0) continue;                                     /* NaN anchor, :147 */
+            for (int j = 0; j < k; ++j, ++q) {
+                if (!(orc_keyed_uniform(seed, 0, 5, (uint32_t)a, (uint32_t)q) >= 0.5)) continue;     /* :150 */
+                const int32_t* A = in_idx + in_ptr[i];
+                const int32_t* B = out_idx + out_ptr[cur];
+                const int64_t na = in_ptr[i + 1] - in_ptr[i], nb = out_ptr[cur + 1] - out_ptr[cur];
+                const int64_t len = orc_union_pick(A, na, B, nb, C, nc, -1, 0);
+                const double u = orc_keyed_uniform(seed, 0, 6, (uint32_t)a, (uint32_t)q);
+                int32_t dest = cur;
+                orc_union_pick(A, na, B, nb, C, nc, (int64_t)(u * (double)len), &dest);                 /* :155 */
+                cur = dest;
+                r[nv++] = cur;
+            }
+            cur = i;                                                 /* :160-161 */
+            r[nv++] = cur;
+        }
+    }
+    return 0;
+}

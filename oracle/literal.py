@@ -76,9 +76,44 @@ def subsample_csv(out_dir, n_households, seed, force_households=()):
     return ind_path, os.path.join(REFERENCE_DIR, "Data", "bldg_with_inst_orig.csv")
 
 
-def reference_setup(ind_csv, bld_csv, seed, verbose=False):
+class _NumpyProxy:
+    def __init__(self, rnd):
+        self.random = rnd
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+class _RoutineRandom:
+    """Stands in for `np.random` / `random.choice` inside the exec'd SETUP slice when the routine draws are injected
+    (contagious3.py:150 `np.random.randint(2)`, :155 `choice(union)`).  Keyed on WHAT the draw is for: agent row n and
+    the index q of the coin among that agent's coins; the choice that follows a successful coin shares its q.
+        coin   = 1 if u(seed, 0, STREAM_ROUTINE_COIN,   n, q) >= 0.5 else 0
+        choice = union[int(u(seed, 0, STREAM_ROUTINE_CHOICE, n, q) * len(union))]"""
+    STREAM_COIN, STREAM_CHOICE = 5, 6
+
+    def __init__(self, ns, seed):
+        from . import philox_np
+        self.ns, self.seed, self.p = ns, seed, philox_np
+        self.agent, self.q = None, -1
+
+    def randint(self, high):
+        assert high == 2
+        n = self.ns["n"]
+        if n != self.agent:
+            self.agent, self.q = n, -1
+        self.q += 1
+        return int(self.p.keyed_uniform(self.seed, 0, self.STREAM_COIN, np.array([n]), self.q)[0] >= 0.5)
+
+    def choice(self, seq):
+        u = self.p.keyed_uniform(self.seed, 0, self.STREAM_CHOICE, np.array([self.ns["n"]]), self.q)[0]
+        return seq[int(u * len(seq))]
+
+
+def reference_setup(ind_csv, bld_csv, seed, verbose=False, routine_seed=None):
     """create_data + contagious3.py:119-170, literally.  Returns dict(agents, households, build,
-    bld_visits_by_agents, interaction_prob, timings)."""
+    bld_visits_by_agents, interaction_prob, timings).  routine_seed: inject keyed draws into the routine generation
+    (:139-170) and also return the shortest-path matrix `dists` with its `nodes` (what that code reads)."""
     parameters, crd, communities, nx = _import_reference()
     np.random.seed(seed)
     _pyrandom.seed(seed)
@@ -98,10 +133,16 @@ def reference_setup(ind_csv, bld_csv, seed, verbose=False):
         "outputs": {}, "t": _time.time(),
         "print": (print if verbose else (lambda *a, **k: None)),
     }
+    if routine_seed is not None:
+        rr = _RoutineRandom(ns, routine_seed)
+        ns["np"] = _NumpyProxy(rr)
+        ns["choice"] = rr.choice
     t0 = _time.time()
     exec(compile(setup, "contagious3.py[119:170]", "exec"), ns)
     t_setup = _time.time() - t0
+    extra = {"dists": ns["dists"], "nodes": ns["nodes"]} if routine_seed is not None else {}
     return {
+        **extra,
         "agents": ns["agents"], "households": households, "build": ns["build"],
         "bld_visits_by_agents": np.asarray(ns["bld_visits_by_agents"], dtype=np.float64),
         "interaction_prob": ns["interaction_prob"],
@@ -200,14 +241,6 @@ class _RandomProxy:
 
     def randint(self, *a, **k):
         raise RuntimeError("np.random.randint is not used by the day loop")
-
-
-class _NumpyProxy:
-    def __init__(self, rnd):
-        self.random = rnd
-
-    def __getattr__(self, name):
-        return getattr(np, name)
 
 
 SNAP_COLS = {"status": 13, "t_inf": 16, "n_inf": 17, "t_q": 19, "n_q": 20, "src_id": 21, "t_adm": 24, "n_adm": 25}

@@ -63,6 +63,22 @@ def lib():
     return _lib
 
 
+def routines(home, anchors, out_csr, in_csr, near_csr, seed, V=10, k=2):
+    """oracle/dys_oracle.c:orc_routines -- routine generation (contagious3.py:139-170) on sorted neighbourhood lists"""
+    L = lib()
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    home, anchors = c(home, np.int32), c(anchors, np.int32)
+    ptrs = [c(x[0], np.int64) for x in (out_csr, in_csr, near_csr)]
+    idxs = [c(x[1], np.int32) for x in (out_csr, in_csr, near_csr)]
+    out = np.zeros((len(home), V), dtype=np.int32)
+    L.orc_routines.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_uint64, C.c_void_p]
+    rc = L.orc_routines(len(home), V, k, _p(home), _p(anchors), _p(ptrs[0]), _p(idxs[0]), _p(ptrs[1]), _p(idxs[1]),
+                        _p(ptrs[2]), _p(idxs[2]), seed, _p(out))
+    if rc != 0:
+        raise RuntimeError("orc_routines failed")
+    return out
+
+
 def max_threads():
     return int(lib().orc_max_threads())
 

@@ -90,3 +90,60 @@ def test_fused_windows_equal_single_days_at_scale():
     assert int(b.stats(day - 1)[9]) > 50_000      # a real epidemic: blocks settle and push unevenly
     a.close()
     b.close()
+
+
+def test_one_million_agents_365_days_vs_oracle(oracle_lib):
+    """BASELINE.json configs[1] at full size on the PRODUCT path: the 1 M-agent city, 365 days in week-long dys_step_many
+    windows (k_days), against the C oracle -- the integer stats and histograms of every day, the whole state after every
+    window."""
+    from dysturbd_b200 import engine
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import COMMUNITY, synth_population
+    pop = synth_population(COMMUNITY * 89, seed=1, seeds_per_22493=20)
+    prm = EpiParams(norm_factor=6.0, seed=20201019)
+    g = engine.Engine(pop, prm)
+    o = oracle_lib.OracleSim(pop, prm)
+    day = 0
+    while day < 365:
+        n = min(7, 365 - day)
+        g.step_many(day, n)
+        for d in range(day, day + n):
+            so = o.step(d)
+            out = g.outputs(d)
+            assert np.array_equal(out["stats"][:14], so[:14]), "day %d: %s vs %s" % (d, out["stats"][:14], so[:14])
+            assert np.array_equal(out["stats"][32:53], so[32:53]), "histogram day %d" % d
+            assert np.array_equal(out["sa_hist"], o.sa_hist()) and np.array_equal(out["building_counts"], o.building_counts()), d
+        day += n
+        sg, so_ = g.state(), o.state()
+        for k in sg:
+            assert np.array_equal(sg[k], so_[k]), "%s after day %d" % (k, day - 1)
+    assert int(g.stats(364)[9]) > 300_000
+    g.close()
+
+
+def test_ten_million_agents_lockdown_and_compliance_vs_oracle(oracle_lib):
+    """BASELINE.json configs[2] at full size: the 10 M-agent metro under ['GRADUAL', 'ALL'] with quarantine compliance 0.7,
+    30 days through the documented host loop (EpidemicModel: 4-day windows, flags decided on the host every day) -- the CUDA
+    engine against the same loop over the C oracle: every day's Stats and the final state."""
+    from dysturbd_b200.host import EpidemicModel
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import COMMUNITY, synth_population
+    pop = synth_population(COMMUNITY * 888, seed=2, seeds_per_22493=400)      # many seeds: R crosses 1 and 2 within a month
+    prm = EpiParams(norm_factor=9.0, compliance=0.7, seed=4242)
+    sc = ["GRADUAL", "ALL"]
+    a = EpidemicModel(None, None, None, None, scenario=sc, params=prm, population=pop, compact=True, choice_seed=5)
+    b = EpidemicModel(None, None, None, None, scenario=sc, params=prm, population=pop, compact=True, choice_seed=5,
+                      backend=oracle_lib.OracleSim)
+    a.run(max_days=30, finalize=False)
+    b.run(max_days=30, finalize=False)
+    sa, sb = a.outputs["Results"]["Stats"], b.outputs["Results"]["Stats"]
+    assert len(sa) == len(sb) == 30
+    for d in range(30):
+        assert sa[d] == sb[d], (d, sa[d], sb[d])
+        assert np.array_equal(a.outputs["Results"]["SAs"][d]["R"], b.outputs["Results"]["SAs"][d]["R"]), d
+        assert np.array_equal(a.outputs["Results"]["Buildings"][d], b.outputs["Results"]["Buildings"][d]), d
+    assert max(s["Closed buildings"] for s in sa.values()) > 0 and sa[29]["Quarantined"] > 0
+    xa, xb = a.sim.state(), b.sim.state()
+    for k in xa:
+        assert np.array_equal(xa[k], xb[k]), k
+    a.sim.close()
