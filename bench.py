@@ -434,8 +434,8 @@ def run_ours(args):
         achieved = per_gpu(survey_b) / (k_ms * 1e-3) / 1e9
         d_ach = per_gpu(design_b) / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm",
-                "kernel": "k_days (per simulated day: warp-granular agent pass + push of the warps' own frontiers, one grid "
-                          "barrier; one cooperative launch per %d days)" % win,
+                "kernel": "k_days (per simulated day: sweep + settle of the block's pieces, push of the block's own frontier for "
+                          "the next day, ONE grid barrier; one cooperative launch per %d days)" % win,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                 "traffic": None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum is not measurable inside this process; the ncu "

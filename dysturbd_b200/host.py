@@ -133,7 +133,8 @@ class EpidemicModel:
         self._R = {}                 # day -> R of that day (contagious3.py:281)
         self._flags = {0: self.pop.open.astype(float)}      # day -> build[:,10] in force on that day
         self._queued = 0             # next day to queue
-        closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
+        closes = self._closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
+        self._ones = np.ones(self.pop.B)
         self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
         # lockdown = 'host'   phase H here, with the reference's np.random.choice (exact for every scenario)
         #            'keyed'  phase H here, GRADUAL half closures on keyed draws (the host twin of the device policy)
@@ -168,7 +169,11 @@ class EpidemicModel:
         """phase H (contagious3.py:368-385): the flags of `day` were decided at the end of day-1 from Known R"""
         if day not in self._flags:
             prev = day - 1
-            if 'DIFF' in self.scenario:
+            if not self._closes:
+                # no ALL / EDU / REL keyword: building_lockdown closes nothing whatever R is (contagious3.py:57-107), so the
+                # flags of every day after day 0 are all ones -- known without waiting for R (week-long windows)
+                self._flags[day] = self._ones
+            elif 'DIFF' in self.scenario:
                 if prev != 0:
                     raise KeyError('Vis_R')      # the reference reads a key it never writes (:371 vs :319)
                 self._flags[day] = np.ones(self.pop.B)

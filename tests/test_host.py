@@ -116,3 +116,39 @@ def test_window_length_follows_the_lockdown_lag():
     assert mk(['EDU', 'REL']).window == 4
     assert mk(['ALL'], diagnosis=3).window == 2
     assert mk(['ALL'], diagnosis=1).window == 1
+
+
+def test_windowed_run_equals_daily_run(oracle_lib):
+    """EpidemicModel.run() queues whole windows of days ahead of the day it consumes (two windows in flight, resumable
+    with finalize=False).  Over a backend that offers step_many (here the C oracle behind a window adapter) it must produce
+    exactly what the day-by-day loop produces -- for a scenario that closes nothing (week-long windows: the flags must not
+    wait for R) and for a lockdown scenario (4-day windows)."""
+    from dysturbd_b200.host import EpidemicModel
+
+    class Windowed(oracle_lib.OracleSim):
+        def step_many(self, first, n, flags=None):
+            self._out = getattr(self, "_out", {})
+            for k in range(n):
+                if flags is not None:
+                    self.set_open(flags[k])
+                self.step(first + k)
+                a, s = self.events()
+                ev = np.stack([a, s], 1) if len(a) else np.zeros((0, 2), np.int32)
+                self._out[first + k] = dict(stats=self.stats(), sa_hist=self.sa_hist(), building_counts=self.building_counts(),
+                                            events=ev, n_events=len(a))
+
+        def outputs(self, d):
+            return self._out[d]
+
+    pop = synth_population(COMMUNITY * 2, seed=2, seeds_per_22493=400)
+    prm = EpiParams(norm_factor=6.0, seed=1)
+    for sc, win in ((["noLockdown"], 7), (["GRADUAL", "ALL"], 4)):
+        a = EpidemicModel(None, None, None, None, scenario=sc, params=prm, population=pop, compact=True, choice_seed=5, backend=Windowed)
+        assert a.window == win
+        a.run(max_days=5, finalize=False)
+        a.run(max_days=40, finalize=False)
+        b = EpidemicModel(None, None, None, None, scenario=sc, params=prm, population=pop, compact=True, choice_seed=5,
+                          backend=oracle_lib.OracleSim)
+        b.run(max_days=40, finalize=False)
+        assert a.outputs["Results"]["Stats"] == b.outputs["Results"]["Stats"], sc
+        assert a.day == b.day == 40
