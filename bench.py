@@ -535,27 +535,32 @@ def run_extras(args, pop, prm, local, stream_of):
         e.close()
     except engine.DysError as ex:
         out["batched_replicas"] = {"error": str(ex)}
-    try:
-        e = engine.Engine(pop, prm, device=local)
-        ts = []
-        for _ in range(3):
-            e.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
-            m = EpidemicModel(None, None, None, None, scenario=["GRADUAL", "ALL"], params=prm, population=pop, compact=True,
-                              backend=lambda p_, q_: e, choice_seed=7)
-            m.run(max_days=W, finalize=False)
-            b0 = e.h2d_bytes()
-            t = time.perf_counter()
-            m.run(max_days=W + K, finalize=False)
-            ts.append((time.perf_counter() - t) / max(1, m.day - W))
-            h2d = (e.h2d_bytes() - b0) / max(1, m.day - W)
-            closed = max(s["Closed buildings"] for s in m.outputs["Results"]["Stats"].values())
-        out["e2e_lockdown"] = {"scenario": "GRADUAL,ALL", "days": K, "value": pop.N / float(np.median(ts)), "unit": "agent-days/s",
-                               "ms_per_step": float(np.median(ts)) * 1e3, "h2d_bytes_per_step": h2d,
-                               "max_closed_buildings": int(closed), "window_days": m.window,
-                               "api": "EpidemicModel(compact=True, scenario=['GRADUAL','ALL']).run()"}
-        e.close()
-    except engine.DysError as ex:
-        out["e2e_lockdown"] = {"error": str(ex)}
+    for key, mode in (("e2e_lockdown", "host"), ("e2e_lockdown_device", "device")):
+        try:
+            e = engine.Engine(pop, prm, device=local)
+            ts = []
+            for _ in range(3):
+                e.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
+                m = EpidemicModel(None, None, None, None, scenario=["GRADUAL", "ALL"], params=prm, population=pop, compact=True,
+                                  backend=lambda p_, q_: e, choice_seed=7, lockdown=mode)
+                m.run(max_days=W, finalize=False)
+                b0 = e.h2d_bytes()
+                t = time.perf_counter()
+                m.run(max_days=W + K, finalize=False)
+                ts.append((time.perf_counter() - t) / max(1, m.day - W))
+                h2d = (e.h2d_bytes() - b0) / max(1, m.day - W)
+                closed = max(s["Closed buildings"] for s in m.outputs["Results"]["Stats"].values())
+            out[key] = {"scenario": "GRADUAL,ALL", "policy": mode, "days": K, "value": pop.N / float(np.median(ts)), "unit": "agent-days/s",
+                        "ms_per_step": float(np.median(ts)) * 1e3, "h2d_bytes_per_step": h2d,
+                        "max_closed_buildings": int(closed), "window_days": m.window,
+                        "api": "EpidemicModel(compact=True, scenario=['GRADUAL','ALL'], lockdown='%s').run()" % mode,
+                        "what": ("phase H on the host with the reference's np.random.choice: 4-day windows, the flags travel"
+                                 if mode == "host" else
+                                 "phase H inside the day kernel (dys_set_lockdown; keyed half closures): week-long windows, no "
+                                 "flags travel")}
+            e.close()
+        except engine.DysError as ex:
+            out[key] = {"error": str(ex)}
     return out
 
 

@@ -135,6 +135,8 @@ static void dev_free(dys_handle* h, const void* p)
 
 static int check_abort(dys_handle* h)
 {
+    if (h->h_abort && *h->h_abort >= 1000)
+        return fail(h, DYS_ERR_ABORTED, "internal consistency check %d failed (checked build, see DYS_ASSERT in csrc/)", *h->h_abort - 1000);
     if (h->h_abort && *h->h_abort)
         return fail(h, DYS_ERR_ABORTED, "a launch was abandoned (%s); reload the state with dys_set_state",
                     *h->h_abort == 2 ? "a grid barrier or peer wait timed out: DYS_SPIN_TIMEOUT_MS" : "dys_abort");
@@ -151,7 +153,7 @@ static int copy_in(dys_handle* h, void* dst, const void* src, size_t bytes)
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
-extern "C" const char* dys_version(void) { return "dysturbd-b200 0.1 (sm_100a)"; }
+extern "C" const char* dys_version(void) { return DYS_CHECKS ? "dysturbd-b200 0.2 (sm_100a, checked build)" : "dysturbd-b200 0.2 (sm_100a)"; }
 
 extern "C" const char* dys_last_error(const dys_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -1288,14 +1290,17 @@ extern "C" int dys_compute_r_rows(const void* hist, int32_t elem_bytes, int64_t 
                                   int32_t recover, double* out)
 {
     if (!hist || !pdf || !out || rows < 0 || (elem_bytes != 4 && elem_bytes != 8) || recover < 1 || recover > HIST_LEN) return DYS_ERR_INVALID_ARG;
+    // (host code of this file is compiled with -ffp-contract=off: every product and every sum is rounded on its own)
     for (int64_t r = 0; r < rows; ++r) {
-        volatile double sum_I = 0.0;      // (volatile: every product and every sum is rounded to double on its own)
-        double first = 0.0;
-        for (int i = 0; i < recover; ++i) {
-            const double n = elem_bytes == 4 ? (double)((const int32_t*)hist)[r * row_stride + i] : (double)((const int64_t*)hist)[r * row_stride + i];
-            if (i == 0) { first = n; continue; }
-            volatile double prod = n * pdf[i];
-            sum_I = sum_I + prod;
+        double sum_I = 0.0, first;
+        if (elem_bytes == 4) {
+            const int32_t* hrow = (const int32_t*)hist + r * row_stride;
+            first = (double)hrow[0];
+            for (int i = 1; i < recover; ++i) sum_I = sum_I + (double)hrow[i] * pdf[i];
+        } else {
+            const int64_t* hrow = (const int64_t*)hist + r * row_stride;
+            first = (double)hrow[0];
+            for (int i = 1; i < recover; ++i) sum_I = sum_I + (double)hrow[i] * pdf[i];
         }
         out[r] = sum_I > 0.0 ? first / sum_I : 0.0;
     }

@@ -5,6 +5,19 @@
 
 #include "philox.cuh"
 
+// DYS_CHECKS=1 (the "checked" build, dysturbd_b200/_build.py --checked): bounds checks on every index the day kernels form
+// -- work list, frontier, edge records, mailboxes, member lists, output blocks, remote snapshot bytes, work words.  A
+// failed check stores 1000 + its code in the abort word; the launch ends at its next spin check and the host reports
+// DYS_ERR_ABORTED with the code.  (compute-sanitizer is not available on the pool these kernels are developed on.)
+#ifndef DYS_CHECKS
+#define DYS_CHECKS 0
+#endif
+#if DYS_CHECKS
+#define DYS_ASSERT(ctx, cond, code) do { if (!(cond) && (ctx).abort_word) *(ctx).abort_word = 1000 + (code); } while (0)
+#else
+#define DYS_ASSERT(ctx, cond, code) do { } while (0)
+#endif
+
 namespace dys {
 
 // reference status code (agents[:,13], contagious3.py:115-118) times two; 0 pads the arrays to 1024 agents

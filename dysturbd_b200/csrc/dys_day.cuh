@@ -97,9 +97,13 @@ __device__ __forceinline__ void att_or(uint8_t* att, int64_t a, uint32_t bit)
 __device__ __forceinline__ void raise_household(const DevCtx& c, int64_t a, int hh_slot, int hh_size, uint8_t* att, uint8_t* qflag,
                                                 int32_t* df)
 {
+    DYS_ASSERT(c, hh_slot >= 0 && hh_size >= 0 && (int64_t)hh_slot + hh_size <= c.n_loc, 6);
     for (int t = 0; t < hh_size; ++t) att_or(att, __ldg(c.hh_mem + hh_slot + t), ATT_HH);
     if (c.trig_ptr)
-        for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) qflag[c.trig_hh[t]] = 1;   // same-value byte stores
+        for (int64_t t = c.trig_ptr[a]; t < c.trig_ptr[a + 1]; ++t) {
+            DYS_ASSERT(c, c.trig_hh[t] >= 0 && c.trig_hh[t] < c.H, 7);
+            qflag[c.trig_hh[t]] = 1;                                                             // same-value byte stores
+        }
     df[DF_ANY_ND] = 1;
 }
 
@@ -113,6 +117,7 @@ __device__ __forceinline__ void remote_ib_word(const DevCtx& c, const int64_t ga
 {
     for (int p = 1; p < c.n_wr; ++p)
         if (ga0 >= c.pub_lo[p] && ga0 < c.pub_lo[p] + c.pub_n[p]) {
+            DYS_ASSERT(c, ga0 >= 0 && ga0 + 4 <= c.ib_stride, 5);
             if (!listed) *reinterpret_cast<uint32_t*>(c.ib_wr[p] + ga0) = 0u;
             else
                 for (int j = 0; j < 4; ++j)
@@ -289,6 +294,8 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
             rec[k] = make_uint4(0u, 0u, 0u, 0u);       // class 0: a padding lane never passes the exposure test
             fe[k] = 0u;
             if (f < total) {
+                DYS_ASSERT(c, row >= 0 && row < nr && f >= w.off[row], 1);
+                DYS_ASSERT(c, w.t0[row] + (f - w.off[row]) >= 0 && w.t0[row] + (f - w.off[row]) < __ldg(c.tptr + c.rt_n), 2);
                 rec[k] = __ldg(edges + (w.t0[row] + (f - w.off[row])));
                 fe[k] = w.fe[row];
             }
@@ -335,6 +342,7 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
             if (!ok_free && !ok_iso) continue;
             const uint32_t ul = rec[k].x & COL_MASK;
             const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe[k] & REL_MASK);
+            DYS_ASSERT(c, (int64_t)ul < c.n_loc && ig >= c.rt_lo && ig < c.rt_lo + c.rt_n, 3);
             if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
                 if (CHECK) {
                     const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
@@ -487,6 +495,7 @@ __device__ __forceinline__ bool push_scan_body(const DevCtx& c, const int day, B
                 for (int b = 0; b < 4; ++b) {
                     const uint32_t byte = (v >> (8 * b)) & 0xFFu;
                     if ((vm >> (8 * b)) & 0x80u) {
+                        DYS_ASSERT(c, pos < FCAP && il0 + b - base <= (int64_t)REL_MASK, 4);
                         sm.front[pos++] = (uint32_t)(il0 + b - base) | (byte << 24);
                         prefetch_l2(c.tptr + il0 + b);          // the row extent is needed when the frontier is pushed
                     }
@@ -668,6 +677,7 @@ DYS_SETTLE_FN Settled settle_agent(const DevCtx& c, const int day, const int64_t
         if (k >= 0 && k < HIST_LEN) {
             if (k == 0) evb |= EVB_DAILY_INF;
             kbin = k;
+            DYS_ASSERT(c, sa_a < c.S_out && home_a >= 0 && home_a < c.B_out, 8);
             if (c.sa_hist && sa_a >= 0) atomicAdd(&c.sa_hist[(size_t)sa_a * HIST_LEN + k], 1);
             if (c.io_mat && infected_today) {
                 // contagious3.py:356-366: row = area of today's infected, column = area of the infector
@@ -874,6 +884,7 @@ DYS_BLOCK_FN void settle_list(const DevCtx& c, const int day, BlockScratch& sm, 
             if (lane == 0) atomicAdd(&sm.ev[EV_EVENTS], (unsigned)__popc(evm));
             if (c.ev) {
                 ev_base = __shfl_sync(0xffffffffu, ev_base, 0);
+                DYS_ASSERT(c, ev_base >= 0 && ev_base + __popc(evm) <= c.n_pad, 13);
                 if (infected_today) c.ev[ev_base + __popc(evm & lt_mask)] = make_int2((int)(c.lo + a), infector);
             }
         }
@@ -886,7 +897,8 @@ DYS_BLOCK_FN void settle_list(const DevCtx& c, const int day, BlockScratch& sm, 
                 if (lane == 0) base = (int)atomicAdd(&sm.n_front, (unsigned)__popc(fm));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (f) {
-                    sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
+                    DYS_ASSERT(c, base + __popc(fm & lt_mask) < FCAP, 12);
+                sm.front[base + __popc(fm & lt_mask)] = rel | (ibn << 24);
                     prefetch_l2(cn->tptr + fmap.at(rel));
                 }
             }
@@ -944,6 +956,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
         sw[r] = aw[r] = 0;
         if (sl < b_n) {
             const int64_t a0 = ((b_lo + sl) << 7) + lane * 4;
+            DYS_ASSERT(c, b_lo >= 0 && a0 + 4 <= c.n_pad && a0 >= a_base, 10);
             sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
             aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
         }
@@ -996,6 +1009,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if ((work >> j) & 1u) {
+                        DYS_ASSERT(c, pos < LTOT && rel0 + j <= REL_MASK, 9);
                         sm.list[pos++] = (rel0 + j) | (((sw[r] >> (8 * j)) & 0xFu) << 24) | (((aw[r] >> (8 * j)) & 0x3u) << 28);
 #if DYS_PREFETCH_REC
                         prefetch_l2(c.rec + a0 + j);      // the record is needed when the list is settled
@@ -1019,6 +1033,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             sw[r] = aw[r] = 0;
             if (sl < nb_n) {
                 const int64_t a0 = ((nb_lo + sl) << 7) + lane * 4;
+                DYS_ASSERT(c, nb_lo >= 0 && a0 + 4 <= c.n_pad && a0 >= a_base, 11);
                 sw[r] = *reinterpret_cast<const uint32_t*>(c.status + a0);
                 aw[r] = *reinterpret_cast<const uint32_t*>(c.att + a0);
             }

@@ -150,14 +150,13 @@ def _ptr(x, dtype=None, n=None):
 def compute_R_rows(hist, pdf, recover, out=None):
     """compute_R (contagious3.py:29-42) for every row of an int32 / int64 [rows, >=21] histogram (host memory), by the
     library's C helper: the reference's order of float operations, bit for bit"""
-    lib = load_library()
-    hist = np.ascontiguousarray(hist)
-    if hist.ndim == 1:
-        hist = hist[None, :]
+    lib = _lib or load_library()
+    if not hist.flags.c_contiguous:
+        hist = np.ascontiguousarray(hist)
+    rows, stride = (1, hist.shape[0]) if hist.ndim == 1 else hist.shape
     if out is None:
-        out = np.empty(hist.shape[0], dtype=np.float64)
-    rc = lib.dys_compute_r_rows(hist.ctypes.data, hist.dtype.itemsize, hist.shape[0], hist.shape[1], pdf.ctypes.data, int(recover),
-                                out.ctypes.data)
+        out = np.empty(rows, dtype=np.float64)
+    rc = lib.dys_compute_r_rows(hist.ctypes.data, hist.dtype.itemsize, rows, stride, pdf.ctypes.data, int(recover), out.ctypes.data)
     if rc != 0:
         raise DysError(rc, "dys_compute_r_rows: bad argument")
     return out

@@ -135,6 +135,7 @@ class EpidemicModel:
         self._queued = 0             # next day to queue
         closes = self._closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
         self._ones = np.ones(self.pop.B)
+        self._open_window = None
         self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
         # lockdown = 'host'   phase H here, with the reference's np.random.choice (exact for every scenario)
         #            'keyed'  phase H here, GRADUAL half closures on keyed draws (the host twin of the device policy)
@@ -192,7 +193,13 @@ class EpidemicModel:
             self.sim.step_many(first, n, None)
             self._queued += n
             return
-        flags = np.stack([self._flags_for(first + k) for k in range(n)]).astype(np.uint8)
+        fl = [self._flags_for(first + k) for k in range(n)]
+        if all(f is self._ones for f in fl):     # (a scenario that closes nothing: the same all-open window every time)
+            if self._open_window is None or len(self._open_window) < n:
+                self._open_window = np.ones((self.MAX_WINDOW, self.pop.B), dtype=np.uint8)
+            flags = self._open_window[:n]
+        else:
+            flags = np.stack(fl).astype(np.uint8)
         if self.flags_log is not None:
             for k in range(n):
                 self.flags_log[first + k] = flags[k]
@@ -247,12 +254,13 @@ class EpidemicModel:
                     g = self._reduce(np.stack([sim.outputs(d)["stats"] for d in days]))
                     self._gstats = dict(zip(days, g))
                 st = self._gstats.pop(day)
-            ev = o["events"]
+            ev = self._ev_pairs = o["events"]
             if sort_events:
                 order = np.argsort(ev[:, 0], kind="stable")
                 return st, sa_hist, bc, ev[order, 0], ev[order, 1]
             return st, sa_hist, bc, ev[:, 0], ev[:, 1]
         ev_a, ev_s = sim.events(day)
+        self._ev_pairs = None
         return sim.stats(day), sim.sa_hist(day), sim.building_counts(day), ev_a, ev_s
 
     def _stats_dict(self, st, R, vis_R, closed_today):
@@ -280,6 +288,7 @@ class EpidemicModel:
         p, day, prm = self.pop, self.day, self.params
         res = self.outputs['Results']
         st, sa_hist, bc, ev_a, ev_s = self._day_arrays(day, sort_events=False)
+        ev = self._ev_pairs
         if self.lockdown == 'device':
             closed_today = int(st[_engine.ST_CLOSED])
         else:
@@ -296,7 +305,7 @@ class EpidemicModel:
         S = self._stats_dict(st, R, self._known_R(day), closed_today)
         res['Stats'][day] = S
         res['Buildings'][day] = np.array(bc, dtype=np.int32)
-        res['IO_mat'][day] = np.stack([ev_a, ev_s], axis=1) if len(ev_a) else np.zeros((0, 2), dtype=np.int32)
+        res['IO_mat'][day] = np.array(ev, dtype=np.int32) if ev is not None else np.stack([ev_a, ev_s], axis=1).astype(np.int32)
         self._active = S['Active infected']
         self.day += 1
         return S
