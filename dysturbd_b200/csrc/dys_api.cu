@@ -374,6 +374,26 @@ static int init_lockdown(dys_handle* h)
     return DYS_OK;
 }
 
+// peer mode with a boundary split runs two service blocks (fold / plan and halo push), see k_days
+static int n_service_blocks(const dys_handle* h) { return (h->n_peers > 1 && h->c.bnd_ok && h->days_grid > 8) ? 2 : 1; }
+
+// until measured costs exist the work blocks of k_days get equal runs of pieces
+static int init_cut(dys_handle* h)
+{
+    DevCtx& c = h->c;
+    if (!h->buf.bounds[0]) return DYS_OK;
+    const int n_work = h->days_grid - n_service_blocks(h);
+    const int64_t n_pieces = c.n_pad / 128 * (int64_t)h->R, per = (n_pieces + n_work - 1) / n_work;
+    std::vector<int32_t> cut((size_t)h->days_grid + 1, (int32_t)n_pieces);
+    for (int b = 0; b <= n_work; ++b) cut[(size_t)b] = (int32_t)((int64_t)b * per < n_pieces ? (int64_t)b * per : n_pieces);
+    for (int k = 0; k < 3; ++k) {
+        CK(h, cudaMemcpyAsync(h->buf.bounds[k], cut.data(), sizeof(int32_t) * cut.size(), cudaMemcpyHostToDevice, h->stream));
+        if (k < 2) CK(h, cudaMemsetAsync(h->buf.piece_work[k], 0, sizeof(uint32_t) * (size_t)n_pieces, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));      // `cut` leaves scope
+    return DYS_OK;
+}
+
 // state was (re)loaded: the snapshot, attention bytes, mailboxes, flag rings, partial sums and the cut start clean
 static int reset_day_scratch(dys_handle* h)
 {
@@ -388,17 +408,7 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaMemsetAsync(h->buf.df, 0, sizeof(int32_t) * DF_RING * DF_LEN * R, h->stream));
     CK(h, cudaMemsetAsync(h->buf.part, 0, sizeof(unsigned long long) * PART_RING * N_SLOTS * N_STATS * R, h->stream));
     CK(h, cudaMemsetAsync(c.ticket, 0, sizeof(unsigned int), h->stream));
-    if (h->buf.bounds[0]) {      // until measured costs exist the blocks of k_days get equal runs of pieces
-        const int n_work = h->days_grid - 1;
-        const int64_t n_pieces = c.n_pad / 128 * (int64_t)R, per = (n_pieces + n_work - 1) / n_work;
-        std::vector<int32_t> cut((size_t)n_work + 1);
-        for (int b = 0; b <= n_work; ++b) cut[(size_t)b] = (int32_t)((int64_t)b * per < n_pieces ? (int64_t)b * per : n_pieces);
-        for (int k = 0; k < 3; ++k) {
-            CK(h, cudaMemcpyAsync(h->buf.bounds[k], cut.data(), sizeof(int32_t) * cut.size(), cudaMemcpyHostToDevice, h->stream));
-            if (k < 2) CK(h, cudaMemsetAsync(h->buf.piece_work[k], 0, sizeof(uint32_t) * (size_t)n_pieces, h->stream));
-        }
-        CK(h, cudaStreamSynchronize(h->stream));      // `cut` leaves scope
-    }
+    { int rcut = init_cut(h); if (rcut != DYS_OK) return rcut; }
     if (h->ld.mode) { int rl = init_lockdown(h); if (rl != DYS_OK) return rl; }
     h->ib_day = -1;
     h->begun = false;
@@ -815,6 +825,19 @@ static void bind_peers(dys_handle* h)
         }
     }
     c.epoch = h->pub_epoch;
+    // boundary split: every pub range must be a prefix or a suffix of the owned range (contiguous shards of communities)
+    const int64_t n_pieces = c.n_pad >> 7;
+    int64_t a = 0, b = n_pieces;
+    bool ok = h->n_peers > 1 && p > 1;
+    for (int q = 1; q < p && ok; ++q) {
+        const int64_t lo = (c.pub_lo[q] - c.lo) >> 7, hi = lo + (c.pub_n[q] >> 7);
+        if (c.pub_n[q] == 0) continue;
+        if (lo == 0) a = hi > a ? hi : a;
+        else if (hi == n_pieces) b = lo < b ? lo : b;
+        else ok = false;
+    }
+    if (a >= b) ok = false;                        // (the whole slice is boundary: nothing to overlap with)
+    c.bnd_ok = ok ? 1 : 0; c.bnd_a = (int32_t)a; c.bnd_b = (int32_t)b;
 }
 
 // phase A on its own for `day`: the day's attention bytes / quirk flags / flag block start clean, k_snapshot raises
@@ -1424,7 +1447,8 @@ extern "C" int dys_peer_attach(dys_handle* h, int n_ranks, const void* handles /
     }
     h->n_peers = n_ranks;
     h->ib_day = -1;
-    return DYS_OK;
+    bind_peers(h);
+    return init_cut(h);          // (the number of work blocks changed)
 }
 
 extern "C" int dys_peer_detach(dys_handle* h)
@@ -1442,7 +1466,8 @@ extern "C" int dys_peer_detach(dys_handle* h)
     h->n_peers = 1;
     h->partner_mask = 0;
     h->ib_day = -1;
-    return DYS_OK;
+    bind_peers(h);
+    return init_cut(h);
 }
 
 // ---- routine generation (contagious3.py:139-170): no handle needed, host arrays in, host array out ----

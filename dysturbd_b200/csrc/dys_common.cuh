@@ -138,6 +138,10 @@ struct DevCtx {
     unsigned long long* arrive_at[8];    // write target p >= 1: the counter of this rank on that GPU
     uint32_t expect_in[8];               // units per day from rank r (0: not a partner)
     uint32_t units_out[8];               // write target p >= 1: units per day this rank delivers there (pieces + 1)
+    // the owned pieces that lie in SOME partner's halo form a prefix [0, bnd_a) and a suffix [bnd_b, n_pieces) of the owned
+    // range (shards are contiguous runs of communities): k_days settles them FIRST every day, spread over all blocks, so
+    // that their bytes reach the partners while the bulk of the day is still being processed (bnd_ok = 0: no such split)
+    int32_t bnd_ok, bnd_a, bnd_b;
     unsigned long long epoch;            // publications that preceded this day's own: the bytes this day READS were the epoch-th
     // ---- the view of ONE day (bind_day) ----
     // day-start snapshot bytes of ALL agents, double buffered by day parity: the scan push of day d reads buffer d&1, the

@@ -922,7 +922,7 @@ DYS_BLOCK_FN void settle_list(const DevCtx& c, const int day, BlockScratch& sm, 
 // ---------------------------------------------------------------------------------------------------------------
 template <int VARIANT, bool PEERS>
 __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, BlockScratch& sm, const DevCtx* cn, WorkSrc ws,
-                                           const int64_t a_base)
+                                           const int64_t a_base, const bool record_cost = true)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < HIST_LEN) sm.hist[tid] = 0;
@@ -983,7 +983,7 @@ __device__ __forceinline__ void agent_body(const DevCtx& c, const int day, Block
             const uint32_t wk = ~(idle_s | idle_r | zb(sw[r])) & 0x80808080u;         // 0x80 per agent that must be settled
             const uint32_t work = ((wk >> 7) | (wk >> 14) | (wk >> 21) | (wk >> 28)) & 0xFu;
             const int mine = __popc(work);
-            if (c.piece_work) {
+            if (c.piece_work && record_cost) {
                 // what this piece costs a block (ns, measured with DYS_TRACE): ~50 for the sweep and ~65 per agent that is
                 // settled (most of them are infectious and push a row tomorrow as well)
                 const uint32_t cost = __reduce_add_sync(0xffffffffu, 65u * mine);
@@ -1178,7 +1178,7 @@ struct DayPlan {
     int32_t test_hang_block;                        // tests (DYS_TEST_HANG_BLOCK): this block leaves before the first barrier; -1 = none
 };
 
-__device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const DayPlan& plan, const int k)
+__device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const DayPlan& plan, const int k, const int wb)
 {
     c = c0;
     bind_day(c, plan.buf, plan.first_day + k);
@@ -1204,7 +1204,7 @@ __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const
     // this block's run of pieces on that day: its cut was finished at least a day ago (plan_cut runs three days ahead), so
     // fetching it here -- while the view is built, a day early for every day but the window's first -- costs no round trip later
     const int32_t* cut = plan.buf.bounds[(plan.first_day + k) % 3];
-    if (cut && gridDim.x > 1 && blockIdx.x > 0) { c.cut_first = __ldcg(cut + blockIdx.x - 1); c.cut_last = __ldcg(cut + blockIdx.x); }
+    if (cut && gridDim.x > 1 && wb >= 0) { c.cut_first = __ldcg(cut + wb); c.cut_last = __ldcg(cut + wb + 1); }
 }
 
 // The service block re-cuts the population for the day after tomorrow: contiguous runs of pieces with equal measured
@@ -1396,13 +1396,17 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     // Block 0 owns no agents: it folds each day's statistics and re-cuts the population after the barrier while the
     // others are already in the next day.  (The FIRST block, because the warp schedulers favour the oldest warps of an
     // SM: as the youngest block it was starved by its three busy neighbours and became the one everybody waited for.)
+    // Peer mode with a boundary split: block 1 owns no agents either -- it waits for the partners' bytes and pushes the halo
+    // agents' rows for tomorrow while the work blocks are busy with the bulk of today.
+    const int n_service = (PEERS && peers && c0.bnd_ok && gridDim.x > 8) ? 2 : 1;
     const bool service = gridDim.x > 1 && blockIdx.x == 0;
-    const int n_work = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
-    const int wb = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+    const bool halo_block = n_service == 2 && blockIdx.x == 1;
+    const int n_work = gridDim.x > 1 ? (int)gridDim.x - n_service : 1;
+    const int wb = gridDim.x > 1 ? (int)blockIdx.x - n_service : 0;
     const int64_t n_pieces = c0.n_pad >> 7, n_pieces_all = n_pieces * n_rep;
     // long runs are balanced dynamically (work words + stealing), short ones by the measured cut alone
     const bool stealing = MULTI && plan.work != nullptr && gridDim.x > 1 && n_pieces_all > 32ll * n_work;
-    if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0);
+    if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0, wb);
     __syncthreads();
     if ((int)blockIdx.x == plan.test_hang_block) return;      // (tests: the others must time out at the barrier, not hang)
     // the view of replica r of a day: with one replica the day's view itself, no copy
@@ -1417,7 +1421,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         const int day = plan.first_day + k;
         const DevCtx& c = s_c[k & 1];
         const bool local_push = c0.io_mat == nullptr && k + 1 < plan.n_days;
-        if (threadIdx.x == 0 && k + 1 < plan.n_days) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1);
+        if (threadIdx.x == 0 && k + 1 < plan.n_days) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1, wb);
         __syncthreads();
         unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * TRACE_SLOTS : nullptr;
         auto stamp = [&](int i) {
@@ -1450,7 +1454,21 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 P0 = wb * per < n_pieces_all ? wb * per : n_pieces_all;
                 P1 = P0 + per < n_pieces_all ? P0 + per : n_pieces_all;
             }
-            // (one loop, one call site of agent_body: first the segments of the own run, then stolen batches)
+            int bnd_seg = 0;                    // boundary pieces this block settles first: up to two ranges
+            int64_t bnd_lo[2] = {0, 0}, bnd_hi[2] = {0, 0};
+            if (n_service == 2 && wb >= 0 && wb < n_work) {
+                // the boundary pieces (prefix [0, a) and suffix [b, n) of the owned range) are dealt to ALL work blocks and
+                // settled before anything else; the own run covers the interior only (their recorded cost stays 0, so the
+                // planned cut ignores them)
+                const int64_t a = c.bnd_a, b = c.bnd_b, nb = a + (n_pieces - b);
+                const int64_t q = (nb + n_work - 1) / n_work;
+                const int64_t i0 = (int64_t)wb * q < nb ? (int64_t)wb * q : nb, i1 = i0 + q < nb ? i0 + q : nb;
+                if (i0 < a) { bnd_lo[bnd_seg] = i0; bnd_hi[bnd_seg] = i1 < a ? i1 : a; ++bnd_seg; }
+                if (i1 > a) { bnd_lo[bnd_seg] = b + ((i0 > a ? i0 : a) - a); bnd_hi[bnd_seg] = b + (i1 - a); ++bnd_seg; }
+                P0 = P0 > a ? P0 : a;
+                P1 = P1 < b ? P1 : b;
+            }
+            // (one loop, one call site of agent_body: boundary pieces, then the segments of the own run, then stolen batches)
             int64_t P = P0;
             bool announced = false;
             const unsigned int all_done = (unsigned)(k + 1) * (unsigned)n_work;
@@ -1458,7 +1476,14 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 int r;
                 WorkSrc ws;
                 int64_t a_base;
-                if (P < P1) {
+                bool record = true;
+                if (bnd_seg > 0) {
+                    --bnd_seg;
+                    r = 0;
+                    a_base = bnd_lo[bnd_seg] << 7;
+                    ws = WorkSrc{nullptr, 0, bnd_lo[bnd_seg], bnd_hi[bnd_seg]};
+                    record = false;
+                } else if (P < P1) {
                     r = (int)(P / n_pieces);
                     const int64_t p0 = P - (int64_t)r * n_pieces;
                     const int64_t p1 = P1 - (int64_t)r * n_pieces < n_pieces ? P1 - (int64_t)r * n_pieces : n_pieces;
@@ -1515,7 +1540,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 }
                 const DevCtx& cr = replica_view(c, 0, r);
                 const DevCtx* cnr = cn ? &replica_view(*cn, 1, r) : nullptr;
-                agent_body<3, PEERS>(cr, day, sm, cnr, ws, a_base);
+                agent_body<3, PEERS>(cr, day, sm, cnr, ws, a_base, record);
                 if (cnr) publish_push_counters(*cnr, sm);
                 __syncthreads();
             }
@@ -1524,10 +1549,12 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             // One token per day and partner (the partners stay within a day of each other even if no bytes travel one way),
             // then the push of the HALO agents' rows for tomorrow: their bytes arrive from the peers as those finish today's
             // agent pass.  A few blocks share it -- the halo is a community or two -- and everybody meets at the barrier.
-            if (wb == 0 && threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr) atomicAdd_system(c.arrive_at[threadIdx.x], 1ull);
-            const int n_halo = HALO_BLOCKS < n_work ? HALO_BLOCKS : n_work;
-            if (cn && wb >= 0 && wb < n_halo) {
-                if (push_scan_body<true, true>(*cn, day + 1, sm, n_halo, wb)) return;
+            if ((n_service == 2 ? halo_block : wb == 0) && threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr)
+                atomicAdd_system(c.arrive_at[threadIdx.x], 1ull);
+            const int n_halo = n_service == 2 ? 1 : (HALO_BLOCKS < n_work ? HALO_BLOCKS : n_work);
+            const int hb = n_service == 2 ? (halo_block ? 0 : -1) : wb;
+            if (cn && hb >= 0 && hb < n_halo) {
+                if (push_scan_body<true, true>(*cn, day + 1, sm, n_halo, hb)) return;
             }
         }
         stamp(3);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""The workload of the compute-sanitizer runs (profiles/r02_sanitizer_*.txt): a 30 k-agent city through
-dys_step_many windows -- single run, two replicas in one launch, the device lockdown policy -- and, under torchrun with two
-ranks, the peer exchange fused into the window.
+"""The workload of the checked-build runs (tests/test_gpu_checked.py; compute-sanitizer where a pool allows it): a 30 k-agent
+city through dys_step_many windows -- single run, two replicas in one launch, the device lockdown policy -- and, under
+torchrun with two ranks, the peer exchange fused into the window.
   compute-sanitizer --tool racecheck|synccheck|memcheck python tools/sanitize_run.py
   compute-sanitizer --tool memcheck --target-processes all python -m torch.distributed.run --nproc-per-node 2 tools/sanitize_run.py --peer"""
 import os
@@ -18,6 +18,8 @@ def main():
     from dysturbd_b200 import engine
     from dysturbd_b200.population import EpiParams
     from dysturbd_b200.synth import COMMUNITY, synth_population
+    if "--version" in sys.argv:
+        print(engine.load_library().dys_version().decode())
     if "--peer" in sys.argv:
         import torch
         import torch.distributed as dist
