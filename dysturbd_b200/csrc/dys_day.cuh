@@ -1455,16 +1455,16 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 P1 = P0 + per < n_pieces_all ? P0 + per : n_pieces_all;
             }
             int bnd_seg = 0;                    // boundary pieces this block settles first: up to two ranges
-            int64_t bnd_lo[2] = {0, 0}, bnd_hi[2] = {0, 0};
-            if (n_service == 2 && wb >= 0 && wb < n_work) {
+            int64_t bnd_lo0 = 0, bnd_hi0 = 0, bnd_lo1 = 0, bnd_hi1 = 0;
+            if (PEERS && n_service == 2 && wb >= 0 && wb < n_work) {
                 // the boundary pieces (prefix [0, a) and suffix [b, n) of the owned range) are dealt to ALL work blocks and
                 // settled before anything else; the own run covers the interior only (their recorded cost stays 0, so the
                 // planned cut ignores them)
                 const int64_t a = c.bnd_a, b = c.bnd_b, nb = a + (n_pieces - b);
                 const int64_t q = (nb + n_work - 1) / n_work;
                 const int64_t i0 = (int64_t)wb * q < nb ? (int64_t)wb * q : nb, i1 = i0 + q < nb ? i0 + q : nb;
-                if (i0 < a) { bnd_lo[bnd_seg] = i0; bnd_hi[bnd_seg] = i1 < a ? i1 : a; ++bnd_seg; }
-                if (i1 > a) { bnd_lo[bnd_seg] = b + ((i0 > a ? i0 : a) - a); bnd_hi[bnd_seg] = b + (i1 - a); ++bnd_seg; }
+                if (i0 < a) { bnd_lo0 = i0; bnd_hi0 = i1 < a ? i1 : a; bnd_seg |= 1; }
+                if (i1 > a) { bnd_lo1 = b + ((i0 > a ? i0 : a) - a); bnd_hi1 = b + (i1 - a); bnd_seg |= 2; }
                 P0 = P0 > a ? P0 : a;
                 P1 = P1 < b ? P1 : b;
             }
@@ -1477,11 +1477,13 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                 WorkSrc ws;
                 int64_t a_base;
                 bool record = true;
-                if (bnd_seg > 0) {
-                    --bnd_seg;
+                if (PEERS && bnd_seg != 0) {
+                    const bool first = (bnd_seg & 1) != 0;
+                    const int64_t lo = first ? bnd_lo0 : bnd_lo1, hi = first ? bnd_hi0 : bnd_hi1;
+                    bnd_seg &= first ? ~1 : ~2;
                     r = 0;
-                    a_base = bnd_lo[bnd_seg] << 7;
-                    ws = WorkSrc{nullptr, 0, bnd_lo[bnd_seg], bnd_hi[bnd_seg]};
+                    a_base = lo << 7;
+                    ws = WorkSrc{nullptr, 0, lo, hi};
                     record = false;
                 } else if (P < P1) {
                     r = (int)(P / n_pieces);
