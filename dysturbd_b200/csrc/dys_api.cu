@@ -262,7 +262,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         h->off_sa = sizeof(int64_t) * N_STATS;
         h->off_bc = h->off_sa + ((p.flags & DYS_WANT_SA_HIST) ? up16(sizeof(int32_t) * (size_t)(c.S_out * HIST_LEN)) : 0);
         h->off_ev = h->off_bc + ((p.flags & DYS_WANT_BUILDING_COUNTS) ? up16(sizeof(int32_t) * (size_t)c.B_out) : 0);
-        h->ev_inline = (p.flags & DYS_WANT_EVENTS) ? (c.n_pad / 64 > 1024 ? c.n_pad / 64 : 1024) : 0;
+        h->ev_inline = (p.flags & DYS_WANT_EVENTS) ? (c.n_pad / 32 > 1024 ? c.n_pad / 32 : 1024) : 0;
         if (h->ev_inline > c.n_pad) h->ev_inline = c.n_pad;
         h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
         h->out_dev_bytes = h->off_ev + ((p.flags & DYS_WANT_EVENTS) ? sizeof(int2) * (size_t)c.n_pad : 0);
@@ -375,7 +375,7 @@ static int init_lockdown(dys_handle* h)
 }
 
 // peer mode with a boundary split runs two service blocks (fold / plan and halo push), see k_days
-static int n_service_blocks(const dys_handle* h) { return (h->n_peers > 1 && h->c.bnd_ok && h->days_grid > 8) ? 2 : 1; }
+static int n_service_blocks(const dys_handle* h) { return (h->n_peers > 1 && h->c.bnd_ok && h->days_grid > 4 * HALO_BLOCKS) ? 1 + HALO_BLOCKS : 1; }
 
 // until measured costs exist the work blocks of k_days get equal runs of pieces
 static int init_cut(dys_handle* h)
@@ -1252,8 +1252,11 @@ extern "C" int dys_get_events(dys_handle* h, int32_t day, int32_t* agent, int32_
         const int i = find_out_slot(h, day);
         if (h->steps - h->out_step[i] >= DYS_OUT_RING) return fail(h, DYS_ERR_NOT_AVAILABLE, "events of day %d beyond the first %d were overwritten", day, o.events_inline);
         rest.resize((size_t)cnt * 2);
-        rc = copy_out(h, rest.data(), h->d_out[i] + (size_t)sel_rep(h) * h->out_dev_bytes + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt);
-        if (rc != DYS_OK) return rc;
+        // (on the upload stream: the main and copy streams may hold windows queued AFTER this day, which this fetch must
+        // not wait for; the day itself is complete -- dys_get_outputs above waited for its block)
+        CK(h, cudaMemcpyAsync(rest.data(), h->d_out[i] + (size_t)sel_rep(h) * h->out_dev_bytes + h->off_ev, sizeof(int32_t) * 2 * (size_t)cnt,
+                              cudaMemcpyDeviceToHost, h->up_stream));
+        CK(h, cudaStreamSynchronize(h->up_stream));
         pairs = rest.data();
     }
     for (int64_t k = 0; k < cnt; ++k) {

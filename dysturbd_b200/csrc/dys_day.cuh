@@ -235,7 +235,7 @@ template <bool CHECK>
 DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w, const double* __restrict__ s_pdf,
                              const RowRef row0, const FrontMap fmap)
 {
-    unsigned int cnt[4] = {0u, 0u, 0u, 0u};      // entries scanned, candidates, Bernoulli draws, successes
+    unsigned int n_cand = 0u, n_expo = 0u, n_hit = 0u;      // candidates, Bernoulli draws, successes of the whole group
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool any_closed = c.n_closed != 0;
@@ -265,7 +265,6 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
     __syncwarp();
     w.off[lane] = end - mylen;
     __syncwarp();
-    cnt[0] += mylen;
     // two entries per lane and step: every entry of the transposed network can be exposed (the others were left out at
     // load time), so nearly every lane draws its Bernoulli and the Philox rounds run on full warps
     // (DYS_PIPE_PUSH: the records of step f0 + 64 are requested before the pairs of step f0 are evaluated)
@@ -327,49 +326,57 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
             const bool iso_i = (ib_i & IB_ISO) != 0;
             const bool x_iso = (cls & CLS_HH) | ((cls & CLS_HO) && !iso_i);                      // u isolated at home
             const bool x_free = x_iso | ((cls & CLS_OH) != 0) | ((cls & CLS_OO) && !iso_i);      // u moves freely
-            bool ok_free, ok_iso, iso_u = false;
+            // (the counters are warp-uniform -- a ballot and a popcount per 32 pairs on the uniform datapath -- instead of four
+            // per-lane registers carried through the loop: the day kernel lives under a 64-register cap)
+            bool ok_free, ok_iso, iso_u = false, cand;
             if (CHECK) {
                 const bool sus = in_set(M_SUS, st_u[k]);
                 iso_u = (st_u[k] == ST_QH);
-                cnt[1] += sus;
+                cand = sus;
                 ok_free = sus && !iso_u && x_free;
                 ok_iso = sus && iso_u && x_iso;
             } else {
-                cnt[1] += x_free;
+                cand = x_free;
                 ok_free = x_free;
                 ok_iso = x_iso;
             }
-            if (!ok_free && !ok_iso) continue;
-            const uint32_t ul = rec[k].x & COL_MASK;
-            const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe[k] & REL_MASK);
-            DYS_ASSERT(c, (int64_t)ul < c.n_loc && ig >= c.rt_lo && ig < c.rt_lo + c.rt_n, 3);
-            if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
-                if (CHECK) {
-                    const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
-                    ok_free = ok_free && ok;
-                    ok_iso = ok_iso && ok;
-                } else {
-                    ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
-                    ok_iso = ok_iso && exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
+            n_cand += __popc(__ballot_sync(0xffffffffu, cand));
+            bool expo = ok_free || ok_iso, hit = false;
+            if (expo) {
+                const uint32_t ul = rec[k].x & COL_MASK;
+                const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe[k] & REL_MASK);
+                DYS_ASSERT(c, (int64_t)ul < c.n_loc && ig >= c.rt_lo && ig < c.rt_lo + c.rt_n, 3);
+                if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
+                    if (CHECK) {
+                        const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
+                        ok_free = ok_free && ok;
+                        ok_iso = ok_iso && ok;
+                    } else {
+                        ok_free = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, false, iso_i);
+                        ok_iso = ok_iso && exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, true, iso_i);
+                    }
+                    expo = ok_free || ok_iso;
                 }
-                if (!ok_free && !ok_iso) continue;
+                if (expo) {
+                    // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
+                    // rounded separately (no add follows, so no FMA can form); the first product comes with the record
+                    double p = __dmul_rn(__hiloint2double((int)rec[k].w, (int)rec[k].z), s_pdf[ib_i & IB_DAYS]);
+                    p = __dmul_rn(p, c.norm_factor);
+                    if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
+                    const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
+                    if (p > u) {                                                       // :240, :248
+                        hit = true;
+                        if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
+                        if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
+                        att_or(c.att, ul, ATT_HIT);
+                    }
+                }
             }
-            ++cnt[2];
-            // contagious3.py:232-238: ((ip[u,i] * risk[u]) * pdf(days since i's infection)) * norm_factor, each product
-            // rounded separately (no add follows, so no FMA can form); the first product comes with the record
-            double p = __dmul_rn(__hiloint2double((int)rec[k].w, (int)rec[k].z), s_pdf[ib_i & IB_DAYS]);
-            p = __dmul_rn(p, c.norm_factor);
-            if (CHECK && c.pair_prob) c.pair_prob[(size_t)ug * c.n_glob + ig] = p;
-            const double u = draw(c.u_pair, ug * c.n_glob + ig, c.seed, day, STREAM_INFECTION, (uint32_t)ug, (uint32_t)ig);
-            if (p > u) {                                                           // :240, :248
-                ++cnt[3];
-                if (ok_free) atomicMax(&c.mb_any[ul], (int)ig);
-                if (ok_iso) atomicMax(&c.mb_iso[ul], (int)ig);
-                att_or(c.att, ul, ATT_HIT);
-            }
+            n_expo += __popc(__ballot_sync(0xffffffffu, expo));
+            n_hit += __popc(__ballot_sync(0xffffffffu, hit));
         }
     }
-    return make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    return make_uint4((unsigned)total, n_cand, n_expo, n_hit);      // (the same four numbers in every lane)
 }
 
 // the block-wide frontier (sm.front[0 .. n_front), halo-relative index = fmap_base + rel), dealt to the warps in groups of
@@ -396,11 +403,10 @@ DYS_BLOCK_FN void push_frontier(const DevCtx& c, const int day, BlockScratch& sm
         const uint4 d = push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, cur, fmap);
         cnt[0] += d.x; cnt[1] += d.y; cnt[2] += d.z; cnt[3] += d.w;
     }
+    if (lane == 0)      // (push_group's counts are per group, the same in every lane)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const unsigned int x = __reduce_add_sync(0xffffffffu, cnt[k]);
-        if (lane == 0 && x) atomicAdd(&sm.push_acc[k], x);
-    }
+        for (int k = 0; k < 4; ++k)
+            if (cnt[k]) atomicAdd(&sm.push_acc[k], cnt[k]);
 }
 
 // what a push of day X clears before the agent pass of day X fills it / raises into it (grid-strided, any block)
@@ -1396,11 +1402,12 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     // Block 0 owns no agents: it folds each day's statistics and re-cuts the population after the barrier while the
     // others are already in the next day.  (The FIRST block, because the warp schedulers favour the oldest warps of an
     // SM: as the youngest block it was starved by its three busy neighbours and became the one everybody waited for.)
-    // Peer mode with a boundary split: block 1 owns no agents either -- it waits for the partners' bytes and pushes the halo
-    // agents' rows for tomorrow while the work blocks are busy with the bulk of today.
-    const int n_service = (PEERS && peers && c0.bnd_ok && gridDim.x > 8) ? 2 : 1;
+    // Peer mode with a boundary split: HALO_BLOCKS more blocks own no agents either -- they wait for the partners' bytes and
+    // push the halo agents' rows for tomorrow while the work blocks are busy with the bulk of today (the halo is ~1 % of a
+    // day's push work: one block alone would be the last to reach the barrier).
+    const int n_service = (PEERS && peers && c0.bnd_ok && gridDim.x > 4 * HALO_BLOCKS) ? 1 + HALO_BLOCKS : 1;
     const bool service = gridDim.x > 1 && blockIdx.x == 0;
-    const bool halo_block = n_service == 2 && blockIdx.x == 1;
+    const bool halo_block = n_service > 1 && blockIdx.x >= 1 && (int)blockIdx.x < n_service;
     const int n_work = gridDim.x > 1 ? (int)gridDim.x - n_service : 1;
     const int wb = gridDim.x > 1 ? (int)blockIdx.x - n_service : 0;
     const int64_t n_pieces = c0.n_pad >> 7, n_pieces_all = n_pieces * n_rep;
@@ -1456,7 +1463,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             }
             int bnd_seg = 0;                    // boundary pieces this block settles first: up to two ranges
             int64_t bnd_lo0 = 0, bnd_hi0 = 0, bnd_lo1 = 0, bnd_hi1 = 0;
-            if (PEERS && n_service == 2 && wb >= 0 && wb < n_work) {
+            if (PEERS && n_service > 1 && wb >= 0 && wb < n_work) {
                 // the boundary pieces (prefix [0, a) and suffix [b, n) of the owned range) are dealt to ALL work blocks and
                 // settled before anything else; the own run covers the interior only (their recorded cost stays 0, so the
                 // planned cut ignores them)
@@ -1551,10 +1558,10 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
             // One token per day and partner (the partners stay within a day of each other even if no bytes travel one way),
             // then the push of the HALO agents' rows for tomorrow: their bytes arrive from the peers as those finish today's
             // agent pass.  A few blocks share it -- the halo is a community or two -- and everybody meets at the barrier.
-            if ((n_service == 2 ? halo_block : wb == 0) && threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr)
+            if ((n_service > 1 ? blockIdx.x == 1 : wb == 0) && threadIdx.x >= 1 && (int)threadIdx.x < c.n_wr)
                 atomicAdd_system(c.arrive_at[threadIdx.x], 1ull);
-            const int n_halo = n_service == 2 ? 1 : (HALO_BLOCKS < n_work ? HALO_BLOCKS : n_work);
-            const int hb = n_service == 2 ? (halo_block ? 0 : -1) : wb;
+            const int n_halo = HALO_BLOCKS < n_work ? HALO_BLOCKS : n_work;
+            const int hb = n_service > 1 ? (halo_block ? (int)blockIdx.x - 1 : -1) : wb;
             if (cn && hb >= 0 && hb < n_halo) {
                 if (push_scan_body<true, true>(*cn, day + 1, sm, n_halo, hb)) return;
             }

@@ -37,15 +37,18 @@ def compute_R_rows(sa_hist, pdf, recover):
     return np.where(sum_I > 0, new / np.where(sum_I > 0, sum_I, 1.0), 0.0)
 
 
-def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None):
+def building_classes(lu, usg):
+    """the three index sets building_lockdown works on (contagious3.py:63, 67-70, 74): EDU codes, REL codes, land use >= 3"""
+    return np.where(np.isin(usg, EDU_CODES))[0], np.where(np.isin(usg, REL_CODES))[0], np.where(lu >= 3)[0]
+
+
+def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None):
     """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
     (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice.
     keyed = (seed, day): the half closures of GRADUAL close each building of the class with probability 1/2 on the keyed
     draw u(day, STREAM_LOCKDOWN, building) instead -- the host twin of the device policy (dys_set_lockdown)."""
     lockdown = np.ones(len(lu))
-    edu = np.where(np.isin(usg, EDU_CODES))[0]
-    rel = np.where(np.isin(usg, REL_CODES))[0]
-    non_res = np.where(lu >= 3)[0]
+    edu, rel, non_res = classes if classes is not None else building_classes(lu, usg)
 
     def close(idx, half):
         if half and keyed is not None:
@@ -136,6 +139,7 @@ class EpidemicModel:
         closes = self._closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
         self._ones = np.ones(self.pop.B)
         self._open_window = None
+        self._classes = building_classes(self.pop.bld_lu, self.pop.bld_usg)      # (static: not recomputed every day)
         self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
         # lockdown = 'host'   phase H here, with the reference's np.random.choice (exact for every scenario)
         #            'keyed'  phase H here, GRADUAL half closures on keyed draws (the host twin of the device policy)
@@ -183,7 +187,8 @@ class EpidemicModel:
                 prevVR = self._known_R(prev - 1) if prev != 0 else 0
                 self._flags[day] = building_lockdown(self.pop.bld_lu, self.pop.bld_usg, cur, self.scenario,
                                                      self._known_R(prev), prevVR, self._choice,
-                                                     keyed=(self.params.seed, prev) if self.lockdown == 'keyed' else None)
+                                                     keyed=(self.params.seed, prev) if self.lockdown == 'keyed' else None,
+                                                     classes=self._classes)
             self._flags.pop(day - 20, None)
         return self._flags[day]
 
