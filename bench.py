@@ -202,8 +202,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the host loop's per-window sum of 64-integer stats blocks goes over gloo (host memory): a collective KERNEL would
+        # have to find room on a GPU whose SMs are all held by the persistent day kernel
+        gloo = dist.new_group(backend="gloo")
     pop, n_total = make_population(args, rank, world)
     prm = make_params(args)
     W, K, R = args.warmup, args.steps, args.replicas
@@ -261,9 +265,9 @@ def run_ours(args):
     # pass A: end to end through the documented host API (also records the flags and counters of every day)
     # ------------------------------------------------------------------------------------------------------------
     def reduce_stats(block):
-        t = torch.from_numpy(np.ascontiguousarray(block)).cuda()
-        dist.all_reduce(t)
-        return t.cpu().numpy()
+        t = torch.from_numpy(np.array(block, dtype=np.int64))
+        dist.all_reduce(t, group=gloo)
+        return t.numpy()
 
     def e2e_once(sc, collect):
         """one replay: W warm-up days and K timed days through EpidemicModel.run()"""

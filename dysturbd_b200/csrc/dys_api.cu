@@ -63,6 +63,7 @@ struct dys_handle {
     int32_t out_day[DYS_OUT_RING];
     int64_t out_step[DYS_OUT_RING];
     cudaEvent_t out_ev[DYS_OUT_RING];
+    int out_ev_of[DYS_OUT_RING];                          // the slot whose event covers this slot's copy (a window ships as one)
     std::vector<int64_t> hist_stats;                      // [DYS_STATS_RING][R][N_STATS] stats of days that left the output ring
     int32_t hist_day[DYS_STATS_RING];
     uint8_t* h_open = nullptr;                            // pinned shadow of the open flags
@@ -83,6 +84,9 @@ struct dys_handle {
     uint32_t partner_mask = 0;       // ranks this rank exchanges bytes with (either direction)
     int push_grid = 0;               // persistent grid of k_push
     int last_slot = 0;
+    bool no_steal = false;
+    bool test_hooks = false;          // DYS_TEST_HANG_BLOCK was set when the handle was created
+    int64_t plan_max = 16384;
     bool no_fuse = false;            // DYS_NO_FUSE=1 in the environment: dys_step_many launches two kernels a day
     const char* trace_path = nullptr;          // DYS_TRACE=<file> (developer): per-block phase timestamps of every fused window
     unsigned long long* d_trace = nullptr;
@@ -194,12 +198,14 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     h->p = p;
     h->device = device;
     h->R = R;
-    for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; h->out_ev[i] = nullptr; }
+    for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; h->out_ev[i] = nullptr; h->out_ev_of[i] = i; }
     for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
     h->hist_stats.assign((size_t)DYS_STATS_RING * R * N_STATS, 0);
     h->rep.assign((size_t)R, RepParam{p.norm_factor, p.compliance, p.seed});
     { const char* nf = getenv("DYS_NO_FUSE"); h->no_fuse = nf && nf[0] == '1'; }
     h->trace_path = getenv("DYS_TRACE");
+    h->test_hooks = getenv("DYS_TEST_HANG_BLOCK") != nullptr;
+    { const char* t = getenv("DYS_PLAN_MAX"); if (t) h->plan_max = atoll(t); }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -267,7 +273,9 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
         h->out_dev_bytes = h->off_ev + ((p.flags & DYS_WANT_EVENTS) ? sizeof(int2) * (size_t)c.n_pad : 0);
         c.out_stride = (int64_t)h->out_dev_bytes;
-        for (int k = 0; k < DYS_OUT_RING; ++k) A(dev_alloc(h, &h->d_out[k], (int64_t)h->out_dev_bytes * R));
+        // (one allocation: the slots of a window are neighbours, so a whole window ships in one or two 2-D copies)
+        A(dev_alloc(h, &h->d_out[0], (int64_t)h->out_dev_bytes * R * DYS_OUT_RING));
+        for (int k = 1; k < DYS_OUT_RING; ++k) h->d_out[k] = h->d_out[0] ? h->d_out[0] + (size_t)k * h->out_dev_bytes * R : nullptr;
     }
     if (p.flags & DYS_WANT_IO_MAT) A(dev_alloc(h, &c.io_mat, c.S * c.S));
     c.pdf = d_pdf;
@@ -295,9 +303,13 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         A(dev_alloc(h, &h->d_open_ring[k], (int64_t)MAX_FUSED_DAYS * c.B));
         if (rc == DYS_OK && cudaMallocHost((void**)&h->h_open_ring[k], (size_t)MAX_FUSED_DAYS * (size_t)c.B) != cudaSuccess) rc = DYS_ERR_CUDA;
     }
-    A(dev_alloc(h, &h->d_barrier, 4));
-    A(dev_alloc(h, &h->d_work, h->days_grid > 0 ? h->days_grid : 1));
-    { const char* t = getenv("DYS_NO_STEAL"); if (t && t[0] == '1') h->d_work = nullptr; }      // (developer: ablation)
+    {   // barrier counters and work words in one allocation: one memset per window
+        unsigned long long* blk = nullptr;
+        A(dev_alloc(h, &blk, 2 + (h->days_grid > 0 ? h->days_grid : 1)));
+        h->d_barrier = (unsigned int*)blk;
+        h->d_work = blk ? blk + 2 : nullptr;
+    }
+    { const char* t = getenv("DYS_NO_STEAL"); h->no_steal = t && t[0] == '1'; }      // (developer: ablation)
     if (rc == DYS_OK) {
         void* ab = nullptr;
         if (cudaHostAlloc(&ab, 64, cudaHostAllocMapped) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -375,7 +387,7 @@ static int init_lockdown(dys_handle* h)
 }
 
 // peer mode with a boundary split runs two service blocks (fold / plan and halo push), see k_days
-static int n_service_blocks(const dys_handle* h) { return (h->n_peers > 1 && h->c.bnd_ok && h->days_grid > 4 * HALO_BLOCKS) ? 1 + HALO_BLOCKS : 1; }
+static int n_service_blocks(const dys_handle* h) { return (DYS_BOUNDARY_FIRST && h->n_peers > 1 && h->c.bnd_ok && h->days_grid > 4 * HALO_BLOCKS) ? 1 + HALO_BLOCKS : 1; }
 
 // until measured costs exist the work blocks of k_days get equal runs of pieces
 static int init_cut(dys_handle* h)
@@ -927,7 +939,7 @@ static int step_begin(dys_handle* h, int32_t day, const dys_injected* inj)
 static int retire_slot(dys_handle* h, int slot)
 {
     if (h->out_day[slot] >= 0) {
-        CK(h, cudaEventSynchronize(h->out_ev[slot]));
+        CK(h, cudaEventSynchronize(h->out_ev[h->out_ev_of[slot]]));
         const int hs = (int)(h->out_step[slot] % DYS_STATS_RING);
         for (int r = 0; r < h->R; ++r)
             memcpy(&h->hist_stats[((size_t)hs * h->R + r) * N_STATS], h->h_out + ((size_t)slot * h->R + r) * h->out_copy_bytes,
@@ -947,8 +959,34 @@ static int ship_day(dys_handle* h, int32_t day, int slot, int64_t step)
     else CK(h, cudaMemcpy2DAsync(dst, h->out_copy_bytes, h->d_out[slot], h->out_dev_bytes, h->out_copy_bytes, (size_t)h->R,
                                  cudaMemcpyDeviceToHost, h->copy_stream));
     CK(h, cudaEventRecord(h->out_ev[slot], h->copy_stream));
+    h->out_ev_of[slot] = slot;
     h->out_day[slot] = day;
     h->out_step[slot] = step;
+    return DYS_OK;
+}
+
+// a window of days ships as ONE unit: one event after the launch, one or two 2-D copies (the ring may wrap), one event after
+// the copies -- 5 API calls instead of 4 per day (at 1 M agents the host has ~25 us per simulated day to keep the GPU fed)
+static int ship_window(dys_handle* h, int32_t first_day, int32_t n_days)
+{
+    const int s0 = (int)(h->steps % DYS_OUT_RING), last = (int)((h->steps + n_days - 1) % DYS_OUT_RING);
+    CK(h, cudaEventRecord(h->day_done[last], h->stream));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->day_done[last], 0));
+    for (int done = 0; done < n_days;) {
+        const int s = (s0 + done) % DYS_OUT_RING;
+        const int n = (n_days - done) < (DYS_OUT_RING - s) ? (n_days - done) : (DYS_OUT_RING - s);
+        CK(h, cudaMemcpy2DAsync(h->h_out + (size_t)s * h->R * h->out_copy_bytes, h->out_copy_bytes, h->d_out[s], h->out_dev_bytes,
+                                h->out_copy_bytes, (size_t)n * h->R, cudaMemcpyDeviceToHost, h->copy_stream));
+        done += n;
+    }
+    CK(h, cudaEventRecord(h->out_ev[last], h->copy_stream));
+    for (int k = 0; k < n_days; ++k) {
+        const int slot = (s0 + k) % DYS_OUT_RING;
+        h->out_ev_of[slot] = last;
+        h->out_day[slot] = first_day + k;
+        h->out_step[slot] = h->steps + k;
+        h->last_slot = slot;
+    }
     return DYS_OK;
 }
 
@@ -1004,7 +1042,8 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     plan.want_sa = (h->p.flags & DYS_WANT_SA_HIST) != 0;
     plan.want_bc = (h->p.flags & DYS_WANT_BUILDING_COUNTS) != 0;
     plan.want_ev = (h->p.flags & DYS_WANT_EVENTS) != 0;
-    { const char* t = getenv("DYS_TEST_HANG_BLOCK"); plan.test_hang_block = t ? atoi(t) : -1; }
+    plan.test_hang_block = -1;
+    if (h->test_hooks) { const char* t = getenv("DYS_TEST_HANG_BLOCK"); plan.test_hang_block = t ? atoi(t) : -1; }
     bind_peers(h);
     plan.buf = h->buf;
     // Open flags: the caller's vectors are this window's host input.  They are staged in one of two pinned rings (by
@@ -1054,12 +1093,11 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         if (rc != DYS_OK) return rc;
     }
     bind_day(c, h->buf, first_day);    // (k_days binds every day's view itself)
-    CK(h, cudaMemsetAsync(h->d_barrier, 0, 4 * sizeof(unsigned int), h->stream));
-    if (h->d_work) CK(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned long long) * (size_t)h->days_grid, h->stream));
-    plan.work = h->d_work;
+    CK(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned long long) * (size_t)(2 + h->days_grid), h->stream));
+    plan.work = h->no_steal ? nullptr : h->d_work;
     // (the service block plans the cut alone: beyond a few staging chunks of pieces it would be late for the next barrier,
     // and the equal split + stealing balances as well -- profiles/r02e_ab.txt)
-    { const char* t = getenv("DYS_PLAN_MAX"); plan.plan_max_pieces = t ? atoll(t) : 16384; }
+    plan.plan_max_pieces = h->plan_max;
     plan.epoch0 = h->pub_epoch;
     if (h->n_peers > 1) h->pub_epoch += (unsigned long long)n_days;      // every day of the window publishes tomorrow's bytes
     unsigned int* bar = h->d_barrier;
@@ -1070,7 +1108,7 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         plan.trace = h->d_trace;
     }
     // the kernel variant: PEERS carries the exchange code, MULTI the replica views and the work stealing of long runs
-    const bool multi = h->R > 1 || (h->d_work && (c.n_pad >> 7) > 32ll * (h->days_grid - 1));
+    const bool multi = h->R > 1 || (!h->no_steal && (c.n_pad >> 7) > 32ll * (h->days_grid - 1));
     const void* kern = h->n_peers > 1 ? (multi ? (const void*)k_days<true, true> : (const void*)k_days<true, false>)
                                       : (multi ? (const void*)k_days<false, true> : (const void*)k_days<false, false>);
     CK(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
@@ -1098,13 +1136,8 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         CK(h, cudaMemcpyAsync((void*)c.open, cur_dev, (size_t)c.B, cudaMemcpyDeviceToDevice, h->stream));
         c.n_closed = cur_closed;
     }
-    for (int k = 0; k < n_days; ++k) {
-        const int slot = (int)((h->steps + k) % DYS_OUT_RING);
-        CK(h, cudaEventRecord(h->day_done[slot], h->stream));
-        rc = ship_day(h, first_day + k, slot, h->steps + k);
-        if (rc != DYS_OK) return rc;
-        h->last_slot = slot;
-    }
+    rc = ship_window(h, first_day, n_days);
+    if (rc != DYS_OK) return rc;
     h->steps += n_days;
     h->last_day = first_day + n_days - 1;
     h->ib_day = first_day + n_days;
@@ -1163,7 +1196,7 @@ extern "C" int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out)
     if (!h || !out) return DYS_ERR_INVALID_ARG;
     const int i = find_out_slot(h, day);
     if (i < 0) return fail(h, DYS_ERR_NOT_AVAILABLE, "outputs of day %d are not in the ring (the last %d days are kept)", day, DYS_OUT_RING);
-    CK(h, cudaEventSynchronize(h->out_ev[i]));
+    CK(h, cudaEventSynchronize(h->out_ev[h->out_ev_of[i]]));
     { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
     const unsigned char* base = h->h_out + ((size_t)i * h->R + sel_rep(h)) * h->out_copy_bytes;
     out->day = day;
@@ -1182,7 +1215,7 @@ extern "C" int dys_get_stats(dys_handle* h, int32_t day, int64_t* out)
     if (!h || !out) return DYS_ERR_INVALID_ARG;
     const int i = find_out_slot(h, day);
     if (i >= 0) {
-        CK(h, cudaEventSynchronize(h->out_ev[i]));
+        CK(h, cudaEventSynchronize(h->out_ev[h->out_ev_of[i]]));
         { int ra = check_abort(h); if (ra != DYS_OK) return ra; }
         memcpy(out, h->h_out + ((size_t)i * h->R + sel_rep(h)) * h->out_copy_bytes, sizeof(int64_t) * N_STATS);
         return DYS_OK;

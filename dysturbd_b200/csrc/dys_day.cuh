@@ -47,6 +47,9 @@
 #ifndef DYS_PREFETCH_REC
 #define DYS_PREFETCH_REC 0
 #endif
+#ifndef DYS_BOUNDARY_FIRST
+#define DYS_BOUNDARY_FIRST 0
+#endif
 #ifndef DYS_ROW_REDUX
 #define DYS_ROW_REDUX 1
 #endif
@@ -1405,7 +1408,10 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     // Peer mode with a boundary split: HALO_BLOCKS more blocks own no agents either -- they wait for the partners' bytes and
     // push the halo agents' rows for tomorrow while the work blocks are busy with the bulk of today (the halo is ~1 % of a
     // day's push work: one block alone would be the last to reach the barrier).
-    const int n_service = (PEERS && peers && c0.bnd_ok && gridDim.x > 4 * HALO_BLOCKS) ? 1 + HALO_BLOCKS : 1;
+    // (DYS_BOUNDARY_FIRST, off: measured at N = 2, 1 M agents per GPU -- 44.9 us per day with the split and 16 halo blocks,
+    // 46.8 with one, against 37.5 when the first 16 work blocks push the halo rows after their own work: the extra
+    // agent_body call + system fence of the boundary phase costs more than the exchange latency it hides)
+    const int n_service = (DYS_BOUNDARY_FIRST && PEERS && peers && c0.bnd_ok && gridDim.x > 4 * HALO_BLOCKS) ? 1 + HALO_BLOCKS : 1;
     const bool service = gridDim.x > 1 && blockIdx.x == 0;
     const bool halo_block = n_service > 1 && blockIdx.x >= 1 && (int)blockIdx.x < n_service;
     const int n_work = gridDim.x > 1 ? (int)gridDim.x - n_service : 1;
