@@ -48,12 +48,13 @@ __device__ __forceinline__ uint8_t infectious_byte(uint32_t st, int day, int t_i
 constexpr uint32_t COL_MASK = 0x07FFFFFFu;
 constexpr int CLS_SHIFT = 28;
 constexpr uint32_t CLS_HH = 1u, CLS_HO = 2u, CLS_OH = 4u, CLS_OO = 8u;
+constexpr uint32_t EDGE_ONE_BLD = 0x80000000u;
 // one non-zero of the transposed interaction_prob, 16 bytes so that a lane fetches it with one 128-bit load.  The first
 // product of contagious3.py:232 -- interaction_prob[u,i] * agents[u,14] -- only involves static data, so it is formed once
 // at load time (same IEEE multiply, same rounding) and the push never gathers risk[u].
 struct __align__(16) TEdge {
     uint32_t colx;                       // u | class << 28
-    uint32_t pad;
+    uint32_t pad;                        // EDGE_ONE_BLD | b: the pair shares exactly one building, b (closures: exposure = class && open[b])
     double val;                          // ip[u,i] * risk[u]
 };
 

@@ -349,7 +349,14 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
                 const uint32_t ul = rec[k].x & COL_MASK;
                 const int64_t ug = c.lo + ul, ig = c.rt_lo + fmap.at(fe[k] & REL_MASK);
                 DYS_ASSERT(c, (int64_t)ul < c.n_loc && ig >= c.rt_lo && ig < c.rt_lo + c.rt_n, 3);
-                if (any_closed) {      // closed buildings: the class is only a superset, re-check the routines
+                if (any_closed && (rec[k].y & EDGE_ONE_BLD)) {
+                    // closed buildings, and the pair shares ONE building: the class test above already is the exposure test
+                    // for that building -- it only has to be open (one byte from a table that lives in L2)
+                    const bool open_b = __ldg(c.open + (rec[k].y & ~EDGE_ONE_BLD)) != 0;
+                    ok_free = ok_free && open_b;
+                    ok_iso = ok_iso && open_b;
+                    expo = ok_free || ok_iso;
+                } else if (any_closed) {      // ... several buildings: the class is only a superset, re-check the routines
                     if (CHECK) {
                         const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
                         ok_free = ok_free && ok;
@@ -399,10 +406,16 @@ DYS_BLOCK_FN void push_frontier(const DevCtx& c, const int day, BlockScratch& sm
         return load_row(c, sm.front + q0, nb, fmap);
     };
     unsigned int cnt[4] = {0u, 0u, 0u, 0u};
+#if DYS_PIPE_PUSH
     RowRef next = wid < n_groups ? rows_of(wid) : RowRef{0u, 0, 0};
+#endif
     for (int g = wid; g < n_groups; g += WARPS) {
+#if DYS_PIPE_PUSH
         const RowRef cur = next;
         if (g + WARPS < n_groups) next = rows_of(g + WARPS);      // the next group's row extents, in flight under this group
+#else
+        const RowRef cur = rows_of(g);
+#endif
         const uint4 d = push_group<CHECK>(c, day, sm.pw[wid], sm.pdf, cur, fmap);
         cnt[0] += d.x; cnt[1] += d.y; cnt[2] += d.z; cnt[3] += d.w;
     }
@@ -820,15 +833,20 @@ DYS_BLOCK_FN void settle_list(const DevCtx& c, const int day, BlockScratch& sm, 
     const unsigned lt_mask = (1u << lane) - 1u;
     const FrontMap fmap{c.lo - c.rt_lo + a_base};
     const int n_list = (int)sm.n_list;
+#if DYS_PIPE_SETTLE
     // the next round's records are requested before this round is settled
     uint32_t le_n = tid < n_list ? sm.list[tid] : 0u;
     Loaded L_n;
     L_n.mb = -1;
     if (tid < n_list) L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
+#endif
     for (int k0 = 0; k0 < n_list; k0 += BLOCK) {
         const int k = k0 + tid;
 #if !DYS_PIPE_SETTLE
-        if (k0 > 0 && k < n_list) {
+        uint32_t le_n = 0u;
+        Loaded L_n;
+        L_n.mb = -1;
+        if (k < n_list) {
             le_n = sm.list[k];
             L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
         }
@@ -844,8 +862,8 @@ DYS_BLOCK_FN void settle_list(const DevCtx& c, const int day, BlockScratch& sm, 
         const uint32_t rel = le & REL_MASK;
         const int64_t a = a_base + rel;
         const uint32_t st = valid ? (le >> 24) & 0xFu : (uint32_t)ST_PAD, att = (le >> 28) & 0x3u;
-        L_n.mb = -1;
 #if DYS_PIPE_SETTLE
+        L_n.mb = -1;
         if (k + BLOCK < n_list) {
             le_n = sm.list[k + BLOCK];
             L_n = load_agent(c, a_base + (le_n & REL_MASK), (le_n >> 24) & 0xFu, (le_n >> 28) & 0x3u);
@@ -1187,9 +1205,19 @@ struct DayPlan {
     int32_t test_hang_block;                        // tests (DYS_TEST_HANG_BLOCK): this block leaves before the first barrier; -1 = none
 };
 
+// the whole block copies a context (a single thread took ~950 instructions for it, at the start of every day, with
+// everybody else waiting at the barrier behind it -- 6 % of the kernel's instructions in the ncu source view of r02p)
+__device__ __forceinline__ void copy_ctx(DevCtx& dst, const DevCtx& src)
+{
+    static_assert(sizeof(DevCtx) % 4 == 0, "word copy");
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(&src);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevCtx) / 4); i += blockDim.x) d[i] = q[i];
+}
+
+// one thread: turn a copy of the launch context into the view of day first_day + k
 __device__ __forceinline__ void bind_plan_day(DevCtx& c, const DevCtx& c0, const DayPlan& plan, const int k, const int wb)
 {
-    c = c0;
     bind_day(c, plan.buf, plan.first_day + k);
     c.open = plan.open[k];
     c.n_closed = plan.n_closed[k];
@@ -1392,7 +1420,8 @@ __device__ __forceinline__ bool grid_barrier(const DevCtx& c, unsigned int* coun
 // PEERS = false: the single-GPU kernel carries none of the exchange code (16 % faster than the generic one at 1 M agents)
 // MULTI = false: one replica and runs short enough for the planned cut alone -- no replica views, no work words, no stealing
 template <bool PEERS, bool MULTI>
-__global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPlan plan, unsigned int* barrier_counter)
+__global__ void __launch_bounds__(BLOCK, 4) k_days(const __grid_constant__ DevCtx c0, const __grid_constant__ DayPlan plan,
+                                                   unsigned int* barrier_counter)
 {
     __shared__ BlockScratch sm;
     __shared__ DevCtx s_c[2];            // today's and tomorrow's view of the context (read like kernel parameters)
@@ -1419,6 +1448,8 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     const int64_t n_pieces = c0.n_pad >> 7, n_pieces_all = n_pieces * n_rep;
     // long runs are balanced dynamically (work words + stealing), short ones by the measured cut alone
     const bool stealing = MULTI && plan.work != nullptr && gridDim.x > 1 && n_pieces_all > 32ll * n_work;
+    copy_ctx(s_c[0], c0);
+    __syncthreads();
     if (threadIdx.x == 0) bind_plan_day(s_c[0], c0, plan, 0, wb);
     __syncthreads();
     if ((int)blockIdx.x == plan.test_hang_block) return;      // (tests: the others must time out at the barrier, not hang)
@@ -1426,7 +1457,9 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
     auto replica_view = [&](const DevCtx& day_view, const int slot, const int r) -> const DevCtx& {
         if (!MULTI || n_rep == 1) return day_view;
         __syncthreads();                       // (everybody is done with the previous occupant of the slot)
-        if (threadIdx.x == 0) { s_r[slot] = day_view; shift_replica(s_r[slot], r); }
+        copy_ctx(s_r[slot], day_view);
+        __syncthreads();
+        if (threadIdx.x == 0) shift_replica(s_r[slot], r);
         __syncthreads();
         return s_r[slot];
     };
@@ -1434,7 +1467,11 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
         const int day = plan.first_day + k;
         const DevCtx& c = s_c[k & 1];
         const bool local_push = c0.io_mat == nullptr && k + 1 < plan.n_days;
-        if (threadIdx.x == 0 && k + 1 < plan.n_days) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1, wb);
+        if (k + 1 < plan.n_days) {
+            copy_ctx(s_c[(k + 1) & 1], c0);
+            __syncthreads();
+            if (threadIdx.x == 0) bind_plan_day(s_c[(k + 1) & 1], c0, plan, k + 1, wb);
+        }
         __syncthreads();
         unsigned long long* tr = plan.trace ? plan.trace + ((size_t)k * gridDim.x + blockIdx.x) * TRACE_SLOTS : nullptr;
         auto stamp = [&](int i) {
@@ -1546,6 +1583,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const DevCtx c0, const DayPla
                     __syncthreads();
                     if (n == 0) {
                         if (finished) break;
+                        __nanosleep(400);          // (nothing to take right now: do not hammer the work words and the issue slots)
                         continue;
                     }
                     r = (int)(Pst / n_pieces);

@@ -105,16 +105,25 @@ __global__ void k_validate_routine(const int32_t* __restrict__ routine, int64_t 
 // buildings it is a superset that exposed_slow() re-checks.  Class 0 = the pair never shares a building: its exposure
 // factor (contagious3.py:230-236) is 0 on every day, so P = 0 and `P > U` can never hold -- such non-zeros are left out
 // of the transposed network altogether (three quarters of the synthetic city's, most of the shipped city's).
+// `shared` (optional): the ONE building the pair shares, or -1 if it shares several different ones.  With a single shared
+// building b the exposure under closures is simply (class test) && open[b]; only pairs that share several buildings need
+// the routine tables on a lockdown day (exposed_slow).
 __device__ __forceinline__ uint32_t pair_class(const int32_t* __restrict__ ru /* [V] routine of u */,
-                                               const int32_t* __restrict__ ri /* [V] routine of i */, const int V)
+                                               const int32_t* __restrict__ ri /* [V] routine of i */, const int V,
+                                               int32_t* shared = nullptr)
 {
     uint32_t cls = 0;
+    int32_t one = -2;                    // -2: none yet, -1: several
     for (int t = 0; t < V; ++t) {
         const int32_t bi = ri[t];
         if (bi < 0) continue;
         for (int s = 0; s < V; ++s)
-            if (ru[s] == bi) cls |= (s == 0) ? (t == 0 ? CLS_HH : CLS_HO) : (t == 0 ? CLS_OH : CLS_OO);
+            if (ru[s] == bi) {
+                cls |= (s == 0) ? (t == 0 ? CLS_HH : CLS_HO) : (t == 0 ? CLS_OH : CLS_OO);
+                one = (one == -2 || one == bi) ? bi : -1;
+            }
     }
+    if (shared) *shared = one;
     return cls;
 }
 
@@ -195,12 +204,13 @@ __global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const in
     for (int s = 0; s < 16; ++s) ru[s] = s < V ? c.routine[(c.lo + u - c.rt_lo) * V + s] : -1;
     for (int64_t e = rowptr[u] + lane; e < rowptr[u + 1]; e += 32) {
         const int32_t i = col[e];
-        const uint32_t cls = pair_class(ru, c.routine + ((int64_t)i - c.rt_lo) * V, V);
+        int32_t one = -1;
+        const uint32_t cls = pair_class(ru, c.routine + ((int64_t)i - c.rt_lo) * V, V, &one);
         if (!cls) continue;
         const unsigned long long pos = atomicAdd(&cursor[i - c.rt_lo], 1ull);
         TEdge t;
         t.colx = (uint32_t)u | (cls << CLS_SHIFT);
-        t.pad = 0u;
+        t.pad = one >= 0 ? (EDGE_ONE_BLD | (uint32_t)one) : 0u;
         t.val = __dmul_rn(val[e], c.risk[u]);      // contagious3.py:232, first product (both factors are static)
         tedge[pos] = t;
     }
