@@ -293,7 +293,7 @@ __device__ __noinline__ bool exposed_slow(const int32_t* __restrict__ routine, c
     const int32_t* ri = routine + ig * V;
     for (int s = 0; s < V; ++s) {
         const int32_t bu = __ldg(ru + s);
-        if (bu < 0 || (s > 0 && iso_u) || !__ldg(open + bu)) continue;
+        if (bu < 0 || (s > 0 && iso_u) || !__ldcg(open + bu)) continue;      // (ld.cg: the device lockdown policy rewrites the flags inside a launch)
         for (int t = 0; t < V; ++t) {
             if (t > 0 && iso_i) break;
             if (__ldg(ri + t) == bu) return true;

@@ -352,7 +352,7 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
                 if (any_closed && (rec[k].y & EDGE_ONE_BLD)) {
                     // closed buildings, and the pair shares ONE building: the class test above already is the exposure test
                     // for that building -- it only has to be open (one byte from a table that lives in L2)
-                    const bool open_b = __ldg(c.open + (rec[k].y & ~EDGE_ONE_BLD)) != 0;
+                    const bool open_b = __ldcg(c.open + (rec[k].y & ~EDGE_ONE_BLD)) != 0;
                     ok_free = ok_free && open_b;
                     ok_iso = ok_iso && open_b;
                     expo = ok_free || ok_iso;
