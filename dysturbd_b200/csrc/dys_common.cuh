@@ -48,7 +48,8 @@ __device__ __forceinline__ uint8_t infectious_byte(uint32_t st, int day, int t_i
 constexpr uint32_t COL_MASK = 0x07FFFFFFu;
 constexpr int CLS_SHIFT = 28;
 constexpr uint32_t CLS_HH = 1u, CLS_HO = 2u, CLS_OH = 4u, CLS_OO = 8u;
-constexpr uint32_t EDGE_ONE_BLD = 0x80000000u;
+constexpr uint32_t EDGE_ONE_BLD = 0x80000000u;      // pad: the pair shares exactly one building (low 31 bits)
+constexpr uint32_t EDGE_MASKS = 0x40000000u;        // pad: bits 0-9 slots of u that meet any slot of i, bits 10-19 ... the home slot of i
 // one non-zero of the transposed interaction_prob, 16 bytes so that a lane fetches it with one 128-bit load.  The first
 // product of contagious3.py:232 -- interaction_prob[u,i] * agents[u,14] -- only involves static data, so it is formed once
 // at load time (same IEEE multiply, same rounding) and the push never gathers risk[u].
@@ -282,6 +283,22 @@ __device__ __forceinline__ void grid_clear16(uint8_t* p, int64_t n_bytes)
     const int64_t n = (n_bytes + 15) >> 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         q[i] = make_uint4(0, 0, 0, 0);
+}
+
+// exposure under closures from the edge's slot masks: some allowed slot of u whose building is open (u isolated: slot 0
+// only; i isolated: only the slots that meet i's home slot) -- a load per set bit instead of the V x V walk below
+__device__ __forceinline__ bool exposed_masks(const int32_t* __restrict__ routine, const uint8_t* __restrict__ open, int V, int64_t ug,
+                                              uint32_t pad, bool iso_u, bool iso_i)
+{
+    uint32_t m = iso_i ? (pad >> 10) & 0x3FFu : pad & 0x3FFu;
+    if (iso_u) m &= 1u;
+    const int32_t* ru = routine + ug * V;
+    while (m) {
+        const int s = __ffs(m) - 1;
+        m &= m - 1;
+        if (__ldcg(open + __ldg(ru + s))) return true;
+    }
+    return false;
 }
 
 // exact exposure test for days with closed buildings (contagious3.py:181-189, :230-231): a shared building must be

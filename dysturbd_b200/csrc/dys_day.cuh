@@ -356,7 +356,17 @@ DYS_PUSH_FN uint4 push_group(const DevCtx& c, const int day, PushWarpScratch& w,
                     ok_free = ok_free && open_b;
                     ok_iso = ok_iso && open_b;
                     expo = ok_free || ok_iso;
-                } else if (any_closed) {      // ... several buildings: the class is only a superset, re-check the routines
+                } else if (any_closed && (rec[k].y & EDGE_MASKS)) {      // ... several buildings: which slots of u meet i
+                    if (CHECK) {
+                        const bool ok = exposed_masks(c.routine, c.open, c.V, ug - c.rt_lo, rec[k].y, iso_u, iso_i);
+                        ok_free = ok_free && ok;
+                        ok_iso = ok_iso && ok;
+                    } else {
+                        ok_free = exposed_masks(c.routine, c.open, c.V, ug - c.rt_lo, rec[k].y, false, iso_i);
+                        ok_iso = ok_iso && exposed_masks(c.routine, c.open, c.V, ug - c.rt_lo, rec[k].y, true, iso_i);
+                    }
+                    expo = ok_free || ok_iso;
+                } else if (any_closed) {      // (V > 10: no room for the masks) re-check the routines
                     if (CHECK) {
                         const bool ok = exposed_slow(c.routine, c.open, c.V, ug - c.rt_lo, ig - c.rt_lo, iso_u, iso_i);
                         ok_free = ok_free && ok;

@@ -110,9 +110,9 @@ __global__ void k_validate_routine(const int32_t* __restrict__ routine, int64_t 
 // the routine tables on a lockdown day (exposed_slow).
 __device__ __forceinline__ uint32_t pair_class(const int32_t* __restrict__ ru /* [V] routine of u */,
                                                const int32_t* __restrict__ ri /* [V] routine of i */, const int V,
-                                               int32_t* shared = nullptr)
+                                               int32_t* shared = nullptr, uint32_t* masks = nullptr)
 {
-    uint32_t cls = 0;
+    uint32_t cls = 0, m_all = 0, m_home = 0;      // slots of u that meet ANY slot of i / the home slot of i
     int32_t one = -2;                    // -2: none yet, -1: several
     for (int t = 0; t < V; ++t) {
         const int32_t bi = ri[t];
@@ -121,9 +121,12 @@ __device__ __forceinline__ uint32_t pair_class(const int32_t* __restrict__ ru /*
             if (ru[s] == bi) {
                 cls |= (s == 0) ? (t == 0 ? CLS_HH : CLS_HO) : (t == 0 ? CLS_OH : CLS_OO);
                 one = (one == -2 || one == bi) ? bi : -1;
+                m_all |= 1u << s;
+                if (t == 0) m_home |= 1u << s;
             }
     }
     if (shared) *shared = one;
+    if (masks) *masks = m_all | (m_home << 10);
     return cls;
 }
 
@@ -205,12 +208,13 @@ __global__ void __launch_bounds__(256) k_fill_transpose(const DevCtx c, const in
     for (int64_t e = rowptr[u] + lane; e < rowptr[u + 1]; e += 32) {
         const int32_t i = col[e];
         int32_t one = -1;
-        const uint32_t cls = pair_class(ru, c.routine + ((int64_t)i - c.rt_lo) * V, V, &one);
+        uint32_t masks = 0;
+        const uint32_t cls = pair_class(ru, c.routine + ((int64_t)i - c.rt_lo) * V, V, &one, &masks);
         if (!cls) continue;
         const unsigned long long pos = atomicAdd(&cursor[i - c.rt_lo], 1ull);
         TEdge t;
         t.colx = (uint32_t)u | (cls << CLS_SHIFT);
-        t.pad = one >= 0 ? (EDGE_ONE_BLD | (uint32_t)one) : 0u;
+        t.pad = one >= 0 ? (EDGE_ONE_BLD | (uint32_t)one) : (V <= 10 ? (EDGE_MASKS | masks) : 0u);
         t.val = __dmul_rn(val[e], c.risk[u]);      // contagious3.py:232, first product (both factors are static)
         tedge[pos] = t;
     }
