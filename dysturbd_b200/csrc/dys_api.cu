@@ -1331,6 +1331,44 @@ extern "C" int dys_get_pair_prob(dys_handle* h, double* out)
     return copy_out(h, out, h->d_pair_prob, sizeof(double) * (size_t)(h->c.n_glob * h->c.n_glob));
 }
 
+// Everything the host loop needs from one day, in ONE call: waits for the day's block, copies the stats and the per-building
+// counts out of the pinned ring, and forms R (global and per owned area) from the integer histograms -- compute_R,
+// contagious3.py:29-42, in the reference's order of float operations.  (The host loop has ~20 us per simulated day at 1 M
+// agents; a Python-level consumer spends that on array bookkeeping alone.)
+extern "C" int dys_consume_day(dys_handle* h, int32_t day, const double* pdf, int32_t recover, int64_t* stats /* [64] */,
+                               double* R_global /* [1] */, double* R_areas /* [S_out] or NULL */,
+                               int32_t* building_counts /* [B_out] or NULL */, int32_t* events /* [cap][2] or NULL */,
+                               int64_t events_cap, int64_t* n_events)
+{
+    if (!h || !pdf || !stats || !R_global) return DYS_ERR_INVALID_ARG;
+    dys_day_outputs o;
+    int rc = dys_get_outputs(h, day, &o);
+    if (rc != DYS_OK) return rc;
+    memcpy(stats, o.stats, sizeof(int64_t) * N_STATS);
+    if (n_events) *n_events = o.n_events;
+    rc = dys_compute_r_rows(o.stats + HIST0, 8, 1, HIST_LEN, pdf, recover, R_global);
+    if (rc == DYS_OK && R_areas) {
+        if (!o.sa_hist) return fail(h, DYS_ERR_NOT_AVAILABLE, "sa_hist was not requested in dys_params.flags");
+        rc = dys_compute_r_rows(o.sa_hist, 4, h->c.S_out, HIST_LEN, pdf, recover, R_areas);
+    }
+    if (rc == DYS_OK && building_counts) {
+        if (!o.building_counts) return fail(h, DYS_ERR_NOT_AVAILABLE, "building counts were not requested in dys_params.flags");
+        memcpy(building_counts, o.building_counts, sizeof(int32_t) * (size_t)h->c.B_out);
+    }
+    if (rc == DYS_OK && events && o.n_events > 0) {
+        if (!o.events) return fail(h, DYS_ERR_NOT_AVAILABLE, "events were not requested in dys_params.flags");
+        if (o.n_events > events_cap) return fail(h, DYS_ERR_INVALID_ARG, "dys_consume_day: %lld events, room for %lld", (long long)o.n_events, (long long)events_cap);
+        if (o.n_events <= o.events_inline) memcpy(events, o.events, sizeof(int32_t) * 2 * (size_t)o.n_events);
+        else {      // (more than travel with the block: fetch, de-interleave back into pairs)
+            std::vector<int32_t> a((size_t)o.n_events), b((size_t)o.n_events);
+            int64_t n = 0;
+            rc = dys_get_events(h, day, a.data(), b.data(), o.n_events, &n);
+            for (int64_t k = 0; rc == DYS_OK && k < n; ++k) { events[2 * k] = a[(size_t)k]; events[2 * k + 1] = b[(size_t)k]; }
+        }
+    }
+    return rc;
+}
+
 extern "C" int dys_sync(dys_handle* h)
 {
     if (!h) return DYS_ERR_INVALID_ARG;

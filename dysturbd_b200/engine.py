@@ -67,7 +67,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach",
-           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown", "dys_generate_routines"]
+           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown", "dys_generate_routines", "dys_consume_day"]
 
 _lib = None
 
@@ -118,6 +118,7 @@ def load_library():
     lib.dys_select_replica.argtypes = [vp, i32]
     lib.dys_abort.argtypes = [vp]
     lib.dys_set_lockdown.argtypes = [vp, i32, vp]
+    lib.dys_consume_day.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, i64, vp]
     lib.dys_generate_routines.argtypes = [C.c_int, i64, i64, i32, i32] + [vp] * 8 + [C.c_uint64, vp]
     lib.dys_h2d_bytes.argtypes = [vp]
     lib.dys_h2d_bytes.restype = i64
@@ -338,6 +339,12 @@ class Engine:
             else:
                 ev = np.zeros((0, 2), dtype=np.int32)
         return {"stats": views[0], "sa_hist": views[1], "building_counts": views[2], "events": ev, "n_events": n_ev}
+
+    def consume_day(self, day, pdf_ptr, recover, stats_ptr, r_ptr, r_sa_ptr, bc_ptr, ev_ptr, ev_cap, n_ev_ptr):
+        """dys_consume_day on raw addresses (the host loop pre-computes them: one ctypes call per simulated day)"""
+        rc = self.lib.dys_consume_day(self.h, day, pdf_ptr, recover, stats_ptr, r_ptr, r_sa_ptr, bc_ptr, ev_ptr, ev_cap, n_ev_ptr)
+        if rc != 0:
+            self._ck(rc)
 
     def stats(self, day):
         out = np.zeros(N_STATS, dtype=np.int64)

@@ -125,6 +125,9 @@ class EpidemicModel:
         self._pdf = [float(x) for x in self.params.pdf]
         self._pdf_arr = np.ascontiguousarray(self.params.pdf, dtype=np.float64)
         self._n_closed_cache = {}
+        self._ck, self._ck_base = None, 0
+        self._ev_arena, self._ev_used = None, 0
+        self._ev_room = max(1024, (self.pop.N + 1023) // 1024 * 1024)      # a day cannot infect more agents than there are
         try:                                     # the library's host-side helper (exact); numpy otherwise (also exact)
             _engine.load_library()
             self._R_rows = _engine.compute_R_rows
@@ -284,16 +287,46 @@ class EpidemicModel:
         S['Susceptible'] = self.pop.N_glob - S['Total infected']
         return S
 
+    CHUNK = 64                   # days per block of preallocated compact outputs
+
+    def _new_chunk(self):
+        n, S, B = self.CHUNK, self._s1 - self._s0, self.sim.B_out
+        ck = dict(st=np.empty((n, 64), np.int64), R=np.empty(n, np.float64), Rsa=np.empty((n, S), np.float64),
+                  bc=np.empty((n, B), np.int32), nev=np.zeros(1, np.int64))
+        ck["ptr"] = {k: v.ctypes.data for k, v in ck.items()}
+        self._ck_base, self._ck = self.day, ck
+
     def _consume_compact(self):
         """compact=True: the same numbers as arrays -- 'SAs'[day] = {'R': float64[S], 'vis_R': float64[S]} (owned areas),
         'Buildings'[day] = int32[B] infected residents per owned building (buildings_table() gives the reference's
         [count, fraction] rows), 'IO_mat'[day] = int32[n, 2] (infected, infector) agent rows (io_pairs() gives the area
-        pairs the reference counts).  The floats are formed by the library's host-side helper in the reference's order of
-        operations (dys_compute_r_rows), a few microseconds per day whatever the number of areas."""
-        p, day, prm = self.pop, self.day, self.params
+        pairs the reference counts).  On the CUDA engine a day is ONE library call (dys_consume_day: copies out of the pinned
+        ring + compute_R in the reference's order of float operations) into preallocated blocks of 64 days."""
+        p, day, prm, sim = self.pop, self.day, self.params, self.sim
         res = self.outputs['Results']
-        st, sa_hist, bc, ev_a, ev_s = self._day_arrays(day, sort_events=False)
-        ev = self._ev_pairs
+        fast = self._reduce is None and hasattr(sim, "consume_day")
+        if fast:
+            i = day - self._ck_base
+            if self._ck is None or i >= self.CHUNK:
+                self._new_chunk()
+                i = 0
+            ck, ptr = self._ck, self._ck["ptr"]
+            if self._ev_arena is None or self._ev_used + self._ev_room > len(self._ev_arena):
+                self._ev_arena, self._ev_used = np.empty((max(1 << 20, 4 * self._ev_room), 2), np.int32), 0
+            S = ck["Rsa"].shape[1]
+            sim.consume_day(day, self._pdf_arr.ctypes.data, prm.recover, ptr["st"] + i * 512, ptr["R"] + i * 8, ptr["Rsa"] + i * 8 * S,
+                            ptr["bc"] + i * 4 * ck["bc"].shape[1], self._ev_arena.ctypes.data + self._ev_used * 8, self._ev_room, ptr["nev"])
+            st, R, R_sa, bc = ck["st"][i], float(ck["R"][i]), ck["Rsa"][i], ck["bc"][i]
+            n_ev = int(ck["nev"][0])
+            ev_pairs = self._ev_arena[self._ev_used:self._ev_used + n_ev]
+            self._ev_used += n_ev
+        else:
+            st, sa_hist, bc, ev_a, ev_s = self._day_arrays(day, sort_events=False)
+            ev = self._ev_pairs
+            R = float(self._R_rows(st[HIST0:HIST0 + HIST_LEN], self._pdf_arr, prm.recover)[0])
+            R_sa = self._R_rows(np.asarray(sa_hist)[:self._s1 - self._s0], self._pdf_arr, prm.recover)
+            bc = np.array(bc, dtype=np.int32)
+            ev_pairs = np.array(ev, dtype=np.int32) if ev is not None else np.stack([ev_a, ev_s], axis=1).astype(np.int32)
         if self.lockdown == 'device':
             closed_today = int(st[_engine.ST_CLOSED])
         else:
@@ -302,15 +335,13 @@ class EpidemicModel:
             if closed_today is None:
                 closed_today = int((flags == 0).sum())
                 self._n_closed_cache = {id(flags): closed_today}
-        R = float(self._R_rows(st[HIST0:HIST0 + HIST_LEN], self._pdf_arr, prm.recover)[0])
         self._R[day] = R
-        R_sa = self._R_rows(np.asarray(sa_hist)[:self._s1 - self._s0], self._pdf_arr, prm.recover)
         dz = prm.diagnosis
         res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - dz]['R'] if day > dz else np.zeros(len(R_sa))}
         S = self._stats_dict(st, R, self._known_R(day), closed_today)
         res['Stats'][day] = S
-        res['Buildings'][day] = np.array(bc, dtype=np.int32)
-        res['IO_mat'][day] = np.array(ev, dtype=np.int32) if ev is not None else np.stack([ev_a, ev_s], axis=1).astype(np.int32)
+        res['Buildings'][day] = bc
+        res['IO_mat'][day] = ev_pairs
         self._active = S['Active infected']
         self.day += 1
         return S

@@ -210,6 +210,12 @@ typedef struct dys_day_outputs {
     int64_t events_capacity;     /* pairs the block can carry: events[0 .. events_capacity) is addressable on every day */
 } dys_day_outputs;
 int dys_get_outputs(dys_handle* h, int32_t day, dys_day_outputs* out);
+/* Everything the host loop needs from one day in ONE call: waits for the day's block (like dys_get_outputs), copies stats,
+ * per-building counts and the (infected, infector) pairs out of the pinned ring into caller memory, and forms R
+ * (compute_R, contagious3.py:29-42, same order of float operations) for the global histogram and for every owned area. */
+int dys_consume_day(dys_handle* h, int32_t day, const double* pdf, int32_t recover, int64_t* stats /* [DYS_N_STATS] */,
+                    double* R_global /* [1] */, double* R_areas /* [areas] or NULL */, int32_t* building_counts /* [buildings] or NULL */,
+                    int32_t* events /* [events_cap][2] or NULL */, int64_t events_cap, int64_t* n_events /* nullable */);
 /* P for every evaluated pair of the most recent day (tests; requires injected mode): out[N*N] */
 int dys_get_pair_prob(dys_handle* h, double* out);
 
