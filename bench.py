@@ -457,7 +457,7 @@ def run_ours(args):
     d2h_day = 0
     if not replicas_mode:
         o = m0.sim.sim if world > 1 else m0.sim
-        d2h_day = 64 * 8 + o.S_out * 21 * 4 + o.B_out * 4 + max(1024, ((pop.N + 1023) // 1024 * 1024) // 32) * 8
+        d2h_day = 64 * 8 + o.S_out * 21 * 4 + o.B_out * 4 + max(1024, ((pop.N + 1023) // 1024 * 1024) // 64) * 8
     else:
         d2h_day = 64 * 8 * R
     line = {

@@ -268,7 +268,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
         h->off_sa = sizeof(int64_t) * N_STATS;
         h->off_bc = h->off_sa + ((p.flags & DYS_WANT_SA_HIST) ? up16(sizeof(int32_t) * (size_t)(c.S_out * HIST_LEN)) : 0);
         h->off_ev = h->off_bc + ((p.flags & DYS_WANT_BUILDING_COUNTS) ? up16(sizeof(int32_t) * (size_t)c.B_out) : 0);
-        h->ev_inline = (p.flags & DYS_WANT_EVENTS) ? (c.n_pad / 32 > 1024 ? c.n_pad / 32 : 1024) : 0;
+        h->ev_inline = (p.flags & DYS_WANT_EVENTS) ? (c.n_pad / 64 > 1024 ? c.n_pad / 64 : 1024) : 0;
         if (h->ev_inline > c.n_pad) h->ev_inline = c.n_pad;
         h->out_copy_bytes = h->off_ev + sizeof(int2) * (size_t)h->ev_inline;
         h->out_dev_bytes = h->off_ev + ((p.flags & DYS_WANT_EVENTS) ? sizeof(int2) * (size_t)c.n_pad : 0);

@@ -42,12 +42,12 @@ def building_classes(lu, usg):
     return np.where(np.isin(usg, EDU_CODES))[0], np.where(np.isin(usg, REL_CODES))[0], np.where(lu >= 3)[0]
 
 
-def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None):
+def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None, dtype=float):
     """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
     (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice.
     keyed = (seed, day): the half closures of GRADUAL close each building of the class with probability 1/2 on the keyed
     draw u(day, STREAM_LOCKDOWN, building) instead -- the host twin of the device policy (dys_set_lockdown)."""
-    lockdown = np.ones(len(lu))
+    lockdown = np.ones(len(lu), dtype=dtype)      # (the reference's float64 vector; the model keeps its flags as bytes)
     edu, rel, non_res = classes if classes is not None else building_classes(lu, usg)
 
     def close(idx, half):
@@ -73,7 +73,7 @@ def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, clas
             if prevVR <= 1 or prevVR >= 2:
                 apply(True)
             else:
-                lockdown = np.array(current, dtype=float)
+                lockdown = np.array(current, dtype=dtype)
         elif vR >= 2:
             apply(False)
     elif 1 < vR:
@@ -137,10 +137,10 @@ class EpidemicModel:
         if self._reduce is not None:
             self._active = int(self._reduce(np.array([[self._active] + [0] * 63], dtype=np.int64))[0, 0])
         self._R = {}                 # day -> R of that day (contagious3.py:281)
-        self._flags = {0: self.pop.open.astype(float)}      # day -> build[:,10] in force on that day
+        self._flags = {0: self.pop.open.astype(np.uint8)}   # day -> build[:,10] in force on that day (0 / 1 bytes)
         self._queued = 0             # next day to queue
         closes = self._closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
-        self._ones = np.ones(self.pop.B)
+        self._ones = np.ones(self.pop.B, dtype=np.uint8)
         self._open_window = None
         self._classes = building_classes(self.pop.bld_lu, self.pop.bld_usg)      # (static: not recomputed every day)
         self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
@@ -184,14 +184,14 @@ class EpidemicModel:
             elif 'DIFF' in self.scenario:
                 if prev != 0:
                     raise KeyError('Vis_R')      # the reference reads a key it never writes (:371 vs :319)
-                self._flags[day] = np.ones(self.pop.B)
+                self._flags[day] = self._ones
             else:
                 cur = self._flags_for(prev)
                 prevVR = self._known_R(prev - 1) if prev != 0 else 0
                 self._flags[day] = building_lockdown(self.pop.bld_lu, self.pop.bld_usg, cur, self.scenario,
                                                      self._known_R(prev), prevVR, self._choice,
                                                      keyed=(self.params.seed, prev) if self.lockdown == 'keyed' else None,
-                                                     classes=self._classes)
+                                                     classes=self._classes, dtype=np.uint8)
             self._flags.pop(day - 20, None)
         return self._flags[day]
 
@@ -207,7 +207,7 @@ class EpidemicModel:
                 self._open_window = np.ones((self.MAX_WINDOW, self.pop.B), dtype=np.uint8)
             flags = self._open_window[:n]
         else:
-            flags = np.stack(fl).astype(np.uint8)
+            flags = np.stack(fl)
         if self.flags_log is not None:
             for k in range(n):
                 self.flags_log[first + k] = flags[k]
@@ -230,7 +230,7 @@ class EpidemicModel:
         p, sim, day, prm = self.pop, self.sim, self.day, self.params
         res = self.outputs['Results']
         st, sa_hist, bc, ev_a, ev_s = self._day_arrays(day, sort_events=True)
-        closed_today = int(st[_engine.ST_CLOSED]) if self.lockdown == 'device' else int((self._flags_for(day) == 0).sum())
+        closed_today = int(st[_engine.ST_CLOSED]) if self.lockdown == 'device' else (self.pop.B - int(np.count_nonzero(self._flags_for(day))))
         hist = st[HIST0:HIST0 + HIST_LEN]
         R = compute_R_from_hist(hist, self._pdf, prm.recover)
         self._R[day] = R
@@ -333,7 +333,7 @@ class EpidemicModel:
             flags = self._flags_for(day)
             closed_today = self._n_closed_cache.get(id(flags))
             if closed_today is None:
-                closed_today = int((flags == 0).sum())
+                closed_today = len(flags) - int(np.count_nonzero(flags))
                 self._n_closed_cache = {id(flags): closed_today}
         self._R[day] = R
         dz = prm.diagnosis
