@@ -318,7 +318,10 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
             *h->h_abort = 0;
             void* dab = nullptr;
             if (cudaHostGetDevicePointer(&dab, ab, 0) != cudaSuccess) rc = DYS_ERR_CUDA;
-            c.abort_word = (volatile int32_t*)dab;
+            c.abort_host = (volatile int32_t*)dab;
+            int32_t* dword = nullptr;
+            A(dev_alloc(h, &dword, 16));
+            c.abort_word = dword;
         }
     }
     if (rc == DYS_OK && cudaMemcpyAsync(d_pdf, p.pdf_table, sizeof(double) * DYS_PDF_LEN, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = DYS_ERR_CUDA;
@@ -348,7 +351,7 @@ extern "C" int dys_destroy(dys_handle* h)
 {
     if (!h) return DYS_OK;
     cudaSetDevice(h->device);
-    if (h->h_abort) *h->h_abort = 1;      // a launch that is still spinning ends
+    if (h->h_abort) dys_abort(h);         // a launch that is still spinning ends
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamDestroy(h->up_stream); }
     for (void* p : h->allocs) cudaFree(p);
@@ -431,7 +434,11 @@ static int reset_day_scratch(dys_handle* h)
     CK(h, cudaStreamSynchronize(h->up_stream));
     for (int i = 0; i < DYS_OUT_RING; ++i) { h->out_day[i] = -1; h->out_step[i] = -1; }
     for (int i = 0; i < DYS_STATS_RING; ++i) h->hist_day[i] = -1;
-    if (h->h_abort) *h->h_abort = 0;
+    if (h->h_abort) {
+        *h->h_abort = 0;
+        CK(h, cudaMemsetAsync((void*)h->c.abort_word, 0, sizeof(int32_t), h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
     return DYS_OK;
 }
 
@@ -654,6 +661,12 @@ extern "C" int dys_abort(dys_handle* h)
 {
     if (!h || !h->h_abort) return DYS_ERR_INVALID_ARG;
     *h->h_abort = 1;
+    // the word the kernels poll lives in device memory: a copy on the upload stream reaches it while a launch is running
+    static const int32_t one = 1;
+    if (h->up_stream && h->c.abort_word) {
+        cudaSetDevice(h->device);
+        cudaMemcpyAsync((void*)h->c.abort_word, &one, sizeof one, cudaMemcpyHostToDevice, h->up_stream);
+    }
     return DYS_OK;
 }
 

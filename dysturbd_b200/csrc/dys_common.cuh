@@ -13,7 +13,7 @@
 #define DYS_CHECKS 0
 #endif
 #if DYS_CHECKS
-#define DYS_ASSERT(ctx, cond, code) do { if (!(cond) && (ctx).abort_word) *(ctx).abort_word = 1000 + (code); } while (0)
+#define DYS_ASSERT(ctx, cond, code) do { if (!(cond) && (ctx).abort_word) { *(ctx).abort_word = 1000 + (code); *(ctx).abort_host = 1000 + (code); } } while (0)
 #else
 #define DYS_ASSERT(ctx, cond, code) do { } while (0)
 #endif
@@ -111,7 +111,9 @@ struct DevCtx {
     int64_t ib_stride, out_stride;       // bytes between two replicas' snapshot buffers / output blocks
     const RepParam* rep_params;          // [n_rep] or null (n_rep == 1: the fields above)
     // spinning loops (grid barrier, peer waits) give up when *abort_word != 0 or after spin_timeout_ns (then they set it)
-    volatile int32_t* abort_word;        // pinned host memory mapped into the device: the host can read and set it at any time
+    volatile int32_t* abort_word;        // DEVICE memory: polled by the spinning loops (the host sets it with a copy on a side stream)
+    volatile int32_t* abort_host;        // its mirror in mapped pinned host memory: written (never polled) by the device when a
+                                         // wait times out or a check fails, read by the host without any CUDA call
     unsigned long long spin_timeout_ns;
     // mutable state, owned agents
     uint8_t* status;
