@@ -335,10 +335,18 @@ def run_ours(args):
     # ------------------------------------------------------------------------------------------------------------
     # pass B: resident throughput (`value`): CUDA events on the library's stream, right around the launches
     # ------------------------------------------------------------------------------------------------------------
+    last_flags = [None]
+
     def flags_of(d, n):
+        """the recorded flag vectors of days d .. d+n-1, or None when none of them differs from the vector in force (the
+        library keeps the last vector of a window as the standing one): unchanged flags are not uploaded again"""
         if flags_rec is None:
             return None
-        return np.stack([flags_rec[min(x, max(flags_rec))] for x in range(d, d + n)])
+        fl = [flags_rec[min(x, max(flags_rec))] for x in range(d, d + n)]
+        if d > 0 and last_flags[0] is not None and all(f is last_flags[0] or np.array_equal(f, last_flags[0]) for f in fl):
+            return None
+        last_flags[0] = fl[-1]
+        return np.stack(fl)
 
     def run_resident(first_day, last_day, win):
         d = first_day
