@@ -243,7 +243,11 @@ def run_ours(args):
         eng.set_replica_params(norms, comps, 20201019 + idx)
         raw = eng
     elif world == 1:
+        # the day's building flags are this path's only per-day HOST input (contagious3.py:384 re-assigns build[:,10] every
+        # day): in the end-to-end pass every day's vector travels, changed or not (the library would skip unchanged ones)
+        os.environ["DYS_UPLOAD_ALWAYS"] = "1"
         eng = raw = engine.Engine(pop, prm, device=local, flags=all_out)
+        del os.environ["DYS_UPLOAD_ALWAYS"]
     else:
         eng = ShardedEngine(pop, prm, device=local, mode=args.exchange, flags=all_out)
         raw = eng.sim

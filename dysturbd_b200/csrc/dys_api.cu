@@ -84,6 +84,7 @@ struct dys_handle {
     uint32_t partner_mask = 0;       // ranks this rank exchanges bytes with (either direction)
     int push_grid = 0;               // persistent grid of k_push
     int last_slot = 0;
+    bool upload_always = false;       // DYS_UPLOAD_ALWAYS=1: every offered flag vector travels (bench accounting of host inputs)
     bool no_steal = false;
     bool test_hooks = false;          // DYS_TEST_HANG_BLOCK was set when the handle was created
     int64_t plan_max = 16384;
@@ -205,6 +206,7 @@ extern "C" int dys_create(const dys_params* params, int device, dys_handle** out
     { const char* nf = getenv("DYS_NO_FUSE"); h->no_fuse = nf && nf[0] == '1'; }
     h->trace_path = getenv("DYS_TRACE");
     h->test_hooks = getenv("DYS_TEST_HANG_BLOCK") != nullptr;
+    { const char* t = getenv("DYS_UPLOAD_ALWAYS"); h->upload_always = t && t[0] == '1'; }
     { const char* t = getenv("DYS_PLAN_MAX"); if (t) h->plan_max = atoll(t); }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -1065,6 +1067,7 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     const uint8_t* cur_dev = c.open;
     int32_t cur_closed = c.n_closed;
     const int wp = (int)(h->windows & 1);
+    bool ring_touched = false;
     plan.ld = h->ld;
     if (h->ld.mode) {
         if (open_flags) return fail(h, DYS_ERR_INVALID_ARG, "the device lockdown policy decides the flags: open_flags must be NULL");
@@ -1072,24 +1075,36 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
         if (h->last_day >= 0 && first_day != h->last_day + 1) return fail(h, DYS_ERR_STATE, "the device lockdown policy needs consecutive days");
     }
     if (open_flags) {
+        // only the days whose vector differs from the one in force before them travel: a lockdown scenario changes its
+        // flags on a handful of days, and a metro's vector is half a megabyte (staging 7 of them per window made the
+        // HOST the bottleneck of a 10 M-agent run)
         const size_t B = (size_t)c.B;
         if (h->ring_used[wp]) CK(h, cudaEventSynchronize(h->up_done[wp]));      // (two windows ago: long done)
-        memcpy(h->h_open_ring[wp], open_flags, (size_t)n_days * B);
-        if (h->ring_used[wp]) CK(h, cudaStreamWaitEvent(h->up_stream, h->ring_free[wp], 0));
-        CK(h, cudaMemcpyAsync(h->d_open_ring[wp], h->h_open_ring[wp], (size_t)n_days * B, cudaMemcpyHostToDevice, h->up_stream));
-        CK(h, cudaEventRecord(h->up_done[wp], h->up_stream));
-        CK(h, cudaStreamWaitEvent(h->stream, h->up_done[wp], 0));
-        h->h2d_bytes += (int64_t)n_days * (int64_t)B;
+        bool waited = !h->ring_used[wp];
+        int uploads = 0;
         for (int k = 0; k < n_days; ++k) {
             const uint8_t* f = open_flags + (size_t)k * B;
-            int32_t closed = 0;
-            for (size_t b = 0; b < B; ++b) closed += f[b] == 0;
-            plan.open[k] = h->d_open_ring[wp] + (size_t)k * B;
-            plan.n_closed[k] = closed;
+            if (memcmp(h->h_open, f, B) != 0 || h->upload_always) {
+                uint8_t* stage = h->h_open_ring[wp] + (size_t)k * B;
+                memcpy(stage, f, B);
+                memcpy(h->h_open, f, B);
+                int32_t closed = 0;
+                for (size_t b = 0; b < B; ++b) closed += f[b] == 0;
+                if (!waited) { CK(h, cudaStreamWaitEvent(h->up_stream, h->ring_free[wp], 0)); waited = true; }
+                CK(h, cudaMemcpyAsync(h->d_open_ring[wp] + (size_t)k * B, stage, B, cudaMemcpyHostToDevice, h->up_stream));
+                h->h2d_bytes += (int64_t)B;
+                cur_dev = h->d_open_ring[wp] + (size_t)k * B;
+                cur_closed = closed;
+                ++uploads;
+            }
+            plan.open[k] = cur_dev;
+            plan.n_closed[k] = cur_closed;
         }
-        cur_dev = plan.open[n_days - 1];
-        cur_closed = plan.n_closed[n_days - 1];
-        memcpy(h->h_open, open_flags + (size_t)(n_days - 1) * B, B);
+        if (uploads) {
+            CK(h, cudaEventRecord(h->up_done[wp], h->up_stream));
+            CK(h, cudaStreamWaitEvent(h->stream, h->up_done[wp], 0));
+        }
+        ring_touched = uploads > 0;
     } else {
         for (int k = 0; k < n_days; ++k) { plan.open[k] = cur_dev; plan.n_closed[k] = cur_closed; }
     }
@@ -1125,11 +1140,7 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     const void* kern = h->n_peers > 1 ? (multi ? (const void*)k_days<true, true> : (const void*)k_days<true, false>)
                                       : (multi ? (const void*)k_days<false, true> : (const void*)k_days<false, false>);
     CK(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)h->days_grid), dim3(256), args, 0, h->stream));
-    if (open_flags) {
-        CK(h, cudaEventRecord(h->ring_free[wp], h->stream));
-        h->ring_used[wp] = true;
-        ++h->windows;
-    }
+
     if (plan.trace) {      // developer tracing: synchronous, appended as text
         std::vector<unsigned long long> tr(trace_words);
         CK(h, cudaMemcpyAsync(tr.data(), h->d_trace, trace_words * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1148,6 +1159,11 @@ static int step_fused(dys_handle* h, int32_t first_day, int32_t n_days, const ui
     if (cur_dev != c.open) {      // the flags in force after the window become the standing vector
         CK(h, cudaMemcpyAsync((void*)c.open, cur_dev, (size_t)c.B, cudaMemcpyDeviceToDevice, h->stream));
         c.n_closed = cur_closed;
+    }
+    if (ring_touched) {           // (after the copy above: it still reads the ring)
+        CK(h, cudaEventRecord(h->ring_free[wp], h->stream));
+        h->ring_used[wp] = true;
+        ++h->windows;
     }
     rc = ship_window(h, first_day, n_days);
     if (rc != DYS_OK) return rc;
