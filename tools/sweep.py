@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Monte-Carlo parameter sweep (BASELINE.json configs[4]): replicas of one loaded city over a grid of
-norm_factor x quarantine compliance.  Replicas are independent: each GPU runs its share with no communication;
-a replica reuses the loaded population (dys_set_state + dys_set_run), so only the 11 bytes of state per agent are
-re-sent.  usage:  python tools/sweep.py [--agents-communities 89] [--grid 4] [--days 120]
-                  torchrun --nproc-per-node N tools/sweep.py ...        (replicas are dealt round-robin to the ranks)"""
+norm_factor x quarantine compliance, batched into ONE launch per window (dys_params.n_replicas); replicas are
+independent, so several GPUs each run their share with no communication.
+usage:  python tools/sweep.py [--communities 89] [--grid 4] [--days 120]
+        torchrun --nproc-per-node N tools/sweep.py ...        (the grid is dealt round-robin to the ranks)"""
 import argparse
 import json
 import os
@@ -28,23 +28,24 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     pop = synth_population(COMMUNITY * a.communities, seed=1)
-    eng = engine.Engine(pop, EpiParams(), device=local, flags=0)
-    init = pop.copy_state()
     norms = np.linspace(3.0, 9.0, a.grid)
     comps = np.linspace(0.25, 1.0, a.grid)
     jobs = [(i, j) for i in range(a.grid) for j in range(a.grid)][rank::world]
-    out, t0 = [], time.perf_counter()
-    for i, j in jobs:
-        eng.set_state(init["status"], init["t_inf"], init["t_q"], init["t_adm"], init["src"])
-        eng.set_run(norm_factor=float(norms[i]), compliance=float(comps[j]), seed=1000 + i * a.grid + j)
-        d = 0
-        while d < a.days:
-            n = min(7, a.days - d)
-            eng.step_many(d, n)
-            d += n
+    eng = engine.Engine(pop, EpiParams(), device=local, flags=0, replicas=len(jobs))
+    eng.set_replica_params([norms[i] for i, _ in jobs], [comps[j] for _, j in jobs], [1000 + i * a.grid + j for i, j in jobs])
+    t0 = time.perf_counter()
+    d = 0
+    while d < a.days:
+        n = min(7, a.days - d)
+        eng.step_many(d, n)
+        d += n
+    eng.sync()
+    dt = time.perf_counter() - t0
+    out = []
+    for r, (i, j) in enumerate(jobs):
+        eng.select_replica(r)
         s = eng.stats(a.days - 1)
         out.append({"norm_factor": float(norms[i]), "compliance": float(comps[j]), "ever_infected": int(s[9]), "dead": int(s[7])})
-    dt = time.perf_counter() - t0
     print(json.dumps({"rank": rank, "replicas": len(jobs), "seconds": dt, "agent_days_per_s": pop.N * a.days * len(jobs) / dt,
                       "results": out}))
 
