@@ -387,6 +387,7 @@ static int init_lockdown(dys_handle* h)
     for (size_t r = 0; r < R; ++r) nc[r] = c.n_closed;
     CK(h, cudaMemcpyAsync(h->ld.n_closed, nc.data(), sizeof(int32_t) * nc.size(), cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemsetAsync(h->ld.r_hist, 0, sizeof(double) * 16 * R, h->stream));
+    if (h->ld.r_sa) CK(h, cudaMemsetAsync(h->ld.r_sa, 0, sizeof(double) * 16 * R * (size_t)h->ld.S, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return DYS_OK;
 }
@@ -627,22 +628,28 @@ extern "C" int dys_select_replica(dys_handle* h, int32_t r)
     return DYS_OK;
 }
 
-extern "C" int dys_set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* bld_class)
+static int set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* bld_class, const int32_t* bld_area, const char* who)
 {
     if (!h) return DYS_ERR_INVALID_ARG;
-    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "dys_set_lockdown before dys_load_population");
+    if (!h->have_pop) return fail(h, DYS_ERR_STATE, "%s before dys_load_population", who);
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->stream));
     if (scenario == 0) { h->ld.mode = 0; return DYS_OK; }
-    if (!bld_class) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_lockdown: null bld_class");
-    if (scenario & ~(SC_GRADUAL | SC_ALL | SC_EDU | SC_REL)) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_lockdown: unknown scenario bits");
+    if (!bld_class) return fail(h, DYS_ERR_INVALID_ARG, "%s: null bld_class", who);
+    if (scenario & ~(SC_GRADUAL | SC_ALL | SC_EDU | SC_REL)) return fail(h, DYS_ERR_INVALID_ARG, "%s: unknown scenario bits", who);
     if (h->p.world > 1) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy needs the GLOBAL R: not in sharded mode (use the host policy)");
     if (h->c.diagnosis < 2 || h->c.diagnosis > 12) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy needs 2 <= diagnosis <= 12");
-    if (h->steps != 0 && h->last_day >= 0) return fail(h, DYS_ERR_STATE, "dys_set_lockdown after the run has started: reload the state first");
+    if (h->steps != 0 && h->last_day >= 0) return fail(h, DYS_ERR_STATE, "%s after the run has started: reload the state first", who);
     if (h->days_grid < 2) return fail(h, DYS_ERR_NOT_AVAILABLE, "the device lockdown policy needs the cooperative k_days launch");
     DevCtx& c = h->c;
     const int64_t R = h->R;
     int rc = DYS_OK;
+    if (bld_area) {
+        if (!(h->p.flags & DYS_WANT_SA_HIST)) return fail(h, DYS_ERR_NOT_AVAILABLE, "%s: the per-area policy reads the per-area histogram (DYS_WANT_SA_HIST)", who);
+        if (!(scenario & (SC_ALL | SC_EDU | SC_REL))) return fail(h, DYS_ERR_INVALID_ARG, "%s: no building class to close", who);
+        for (int64_t b = 0; b < c.B; ++b)
+            if (bld_area[b] < 0 || bld_area[b] >= c.S) return fail(h, DYS_ERR_INVALID_ARG, "%s: bld_area[%lld] = %d outside [0, %lld)", who, (long long)b, bld_area[b], (long long)c.S);
+    }
     if (!h->ld.flags) {
         uint8_t* cls = nullptr;
         rc = dev_alloc(h, &cls, c.B);
@@ -652,11 +659,32 @@ extern "C" int dys_set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* 
         if (rc != DYS_OK) return rc;
         h->ld.bld_class = cls;
     }
+    if (bld_area && !h->ld.r_sa) {
+        int32_t* area = nullptr;
+        rc = dev_alloc(h, &area, c.B);
+        if (rc == DYS_OK) rc = dev_alloc(h, &h->ld.r_sa, 16 * R * c.S);
+        if (rc == DYS_OK) rc = dev_alloc(h, &h->ld.what_sa, R * c.S);
+        if (rc != DYS_OK) return rc;
+        h->ld.bld_area = area;
+        h->ld.S = (int32_t)c.S;
+    }
     rc = copy_in(h, (void*)h->ld.bld_class, bld_class, (size_t)c.B);
+    if (rc == DYS_OK && bld_area) rc = copy_in(h, (void*)h->ld.bld_area, bld_area, sizeof(int32_t) * (size_t)c.B);
     if (rc != DYS_OK) return rc;
-    h->ld.scen = scenario;
+    h->ld.scen = scenario | (bld_area ? SC_DIFF : 0);
     h->ld.mode = 1;
     return init_lockdown(h);
+}
+
+extern "C" int dys_set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* bld_class)
+{
+    return set_lockdown(h, scenario, bld_class, nullptr, "dys_set_lockdown");
+}
+
+extern "C" int dys_set_lockdown_areas(dys_handle* h, int32_t scenario, const uint8_t* bld_class, const int32_t* bld_area)
+{
+    if (h && scenario != 0 && !bld_area) return fail(h, DYS_ERR_INVALID_ARG, "dys_set_lockdown_areas: null bld_area");
+    return set_lockdown(h, scenario, bld_class, bld_area, "dys_set_lockdown_areas");
 }
 
 extern "C" int dys_abort(dys_handle* h)

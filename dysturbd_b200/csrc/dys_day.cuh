@@ -1188,7 +1188,10 @@ __global__ void __launch_bounds__(BLOCK) k_publish(const DevCtx c) { publish_bod
 // (compute_R, :29-42, in the reference's order of float operations) and decides the open flags THREE days ahead -- the
 // decision for day t uses `Known R` of days t-1 and t-2, i.e. R of days t-1-diagnosis and t-2-diagnosis (:306-309), which are
 // long known -- so a whole run needs no host round trip and no flag upload.
+// SC_DIFF (contagious3.py:368-376, with the 'Vis_R' key of :371 read as the 'vis_R' that :319 writes): the same rule applied
+// area by area, each area on the R of its own residents (the day's per-area histogram, complete after the barrier).
 constexpr int SC_GRADUAL = 1, SC_ALL = 2, SC_EDU = 4, SC_REL = 8;      // scenario keywords; building class bits = 2, 4, 8
+constexpr int SC_DIFF = 16;
 struct LockdownPlan {
     int32_t mode;                                   // 0: the flags come from the host
     int32_t scen;                                   // SC_* bits
@@ -1196,6 +1199,10 @@ struct LockdownPlan {
     uint8_t* flags;                                 // [4][n_rep][B] ring by day & 3
     int32_t* n_closed;                              // [4][n_rep]
     double* r_hist;                                 // [16][n_rep] ring by day & 15: R of that day
+    const int32_t* bld_area;                        // SC_DIFF: [B] the building's area (row of the per-area histogram)
+    double* r_sa;                                   // SC_DIFF: [n_rep][16][S] ring by day & 15: per-area R of that day
+    uint8_t* what_sa;                               // SC_DIFF: [n_rep][S] the decision per area (scratch of the service block)
+    int32_t S;
 };
 
 constexpr int MAX_FUSED_DAYS = 14;
@@ -1361,7 +1368,7 @@ __device__ __forceinline__ void plan_cut(const uint32_t* __restrict__ work, int3
 // (slots 28-30), and the flags of day + 3
 __device__ __noinline__ void lockdown_service(const LockdownPlan ld, const int64_t B, const int recover, const int diagnosis,
                                               const double* __restrict__ pdf, const uint64_t seed, const int day, const int r,
-                                              const int n_rep, int64_t* __restrict__ stats)
+                                              const int n_rep, int64_t* __restrict__ stats, const int32_t* __restrict__ sa_hist)
 {
     __shared__ double s_vr[2];
     __shared__ int s_closed;
@@ -1381,13 +1388,38 @@ __device__ __noinline__ void lockdown_service(const LockdownPlan ld, const int64
         s_closed = 0;
     }
     __syncthreads();
-    const double vR = s_vr[0], prevVR = s_vr[1];
     enum { OPEN, FULL, HALF, KEEP };
-    int what = OPEN;                                                                            // building_lockdown, :57-107
-    if (ld.scen & SC_GRADUAL) {
-        if (vR > 1.0 && vR < 2.0) what = (prevVR <= 1.0 || prevVR >= 2.0) ? HALF : KEEP;
-        else if (vR >= 2.0) what = FULL;
-    } else if (vR > 1.0) what = FULL;
+    auto decide = [&](const double vR, const double prevVR) {                                   // building_lockdown, :57-107
+        if (ld.scen & SC_GRADUAL) {
+            if (vR > 1.0 && vR < 2.0) return (prevVR <= 1.0 || prevVR >= 2.0) ? HALF : KEEP;
+            return vR >= 2.0 ? FULL : OPEN;
+        }
+        return vR > 1.0 ? FULL : OPEN;
+    };
+    const bool diff = (ld.scen & SC_DIFF) != 0;
+    const uint8_t* what_sa = nullptr;
+    int what;
+    if (diff) {
+        // per area: R of the area's residents today (sas_R, :282-291) into the area's history, then the decision from the
+        // area's visible R of days t-1 and t-2 (sas_vis_R, :311-318; :369-376).  t-1-diagnosis <= day: already in the ring.
+        const int S = ld.S;
+        double* ring = ld.r_sa + (size_t)r * 16 * S;
+        uint8_t* w_out = ld.what_sa + (size_t)r * S;
+        int any = 0;
+        for (int s = tid; s < S; s += blockDim.x) {
+            const int32_t* hs = sa_hist + (size_t)s * HIST_LEN;
+            double sum_I = 0.0;
+            for (int i = 1; i < recover; ++i) sum_I = __dadd_rn(sum_I, __dmul_rn((double)__ldcg(hs + i), pdf[i]));
+            ring[(size_t)(day & 15) * S + s] = sum_I > 0.0 ? __ddiv_rn((double)__ldcg(hs), sum_I) : 0.0;
+            auto known_s = [&](const int d) { return d > diagnosis ? ring[(size_t)((d - diagnosis) & 15) * S + s] : 0.0; };
+            const int w = decide(known_s(t - 1), (t - 1 != 0) ? known_s(t - 2) : 0.0);
+            w_out[s] = (uint8_t)w;
+            any |= w != OPEN;
+        }
+        what = __syncthreads_or(any) ? KEEP : OPEN;          // (anything but OPEN: some area decides per building below)
+        what_sa = w_out;
+    } else
+        what = decide(s_vr[0], s_vr[1]);
     const uint32_t classes = (ld.scen & SC_ALL) ? (uint32_t)SC_ALL : (uint32_t)(ld.scen & (SC_EDU | SC_REL));
     uint8_t* dst = ld.flags + ((size_t)(t & 3) * n_rep + r) * B;
     const uint8_t* prev = ld.flags + ((size_t)((t - 1) & 3) * n_rep + r) * B;
@@ -1396,12 +1428,13 @@ __device__ __noinline__ void lockdown_service(const LockdownPlan ld, const int64
     int closed = 0;
     for (int64_t b = tid; b < B; b += blockDim.x) {
         uint8_t f = 1;
+        const int w = diff ? (int)what_sa[__ldg(ld.bld_area + b)] : what;
         const bool in_class = (__ldg(ld.bld_class + b) & classes) != 0;
-        if (what == FULL) f = in_class ? 0 : 1;
+        if (w == FULL) f = in_class ? 0 : 1;
         // (the reference draws exactly half of each class with np.random.choice; the device policy closes each building of
         // the class with probability 1/2 on a keyed draw -- host twin: host.building_lockdown(keyed=...))
-        else if (what == HALF) f = (in_class && keyed_uniform(seed, (uint32_t)(t - 1), STREAM_LOCKDOWN, (uint32_t)b, 0u) < 0.5) ? 0 : 1;
-        else if (what == KEEP) f = prev[b];
+        else if (w == HALF) f = (in_class && keyed_uniform(seed, (uint32_t)(t - 1), STREAM_LOCKDOWN, (uint32_t)b, 0u) < 0.5) ? 0 : 1;
+        else if (w == KEEP) f = prev[b];
         dst[b] = f;
         closed += f == 0;
     }
@@ -1630,7 +1663,8 @@ __global__ void __launch_bounds__(BLOCK, 4) k_days(const __grid_constant__ DevCt
                 int64_t* st = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(c.stats) + (size_t)r * c.out_stride);
                 fold_stats(c.part + (size_t)r * N_STATS * N_SLOTS, st);
                 if (plan.ld.mode)
-                    lockdown_service(plan.ld, c.B, c.recover, c.diagnosis, c.pdf, c.rep_params ? c.rep_params[r].seed : c.seed, day, r, n_rep, st);
+                    lockdown_service(plan.ld, c.B, c.recover, c.diagnosis, c.pdf, c.rep_params ? c.rep_params[r].seed : c.seed, day, r, n_rep, st,
+                                     c.sa_hist ? reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(c.sa_hist) + (size_t)r * c.out_stride) : nullptr);
             }
             // today's piece costs are complete: cut the population for the day after tomorrow (same parity as today)
             // (two days out of four: the load shifts over weeks, and a block that plans is late for the next barrier on a

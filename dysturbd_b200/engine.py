@@ -67,7 +67,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach",
-           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown", "dys_generate_routines", "dys_consume_day"]
+           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown", "dys_set_lockdown_areas", "dys_generate_routines", "dys_consume_day"]
 
 _lib = None
 
@@ -118,6 +118,7 @@ def load_library():
     lib.dys_select_replica.argtypes = [vp, i32]
     lib.dys_abort.argtypes = [vp]
     lib.dys_set_lockdown.argtypes = [vp, i32, vp]
+    lib.dys_set_lockdown_areas.argtypes = [vp, i32, vp, vp]
     lib.dys_consume_day.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, i64, vp]
     lib.dys_generate_routines.argtypes = [C.c_int, i64, i64, i32, i32] + [vp] * 8 + [C.c_uint64, vp]
     lib.dys_h2d_bytes.argtypes = [vp]
@@ -259,12 +260,19 @@ class Engine:
         self._ck(self.lib.dys_select_replica(self.h, int(r)))
         self._views = {}
 
-    def set_lockdown(self, scenario_bits, bld_class=None):
-        """decide the open flags on the device from now on (dys_set_lockdown); scenario_bits = 0 switches it off"""
+    def set_lockdown(self, scenario_bits, bld_class=None, bld_area=None):
+        """decide the open flags on the device from now on (dys_set_lockdown); scenario_bits = 0 switches it off.
+        bld_area [B]: the per-area (DIFF) policy, each area on its own residents' R (dys_set_lockdown_areas)"""
         p = None
         if bld_class is not None:
             p, _keep = _ptr(np.ascontiguousarray(bld_class, dtype=np.uint8), None, self.pop.B)
-        self._ck(self.lib.dys_set_lockdown(self.h, int(scenario_bits), p))
+        if bld_area is not None:
+            a = np.ascontiguousarray(bld_area, dtype=np.int32)
+            if a.shape != (self.pop.B,):
+                raise ValueError("bld_area must have one entry per building")
+            self._ck(self.lib.dys_set_lockdown_areas(self.h, int(scenario_bits), p, a.ctypes.data))
+        else:
+            self._ck(self.lib.dys_set_lockdown(self.h, int(scenario_bits), p))
 
     def abort(self):
         self._ck(self.lib.dys_abort(self.h))

@@ -42,18 +42,20 @@ def building_classes(lu, usg):
     return np.where(np.isin(usg, EDU_CODES))[0], np.where(np.isin(usg, REL_CODES))[0], np.where(lu >= 3)[0]
 
 
-def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None, dtype=float):
+def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None, dtype=float, ids=None):
     """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
     (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice.
     keyed = (seed, day): the half closures of GRADUAL close each building of the class with probability 1/2 on the keyed
-    draw u(day, STREAM_LOCKDOWN, building) instead -- the host twin of the device policy (dys_set_lockdown)."""
+    draw u(day, STREAM_LOCKDOWN, building) instead -- the host twin of the device policy (dys_set_lockdown).
+    ids: the buildings' indices in the whole table when lu / usg / current are the rows of ONE area (the DIFF scenarios call
+    this once per area, contagious3.py:368-376); the keyed draws are keyed on those."""
     lockdown = np.ones(len(lu), dtype=dtype)      # (the reference's float64 vector; the model keeps its flags as bytes)
     edu, rel, non_res = classes if classes is not None else building_classes(lu, usg)
 
     def close(idx, half):
         if half and keyed is not None:
             from .philox_host import STREAM_LOCKDOWN, keyed_uniform
-            lockdown[idx[keyed_uniform(keyed[0], keyed[1], STREAM_LOCKDOWN, idx) < 0.5]] = 0
+            lockdown[idx[keyed_uniform(keyed[0], keyed[1], STREAM_LOCKDOWN, idx if ids is None else ids[idx]) < 0.5]] = 0
         elif half:
             lockdown[choice(idx, replace=False, size=int(idx.size * 0.5))] = 0
         else:
@@ -94,7 +96,7 @@ class EpidemicModel:
 
     def __init__(self, agents, build, bld_visits_by_agents, interaction_prob, scenario=('noLockdown',), params=None,
                  device=0, choice_seed=None, backend=None, population=None, compact=False, reduce_stats=None,
-                 upload_flags=True, keep_raw=False, lockdown='host'):
+                 upload_flags=True, keep_raw=False, lockdown='host', diff_key_fix=False):
         self.params = params or EpiParams()
         self.pop = population or Population.from_reference(agents, build, bld_visits_by_agents, interaction_prob,
                                                                    diagnosis=self.params.diagnosis)
@@ -137,6 +139,21 @@ class EpidemicModel:
         if self._reduce is not None:
             self._active = int(self._reduce(np.array([[self._active] + [0] * 63], dtype=np.int64))[0, 0])
         self._R = {}                 # day -> R of that day (contagious3.py:281)
+        # DIFF (per-area lockdown, contagious3.py:368-376).  The reference reads SAs[day-1]['Vis_R'] there but writes that
+        # dict under 'vis_R' (:319): every DIFF run ends in KeyError on day 1, and so does this class by default.
+        # diff_key_fix=True reads the key that is written -- the per-area policy the code evidently meant (pinned by the
+        # '*_keyfix' golden fixtures, made from the reference's own text with that one key repaired at exec time).
+        self._diff = 'DIFF' in self.scenario
+        self._diff_fix = bool(diff_key_fix)
+        self._Rsa = {}               # day -> per-area R of that day [S] (kept for the DIFF decision only)
+        if self._diff and self._diff_fix:
+            if self._reduce is not None:
+                raise NotImplementedError("DIFF decides per area from the rank's own areas: not wired for sharded populations")
+            area = np.maximum(np.asarray(p.bld_sa, dtype=np.int64), 0)
+            order = np.argsort(area, kind="stable")
+            cuts = np.searchsorted(area[order], np.arange(p.S + 1))
+            self._area_blds = [order[cuts[k]:cuts[k + 1]] for k in range(p.S)]          # building rows of each area, ascending
+            self._bld_area = area
         self._flags = {0: self.pop.open.astype(np.uint8)}   # day -> build[:,10] in force on that day (0 / 1 bytes)
         self._queued = 0             # next day to queue
         closes = self._closes = any(k in self.scenario for k in ('ALL', 'EDU', 'REL', 'DIFF'))
@@ -154,8 +171,8 @@ class EpidemicModel:
                                       ('REL', _engine.SC_REL)) if k in self.scenario)
             cls = (np.where(p.bld_lu >= 3, _engine.CLASS_NONRES, 0) | np.where(np.isin(p.bld_usg, EDU_CODES), _engine.CLASS_EDU, 0) |
                    np.where(np.isin(p.bld_usg, REL_CODES), _engine.CLASS_REL, 0)).astype(np.uint8)
-            if (bits & ~_engine.SC_GRADUAL) and 'DIFF' not in self.scenario:      # (DIFF: the host path mirrors the reference's KeyError)
-                self.sim.set_lockdown(bits, cls)
+            if (bits & ~_engine.SC_GRADUAL) and (not self._diff or self._diff_fix):   # (DIFF as shipped: the host path mirrors the reference's KeyError)
+                self.sim.set_lockdown(bits, cls, self._bld_area.astype(np.int32) if self._diff else None)
                 self.window = self.MAX_WINDOW
             else:
                 self.lockdown = 'host'           # a scenario that closes nothing
@@ -181,10 +198,12 @@ class EpidemicModel:
                 # no ALL / EDU / REL keyword: building_lockdown closes nothing whatever R is (contagious3.py:57-107), so the
                 # flags of every day after day 0 are all ones -- known without waiting for R (week-long windows)
                 self._flags[day] = self._ones
-            elif 'DIFF' in self.scenario:
+            elif self._diff and not self._diff_fix:
                 if prev != 0:
                     raise KeyError('Vis_R')      # the reference reads a key it never writes (:371 vs :319)
                 self._flags[day] = self._ones
+            elif self._diff:
+                self._flags[day] = self._diff_flags(prev)
             else:
                 cur = self._flags_for(prev)
                 prevVR = self._known_R(prev - 1) if prev != 0 else 0
@@ -194,6 +213,26 @@ class EpidemicModel:
                                                      classes=self._classes, dtype=np.uint8)
             self._flags.pop(day - 20, None)
         return self._flags[day]
+
+    def _sa_known_R(self, day):
+        d = self.params.diagnosis
+        return self._Rsa[day - d] if day > d else np.zeros(self.pop.S)                          # :311-318
+
+    def _diff_flags(self, prev):
+        """contagious3.py:368-376 (with the key repaired): building_lockdown once per area, in ascending area order, on the
+        area's own rows with the area's visible R of `prev` and of the day before.  Areas whose visible R is <= 1 are all
+        open and draw nothing, so only the others are visited (same np.random.choice sequence as the reference)."""
+        p, sc = self.pop, self.scenario
+        vR = self._sa_known_R(prev)
+        pv = self._sa_known_R(prev - 1) if prev != 0 else np.zeros(p.S)
+        cur = self._flags_for(prev)
+        out = np.ones(p.B, dtype=np.uint8)
+        keyed = (self.params.seed, prev) if self.lockdown == 'keyed' else None
+        for s in np.nonzero(vR > 1)[0]:
+            m = self._area_blds[s]
+            out[m] = building_lockdown(p.bld_lu[m], p.bld_usg[m], cur[m], sc, float(vR[s]), float(pv[s]), self._choice,
+                                       keyed=keyed, dtype=np.uint8, ids=m)
+        return out
 
     def _queue(self, n):
         first = self._queued
@@ -238,6 +277,9 @@ class EpidemicModel:
         sas = [float(x) for x in p.sa_ids]
         res['SAs'][day] = {'R': {sa: compute_R_from_hist(sa_hist[k], self._pdf, prm.recover) for k, sa in enumerate(sas)}}
         res['SAs'][day]['vis_R'] = {sa: (res['SAs'][day - prm.diagnosis]['R'][sa] if day > prm.diagnosis else 0) for sa in sas}
+        if self._diff:
+            self._Rsa[day] = np.array([res['SAs'][day]['R'][sa] for sa in sas], dtype=np.float64)
+            self._Rsa.pop(day - 2 * prm.diagnosis - 4, None)
         S = self._stats_dict(st, R, vis_R, closed_today)
         res['Stats'][day] = S
         res['Buildings'][day] = [[float(p.bld_ids[b]), int(bc[b]), int(bc[b]) / int(self._bld_pop[b])] for b in self._inhabited]
@@ -338,6 +380,9 @@ class EpidemicModel:
         self._R[day] = R
         dz = prm.diagnosis
         res['SAs'][day] = {'R': R_sa, 'vis_R': res['SAs'][day - dz]['R'] if day > dz else np.zeros(len(R_sa))}
+        if self._diff:
+            self._Rsa[day] = R_sa
+            self._Rsa.pop(day - 2 * dz - 4, None)
         S = self._stats_dict(st, R, self._known_R(day), closed_today)
         res['Stats'][day] = S
         res['Buildings'][day] = bc
@@ -381,7 +426,7 @@ class EpidemicModel:
         if hasattr(self.sim, "sync"):
             self.sim.sync()
         return {'day': self.day, 'state': {k: np.array(v) for k, v in self.sim.state().items()}, 'R': dict(self._R),
-                'flags': {d: np.array(f) for d, f in self._flags.items()}, 'active': self._active,
+                'R_areas': {d: np.array(v) for d, v in self._Rsa.items()}, 'flags': {d: np.array(f) for d, f in self._flags.items()}, 'active': self._active,
                 'choice_state': self._choice.__self__.get_state(), 'outputs': copy.deepcopy(self.outputs),
                 'scenario': list(self.scenario)}
 
@@ -394,6 +439,7 @@ class EpidemicModel:
         self.sim.set_state(st['status'], st['t_inf'], st['t_q'], st['t_adm'], st['src'])
         self.day = self._queued = int(ck['day'])
         self._R = dict(ck['R'])
+        self._Rsa = {d: np.array(v) for d, v in ck.get('R_areas', {}).items()}
         self._flags = {d: np.array(f) for d, f in ck['flags'].items()}
         self._active = int(ck['active'])
         self._choice.__self__.set_state(ck['choice_state'])

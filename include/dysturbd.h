@@ -167,6 +167,13 @@ int dys_select_replica(dys_handle* h, int32_t r);
 enum { DYS_SC_GRADUAL = 1, DYS_SC_ALL = 2, DYS_SC_EDU = 4, DYS_SC_REL = 8 };
 enum { DYS_CLASS_NONRES = 2, DYS_CLASS_EDU = 4, DYS_CLASS_REL = 8 };
 int dys_set_lockdown(dys_handle* h, int32_t scenario, const uint8_t* bld_class);
+/* The DIFF scenarios (contagious3.py:368-376): the same rule applied area by area -- bld_area[B] = the building's area
+ * (row of the per-area histogram, 0 <= bld_area[b] < S; build[:,3] ranked), each area judged on the R of its own residents
+ * `diagnosis` days back (sas_vis_R, :311-318) and the day before.  As shipped, the reference cannot run these scenarios: :371
+ * reads SAs[day-1]['Vis_R'] while :319 writes 'vis_R' (KeyError on day 1); this entry point implements the loop with
+ * that key read as written (pinned by the tests/golden '*_keyfix' fixtures, made from the reference's text with the one
+ * key repaired).  Needs DYS_WANT_SA_HIST; the other conditions of dys_set_lockdown apply. */
+int dys_set_lockdown_areas(dys_handle* h, int32_t scenario, const uint8_t* bld_class, const int32_t* bld_area);
 /* asks a running launch to end at its next spin check (grid barrier / peer wait); the handle then reports
  * DYS_ERR_ABORTED until dys_set_state / dys_load_population.  Safe to call from another host thread. */
 int dys_abort(dys_handle* h);

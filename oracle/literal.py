@@ -247,8 +247,12 @@ SNAP_COLS = {"status": 13, "t_inf": 16, "n_inf": 17, "t_q": 19, "n_q": 20, "src_
 
 
 def reference_days(setup, scenario, max_days, draws, choice_seed=12345, capture_prob=False, verbose=False,
-                   overrides=None):
+                   overrides=None, diff_key_fix=False):
     """Run contagious3.py:172-387 literally for at most max_days days on a COPY of `setup`.
+    diff_key_fix: the ONE departure from the unmodified text this harness can make, and only on request: the `DIFF`
+    branch reads outputs['Results']['SAs'][day-1]['Vis_R'] (:371) while the loop writes that dict under 'vis_R' (:319), so
+    every DIFF scenario dies with KeyError on day 1.  With diff_key_fix the read uses the key that is written (SURVEY.md
+    section 8f-3: "the DIFF per-area variant after fixing the 'Vis_R' key"); fixtures made this way say so in their meta.
     Returns dict(snapshots=[per-day dict of agent columns + open flags for the NEXT day], outputs=the
     reference's own outputs dict, day_seconds=[...], P=[per-day (uninfected, infected, infection_prob)] if capture_prob)."""
     parameters, _, _, _ = _import_reference()
@@ -263,6 +267,10 @@ def reference_days(setup, scenario, max_days, draws, choice_seed=12345, capture_
     tail = "    day += 1"
     assert loop.count(tail) == 1
     loop = loop.replace(tail, "    __snapshot__()\n" + tail)
+    if diff_key_fix:
+        bad = "['Vis_R'][s]"
+        assert loop.count(bad) == 1 and loop.count("['vis_R'] = sas_vis_R") == 1
+        loop = loop.replace(bad, "['vis_R'][s]")
     if capture_prob:
         probe = "    rand_cont = np.random.random(infection_prob.shape)"
         assert loop.count(probe) == 1

@@ -52,13 +52,13 @@ def save(name, setup, run, meta):
           "total infected", outputs["Results"]["Stats"][len(snaps) - 1]["Total infected"])
 
 
-def city(name, n_households, csv_seed, setup_seed, scenario, norm, draws_kind, draws_seed, days, force_hh=(0,)):
+def city(name, n_households, csv_seed, setup_seed, scenario, norm, draws_kind, draws_seed, days, force_hh=(0,), diff_key_fix=False):
     ind, bld = literal.subsample_csv("/tmp/dys_golden_" + name, n_households, csv_seed, force_households=force_hh)
     setup = literal.reference_setup(ind, bld, seed=setup_seed)
     n = len(setup["agents"])
     draws = literal.DenseDraws(n, draws_seed) if draws_kind == "dense" else literal.PhiloxDraws(n, draws_seed)
-    run = literal.reference_days(setup, scenario, days, draws, overrides={"norm_factor": norm})
-    save(name, setup, run, dict(kind="city_subsample", n_households=n_households, csv_seed=csv_seed, setup_seed=setup_seed,
+    run = literal.reference_days(setup, scenario, days, draws, overrides={"norm_factor": norm}, diff_key_fix=diff_key_fix)
+    save(name, setup, run, dict(kind="city_subsample", diff_key_fix=diff_key_fix, n_households=n_households, csv_seed=csv_seed, setup_seed=setup_seed,
                                 scenario=scenario, norm_factor=norm, draws=draws_kind, draws_seed=draws_seed,
                                 choice_seed=12345))
 
@@ -80,6 +80,12 @@ def synthetic(name, n, seed, scenario, norm, draws_seed, days):
 
 if __name__ == "__main__":
     assert literal.available(), "needs /root/reference"
+    if "--diff" in sys.argv:
+        # the DIFF (per-area) lockdown with the reference's 'Vis_R' / 'vis_R' key mismatch repaired at exec time
+        # (literal.reference_days(diff_key_fix=True)); unrepaired, every DIFF scenario raises KeyError on day 1
+        city("city300_philox_diff_all_keyfix", 300, 1, 7, ["DIFF", "ALL"], 3.0, "philox", 99, 60, diff_key_fix=True)
+        city("city800_philox_diff_gradual_edu_rel_keyfix", 800, 2, 11, ["DIFF", "GRADUAL", "EDU", "REL"], 3.0, "philox", 5, 70, diff_key_fix=True)
+        sys.exit(0)
     # shipped city, household sub-samples (household id 0 forced in: exercises the whole-row isin of contagious3.py:267)
     city("city300_dense_nolockdown", 300, 1, 7, ["noLockdown"], 3.0, "dense", 3, 60)
     city("city300_philox_gradual_all", 300, 1, 7, ["GRADUAL", "ALL"], 3.0, "philox", 99, 60)

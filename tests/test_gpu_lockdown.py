@@ -9,13 +9,15 @@ from helpers import Fixture, compare_outputs
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["synth2000_philox_all", "city800_philox_edu_rel"])
+@pytest.mark.parametrize("name", ["synth2000_philox_all", "city800_philox_edu_rel", "city300_philox_diff_all_keyfix"])
 def test_device_lockdown_reproduces_the_reference(name):
     """ALL and EDU+REL close whole classes: no random choice is involved, so the device policy must reproduce the literal
-    contagious3.py run -- every Stats entry (Closed buildings, R, Known R included), SAs, Buildings, IO_mat, every day."""
+    contagious3.py run -- every Stats entry (Closed buildings, R, Known R included), SAs, Buildings, IO_mat, every day.
+    The DIFF fixture (per-area decisions on per-area R, dys_set_lockdown_areas) is the reference's text with its 'Vis_R' key
+    repaired (oracle/literal.py)."""
     from dysturbd_b200.host import EpidemicModel
     fx = Fixture(name)
-    m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params, lockdown='device')
+    m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params, lockdown='device', **fx.model_kw)
     assert m.lockdown == 'device' and m.window == 7
     m.run(max_days=fx.days)
     compare_outputs(m.outputs, fx.outputs, fx.days)
@@ -32,7 +34,7 @@ def _city(n=40000, seed=21):
     return synth_population(n, seed=seed, seeds_per_22493=120)
 
 
-@pytest.mark.parametrize("scenario", [["GRADUAL", "ALL"], ["GRADUAL", "EDU", "REL"], ["ALL"]])
+@pytest.mark.parametrize("scenario", [["GRADUAL", "ALL"], ["GRADUAL", "EDU", "REL"], ["ALL"], ["DIFF", "GRADUAL", "ALL"], ["DIFF", "EDU", "REL"]])
 def test_device_lockdown_equals_its_host_twin(scenario):
     """the keyed rule on the device (week-long windows, no uploads) against the same rule decided on the host day by day
     (4-day windows, flags uploaded): identical Stats every day and identical final state"""
@@ -40,8 +42,10 @@ def test_device_lockdown_equals_its_host_twin(scenario):
     from dysturbd_b200.population import EpiParams
     pop = _city()
     prm = EpiParams(norm_factor=7.0, seed=99)
-    a = EpidemicModel(None, None, None, None, scenario=scenario, params=prm, population=pop, lockdown='device', compact=True)
-    b = EpidemicModel(None, None, None, None, scenario=scenario, params=prm, population=pop, lockdown='keyed', compact=True)
+    kw = {"diff_key_fix": True} if "DIFF" in scenario else {}
+    a = EpidemicModel(None, None, None, None, scenario=scenario, params=prm, population=pop, lockdown='device', compact=True, **kw)
+    b = EpidemicModel(None, None, None, None, scenario=scenario, params=prm, population=pop, lockdown='keyed', compact=True, **kw)
+    assert a.lockdown == 'device'
     a.run(max_days=120)
     b.run(max_days=120)
     sa, sb = a.outputs['Results']['Stats'], b.outputs['Results']['Stats']

@@ -60,7 +60,7 @@ def test_epidemic_model_outputs_match_reference(name, eng):
     from dysturbd_b200.host import EpidemicModel
     fx = Fixture(name)
     m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
-                      choice_seed=fx.meta["choice_seed"])
+                      choice_seed=fx.meta["choice_seed"], **fx.model_kw)
     out = m.run(max_days=fx.days)
     compare_outputs(out, fx.outputs, fx.days)
     chain = np.array(out["Results"]["Infections chain"])

@@ -22,7 +22,7 @@ def test_host_outputs_match_reference(name, oracle_lib):
     from dysturbd_b200.host import EpidemicModel
     fx = Fixture(name)
     m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
-                      choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim)
+                      choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim, **fx.model_kw)
     out = m.run(max_days=fx.days)
     assert m.day == fx.days
     compare_outputs(out, fx.outputs, fx.days)
@@ -51,7 +51,7 @@ def test_written_json_is_the_reference_file(oracle_lib, tmp_path):
     from dysturbd_b200.host import EpidemicModel
     fx = Fixture("city300_philox_gradual_all")
     m = EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
-                      choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim)
+                      choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim, **fx.model_kw)
     m.run(max_days=fx.days)
     path = tmp_path / "sim0.json"
     m.write_json(path, total_time=1.5)
@@ -69,7 +69,7 @@ def test_checkpoint_and_resume(oracle_lib):
     from dysturbd_b200.host import EpidemicModel
     fx = Fixture("city300_philox_gradual_all")
     mk = lambda: EpidemicModel(fx.agents, fx.build, fx.visits, fx.ip, scenario=fx.scenario, params=fx.params,
-                               choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim)
+                               choice_seed=fx.meta["choice_seed"], backend=oracle_lib.OracleSim, **fx.model_kw)
     a = mk()
     for _ in range(9):
         a.step()
