@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dys_api.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "dys_common.cuh"), os.path.join(HERE, "csrc", "dys_day.cuh"),
-        os.path.join(HERE, "csrc", "dys_load.cuh"), os.path.join(HERE, "csrc", "dys_routine.cuh"), os.path.join(HERE, "csrc", "philox.cuh"),
+        os.path.join(HERE, "csrc", "dys_load.cuh"), os.path.join(HERE, "csrc", "dys_routine.cuh"), os.path.join(HERE, "csrc", "dys_network.cuh"),
+        os.path.join(HERE, "csrc", "philox.cuh"),
         os.path.join(HERE, "..", "include", "dysturbd.h")]
 LIB = os.path.join(HERE, "libdysturbd.so")
 

@@ -9,12 +9,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cmath>
+#include <ctime>
 #include <string>
 #include <vector>
 
 #include "dys_day.cuh"
 #include "dys_load.cuh"
 #include "dys_routine.cuh"
+#include "dys_network.cuh"
 
 using namespace dys;
 
@@ -157,6 +161,275 @@ static int copy_in(dys_handle* h, void* dst, const void* src, size_t bytes)
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+// ---- network construction: handle-free calls, host pointers in and out ----
+namespace {
+struct DevTmp {                      // device scratch of one call, freed on every exit path
+    std::vector<void*> ptrs;
+    cudaError_t e = cudaSuccess;
+    template <typename T>
+    T* get(size_t count)
+    {
+        void* d = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&d, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(d);
+        return (T*)d;
+    }
+    template <typename T>
+    T* up(const T* src, size_t count)
+    {
+        T* d = get<T>(count);
+        if (e == cudaSuccess && count) e = cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice);
+        return d;
+    }
+    ~DevTmp() { for (void* p : ptrs) cudaFree(p); }
+};
+
+int pick_device(int device, const char* who)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, DYS_ERR_CUDA, "%s: no CUDA device: this library has no CPU fallback", who);
+    if (device < 0 || device >= ndev) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: device %d out of range", who, device);
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: cudaSetDevice failed", who);
+    return DYS_OK;
+}
+}  // namespace
+
+extern "C" int dys_similarity_edges(int device, int64_t n, const double* age, const double* income, const double* x, const double* y,
+                                    const int64_t* household, double w_a, double w_i, double w_d, double min_prob,
+                                    int64_t* indptr /* [n+1] out */, int64_t capacity, int32_t* col, double* prob, double* maxes /* [3] out, nullable */)
+{
+    const char* who = "dys_similarity_edges";
+    if (n <= 0 || !age || !income || !x || !y || !household || !indptr) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: null or empty argument", who);
+    if (n > 0x7fffffffll) return fail(nullptr, DYS_ERR_RANGE, "%s: more than 2^31 - 1 agents", who);
+    for (int64_t i = 0; i < n; ++i)
+        if (!std::isfinite(age[i]) || !std::isfinite(income[i]) || !std::isfinite(x[i]) || !std::isfinite(y[i]))
+            return fail(nullptr, DYS_ERR_RANGE, "%s: agent %lld has a non-finite age, income or home coordinate", who, (long long)i);
+    int rc = pick_device(device, who);
+    if (rc != DYS_OK) return rc;
+    // normalisers: max |difference| of a column = max - min (exactly: rounded subtraction is monotone); the largest home
+    // distance is searched over the DISTINCT home coordinates
+    SimParams q{};
+    q.n = n;
+    const auto mm_a = std::minmax_element(age, age + n), mm_i = std::minmax_element(income, income + n);
+    q.max_age = *mm_a.second - *mm_a.first;
+    q.max_inc = *mm_i.second - *mm_i.first;
+    std::vector<std::pair<double, double>> pts((size_t)n);
+    for (int64_t i = 0; i < n; ++i) pts[(size_t)i] = {x[i], y[i]};
+    std::sort(pts.begin(), pts.end());
+    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    const int64_t U = (int64_t)pts.size();
+    std::vector<double> ux((size_t)U), uy((size_t)U);
+    for (int64_t i = 0; i < U; ++i) { ux[(size_t)i] = pts[(size_t)i].first; uy[(size_t)i] = pts[(size_t)i].second; }
+    DevTmp t;
+    const double* d_ux = t.up(ux.data(), (size_t)U);
+    const double* d_uy = t.up(uy.data(), (size_t)U);
+    unsigned long long* d_max = t.get<unsigned long long>(1);
+    if (t.e == cudaSuccess) t.e = cudaMemset(d_max, 0, 8);
+    unsigned long long bits = 0;
+    if (t.e == cudaSuccess) {
+        k_max_d2<<<grid_for(U, NET_BLOCK), NET_BLOCK>>>(d_ux, d_uy, U, d_max);
+        t.e = cudaMemcpy(&bits, d_max, 8, cudaMemcpyDeviceToHost);
+    }
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    double max_d2;
+    memcpy(&max_d2, &bits, 8);
+    q.max_dist = std::sqrt(max_d2);
+    q.w_a = w_a; q.w_i = w_i; q.w_d = w_d; q.min_prob = min_prob;
+    const auto unit = [](double w) { return w > 0.0 && w <= 1.0; };
+    q.prefilter = unit(w_a) && unit(w_i) && unit(w_d) && min_prob >= 0.0 && min_prob < 1.0 && q.max_age > 0.0 && q.max_inc > 0.0 && q.max_dist > 0.0;
+    const double slack = (1.0 - min_prob) * 1.001 + 1e-9;
+    q.pre_a = slack * q.max_age;
+    q.pre_i = slack * q.max_inc;
+    q.pre_d2 = slack * q.max_dist * slack * q.max_dist * 1.001;
+    if (maxes) { maxes[0] = q.max_age; maxes[1] = q.max_inc; maxes[2] = q.max_dist; }
+    const double* d_age = t.up(age, (size_t)n);
+    const double* d_inc = t.up(income, (size_t)n);
+    const double* d_x = t.up(x, (size_t)n);
+    const double* d_y = t.up(y, (size_t)n);
+    const int64_t* d_hh = t.up(household, (size_t)n);
+    int64_t* d_cnt = t.get<int64_t>((size_t)n + 1);
+    const unsigned grid = grid_for(n, NET_ROWS);
+    if (t.e == cudaSuccess) {
+        k_sim_edges<false><<<grid, NET_BLOCK>>>(q, d_age, d_inc, d_x, d_y, d_hh, d_cnt, nullptr, nullptr, nullptr);
+        t.e = cudaMemcpy(indptr + 1, d_cnt, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    }
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    indptr[0] = 0;
+    for (int64_t i = 0; i < n; ++i) indptr[i + 1] += indptr[i];
+    const int64_t E = indptr[n];
+    if (!col && !prob) return DYS_OK;                                   // sizing call: indptr[n] = number of edges
+    if (!col || !prob) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: col and prob go together", who);
+    if (capacity < E) return fail(nullptr, DYS_ERR_RANGE, "%s: %lld edges do not fit the capacity of %lld", who, (long long)E, (long long)capacity);
+    if (t.e == cudaSuccess) t.e = cudaMemcpy(d_cnt, indptr, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice);
+    int32_t* d_col = t.get<int32_t>((size_t)E);
+    double* d_prob = t.get<double>((size_t)E);
+    if (t.e == cudaSuccess) {
+        k_sim_edges<true><<<grid, NET_BLOCK>>>(q, d_age, d_inc, d_x, d_y, d_hh, nullptr, d_cnt, d_col, d_prob);
+        t.e = cudaGetLastError();
+        if (t.e == cudaSuccess && E) t.e = cudaMemcpy(col, d_col, 4 * (size_t)E, cudaMemcpyDeviceToHost);
+        if (t.e == cudaSuccess && E) t.e = cudaMemcpy(prob, d_prob, 8 * (size_t)E, cudaMemcpyDeviceToHost);
+    }
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    return DYS_OK;
+}
+
+namespace {
+struct SpCsrOut {                    // the reachable vertices of every source as CSR instead of dense rows
+    int64_t* ptr;                    // [n_sources + 1]
+    int64_t capacity;
+    int32_t* col;
+    double* dist;
+    int32_t skip_self;
+};
+}  // namespace
+
+static int shortest_paths_impl(const char* who, int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
+                               int64_t n_sources, const int32_t* sources, double* out /* [n_sources][n] or null */,
+                               const SpCsrOut* csr /* or null */, double* info /* [4], nullable */)
+{
+    const auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; };
+    const double t_start = now();
+    double t_relax = 0.0, t_out = 0.0;
+    if (n <= 0 || !indptr || n_sources < 0 || (n_sources && (!sources || (!out && !csr)))) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: null or empty argument", who);
+    if (csr && (!csr->ptr || csr->capacity < 0 || (csr->capacity && (!csr->col || !csr->dist)))) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: bad output arrays", who);
+    if (csr) csr->ptr[0] = 0;
+    if (n > 0x7fffffffll) return fail(nullptr, DYS_ERR_RANGE, "%s: more than 2^31 - 1 vertices", who);
+    const int64_t E = indptr[n];
+    if (indptr[0] != 0 || E < 0 || (E && (!indices || !weights))) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: bad CSR arrays", who);
+    for (int64_t v = 0; v < n; ++v)
+        if (indptr[v + 1] < indptr[v]) return fail(nullptr, DYS_ERR_RANGE, "%s: indptr is not monotone at row %lld", who, (long long)v);
+    for (int64_t e = 0; e < E; ++e) {
+        if (indices[e] < 0 || indices[e] >= n) return fail(nullptr, DYS_ERR_RANGE, "%s: edge %lld points outside the graph", who, (long long)e);
+        if (!(weights[e] >= 0.0)) return fail(nullptr, DYS_ERR_RANGE, "%s: edge %lld has a negative or NaN weight", who, (long long)e);
+    }
+    for (int64_t k = 0; k < n_sources; ++k)
+        if (sources[k] < 0 || sources[k] >= n) return fail(nullptr, DYS_ERR_RANGE, "%s: source %lld outside the graph", who, (long long)k);
+    if (info) info[0] = info[1] = info[2] = info[3] = 0.0;
+    if (n_sources == 0) return DYS_OK;
+    int rc = pick_device(device, who);
+    if (rc != DYS_OK) return rc;
+    // in-edge lists (a vertex pulls from its predecessors): counting sort of the edges by destination, sources ascending
+    std::vector<int64_t> in_ptr((size_t)n + 1, 0);
+    for (int64_t e = 0; e < E; ++e) ++in_ptr[(size_t)indices[e] + 1];
+    for (int64_t v = 0; v < n; ++v) in_ptr[(size_t)v + 1] += in_ptr[(size_t)v];
+    std::vector<int32_t> in_src((size_t)E);
+    std::vector<double> in_w((size_t)E);
+    {
+        std::vector<int64_t> cur(in_ptr.begin(), in_ptr.end() - 1);
+        for (int64_t u = 0; u < n; ++u)
+            for (int64_t e = indptr[u]; e < indptr[u + 1]; ++e) {
+                const int64_t at = cur[(size_t)indices[e]]++;
+                in_src[(size_t)at] = (int32_t)u;
+                in_w[(size_t)at] = weights[e];
+            }
+    }
+    // sources per batch: a multiple of 32, at most 1024, and D[n][batch] plus its transposed copy within ~4 GB
+    int64_t max_batch = 1024;
+    if (const char* e = getenv("DYS_SP_BATCH")) max_batch = std::max<int64_t>(32, std::min<int64_t>(1024, atoll(e) / 32 * 32));
+    int64_t batch = std::min<int64_t>(max_batch, ((n_sources + 31) / 32) * 32);
+    while (batch > 32 && (double)n * (double)batch * 16.0 > 4.0e9) batch -= 32;
+    const char* e_pv = getenv("DYS_SP_VERTEX_MARKS");                   // developer A/B: one "changed" mark per vertex
+    const int fpv = (e_pv && atoi(e_pv)) ? 1 : (int)(batch / 32);
+    DevTmp t;
+    const int64_t* d_ptr = t.up(in_ptr.data(), (size_t)n + 1);
+    const int32_t* d_src = t.up(in_src.data(), (size_t)E);
+    const double* d_w = t.up(in_w.data(), (size_t)E);
+    double* d_D = t.get<double>((size_t)n * (size_t)batch);
+    double* d_out = t.get<double>((size_t)n * (size_t)batch);
+    int32_t* d_sources = t.get<int32_t>((size_t)batch);
+    int64_t* d_cnt = csr ? t.get<int64_t>((size_t)batch + 1) : nullptr;
+    int32_t* d_ccol = nullptr;
+    double* d_cdist = nullptr;
+    size_t c_room = 0;                                                  // (grown to the largest batch seen)
+    std::vector<int64_t> h_cnt((size_t)batch + 1);
+    const size_t n_marks = (size_t)n * (size_t)fpv;
+    uint8_t* d_dirty = t.get<uint8_t>(2 * n_marks);
+    constexpr int GROUP = 8;                                            // sweeps queued between two looks at the `changed` words
+    int32_t* d_changed = t.get<int32_t>(GROUP);
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    const unsigned relax_grid = grid_for(n * batch, NET_BLOCK);
+    int total_sweeps = 0;
+    for (int64_t k0 = 0; k0 < n_sources && t.e == cudaSuccess; k0 += batch) {
+        const int nb = (int)std::min<int64_t>(batch, n_sources - k0);
+        t.e = cudaMemcpy(d_sources, sources + k0, 4 * (size_t)nb, cudaMemcpyHostToDevice);
+        if (t.e == cudaSuccess) t.e = cudaMemset(d_dirty, 0, 2 * n_marks);
+        if (t.e != cudaSuccess) break;
+        const double t0 = now();
+        k_sp_init<<<relax_grid, NET_BLOCK>>>(d_D, n, (int)batch, d_sources, nb, d_dirty, fpv);
+        int cur = 0;
+        bool done = false;
+        // every sweep moves the frontier at least one edge further along each shortest path: n sweeps always suffice
+        for (int64_t guard = 0; !done && guard <= n + GROUP; guard += GROUP) {
+            t.e = cudaMemsetAsync(d_changed, 0, 4 * GROUP);
+            for (int g = 0; g < GROUP && t.e == cudaSuccess; ++g) {
+                uint8_t* prev = d_dirty + (size_t)cur * n_marks;
+                uint8_t* next = d_dirty + (size_t)(cur ^ 1) * n_marks;
+                t.e = cudaMemsetAsync(next, 0, n_marks);
+                k_sp_relax<<<relax_grid, NET_BLOCK>>>(n, (int)batch, d_ptr, d_src, d_w, d_D, prev, next, d_changed + g, fpv);
+                cur ^= 1;
+            }
+            int32_t ch[GROUP];
+            if (t.e == cudaSuccess) t.e = cudaMemcpy(ch, d_changed, sizeof(ch), cudaMemcpyDeviceToHost);
+            if (t.e != cudaSuccess) break;
+            for (int g = 0; g < GROUP; ++g) {
+                if (!ch[g]) { done = true; break; }
+                ++total_sweeps;
+            }
+        }
+        if (t.e != cudaSuccess) break;
+        if (!done) return fail(nullptr, DYS_ERR_STATE, "%s: the relaxation did not settle", who);
+        const double t1 = now();
+        t_relax += t1 - t0;
+        k_sp_transpose<<<dim3(grid_for(n, 32), (unsigned)(batch / 32)), NET_BLOCK>>>(d_D, n, (int)batch, nb, d_out);
+        if (out) t.e = cudaMemcpy(out + k0 * n, d_out, 8 * (size_t)nb * (size_t)n, cudaMemcpyDeviceToHost);
+        if (csr && t.e == cudaSuccess) {
+            const unsigned cgrid = grid_for((int64_t)nb * 32, NET_BLOCK);
+            k_sp_compact<false><<<cgrid, NET_BLOCK>>>(d_out, n, nb, d_sources, csr->skip_self, d_cnt + 1, nullptr, nullptr, nullptr);
+            t.e = cudaMemcpy(h_cnt.data() + 1, d_cnt + 1, 8 * (size_t)nb, cudaMemcpyDeviceToHost);
+            if (t.e != cudaSuccess) break;
+            h_cnt[0] = 0;
+            for (int k = 0; k < nb; ++k) h_cnt[(size_t)k + 1] += h_cnt[(size_t)k];
+            const int64_t m = h_cnt[(size_t)nb], base = csr->ptr[k0];
+            if (base + m > csr->capacity)
+                return fail(nullptr, DYS_ERR_RANGE, "%s: the reachable pairs do not fit the capacity of %lld (at least %lld after %lld sources)", who,
+                            (long long)csr->capacity, (long long)(base + m), (long long)(k0 + nb));
+            for (int k = 0; k < nb; ++k) csr->ptr[k0 + k + 1] = base + h_cnt[(size_t)k + 1];
+            if (m > 0) {
+                if ((size_t)m > c_room) {
+                    c_room = (size_t)m + (size_t)m / 4;
+                    d_ccol = t.get<int32_t>(c_room);
+                    d_cdist = t.get<double>(c_room);
+                }
+                if (t.e == cudaSuccess) t.e = cudaMemcpy(d_cnt, h_cnt.data(), 8 * (size_t)(nb + 1), cudaMemcpyHostToDevice);
+                if (t.e != cudaSuccess) break;
+                k_sp_compact<true><<<cgrid, NET_BLOCK>>>(d_out, n, nb, d_sources, csr->skip_self, nullptr, d_cnt, d_ccol, d_cdist);
+                t.e = cudaMemcpy(csr->col + base, d_ccol, 4 * (size_t)m, cudaMemcpyDeviceToHost);
+                if (t.e == cudaSuccess) t.e = cudaMemcpy(csr->dist + base, d_cdist, 8 * (size_t)m, cudaMemcpyDeviceToHost);
+            }
+        }
+        t_out += now() - t1;
+    }
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    if (info) { info[0] = (double)total_sweeps; info[1] = now() - t_start - t_relax - t_out; info[2] = t_relax; info[3] = t_out; }
+    return DYS_OK;
+}
+
+extern "C" int dys_shortest_paths(int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
+                                  int64_t n_sources, const int32_t* sources, double* out /* [n_sources][n] */, double* info /* [4], nullable */)
+{
+    if (n_sources > 0 && !out) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_shortest_paths: null out");
+    return shortest_paths_impl("dys_shortest_paths", device, n, indptr, indices, weights, n_sources, sources, out, nullptr, info);
+}
+
+extern "C" int dys_shortest_paths_csr(int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
+                                      int64_t n_sources, const int32_t* sources, int32_t skip_self, int64_t* out_ptr /* [n_sources + 1] */,
+                                      int64_t capacity, int32_t* out_col, double* out_dist, double* info /* [4], nullable */)
+{
+    if (!out_ptr) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_shortest_paths_csr: null out_ptr");
+    const SpCsrOut csr{out_ptr, capacity, out_col, out_dist, skip_self};
+    return shortest_paths_impl("dys_shortest_paths_csr", device, n, indptr, indices, weights, n_sources, sources, nullptr, &csr, info);
+}
 
 extern "C" const char* dys_version(void) { return DYS_CHECKS ? "dysturbd-b200 0.2 (sm_100a, checked build)" : "dysturbd-b200 0.2 (sm_100a)"; }
 

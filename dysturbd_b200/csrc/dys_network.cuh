@@ -1,0 +1,238 @@
+// Network construction on the device: the two O(N^2) steps that precede the day loop.
+//
+//  * k_sim_edges   -- the agent-agent edges of communities.create_network (communities.py:22-40, 65-70): every ordered pair is
+//                     scored as the reference scores it (same float64 operations in the same order, no fused multiply-add),
+//                     pairs above the threshold come out as CSR rows in np.where order.  No N x N matrix exists anywhere:
+//                     a block keeps 8 rows and walks the columns in shared-memory tiles.
+//  * k_sp_relax    -- contagious3.py:124-130, scipy.sparse.csgraph.shortest_path: label-correcting relaxation for a batch of
+//                     sources at once, D[vertex][source] with the sources contiguous (a warp relaxes one vertex for 32 sources:
+//                     every neighbour read is one 256-byte line).  Distances are the left-to-right sums d(v) = fl(d(u) + w(u,v));
+//                     the least fixed point of that recurrence is unique (rounded addition is monotone and fl(d + w) >= d for
+//                     w >= 0), so the result is bit-identical to Dijkstra's whatever order the relaxations happen in.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dys {
+
+constexpr int NET_BLOCK = 256;
+constexpr int NET_ROWS = NET_BLOCK / 32;      // rows per block of k_sim_edges (one warp each)
+constexpr int NET_TILE = 256;                 // columns staged per step
+
+__device__ __forceinline__ void atomic_max_double_nonneg(unsigned long long* addr, const double v)
+{
+    atomicMax(addr, (unsigned long long)__double_as_longlong(v));      // (non-negative doubles order like their bit patterns)
+}
+
+// max over pairs of dx^2 + dy^2 (the largest distance is its sqrt: sqrt is monotone) -- communities.py:36 `np.max(agent_dists)`
+__global__ void __launch_bounds__(NET_BLOCK) k_max_d2(const double* __restrict__ x, const double* __restrict__ y, const int64_t n,
+                                                      unsigned long long* __restrict__ out_bits)
+{
+    __shared__ double sx[NET_TILE], sy[NET_TILE];
+    __shared__ double s_red[NET_BLOCK / 32];
+    const int64_t i = (int64_t)blockIdx.x * NET_BLOCK + threadIdx.x;
+    const double xi = i < n ? x[i] : 0.0, yi = i < n ? y[i] : 0.0;
+    double best = 0.0;
+    for (int64_t j0 = 0; j0 < n; j0 += NET_TILE) {
+        const int64_t j = j0 + threadIdx.x;
+        sx[threadIdx.x] = j < n ? x[j] : xi;
+        sy[threadIdx.x] = j < n ? y[j] : yi;
+        __syncthreads();
+        if (i < n) {
+            const int m = (int)((n - j0) < NET_TILE ? (n - j0) : NET_TILE);
+            for (int k = 0; k < m; ++k) {
+                const double dx = __dsub_rn(sx[k], xi), dy = __dsub_rn(sy[k], yi);
+                const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                best = d2 > best ? d2 : best;
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < NET_BLOCK / 32; ++k) best = s_red[k] > best ? s_red[k] : best;
+        atomic_max_double_nonneg(out_bits, best);
+    }
+}
+
+struct SimParams {
+    int64_t n;
+    double max_age, max_inc, max_dist;       // the three normalisers (communities.py:27, 30, 36)
+    double w_a, w_i, w_d, min_prob;
+    int32_t prefilter;                       // 1: pre_* bound the pairs that can pass (weights in (0, 1], finite positive normalisers)
+    double pre_a, pre_i, pre_d2;
+};
+
+// FILL = false: count[i] = edges of row i.  FILL = true: col / prob at rowptr[i] + rank, columns ascending.
+template <bool FILL>
+__global__ void __launch_bounds__(NET_BLOCK) k_sim_edges(const SimParams q, const double* __restrict__ age, const double* __restrict__ inc,
+                                                         const double* __restrict__ x, const double* __restrict__ y,
+                                                         const int64_t* __restrict__ hh, int64_t* __restrict__ count,
+                                                         const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+                                                         double* __restrict__ prob)
+{
+    __shared__ double s_age[NET_TILE], s_inc[NET_TILE], s_x[NET_TILE], s_y[NET_TILE];
+    __shared__ int64_t s_hh[NET_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * NET_ROWS + warp;
+    const bool row = i < q.n;
+    const double age_i = row ? age[i] : 0.0, inc_i = row ? inc[i] : 0.0, x_i = row ? x[i] : 0.0, y_i = row ? y[i] : 0.0;
+    const int64_t hh_i = row ? hh[i] : -1;
+    int64_t k = FILL && row ? rowptr[i] : 0;
+    for (int64_t j0 = 0; j0 < q.n; j0 += NET_TILE) {
+        const int64_t jt = j0 + threadIdx.x;
+        if (jt < q.n) {
+            s_age[threadIdx.x] = age[jt]; s_inc[threadIdx.x] = inc[jt]; s_x[threadIdx.x] = x[jt]; s_y[threadIdx.x] = y[jt];
+            s_hh[threadIdx.x] = hh[jt];
+        }
+        __syncthreads();
+        if (row) {
+            for (int t = 0; t < NET_TILE; t += 32) {
+                const int64_t j = j0 + t + lane;
+                bool edge = false;
+                double p = 0.0;
+                if (j < q.n && j != i) {
+                    const int s = t + lane;
+                    if (s_hh[s] == hh_i) {
+                        p = 1.0;                                                                // communities.py:39
+                        edge = p > q.min_prob;
+                    } else {
+                        const double da = fabs(__dsub_rn(s_age[s], age_i));                     // :29
+                        const double di = fabs(__dsub_rn(s_inc[s], inc_i));                     // :24
+                        const double dx = __dsub_rn(s_x[s], x_i), dy = __dsub_rn(s_y[s], y_i);
+                        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));      // :35 (minkowski, p = 2)
+                        // every factor is <= 1 and so are the weights: a pair whose age, income or distance factor alone is
+                        // below the threshold cannot pass (rounded products are monotone).  The bounds carry a 0.1 % margin.
+                        if (!(q.prefilter && (da > q.pre_a || di > q.pre_i || d2 > q.pre_d2))) {
+                            const double fa = __dsub_rn(1.0, __ddiv_rn(da, q.max_age));         // :30
+                            const double fi = __dsub_rn(1.0, __ddiv_rn(di, q.max_inc));         // :27
+                            const double fd = __dsub_rn(1.0, __ddiv_rn(__dsqrt_rn(d2), q.max_dist));  // :36
+                            p = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(q.w_a, fa), q.w_i), fi), q.w_d), fd);   // :38
+                            edge = p > q.min_prob;                                              // :65
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, edge);
+                if (FILL && edge) {
+                    const int64_t at = k + __popc(m & ((1u << lane) - 1u));
+                    col[at] = (int32_t)j;
+                    prob[at] = p;
+                }
+                k += __popc(m);
+            }
+        }
+        __syncthreads();
+    }
+    if (!FILL && row && lane == 0) count[i] = k;
+}
+
+// ---- shortest paths ----
+// D[v * batch + s]: distance from source s of the batch to vertex v
+__global__ void __launch_bounds__(NET_BLOCK) k_sp_init(double* __restrict__ D, const int64_t n, const int batch,
+                                                       const int32_t* __restrict__ sources, const int n_src, uint8_t* __restrict__ dirty,
+                                                       const int flags_per_vertex)
+{
+    const int64_t at = (int64_t)blockIdx.x * NET_BLOCK + threadIdx.x;
+    if (at >= n * batch) return;
+    const int64_t v = at / batch;
+    const int s = (int)(at - v * batch);
+    const bool is_src = s < n_src && sources[s] == v;
+    D[at] = is_src ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);
+    if (is_src) dirty[v * flags_per_vertex + (flags_per_vertex > 1 ? (s >> 5) : 0)] = 1;
+}
+
+// One warp = vertex v x 32 sources.  A vertex is looked at only if an in-neighbour changed in the previous sweep, and only
+// those neighbours are read.  The "changed" marks are kept per (vertex, group of 32 sources) -- flags_per_vertex = batch / 32 --
+// so a warp only follows the wave fronts of its own sources (flags_per_vertex = 1: one mark per vertex for the whole batch).  Updates are in place: a value read here is a real path length at all times, so reading one that
+// another warp is just improving is harmless (the neighbour is marked again and v comes back in the next sweep).
+__global__ void __launch_bounds__(NET_BLOCK) k_sp_relax(const int64_t n, const int batch, const int64_t* __restrict__ in_ptr,
+                                                        const int32_t* __restrict__ in_src, const double* __restrict__ in_w,
+                                                        double* D, const uint8_t* __restrict__ dirty_prev,
+                                                        uint8_t* __restrict__ dirty_next, int32_t* __restrict__ changed,
+                                                        const int flags_per_vertex)
+{
+    const int groups = batch >> 5;
+    const int64_t wid = ((int64_t)blockIdx.x * NET_BLOCK + threadIdx.x) >> 5;
+    if (wid >= n * groups) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t v = wid / groups;
+    const int g = (int)(wid - v * groups);
+    const int64_t e0 = in_ptr[v], e1 = in_ptr[v + 1];
+    const int64_t fs = flags_per_vertex;
+    const int fo = flags_per_vertex > 1 ? g : 0;
+    bool any = false;
+    for (int64_t e = e0 + lane; e < e1; e += 32) any |= dirty_prev[in_src[e] * fs + fo] != 0;
+    if (!__any_sync(0xffffffffu, any)) return;
+    double* mine = D + v * batch + g * 32 + lane;
+    const double old = *reinterpret_cast<volatile double*>(mine);
+    double best = old;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int32_t u = in_src[e];
+        if (!dirty_prev[u * fs + fo]) continue;
+        const double cand = __dadd_rn(*reinterpret_cast<const volatile double*>(D + (int64_t)u * batch + g * 32 + lane), in_w[e]);
+        best = cand < best ? cand : best;
+    }
+    const bool better = best < old;
+    if (better) *reinterpret_cast<volatile double*>(mine) = best;
+    if (__any_sync(0xffffffffu, better) && lane == 0) {
+        dirty_next[v * fs + fo] = 1;
+        *changed = 1;
+    }
+}
+
+// out[s][v] = D[v][s] (row-major rows per source, what shortest_path returns)
+__global__ void __launch_bounds__(NET_BLOCK) k_sp_transpose(const double* __restrict__ D, const int64_t n, const int batch, const int n_src,
+                                                            double* __restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    const int64_t v0 = (int64_t)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    for (int r = ty; r < 32; r += NET_BLOCK / 32) {
+        const int64_t v = v0 + r;
+        tile[r][tx] = (v < n && s0 + tx < batch) ? D[v * batch + s0 + tx] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += NET_BLOCK / 32) {
+        const int s = s0 + r;
+        const int64_t v = v0 + tx;
+        if (s < n_src && v < n) out[(int64_t)s * n + v] = tile[tx][r];
+    }
+}
+
+// rows[s][v] (what k_sp_transpose wrote) -> the reachable vertices of every source as CSR: FILL = false counts, FILL = true
+// writes (vertex, distance) at ptr[s] + rank, vertices ascending.  skip_self leaves the source itself out (the reference
+// sets the diagonal to inf before it takes exp(-dists), contagious3.py:126-127).
+template <bool FILL>
+__global__ void __launch_bounds__(NET_BLOCK) k_sp_compact(const double* __restrict__ rows, const int64_t n, const int n_src,
+                                                          const int32_t* __restrict__ sources, const int skip_self,
+                                                          int64_t* __restrict__ count, const int64_t* __restrict__ ptr,
+                                                          int32_t* __restrict__ col, double* __restrict__ dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = (int)(((int64_t)blockIdx.x * NET_BLOCK + threadIdx.x) >> 5);
+    if (s >= n_src) return;
+    const double* row = rows + (int64_t)s * n;
+    const int64_t self = skip_self ? (int64_t)sources[s] : -1;
+    int64_t k = FILL ? ptr[s] : 0;
+    for (int64_t v0 = 0; v0 < n; v0 += 32) {
+        const int64_t v = v0 + lane;
+        const double d = v < n ? row[v] : __longlong_as_double(0x7ff0000000000000ll);
+        const bool keep = d < __longlong_as_double(0x7ff0000000000000ll) && v != self;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (FILL && keep) {
+            const int64_t at = k + __popc(m & ((1u << lane) - 1u));
+            col[at] = (int32_t)v;
+            dist[at] = d;
+        }
+        k += __popc(m);
+    }
+    if (!FILL && lane == 0) count[s] = k;
+}
+
+}  // namespace dys

@@ -1,0 +1,148 @@
+"""Network construction on the GPU: the host-side mirror of what the reference does between
+`create_data` and the day loop --
+
+    G = create_network(agents, households, build)                 communities.py:7-77
+    dists = shortest_path(nx.to_scipy_sparse_matrix(G), ...)      contagious3.py:124-126
+    interaction_prob = np.exp(-dists[agent rows][:, agent cols])  contagious3.py:127-130
+
+-- for the agent block of that graph.  The reference materialises five N x N float64 matrices for the edges and an
+(N + B)^2 distance matrix; here the edges come out of `dys_similarity_edges` as CSR (no N x N array anywhere) and the
+distances out of `dys_shortest_paths` in row batches that are turned into interaction_prob rows at once.  Agent -> agent
+paths only run through agent nodes (agents have no incoming edge from a building), so the agent block is the whole story
+for interaction_prob.
+
+What stays on the host, on purpose: `-np.log(p)` over the E edges and `np.exp(-d)` over the reachable pairs.  Both are
+the reference's own numpy calls; a device log / exp is a different libm and would not be bit-identical, while the edge
+probabilities and the path sums are IEEE add / multiply / divide / sqrt only and ARE bit-identical on the device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import engine
+
+
+def agent_columns(agents, households, build):
+    """the per-agent columns create_network derives (communities.py:23-35), with its `argmax` look-ups: an id that is not
+    found resolves to row 0, as there"""
+    def rows_of(keys, table):
+        order = np.argsort(table, kind="stable")
+        pos = np.searchsorted(table[order], keys)
+        pos = np.minimum(pos, len(table) - 1)
+        hit = table[order][pos] == keys
+        return np.where(hit, order[pos], 0)           # (argmax of an all-False column is 0)
+    agent_hh = rows_of(agents[:, 1], households[:, 0])                                         # :23
+    hh_home = households[agent_hh, 1]                                                           # :33
+    agent_homes = rows_of(hh_home, build[:, 0])                                                 # :34
+    return dict(age=np.ascontiguousarray(agents[:, 4], dtype=np.float64),
+                income=np.ascontiguousarray(households[agent_hh, 2], dtype=np.float64),
+                x=np.ascontiguousarray(build[agent_homes, 6], dtype=np.float64),
+                y=np.ascontiguousarray(build[agent_homes, 7], dtype=np.float64),
+                household=np.ascontiguousarray(agent_hh, dtype=np.int64))
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise engine.DysError(rc, (lib.dys_last_error(None) or b"").decode())
+
+
+def similarity_edges(cols, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):
+    """communities.py:22-40, 65-70 -> (indptr[n+1], col[E], prob[E]) with prob == agents_prob[i, j] bit for bit"""
+    lib = engine.load_library()
+    n = len(cols["age"])
+    lib.dys_similarity_edges.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 5 + [C.c_double] * 4 + [C.c_void_p, C.c_int64] + [C.c_void_p] * 3
+    p = lambda k, dt: np.ascontiguousarray(cols[k], dtype=dt)
+    arr = [p("age", np.float64), p("income", np.float64), p("x", np.float64), p("y", np.float64), p("household", np.int64)]
+    head = [device, n] + [a.ctypes.data for a in arr] + [float(w_a), float(w_i), float(w_d), float(min_prob)]
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    _check(lib, lib.dys_similarity_edges(*head, indptr.ctypes.data, 0, None, None, None))      # sizing pass
+    E = int(indptr[-1])
+    col, prob = np.empty(E, dtype=np.int32), np.empty(E, dtype=np.float64)
+    _check(lib, lib.dys_similarity_edges(*head, indptr.ctypes.data, E, col.ctypes.data, prob.ctypes.data, None))
+    return indptr, col, prob
+
+
+def edge_weights(prob):
+    """the weight create_network gives an edge (communities.py:70): -log(p), with numpy's log as there"""
+    return -np.log(prob)
+
+
+def shortest_paths(indptr, indices, weights, sources, device=0, return_sweeps=False, return_info=False):
+    """scipy.sparse.csgraph.shortest_path(g, directed=True, indices=sources) -> float64 [len(sources), n]
+    return_info: also dict(sweeps, prep_s, relax_s, download_s) as the library measured them"""
+    lib = engine.load_library()
+    lib.dys_shortest_paths.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    sources = np.ascontiguousarray(sources, dtype=np.int32)
+    n = len(indptr) - 1
+    out = np.empty((len(sources), n), dtype=np.float64)
+    info = np.zeros(4)
+    _check(lib, lib.dys_shortest_paths(device, n, indptr.ctypes.data, indices.ctypes.data, weights.ctypes.data, len(sources),
+                                       sources.ctypes.data, out.ctypes.data, info.ctypes.data))
+    if return_info:
+        return out, dict(sweeps=int(info[0]), prep_s=info[1], relax_s=info[2], download_s=info[3])
+    return (out, int(info[0])) if return_sweeps else out
+
+
+def shortest_paths_csr(indptr, indices, weights, sources, capacity, skip_self=True, device=0, return_info=False):
+    """the same distances as CSR over the reachable vertices only: (ptr[len(sources)+1], col, dist), compacted on the device"""
+    lib = engine.load_library()
+    lib.dys_shortest_paths_csr.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    sources = np.ascontiguousarray(sources, dtype=np.int32)
+    ptr = np.zeros(len(sources) + 1, dtype=np.int64)
+    col, dist = np.empty(int(capacity), dtype=np.int32), np.empty(int(capacity), dtype=np.float64)
+    info = np.zeros(4)
+    _check(lib, lib.dys_shortest_paths_csr(device, len(indptr) - 1, indptr.ctypes.data, indices.ctypes.data, weights.ctypes.data,
+                                           len(sources), sources.ctypes.data, int(bool(skip_self)), ptr.ctypes.data, int(capacity),
+                                           col.ctypes.data, dist.ctypes.data, info.ctypes.data))
+    m = int(ptr[-1])
+    out = (ptr, col[:m], dist[:m])
+    return out + (dict(sweeps=int(info[0]), prep_s=info[1], relax_s=info[2], download_s=info[3]),) if return_info else out
+
+
+def components(indptr, indices):
+    """weakly connected components of the CSR graph (labels [n]); sources of one component share the vertices they reach"""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    n = len(indptr) - 1
+    g = sp.csr_matrix((np.ones(len(indices), dtype=np.int8), indices, indptr), shape=(n, n))
+    return connected_components(g, directed=True, connection="weak")[1]
+
+
+def interaction_prob(indptr, indices, weights, device=0, rows_per_call=2048):
+    """contagious3.py:124-130 for the agent block: interaction_prob = exp(-shortest path), 0 on the diagonal and where no
+    path exists, as a scipy CSR matrix (sorted indices).  Sources go to the device grouped by component and come back as
+    compacted (vertex, distance) lists, so neither an n x n matrix nor dense rows ever exist on the host."""
+    import scipy.sparse as sp
+    n = len(indptr) - 1
+    labels = components(indptr, indices)
+    reach = np.bincount(labels)[labels] - 1                      # vertices a source can reach at most (its component, less itself)
+    order = np.argsort(labels, kind="stable").astype(np.int32)
+    cols, vals, counts = [], [], np.zeros(n, dtype=np.int64)
+    for k0 in range(0, n, rows_per_call):
+        src = order[k0:k0 + rows_per_call]
+        ptr, c, d = shortest_paths_csr(indptr, indices, weights, src, int(reach[src].sum()), skip_self=True, device=device)
+        counts[src] = np.diff(ptr)
+        cols.append(c)
+        vals.append(np.exp(-d))                                                                 # :127
+    # rows were produced in `order`; put them back in agent order
+    cols, vals = np.concatenate(cols), np.concatenate(vals)
+    start_in_order = np.concatenate([[0], np.cumsum(counts[order])])[:-1]
+    out_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    pos_of = np.empty(n, dtype=np.int64)
+    pos_of[order] = start_in_order
+    take = np.arange(out_ptr[-1]) + np.repeat(pos_of - out_ptr[:-1], counts)
+    return sp.csr_matrix((vals[take], cols[take], out_ptr), shape=(n, n))
+
+
+def create_interaction(agents, households, build, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):
+    """agents, households, build (create_data's arrays) -> interaction_prob, i.e. communities.create_network's agent edges,
+    the all-pairs shortest paths and contagious3.py:127 in one go.  Returns (interaction_prob CSR, (indptr, col, weight))."""
+    indptr, col, prob = similarity_edges(agent_columns(agents, households, build), min_prob, w_a, w_i, w_d, device)
+    w = edge_weights(prob)
+    return interaction_prob(indptr, col, w, device=device), (indptr, col, w)

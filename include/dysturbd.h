@@ -271,6 +271,33 @@ int dys_generate_routines(int device, int64_t n_agents, int64_t n_bld, int32_t V
                           const int32_t* anchors, const int64_t* out_ptr, const int32_t* out_idx, const int64_t* in_ptr,
                           const int32_t* in_idx, const int64_t* near_ptr, const int32_t* near_idx, uint64_t seed,
                           int32_t* routine);
+/* Network construction (communities.py:22-40, 65-70 and contagious3.py:124-130) -- the two O(N^2) steps before the day loop.
+ * All pointers are HOST pointers.
+ *
+ * dys_similarity_edges: the agent-agent edges of create_network without its N x N matrices.  Per agent: age (agents[:,4]),
+ * household income (households[agent_hh, 2]), home coordinates (build[agent_homes, 6:8]) and household row (agent_hh).
+ * For every ordered pair i != j,  p = ((((w_a * fa) * w_i) * fi) * w_d) * fd  with  f = 1 - |difference| / max |difference|
+ * (Euclidean home distance for fd), p = 1 inside a household; an edge wherever p > min_prob.  Same float64 operations in the
+ * same order as the reference, so `prob` is bit-identical to agents_prob[i, j]; the caller forms the weight -log(p).
+ * Output: CSR with rows and columns ascending (np.where order).  indptr[n+1] is always written; with col == prob == NULL the
+ * call only sizes (indptr[n] = number of edges), otherwise capacity must hold them.  maxes[3] (nullable) = the normalisers. */
+int dys_similarity_edges(int device, int64_t n, const double* age, const double* income, const double* x, const double* y,
+                         const int64_t* household, double w_a, double w_i, double w_d, double min_prob, int64_t* indptr,
+                         int64_t capacity, int32_t* col, double* prob, double* maxes);
+/* dys_shortest_paths: scipy.sparse.csgraph.shortest_path(g, directed=True, indices=sources) for a CSR graph with non-negative
+ * weights (explicit zeros are edges, as in scipy): out[k][v] = length of the shortest path sources[k] -> v, +inf where there
+ * is none.  Bit-identical to Dijkstra's left-to-right sums.  Give the sources grouped by connected component:
+ * a batch of sources only touches the vertices its sources can reach.  info[4] (nullable) = relaxation sweeps that changed
+ * something (summed over the batches), then seconds spent on preparation + upload, in the relaxation, on transpose + download. */
+int dys_shortest_paths(int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
+                       int64_t n_sources, const int32_t* sources, double* out, double* info);
+/* the same distances, but only the vertices each source reaches, compacted on the device: out_ptr[n_sources + 1], then
+ * (out_col, out_dist) with the vertices of a source ascending -- a third of the bytes of the dense rows on the shipped city.
+ * skip_self != 0 leaves the source itself out (contagious3.py:126 sets the diagonal to inf before :127 takes exp(-dists)).
+ * capacity = entries out_col / out_dist can hold (the sizes of the sources' weak components bound it); DYS_ERR_RANGE if short. */
+int dys_shortest_paths_csr(int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
+                           int64_t n_sources, const int32_t* sources, int32_t skip_self, int64_t* out_ptr, int64_t capacity,
+                           int32_t* out_col, double* out_dist, double* info);
 const char* dys_version(void);
 
 #ifdef __cplusplus

@@ -418,3 +418,133 @@ int orc_routines(int64_t N, int32_t V, int32_t k, const int32_t* home, const int
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Network construction.  TEST INFRASTRUCTURE like everything in this file.
+ *
+ * orc_similarity_edges -- the agent-agent edges of communities.create_network (communities.py:22-40, 65-70) without the
+ * N x N matrices: for every ordered pair (i, j), i != j,
+ *     p = ((((w_a * fa) * w_i) * fi) * w_d) * fd          (communities.py:38, evaluated left to right)
+ *     fa = 1 - |age_j - age_i| / max|age diff|            (:29-30)
+ *     fi = 1 - |inc_j - inc_i| / max|income diff|         (:24-27)
+ *     fd = 1 - sqrt(dx^2 + dy^2) / max home distance      (:35-36, scipy.spatial.distance_matrix, p = 2)
+ *     p  = 1 if both agents are of one household          (:39)
+ * and an edge wherever p > min_prob (:65-70), rows ascending, columns ascending inside a row (np.where order).  The caller
+ * forms the weight -log(p) (the reference's np.log).  Two passes: count[n] (fill = 0), then fill with rowptr = scan(count).
+ * max_d2 = max over pairs of dx^2 + dy^2 (its sqrt is the largest distance: sqrt is monotone) is computed here too.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include <math.h>
+
+static double pair_prob(const double* age, const double* inc, const double* x, const double* y, const int64_t* hh,
+                        int64_t i, int64_t j, double max_age, double max_inc, double max_dist, double w_a, double w_i, double w_d)
+{
+    if (hh[i] == hh[j]) return 1.0;
+    const double fa = 1.0 - fabs(age[j] - age[i]) / max_age;
+    const double fi = 1.0 - fabs(inc[j] - inc[i]) / max_inc;
+    const double dx = x[j] - x[i], dy = y[j] - y[i];
+    const double fd = 1.0 - sqrt(dx * dx + dy * dy) / max_dist;
+    return ((((w_a * fa) * w_i) * fi) * w_d) * fd;
+}
+
+int orc_similarity_edges(int64_t n, const double* age, const double* inc, const double* x, const double* y, const int64_t* hh,
+                         double w_a, double w_i, double w_d, double min_prob, int fill, int64_t* count /* [n] */,
+                         const int64_t* rowptr /* [n+1], fill only */, int32_t* col, double* prob, double* maxes /* [3] out */)
+{
+    double lo_a = age[0], hi_a = age[0], lo_i = inc[0], hi_i = inc[0], max_d2 = 0.0;
+    for (int64_t i = 1; i < n; ++i) {
+        if (age[i] < lo_a) lo_a = age[i];
+        if (age[i] > hi_a) hi_a = age[i];
+        if (inc[i] < lo_i) lo_i = inc[i];
+        if (inc[i] > hi_i) hi_i = inc[i];
+    }
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_d2)
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = i + 1; j < n; ++j) {
+            const double dx = x[j] - x[i], dy = y[j] - y[i];
+            const double d2 = dx * dx + dy * dy;
+            if (d2 > max_d2) max_d2 = d2;
+        }
+    const double max_age = hi_a - lo_a, max_inc = hi_i - lo_i, max_dist = sqrt(max_d2);
+    maxes[0] = max_age; maxes[1] = max_inc; maxes[2] = max_dist;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t k = fill ? rowptr[i] : 0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const double p = pair_prob(age, inc, x, y, hh, i, j, max_age, max_inc, max_dist, w_a, w_i, w_d);
+            if (p > min_prob) {
+                if (fill) { col[k] = (int32_t)j; prob[k] = p; }
+                ++k;
+            }
+        }
+        if (!fill) count[i] = k;
+    }
+    return 0;
+}
+
+/* orc_shortest_paths -- contagious3.py:124-130: scipy.sparse.csgraph.shortest_path(g, directed=True) restricted to the rows
+ * of `sources`.  Dijkstra with a binary heap (lazy deletion); distances are the left-to-right sums d(v) = d(u) + w(u, v) along
+ * the path, which makes the result the least fixed point of d(v) = min_u fl(d(u) + w(u,v)) -- unique, whatever the order
+ * of relaxations, because rounded addition is monotone and fl(d + w) >= d for w >= 0.  out[k][v] = inf where unreachable. */
+typedef struct { double d; int32_t v; } heap_item;
+
+static void heap_push(heap_item* h, int64_t* n, double d, int32_t v)
+{
+    int64_t i = (*n)++;
+    while (i > 0) {
+        const int64_t p = (i - 1) / 2;
+        if (h[p].d <= d) break;
+        h[i] = h[p];
+        i = p;
+    }
+    h[i].d = d; h[i].v = v;
+}
+
+static heap_item heap_pop(heap_item* h, int64_t* n)
+{
+    const heap_item top = h[0], last = h[--(*n)];
+    int64_t i = 0;
+    for (;;) {
+        int64_t c = 2 * i + 1;
+        if (c >= *n) break;
+        if (c + 1 < *n && h[c + 1].d < h[c].d) ++c;
+        if (last.d <= h[c].d) break;
+        h[i] = h[c];
+        i = c;
+    }
+    h[i] = last;
+    return top;
+}
+
+int orc_shortest_paths(int64_t n, const int64_t* indptr, const int32_t* indices, const double* w, int64_t n_src,
+                       const int32_t* sources, double* out /* [n_src][n] */)
+{
+    const int64_t E = indptr[n];
+    for (int64_t e = 0; e < E; ++e)
+        if (!(w[e] >= 0.0) || indices[e] < 0 || indices[e] >= n) return -1;
+    int bad = 0;
+#pragma omp parallel
+    {
+        heap_item* heap = (heap_item*)malloc(sizeof(heap_item) * (size_t)(E + n + 1));
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t k = 0; k < n_src; ++k) {
+            double* d = out + k * n;
+            const int32_t s = sources[k];
+            if (!heap || s < 0 || s >= n) { bad = 1; continue; }
+            for (int64_t v = 0; v < n; ++v) d[v] = INFINITY;
+            int64_t hn = 0;
+            d[s] = 0.0;
+            heap_push(heap, &hn, 0.0, s);
+            while (hn > 0) {
+                const heap_item it = heap_pop(heap, &hn);
+                if (it.d > d[it.v]) continue;
+                for (int64_t e = indptr[it.v]; e < indptr[it.v + 1]; ++e) {
+                    const double nd = it.d + w[e];
+                    if (nd < d[indices[e]]) { d[indices[e]] = nd; heap_push(heap, &hn, nd, indices[e]); }
+                }
+            }
+        }
+        free(heap);
+    }
+    return bad ? -1 : 0;
+}

@@ -21,7 +21,7 @@ STAT_NAMES = ["active", "daily_inf", "recovered", "quarantined", "daily_quar", "
 def build(force=False):
     src = os.path.join(HERE, "dys_oracle.c")
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off", "-shared", src, "-o", LIB])
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off", "-shared", src, "-o", LIB, "-lm"])
     return LIB
 
 
@@ -202,3 +202,33 @@ class OracleSim:
     def events(self, day=None):
         n = int(self._stats[STAT_NAMES.index("n_events")])
         return self.ev_agent[:n].copy(), self.ev_src[:n].copy()
+
+
+def similarity_edges(age, income, x, y, hh, min_prob, w_a=1.0, w_i=1.0, w_d=1.0):
+    """oracle/dys_oracle.c:orc_similarity_edges -- communities.py:22-40, 65-70 without the N x N matrices.
+    Returns (indptr[n+1], col, prob, (max age diff, max income diff, max distance))."""
+    L = lib()
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    age, income, x, y, hh = c(age, np.float64), c(income, np.float64), c(x, np.float64), c(y, np.float64), c(hh, np.int64)
+    n = len(age)
+    L.orc_similarity_edges.argtypes = [C.c_int64] + [C.c_void_p] * 5 + [C.c_double] * 4 + [C.c_int] + [C.c_void_p] * 5
+    count, maxes = np.zeros(n, dtype=np.int64), np.zeros(3)
+    args = (n, _p(age), _p(income), _p(x), _p(y), _p(hh), w_a, w_i, w_d, min_prob)
+    assert L.orc_similarity_edges(*args, 0, _p(count), None, None, None, _p(maxes)) == 0
+    indptr = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
+    col, prob = np.zeros(indptr[-1], dtype=np.int32), np.zeros(indptr[-1])
+    assert L.orc_similarity_edges(*args, 1, None, _p(indptr), _p(col), _p(prob), _p(maxes)) == 0
+    return indptr, col, prob, tuple(maxes)
+
+
+def shortest_paths(indptr, indices, w, sources):
+    """oracle/dys_oracle.c:orc_shortest_paths -- scipy.sparse.csgraph.shortest_path(g, directed=True, indices=sources)"""
+    L = lib()
+    indptr, indices = np.ascontiguousarray(indptr, dtype=np.int64), np.ascontiguousarray(indices, dtype=np.int32)
+    w, sources = np.ascontiguousarray(w, dtype=np.float64), np.ascontiguousarray(sources, dtype=np.int32)
+    n = len(indptr) - 1
+    out = np.empty((len(sources), n))
+    L.orc_shortest_paths.argtypes = [C.c_int64] + [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 2
+    if L.orc_shortest_paths(n, _p(indptr), _p(indices), _p(w), len(sources), _p(sources), _p(out)) != 0:
+        raise RuntimeError("orc_shortest_paths: negative weight, bad index or bad source")
+    return out

@@ -1,0 +1,126 @@
+"""SURVEY.md 8f-2 on the GPU: dys_similarity_edges and dys_shortest_paths through the C ABI against the reference's own graph
+(golden fixtures), the oracle and scipy's shortest_path (the call the reference makes)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.csgraph import shortest_path
+
+from helpers import GOLDEN, REF_DIR
+from test_network import _csr_from_edges, _fixture, _ulp_close, check_edges_against_reference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("which", ["city300", "full_city"])
+def test_similarity_edges_match_the_reference_graph(which, oracle_lib):
+    """every edge of the reference's G between agents, in np.where order, with agents_prob bit for bit (the oracle's value)"""
+    from dysturbd_b200 import network
+    z = _fixture() if which == "city300" else np.load(os.path.join(REF_DIR, "config1_inputs.npz"))
+    cols = network.agent_columns(z["agents"], z["households"], z["build"])
+    indptr, col, prob = network.similarity_edges(cols)
+    check_edges_against_reference(indptr, col, prob, z)
+    o_ptr, o_col, o_prob, _ = oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"], 0.95)
+    assert np.array_equal(indptr, o_ptr) and np.array_equal(col, o_col) and np.array_equal(prob, o_prob)
+
+
+@pytest.mark.parametrize("kw", [dict(min_prob=0.9, w_a=0.97, w_i=1.0, w_d=0.99),      # weights below 1: the pre-filter stays on
+                                dict(min_prob=0.8, w_a=1.25, w_i=1.0, w_d=1.0),        # a weight above 1: every pair is evaluated
+                                dict(min_prob=0.999)])
+def test_similarity_edges_other_parameters(kw, oracle_lib):
+    from dysturbd_b200 import network
+    z = _fixture()
+    cols = network.agent_columns(z["agents"], z["households"], z["build"])
+    indptr, col, prob = network.similarity_edges(cols, **kw)
+    o_ptr, o_col, o_prob, _ = oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"],
+                                                           kw["min_prob"], kw.get("w_a", 1.0), kw.get("w_i", 1.0), kw.get("w_d", 1.0))
+    assert indptr[-1] > 0
+    assert np.array_equal(indptr, o_ptr) and np.array_equal(col, o_col) and np.array_equal(prob, o_prob)
+
+
+def test_shortest_paths_equal_scipy_city300():
+    from dysturbd_b200 import network
+    z = _fixture()
+    n = len(z["agents"])
+    indptr, idx, w = _csr_from_edges(n, z["edge_row"], z["edge_col"], z["edge_w"])
+    ref = shortest_path(sp.csr_matrix((w, idx, indptr), shape=(n, n)), directed=True, return_predecessors=False)
+    got, sweeps = network.shortest_paths(indptr, idx, w, np.arange(n), return_sweeps=True)
+    assert np.array_equal(got, ref) and sweeps > 3
+    some = np.array([5, 5, 700, 0, 123], dtype=np.int32)                           # a short, unsorted list with a repeat
+    assert np.array_equal(network.shortest_paths(indptr, idx, w, some), ref[some])
+
+
+def test_shortest_paths_equal_scipy_full_city():
+    """the shipped city's own graph (22 493 vertices, 311 512 edges, 236 components): 1 536 sources in two batches, grouped by
+    component as the adapter sends them, and a strided sample in agent order"""
+    from dysturbd_b200 import network
+    z = np.load(os.path.join(REF_DIR, "config1_inputs.npz"))
+    n = len(z["agents"])
+    indptr, idx, w = _csr_from_edges(n, z["edge_row"], z["edge_col"], z["edge_w"])
+    g = sp.csr_matrix((w, idx, indptr), shape=(n, n))
+    order = np.argsort(network.components(indptr, idx), kind="stable").astype(np.int32)
+    for src in (order[4000:5536], np.arange(0, n, n // 64)[:64].astype(np.int32)):
+        assert np.array_equal(network.shortest_paths(indptr, idx, w, src), shortest_path(g, directed=True, indices=src))
+
+
+def test_shortest_paths_csr_is_the_compacted_dense_result():
+    from dysturbd_b200 import engine, network
+    z = _fixture()
+    n = len(z["agents"])
+    indptr, idx, w = _csr_from_edges(n, z["edge_row"], z["edge_col"], z["edge_w"])
+    src = np.random.RandomState(1).permutation(n)[:300].astype(np.int32)
+    dense = network.shortest_paths(indptr, idx, w, src)
+    for skip in (True, False):
+        d = dense.copy()
+        if skip:
+            d[np.arange(len(src)), src] = np.inf
+        r, c = np.nonzero(np.isfinite(d))
+        ptr, col, dist = network.shortest_paths_csr(indptr, idx, w, src, capacity=len(r) + 7, skip_self=skip)
+        assert np.array_equal(np.diff(ptr), np.bincount(r, minlength=len(src)))
+        assert np.array_equal(col, c) and np.array_equal(dist, d[r, c])
+    with pytest.raises(engine.DysError):
+        network.shortest_paths_csr(indptr, idx, w, src, capacity=10)
+
+
+def test_shortest_paths_directed_random_graph(oracle_lib):
+    """one-way edges, zero weights, vertices without edges"""
+    from dysturbd_b200 import network
+    rs = np.random.RandomState(3)
+    n, E = 3000, 9000
+    row, col = rs.randint(0, n - 50, E), rs.randint(0, n - 50, E)            # the last 50 vertices are isolated
+    keep = row != col
+    key = np.unique(row[keep].astype(np.int64) * n + col[keep])              # no parallel edges (scipy would add them up)
+    row, col = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    w = np.where(rs.rand(len(key)) < 0.2, 0.0, rs.rand(len(key)))
+    indptr, idx, ww = _csr_from_edges(n, row, col, w)
+    src = rs.permutation(n)[:700].astype(np.int32)
+    got = network.shortest_paths(indptr, idx, ww, src)
+    assert np.array_equal(got, oracle_lib.shortest_paths(indptr, idx, ww, src))
+    g = sp.csr_matrix((ww, idx, indptr), shape=(n, n))
+    assert np.array_equal(got, shortest_path(g, directed=True, indices=src))
+
+
+def test_create_interaction_reproduces_interaction_prob():
+    """agents, households, build -> interaction_prob, everything between create_data and the day loop: the reference's matrix"""
+    from dysturbd_b200 import network
+    z = _fixture()
+    ip, (indptr, col, w) = network.create_interaction(z["agents"], z["households"], z["build"])
+    assert np.array_equal(ip.indptr, z["ip_indptr"]) and np.array_equal(ip.indices, z["ip_indices"])
+    assert _ulp_close(ip.data, z["ip_data"])
+    ip2 = network.interaction_prob(indptr, col, w, rows_per_call=96)
+    assert np.array_equal(ip2.indptr, ip.indptr) and np.array_equal(ip2.indices, ip.indices) and np.array_equal(ip2.data, ip.data)
+
+
+def test_network_calls_reject_bad_input():
+    from dysturbd_b200 import engine, network
+    indptr, idx = np.array([0, 1, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32)
+    with pytest.raises(engine.DysError):
+        network.shortest_paths(indptr, idx, np.array([0.5, -0.1]), [0])
+    with pytest.raises(engine.DysError):
+        network.shortest_paths(indptr, idx, np.array([0.5, 0.1]), [2])
+    with pytest.raises(engine.DysError):
+        network.shortest_paths(indptr, np.array([1, 7], dtype=np.int32), np.array([0.5, 0.1]), [0])
+    cols = dict(age=np.array([1.0, np.nan]), income=np.zeros(2), x=np.zeros(2), y=np.zeros(2), household=np.zeros(2, dtype=np.int64))
+    with pytest.raises(engine.DysError):
+        network.similarity_edges(cols)

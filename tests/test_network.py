@@ -1,0 +1,116 @@
+"""SURVEY.md 8f-2, CPU side: the oracle restatement of the network construction (oracle/dys_oracle.c: orc_similarity_edges,
+orc_shortest_paths) against the REFERENCE's own graph -- the agent-agent edges communities.create_network put into G and the
+interaction_prob contagious3.py:124-130 derived from it (tests/golden/network_city300.npz, tests/golden/config1/) -- and
+against scipy's shortest_path, the very call the reference makes.  The host adapter (dysturbd_b200/network.py) is driven
+with the oracle standing in for the two device calls."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.csgraph import shortest_path
+
+from helpers import GOLDEN, REF_DIR
+
+
+def _ulp_close(a, b):
+    return np.all(np.abs(a - b) <= np.spacing(np.maximum(np.abs(a), np.abs(b))))
+
+
+def _fixture():
+    return np.load(os.path.join(GOLDEN, "network_city300.npz"))
+
+
+def _csr_from_edges(n, row, col, w):
+    order = np.lexsort((col, row))
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(row, minlength=n))]).astype(np.int64)
+    return indptr, col[order].astype(np.int32), w[order]
+
+
+def check_edges_against_reference(indptr, col, prob, z):
+    """(indptr, col, prob) vs the agent-agent edges of the reference's G: same pairs in np.where order, weights -log(p)"""
+    n = len(z["agents"])
+    assert indptr[-1] == len(z["edge_row"])
+    assert np.array_equal(np.repeat(np.arange(n), np.diff(indptr)), z["edge_row"])
+    assert np.array_equal(col, z["edge_col"])
+    w = -np.log(prob)
+    assert _ulp_close(w, z["edge_w"])          # (equal bit for bit where numpy's log is the one that made the fixture)
+    return w
+
+
+def test_similarity_edges_oracle_matches_reference_graph(oracle_lib):
+    from dysturbd_b200 import network
+    z = _fixture()
+    cols = network.agent_columns(z["agents"], z["households"], z["build"])
+    indptr, col, prob, maxes = oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"], 0.95)
+    check_edges_against_reference(indptr, col, prob, z)
+    assert (prob == 1.0).sum() > 100 and (prob < 1.0).sum() > 100       # household edges and similarity edges both occur
+
+
+def test_similarity_edges_oracle_full_city(oracle_lib):
+    """the full shipped city: 22 493 agents, 311 512 edges of the reference's own graph"""
+    from dysturbd_b200 import network
+    z = np.load(os.path.join(REF_DIR, "config1_inputs.npz"))
+    cols = network.agent_columns(z["agents"], z["households"], z["build"])
+    indptr, col, prob, _ = oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"], 0.95)
+    check_edges_against_reference(indptr, col, prob, z)
+
+
+def test_agent_columns_follow_argmax(oracle_lib):
+    """communities.py:23, 34 look ids up with (table[:, None] == keys).argmax(axis=0): first match, row 0 when there is none"""
+    from dysturbd_b200 import network
+    z = _fixture()
+    agents, hhs, build = z["agents"].copy(), z["households"], z["build"]
+    agents[5, 1] = -12345.0                                   # a household id that does not exist
+    cols = network.agent_columns(agents, hhs, build)
+    agent_hh = (hhs[:, 0][:, None] == agents[:, 1]).argmax(axis=0)
+    homes = (build[:, 0][:, None] == hhs[agent_hh, 1]).argmax(axis=0)
+    assert np.array_equal(cols["household"], agent_hh) and agent_hh[5] == 0
+    assert np.array_equal(cols["x"], build[homes, 6]) and np.array_equal(cols["income"], hhs[agent_hh, 2])
+
+
+def test_shortest_paths_oracle_equals_scipy(oracle_lib):
+    z = _fixture()
+    n = len(z["agents"])
+    indptr, idx, w = _csr_from_edges(n, z["edge_row"], z["edge_col"], z["edge_w"])
+    g = sp.csr_matrix((w, idx, indptr), shape=(n, n))
+    ref = shortest_path(g, directed=True, return_predecessors=False)
+    got = oracle_lib.shortest_paths(indptr, idx, w, np.arange(n))
+    assert np.array_equal(got, ref)
+    assert np.isfinite(ref).mean() < 0.5 and (ref == 0).sum() > n                 # several components; zero-weight household edges
+
+
+def test_shortest_paths_oracle_full_city_sample(oracle_lib):
+    z = np.load(os.path.join(REF_DIR, "config1_inputs.npz"))
+    n = len(z["agents"])
+    indptr, idx, w = _csr_from_edges(n, z["edge_row"], z["edge_col"], z["edge_w"])
+    g = sp.csr_matrix((w, idx, indptr), shape=(n, n))
+    src = np.arange(0, n, n // 96)[:96].astype(np.int32)
+    assert np.array_equal(oracle_lib.shortest_paths(indptr, idx, w, src), shortest_path(g, directed=True, indices=src))
+
+
+def test_interaction_prob_adapter_reproduces_the_reference(oracle_lib, monkeypatch):
+    """dysturbd_b200/network.py end to end (agent columns -> edges -> -log p -> shortest paths by component batches ->
+    exp(-d) -> CSR in agent order) with the oracle in place of the two device calls == the reference's interaction_prob"""
+    from dysturbd_b200 import network
+    z = _fixture()
+
+    def edges(cols, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):
+        return oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"], min_prob, w_a, w_i, w_d)[:3]
+    monkeypatch.setattr(network, "similarity_edges", edges)
+
+    def paths_csr(indptr, idx, w, src, capacity, skip_self=True, device=0):
+        d = oracle_lib.shortest_paths(indptr, idx, w, src)
+        if skip_self:
+            d[np.arange(len(src)), src] = np.inf
+        r, c = np.nonzero(np.isfinite(d))
+        assert len(r) <= capacity
+        return np.concatenate([[0], np.cumsum(np.bincount(r, minlength=len(src)))]), c.astype(np.int32), d[r, c]
+    monkeypatch.setattr(network, "shortest_paths_csr", paths_csr)
+    ip, (indptr, col, w) = network.create_interaction(z["agents"], z["households"], z["build"])
+    n = len(z["agents"])
+    ip2 = network.interaction_prob(indptr, col, w, rows_per_call=100)              # several calls, components split across them
+    for m in (ip, ip2):
+        assert np.array_equal(m.indptr, z["ip_indptr"]) and np.array_equal(m.indices, z["ip_indices"])
+        assert _ulp_close(m.data, z["ip_data"])
+    assert ip.shape == (n, n)
