@@ -577,7 +577,50 @@ def run_extras(args, pop, prm, local, stream_of):
             e.close()
         except engine.DysError as ex:
             out[key] = {"error": str(ex)}
+    try:
+        out["network_construction"] = network_extra(local)
+    except Exception as ex:                       # noqa: BLE001  (a side measurement must never cost the bench line)
+        out["network_construction"] = {"error": repr(ex)}
     return out
+
+
+def network_extra(local):
+    """SURVEY.md 8f-2 on the full shipped city (the committed config-1 inputs: 22 493 agents): the agent-agent edges of
+    communities.create_network and the all-pairs shortest paths of contagious3.py:124-130, host arrays in, host arrays out.
+    The edge list is checked against the reference's own graph (stored with the fixture) before anything is timed."""
+    from dysturbd_b200 import network
+    path = os.path.join(ROOT, "tests", "golden", "config1", "config1_inputs.npz")
+    if not os.path.exists(path):
+        return {"error": "tests/golden/config1/config1_inputs.npz is missing"}
+    z = np.load(path)
+    n = len(z["agents"])
+    cols = network.agent_columns(z["agents"], z["households"], z["build"])
+    indptr, col, prob = network.similarity_edges(cols, device=local)
+    same = bool(indptr[-1] == len(z["edge_row"]) and np.array_equal(col, z["edge_col"]) and
+                np.array_equal(np.repeat(np.arange(n), np.diff(indptr)), z["edge_row"]))
+    t = time.perf_counter()
+    network.similarity_edges(cols, device=local)
+    t_edges = time.perf_counter() - t
+    w = network.edge_weights(prob)
+    labels = network.components(indptr, col)
+    reach = np.bincount(labels)[labels] - 1
+    order = np.argsort(labels, kind="stable").astype(np.int32)
+    tot = {"sweeps": 0, "prep_s": 0.0, "relax_s": 0.0, "download_s": 0.0}
+    pairs = 0
+    t = time.perf_counter()
+    for k0 in range(0, n, 2048):
+        src = order[k0:k0 + 2048]
+        _, c, _, info = network.shortest_paths_csr(indptr, col, w, src, int(reach[src].sum()), device=local, return_info=True)
+        pairs += len(c)
+        for k in tot:
+            tot[k] += info[k]
+    t_paths = time.perf_counter() - t
+    ref = json.loads(str(z["timings"])) if "timings" in z.files else {}
+    return {"workload": "shipped city, %d agents" % n, "edges": int(indptr[-1]), "edges_equal_reference_graph": same,
+            "similarity_edges_s": t_edges, "shortest_paths_s": t_paths, "reachable_pairs": int(pairs), **tot,
+            "reference_network_time_s": ref.get("network_time"), "reference_interaction_time_s": ref.get("interaction_time"),
+            "what": "dys_similarity_edges (sizing + fill) and dys_shortest_paths_csr for every agent, wall clock through the Python "
+                    "adapter, host arrays in and out; reference figures: contagious3.py's own timers when the fixture was made"}
 
 
 def eng_bytes(pop):

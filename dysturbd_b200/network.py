@@ -86,8 +86,9 @@ def shortest_paths(indptr, indices, weights, sources, device=0, return_sweeps=Fa
     return (out, int(info[0])) if return_sweeps else out
 
 
-def shortest_paths_csr(indptr, indices, weights, sources, capacity, skip_self=True, device=0, return_info=False):
-    """the same distances as CSR over the reachable vertices only: (ptr[len(sources)+1], col, dist), compacted on the device"""
+def shortest_paths_csr(indptr, indices, weights, sources, capacity=None, skip_self=True, device=0, return_info=False, out=None):
+    """the same distances as CSR over the reachable vertices only: (ptr[len(sources)+1], col, dist), compacted on the device.
+    out = (col_buffer, dist_buffer, offset): write into caller-owned arrays from `offset` on (the views returned alias them)"""
     lib = engine.load_library()
     lib.dys_shortest_paths_csr.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
@@ -95,14 +96,20 @@ def shortest_paths_csr(indptr, indices, weights, sources, capacity, skip_self=Tr
     weights = np.ascontiguousarray(weights, dtype=np.float64)
     sources = np.ascontiguousarray(sources, dtype=np.int32)
     ptr = np.zeros(len(sources) + 1, dtype=np.int64)
-    col, dist = np.empty(int(capacity), dtype=np.int32), np.empty(int(capacity), dtype=np.float64)
+    if out is None:
+        col, dist, off = np.empty(int(capacity), dtype=np.int32), np.empty(int(capacity), dtype=np.float64), 0
+    else:
+        col, dist, off = out
+        if col.dtype != np.int32 or dist.dtype != np.float64 or not (col.flags.c_contiguous and dist.flags.c_contiguous) or len(col) != len(dist):
+            raise TypeError("out = (int32[m], float64[m], offset), both contiguous")
+    room = len(col) - off if capacity is None else min(int(capacity), len(col) - off)
     info = np.zeros(4)
     _check(lib, lib.dys_shortest_paths_csr(device, len(indptr) - 1, indptr.ctypes.data, indices.ctypes.data, weights.ctypes.data,
-                                           len(sources), sources.ctypes.data, int(bool(skip_self)), ptr.ctypes.data, int(capacity),
-                                           col.ctypes.data, dist.ctypes.data, info.ctypes.data))
+                                           len(sources), sources.ctypes.data, int(bool(skip_self)), ptr.ctypes.data, room,
+                                           col.ctypes.data + 4 * off, dist.ctypes.data + 8 * off, info.ctypes.data))
     m = int(ptr[-1])
-    out = (ptr, col[:m], dist[:m])
-    return out + (dict(sweeps=int(info[0]), prep_s=info[1], relax_s=info[2], download_s=info[3]),) if return_info else out
+    res = (ptr, col[off:off + m], dist[off:off + m])
+    return res + (dict(sweeps=int(info[0]), prep_s=info[1], relax_s=info[2], download_s=info[3]),) if return_info else res
 
 
 def components(indptr, indices):
@@ -116,28 +123,24 @@ def components(indptr, indices):
 
 def interaction_prob(indptr, indices, weights, device=0, rows_per_call=2048):
     """contagious3.py:124-130 for the agent block: interaction_prob = exp(-shortest path), 0 on the diagonal and where no
-    path exists, as a scipy CSR matrix (sorted indices).  Sources go to the device grouped by component and come back as
-    compacted (vertex, distance) lists, so neither an n x n matrix nor dense rows ever exist on the host."""
+    path exists, as a scipy CSR matrix (sorted indices).  The sources go to the device in agent order and come back as
+    compacted (vertex, distance) lists written straight into the final arrays, so neither an n x n matrix nor dense rows
+    ever exist on the host and nothing is reordered; exp runs in place."""
     import scipy.sparse as sp
     n = len(indptr) - 1
     labels = components(indptr, indices)
-    reach = np.bincount(labels)[labels] - 1                      # vertices a source can reach at most (its component, less itself)
-    order = np.argsort(labels, kind="stable").astype(np.int32)
-    cols, vals, counts = [], [], np.zeros(n, dtype=np.int64)
+    total = int((np.bincount(labels)[labels] - 1).sum())         # a source reaches at most its weak component, less itself
+    col, val = np.empty(total, dtype=np.int32), np.empty(total, dtype=np.float64)
+    out_ptr = np.zeros(n + 1, dtype=np.int64)
+    pos = 0
     for k0 in range(0, n, rows_per_call):
-        src = order[k0:k0 + rows_per_call]
-        ptr, c, d = shortest_paths_csr(indptr, indices, weights, src, int(reach[src].sum()), skip_self=True, device=device)
-        counts[src] = np.diff(ptr)
-        cols.append(c)
-        vals.append(np.exp(-d))                                                                 # :127
-    # rows were produced in `order`; put them back in agent order
-    cols, vals = np.concatenate(cols), np.concatenate(vals)
-    start_in_order = np.concatenate([[0], np.cumsum(counts[order])])[:-1]
-    out_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    pos_of = np.empty(n, dtype=np.int64)
-    pos_of[order] = start_in_order
-    take = np.arange(out_ptr[-1]) + np.repeat(pos_of - out_ptr[:-1], counts)
-    return sp.csr_matrix((vals[take], cols[take], out_ptr), shape=(n, n))
+        src = np.arange(k0, min(n, k0 + rows_per_call), dtype=np.int32)
+        ptr, _, d = shortest_paths_csr(indptr, indices, weights, src, skip_self=True, device=device, out=(col, val, pos))
+        out_ptr[k0 + 1:k0 + 1 + len(src)] = pos + ptr[1:]
+        np.negative(d, out=d)
+        np.exp(d, out=d)                                                                        # :127
+        pos += int(ptr[-1])
+    return sp.csr_matrix((val[:pos], col[:pos], out_ptr), shape=(n, n))
 
 
 def create_interaction(agents, households, build, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):

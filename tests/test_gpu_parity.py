@@ -252,3 +252,45 @@ def test_replica_sweep_is_reproducible(eng, oracle_lib):
         sizes[(norm, comp)] = int(o.stats()[9])
     assert sizes[(8.0, 1.0)] > sizes[(4.0, 1.0)]
     g.close()
+
+
+def test_population_loaded_with_recovered_agents(eng, oracle_lib):
+    """agents that are ALREADY recovered when the run starts (immune at day 0, or infected shortly before it) stay in the
+    days-since-infection histograms, per-area histograms and R for 21 days exactly as in the reference's compute_R
+    (contagious3.py:29-42) -- the sweep may only skip a recovered agent once day - t_inf >= 21 (dys_load.cuh, r_idle_day).
+    Day by day through dys_step, and in week-long dys_step_many windows."""
+    from dysturbd_b200.population import EpiParams
+    from dysturbd_b200.synth import synth_population
+    import copy
+    pop = copy.copy(synth_population(9000, seed=8, seeds_per_22493=150))
+    rs = np.random.RandomState(2)
+    sus = np.nonzero(pop.status == 2)[0]
+    pick = rs.choice(sus, 600, replace=False)
+    pop.status, pop.t_inf = pop.status.copy(), pop.t_inf.copy()
+    pop.status[pick] = 12
+    pop.t_inf[pick] = rs.choice([0, -4, -15, 6], size=len(pick))          # (6: the reference would count it as infected on day 6)
+    prm = EpiParams(norm_factor=6.0, seed=77)
+    days = 35
+    g, o = eng.Engine(pop, prm), oracle_lib.OracleSim(pop, prm)
+    ref_stats, ref_hist = [], []
+    for d in range(days):
+        g.step(d)
+        o.step(d)
+        xa, xb = o.stats(d), g.stats(d)
+        assert np.array_equal(xa[:14], xb[:14]) and np.array_equal(xa[32:53], xb[32:53]), d
+        assert np.array_equal(o.sa_hist(d), g.sa_hist(d)), d
+        ref_stats.append(np.array(xa))
+        ref_hist.append(np.array(o.sa_hist(d)))
+    assert sum(int(s[32 + 1:32 + 21].sum()) for s in ref_stats[:5]) > 1000      # the loaded agents really sit in the bins
+    sa, sb = o.state(), g.state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    g.close()
+    w = eng.Engine(pop, prm)
+    for d0 in range(0, days, 7):
+        w.step_many(d0, 7)
+        for d in range(d0, d0 + 7):
+            x = w.stats(d)
+            assert np.array_equal(x[:14], ref_stats[d][:14]) and np.array_equal(x[32:53], ref_stats[d][32:53]), d
+            assert np.array_equal(w.sa_hist(d), ref_hist[d]), d
+    w.close()

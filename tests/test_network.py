@@ -99,13 +99,15 @@ def test_interaction_prob_adapter_reproduces_the_reference(oracle_lib, monkeypat
         return oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"], min_prob, w_a, w_i, w_d)[:3]
     monkeypatch.setattr(network, "similarity_edges", edges)
 
-    def paths_csr(indptr, idx, w, src, capacity, skip_self=True, device=0):
+    def paths_csr(indptr, idx, w, src, capacity=None, skip_self=True, device=0, out=None):
         d = oracle_lib.shortest_paths(indptr, idx, w, src)
         if skip_self:
             d[np.arange(len(src)), src] = np.inf
         r, c = np.nonzero(np.isfinite(d))
-        assert len(r) <= capacity
-        return np.concatenate([[0], np.cumsum(np.bincount(r, minlength=len(src)))]), c.astype(np.int32), d[r, c]
+        col, dist, off = out
+        assert off + len(r) <= len(col)
+        col[off:off + len(r)], dist[off:off + len(r)] = c, d[r, c]
+        return np.concatenate([[0], np.cumsum(np.bincount(r, minlength=len(src)))]), col[off:off + len(r)], dist[off:off + len(r)]
     monkeypatch.setattr(network, "shortest_paths_csr", paths_csr)
     ip, (indptr, col, w) = network.create_interaction(z["agents"], z["households"], z["build"])
     n = len(z["agents"])
