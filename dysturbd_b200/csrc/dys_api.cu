@@ -324,13 +324,13 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
                 in_w[(size_t)at] = weights[e];
             }
     }
-    // sources per batch: a multiple of 32, at most 1024, and D[n][batch] plus its transposed copy within ~4 GB
+    // sources per batch: a multiple of 128 (a warp of k_sp_relax), at most 1024, and D[n][batch] plus its transposed copy within ~4 GB
     int64_t max_batch = 1024;
-    if (const char* e = getenv("DYS_SP_BATCH")) max_batch = std::max<int64_t>(32, std::min<int64_t>(1024, atoll(e) / 32 * 32));
-    int64_t batch = std::min<int64_t>(max_batch, ((n_sources + 31) / 32) * 32);
-    while (batch > 32 && (double)n * (double)batch * 16.0 > 4.0e9) batch -= 32;
+    if (const char* e = getenv("DYS_SP_BATCH")) max_batch = std::max<int64_t>(SP_CHUNK, std::min<int64_t>(1024, atoll(e) / SP_CHUNK * SP_CHUNK));
+    int64_t batch = std::min<int64_t>(max_batch, ((n_sources + SP_CHUNK - 1) / SP_CHUNK) * SP_CHUNK);
+    while (batch > SP_CHUNK && (double)n * (double)batch * 16.0 > 4.0e9) batch -= SP_CHUNK;
     const char* e_pv = getenv("DYS_SP_VERTEX_MARKS");                   // developer A/B: one "changed" mark per vertex
-    const int fpv = (e_pv && atoi(e_pv)) ? 1 : (int)(batch / 32);
+    const int fpv = (e_pv && atoi(e_pv)) ? 1 : (int)(batch / SP_CHUNK);
     DevTmp t;
     const int64_t* d_ptr = t.up(in_ptr.data(), (size_t)n + 1);
     const int32_t* d_src = t.up(in_src.data(), (size_t)E);
@@ -348,7 +348,8 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
     constexpr int GROUP = 8;                                            // sweeps queued between two looks at the `changed` words
     int32_t* d_changed = t.get<int32_t>(GROUP);
     if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
-    const unsigned relax_grid = grid_for(n * batch, NET_BLOCK);
+    const unsigned init_grid = grid_for(n * batch, NET_BLOCK);
+    const unsigned relax_grid = grid_for(n * (batch / SP_CHUNK) * 32, NET_BLOCK);
     int total_sweeps = 0;
     for (int64_t k0 = 0; k0 < n_sources && t.e == cudaSuccess; k0 += batch) {
         const int nb = (int)std::min<int64_t>(batch, n_sources - k0);
@@ -356,7 +357,7 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
         if (t.e == cudaSuccess) t.e = cudaMemset(d_dirty, 0, 2 * n_marks);
         if (t.e != cudaSuccess) break;
         const double t0 = now();
-        k_sp_init<<<relax_grid, NET_BLOCK>>>(d_D, n, (int)batch, d_sources, nb, d_dirty, fpv);
+        k_sp_init<<<init_grid, NET_BLOCK>>>(d_D, n, (int)batch, d_sources, nb, d_dirty, fpv);
         int cur = 0;
         bool done = false;
         // every sweep moves the frontier at least one edge further along each shortest path: n sweeps always suffice

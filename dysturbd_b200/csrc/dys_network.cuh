@@ -132,10 +132,11 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sim_edges(const SimParams q, cons
 }
 
 // ---- shortest paths ----
+constexpr int SP_CHUNK = 128;                 // sources per warp of k_sp_relax (four per lane)
 // D[v * batch + s]: distance from source s of the batch to vertex v
 __global__ void __launch_bounds__(NET_BLOCK) k_sp_init(double* __restrict__ D, const int64_t n, const int batch,
                                                        const int32_t* __restrict__ sources, const int n_src, uint8_t* __restrict__ dirty,
-                                                       const int flags_per_vertex)
+                                                       const int marks_per_vertex)
 {
     const int64_t at = (int64_t)blockIdx.x * NET_BLOCK + threadIdx.x;
     if (at >= n * batch) return;
@@ -143,42 +144,52 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sp_init(double* __restrict__ D, c
     const int s = (int)(at - v * batch);
     const bool is_src = s < n_src && sources[s] == v;
     D[at] = is_src ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);
-    if (is_src) dirty[v * flags_per_vertex + (flags_per_vertex > 1 ? (s >> 5) : 0)] = 1;
+    if (is_src) dirty[v * marks_per_vertex + (marks_per_vertex > 1 ? s / SP_CHUNK : 0)] = 1;
 }
 
-// One warp = vertex v x 32 sources.  A vertex is looked at only if an in-neighbour changed in the previous sweep, and only
-// those neighbours are read.  The "changed" marks are kept per (vertex, group of 32 sources) -- flags_per_vertex = batch / 32 --
-// so a warp only follows the wave fronts of its own sources (flags_per_vertex = 1: one mark per vertex for the whole batch).  Updates are in place: a value read here is a real path length at all times, so reading one that
-// another warp is just improving is harmless (the neighbour is marked again and v comes back in the next sweep).
+// One warp = vertex v x 128 sources, four per lane (two 16-byte loads per neighbour and lane: the per-edge work -- index,
+// mark, weight -- is shared by four relaxations; the ncu capture of the one-source-per-lane version showed the kernel bound by
+// instruction issue at 6 % of the L2 throughput).  A vertex is looked at only if an in-neighbour changed in the previous
+// sweep, and only those neighbours are read.  The "changed" marks are kept per (vertex, 128 sources) -- marks_per_vertex =
+// batch / 128 -- so a warp only follows the wave fronts of its own sources (marks_per_vertex = 1: one mark per vertex for the
+// whole batch).  Updates are in place: a value read here is a real path length at all times, so reading one that another
+// warp is just improving is harmless (the neighbour is marked again and v comes back in the next sweep).
 __global__ void __launch_bounds__(NET_BLOCK) k_sp_relax(const int64_t n, const int batch, const int64_t* __restrict__ in_ptr,
                                                         const int32_t* __restrict__ in_src, const double* __restrict__ in_w,
                                                         double* D, const uint8_t* __restrict__ dirty_prev,
                                                         uint8_t* __restrict__ dirty_next, int32_t* __restrict__ changed,
-                                                        const int flags_per_vertex)
+                                                        const int marks_per_vertex)
 {
-    const int groups = batch >> 5;
+    const int chunks = batch / SP_CHUNK;
     const int64_t wid = ((int64_t)blockIdx.x * NET_BLOCK + threadIdx.x) >> 5;
-    if (wid >= n * groups) return;
+    if (wid >= n * chunks) return;
     const int lane = threadIdx.x & 31;
-    const int64_t v = wid / groups;
-    const int g = (int)(wid - v * groups);
+    const int64_t v = wid / chunks;
+    const int c = (int)(wid - v * chunks);
     const int64_t e0 = in_ptr[v], e1 = in_ptr[v + 1];
-    const int64_t fs = flags_per_vertex;
-    const int fo = flags_per_vertex > 1 ? g : 0;
+    const int64_t fs = marks_per_vertex;
+    const int fo = marks_per_vertex > 1 ? c : 0;
     bool any = false;
     for (int64_t e = e0 + lane; e < e1; e += 32) any |= dirty_prev[in_src[e] * fs + fo] != 0;
     if (!__any_sync(0xffffffffu, any)) return;
-    double* mine = D + v * batch + g * 32 + lane;
-    const double old = *reinterpret_cast<volatile double*>(mine);
-    double best = old;
+    const int64_t off = (int64_t)c * SP_CHUNK + lane * 4;
+    double2* mine = reinterpret_cast<double2*>(D + v * batch + off);
+    const double2 o0 = __ldcg(mine), o1 = __ldcg(mine + 1);
+    double2 b0 = o0, b1 = o1;
     for (int64_t e = e0; e < e1; ++e) {
         const int32_t u = in_src[e];
         if (!dirty_prev[u * fs + fo]) continue;
-        const double cand = __dadd_rn(*reinterpret_cast<const volatile double*>(D + (int64_t)u * batch + g * 32 + lane), in_w[e]);
-        best = cand < best ? cand : best;
+        const double w = in_w[e];
+        const double2* theirs = reinterpret_cast<const double2*>(D + (int64_t)u * batch + off);
+        const double2 x0 = __ldcg(theirs), x1 = __ldcg(theirs + 1);
+        const double c0 = __dadd_rn(x0.x, w), c1 = __dadd_rn(x0.y, w), c2 = __dadd_rn(x1.x, w), c3 = __dadd_rn(x1.y, w);
+        b0.x = c0 < b0.x ? c0 : b0.x;
+        b0.y = c1 < b0.y ? c1 : b0.y;
+        b1.x = c2 < b1.x ? c2 : b1.x;
+        b1.y = c3 < b1.y ? c3 : b1.y;
     }
-    const bool better = best < old;
-    if (better) *reinterpret_cast<volatile double*>(mine) = best;
+    const bool better = b0.x < o0.x || b0.y < o0.y || b1.x < o1.x || b1.y < o1.y;
+    if (better) { __stcg(mine, b0); __stcg(mine + 1, b1); }
     if (__any_sync(0xffffffffu, better) && lane == 0) {
         dirty_next[v * fs + fo] = 1;
         *changed = 1;
