@@ -121,26 +121,32 @@ def components(indptr, indices):
     return connected_components(g, directed=True, connection="weak")[1]
 
 
-def interaction_prob(indptr, indices, weights, device=0, rows_per_call=2048):
+def interaction_prob(indptr, indices, weights, device=0, rows_per_call=2048, row_range=None):
     """contagious3.py:124-130 for the agent block: interaction_prob = exp(-shortest path), 0 on the diagonal and where no
     path exists, as a scipy CSR matrix (sorted indices).  The sources go to the device in agent order and come back as
     compacted (vertex, distance) lists written straight into the final arrays, so neither an n x n matrix nor dense rows
-    ever exist on the host and nothing is reordered; exp runs in place."""
+    ever exist on the host and nothing is reordered; exp runs in place.
+    row_range = (lo, hi): only the rows of agents lo..hi-1, as a (hi - lo) x n matrix.  Rows are independent: several GPUs
+    (one process each, `device` = its GPU) take disjoint ranges and nothing is exchanged; scipy.sparse.vstack of the
+    pieces in rank order is the whole matrix."""
     import scipy.sparse as sp
     n = len(indptr) - 1
+    lo, hi = (0, n) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    if not 0 <= lo <= hi <= n:
+        raise ValueError("row_range outside [0, %d]" % n)
     labels = components(indptr, indices)
-    total = int((np.bincount(labels)[labels] - 1).sum())         # a source reaches at most its weak component, less itself
+    total = int((np.bincount(labels)[labels[lo:hi]] - 1).sum())  # a source reaches at most its weak component, less itself
     col, val = np.empty(total, dtype=np.int32), np.empty(total, dtype=np.float64)
-    out_ptr = np.zeros(n + 1, dtype=np.int64)
+    out_ptr = np.zeros(hi - lo + 1, dtype=np.int64)
     pos = 0
-    for k0 in range(0, n, rows_per_call):
-        src = np.arange(k0, min(n, k0 + rows_per_call), dtype=np.int32)
+    for k0 in range(lo, hi, rows_per_call):
+        src = np.arange(k0, min(hi, k0 + rows_per_call), dtype=np.int32)
         ptr, _, d = shortest_paths_csr(indptr, indices, weights, src, skip_self=True, device=device, out=(col, val, pos))
-        out_ptr[k0 + 1:k0 + 1 + len(src)] = pos + ptr[1:]
+        out_ptr[k0 - lo + 1:k0 - lo + 1 + len(src)] = pos + ptr[1:]
         np.negative(d, out=d)
         np.exp(d, out=d)                                                                        # :127
         pos += int(ptr[-1])
-    return sp.csr_matrix((val[:pos], col[:pos], out_ptr), shape=(n, n))
+    return sp.csr_matrix((val[:pos], col[:pos], out_ptr), shape=(hi - lo, n))
 
 
 def create_interaction(agents, households, build, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):

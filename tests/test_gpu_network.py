@@ -112,6 +112,22 @@ def test_create_interaction_reproduces_interaction_prob():
     assert np.array_equal(ip2.indptr, ip.indptr) and np.array_equal(ip2.indices, ip.indices) and np.array_equal(ip2.data, ip.data)
 
 
+def test_network_built_on_the_device_drives_the_day_loop():
+    """closing the loop: agents, households, build -> interaction_prob on the GPU (no reference matrix involved) -> the day
+    kernels -> the agent state and Stats of the literal reference run on every day of the golden fixture of the same city"""
+    from dysturbd_b200 import engine as eng, network
+    from dysturbd_b200.population import Population
+    from helpers import Fixture, run_against_fixture
+    z = _fixture()
+    fx = Fixture("city300_philox_gradual_all")
+    assert np.array_equal(fx.build, z["build"]) and np.array_equal(fx.agents[:, 0], z["agents"][:, 0])      # the same city
+    ip, _ = network.create_interaction(z["agents"], z["households"], z["build"])
+    pop = Population.from_reference(fx.agents, fx.build, fx.visits, ip)
+    sim = eng.Engine(pop, fx.params)
+    assert run_against_fixture(sim, fx) == fx.days
+    sim.close()
+
+
 def test_network_calls_reject_bad_input():
     from dysturbd_b200 import engine, network
     indptr, idx = np.array([0, 1, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32)

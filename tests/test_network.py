@@ -116,3 +116,8 @@ def test_interaction_prob_adapter_reproduces_the_reference(oracle_lib, monkeypat
         assert np.array_equal(m.indptr, z["ip_indptr"]) and np.array_equal(m.indices, z["ip_indices"])
         assert _ulp_close(m.data, z["ip_data"])
     assert ip.shape == (n, n)
+    # rows are independent: two "ranks" take disjoint row ranges, stacking their pieces gives the whole matrix
+    cut = n // 3
+    parts = [network.interaction_prob(indptr, col, w, row_range=r) for r in ((0, cut), (cut, n))]
+    whole = sp.vstack(parts).tocsr()
+    assert np.array_equal(whole.indptr, ip.indptr) and np.array_equal(whole.indices, ip.indices) and np.array_equal(whole.data, ip.data)
