@@ -274,6 +274,63 @@ extern "C" int dys_similarity_edges(int device, int64_t n, const double* age, co
     return DYS_OK;
 }
 
+// numpy's pairwise_sum(a, n) flattened into a stack program (see k_bld_rowsum)
+static void pairwise_program(int64_t j0, int64_t n, std::vector<SumOp>& prog)
+{
+    if (n <= 128) { prog.push_back(SumOp{(int32_t)j0, (int32_t)n}); return; }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    pairwise_program(j0, n2, prog);
+    pairwise_program(j0 + n2, n - n2, prog);
+    prog.push_back(SumOp{0, 0});
+}
+
+extern "C" int dys_building_edges(int device, int64_t n_bld, const double* floor_space, const double* x, const double* y, double min_prob,
+                                  int64_t* indptr /* [n_bld+1] out */, int64_t capacity, int32_t* col, double* prob)
+{
+    const char* who = "dys_building_edges";
+    if (n_bld <= 0 || !floor_space || !x || !y || !indptr) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: null or empty argument", who);
+    if (n_bld > 0x7fffffffll) return fail(nullptr, DYS_ERR_RANGE, "%s: more than 2^31 - 1 buildings", who);
+    for (int64_t i = 0; i < n_bld; ++i)
+        if (!std::isfinite(floor_space[i]) || !std::isfinite(x[i]) || !std::isfinite(y[i]))
+            return fail(nullptr, DYS_ERR_RANGE, "%s: building %lld has a non-finite floor space or coordinate", who, (long long)i);
+    int rc = pick_device(device, who);
+    if (rc != DYS_OK) return rc;
+    std::vector<SumOp> prog;
+    pairwise_program(0, n_bld, prog);
+    DevTmp t;
+    const double* d_fs = t.up(floor_space, (size_t)n_bld);
+    const double* d_x = t.up(x, (size_t)n_bld);
+    const double* d_y = t.up(y, (size_t)n_bld);
+    const SumOp* d_prog = t.up(prog.data(), prog.size());
+    double* d_sum = t.get<double>((size_t)n_bld);
+    int64_t* d_cnt = t.get<int64_t>((size_t)n_bld + 1);
+    const unsigned grid = grid_for(n_bld, NET_ROWS);
+    if (t.e == cudaSuccess) {
+        k_bld_rowsum<<<grid_for(n_bld, NET_BLOCK), NET_BLOCK>>>(n_bld, d_fs, d_x, d_y, d_prog, (int)prog.size(), d_sum);
+        k_bld_edges<false><<<grid, NET_BLOCK>>>(n_bld, min_prob, d_fs, d_x, d_y, d_sum, d_cnt, nullptr, nullptr, nullptr);
+        t.e = cudaMemcpy(indptr + 1, d_cnt, 8 * (size_t)n_bld, cudaMemcpyDeviceToHost);
+    }
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    indptr[0] = 0;
+    for (int64_t i = 0; i < n_bld; ++i) indptr[i + 1] += indptr[i];
+    const int64_t E = indptr[n_bld];
+    if (!col && !prob) return DYS_OK;                                   // sizing call
+    if (!col || !prob) return fail(nullptr, DYS_ERR_INVALID_ARG, "%s: col and prob go together", who);
+    if (capacity < E) return fail(nullptr, DYS_ERR_RANGE, "%s: %lld edges do not fit the capacity of %lld", who, (long long)E, (long long)capacity);
+    if (t.e == cudaSuccess) t.e = cudaMemcpy(d_cnt, indptr, 8 * (size_t)(n_bld + 1), cudaMemcpyHostToDevice);
+    int32_t* d_col = t.get<int32_t>((size_t)E);
+    double* d_prob = t.get<double>((size_t)E);
+    if (t.e == cudaSuccess) {
+        k_bld_edges<true><<<grid, NET_BLOCK>>>(n_bld, min_prob, d_fs, d_x, d_y, d_sum, nullptr, d_cnt, d_col, d_prob);
+        t.e = cudaGetLastError();
+        if (t.e == cudaSuccess && E) t.e = cudaMemcpy(col, d_col, 4 * (size_t)E, cudaMemcpyDeviceToHost);
+        if (t.e == cudaSuccess && E) t.e = cudaMemcpy(prob, d_prob, 8 * (size_t)E, cudaMemcpyDeviceToHost);
+    }
+    if (t.e != cudaSuccess) return fail(nullptr, DYS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(t.e));
+    return DYS_OK;
+}
+
 namespace {
 struct SpCsrOut {                    // the reachable vertices of every source as CSR instead of dense rows
     int64_t* ptr;                    // [n_sources + 1]

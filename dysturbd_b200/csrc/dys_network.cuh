@@ -131,6 +131,102 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sim_edges(const SimParams q, cons
     if (!FILL && row && lane == 0) count[i] = k;
 }
 
+// ---- building-building edges (communities.py:12-21, 53-54): the gravity model ----
+// scores[i][j] = fs[j] / dist(i,j)^2 with dist^2 the SQUARE OF THE ROUNDED DISTANCE (`distance_matrix(...)**beta`, beta = 2), a zero
+// replaced by 0.00001 (:14) and scores[i][i] = 0 (:17); prob = scores / row sum (:19); an edge wherever prob > min_prob, i != j.
+__device__ __forceinline__ double bld_score(const double fs_j, const double x_i, const double y_i, const double x_j, const double y_j,
+                                            const bool self)
+{
+    const double dx = __dsub_rn(x_j, x_i), dy = __dsub_rn(y_j, y_i);
+    const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    double d2 = __dmul_rn(d, d);
+    if (d2 == 0.0) d2 = 0.00001;
+    return self ? 0.0 : __ddiv_rn(fs_j, d2);
+}
+
+// The row sum is numpy's `scores.sum(axis=1)`: PAIRWISE summation of the contiguous row.  Its shape depends on B alone, so the
+// host flattens numpy's recursion into a program -- LEAF(j0, n <= 128): push the sum of that block (eight strided accumulators,
+// combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remainder; fewer than 8 elements: a plain loop); ADD: pop two, push
+// their sum -- and every row (one thread each) runs the same program: no divergence, operand loads are warp-uniform.
+struct SumOp { int32_t j0, n; };              // n > 0: LEAF;  n == 0: ADD
+__global__ void __launch_bounds__(NET_BLOCK) k_bld_rowsum(const int64_t B, const double* __restrict__ fs, const double* __restrict__ x,
+                                                          const double* __restrict__ y, const SumOp* __restrict__ prog, const int n_ops,
+                                                          double* __restrict__ row_sum)
+{
+    const int64_t i = (int64_t)blockIdx.x * NET_BLOCK + threadIdx.x;
+    if (i >= B) return;
+    const double x_i = x[i], y_i = y[i];
+    double stack[40];
+    int sp = 0;
+    for (int op = 0; op < n_ops; ++op) {
+        const SumOp o = prog[op];
+        if (o.n == 0) {
+            --sp;
+            stack[sp - 1] = __dadd_rn(stack[sp - 1], stack[sp]);
+            continue;
+        }
+        auto score = [&](const int64_t j) { return bld_score(fs[j], x_i, y_i, x[j], y[j], j == i); };
+        double res;
+        if (o.n < 8) {
+            res = 0.0;
+            for (int k = 0; k < o.n; ++k) res = __dadd_rn(res, score(o.j0 + k));
+        } else {
+            double r[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = score(o.j0 + q);
+            int k = 8;
+            for (; k < o.n - (o.n % 8); k += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r[q] = __dadd_rn(r[q], score(o.j0 + k + q));
+            }
+            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            for (; k < o.n; ++k) res = __dadd_rn(res, score(o.j0 + k));
+        }
+        stack[sp++] = res;
+    }
+    row_sum[i] = stack[0];
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(NET_BLOCK) k_bld_edges(const int64_t B, const double min_prob, const double* __restrict__ fs,
+                                                         const double* __restrict__ x, const double* __restrict__ y,
+                                                         const double* __restrict__ row_sum, int64_t* __restrict__ count,
+                                                         const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+                                                         double* __restrict__ prob)
+{
+    __shared__ double s_fs[NET_TILE], s_x[NET_TILE], s_y[NET_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * NET_ROWS + warp;
+    const bool row = i < B;
+    const double x_i = row ? x[i] : 0.0, y_i = row ? y[i] : 0.0, sum_i = row ? row_sum[i] : 1.0;
+    int64_t k = FILL && row ? rowptr[i] : 0;
+    for (int64_t j0 = 0; j0 < B; j0 += NET_TILE) {
+        const int64_t jt = j0 + threadIdx.x;
+        if (jt < B) { s_fs[threadIdx.x] = fs[jt]; s_x[threadIdx.x] = x[jt]; s_y[threadIdx.x] = y[jt]; }
+        __syncthreads();
+        if (row) {
+            for (int t = 0; t < NET_TILE; t += 32) {
+                const int64_t j = j0 + t + lane;
+                bool edge = false;
+                double p = 0.0;
+                if (j < B && j != i) {
+                    p = __ddiv_rn(bld_score(s_fs[t + lane], x_i, y_i, s_x[t + lane], s_y[t + lane], false), sum_i);     // :19
+                    edge = p > min_prob;                                                                               // :53
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, edge);
+                if (FILL && edge) {
+                    const int64_t at = k + __popc(m & ((1u << lane) - 1u));
+                    col[at] = (int32_t)j;
+                    prob[at] = p;
+                }
+                k += __popc(m);
+            }
+        }
+        __syncthreads();
+    }
+    if (!FILL && row && lane == 0) count[i] = k;
+}
+
 // ---- shortest paths ----
 constexpr int SP_CHUNK = 128;                 // sources per warp of k_sp_relax (four per lane)
 // D[v * batch + s]: distance from source s of the batch to vertex v

@@ -67,7 +67,7 @@ EXPORTS = ["dys_create", "dys_destroy", "dys_last_error", "dys_load_population",
            "dys_get_sa_hist", "dys_get_building_counts", "dys_get_events", "dys_get_io_mat", "dys_get_state",
            "dys_get_pair_prob", "dys_get_outputs", "dys_sync", "dys_get_kernel_times", "dys_device_buffer", "dys_cuda_stream",
            "dys_device_bytes", "dys_version", "dys_keyed_uniform_device", "dys_peer_export", "dys_peer_attach", "dys_peer_detach",
-           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown", "dys_set_lockdown_areas", "dys_generate_routines", "dys_consume_day", "dys_similarity_edges", "dys_shortest_paths", "dys_shortest_paths_csr"]
+           "dys_set_replica_params", "dys_select_replica", "dys_abort", "dys_h2d_bytes", "dys_compute_r_rows", "dys_set_lockdown", "dys_set_lockdown_areas", "dys_generate_routines", "dys_consume_day", "dys_similarity_edges", "dys_building_edges", "dys_shortest_paths", "dys_shortest_paths_csr"]
 
 _lib = None
 

@@ -62,6 +62,64 @@ def similarity_edges(cols, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):
     return indptr, col, prob
 
 
+def building_edges(build, min_prob=0.00161, device=0):
+    """communities.py:12-21, 53-54 -> (indptr[B+1], col[E], prob[E]) over the rows of `build`, prob == bld_prob[i, j] bit for bit"""
+    lib = engine.load_library()
+    lib.dys_building_edges.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    fs, x, y = (np.ascontiguousarray(build[:, k], dtype=np.float64) for k in (4, 6, 7))
+    B = len(fs)
+    indptr = np.zeros(B + 1, dtype=np.int64)
+    head = [device, B, fs.ctypes.data, x.ctypes.data, y.ctypes.data, float(min_prob), indptr.ctypes.data]
+    _check(lib, lib.dys_building_edges(*head, 0, None, None))                                   # sizing pass
+    E = int(indptr[-1])
+    col, prob = np.empty(E, dtype=np.int32), np.empty(E, dtype=np.float64)
+    _check(lib, lib.dys_building_edges(*head, E, col.ctypes.data, prob.ctypes.data))
+    return indptr, col, prob
+
+
+def create_graph(agents, households, build, a_min_prob=0.95, b_min_prob=0.00161, w_a=1.0, w_i=1.0, w_d=1.0, device=0):
+    """communities.create_network(agents, households, build) as arrays: (nodes, indptr, indices, weights) -- the node ids
+    (buildings and agents, ascending) and the CSR adjacency of the reference's DiGraph G with its weights -log(p):
+    building -> building (gravity model, :52-54), agent -> home / workplace / other regular building (weight log 1 = 0,
+    :56-61; a building named twice by an agent is one edge, as in a DiGraph) and agent -> agent (:65-70)."""
+    cols = agent_columns(agents, households, build)
+    b_ptr, b_col, b_prob = building_edges(build, b_min_prob, device=device)
+    a_ptr, a_col, a_prob = similarity_edges(cols, a_min_prob, w_a, w_i, w_d, device=device)
+    N, B = len(agents), len(build)
+    ids_b, ids_a = build[:, 0], agents[:, 0]
+    hh_home = households[cols["household"], 1]
+    u = [np.repeat(ids_b, np.diff(b_ptr)), ids_a]                                               # :52-56
+    v = [ids_b[b_col], hh_home]
+    w = [-np.log(b_prob), np.full(N, np.log(1))]
+    for c in (12, 18):                                                                          # :58-61
+        has = ~np.isnan(agents[:, c])
+        u.append(ids_a[has]); v.append(agents[has, c]); w.append(np.full(int(has.sum()), np.log(1)))
+    u.append(np.repeat(ids_a, np.diff(a_ptr))); v.append(ids_a[a_col]); w.append(edge_weights(a_prob))   # :65-70
+    u, v, w = np.concatenate(u), np.concatenate(v), np.concatenate(w)
+    nodes = np.unique(np.concatenate([u, v]))
+    r, c = np.searchsorted(nodes, u), np.searchsorted(nodes, v)
+    key = r.astype(np.int64) * len(nodes) + c
+    _, last = np.unique(key[::-1], return_index=True)                                           # a repeated (u, v): the LAST weight stands
+    keep = np.sort(len(key) - 1 - last)
+    r, c, w = r[keep], c[keep], w[keep]
+    order = np.lexsort((c, r))
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=len(nodes)))]).astype(np.int64)
+    return nodes, indptr, c[order].astype(np.int32), w[order]
+
+
+def all_pairs(indptr, indices, weights, device=0, rows_per_call=4096, diagonal_inf=True):
+    """contagious3.py:125-126: the dense `dists` of a graph (every node a source), float64 [n, n], +inf where there is no
+    path and -- as the reference leaves it for everything that follows (:126 np.fill_diagonal) -- on the diagonal"""
+    n = len(indptr) - 1
+    out = np.empty((n, n), dtype=np.float64)
+    for k0 in range(0, n, rows_per_call):
+        src = np.arange(k0, min(n, k0 + rows_per_call), dtype=np.int32)
+        out[k0:k0 + len(src)] = shortest_paths(indptr, indices, weights, src, device=device)
+    if diagonal_inf:
+        np.fill_diagonal(out, np.inf)
+    return out
+
+
 def edge_weights(prob):
     """the weight create_network gives an edge (communities.py:70): -log(p), with numpy's log as there"""
     return -np.log(prob)

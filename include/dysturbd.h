@@ -284,6 +284,13 @@ int dys_generate_routines(int device, int64_t n_agents, int64_t n_bld, int32_t V
 int dys_similarity_edges(int device, int64_t n, const double* age, const double* income, const double* x, const double* y,
                          const int64_t* household, double w_a, double w_i, double w_d, double min_prob, int64_t* indptr,
                          int64_t capacity, int32_t* col, double* prob, double* maxes);
+/* dys_building_edges: the building-building edges of create_network (communities.py:12-21, 53-54), the gravity model
+ *   scores[i][j] = floor_space[j] / dist(i, j)^2   (the square of the ROUNDED Euclidean distance; 0 -> 0.00001; scores[i][i] = 0)
+ *   prob = scores / row sum,   an edge i -> j wherever prob > min_prob, i != j.
+ * The row sum is numpy's pairwise `scores.sum(axis=1)`, reproduced addition by addition, so `prob` is bit-identical to
+ * bld_prob[i, j]; the caller forms -log(prob).  Output protocol as dys_similarity_edges. */
+int dys_building_edges(int device, int64_t n_bld, const double* floor_space, const double* x, const double* y, double min_prob,
+                       int64_t* indptr, int64_t capacity, int32_t* col, double* prob);
 /* dys_shortest_paths: scipy.sparse.csgraph.shortest_path(g, directed=True, indices=sources) for a CSR graph with non-negative
  * weights (explicit zeros are edges, as in scipy): out[k][v] = length of the shortest path sources[k] -> v, +inf where there
  * is none.  Bit-identical to Dijkstra's left-to-right sums.  Give the sources grouped by connected component:

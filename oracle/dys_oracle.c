@@ -548,3 +548,61 @@ int orc_shortest_paths(int64_t n, const int64_t* indptr, const int32_t* indices,
     }
     return bad ? -1 : 0;
 }
+
+/* orc_building_edges -- the building-building edges of communities.create_network (communities.py:12-21, 53-54): the gravity
+ * model  scores[i][j] = fs[j] / dist(i, j)^beta  with beta = 2 (dist^2 is the SQUARE OF THE ROUNDED DISTANCE, as
+ * `distance_matrix(...)**beta` forms it; a zero becomes 0.00001, :14), scores[i][i] = 0, prob = scores / row sum, an edge
+ * i -> j wherever prob > min_prob and i != j.  The row sum is numpy's `scores.sum(axis=1)`: PAIRWISE summation over the
+ * contiguous row (blocks of <= 128 elements with eight strided accumulators, halves split at a multiple of 8) -- restated
+ * here because the order of the additions decides the last bit of every probability. */
+static double bld_score(const double* fs, const double* x, const double* y, int64_t i, int64_t j)
+{
+    if (i == j) return 0.0;
+    const double dx = x[j] - x[i], dy = y[j] - y[i];
+    const double d = sqrt(dx * dx + dy * dy);
+    double d2 = d * d;
+    if (d2 == 0.0) d2 = 0.00001;
+    return fs[j] / d2;
+}
+
+static double bld_pairwise(const double* fs, const double* x, const double* y, int64_t i, int64_t j0, int64_t n)
+{
+    if (n < 8) {
+        double res = 0.;                       /* (numpy starts from 0. here; -0.0 cannot occur: scores are >= 0) */
+        for (int64_t k = 0; k < n; ++k) res += bld_score(fs, x, y, i, j0 + k);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int q = 0; q < 8; ++q) r[q] = bld_score(fs, x, y, i, j0 + q);
+        int64_t k;
+        for (k = 8; k < n - (n % 8); k += 8)
+            for (int q = 0; q < 8; ++q) r[q] += bld_score(fs, x, y, i, j0 + k + q);
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; k < n; ++k) res += bld_score(fs, x, y, i, j0 + k);
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return bld_pairwise(fs, x, y, i, j0, n2) + bld_pairwise(fs, x, y, i, j0 + n2, n - n2);
+}
+
+int orc_building_edges(int64_t B, const double* fs, const double* x, const double* y, double min_prob, int fill,
+                       int64_t* count /* [B] */, const int64_t* rowptr, int32_t* col, double* prob, double* row_sum /* [B] out, nullable */)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < B; ++i) {
+        const double s = bld_pairwise(fs, x, y, i, 0, B);
+        if (row_sum) row_sum[i] = s;
+        int64_t k = fill ? rowptr[i] : 0;
+        for (int64_t j = 0; j < B; ++j) {
+            const double p = bld_score(fs, x, y, i, j) / s;
+            if (p > min_prob && j != i) {
+                if (fill) { col[k] = (int32_t)j; prob[k] = p; }
+                ++k;
+            }
+        }
+        if (!fill) count[i] = k;
+    }
+    return 0;
+}

@@ -232,3 +232,19 @@ def shortest_paths(indptr, indices, w, sources):
     if L.orc_shortest_paths(n, _p(indptr), _p(indices), _p(w), len(sources), _p(sources), _p(out)) != 0:
         raise RuntimeError("orc_shortest_paths: negative weight, bad index or bad source")
     return out
+
+
+def building_edges(fs, x, y, min_prob):
+    """oracle/dys_oracle.c:orc_building_edges -- communities.py:12-21, 53-54 (gravity model between buildings, beta = 2).
+    Returns (indptr[B+1], col, prob, row_sum[B])."""
+    L = lib()
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    fs, x, y = c(fs), c(x), c(y)
+    B = len(fs)
+    L.orc_building_edges.argtypes = [C.c_int64] + [C.c_void_p] * 3 + [C.c_double, C.c_int] + [C.c_void_p] * 5
+    count, row_sum = np.zeros(B, dtype=np.int64), np.zeros(B)
+    assert L.orc_building_edges(B, _p(fs), _p(x), _p(y), min_prob, 0, _p(count), None, None, None, _p(row_sum)) == 0
+    indptr = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
+    col, prob = np.zeros(indptr[-1], dtype=np.int32), np.zeros(indptr[-1])
+    assert L.orc_building_edges(B, _p(fs), _p(x), _p(y), min_prob, 1, None, _p(indptr), _p(col), _p(prob), None) == 0
+    return indptr, col, prob, row_sum

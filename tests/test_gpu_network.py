@@ -8,7 +8,7 @@ import scipy.sparse as sp
 from scipy.sparse.csgraph import shortest_path
 
 from helpers import GOLDEN, REF_DIR
-from test_network import _csr_from_edges, _fixture, _ulp_close, check_edges_against_reference
+from test_network import _csr_from_edges, _fixture, _ulp_close, check_edges_against_reference, check_graph_against_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -126,6 +126,43 @@ def test_network_built_on_the_device_drives_the_day_loop():
     sim = eng.Engine(pop, fx.params)
     assert run_against_fixture(sim, fx) == fx.days
     sim.close()
+
+
+def test_building_edges_match_the_oracle_and_the_reference_graph(oracle_lib):
+    """the gravity model between buildings with numpy's pairwise row sums reproduced on the device: bld_prob bit for bit
+    (shipped city's 1 015 buildings; random layouts on both sides of the pairwise block and split sizes)"""
+    from dysturbd_b200 import network
+    build = _fixture()["build"]
+    indptr, col, prob = network.building_edges(build)
+    o_ptr, o_col, o_prob, _ = oracle_lib.building_edges(build[:, 4], build[:, 6], build[:, 7], 0.00161)
+    assert indptr[-1] == 83728
+    assert np.array_equal(indptr, o_ptr) and np.array_equal(col, o_col) and np.array_equal(prob, o_prob)
+    rs = np.random.RandomState(5)
+    for B in (5, 8, 127, 128, 129, 300, 2500):
+        b = np.zeros((B, 15))
+        b[:, 4], b[:, 6], b[:, 7] = rs.rand(B) * 1000 + 1, rs.rand(B) * 5000, rs.rand(B) * 5000
+        if B > 20:
+            b[5, 6:8] = b[6, 6:8]
+        got = network.building_edges(b, min_prob=0.5 / B)
+        exp = oracle_lib.building_edges(b[:, 4], b[:, 6], b[:, 7], 0.5 / B)
+        assert got[0][-1] > 0 and all(np.array_equal(g, e) for g, e in zip(got, exp[:3])), B
+
+
+def test_whole_setup_on_the_device():
+    """everything between create_data and the day loop: agents, households, build -> G (all four kinds of edges) -> dists
+    -> neighbourhood lists -> routines, each stage against the reference's own (tests/golden: the whole of G for one city,
+    the lists from the reference's dists and its routines under injected draws for another)"""
+    from dysturbd_b200 import network, routines
+    z = _fixture()
+    check_graph_against_reference(*network.create_graph(z["agents"], z["households"], z["build"]), z)
+    r = np.load(os.path.join(GOLDEN, "routines_city120.npz"))
+    nodes, indptr, idx, w = network.create_graph(r["agents"], r["households"], r["build"])
+    dists = network.all_pairs(indptr, idx, w)
+    nb = routines.neighbourhoods(nodes, dists, r["agents"], r["build"], 1, 6)
+    for name, key in (("out", "out"), ("inn", "in"), ("near", "near")):
+        assert np.array_equal(nb[name][0], r[key + "_ptr"]) and np.array_equal(nb[name][1], r[key + "_idx"]), name
+    visits = routines.to_visits(routines.generate(nb, int(r["seed"]), V=r["visits"].shape[1], k=int(r["k"])), nb["bld_ids"])
+    assert np.array_equal(visits, r["visits"], equal_nan=True)
 
 
 def test_network_calls_reject_bad_input():

@@ -121,3 +121,84 @@ def test_interaction_prob_adapter_reproduces_the_reference(oracle_lib, monkeypat
     parts = [network.interaction_prob(indptr, col, w, row_range=r) for r in ((0, cut), (cut, n))]
     whole = sp.vstack(parts).tocsr()
     assert np.array_equal(whole.indptr, ip.indptr) and np.array_equal(whole.indices, ip.indices) and np.array_equal(whole.data, ip.data)
+
+
+def _oracle_standins(monkeypatch, oracle_lib):
+    from dysturbd_b200 import network
+
+    def edges(cols, min_prob=0.95, w_a=1.0, w_i=1.0, w_d=1.0, device=0):
+        return oracle_lib.similarity_edges(cols["age"], cols["income"], cols["x"], cols["y"], cols["household"], min_prob, w_a, w_i, w_d)[:3]
+    monkeypatch.setattr(network, "similarity_edges", edges)
+    monkeypatch.setattr(network, "building_edges", lambda build, min_prob=0.00161, device=0:
+                        oracle_lib.building_edges(build[:, 4], build[:, 6], build[:, 7], min_prob)[:3])
+    monkeypatch.setattr(network, "shortest_paths", lambda indptr, idx, w, src, device=0: oracle_lib.shortest_paths(indptr, idx, w, src))
+    return network
+
+
+def check_graph_against_reference(nodes, indptr, idx, w, z):
+    """(nodes, CSR) vs the reference's DiGraph G: same nodes, same edges, same weights (zeros with their sign)"""
+    assert np.array_equal(nodes, np.sort(z["g_nodes"]))
+    assert indptr[-1] == len(z["g_u"])
+    ref = {(a, b): c for a, b, c in zip(z["g_u"], z["g_v"], z["g_w"])}
+    rows = np.repeat(np.arange(len(nodes)), np.diff(indptr))
+    mine = {(nodes[r], nodes[c]): x for r, c, x in zip(rows, idx, w)}
+    assert mine.keys() == ref.keys()
+    a = np.array([mine[k] for k in ref])
+    b = np.array([ref[k] for k in ref])
+    assert _ulp_close(a, b) and np.array_equal(np.signbit(a), np.signbit(b))
+
+
+def test_building_edges_oracle_matches_reference_graph_and_numpy(oracle_lib):
+    """the gravity model between buildings: the 83 728 building -> building edges of the reference's G, and the row sums
+    against numpy's own pairwise `sum(axis=1)` for sizes on both sides of its block and split thresholds"""
+    z = _fixture()
+    build = z["build"]
+    indptr, col, prob, _ = oracle_lib.building_edges(build[:, 4], build[:, 6], build[:, 7], 0.00161)
+    bb = (z["g_u"] < 4000000) & (z["g_v"] < 4000000)
+    row_of = {b: i for i, b in enumerate(build[:, 0])}
+    r = np.array([row_of[a] for a in z["g_u"][bb]])
+    c = np.array([row_of[a] for a in z["g_v"][bb]])
+    order = np.lexsort((c, r))
+    assert np.array_equal(np.repeat(np.arange(len(build)), np.diff(indptr)), r[order]) and np.array_equal(col, c[order])
+    assert _ulp_close(-np.log(prob), z["g_w"][bb][order])
+    rs = np.random.RandomState(0)
+    for B in (5, 8, 100, 128, 129, 300, 1000, 3000):
+        fs, x, y = rs.rand(B) * 1000 + 1, rs.rand(B) * 5000, rs.rand(B) * 5000
+        if B > 20:
+            x[5], y[5] = x[6], y[6]                               # two buildings on one spot: the 0 -> 0.00001 rule (:14)
+        d = (np.sqrt((x[None, :] - x[:, None]) ** 2 + (y[None, :] - y[:, None]) ** 2)) ** 2
+        d[d == 0] = 0.00001
+        sc = fs / d
+        np.fill_diagonal(sc, 0)
+        assert np.array_equal(oracle_lib.building_edges(fs, x, y, 0.5)[3], sc.sum(axis=1)), B
+
+
+def test_create_graph_is_the_reference_graph(oracle_lib, monkeypatch):
+    """network.create_graph == communities.create_network: every node and edge of G (building gravity edges, agent -> home /
+    work / other, agent -> agent), and the distance matrix over it == scipy's on the reference's own G"""
+    network = _oracle_standins(monkeypatch, oracle_lib)
+    z = _fixture()
+    nodes, indptr, idx, w = network.create_graph(z["agents"], z["households"], z["build"])
+    check_graph_against_reference(nodes, indptr, idx, w, z)
+    gn = z["g_nodes"]
+    pos = {v: i for i, v in enumerate(gn)}
+    G = sp.csr_matrix((z["g_w"], (np.array([pos[a] for a in z["g_u"]]), np.array([pos[a] for a in z["g_v"]]))), shape=(len(gn), len(gn)))
+    ref = shortest_path(G, directed=True, return_predecessors=False)
+    perm = np.array([pos[v] for v in nodes])
+    assert np.array_equal(network.all_pairs(indptr, idx, w, rows_per_call=500, diagonal_inf=False), ref[np.ix_(perm, perm)])
+
+
+def test_whole_setup_chain_reproduces_the_routine_inputs(oracle_lib, monkeypatch):
+    """agents, households, build -> graph -> distances -> the neighbourhood lists of the routine kernel: exactly the lists
+    derived from the reference's own `dists` (tests/golden/routines_city120.npz), and then the reference's routines"""
+    from dysturbd_b200 import routines
+    network = _oracle_standins(monkeypatch, oracle_lib)
+    z = np.load(os.path.join(GOLDEN, "routines_city120.npz"))
+    nodes, indptr, idx, w = network.create_graph(z["agents"], z["households"], z["build"])
+    dists = network.all_pairs(indptr, idx, w)
+    nb = routines.neighbourhoods(nodes, dists, z["agents"], z["build"], 1, 6)
+    assert np.array_equal(nb["bld_ids"], z["bld_ids"]) and np.array_equal(nb["home"], z["home"]) and np.array_equal(nb["anchors"], z["anchors"])
+    for name, key in (("out", "out"), ("inn", "in"), ("near", "near")):
+        assert np.array_equal(nb[name][0], z[key + "_ptr"]) and np.array_equal(nb[name][1], z[key + "_idx"]), name
+    r = oracle_lib.routines(nb["home"], nb["anchors"], nb["out"], nb["inn"], nb["near"], int(z["seed"]), V=z["visits"].shape[1], k=int(z["k"]))
+    assert np.array_equal(routines.to_visits(r, nb["bld_ids"]), z["visits"], equal_nan=True)
