@@ -338,6 +338,8 @@ struct SpCsrOut {                    // the reachable vertices of every source a
     int32_t* col;
     double* dist;
     int32_t skip_self;
+    double max_dist;                 // keep d < max_dist (+inf: every reachable vertex)
+    const uint8_t* col_keep;         // [n] or null: only these vertices are listed
 };
 }  // namespace
 
@@ -396,6 +398,8 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
     double* d_out = t.get<double>((size_t)n * (size_t)batch);
     int32_t* d_sources = t.get<int32_t>((size_t)batch);
     int64_t* d_cnt = csr ? t.get<int64_t>((size_t)batch + 1) : nullptr;
+    const double bound = csr ? csr->max_dist : (double)INFINITY;
+    const uint8_t* d_keep = (csr && csr->col_keep) ? t.up(csr->col_keep, (size_t)n) : nullptr;
     int32_t* d_ccol = nullptr;
     double* d_cdist = nullptr;
     size_t c_room = 0;                                                  // (grown to the largest batch seen)
@@ -424,7 +428,7 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
                 uint8_t* prev = d_dirty + (size_t)cur * n_marks;
                 uint8_t* next = d_dirty + (size_t)(cur ^ 1) * n_marks;
                 t.e = cudaMemsetAsync(next, 0, n_marks);
-                k_sp_relax<<<relax_grid, NET_BLOCK>>>(n, (int)batch, d_ptr, d_src, d_w, d_D, prev, next, d_changed + g, fpv);
+                k_sp_relax<<<relax_grid, NET_BLOCK>>>(n, (int)batch, d_ptr, d_src, d_w, d_D, prev, next, d_changed + g, fpv, bound);
                 cur ^= 1;
             }
             int32_t ch[GROUP];
@@ -443,7 +447,7 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
         if (out) t.e = cudaMemcpy(out + k0 * n, d_out, 8 * (size_t)nb * (size_t)n, cudaMemcpyDeviceToHost);
         if (csr && t.e == cudaSuccess) {
             const unsigned cgrid = grid_for((int64_t)nb * 32, NET_BLOCK);
-            k_sp_compact<false><<<cgrid, NET_BLOCK>>>(d_out, n, nb, d_sources, csr->skip_self, d_cnt + 1, nullptr, nullptr, nullptr);
+            k_sp_compact<false><<<cgrid, NET_BLOCK>>>(d_out, n, nb, d_sources, csr->skip_self, bound, d_keep, d_cnt + 1, nullptr, nullptr, nullptr);
             t.e = cudaMemcpy(h_cnt.data() + 1, d_cnt + 1, 8 * (size_t)nb, cudaMemcpyDeviceToHost);
             if (t.e != cudaSuccess) break;
             h_cnt[0] = 0;
@@ -461,7 +465,7 @@ static int shortest_paths_impl(const char* who, int device, int64_t n, const int
                 }
                 if (t.e == cudaSuccess) t.e = cudaMemcpy(d_cnt, h_cnt.data(), 8 * (size_t)(nb + 1), cudaMemcpyHostToDevice);
                 if (t.e != cudaSuccess) break;
-                k_sp_compact<true><<<cgrid, NET_BLOCK>>>(d_out, n, nb, d_sources, csr->skip_self, nullptr, d_cnt, d_ccol, d_cdist);
+                k_sp_compact<true><<<cgrid, NET_BLOCK>>>(d_out, n, nb, d_sources, csr->skip_self, bound, d_keep, nullptr, d_cnt, d_ccol, d_cdist);
                 t.e = cudaMemcpy(csr->col + base, d_ccol, 4 * (size_t)m, cudaMemcpyDeviceToHost);
                 if (t.e == cudaSuccess) t.e = cudaMemcpy(csr->dist + base, d_cdist, 8 * (size_t)m, cudaMemcpyDeviceToHost);
             }
@@ -481,11 +485,13 @@ extern "C" int dys_shortest_paths(int device, int64_t n, const int64_t* indptr, 
 }
 
 extern "C" int dys_shortest_paths_csr(int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
-                                      int64_t n_sources, const int32_t* sources, int32_t skip_self, int64_t* out_ptr /* [n_sources + 1] */,
+                                      int64_t n_sources, const int32_t* sources, int32_t skip_self, double max_dist,
+                                      const uint8_t* col_keep /* [n], nullable */, int64_t* out_ptr /* [n_sources + 1] */,
                                       int64_t capacity, int32_t* out_col, double* out_dist, double* info /* [4], nullable */)
 {
     if (!out_ptr) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_shortest_paths_csr: null out_ptr");
-    const SpCsrOut csr{out_ptr, capacity, out_col, out_dist, skip_self};
+    if (!(max_dist > 0.0)) return fail(nullptr, DYS_ERR_INVALID_ARG, "dys_shortest_paths_csr: max_dist must be positive (+inf for no bound)");
+    const SpCsrOut csr{out_ptr, capacity, out_col, out_dist, skip_self, max_dist, col_keep};
     return shortest_paths_impl("dys_shortest_paths_csr", device, n, indptr, indices, weights, n_sources, sources, nullptr, &csr, info);
 }
 

@@ -254,8 +254,11 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sp_relax(const int64_t n, const i
                                                         const int32_t* __restrict__ in_src, const double* __restrict__ in_w,
                                                         double* D, const uint8_t* __restrict__ dirty_prev,
                                                         uint8_t* __restrict__ dirty_next, int32_t* __restrict__ changed,
-                                                        const int marks_per_vertex)
+                                                        const int marks_per_vertex, const double bound)
 {
+    // bound: only distances BELOW it are wanted (+inf: all).  A label that is not below the bound is never stored, so the wave
+    // fronts stop at that radius; exact for every entry below the bound, because weights are >= 0 and rounded sums monotone:
+    // a path through a vertex at or beyond the bound cannot come back under it.
     const int chunks = batch / SP_CHUNK;
     const int64_t wid = ((int64_t)blockIdx.x * NET_BLOCK + threadIdx.x) >> 5;
     if (wid >= n * chunks) return;
@@ -279,10 +282,10 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sp_relax(const int64_t n, const i
         const double2* theirs = reinterpret_cast<const double2*>(D + (int64_t)u * batch + off);
         const double2 x0 = __ldcg(theirs), x1 = __ldcg(theirs + 1);
         const double c0 = __dadd_rn(x0.x, w), c1 = __dadd_rn(x0.y, w), c2 = __dadd_rn(x1.x, w), c3 = __dadd_rn(x1.y, w);
-        b0.x = c0 < b0.x ? c0 : b0.x;
-        b0.y = c1 < b0.y ? c1 : b0.y;
-        b1.x = c2 < b1.x ? c2 : b1.x;
-        b1.y = c3 < b1.y ? c3 : b1.y;
+        b0.x = (c0 < b0.x && c0 < bound) ? c0 : b0.x;
+        b0.y = (c1 < b0.y && c1 < bound) ? c1 : b0.y;
+        b1.x = (c2 < b1.x && c2 < bound) ? c2 : b1.x;
+        b1.y = (c3 < b1.y && c3 < bound) ? c3 : b1.y;
     }
     const bool better = b0.x < o0.x || b0.y < o0.y || b1.x < o1.x || b1.y < o1.y;
     if (better) { __stcg(mine, b0); __stcg(mine + 1, b1); }
@@ -312,12 +315,14 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sp_transpose(const double* __rest
     }
 }
 
-// rows[s][v] (what k_sp_transpose wrote) -> the reachable vertices of every source as CSR: FILL = false counts, FILL = true
+// rows[s][v] (what k_sp_transpose wrote) -> the vertices of every source that are nearer than `bound` (+inf: every reachable
+// one) and, if col_keep is given, marked in it, as CSR: FILL = false counts, FILL = true
 // writes (vertex, distance) at ptr[s] + rank, vertices ascending.  skip_self leaves the source itself out (the reference
 // sets the diagonal to inf before it takes exp(-dists), contagious3.py:126-127).
 template <bool FILL>
 __global__ void __launch_bounds__(NET_BLOCK) k_sp_compact(const double* __restrict__ rows, const int64_t n, const int n_src,
                                                           const int32_t* __restrict__ sources, const int skip_self,
+                                                          const double bound, const uint8_t* __restrict__ col_keep,
                                                           int64_t* __restrict__ count, const int64_t* __restrict__ ptr,
                                                           int32_t* __restrict__ col, double* __restrict__ dist)
 {
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(NET_BLOCK) k_sp_compact(const double* __restri
     for (int64_t v0 = 0; v0 < n; v0 += 32) {
         const int64_t v = v0 + lane;
         const double d = v < n ? row[v] : __longlong_as_double(0x7ff0000000000000ll);
-        const bool keep = d < __longlong_as_double(0x7ff0000000000000ll) && v != self;
+        const bool keep = d < bound && v != self && (col_keep == nullptr || col_keep[v < n ? v : 0] != 0);
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (FILL && keep) {
             const int64_t at = k + __popc(m & ((1u << lane) - 1u));

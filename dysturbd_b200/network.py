@@ -144,15 +144,20 @@ def shortest_paths(indptr, indices, weights, sources, device=0, return_sweeps=Fa
     return (out, int(info[0])) if return_sweeps else out
 
 
-def shortest_paths_csr(indptr, indices, weights, sources, capacity=None, skip_self=True, device=0, return_info=False, out=None):
+def shortest_paths_csr(indptr, indices, weights, sources, capacity=None, skip_self=True, device=0, return_info=False, out=None,
+                       max_dist=np.inf, col_keep=None):
     """the same distances as CSR over the reachable vertices only: (ptr[len(sources)+1], col, dist), compacted on the device.
-    out = (col_buffer, dist_buffer, offset): write into caller-owned arrays from `offset` on (the views returned alias them)"""
+    out = (col_buffer, dist_buffer, offset): write into caller-owned arrays from `offset` on (the views returned alias them).
+    max_dist: list (and search) only distances < max_dist; col_keep: uint8 [n] mask of the vertices to list."""
     lib = engine.load_library()
-    lib.dys_shortest_paths_csr.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
+    lib.dys_shortest_paths_csr.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
     indices = np.ascontiguousarray(indices, dtype=np.int32)
     weights = np.ascontiguousarray(weights, dtype=np.float64)
     sources = np.ascontiguousarray(sources, dtype=np.int32)
+    keep = None if col_keep is None else np.ascontiguousarray(col_keep, dtype=np.uint8)
+    if keep is not None and keep.shape != (len(indptr) - 1,):
+        raise ValueError("col_keep must have one entry per vertex")
     ptr = np.zeros(len(sources) + 1, dtype=np.int64)
     if out is None:
         col, dist, off = np.empty(int(capacity), dtype=np.int32), np.empty(int(capacity), dtype=np.float64), 0
@@ -163,7 +168,8 @@ def shortest_paths_csr(indptr, indices, weights, sources, capacity=None, skip_se
     room = len(col) - off if capacity is None else min(int(capacity), len(col) - off)
     info = np.zeros(4)
     _check(lib, lib.dys_shortest_paths_csr(device, len(indptr) - 1, indptr.ctypes.data, indices.ctypes.data, weights.ctypes.data,
-                                           len(sources), sources.ctypes.data, int(bool(skip_self)), ptr.ctypes.data, room,
+                                           len(sources), sources.ctypes.data, int(bool(skip_self)), float(max_dist),
+                                           None if keep is None else keep.ctypes.data, ptr.ctypes.data, room,
                                            col.ctypes.data + 4 * off, dist.ctypes.data + 8 * off, info.ctypes.data))
     m = int(ptr[-1])
     res = (ptr, col[off:off + m], dist[off:off + m])

@@ -38,10 +38,50 @@ def neighbourhoods(nodes, dists, agents, build, a_dist, bld_dist):
     inn = _csr(Dbb.T < bld_dist)                               # within bld_dist TO row building (i_nodes, :148)
     in_build = np.isin(bld_ids, build[:, 0])
     near = _csr((dists[np.ix_(an, bn)] < a_dist) & in_build[None, :])      # a_nodes, :144
+    home, anchors = _anchors(bld_ids, agents)
+    return dict(bld_ids=bld_ids, home=home, anchors=anchors, out=out, inn=inn, near=near)
+
+
+def _anchors(bld_ids, agents):
     rank = {float(v): i for i, v in enumerate(bld_ids)}
     reg = agents[:, [12, 18, 7]]                                # agents_reg[:, 2:], :131
     anchors = np.array([[rank[float(x)] if not np.isnan(x) else -1 for x in row] for row in reg], dtype=np.int32)
     home = np.array([rank[float(x)] for x in agents[:, 7]], dtype=np.int32)
+    return home, anchors
+
+
+def neighbourhoods_from_graph(nodes, indptr, indices, weights, agents, build, a_dist, bld_dist, device=0, rows_per_call=4096):
+    """The same lists as neighbourhoods(), cut on the device straight from the graph (network.create_graph) by BOUNDED
+    searches -- no (N + B)^2 distance matrix: `out` = buildings nearer than bld_dist from each building
+    (dys_shortest_paths_csr with max_dist = bld_dist, listing building nodes only), `inn` = its transpose (the distances TO a
+    building are the same numbers read column-wise), `near` = buildings of `build` nearer than a_dist from each agent."""
+    import scipy.sparse as sp
+    from . import network
+    nodes = np.asarray(nodes, dtype=np.float64)
+    if np.any(np.diff(nodes) <= 0):
+        raise ValueError("nodes must be in ascending id order (network.create_graph returns them so)")
+    is_bld = nodes < 4000000                                   # the reference's own test for "is a building", :148,:152
+    bn = np.nonzero(is_bld)[0].astype(np.int32)
+    bld_ids = nodes[bn]
+    rank = np.full(len(nodes), -1, dtype=np.int32)
+    rank[bn] = np.arange(len(bn), dtype=np.int32)
+
+    def lists(sources, bound, keep):
+        ptrs, cols = [np.zeros(1, dtype=np.int64)], []
+        for k0 in range(0, len(sources), rows_per_call):
+            src = sources[k0:k0 + rows_per_call]
+            ptr, col, _ = network.shortest_paths_csr(indptr, indices, weights, src, capacity=len(src) * int(keep.sum()), skip_self=True,
+                                                     device=device, max_dist=bound, col_keep=keep)
+            ptrs.append(ptrs[-1][-1] + ptr[1:])
+            cols.append(rank[col])
+        return np.concatenate(ptrs), (np.concatenate(cols) if cols else np.zeros(0, dtype=np.int32))
+    out = lists(bn, bld_dist, is_bld)                                                           # c_nodes, :152
+    m = sp.csr_matrix((np.ones(len(out[1]), dtype=np.int8), out[1], out[0]), shape=(len(bn), len(bn))).T.tocsr()
+    m.sort_indices()
+    inn = (m.indptr.astype(np.int64), m.indices.astype(np.int32))                                # i_nodes, :148
+    an = np.searchsorted(nodes, agents[:, 0]).astype(np.int32)
+    near = lists(an, a_dist, is_bld & np.isin(nodes, build[:, 0]))                              # a_nodes, :144
+    home, anchors = _anchors(bld_ids, agents)
     return dict(bld_ids=bld_ids, home=home, anchors=anchors, out=out, inn=inn, near=near)
 
 

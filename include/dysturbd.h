@@ -301,10 +301,14 @@ int dys_shortest_paths(int device, int64_t n, const int64_t* indptr, const int32
 /* the same distances, but only the vertices each source reaches, compacted on the device: out_ptr[n_sources + 1], then
  * (out_col, out_dist) with the vertices of a source ascending -- a third of the bytes of the dense rows on the shipped city.
  * skip_self != 0 leaves the source itself out (contagious3.py:126 sets the diagonal to inf before :127 takes exp(-dists)).
+ * max_dist: only vertices with distance < max_dist are listed (INFINITY: every reachable vertex) -- and the search itself stops
+ * there (a label at or beyond the bound is never stored), which is exact for every listed entry: this is the bounded search
+ * behind the routine generation's neighbourhoods, `dists[...] < bld_dist` / `< a_dist` (contagious3.py:144, 148, 152).
+ * col_keep[n] (nullable): list only the marked vertices (e.g. the building nodes).
  * capacity = entries out_col / out_dist can hold (the sizes of the sources' weak components bound it); DYS_ERR_RANGE if short. */
 int dys_shortest_paths_csr(int device, int64_t n, const int64_t* indptr, const int32_t* indices, const double* weights,
-                           int64_t n_sources, const int32_t* sources, int32_t skip_self, int64_t* out_ptr, int64_t capacity,
-                           int32_t* out_col, double* out_dist, double* info);
+                           int64_t n_sources, const int32_t* sources, int32_t skip_self, double max_dist, const uint8_t* col_keep,
+                           int64_t* out_ptr, int64_t capacity, int32_t* out_col, double* out_dist, double* info);
 const char* dys_version(void);
 
 #ifdef __cplusplus

@@ -163,6 +163,27 @@ def test_whole_setup_on_the_device():
         assert np.array_equal(nb[name][0], r[key + "_ptr"]) and np.array_equal(nb[name][1], r[key + "_idx"]), name
     visits = routines.to_visits(routines.generate(nb, int(r["seed"]), V=r["visits"].shape[1], k=int(r["k"])), nb["bld_ids"])
     assert np.array_equal(visits, r["visits"], equal_nan=True)
+    # the same lists by bounded searches on the device (no dense distance matrix)
+    nb2 = routines.neighbourhoods_from_graph(nodes, indptr, idx, w, r["agents"], r["build"], 1, 6, rows_per_call=300)
+    for key in ("out", "inn", "near"):
+        assert np.array_equal(nb2[key][0], nb[key][0]) and np.array_equal(nb2[key][1], nb[key][1]), key
+
+
+def test_bounded_search_lists_exactly_the_entries_below_the_bound():
+    from dysturbd_b200 import network
+    z = _fixture()
+    n = len(z["agents"])
+    indptr, idx, w = _csr_from_edges(n, z["edge_row"], z["edge_col"], z["edge_w"])
+    src = np.arange(0, n, 3, dtype=np.int32)
+    dense = network.shortest_paths(indptr, idx, w, src)
+    dense[np.arange(len(src)), src] = np.inf
+    keep = (np.arange(n) % 5 != 0).astype(np.uint8)
+    for bound in (0.02, 0.1, 0.5):
+        m = (dense < bound) & keep.astype(bool)[None, :]
+        r, c = np.nonzero(m)
+        ptr, col, dist = network.shortest_paths_csr(indptr, idx, w, src, capacity=len(r) + 1, max_dist=bound, col_keep=keep)
+        assert len(r) > 50 and np.array_equal(np.diff(ptr), np.bincount(r, minlength=len(src)))
+        assert np.array_equal(col, c) and np.array_equal(dist, dense[r, c])
 
 
 def test_network_calls_reject_bad_input():

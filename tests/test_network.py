@@ -132,6 +132,18 @@ def _oracle_standins(monkeypatch, oracle_lib):
     monkeypatch.setattr(network, "building_edges", lambda build, min_prob=0.00161, device=0:
                         oracle_lib.building_edges(build[:, 4], build[:, 6], build[:, 7], min_prob)[:3])
     monkeypatch.setattr(network, "shortest_paths", lambda indptr, idx, w, src, device=0: oracle_lib.shortest_paths(indptr, idx, w, src))
+
+    def paths_csr(indptr, idx, w, src, capacity=None, skip_self=True, device=0, out=None, max_dist=np.inf, col_keep=None):
+        d = oracle_lib.shortest_paths(indptr, idx, w, src)
+        if skip_self:
+            d[np.arange(len(src)), src] = np.inf
+        keep = d < max_dist
+        if col_keep is not None:
+            keep &= np.asarray(col_keep, dtype=bool)[None, :]
+        r, c = np.nonzero(keep)
+        assert capacity is None or len(r) <= capacity
+        return np.concatenate([[0], np.cumsum(np.bincount(r, minlength=len(src)))]).astype(np.int64), c.astype(np.int32), d[r, c]
+    monkeypatch.setattr(network, "shortest_paths_csr", paths_csr)
     return network
 
 
@@ -202,3 +214,9 @@ def test_whole_setup_chain_reproduces_the_routine_inputs(oracle_lib, monkeypatch
         assert np.array_equal(nb[name][0], z[key + "_ptr"]) and np.array_equal(nb[name][1], z[key + "_idx"]), name
     r = oracle_lib.routines(nb["home"], nb["anchors"], nb["out"], nb["inn"], nb["near"], int(z["seed"]), V=z["visits"].shape[1], k=int(z["k"]))
     assert np.array_equal(routines.to_visits(r, nb["bld_ids"]), z["visits"], equal_nan=True)
+    # the same lists without the dense matrix: bounded searches listing building nodes only
+    nb2 = routines.neighbourhoods_from_graph(nodes, indptr, idx, w, z["agents"], z["build"], 1, 6, rows_per_call=300)
+    for key in ("bld_ids", "home", "anchors"):
+        assert np.array_equal(nb2[key], nb[key]), key
+    for key in ("out", "inn", "near"):
+        assert np.array_equal(nb2[key][0], nb[key][0]) and np.array_equal(nb2[key][1], nb[key][1]), key
