@@ -615,9 +615,28 @@ def network_extra(local):
         for k in tot:
             tot[k] += info[k]
     t_paths = time.perf_counter() - t
+    # the rest of the setup: the whole graph G, the routine kernel's neighbourhood lists by bounded searches, the routines
+    chain = {}
+    try:
+        from dysturbd_b200 import routines
+        t = time.perf_counter()
+        nodes, g_ptr, g_idx, g_w = network.create_graph(z["agents"], z["households"], z["build"], device=local)
+        chain["create_graph_s"] = time.perf_counter() - t
+        chain["graph_nodes"], chain["graph_edges"] = int(len(nodes)), int(g_ptr[-1])
+        t = time.perf_counter()
+        nb = routines.neighbourhoods_from_graph(nodes, g_ptr, g_idx, g_w, z["agents"], z["build"], 1, 6, device=local)
+        chain["neighbourhood_lists_s"] = time.perf_counter() - t
+        chain["list_entries"] = int(len(nb["out"][1]) + len(nb["inn"][1]) + len(nb["near"][1]))
+        t = time.perf_counter()
+        r = routines.generate(nb, seed=20201019, device=local)
+        chain["routines_s"] = time.perf_counter() - t
+        chain["mean_visits"] = float((r >= 0).sum() / len(r))
+    except Exception as ex:                       # noqa: BLE001
+        chain["error"] = repr(ex)
     ref = json.loads(str(z["timings"])) if "timings" in z.files else {}
     return {"workload": "shipped city, %d agents" % n, "edges": int(indptr[-1]), "edges_equal_reference_graph": same,
             "similarity_edges_s": t_edges, "shortest_paths_s": t_paths, "reachable_pairs": int(pairs), **tot,
+            "setup_chain": chain, "reference_setup_total_s": ref.get("network+apsp+routines"),
             "reference_network_time_s": ref.get("network_time"), "reference_interaction_time_s": ref.get("interaction_time"),
             "what": "dys_similarity_edges (sizing + fill) and dys_shortest_paths_csr for every agent, wall clock through the Python "
                     "adapter, host arrays in and out; reference figures: contagious3.py's own timers when the fixture was made"}
