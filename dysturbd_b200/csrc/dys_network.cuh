@@ -4,9 +4,11 @@
 //                     scored as the reference scores it (same float64 operations in the same order, no fused multiply-add),
 //                     pairs above the threshold come out as CSR rows in np.where order.  No N x N matrix exists anywhere:
 //                     a block keeps 8 rows and walks the columns in shared-memory tiles.
+//  * k_bld_edges   -- the building-building edges of the same function (the gravity model, communities.py:12-21, 53-54), with
+//                     numpy's pairwise row sums reproduced addition by addition (k_bld_rowsum).
 //  * k_sp_relax    -- contagious3.py:124-130, scipy.sparse.csgraph.shortest_path: label-correcting relaxation for a batch of
-//                     sources at once, D[vertex][source] with the sources contiguous (a warp relaxes one vertex for 32 sources:
-//                     every neighbour read is one 256-byte line).  Distances are the left-to-right sums d(v) = fl(d(u) + w(u,v));
+//                     sources at once, D[vertex][source] with the sources contiguous (a warp relaxes one vertex for 128 sources,
+//                     four per lane: every neighbour read is 1 KB contiguous).  Distances are the left-to-right sums d(v) = fl(d(u) + w(u,v));
 //                     the least fixed point of that recurrence is unique (rounded addition is monotone and fl(d + w) >= d for
 //                     w >= 0), so the result is bit-identical to Dijkstra's whatever order the relaxations happen in.
 #pragma once
