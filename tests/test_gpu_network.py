@@ -186,6 +186,38 @@ def test_bounded_search_lists_exactly_the_entries_below_the_bound():
         assert np.array_equal(col, c) and np.array_equal(dist, dense[r, c])
 
 
+def test_network_calls_on_degenerate_inputs(oracle_lib):
+    """no edges, one vertex, no sources, one agent, one household, one building, everybody on one spot"""
+    from dysturbd_b200 import network
+    empty = np.zeros(6, dtype=np.int64)
+    d = network.shortest_paths(empty, np.zeros(0, dtype=np.int32), np.zeros(0), [3, 0])
+    exp = np.full((2, 5), np.inf)
+    exp[0, 3] = exp[1, 0] = 0.0
+    assert np.array_equal(d, exp)
+    assert network.shortest_paths(empty, np.zeros(0, dtype=np.int32), np.zeros(0), []).shape == (0, 5)
+    assert np.array_equal(network.shortest_paths(np.zeros(2, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0), [0]), [[0.0]])
+    ptr, col, dist = network.shortest_paths_csr(empty, np.zeros(0, dtype=np.int32), np.zeros(0), [1, 2], capacity=0)
+    assert np.array_equal(ptr, [0, 0, 0]) and len(col) == 0
+    one = dict(age=np.array([30.0]), income=np.array([1.0]), x=np.array([5.0]), y=np.array([6.0]), household=np.zeros(1, dtype=np.int64))
+    indptr, col, prob = network.similarity_edges(one)
+    assert np.array_equal(indptr, [0, 0]) and len(col) == 0
+    fam = dict(age=np.array([30.0, 5.0, 61.0]), income=np.full(3, 7.0), x=np.full(3, 5.0), y=np.full(3, 6.0), household=np.zeros(3, dtype=np.int64))
+    indptr, col, prob = network.similarity_edges(fam)                    # one household: all six ordered pairs, p = 1 (:39)
+    assert np.array_equal(indptr, [0, 2, 4, 6]) and np.array_equal(col, [1, 2, 0, 2, 0, 1]) and np.all(prob == 1.0)
+    two = dict(age=np.array([30.0, 30.0, 31.0]), income=np.full(3, 7.0), x=np.full(3, 5.0), y=np.full(3, 6.0), household=np.arange(3, dtype=np.int64))
+    got = network.similarity_edges(two)                                  # zero income and distance spread: 0 / 0 = nan, no edge, as in numpy
+    o = oracle_lib.similarity_edges(two["age"], two["income"], two["x"], two["y"], two["household"], 0.95)
+    assert got[0][-1] == 0 and np.array_equal(got[0], o[0])
+    b = np.zeros((1, 15))
+    b[0, 4] = 100.0
+    assert network.building_edges(b)[0][-1] == 0
+    spot = np.zeros((4, 15))
+    spot[:, 4] = [10.0, 20.0, 30.0, 40.0]                                # four buildings on one spot: every distance 0 -> 0.00001 (:14)
+    got = network.building_edges(spot, min_prob=0.1)
+    exp = oracle_lib.building_edges(spot[:, 4], spot[:, 6], spot[:, 7], 0.1)
+    assert got[0][-1] > 0 and all(np.array_equal(g, e) for g, e in zip(got, exp[:3]))
+
+
 def test_network_calls_reject_bad_input():
     from dysturbd_b200 import engine, network
     indptr, idx = np.array([0, 1, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32)
