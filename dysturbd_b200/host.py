@@ -42,13 +42,28 @@ def building_classes(lu, usg):
     return np.where(np.isin(usg, EDU_CODES))[0], np.where(np.isin(usg, REL_CODES))[0], np.where(lu >= 3)[0]
 
 
-def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None, dtype=float, ids=None):
+def building_lockdown(lu, usg, current, sc, vR, prevVR, choice, keyed=None, classes=None, dtype=float, ids=None, cache=None):
     """building_lockdown(b, sc, vR, prevVR) of contagious3.py:57-107 on the two building columns it reads
     (b[:,1] land use, b[:,9] USG code) and b[:,10] (`current`).  `choice` stands for np.random.choice.
     keyed = (seed, day): the half closures of GRADUAL close each building of the class with probability 1/2 on the keyed
     draw u(day, STREAM_LOCKDOWN, building) instead -- the host twin of the device policy (dys_set_lockdown).
     ids: the buildings' indices in the whole table when lu / usg / current are the rows of ONE area (the DIFF scenarios call
-    this once per area, contagious3.py:368-376); the keyed draws are keyed on those."""
+    this once per area, contagious3.py:368-376); the keyed draws are keyed on those.
+    cache (a dict the caller keeps for ONE building table and scenario): the all-open vector and the vector of a full
+    closure never change, so they are formed once and handed out again -- treat the result as read-only."""
+    if cache is not None:
+        # which branch of :57-107 applies is decided by the two R values alone
+        if 'GRADUAL' in sc:
+            what = ('half' if (prevVR <= 1 or prevVR >= 2) else 'keep') if 1 < vR < 2 else ('full' if vR >= 2 else 'open')
+        else:
+            what = 'full' if 1 < vR else 'open'
+        if what == 'keep':
+            return current if isinstance(current, np.ndarray) and current.dtype == dtype else np.array(current, dtype=dtype)
+        if what in ('open', 'full'):
+            if what not in cache:
+                cache[what] = building_lockdown(lu, usg, current, sc, 0 if what == 'open' else 3, 0, choice, classes=classes, dtype=dtype)
+                cache[what].setflags(write=False)
+            return cache[what]
     lockdown = np.ones(len(lu), dtype=dtype)      # (the reference's float64 vector; the model keeps its flags as bytes)
     edu, rel, non_res = classes if classes is not None else building_classes(lu, usg)
 
@@ -160,6 +175,7 @@ class EpidemicModel:
         self._ones = np.ones(self.pop.B, dtype=np.uint8)
         self._open_window = None
         self._classes = building_classes(self.pop.bld_lu, self.pop.bld_usg)      # (static: not recomputed every day)
+        self._ld_cache = {}          # the all-open and the fully closed vector of this scenario (building_lockdown, cache=)
         self.window = max(1, min(self.MAX_WINDOW, (self.params.diagnosis + 1) // 2)) if closes else self.MAX_WINDOW
         # lockdown = 'host'   phase H here, with the reference's np.random.choice (exact for every scenario)
         #            'keyed'  phase H here, GRADUAL half closures on keyed draws (the host twin of the device policy)
@@ -210,7 +226,7 @@ class EpidemicModel:
                 self._flags[day] = building_lockdown(self.pop.bld_lu, self.pop.bld_usg, cur, self.scenario,
                                                      self._known_R(prev), prevVR, self._choice,
                                                      keyed=(self.params.seed, prev) if self.lockdown == 'keyed' else None,
-                                                     classes=self._classes, dtype=np.uint8)
+                                                     classes=self._classes, dtype=np.uint8, cache=self._ld_cache)
             self._flags.pop(day - 20, None)
         return self._flags[day]
 
