@@ -68,3 +68,58 @@ def test_two_rank_sharded_equals_unsharded():
     assert ok, "sharded run diverged from the unsharded oracle"
     assert ever > 2000, ever            # a real epidemic
     assert cross > 0, "no infection crossed the shard boundary: the exchange was not exercised"
+
+
+def _network_worker(rank, world, port, out):
+    """rank r builds the rows [lo, hi) of interaction_prob from the whole graph (rows are independent: no exchange on the data
+    path); the pieces are gathered over gloo only to be compared with the reference's matrix"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dysturbd_b200 import network
+        from oracle import port as oracle_port
+        from helpers import GOLDEN
+        z = np.load(os.path.join(GOLDEN, "network_city300.npz"))
+        n = len(z["agents"])
+        order = np.lexsort((z["edge_col"], z["edge_row"]))
+        indptr = np.concatenate([[0], np.cumsum(np.bincount(z["edge_row"], minlength=n))]).astype(np.int64)
+        idx, w = z["edge_col"][order].astype(np.int32), z["edge_w"][order]
+
+        def paths_csr(indptr, idx, w, src, capacity=None, skip_self=True, device=0, out=None, max_dist=np.inf, col_keep=None):
+            d = oracle_port.shortest_paths(indptr, idx, w, src)                    # (the C oracle stands in for the device call)
+            d[np.arange(len(src)), src] = np.inf
+            r, c = np.nonzero(np.isfinite(d))
+            col, dist_, off = out
+            col[off:off + len(r)], dist_[off:off + len(r)] = c, d[r, c]
+            return np.concatenate([[0], np.cumsum(np.bincount(r, minlength=len(src)))]), col[off:off + len(r)], dist_[off:off + len(r)]
+        network.shortest_paths_csr = paths_csr
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        part = network.interaction_prob(indptr, idx, w, device=rank, row_range=(lo, hi), rows_per_call=150)
+        parts = [None] * world
+        dist.all_gather_object(parts, (part.indptr, part.indices, part.data))
+        if rank == 0:
+            ptr = np.concatenate([[0]] + [p[0][1:] + off for p, off in zip(parts, np.cumsum([0] + [p[0][-1] for p in parts[:-1]]))])
+            ok = np.array_equal(ptr, z["ip_indptr"]) and np.array_equal(np.concatenate([p[1] for p in parts]), z["ip_indices"])
+            data = np.concatenate([p[2] for p in parts])
+            ok &= bool(np.all(np.abs(data - z["ip_data"]) <= np.spacing(z["ip_data"])))
+            out.put((bool(ok), int(ptr[-1])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_interaction_prob_by_row_ranges():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_network_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    ok, nnz = out.get(timeout=10)
+    assert ok, "the row ranges of two ranks do not add up to the reference's interaction_prob"
+    assert nnz == 9308
