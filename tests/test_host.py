@@ -152,3 +152,27 @@ def test_windowed_run_equals_daily_run(oracle_lib):
         b.run(max_days=40, finalize=False)
         assert a.outputs["Results"]["Stats"] == b.outputs["Results"]["Stats"], sc
         assert a.day == b.day == 40
+
+
+def test_building_lockdown_cache_changes_nothing():
+    """building_lockdown(cache=...) hands out the all-open / fully closed vectors it formed once: for every scenario and
+    every (vR, prevVR) around the thresholds of contagious3.py:57-107 the result equals the uncached evaluation, and the
+    np.random.choice stream is consumed identically (half closures are never cached)"""
+    from dysturbd_b200.host import building_classes, building_lockdown
+    rs = np.random.RandomState(4)
+    B = 400
+    lu = rs.randint(1, 6, B).astype(float)
+    usg = rs.choice([5310.0, 5501.0, 5521.0, 5340.0, 1000.0, 2000.0], B)
+    classes = building_classes(lu, usg)
+    values = [0, 0.5, 1.0, 1.0000001, 1.5, 1.9999, 2.0, 2.5, float("nan")]
+    for sc in (['ALL'], ['EDU', 'REL'], ['GRADUAL', 'ALL'], ['GRADUAL', 'EDU'], ['GRADUAL', 'EDU', 'REL'], ['noLockdown']):
+        cache = {}
+        a_rng, b_rng = np.random.RandomState(9), np.random.RandomState(9)
+        cur_a = cur_b = np.ones(B, dtype=np.uint8)
+        for vR in values:
+            for pv in values:
+                x = building_lockdown(lu, usg, cur_a, sc, vR, pv, a_rng.choice, classes=classes, dtype=np.uint8)
+                y = building_lockdown(lu, usg, cur_b, sc, vR, pv, b_rng.choice, classes=classes, dtype=np.uint8, cache=cache)
+                assert np.array_equal(x, y), (sc, vR, pv)
+                cur_a, cur_b = x, y
+        assert a_rng.randint(1 << 30) == b_rng.randint(1 << 30), sc          # the two choice streams are in the same place
