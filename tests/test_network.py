@@ -220,3 +220,26 @@ def test_whole_setup_chain_reproduces_the_routine_inputs(oracle_lib, monkeypatch
         assert np.array_equal(nb2[key], nb[key]), key
     for key in ("out", "inn", "near"):
         assert np.array_equal(nb2[key][0], nb[key][0]) and np.array_equal(nb2[key][1], nb[key][1]), key
+
+
+def test_shortest_paths_oracle_property_random_graphs(oracle_lib):
+    """size-independent check of the fixed-point argument: on random directed graphs -- zero weights, tiny and
+    huge weights side by side, isolated vertices, self loops -- the restatement's left-to-right sums equal scipy's Dijkstra
+    bit for bit, and every finite distance satisfies d(v) <= fl(d(u) + w(u, v)) for every edge (a fixed point)"""
+    rs = np.random.RandomState(11)
+    for trial in range(40):
+        n = int(rs.randint(2, 120))
+        E = int(rs.randint(0, 6 * n))
+        row, col = rs.randint(0, n, E), rs.randint(0, n, E)
+        key = np.unique(row.astype(np.int64) * n + col)
+        row, col = (key // n).astype(np.int32), (key % n).astype(np.int32)
+        scale = rs.choice([1e-300, 1e-9, 1.0, 1e9], len(key))
+        w = np.where(rs.rand(len(key)) < 0.25, 0.0, rs.rand(len(key)) * scale)
+        indptr, idx, ww = _csr_from_edges(n, row, col, w)
+        src = np.arange(n, dtype=np.int32)
+        got = oracle_lib.shortest_paths(indptr, idx, ww, src)
+        g = sp.csr_matrix((ww, idx, indptr), shape=(n, n))
+        assert np.array_equal(got, shortest_path(g, directed=True, return_predecessors=False)), trial
+        rows = np.repeat(np.arange(n), np.diff(indptr))
+        with np.errstate(invalid="ignore"):
+            assert np.all(got[:, idx] <= got[:, rows] + ww[None, :]), trial
